@@ -1,0 +1,128 @@
+/*
+ * rvc_b200.h — C ABI of librvc_b200.so: sm_100a kernels for the RVC-MAKER `Synthesizer.infer` hot path.
+ *
+ * The reference (TheNeodev/RVC-MAKER) has no FFI of its own: the path is a Python class whose arithmetic is
+ * executed by torch.nn.functional calls.  Each entry point below therefore replaces the torch call sites of one
+ * reference function (cited as file:line under main/library/algorithm/).  All pointers are DEVICE pointers unless
+ * marked host; `stream` is a cudaStream_t passed as void*.  No entry point allocates, synchronises or keeps mutable
+ * global state; every function returns 0 on success, a negative RVC_E* code for argument errors or a positive
+ * cudaError_t, and records a message retrievable with rvc_last_error() (thread-local).
+ *
+ * Activation layout: fp32 `[B, C, L]` with explicit batch/channel strides in ELEMENTS (L stride is 1) — the reference's
+ * own NCL layout, so channel slices (the flow's x0/x1 halves) are addressed without copies.
+ */
+#ifndef RVC_B200_H
+#define RVC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVC_ABI_VERSION 3
+
+#define RVC_EINVAL (-1)   /* bad argument */
+#define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
+#define RVC_EALIGN (-3)   /* pointer / stride alignment */
+
+int rvc_abi_version(void);
+const char* rvc_last_error(void);
+/* fills {sm_count, cc_major, cc_minor, max_smem_optin}; returns 0 or cudaError_t */
+int rvc_device_info(int device, int* out4);
+
+/* post-activation codes */
+#define RVC_ACT_NONE 0
+#define RVC_ACT_RELU 1
+#define RVC_ACT_TANH 2
+
+/*
+ * Generic stride-1 Conv1d, fp32 CUDA-core path, with the fusions the path needs.
+ *   in(b,ci,l)  = pre_lrelu ? leaky_relu(x, pre_slope) : x ;  in *= mask[b,l] if in_mask ; zero outside [0,L)
+ *   acc(b,co,l) = sum_{ci,k} w[ci][k][co] * in(b, ci, l - pad + k*dil)
+ *   gated == 0:  v = act(acc + bias[co] + bias_b[b*bias_b_bs + co])
+ *   gated == 1:  v = tanh(acc_t + bias[co] + bias_b[..co]) * sigmoid(acc_s + bias[co+Cout] + bias_b[..co+Cout])
+ *                (acc_s uses weight columns co+Cout; weight tensor has 2*Cout columns)   [commons.py:35-41]
+ *   v = res ? res(b,co,l) + alpha*v : alpha*v ;  v *= out_scale ;  v *= mask[b,l] if out_mask
+ *   y(b,co,l) = beta != 0 ? beta*y(b,co,l) + v : v
+ * Weights are pre-packed as [Cin][K][Cw] fp32 (Cw = Cout, or 2*Cout when gated), weight-norm already folded.
+ * Replaces: F.conv1d call sites of TextEncoder/Encoder/FFN/MultiHeadAttention 1x1 (synthesizers.py:222,302-305,369),
+ * WaveNet (modules.py:43-45), ResidualCouplingLayer pre/post (residuals.py:129), GeneratorNSF.conv_pre/cond
+ * (synthesizers.py:146-147), ResBlock (residuals.py:32-36).
+ */
+typedef struct {
+    const float* x;  int64_t x_bs, x_cs;
+    const float* w;
+    const float* bias;                     /* [Cw] or NULL */
+    const float* bias_b; int64_t bias_b_bs;/* per-batch bias [B][>=Cw] or NULL */
+    const float* mask;                     /* [B][L] (1.0 / 0.0) or NULL */
+    const float* res; int64_t res_bs, res_cs; /* or NULL */
+    float* y;        int64_t y_bs, y_cs;
+    int32_t B, Cin, Cout, L, K, dil, pad;
+    int32_t pre_lrelu; float pre_slope;
+    int32_t in_mask, out_mask;
+    int32_t act, gated;
+    float alpha, out_scale, beta;
+} rvc_conv1d_desc;
+int rvc_conv1d_f32(const rvc_conv1d_desc* d, void* stream);
+
+/*
+ * ConvTranspose1d (stride u, kernel k, padding (k-u)/2, L_out = L_in*u) with fused pre-leaky_relu and the NSF
+ * noise-conv injection:  y = convT(lrelu(x, slope)) + bias + [ Conv1d_{1->Cout}(har, kn, stride sn, pad pn) + nbias ].
+ * w is the folded ConvTranspose1d weight re-packed [Cin][k][Cout]; nw is [Cout][kn] (NULL for the non-f0 Generator).
+ * Replaces GeneratorNSF.forward's `ups(x) + noise_convs(har_source)` (synthesizers.py:150,156) and Generator (:44).
+ */
+typedef struct {
+    const float* x;  int64_t x_bs, x_cs;
+    const float* w;  const float* bias;
+    const float* har; int64_t har_bs;      /* [B][L_in*u*sn] or NULL */
+    const float* nw; const float* nbias;
+    float* y;        int64_t y_bs, y_cs;
+    int32_t B, Cin, Cout, Lin, k, u, kn, sn, pn;
+    float pre_slope;
+} rvc_convtr1d_desc;
+int rvc_convtr1d_f32(const rvc_convtr1d_desc* d, void* stream);
+
+/* y[b,0,l] = tanh( sum_{ci,k} w[ci*7+k] * leaky_relu(x[b,ci,l-3+k], slope) ), no bias — conv_post (synthesizers.py:161). */
+int rvc_conv_post_f32(const float* x, int64_t x_bs, int64_t x_cs, const float* w, float* y, int64_t y_bs,
+                      int32_t B, int32_t C, int32_t L, float slope, void* stream);
+
+/*
+ * TextEncoder front end (synthesizers.py:367-368): x[b,c,t] = leaky_relu((phone[b,t,:].W[c,:] + bias[c] + E[pitch[b,t],c])
+ * * sqrt(H), 0.1) * mask ;  mask[b,t] = t < lengths[b].  wT is W transposed to [D][H]; pitch may be NULL (non-f0).
+ * pitch indices are int64 and gathered exactly.
+ */
+int rvc_embed_f32(const float* phone, const int64_t* pitch, const int64_t* lengths, const float* wT, const float* bias,
+                  const float* emb_pitch, float* x, float* mask, int32_t B, int32_t T, int32_t D, int32_t H, void* stream);
+
+/* y = LayerNorm_C(x + r) * gamma + beta over the channel axis of [B,C,T] (synthesizers.py:179-181, :346-347);
+ * out_mask multiplies by mask[b,t] (the final `x * x_mask`, :348). */
+int rvc_layernorm_f32(const float* x, const float* r, const float* gamma, const float* beta, const float* mask, float* y,
+                      int32_t B, int32_t C, int32_t T, float eps, int32_t out_mask, void* stream);
+
+/*
+ * Relative-position multi-head attention core (synthesizers.py:221-250), heads share the [2w+1, dk] tables:
+ *   s[i,j] = (q_i/sqrt(dk)).k_j + [|j-i|<=w] (q_i/sqrt(dk)).Ek[j-i+w];  s = -1e4 where mask_i*mask_j == 0
+ *   p = softmax_j(s);  out_i = sum_j p[i,j] (v_j + [|j-i|<=w] Ev[j-i+w])
+ * qkv is [B, 3*H, T] (q rows 0..H-1, k rows H..2H-1, v rows 2H..3H-1), out is [B,H,T]; head h owns channels h*dk..
+ */
+int rvc_rel_attention_f32(const float* qkv, const float* mask, const float* emb_k, const float* emb_v, float* out,
+                          int32_t B, int32_t H, int32_t n_heads, int32_t T, int32_t window, void* stream);
+
+/* z_p = (m + exp(logs) * eps * 0.66666) * mask, stats = [B, 2*C, T] (m rows then logs rows) — synthesizers.py:449. */
+int rvc_sample_zp_f32(const float* stats, const float* eps, const float* mask, float* zp, int32_t B, int32_t C, int32_t T,
+                      void* stream);
+
+/*
+ * SineGen + SourceModuleHnNSF, harmonic_num = 0 (synthesizers.py:79-100, :111-112):
+ *   har[b, t*upp+n-1] = tanh(lw * s + lb),  s = 0.1*sin(2*pi*(f0_t/sr*n + phase_t))*uv + (uv*0.003 + (1-uv)*0.1/3)*noise
+ *   phase_t = fmod( sum_{t'<t} (fmod(f0_t'/sr*upp + 0.5, 1) - 0.5), 1 ), prefix sum in fp64 rounded to fp32 per frame.
+ * scratch: B*T floats.
+ */
+int rvc_sine_source_f32(const float* f0, const float* noise, const float* lin_w, const float* lin_b, float* scratch,
+                        float* har, int32_t B, int32_t T, int32_t upp, float sr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVC_B200_H */

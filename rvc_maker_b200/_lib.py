@@ -1,0 +1,90 @@
+"""ctypes binding of librvc_b200.so (declared in include/rvc_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librvc_b200.so")
+ABI_VERSION = 3
+
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class Conv1dDesc(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("x_bs", _i64), ("x_cs", _i64),
+        ("w", _vp),
+        ("bias", _vp),
+        ("bias_b", _vp), ("bias_b_bs", _i64),
+        ("mask", _vp),
+        ("res", _vp), ("res_bs", _i64), ("res_cs", _i64),
+        ("y", _vp), ("y_bs", _i64), ("y_cs", _i64),
+        ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("L", _i32), ("K", _i32), ("dil", _i32), ("pad", _i32),
+        ("pre_lrelu", _i32), ("pre_slope", _f32),
+        ("in_mask", _i32), ("out_mask", _i32),
+        ("act", _i32), ("gated", _i32),
+        ("alpha", _f32), ("out_scale", _f32), ("beta", _f32),
+    ]
+
+
+class ConvTr1dDesc(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("x_bs", _i64), ("x_cs", _i64),
+        ("w", _vp), ("bias", _vp),
+        ("har", _vp), ("har_bs", _i64),
+        ("nw", _vp), ("nbias", _vp),
+        ("y", _vp), ("y_bs", _i64), ("y_cs", _i64),
+        ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("Lin", _i32), ("k", _i32), ("u", _i32), ("kn", _i32), ("sn", _i32), ("pn", _i32),
+        ("pre_slope", _f32),
+    ]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
+SIGNATURES = {
+    "rvc_abi_version": (C.c_int, []),
+    "rvc_last_error": (C.c_char_p, []),
+    "rvc_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "rvc_conv1d_f32": (C.c_int, [C.POINTER(Conv1dDesc), _vp]),
+    "rvc_convtr1d_f32": (C.c_int, [C.POINTER(ConvTr1dDesc), _vp]),
+    "rvc_conv_post_f32": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp]),
+    "rvc_embed_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "rvc_layernorm_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp]),
+    "rvc_rel_attention_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "rvc_sample_zp_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "rvc_sine_source_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the library once; raise loudly when it is absent or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m rvc_maker_b200.build` (needs nvcc, no GPU required). "
+            "rvc_maker_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.rvc_abi_version()
+    if v != ABI_VERSION:
+        raise RuntimeError(f"librvc_b200.so ABI {v} != expected {ABI_VERSION}; rebuild with `python -m rvc_maker_b200.build --force`")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().rvc_last_error().decode(errors="replace")
+        raise RuntimeError(f"librvc_b200 call failed ({what}): rc={rc}: {msg}")

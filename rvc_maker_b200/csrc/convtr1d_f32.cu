@@ -1,0 +1,190 @@
+// ConvTranspose1d (+ fused pre-leaky_relu, bias and NSF noise-conv injection) and conv_post, fp32 CUDA-core path.
+//
+// Phase decomposition: output l = q*u + r - p (p = (k-u)/2) receives x[ci, q-m] * w[ci, co, r + m*u] for the
+// M = ceil(k/u) taps m.  A thread owns ONE phase r, 4 input positions q and 8 output channels, so the weight row it
+// needs is shared by its 32 accumulators; thread index t = r + u*qg makes consecutive threads write consecutive l.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CI_T = 8;
+constexpr int CGN = 2;            // channel groups per CTA
+constexpr int CO_T = 8 * CGN;     // 16 output channels per CTA
+constexpr int WPAD = CO_T + 4;    // padded row: different phases hit different banks
+
+__global__ void __launch_bounds__(256) convtr1d_f32_kernel(const rvc_convtr1d_desc d, const int QG, const int M) {
+    extern __shared__ float smem[];
+    const int u = d.u, k = d.k;
+    const int TQ = u * QG;          // threads along t
+    const int QT = 4 * QG;          // q positions per CTA
+    const int XW = QT + M - 1;
+    float* x_s = smem;                        // [CI_T][XW]
+    float* w_s = smem + CI_T * XW;            // [CI_T][M*u][WPAD]
+    const int KR = M * u;
+
+    const int tid = threadIdx.x;
+    const int t = tid % TQ, cg = tid / TQ;
+    const int r = t % u, qg = t / u;
+    const int q0 = blockIdx.x * QT;
+    const int co0 = blockIdx.y * CO_T;
+    const int b = blockIdx.z;
+    const int p = (k - u) / 2;
+    const int nthreads = TQ * CGN;
+
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+
+    const float* xb = d.x + (int64_t)b * d.x_bs;
+    for (int ci0 = 0; ci0 < d.Cin; ci0 += CI_T) {
+        for (int idx = tid; idx < CI_T * XW; idx += nthreads) {
+            const int ci = idx / XW, j = idx - ci * XW;
+            const int q = q0 - (M - 1) + j;
+            float v = 0.f;
+            if (ci0 + ci < d.Cin && q >= 0 && q < d.Lin) v = rvc::lrelu(xb[(int64_t)(ci0 + ci) * d.x_cs + q], d.pre_slope);
+            x_s[idx] = v;
+        }
+        for (int idx = tid; idx < CI_T * KR * CO_T; idx += nthreads) {
+            const int c = idx % CO_T;
+            const int rr = idx / CO_T;       // ci*KR + kk
+            const int ci = rr / KR, kk = rr - ci * KR;
+            float v = 0.f;
+            if (ci0 + ci < d.Cin && kk < k && co0 + c < d.Cout) v = d.w[((int64_t)(ci0 + ci) * k + kk) * d.Cout + co0 + c];
+            w_s[rr * WPAD + c] = v;
+        }
+        __syncthreads();
+        if (cg < CGN) {
+#pragma unroll 1
+            for (int ci = 0; ci < CI_T; ++ci) {
+#pragma unroll 1
+                for (int m = 0; m < M; ++m) {
+                    const float* wr = w_s + (ci * KR + r + m * u) * WPAD + cg * 8;
+                    const float4 wa = *reinterpret_cast<const float4*>(wr);
+                    const float4 wb = *reinterpret_cast<const float4*>(wr + 4);
+                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                    const float* xr = x_s + ci * XW + (M - 1) - m + qg;
+                    float xv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) xv[i] = xr[QG * i];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(wv[j], xv[i], acc[j][i]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (cg >= CGN) return;
+
+    const int Lout = d.Lin * u;
+    const int64_t har_len = (int64_t)Lout * d.sn;
+    const float* hb = d.har ? d.har + (int64_t)b * d.har_bs : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = q0 + qg + QG * i;
+        const int l = q * u + r - p;
+        if (l < 0 || l >= Lout) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int co = co0 + cg * 8 + j;
+            if (co >= d.Cout) continue;
+            float v = acc[j][i] + (d.bias ? d.bias[co] : 0.f);
+            if (hb) {
+                float nv = d.nbias ? d.nbias[co] : 0.f;
+                const int64_t h0 = (int64_t)l * d.sn - d.pn;
+                const float* nw = d.nw + (int64_t)co * d.kn;
+                for (int jj = 0; jj < d.kn; ++jj) {
+                    const int64_t h = h0 + jj;
+                    if (h >= 0 && h < har_len) nv = fmaf(nw[jj], hb[h], nv);
+                }
+                v += nv;
+            }
+            d.y[(int64_t)b * d.y_bs + (int64_t)co * d.y_cs + l] = v;
+        }
+    }
+}
+
+// conv_post: Cout = 1, k = 7, pad 3, no bias, pre-leaky_relu(slope), tanh.  One thread = 4 consecutive outputs.
+__global__ void __launch_bounds__(256) conv_post_f32_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_cs,
+                                                            const float* __restrict__ w, float* __restrict__ y, int64_t y_bs,
+                                                            int C, int L, float slope) {
+    extern __shared__ float w_s[];  // [C][7]
+    for (int i = threadIdx.x; i < C * 7; i += blockDim.x) w_s[i] = w[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int l0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (l0 >= L) return;
+    const float* xb = x + (int64_t)b * x_bs;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool interior = (l0 >= 4) && (l0 + 8 <= L) && ((x_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0);
+    for (int c = 0; c < C; ++c) {
+        const float* xr = xb + (int64_t)c * x_cs;
+        float win[12];  // x[l0-4 .. l0+7]
+        if (interior) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + l0 - 4);
+            const float4 bq = *reinterpret_cast<const float4*>(xr + l0);
+            const float4 cq = *reinterpret_cast<const float4*>(xr + l0 + 4);
+            win[0] = a.x; win[1] = a.y; win[2] = a.z; win[3] = a.w;
+            win[4] = bq.x; win[5] = bq.y; win[6] = bq.z; win[7] = bq.w;
+            win[8] = cq.x; win[9] = cq.y; win[10] = cq.z; win[11] = cq.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const int l = l0 - 4 + j;
+                win[j] = (l >= 0 && l < L) ? xr[l] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 12; ++j) win[j] = rvc::lrelu(win[j], slope);
+#pragma unroll
+        for (int kk = 0; kk < 7; ++kk) {
+            const float wv = w_s[c * 7 + kk];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(wv, win[i + kk + 1], acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (l0 + i < L) y[(int64_t)b * y_bs + l0 + i] = tanhf(acc[i]);
+}
+
+}  // namespace
+
+RVC_API int rvc_convtr1d_f32(const rvc_convtr1d_desc* dp, void* stream) {
+    if (!dp) return rvc::fail(RVC_EINVAL, "rvc_convtr1d_f32: null descriptor");
+    const rvc_convtr1d_desc& d = *dp;
+    if (!d.x || !d.w || !d.y) return rvc::fail(RVC_EINVAL, "rvc_convtr1d_f32: null x/w/y");
+    if (d.B <= 0 || d.B > 65535 || d.Cin <= 0 || d.Cout <= 0 || d.Lin < 0 || d.k <= 0 || d.u <= 0)
+        return rvc::fail(RVC_ESHAPE, "rvc_convtr1d_f32: bad shape");
+    if (d.k < d.u || ((d.k - d.u) & 1) || d.u > 64)
+        return rvc::fail(RVC_ESHAPE, "rvc_convtr1d_f32: needs k >= u, (k-u) even, u <= 64 (k=%d u=%d)", d.k, d.u);
+    if (d.har && (!d.nw || d.kn <= 0 || d.sn <= 0)) return rvc::fail(RVC_EINVAL, "rvc_convtr1d_f32: noise conv arguments");
+    if (d.Lin == 0) return 0;
+    const int QG = 128 / d.u > 0 ? 128 / d.u : 1;
+    const int M = rvc::cdiv(d.k, d.u);
+    const int QT = 4 * QG, XW = QT + M - 1;
+    const size_t smem = (size_t)(CI_T * XW + CI_T * M * d.u * WPAD) * sizeof(float);
+    if (smem > 200 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_convtr1d_f32: kernel too large for shared memory");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(convtr1d_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return rvc::fail((int)e, "rvc_convtr1d_f32: smem opt-in: %s", cudaGetErrorString(e));
+    }
+    const int p = (d.k - d.u) / 2;
+    const int nq = d.Lin + rvc::cdiv(p, d.u);  // q values that can reach a valid output position
+    dim3 grid(rvc::cdiv(nq, QT), rvc::cdiv(d.Cout, CO_T), d.B);
+    convtr1d_f32_kernel<<<grid, d.u * QG * CGN, smem, (cudaStream_t)stream>>>(d, QG, M);
+    return rvc::check_launch("rvc_convtr1d_f32");
+}
+
+RVC_API int rvc_conv_post_f32(const float* x, int64_t x_bs, int64_t x_cs, const float* w, float* y, int64_t y_bs,
+                                 int32_t B, int32_t C, int32_t L, float slope, void* stream) {
+    if (!x || !w || !y) return rvc::fail(RVC_EINVAL, "rvc_conv_post_f32: null pointer");
+    if (B <= 0 || B > 65535 || C <= 0 || C > 1024 || L < 0) return rvc::fail(RVC_ESHAPE, "rvc_conv_post_f32: bad shape");
+    if (L == 0) return 0;
+    dim3 grid(rvc::cdiv(rvc::cdiv(L, 4), 256), B);
+    conv_post_f32_kernel<<<grid, 256, C * 7 * sizeof(float), (cudaStream_t)stream>>>(x, x_bs, x_cs, w, y, y_bs, C, L, slope);
+    return rvc::check_launch("rvc_conv_post_f32");
+}

@@ -1,0 +1,309 @@
+// TextEncoder-side fp32 kernels: phone/pitch embedding, channel LayerNorm, relative-position attention, z_p sampling.
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// embedding: x[b,c,t] = lrelu((phone[b,t,:].W[c,:] + bias[c] + E[pitch[b,t],c]) * sqrt(H), 0.1) * mask
+// CTA = 128 threads -> tile 32 t x 64 c; thread (tt = tid%16, tc = tid/16): t = t0+tt+16*i (i<2), c = c0+tc*8+j.
+// ------------------------------------------------------------------------------------------------
+constexpr int E_KT = 16;
+__global__ void __launch_bounds__(128) embed_f32_kernel(const float* __restrict__ phone, const int64_t* __restrict__ pitch,
+                                                        const int64_t* __restrict__ lengths, const float* __restrict__ wT,
+                                                        const float* __restrict__ bias, const float* __restrict__ emb_pitch,
+                                                        float* __restrict__ x, float* __restrict__ mask, int T, int D, int H,
+                                                        float scale) {
+    __shared__ float a_s[E_KT][33];
+    __shared__ float w_s[E_KT][64];
+    const int tid = threadIdx.x, tt = tid & 15, tc = tid >> 4;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 64, b = blockIdx.z;
+    const float* pb = phone + (int64_t)b * T * D;
+    float acc[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.f;
+    for (int d0 = 0; d0 < D; d0 += E_KT) {
+        for (int idx = tid; idx < 32 * E_KT; idx += 128) {
+            const int dd = idx & (E_KT - 1), t = idx >> 4;
+            a_s[dd][t] = (t0 + t < T && d0 + dd < D) ? pb[(int64_t)(t0 + t) * D + d0 + dd] : 0.f;
+        }
+        for (int idx = tid; idx < E_KT * 64; idx += 128) {
+            const int c = idx & 63, dd = idx >> 6;
+            w_s[dd][c] = (d0 + dd < D && c0 + c < H) ? wT[(int64_t)(d0 + dd) * H + c0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int dd = 0; dd < E_KT; ++dd) {
+            const float a0 = a_s[dd][tt], a1 = a_s[dd][tt + 16];
+            const float4 wa = *reinterpret_cast<const float4*>(&w_s[dd][tc * 8]);
+            const float4 wb = *reinterpret_cast<const float4*>(&w_s[dd][tc * 8 + 4]);
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[j][0] = fmaf(a0, wv[j], acc[j][0]);
+                acc[j][1] = fmaf(a1, wv[j], acc[j][1]);
+            }
+        }
+        __syncthreads();
+    }
+    const int64_t len = lengths[b];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int t = t0 + tt + 16 * i;
+        if (t >= T) continue;
+        const float m = (t < len) ? 1.f : 0.f;
+        if (blockIdx.y == 0 && tc == 0) mask[(int64_t)b * T + t] = m;
+        const int64_t pi = pitch ? pitch[(int64_t)b * T + t] : 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + tc * 8 + j;
+            if (c >= H) continue;
+            float v = acc[j][i] + bias[c];
+            if (pitch) v += emb_pitch[pi * H + c];
+            v = rvc::lrelu(v * scale, 0.1f) * m;
+            x[((int64_t)b * H + c) * T + t] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over channels of [B,C,T]; blockDim (32 t, 8 channel groups)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ r,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ mask, float* __restrict__ y, int C, int T,
+                                                            float eps, int out_mask) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int t = blockIdx.x * 32 + tx, b = blockIdx.y;
+    const bool ok = t < T;
+    const int64_t base = (int64_t)b * C * T + t;
+    float s = 0.f;
+    if (ok)
+        for (int c = ty; c < C; c += 8) {
+            float v = x[base + (int64_t)c * T];
+            if (r) v += r[base + (int64_t)c * T];
+            s += v;
+        }
+    red[ty][tx] = s;
+    __syncthreads();
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mean += red[i][tx];
+    mean /= (float)C;
+    __syncthreads();
+    float q = 0.f;
+    if (ok)
+        for (int c = ty; c < C; c += 8) {
+            float v = x[base + (int64_t)c * T];
+            if (r) v += r[base + (int64_t)c * T];
+            v -= mean;
+            q = fmaf(v, v, q);
+        }
+    red[ty][tx] = q;
+    __syncthreads();
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) var += red[i][tx];
+    var /= (float)C;
+    const float rstd = rsqrtf(var + eps);
+    if (!ok) return;
+    const float m = out_mask ? mask[(int64_t)b * T + t] : 1.f;
+    for (int c = ty; c < C; c += 8) {
+        float v = x[base + (int64_t)c * T];
+        if (r) v += r[base + (int64_t)c * T];
+        y[base + (int64_t)c * T] = ((v - mean) * rstd * gamma[c] + beta[c]) * m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// relative-position attention, flash-style fp32.  CTA = 128 threads, 32 queries of one (b, head); key tiles of 32.
+// thread (row = tid/4, sub = tid%4): scores for keys sub+4*jj (jj<8); output dims sub+4*dd.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT_BQ = 32, ATT_BK = 32, ATT_MAXDD = 32;  // dk <= 128
+
+__global__ void __launch_bounds__(128) rel_attention_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+                                                                const float* __restrict__ emb_k, const float* __restrict__ emb_v,
+                                                                float* __restrict__ out, int H, int n_heads, int T, int W) {
+    extern __shared__ float smem[];
+    const int dk = H / n_heads;
+    const int DKP = dk + 1;
+    const int NR = 2 * W + 1;
+    float* q_s = smem;                        // [32][DKP]
+    float* k_s = q_s + ATT_BQ * DKP;          // [32][DKP]
+    float* v_s = k_s + ATT_BK * DKP;          // [32][DKP]
+    float* p_s = v_s + ATT_BK * DKP;          // [32][33]
+    float* qe_s = p_s + ATT_BQ * 33;          // [32][NR]
+    float* ev_s = qe_s + ATT_BQ * NR;         // [NR][DKP]
+    float* mk_s = ev_s + NR * DKP;            // [32] key mask
+
+    const int tid = threadIdx.x, row = tid >> 2, sub = tid & 3;
+    const int i0 = blockIdx.x * ATT_BQ;
+    const int h = blockIdx.y % n_heads, b = blockIdx.y / n_heads;
+    const float* qb = qkv + ((int64_t)b * 3 * H + h * dk) * T;
+    const float* kb = qb + (int64_t)H * T;
+    const float* vb = kb + (int64_t)H * T;
+    const float* mb = mask + (int64_t)b * T;
+    const float rs = sqrtf((float)dk);
+
+    for (int idx = tid; idx < ATT_BQ * dk; idx += 128) {
+        const int i = idx & 31, dd = idx >> 5;
+        q_s[i * DKP + dd] = (i0 + i < T) ? qb[(int64_t)dd * T + i0 + i] / rs : 0.f;
+    }
+    for (int idx = tid; idx < NR * dk; idx += 128) {
+        const int dd = idx % dk, rr = idx / dk;
+        ev_s[rr * DKP + dd] = emb_v[rr * dk + dd];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < ATT_BQ * NR; idx += 128) {
+        const int i = idx / NR, rr = idx - i * NR;
+        float s = 0.f;
+        for (int dd = 0; dd < dk; ++dd) s = fmaf(q_s[i * DKP + dd], emb_k[rr * dk + dd], s);
+        qe_s[idx] = s;
+    }
+    const int qi = i0 + row;
+    const float mq = (qi < T) ? mb[qi] : 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[ATT_MAXDD];
+#pragma unroll
+    for (int dd = 0; dd < ATT_MAXDD; ++dd) o[dd] = 0.f;
+    const int ndd = dk >> 2;
+
+    for (int j0 = 0; j0 < T; j0 += ATT_BK) {
+        __syncthreads();
+        for (int idx = tid; idx < ATT_BK * dk; idx += 128) {
+            const int j = idx & 31, dd = idx >> 5;
+            const bool ok = j0 + j < T;
+            k_s[j * DKP + dd] = ok ? kb[(int64_t)dd * T + j0 + j] : 0.f;
+            v_s[j * DKP + dd] = ok ? vb[(int64_t)dd * T + j0 + j] : 0.f;
+        }
+        if (tid < ATT_BK) mk_s[tid] = (j0 + tid < T) ? mb[j0 + tid] : 0.f;
+        __syncthreads();
+        float s[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) s[jj] = 0.f;
+        const float* qr = q_s + row * DKP;
+        for (int dd = 0; dd < dk; ++dd) {
+            const float qv = qr[dd];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) s[jj] = fmaf(qv, k_s[(sub + 4 * jj) * DKP + dd], s[jj]);
+        }
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int jl = sub + 4 * jj, j = j0 + jl;
+            const int rel = j - qi + W;
+            if (rel >= 0 && rel < NR) s[jj] += qe_s[row * NR + rel];
+            if (mq * mk_s[jl] == 0.f) s[jj] = -1e4f;
+            if (j >= T) s[jj] = -INFINITY;
+            tmax = fmaxf(tmax, s[jj]);
+        }
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+        const float m_new = fmaxf(m_run, tmax);
+        const float corr = expf(m_run - m_new);  // exp(-inf) = 0 on the first tile
+        float psum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float pv = expf(s[jj] - m_new);
+            p_s[row * 33 + sub + 4 * jj] = pv;
+            psum += pv;
+        }
+        psum += __shfl_xor_sync(0xffffffffu, psum, 1);
+        psum += __shfl_xor_sync(0xffffffffu, psum, 2);
+        l_run = l_run * corr + psum;
+        m_run = m_new;
+        __syncwarp();
+#pragma unroll
+        for (int dd = 0; dd < ATT_MAXDD; ++dd) o[dd] *= corr;
+        const bool band = (j0 + ATT_BK - 1 >= i0 - W) && (j0 <= i0 + ATT_BQ - 1 + W);
+        for (int jl = 0; jl < ATT_BK; ++jl) {
+            const float pv = p_s[row * 33 + jl];
+            const float* vr = v_s + jl * DKP + sub;
+            const int rel = j0 + jl - qi + W;
+            if (band && rel >= 0 && rel < NR) {
+                const float* er = ev_s + rel * DKP + sub;
+#pragma unroll
+                for (int dd = 0; dd < ATT_MAXDD; ++dd)
+                    if (dd < ndd) o[dd] = fmaf(pv, vr[4 * dd] + er[4 * dd], o[dd]);
+            } else {
+#pragma unroll
+                for (int dd = 0; dd < ATT_MAXDD; ++dd)
+                    if (dd < ndd) o[dd] = fmaf(pv, vr[4 * dd], o[dd]);
+            }
+        }
+    }
+    if (qi < T) {
+        const float inv = 1.f / l_run;
+        float* ob = out + ((int64_t)b * H + h * dk) * T + qi;
+#pragma unroll
+        for (int dd = 0; dd < ATT_MAXDD; ++dd)
+            if (dd < ndd) ob[(int64_t)(sub + 4 * dd) * T] = o[dd] * inv;
+    }
+}
+
+__global__ void sample_zp_f32_kernel(const float* __restrict__ stats, const float* __restrict__ eps, const float* __restrict__ mask,
+                                     float* __restrict__ zp, int C, int T, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = (int)(i % T);
+    const int64_t bc = i / T;
+    const int c = (int)(bc % C);
+    const int64_t b = bc / C;
+    const float m = stats[(b * 2 * C + c) * T + t];
+    const float lg = stats[(b * 2 * C + C + c) * T + t];
+    zp[i] = (m + expf(lg) * eps[i] * 0.66666f) * mask[b * T + t];
+}
+
+}  // namespace
+
+RVC_API int rvc_embed_f32(const float* phone, const int64_t* pitch, const int64_t* lengths, const float* wT, const float* bias,
+                             const float* emb_pitch, float* x, float* mask, int32_t B, int32_t T, int32_t D, int32_t H, void* stream) {
+    if (!phone || !lengths || !wT || !bias || !x || !mask) return rvc::fail(RVC_EINVAL, "rvc_embed_f32: null pointer");
+    if (pitch && !emb_pitch) return rvc::fail(RVC_EINVAL, "rvc_embed_f32: pitch without embedding table");
+    if (B <= 0 || B > 65535 || T < 0 || D <= 0 || H <= 0) return rvc::fail(RVC_ESHAPE, "rvc_embed_f32: bad shape");
+    if (T == 0) return 0;
+    dim3 grid(rvc::cdiv(T, 32), rvc::cdiv(H, 64), B);
+    embed_f32_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(phone, pitch, lengths, wT, bias, emb_pitch, x, mask, T, D, H, sqrtf((float)H));
+    return rvc::check_launch("rvc_embed_f32");
+}
+
+RVC_API int rvc_layernorm_f32(const float* x, const float* r, const float* gamma, const float* beta, const float* mask, float* y,
+                                 int32_t B, int32_t C, int32_t T, float eps, int32_t out_mask, void* stream) {
+    if (!x || !gamma || !beta || !y || (out_mask && !mask)) return rvc::fail(RVC_EINVAL, "rvc_layernorm_f32: null pointer");
+    if (B <= 0 || B > 65535 || C <= 0 || T < 0) return rvc::fail(RVC_ESHAPE, "rvc_layernorm_f32: bad shape");
+    if (T == 0) return 0;
+    dim3 grid(rvc::cdiv(T, 32), B);
+    layernorm_f32_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, r, gamma, beta, mask, y, C, T, eps, out_mask);
+    return rvc::check_launch("rvc_layernorm_f32");
+}
+
+RVC_API int rvc_rel_attention_f32(const float* qkv, const float* mask, const float* emb_k, const float* emb_v, float* out,
+                                     int32_t B, int32_t H, int32_t n_heads, int32_t T, int32_t window, void* stream) {
+    if (!qkv || !mask || !emb_k || !emb_v || !out) return rvc::fail(RVC_EINVAL, "rvc_rel_attention_f32: null pointer");
+    if (B <= 0 || H <= 0 || n_heads <= 0 || H % n_heads || T < 0 || window < 0) return rvc::fail(RVC_ESHAPE, "rvc_rel_attention_f32: bad shape");
+    const int dk = H / n_heads;
+    if (dk % 4 || dk > 4 * ATT_MAXDD) return rvc::fail(RVC_ESHAPE, "rvc_rel_attention_f32: head dim %d must be a multiple of 4 and <= 128", dk);
+    if ((int64_t)B * n_heads > 65535) return rvc::fail(RVC_ESHAPE, "rvc_rel_attention_f32: B*heads > 65535");
+    if (T == 0) return 0;
+    const int DKP = dk + 1, NR = 2 * window + 1;
+    const size_t smem = (size_t)(3 * 32 * DKP + 32 * 33 + 32 * NR + NR * DKP + 32) * sizeof(float);
+    if (smem > 200 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_rel_attention_f32: window too large");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rel_attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return rvc::fail((int)e, "rvc_rel_attention_f32: smem opt-in: %s", cudaGetErrorString(e));
+    }
+    dim3 grid(rvc::cdiv(T, ATT_BQ), B * n_heads);
+    rel_attention_f32_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(qkv, mask, emb_k, emb_v, out, H, n_heads, T, window);
+    return rvc::check_launch("rvc_rel_attention_f32");
+}
+
+RVC_API int rvc_sample_zp_f32(const float* stats, const float* eps, const float* mask, float* zp, int32_t B, int32_t C, int32_t T,
+                                 void* stream) {
+    if (!stats || !eps || !mask || !zp) return rvc::fail(RVC_EINVAL, "rvc_sample_zp_f32: null pointer");
+    if (B <= 0 || C <= 0 || T < 0) return rvc::fail(RVC_ESHAPE, "rvc_sample_zp_f32: bad shape");
+    const int64_t n = (int64_t)B * C * T;
+    if (n == 0) return 0;
+    sample_zp_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(stats, eps, mask, zp, C, T, n);
+    return rvc::check_launch("rvc_sample_zp_f32");
+}

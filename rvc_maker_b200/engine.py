@@ -1,0 +1,371 @@
+"""Host-side execution engine: folds/packs the weights once, builds a launch plan per (B, T) and replays it.
+
+A *plan* is a flat list of C-ABI calls with pre-built descriptors pointing into persistent device workspaces, so a
+replay costs one ctypes call per kernel (and is CUDA-graph capturable).  PyTorch is used only for device memory,
+streams, the RNG draws (same generator/order/shapes as the reference: synthesizers.py:449, :87, :98) and copies.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, Conv1dDesc, ConvTr1dDesc
+
+LRELU_SLOPE = 0.1
+WINDOW = 10
+
+
+class V:
+    """A channel-slice view of a contiguous fp32 [B, Ctot, L] device tensor."""
+
+    __slots__ = ("t", "ptr", "bs", "cs")
+
+    def __init__(self, t, ctot, L, coff=0):
+        self.t = t
+        self.ptr = t.data_ptr() + coff * L * 4
+        self.bs = ctot * L
+        self.cs = L
+
+
+class Plan:
+    def __init__(self):
+        self.ops = []
+        self.keep = []
+        self.launches = 0
+
+    def add(self, name, fn, *args, launches=1):
+        self.ops.append((name, fn, args))
+        self.launches += launches
+
+    def add_py(self, fn):
+        self.ops.append((None, fn, ()))
+
+    def run(self, stream):
+        for name, fn, args in self.ops:
+            if name is None:
+                fn()
+            else:
+                rc = fn(*args, stream)
+                if rc != 0:
+                    _lib.check(rc, name)
+
+
+def _fold_wn(mod):
+    """w = g * v / ||v|| (norm over all dims but 0) in fp32 — torch.nn.utils.parametrizations.weight_norm semantics."""
+    g = mod.parametrizations.weight.original0.detach().float()
+    v = mod.parametrizations.weight.original1.detach().float()
+    n = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+    return v * (g / n)
+
+
+def _f(t):
+    return t.detach().float().contiguous()
+
+
+def _pack_conv(w):
+    """[Cout, Cin, K] -> [Cin][K][Cout]"""
+    return w.permute(1, 2, 0).contiguous()
+
+
+class Engine:
+    def __init__(self, m, device):
+        self.lib = _lib.load()
+        self.dev = device
+        info = (C.c_int * 4)()
+        _lib.check(self.lib.rvc_device_info(device.index if device.index is not None else torch.cuda.current_device(), info), "device_info")
+        self.sm_count, cc_major = info[0], info[1]
+        if cc_major != 10:
+            raise RuntimeError(f"librvc_b200 targets sm_100a (B200); found compute capability {info[1]}.{info[2]}")
+        self.cfg = dict(H=m.hidden_channels, I=m.inter_channels, Fc=m.filter_channels, nh=m.n_heads, nl=m.n_layers, ks=m.kernel_size,
+                        U=m.upsample_initial_channel, G=m.gin_channels, D=m.text_enc_hidden_dim, rates=m.upsample_rates,
+                        uks=m.upsample_kernel_sizes, rks=m.resblock_kernel_sizes, rds=m.resblock_dilation_sizes, sr=float(m.sr),
+                        upp=m.upp, f0=m.use_f0)
+        self._fold(m)
+        self.plans = {}
+
+    # ------------------------------------------------------------------ weight folding / packing
+    def _fold(self, m):
+        c = self.cfg
+        H, I = c["H"], c["I"]
+        half = I // 2
+        W = {}
+        e = m.enc_p
+        W["emb_wT"] = _f(e.emb_phone.weight).t().contiguous()
+        W["emb_b"] = _f(e.emb_phone.bias)
+        W["emb_pitch"] = _f(e.emb_pitch.weight) if c["f0"] else None
+        for i in range(c["nl"]):
+            a = e.encoder.attn_layers[i]
+            W[f"qkv_w{i}"] = _pack_conv(torch.cat([_f(a.conv_q.weight), _f(a.conv_k.weight), _f(a.conv_v.weight)], 0))
+            W[f"qkv_b{i}"] = torch.cat([_f(a.conv_q.bias), _f(a.conv_k.bias), _f(a.conv_v.bias)], 0).contiguous()
+            W[f"o_w{i}"], W[f"o_b{i}"] = _pack_conv(_f(a.conv_o.weight)), _f(a.conv_o.bias)
+            W[f"ek{i}"], W[f"ev{i}"] = _f(a.emb_rel_k)[0].contiguous(), _f(a.emb_rel_v)[0].contiguous()
+            for j, lst in ((1, e.encoder.norm_layers_1), (2, e.encoder.norm_layers_2)):
+                W[f"ln{j}_g{i}"], W[f"ln{j}_b{i}"] = _f(lst[i].gamma), _f(lst[i].beta)
+            f = e.encoder.ffn_layers[i]
+            W[f"f1_w{i}"], W[f"f1_b{i}"] = _pack_conv(_f(f.conv_1.weight)), _f(f.conv_1.bias)
+            W[f"f2_w{i}"], W[f"f2_b{i}"] = _pack_conv(_f(f.conv_2.weight)), _f(f.conv_2.bias)
+        W["proj_w"], W["proj_b"] = _pack_conv(_f(e.proj.weight)), _f(e.proj.bias)
+
+        # flow: the four Flips are folded into channel-reversed pre/post weights (residuals.py:53-58, :91-93)
+        cond_w, cond_b = [], []
+        for f in range(4):
+            cp = m.flow.flows[2 * f]
+            flipped = f in (3, 1)  # an odd number of Flips precedes couplings 3 and 1 in the reverse pass
+            pre_w, post_w, post_b = _f(cp.pre.weight), _f(cp.post.weight), _f(cp.post.bias)
+            if flipped:
+                pre_w, post_w, post_b = pre_w.flip(1), post_w.flip(0), post_b.flip(0)
+            W[f"fl{f}_pre_w"], W[f"fl{f}_pre_b"] = _pack_conv(pre_w), _f(cp.pre.bias)
+            W[f"fl{f}_post_w"], W[f"fl{f}_post_b"] = _pack_conv(post_w), post_b.contiguous()
+            for l in range(3):
+                W[f"fl{f}_in_w{l}"] = _pack_conv(_fold_wn(cp.enc.in_layers[l]))
+                W[f"fl{f}_in_b{l}"] = _f(cp.enc.in_layers[l].bias)
+                rs_w, rs_b = _fold_wn(cp.enc.res_skip_layers[l]), _f(cp.enc.res_skip_layers[l].bias)
+                if l < 2:
+                    W[f"fl{f}_res_w{l}"], W[f"fl{f}_res_b{l}"] = _pack_conv(rs_w[:H]), rs_b[:H].contiguous()
+                    W[f"fl{f}_skip_w{l}"], W[f"fl{f}_skip_b{l}"] = _pack_conv(rs_w[H:]), rs_b[H:].contiguous()
+                else:
+                    W[f"fl{f}_skip_w{l}"], W[f"fl{f}_skip_b{l}"] = _pack_conv(rs_w), rs_b
+            cond_w.append(_fold_wn(cp.enc.cond_layer))
+            cond_b.append(_f(cp.enc.cond_layer.bias))
+        # all speaker-conditioning 1x1 convs (4 x cond_layer + dec.cond) as ONE conv on g (L = 1)
+        cond_w.append(_f(m.dec.cond.weight))
+        cond_b.append(_f(m.dec.cond.bias))
+        W["cond_w"] = _pack_conv(torch.cat(cond_w, 0))
+        W["cond_b"] = torch.cat(cond_b, 0).contiguous()
+        self.cond_off = [f * 6 * H for f in range(4)] + [4 * 6 * H]
+        self.cond_total = 4 * 6 * H + c["U"]
+
+        d = m.dec
+        W["pre_w"], W["pre_b"] = _pack_conv(_f(d.conv_pre.weight)), _f(d.conv_pre.bias)
+        nk = len(c["rks"])
+        for i in range(len(c["rates"])):
+            up = d.ups[i] if c["f0"] else d.ups_and_resblocks[i * (nk + 1)]
+            W[f"up_w{i}"] = _fold_wn(up).permute(0, 2, 1).contiguous()  # [Cin][k][Cout]
+            W[f"up_b{i}"] = _f(up.bias)
+            if c["f0"]:
+                W[f"nz_w{i}"] = _f(d.noise_convs[i].weight)[:, 0, :].contiguous()
+                W[f"nz_b{i}"] = _f(d.noise_convs[i].bias)
+            for j in range(nk):
+                rb = d.resblocks[i * nk + j] if c["f0"] else d.ups_and_resblocks[i * (nk + 1) + 1 + j]
+                for mm in range(len(c["rds"][j])):
+                    W[f"rb{i}_{j}_c1w{mm}"], W[f"rb{i}_{j}_c1b{mm}"] = _pack_conv(_fold_wn(rb.convs1[mm])), _f(rb.convs1[mm].bias)
+                    W[f"rb{i}_{j}_c2w{mm}"], W[f"rb{i}_{j}_c2b{mm}"] = _pack_conv(_fold_wn(rb.convs2[mm])), _f(rb.convs2[mm].bias)
+        W["post_w"] = _f(d.conv_post.weight)[0].contiguous()
+        if c["f0"]:
+            W["lin_w"], W["lin_b"] = _f(d.m_source.l_linear.weight).view(1), _f(d.m_source.l_linear.bias).view(1)
+        W["emb_g"] = _f(m.emb_g.weight)
+        self.W = {k: (v.to(self.dev) if v is not None else None) for k, v in W.items()}
+
+    # ------------------------------------------------------------------ descriptor helpers
+    def _conv(self, plan, name, x, w, y, *, B, Cin, Cout, L, K=1, dil=1, pad=0, bias=None, bias_b=None, bias_b_bs=0, mask=None,
+              in_mask=False, out_mask=False, res=None, pre_slope=None, act=ACT_NONE, gated=False, alpha=1.0, out_scale=1.0, beta=0.0):
+        d = Conv1dDesc()
+        d.x, d.x_bs, d.x_cs = x.ptr, x.bs, x.cs
+        d.w = w.data_ptr()
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.bias_b = bias_b if bias_b is not None else None
+        d.bias_b_bs = bias_b_bs
+        d.mask = mask.data_ptr() if mask is not None else None
+        if res is not None:
+            d.res, d.res_bs, d.res_cs = res.ptr, res.bs, res.cs
+        d.y, d.y_bs, d.y_cs = y.ptr, y.bs, y.cs
+        d.B, d.Cin, d.Cout, d.L, d.K, d.dil, d.pad = B, Cin, Cout, L, K, dil, pad
+        d.pre_lrelu, d.pre_slope = (1, pre_slope) if pre_slope is not None else (0, 0.0)
+        d.in_mask, d.out_mask = int(in_mask), int(out_mask)
+        d.act, d.gated = act, int(gated)
+        d.alpha, d.out_scale, d.beta = alpha, out_scale, beta
+        plan.keep.append(d)
+        plan.add(name, self.lib.rvc_conv1d_f32, C.byref(d))
+
+    def _buf(self, plan, *shape, dtype=torch.float32):
+        t = torch.empty(*shape, dtype=dtype, device=self.dev)
+        plan.keep.append(t)
+        return t
+
+    # ------------------------------------------------------------------ plans
+    def _enc_plan(self, B, T):
+        c, W, lib = self.cfg, self.W, self.lib
+        H, I, Fc, D, ks = c["H"], c["I"], c["Fc"], c["D"], c["ks"]
+        p = Plan()
+        p.phone = self._buf(p, B, T, D)
+        p.pitch = self._buf(p, B, T, dtype=torch.int64) if c["f0"] else None
+        p.lengths = self._buf(p, B, dtype=torch.int64)
+        p.eps_z = self._buf(p, B, I, T)
+        p.mask = self._buf(p, B, T)
+        x, qkv, att, y = self._buf(p, B, H, T), self._buf(p, B, 3 * H, T), self._buf(p, B, H, T), self._buf(p, B, H, T)
+        h = self._buf(p, B, Fc, T)
+        p.stats = self._buf(p, B, 2 * I, T)
+        p.zp = self._buf(p, B, I, T)
+        vx, vqkv, vatt, vy, vh, vst = V(x, H, T), V(qkv, 3 * H, T), V(att, H, T), V(y, H, T), V(h, Fc, T), V(p.stats, 2 * I, T)
+        p.add("embed", lib.rvc_embed_f32, p.phone.data_ptr(), p.pitch.data_ptr() if c["f0"] else None, p.lengths.data_ptr(),
+              W["emb_wT"].data_ptr(), W["emb_b"].data_ptr(), W["emb_pitch"].data_ptr() if c["f0"] else None, x.data_ptr(),
+              p.mask.data_ptr(), B, T, D, H)
+        padl = (ks - 1) // 2
+        for i in range(c["nl"]):
+            self._conv(p, f"qkv{i}", vx, W[f"qkv_w{i}"], vqkv, B=B, Cin=H, Cout=3 * H, L=T, bias=W[f"qkv_b{i}"])
+            p.add(f"attn{i}", lib.rvc_rel_attention_f32, qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(), W[f"ev{i}"].data_ptr(),
+                  att.data_ptr(), B, H, c["nh"], T, WINDOW)
+            self._conv(p, f"attn_o{i}", vatt, W[f"o_w{i}"], vy, B=B, Cin=H, Cout=H, L=T, bias=W[f"o_b{i}"])
+            p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
+                  p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0)
+            self._conv(p, f"ffn1_{i}", vx, W[f"f1_w{i}"], vh, B=B, Cin=H, Cout=Fc, L=T, K=ks, pad=padl, bias=W[f"f1_b{i}"], mask=p.mask,
+                       in_mask=True, act=ACT_RELU)
+            self._conv(p, f"ffn2_{i}", vh, W[f"f2_w{i}"], vy, B=B, Cin=Fc, Cout=H, L=T, K=ks, pad=padl, bias=W[f"f2_b{i}"], mask=p.mask,
+                       in_mask=True, out_mask=True)
+            p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln2_g{i}"].data_ptr(), W[f"ln2_b{i}"].data_ptr(),
+                  p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 1 if i == c["nl"] - 1 else 0)
+        self._conv(p, "proj", vx, W["proj_w"], vst, B=B, Cin=H, Cout=2 * I, L=T, bias=W["proj_b"], mask=p.mask, out_mask=True)
+        p.add("sample_zp", lib.rvc_sample_zp_f32, p.stats.data_ptr(), p.eps_z.data_ptr(), p.mask.data_ptr(), p.zp.data_ptr(), B, I, T)
+        return p
+
+    def _dec_plan(self, B, T):
+        c, W, lib = self.cfg, self.W, self.lib
+        H, I, U, G = c["H"], c["I"], c["U"], c["G"]
+        half = I // 2
+        upp = c["upp"]
+        p = Plan()
+        p.zp = self._buf(p, B, I, T)
+        p.mask = self._buf(p, B, T)
+        p.g = self._buf(p, B, G)
+        p.z = self._buf(p, B, I, T)
+        gc = self._buf(p, B, self.cond_total)
+        hb, acts, outb = self._buf(p, B, H, T), self._buf(p, B, H, T), self._buf(p, B, H, T)
+        vh, va, vo = V(hb, H, T), V(acts, H, T), V(outb, H, T)
+        # speaker conditioning: cond_layer(g) x4 + dec.cond(g) in one launch (modules.py:39, synthesizers.py:147)
+        self._conv(p, "cond", V(p.g, G, 1), W["cond_w"], V(gc, self.cond_total, 1), B=B, Cin=G, Cout=self.cond_total, L=1, bias=W["cond_b"])
+        p.add_py(lambda: p.z.copy_(p.zp))
+        for f in (3, 2, 1, 0):
+            flipped = f in (3, 1)
+            src = V(p.z, I, T, half if flipped else 0)
+            dst = V(p.z, I, T, 0 if flipped else half)
+            self._conv(p, f"fl{f}_pre", src, W[f"fl{f}_pre_w"], vh, B=B, Cin=half, Cout=H, L=T, bias=W[f"fl{f}_pre_b"], mask=p.mask, out_mask=True)
+            for l in range(3):
+                self._conv(p, f"fl{f}_in{l}", vh, W[f"fl{f}_in_w{l}"], va, B=B, Cin=H, Cout=H, L=T, K=5, pad=2, bias=W[f"fl{f}_in_b{l}"],
+                           bias_b=gc.data_ptr() + (self.cond_off[f] + l * 2 * H) * 4, bias_b_bs=self.cond_total, gated=True)
+                if l < 2:
+                    self._conv(p, f"fl{f}_res{l}", va, W[f"fl{f}_res_w{l}"], vh, B=B, Cin=H, Cout=H, L=T, bias=W[f"fl{f}_res_b{l}"], res=vh,
+                               mask=p.mask, out_mask=True)
+                self._conv(p, f"fl{f}_skip{l}", va, W[f"fl{f}_skip_w{l}"], vo, B=B, Cin=H, Cout=H, L=T, bias=W[f"fl{f}_skip_b{l}"],
+                           beta=0.0 if l == 0 else 1.0)
+            self._conv(p, f"fl{f}_post", vo, W[f"fl{f}_post_w"], dst, B=B, Cin=H, Cout=half, L=T, bias=W[f"fl{f}_post_b"], mask=p.mask,
+                       in_mask=True, out_mask=True, res=dst, alpha=-1.0)
+
+        # ---- decoder
+        Lfin = T * upp
+        if c["f0"]:
+            p.f0 = self._buf(p, B, T)
+            p.eps_src = self._buf(p, B, Lfin)
+            har = self._buf(p, B, Lfin)
+            scratch = self._buf(p, B, T)
+            p.add("sine_source", lib.rvc_sine_source_f32, p.f0.data_ptr(), p.eps_src.data_ptr(), W["lin_w"].data_ptr(), W["lin_b"].data_ptr(),
+                  scratch.data_ptr(), har.data_ptr(), B, T, upp, c["sr"], launches=2)
+        xpre = self._buf(p, B, U, T)
+        self._conv(p, "conv_pre", V(p.z, I, T), W["pre_w"], V(xpre, U, T), B=B, Cin=I, Cout=U, L=T, K=7, pad=3, bias=W["pre_b"],
+                   bias_b=gc.data_ptr() + self.cond_off[4] * 4, bias_b_bs=self.cond_total, mask=p.mask, in_mask=True)
+        rates, uks, rks, rds = c["rates"], c["uks"], c["rks"], c["rds"]
+        nk = len(rks)
+        chans = [U // (2 ** (i + 1)) for i in range(len(rates))]
+        lens, L = [], T
+        for u in rates:
+            L *= u
+            lens.append(L)
+        big = max(ch * ln for ch, ln in zip(chans, lens))
+        S = [self._buf(p, B * big) for _ in range(4)]
+        cur, curC, curL = xpre, U, T
+        for i, (u, k) in enumerate(zip(rates, uks)):
+            Ci, Li = chans[i], lens[i]
+            d = ConvTr1dDesc()
+            vx = V(cur, curC, curL)
+            d.x, d.x_bs, d.x_cs = vx.ptr, vx.bs, vx.cs
+            d.w, d.bias = W[f"up_w{i}"].data_ptr(), W[f"up_b{i}"].data_ptr()
+            if c["f0"]:
+                sn = int(math.prod(rates[i + 1:])) if i + 1 < len(rates) else 1
+                kn = 1 if sn == 1 else sn * 2 - sn % 2
+                d.har, d.har_bs = har.data_ptr(), Lfin
+                d.nw, d.nbias = W[f"nz_w{i}"].data_ptr(), W[f"nz_b{i}"].data_ptr()
+                d.kn, d.sn, d.pn = kn, sn, (0 if sn == 1 else (kn - sn) // 2)
+            vs0 = V(S[0], Ci, Li)
+            d.y, d.y_bs, d.y_cs = vs0.ptr, vs0.bs, vs0.cs
+            d.B, d.Cin, d.Cout, d.Lin, d.k, d.u = B, curC, Ci, curL, k, u
+            d.pre_slope = LRELU_SLOPE
+            p.keep.append(d)
+            p.add(f"ups{i}", lib.rvc_convtr1d_f32, C.byref(d))
+            vs1, vs2, vs3 = V(S[1], Ci, Li), V(S[2], Ci, Li), V(S[3], Ci, Li)
+            for j, (kk, dils) in enumerate(zip(rks, rds)):
+                src = vs0
+                for mm, dl in enumerate(dils):
+                    last = mm == len(dils) - 1
+                    self._conv(p, f"rb{i}_{j}_c1_{mm}", src, W[f"rb{i}_{j}_c1w{mm}"], vs1, B=B, Cin=Ci, Cout=Ci, L=Li, K=kk, dil=dl,
+                               pad=(kk * dl - dl) // 2, bias=W[f"rb{i}_{j}_c1b{mm}"], pre_slope=LRELU_SLOPE)
+                    if not last:
+                        self._conv(p, f"rb{i}_{j}_c2_{mm}", vs1, W[f"rb{i}_{j}_c2w{mm}"], vs2, B=B, Cin=Ci, Cout=Ci, L=Li, K=kk,
+                                   pad=(kk - 1) // 2, bias=W[f"rb{i}_{j}_c2b{mm}"], pre_slope=LRELU_SLOPE, res=src)
+                        src = vs2
+                    else:
+                        self._conv(p, f"rb{i}_{j}_c2_{mm}", vs1, W[f"rb{i}_{j}_c2w{mm}"], vs3, B=B, Cin=Ci, Cout=Ci, L=Li, K=kk,
+                                   pad=(kk - 1) // 2, bias=W[f"rb{i}_{j}_c2b{mm}"], pre_slope=LRELU_SLOPE, res=src,
+                                   out_scale=1.0 / nk, beta=0.0 if j == 0 else 1.0)
+            cur, curC, curL = S[3], Ci, Li
+        p.o = self._buf(p, B, 1, Lfin)
+        p.add("conv_post", lib.rvc_conv_post_f32, cur.data_ptr(), curC * curL, curL, W["post_w"].data_ptr(), p.o.data_ptr(), Lfin, B, curC, curL, 0.01)
+        return p
+
+    def plan(self, kind, B, T):
+        key = (kind, B, T)
+        pl = self.plans.get(key)
+        if pl is None:
+            if len(self.plans) >= 8:  # bound the workspace arena: drop the oldest shape
+                self.plans.pop(next(iter(self.plans)))
+            pl = self._enc_plan(B, T) if kind == "enc" else self._dec_plan(B, T)
+            self.plans[key] = pl
+        return pl
+
+    # ------------------------------------------------------------------ infer
+    def infer(self, phone, phone_lengths, pitch, nsff0, sid, rate, out_dtype, noise=None):
+        c = self.cfg
+        if phone.dim() != 3 or phone.shape[2] != c["D"]:
+            raise ValueError(f"phone must be [B, T, {c['D']}], got {tuple(phone.shape)}")
+        B, T = int(phone.shape[0]), int(phone.shape[1])
+        if c["f0"] and (pitch is None or nsff0 is None):
+            raise ValueError("use_f0 model: pitch and nsff0 are required")
+        if sid is None:
+            raise ValueError("sid is required")
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        with torch.cuda.device(self.dev):
+            pe = self.plan("enc", B, T)
+            pe.phone.copy_(phone, non_blocking=True)
+            pe.lengths.copy_(phone_lengths, non_blocking=True)
+            if c["f0"]:
+                pe.pitch.copy_(pitch, non_blocking=True)
+            if noise is not None:
+                pe.eps_z.copy_(noise[0], non_blocking=True)
+            else:
+                pe.eps_z.normal_()  # randn_like(m_p), synthesizers.py:449
+            pe.run(stream)
+
+            head = int(T * (1.0 - rate)) if rate is not None else 0
+            T2 = T - head
+            pd = self.plan("dec", B, T2)
+            pd.zp.copy_(pe.zp[:, :, head:])
+            pd.mask.copy_(pe.mask[:, head:])
+            pd.g.copy_(self.W["emb_g"][sid.to(self.dev)])  # emb_g(sid), :447
+            if c["f0"]:
+                pd.f0.copy_(nsff0[:, head:], non_blocking=True)
+                if noise is not None:
+                    pd.eps_src.copy_(noise[1].reshape(noise[1].shape[0], -1)[:, : T2 * c["upp"]], non_blocking=True)
+                else:
+                    torch.rand(1, 1, 1, device=self.dev)  # rand_ini (:87) — drawn to keep the generator stream aligned, value unused (:88)
+                    pd.eps_src.normal_()                  # randn_like(sine_waves), :98
+            pd.run(stream)
+
+            I = c["I"]
+            o = pd.o.to(out_dtype, copy=True)
+            x_mask = pd.mask.view(B, 1, T2).to(out_dtype, copy=True)
+            z = pd.z.to(out_dtype, copy=True)
+            z_p = pd.zp.to(out_dtype, copy=True)
+            m_p = pe.stats[:, :I].to(out_dtype, copy=True)
+            logs_p = pe.stats[:, I:].to(out_dtype, copy=True)
+        return o, x_mask, (z, z_p, m_p, logs_p)

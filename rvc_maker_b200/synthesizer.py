@@ -1,0 +1,207 @@
+"""Drop-in replacement for the reference ``Synthesizer`` on the inference path, backed by librvc_b200.so.
+
+Boundary mirrored from /root/reference/main/library/algorithm/synthesizers.py:
+  * constructor signature  — ``Synthesizer.__init__`` :397
+  * ``state_dict`` keys    — the module tree built at :397-432 (and residuals.py / modules.py); the on-disk aliases
+                             ``weight_g``/``weight_v`` written by main/inference/train.py:742 load through torch's own
+                             weight-norm compatibility hook, exactly as they do in the reference
+  * ``infer(phone, phone_lengths, pitch, nsff0, sid, rate)`` -> ``(o, x_mask, (z, z_p, m_p, logs_p))`` — :446-465
+  * caller protocol        — ``del net_g.enc_q``; ``load_state_dict(strict=False)``; ``.eval().to(device)``;
+                             ``.half()`` / ``.float()`` (main/inference/convert.py:564-569)
+
+The ``torch.nn`` sub-modules below are PARAMETER CONTAINERS ONLY (so that keys, shapes, dtypes and the weight-norm
+parametrisation match); none of their ``forward`` methods is ever called.  All arithmetic of ``infer`` runs in the
+sm_100a kernels behind the C ABI (include/rvc_b200.h).  There is no CPU / PyTorch fallback: calling ``infer`` on a
+module whose parameters are not on a CUDA device, or without the built library, raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+from torch.nn.utils.parametrizations import weight_norm
+
+LRELU_SLOPE = 0.1
+WINDOW = 10  # Encoder(window_size=10), synthesizers.py:318
+
+
+class _Box(nn.Module):
+    """Parameter container; never called."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("rvc_maker_b200 sub-modules are parameter containers; call Synthesizer.infer")
+
+
+def _wavenet_box(hidden, kernel_size, n_layers, gin):
+    # modules.py:10-33
+    b = _Box()
+    b.in_layers = nn.ModuleList()
+    b.res_skip_layers = nn.ModuleList()
+    if gin != 0:
+        b.cond_layer = weight_norm(nn.Conv1d(gin, 2 * hidden * n_layers, 1), name="weight")
+    for i in range(n_layers):
+        b.in_layers.append(weight_norm(nn.Conv1d(hidden, 2 * hidden, kernel_size, padding=(kernel_size - 1) // 2), name="weight"))
+        b.res_skip_layers.append(weight_norm(nn.Conv1d(hidden, hidden if i == n_layers - 1 else 2 * hidden, 1), name="weight"))
+    return b
+
+
+def _resblock_box(ch, k, dilations):
+    # residuals.py:23-30
+    b = _Box()
+    b.convs1 = nn.ModuleList([weight_norm(nn.Conv1d(ch, ch, k, 1, dilation=d, padding=(k * d - d) // 2)) for d in dilations])
+    b.convs2 = nn.ModuleList([weight_norm(nn.Conv1d(ch, ch, k, 1, dilation=1, padding=(k - 1) // 2)) for _ in dilations])
+    return b
+
+
+class Synthesizer(nn.Module):
+    def __init__(self, spec_channels, segment_size, inter_channels, hidden_channels, filter_channels, n_heads, n_layers,
+                 kernel_size, p_dropout, resblock, resblock_kernel_sizes, resblock_dilation_sizes, upsample_rates,
+                 upsample_initial_channel, upsample_kernel_sizes, spk_embed_dim, gin_channels, sr, use_f0,
+                 text_enc_hidden_dim=768, vocoder="Default", checkpointing=False, onnx=False, **kwargs):
+        super().__init__()
+        if vocoder not in ("Default", None):
+            raise NotImplementedError(f"vocoder={vocoder!r}: only the Default NSF-HiFiGAN / HiFi-GAN generators are on the B200 path")
+        if gin_channels == 0:
+            raise NotImplementedError("gin_channels == 0 is not used by any RVC config")
+        if hidden_channels % n_heads or (hidden_channels // n_heads) % 4:
+            raise ValueError("hidden_channels / n_heads must be a multiple of 4")
+        self.spec_channels = spec_channels
+        self.inter_channels = inter_channels
+        self.hidden_channels = hidden_channels
+        self.filter_channels = filter_channels
+        self.n_heads = n_heads
+        self.n_layers = n_layers
+        self.kernel_size = kernel_size
+        self.p_dropout = float(p_dropout)
+        self.resblock_kernel_sizes = list(resblock_kernel_sizes)
+        self.resblock_dilation_sizes = [list(d) for d in resblock_dilation_sizes]
+        self.upsample_rates = list(upsample_rates)
+        self.upsample_initial_channel = upsample_initial_channel
+        self.upsample_kernel_sizes = list(upsample_kernel_sizes)
+        self.segment_size = segment_size
+        self.gin_channels = gin_channels
+        self.spk_embed_dim = spk_embed_dim
+        self.use_f0 = bool(use_f0)
+        self.sr = sr
+        self.text_enc_hidden_dim = text_enc_hidden_dim
+        self.upp = int(math.prod(self.upsample_rates))
+        H, I, Fc, U, G = hidden_channels, inter_channels, filter_channels, upsample_initial_channel, gin_channels
+
+        # ---- enc_p (TextEncoder :350-364, Encoder :317-338)
+        e = _Box()
+        e.emb_phone = nn.Linear(text_enc_hidden_dim, H)
+        if self.use_f0:
+            e.emb_pitch = nn.Embedding(256, H)
+        enc = _Box()
+        enc.attn_layers, enc.norm_layers_1, enc.ffn_layers, enc.norm_layers_2 = nn.ModuleList(), nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        dk = H // n_heads
+        for _ in range(n_layers):
+            a = _Box()
+            a.conv_q, a.conv_k, a.conv_v, a.conv_o = (nn.Conv1d(H, H, 1) for _ in range(4))
+            a.emb_rel_k = nn.Parameter(torch.randn(1, 2 * WINDOW + 1, dk) * dk ** -0.5)
+            a.emb_rel_v = nn.Parameter(torch.randn(1, 2 * WINDOW + 1, dk) * dk ** -0.5)
+            enc.attn_layers.append(a)
+            for lst in (enc.norm_layers_1, enc.norm_layers_2):
+                n = _Box()
+                n.gamma = nn.Parameter(torch.ones(H))
+                n.beta = nn.Parameter(torch.zeros(H))
+                lst.append(n)
+            f = _Box()
+            f.conv_1 = nn.Conv1d(H, Fc, kernel_size)
+            f.conv_2 = nn.Conv1d(Fc, H, kernel_size)
+            enc.ffn_layers.append(f)
+        e.encoder = enc
+        e.proj = nn.Conv1d(H, I * 2, 1)
+        self.enc_p = e
+
+        # ---- dec (GeneratorNSF :114-142, Generator :21-37)
+        d = _Box()
+        n_up = len(self.upsample_rates)
+        chans = [U // (2 ** (i + 1)) for i in range(n_up)]
+        d.conv_pre = nn.Conv1d(I, U, 7, 1, padding=3)
+        if self.use_f0:
+            ms = _Box()
+            ms.l_linear = nn.Linear(1, 1)
+            d.m_source = ms
+            d.ups, d.noise_convs = nn.ModuleList(), nn.ModuleList()
+            for i, (u, k) in enumerate(zip(self.upsample_rates, self.upsample_kernel_sizes)):
+                if u % 2 or (k - u) % 2:
+                    raise NotImplementedError("odd upsample rates are not used by any RVC config")
+                d.ups.append(weight_norm(nn.ConvTranspose1d(U // (2 ** i), chans[i], k, u, padding=(k - u) // 2)))
+                s = int(math.prod(self.upsample_rates[i + 1:])) if i + 1 < n_up else 1
+                kn = 1 if s == 1 else s * 2 - s % 2
+                d.noise_convs.append(nn.Conv1d(1, chans[i], kernel_size=kn, stride=s, padding=0 if s == 1 else (kn - s) // 2))
+            d.resblocks = nn.ModuleList([_resblock_box(chans[i], k, dl) for i in range(n_up)
+                                         for k, dl in zip(self.resblock_kernel_sizes, self.resblock_dilation_sizes)])
+        else:
+            d.ups_and_resblocks = nn.ModuleList()
+            for i, (u, k) in enumerate(zip(self.upsample_rates, self.upsample_kernel_sizes)):
+                if (k - u) % 2:
+                    raise NotImplementedError("(kernel - stride) must be even")
+                d.ups_and_resblocks.append(weight_norm(nn.ConvTranspose1d(U // (2 ** i), chans[i], k, u, padding=(k - u) // 2)))
+                for kk, dl in zip(self.resblock_kernel_sizes, self.resblock_dilation_sizes):
+                    d.ups_and_resblocks.append(_resblock_box(chans[i], kk, dl))
+        d.conv_post = nn.Conv1d(chans[-1], 1, 7, 1, padding=3, bias=False)
+        d.cond = nn.Conv1d(G, U, 1)
+        self.dec = d
+
+        # ---- enc_q (PosteriorEncoder :373-386) — train-only, kept so `del net_g.enc_q` and full checkpoints work
+        q = _Box()
+        q.pre = nn.Conv1d(spec_channels, H, 1)
+        q.enc = _wavenet_box(H, 5, 16, G)
+        q.proj = nn.Conv1d(H, I * 2, 1)
+        self.enc_q = q
+
+        # ---- flow (ResidualCouplingBlock residuals.py:71-85)
+        fl = _Box()
+        fl.flows = nn.ModuleList()
+        for _ in range(4):
+            c = _Box()
+            c.pre = nn.Conv1d(I // 2, H, 1)
+            c.enc = _wavenet_box(H, 5, 3, G)
+            c.post = nn.Conv1d(H, I // 2, 1)
+            c.post.weight.data.zero_()
+            c.post.bias.data.zero_()
+            fl.flows.append(c)
+            fl.flows.append(_Box())  # Flip: no parameters
+        self.flow = fl
+        self.emb_g = nn.Embedding(spk_embed_dim, G)
+
+        self._engine = None
+        self._noise_override = None  # tests: (eps_z [B,I,T], eps_src [B,T*upp,1] or None)
+
+    # ------------------------------------------------------------------ engine lifetime
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict=True, *a, **k):
+        self._engine = None
+        return super().load_state_dict(state_dict, strict, *a, **k)
+
+    def refold(self):
+        """Drop the folded/packed weight cache (call after mutating parameters in place)."""
+        self._engine = None
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("training forward (synthesizers.py:434-443) is outside the B200 inference path")
+
+    def remove_weight_norm(self):
+        """No-op: weight-norm is folded into packed weights at load time (the reference's own remover raises)."""
+        return None
+
+    # ------------------------------------------------------------------ inference
+    @torch.no_grad()
+    def infer(self, phone, phone_lengths, pitch=None, nsff0=None, sid=None, rate=None):
+        dev = self.emb_g.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("rvc_maker_b200.Synthesizer.infer needs its parameters on a CUDA device (no CPU fallback)")
+        if self._engine is None:
+            from .engine import Engine
+            self._engine = Engine(self, dev)
+        if rate is not None:
+            assert isinstance(rate, torch.Tensor)
+            rate = float(rate.item())
+        noise = self._noise_override
+        return self._engine.infer(phone, phone_lengths, pitch, nsff0, sid, rate, self.emb_g.weight.dtype, noise)

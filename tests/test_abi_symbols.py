@@ -1,0 +1,56 @@
+"""CPU checks of the C-ABI boundary: the library builds, loads and exports every symbol include/rvc_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from rvc_maker_b200 import _lib, build
+
+    build.build()
+    return _lib.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "rvc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rvc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    from rvc_maker_b200 import _lib
+
+    syms = header_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/rvc_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_abi_version_and_error_string(lib):
+    assert lib.rvc_abi_version() == 3
+    # argument validation happens before any CUDA call, so it is checkable without a GPU
+    rc = lib.rvc_conv1d_f32(None, None)
+    assert rc == -1
+    assert b"null descriptor" in lib.rvc_last_error()
+
+
+def test_desc_struct_layout_matches_header():
+    """ctypes struct sizes must equal the C structs (LP64, natural alignment): computed from the header field list."""
+    from rvc_maker_b200._lib import Conv1dDesc, ConvTr1dDesc
+
+    assert ctypes.sizeof(Conv1dDesc) == 176
+    assert ctypes.sizeof(ConvTr1dDesc) == 136
+
+
+def test_no_oracle_import_in_product():
+    pkg = os.path.join(ROOT, "rvc_maker_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("no oracle", ""), fn

@@ -1,0 +1,134 @@
+"""GPU parity: the CUDA path (through the drop-in module -> C ABI) against the committed reference goldens and the oracle.
+
+Tolerances (fp32 CUDA-core path): max-abs <= 2e-5 * max(1, max|ref|) and SNR >= 80 dB (reference fp32 floor
+is 2.4e-7 vs fp64; the bar for the bf16 tensor-core path is max-abs <= 1e-3, SNR >= 40 dB).  Mask and shapes are exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, synth_oracle
+from oracle.make_golden import CASES
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 2e-5
+FP32_SNR = 80.0
+
+
+def build_net(cfg, sd, use_f0, dtype=torch.float32):
+    from rvc_maker_b200 import Synthesizer
+
+    net = Synthesizer(*cases.ctor_args(cfg), use_f0=use_f0, text_enc_hidden_dim=cfg["text_enc_hidden_dim"])
+    del net.enc_q  # convert.py:565
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    net = net.eval().to("cuda:0")
+    return net.half() if dtype == torch.float16 else net.float()
+
+
+def run_net(net, inp, rate=None):
+    net._noise_override = (inp["eps_z"], inp["eps_src"])
+    dev = "cuda:0"
+    mv = lambda t: None if t is None else t.to(dev)
+    r = None if rate is None else torch.tensor(rate)
+    o, x_mask, (z, z_p, m_p, logs_p) = net.infer(mv(inp["phone"]), mv(inp["phone_lengths"]), mv(inp["pitch"]), mv(inp["nsff0"]), mv(inp["sid"]), r)
+    torch.cuda.synchronize()
+    return dict(o=o, x_mask=x_mask, z=z, z_p=z_p, m_p=m_p, logs_p=logs_p)
+
+
+def assert_close(out, ref, tol=FP32_TOL, snr=FP32_SNR, tag=""):
+    for k, r in ref.items():
+        if k.startswith("tap_"):
+            continue
+        r = torch.as_tensor(r)
+        v = out[k].float().cpu()
+        assert tuple(v.shape) == tuple(r.shape), (tag, k, v.shape, r.shape)
+        assert torch.isfinite(v).all(), (tag, k)
+        if k == "x_mask":
+            assert torch.equal(v, r.float()), (tag, k)
+            continue
+        m = cases.metrics(v, r)
+        assert m["max_abs"] <= tol * max(1.0, float(r.abs().max())), (tag, k, m)
+        if float(r.abs().max()) > 0:
+            assert m["snr_db"] >= snr, (tag, k, m)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_matches_reference_golden(name, golden_dir):
+    cname, use_f0, heated, disk, B, T, ragged, rate, wseed, iseed, _ = CASES[name]
+    cfg = cases.CONFIGS[cname]
+    sd = cases.synth_state_dict(cfg, use_f0=use_f0, seed=wseed, heated=heated)
+    if disk:
+        sd = cases.to_disk_form(sd)
+    inp = cases.synth_inputs(cfg, B, T, seed=iseed, ragged=ragged, use_f0=use_f0)
+    out = run_net(build_net(cfg, sd, use_f0), inp, rate)
+    gold = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    assert_close(out, gold, tag=name)
+
+
+@pytest.mark.parametrize("cname,use_f0,B,T,ragged", [
+    ("v2_40k", True, 1, 300, False),
+    ("v2_48k", True, 2, 250, True),
+    ("v1_32k", True, 3, 200, True),
+    ("v2_40k", False, 2, 200, True),
+])
+def test_cuda_matches_oracle_midsize(cname, use_f0, B, T, ragged):
+    cfg = cases.CONFIGS[cname]
+    sd = cases.synth_state_dict(cfg, use_f0=use_f0, seed=4321, heated=True)
+    inp = cases.synth_inputs(cfg, B, T, seed=21, ragged=ragged, use_f0=use_f0)
+    out = run_net(build_net(cfg, sd, use_f0), inp)
+    ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
+                                                      eps_z=inp["eps_z"], eps_src=inp["eps_src"], use_f0=use_f0)
+    assert_close(out, dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl), tag=cname)
+
+
+def test_half_module_protocol():
+    """convert.py:569 `.half()`: inputs arrive fp16, outputs come back fp16, arithmetic stays fp32 inside."""
+    cfg = cases.CONFIGS["tiny"]
+    sd = cases.synth_state_dict(cfg, seed=3, heated=True)
+    inp = cases.synth_inputs(cfg, 2, 32, seed=4)
+    net = build_net(cfg, cases.to_disk_form(sd), True, dtype=torch.float16)
+    inp16 = dict(inp, phone=inp["phone"].half(), nsff0=inp["nsff0"].half())
+    out = run_net(net, inp16)
+    assert out["o"].dtype == torch.float16 and out["z"].dtype == torch.float16
+    sd16 = {k: v.half().float() for k, v in sd.items()}
+    ro, *_ = synth_oracle.infer(sd16, cfg, inp16["phone"].float(), inp["phone_lengths"], inp["pitch"], inp16["nsff0"].float(), inp["sid"],
+                                eps_z=inp["eps_z"], eps_src=inp["eps_src"])
+    m = cases.metrics(out["o"].float().cpu(), ro)
+    assert m["max_abs"] <= 2e-3, m  # fp16 output rounding only
+
+
+def test_rng_stream_matches_reference_order():
+    """Without injected noise the module draws randn[B,I,T], rand[1,1,1], randn[B,T*upp] from torch's CUDA generator."""
+    cfg = cases.CONFIGS["tiny"]
+    sd = cases.synth_state_dict(cfg, seed=3, heated=True)
+    inp = cases.synth_inputs(cfg, 2, 32, seed=4)
+    net = build_net(cfg, sd, True)
+    torch.manual_seed(99)
+    dev = "cuda:0"
+    o1 = net.infer(inp["phone"].to(dev), inp["phone_lengths"].to(dev), inp["pitch"].to(dev), inp["nsff0"].to(dev), inp["sid"].to(dev))[0]
+    torch.manual_seed(99)
+    eps_z = torch.randn(2, cfg["inter_channels"], 32, device=dev)
+    torch.rand(1, 1, 1, device=dev)
+    eps_src = torch.randn(2, 32 * cases.upp_of(cfg), 1, device=dev)
+    net._noise_override = (eps_z, eps_src)
+    o2 = net.infer(inp["phone"].to(dev), inp["phone_lengths"].to(dev), inp["pitch"].to(dev), inp["nsff0"].to(dev), inp["sid"].to(dev))[0]
+    assert torch.equal(o1, o2)
+
+
+def test_inputs_not_mutated_and_errors():
+    cfg = cases.CONFIGS["tiny"]
+    sd = cases.synth_state_dict(cfg, seed=3, heated=True)
+    inp = cases.synth_inputs(cfg, 1, 16, seed=4)
+    net = build_net(cfg, sd, True)
+    ph = inp["phone"].cuda()
+    ph0 = ph.clone()
+    run_net(net, dict(inp, phone=ph))
+    assert torch.equal(ph, ph0)
+    with pytest.raises(ValueError):
+        net.infer(ph[:, :, :5], inp["phone_lengths"].cuda(), inp["pitch"].cuda(), inp["nsff0"].cuda(), inp["sid"].cuda())
+    with pytest.raises(RuntimeError):
+        build_net(cfg, sd, True).cpu().infer(inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"])
