@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds synthesised per second by the Synthesizer.infer hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference algorithm on the host CPU (oracle port)
+
+A *step* is one `infer` over one batch of synthetic input (default: configs[1] = RVC v2 48k f0, one 10 s clip, B=1,
+T=1000 frames).  `value` = whole-job audio-s/s with inputs resident in HBM (per-step CUDA events, max over ranks);
+`e2e` = the same through the public module API from pinned HOST buffers including the D2H read of the waveform.
+Multi-GPU: one process per GPU (torchrun), every rank synthesises its own chunks (weak scaling, no data collective).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def synth_inputs(cfg, B, T, seed=0):
+    """Synthetic inputs of the reference's shapes/dtypes: randn features, smooth f0 with unvoiced runs."""
+    from rvc_maker_b200.pitch import coarse_pitch
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    phone = rng.standard_normal(size=(B, T, cfg["text_enc_hidden_dim"]), dtype=np.float32)
+    f0 = np.zeros((B, T))
+    for b in range(B):
+        lf = np.log(200.0) + np.cumsum(rng.standard_normal(T + 9) * 0.03)
+        f = np.clip(np.exp(np.convolve(lf, np.ones(10) / 10.0, mode="valid")[:T]), 80.0, 600.0)
+        t = 0
+        while t < T:
+            run = int(rng.integers(5, 40))
+            if rng.random() < 0.3:
+                f[t:t + run] = 0.0
+            t += run
+        f0[b] = f
+    return dict(phone=torch.from_numpy(phone), phone_lengths=torch.full((B,), T, dtype=torch.int64),
+                pitch=torch.from_numpy(coarse_pitch(f0).astype(np.int64)), nsff0=torch.from_numpy(f0.astype(np.float32)),
+                sid=torch.zeros(B, dtype=torch.int64))
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def build_net(cfg, device):
+    from rvc_maker_b200 import Synthesizer, configs
+
+    torch.manual_seed(1234)  # the reference's own training seed (main/configs/v2/48000.json:4)
+    net = Synthesizer(*configs.ctor_args(cfg), use_f0=True, text_enc_hidden_dim=cfg["text_enc_hidden_dim"])
+    # zero-initialised flow `post` convs would make the flow a no-op for timing purposes only in value, not in work;
+    # give them small random weights so outputs are non-trivial.
+    for i in range(0, 8, 2):
+        torch.nn.init.normal_(net.flow.flows[i].post.weight, std=0.02)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items() if not k.startswith("enc_q.")}
+    del net.enc_q
+    return net.eval().to(device).float(), sd
+
+
+def cpu_baseline(cfg, sd, inp, steps, warmup):
+    """Reference algorithm on the host cores (oracle port, torch CPU fp32, all threads)."""
+    from oracle import synth_oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    folded = synth_oracle.fold_state_dict(sd)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"], folded=folded)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="v2_48k")
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops-json", default=None, help="write the per-kernel timing table here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    from rvc_maker_b200 import configs
+
+    cfg = configs.CONFIGS[args.config]
+    B, T = args.batch, args.frames
+    upp = int(np.prod(cfg["upsample_rates"]))
+    audio_s = B * T * upp / cfg["sr"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"RVC {args.config} f0 Synthesizer.infer, B={B} x T={T} frames ({audio_s:.1f} s of audio per step), random-init"
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.manual_seed(1234)
+        inp = synth_inputs(cfg, B, T)
+        _, sd = build_net(cfg, "cpu")
+        steps = args.steps
+        Ts = T if (args.steps + args.warmup) <= 24 else max(100, T // 4)  # bounded sample: keep the run within minutes
+        if Ts != T:
+            inp = synth_inputs(cfg, B, Ts)
+        times, cores = cpu_baseline(cfg, sd, inp, steps, args.warmup)
+        a_s = B * Ts * upp / cfg["sr"]
+        val = a_s * len(times) / sum(times)
+        sample = f"{len(times)} steps of B={B} x T={Ts} frames ({a_s:.1f} s audio each), torch CPU fp32 oracle port, {cores} threads"
+        print(json.dumps({
+            "impl": "reference", "metric": "audio_seconds_per_second", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    net, sd = build_net(cfg, dev)
+    host = {k: v.pin_memory() for k, v in synth_inputs(cfg, B, T, seed=rank).items()}
+    devin = {k: v.to(dev) for k, v in host.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(inp):
+        return net.infer(inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"])[0]
+
+    for _ in range(args.warmup):
+        step(devin)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: per-step CUDA events, L2 flushed (untimed) between steps
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t_w0 = time.perf_counter()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(devin)
+        b.record()
+        evs.append((a, b))
+    barrier()
+    t_w1 = time.perf_counter()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---- end-to-end: pinned host inputs -> infer -> waveform back on the host, wall clock
+    for _ in range(2):
+        step(host).cpu()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wav = step(host).to("cpu", non_blocking=False)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop(t_w0, time.perf_counter()) if sampler else None
+
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = wav.numel() * wav.element_size()
+    value = world * audio_s * args.steps / (dev_ms / 1e3)
+    e2e = world * audio_s * args.steps / e2e_s
+
+    out = {
+        "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "l2": "256 MiB memset between steps (untimed); per-step working set > L2",
+                   "parallelism": f"{world} replica(s), independent chunks, no data-path collective"},
+        "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": net._engine.launches_per_infer(B, T) * args.steps,
+        "clocks": clocks,
+    }
+
+    if rank == 0:
+        # ---- per-kernel table + roofline of the dominant kernel family (CUDA events around each launch)
+        rows = net._engine.profile(B, T)
+        fam = {}
+        for r in rows:
+            k = r["kind"].split("[")[0]
+            f = fam.setdefault(k, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            f["ms"] += r["ms"]; f["flops"] += r["flops"]; f["bytes"] += r["bytes"]; f["launches"] += r["launches"]
+        top = max(fam, key=lambda k: fam[k]["ms"])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        f = fam[top]
+        total_ms = sum(v["ms"] for v in fam.values())
+        if f["flops"] / max(f["bytes"], 1.0) > 200.0:
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            ach = f["flops"] / (f["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None}
+        else:
+            peak = peaks.get("hbm_gbs", 6650.0)
+            ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
+        roof.update({"kernel": top, "launches_per_step": f["launches"], "share_of_step": f["ms"] / total_ms,
+                     "peak_source": "MEASURED_PEAKS.json (sustained)" if peaks else "fallback"})
+        out["roofline"] = roof
+        out["kernels"] = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4),
+                              "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2), "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
+                              "launches": v["launches"]} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+        if args.ops_json:
+            json.dump(rows, open(args.ops_json, "w"), indent=0)
+        if world == 1 and not args.no_cpu_baseline:
+            inp = synth_inputs(cfg, B, T)
+            times, cores = cpu_baseline(cfg, sd, inp, 2, 1)
+            out["cpu_baseline"] = {"value": audio_s / min(times), "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                   "sample": f"best of 2 after 1 warm-up of the same step (B={B}, T={T}), torch CPU fp32 oracle port"}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -33,15 +33,18 @@ class V:
 class Plan:
     def __init__(self):
         self.ops = []
+        self.meta = []
         self.keep = []
         self.launches = 0
 
-    def add(self, name, fn, *args, launches=1):
+    def add(self, name, fn, *args, launches=1, flops=0.0, bytes_=0.0, kind="other"):
         self.ops.append((name, fn, args))
+        self.meta.append(dict(name=name, kind=kind, flops=float(flops), bytes=float(bytes_), launches=launches))
         self.launches += launches
 
     def add_py(self, fn):
         self.ops.append((None, fn, ()))
+        self.meta.append(None)
 
     def run(self, stream):
         for name, fn, args in self.ops:
@@ -51,6 +54,23 @@ class Plan:
                 rc = fn(*args, stream)
                 if rc != 0:
                     _lib.check(rc, name)
+
+    def run_timed(self, stream):
+        """Replay with a CUDA-event pair around every C-ABI call (profiling aid; not used for headline numbers)."""
+        evs = []
+        for (name, fn, args), meta in zip(self.ops, self.meta):
+            if name is None:
+                fn()
+                continue
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args, stream)
+            b.record()
+            if rc != 0:
+                _lib.check(rc, name)
+            evs.append((meta, a, b))
+        torch.cuda.synchronize()
+        return [dict(m, ms=a.elapsed_time(b)) for m, a, b in evs]
 
 
 def _fold_wn(mod):
@@ -178,7 +198,10 @@ class Engine:
         d.act, d.gated = act, int(gated)
         d.alpha, d.out_scale, d.beta = alpha, out_scale, beta
         plan.keep.append(d)
-        plan.add(name, self.lib.rvc_conv1d_f32, C.byref(d))
+        g2 = 2 if gated else 1
+        flops = 2.0 * B * Cin * Cout * g2 * K * L
+        bytes_ = 4.0 * (B * Cin * L + B * Cout * L * (1 + (res is not None) + (beta != 0.0)) + Cin * K * Cout * g2)
+        plan.add(name, self.lib.rvc_conv1d_f32, C.byref(d), flops=flops, bytes_=bytes_, kind=f"conv1d_f32[C{Cout}k{K}]")
 
     def _buf(self, plan, *shape, dtype=torch.float32):
         t = torch.empty(*shape, dtype=dtype, device=self.dev)
@@ -202,12 +225,12 @@ class Engine:
         vx, vqkv, vatt, vy, vh, vst = V(x, H, T), V(qkv, 3 * H, T), V(att, H, T), V(y, H, T), V(h, Fc, T), V(p.stats, 2 * I, T)
         p.add("embed", lib.rvc_embed_f32, p.phone.data_ptr(), p.pitch.data_ptr() if c["f0"] else None, p.lengths.data_ptr(),
               W["emb_wT"].data_ptr(), W["emb_b"].data_ptr(), W["emb_pitch"].data_ptr() if c["f0"] else None, x.data_ptr(),
-              p.mask.data_ptr(), B, T, D, H)
+              p.mask.data_ptr(), B, T, D, H, flops=2.0 * B * T * D * H, bytes_=4.0 * B * T * (D + H), kind="embed_f32")
         padl = (ks - 1) // 2
         for i in range(c["nl"]):
             self._conv(p, f"qkv{i}", vx, W[f"qkv_w{i}"], vqkv, B=B, Cin=H, Cout=3 * H, L=T, bias=W[f"qkv_b{i}"])
             p.add(f"attn{i}", lib.rvc_rel_attention_f32, qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(), W[f"ev{i}"].data_ptr(),
-                  att.data_ptr(), B, H, c["nh"], T, WINDOW)
+                  att.data_ptr(), B, H, c["nh"], T, WINDOW, flops=4.0 * B * H * T * T, bytes_=16.0 * B * H * T, kind="rel_attention_f32")
             self._conv(p, f"attn_o{i}", vatt, W[f"o_w{i}"], vy, B=B, Cin=H, Cout=H, L=T, bias=W[f"o_b{i}"])
             p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
                   p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0)
@@ -261,7 +284,7 @@ class Engine:
             har = self._buf(p, B, Lfin)
             scratch = self._buf(p, B, T)
             p.add("sine_source", lib.rvc_sine_source_f32, p.f0.data_ptr(), p.eps_src.data_ptr(), W["lin_w"].data_ptr(), W["lin_b"].data_ptr(),
-                  scratch.data_ptr(), har.data_ptr(), B, T, upp, c["sr"], launches=2)
+                  scratch.data_ptr(), har.data_ptr(), B, T, upp, c["sr"], launches=2, bytes_=8.0 * B * Lfin, kind="sine_source_f32")
         xpre = self._buf(p, B, U, T)
         self._conv(p, "conv_pre", V(p.z, I, T), W["pre_w"], V(xpre, U, T), B=B, Cin=I, Cout=U, L=T, K=7, pad=3, bias=W["pre_b"],
                    bias_b=gc.data_ptr() + self.cond_off[4] * 4, bias_b_bs=self.cond_total, mask=p.mask, in_mask=True)
@@ -292,7 +315,8 @@ class Engine:
             d.B, d.Cin, d.Cout, d.Lin, d.k, d.u = B, curC, Ci, curL, k, u
             d.pre_slope = LRELU_SLOPE
             p.keep.append(d)
-            p.add(f"ups{i}", lib.rvc_convtr1d_f32, C.byref(d))
+            p.add(f"ups{i}", lib.rvc_convtr1d_f32, C.byref(d), flops=2.0 * B * curC * Ci * k * curL, bytes_=4.0 * B * (curC * curL + Ci * Li),
+                  kind="convtr1d_f32")
             vs1, vs2, vs3 = V(S[1], Ci, Li), V(S[2], Ci, Li), V(S[3], Ci, Li)
             for j, (kk, dils) in enumerate(zip(rks, rds)):
                 src = vs0
@@ -310,7 +334,8 @@ class Engine:
                                    out_scale=1.0 / nk, beta=0.0 if j == 0 else 1.0)
             cur, curC, curL = S[3], Ci, Li
         p.o = self._buf(p, B, 1, Lfin)
-        p.add("conv_post", lib.rvc_conv_post_f32, cur.data_ptr(), curC * curL, curL, W["post_w"].data_ptr(), p.o.data_ptr(), Lfin, B, curC, curL, 0.01)
+        p.add("conv_post", lib.rvc_conv_post_f32, cur.data_ptr(), curC * curL, curL, W["post_w"].data_ptr(), p.o.data_ptr(), Lfin, B, curC, curL, 0.01,
+              flops=2.0 * B * curC * 7 * curL, bytes_=4.0 * B * (curC + 1) * curL, kind="conv_post_f32")
         return p
 
     def plan(self, kind, B, T):
@@ -322,6 +347,23 @@ class Engine:
             pl = self._enc_plan(B, T) if kind == "enc" else self._dec_plan(B, T)
             self.plans[key] = pl
         return pl
+
+    def profile(self, B, T, repeats=3):
+        """Per-kernel CUDA-event timings of the (B, T) plans, replayed on the workspaces left by the last infer()."""
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        best = None
+        with torch.cuda.device(self.dev):
+            for _ in range(repeats):
+                rows = self.plan("enc", B, T).run_timed(stream) + self.plan("dec", B, T).run_timed(stream)
+                if best is None:
+                    best = rows
+                else:
+                    for a, b in zip(best, rows):
+                        a["ms"] = min(a["ms"], b["ms"])
+        return best
+
+    def launches_per_infer(self, B, T):
+        return self.plan("enc", B, T).launches + self.plan("dec", B, T).launches
 
     # ------------------------------------------------------------------ infer
     def infer(self, phone, phone_lengths, pitch, nsff0, sid, rate, out_dtype, noise=None):
