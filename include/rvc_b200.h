@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 3
+#define RVC_ABI_VERSION 4
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -121,6 +121,39 @@ int rvc_sample_zp_f32(const float* stats, const float* eps, const float* mask, f
  */
 int rvc_sine_source_f32(const float* f0, const float* noise, const float* lin_w, const float* lin_b, float* scratch,
                         float* har, int32_t B, int32_t T, int32_t upp, float sr, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05) path for the ResBlock convolutions (residuals.py:32-36), C -> C, odd K, "same" padding.
+ *
+ * Packed activation layout: act[b][c / CK][rvc_packed_rows(L)][CK] with CK = 8 (bf16) or 4 (tf32-rounded fp32), i.e.
+ * 16-byte units of CK channels per position; position l lives at row 64 + l and every other row is ZERO (allocate
+ * zero-filled; kernels never write pad rows).  Packed weights: [K][Cin / CK][Cout][CK].
+ */
+#define RVC_DT_BF16 0
+#define RVC_DT_TF32 1
+int64_t rvc_packed_rows(int32_t L);
+/* y_packed = DT(leaky_relu(x, slope)) for fp32 x[B,C,L] (slope = 1 -> identity) */
+int rvc_pack_act(const float* x, int64_t x_bs, int64_t x_cs, void* y, int32_t B, int32_t C, int32_t L, int32_t dtype, float slope,
+                 void* stream);
+/* folded fp32 [Cout][Cin][K] -> packed [K][Cin/CK][Cout][CK] */
+int rvc_pack_weight(const float* w, void* y, int32_t Cout, int32_t Cin, int32_t K, int32_t dtype, void* stream);
+
+/*
+ * One conv job:  v = conv(a) + bias (+ res);  y_f32 = v;  y_act = DT(leaky_relu(v, act_slope));
+ *                acc_out = (beta != 0 ? beta * acc_out : 0) + out_scale * v.      res / y_f32 / acc_out: contiguous fp32 [B,C,L].
+ * Up to three independent jobs (the three ResBlocks of a generator stage) share one persistent launch.
+ */
+typedef struct {
+    const void* a; const void* w; const float* bias;
+    const float* res; float* y_f32; void* y_act; float* acc_out;
+    int32_t K, dil;
+    float act_slope, out_scale, beta;
+} rvc_tc_job;
+typedef struct {
+    rvc_tc_job jobs[3];
+    int32_t njobs, B, C, L, dtype;
+} rvc_conv1d_tc_desc;
+int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,8 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
+DT_BF16, DT_TF32 = 0, 1
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
@@ -45,6 +46,19 @@ class ConvTr1dDesc(C.Structure):
     ]
 
 
+class TcJob(C.Structure):
+    _fields_ = [
+        ("a", _vp), ("w", _vp), ("bias", _vp),
+        ("res", _vp), ("y_f32", _vp), ("y_act", _vp), ("acc_out", _vp),
+        ("K", _i32), ("dil", _i32),
+        ("act_slope", _f32), ("out_scale", _f32), ("beta", _f32),
+    ]
+
+
+class Conv1dTcDesc(C.Structure):
+    _fields_ = [("jobs", TcJob * 3), ("njobs", _i32), ("B", _i32), ("C", _i32), ("L", _i32), ("dtype", _i32)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
 SIGNATURES = {
     "rvc_abi_version": (C.c_int, []),
@@ -58,6 +72,10 @@ SIGNATURES = {
     "rvc_rel_attention_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rvc_sample_zp_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rvc_sine_source_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
+    "rvc_packed_rows": (_i64, [_i32]),
+    "rvc_pack_act": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "rvc_conv1d_tc": (C.c_int, [C.POINTER(Conv1dTcDesc), _vp]),
 }
 
 _lib = None

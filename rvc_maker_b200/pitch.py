@@ -1,7 +1,7 @@
 """Host-side coarse-pitch quantiser — the integer `pitch` input of Synthesizer.infer.
 
 Mirrors VC.get_f0's tail (main/inference/convert.py:318-323, f0_min=50, f0_max=1100 at :196-199): mel scale in float64,
-affine map to 1..255, ``np.rint`` (half-to-even).  Bit-exact by construction; checked against the oracle in tests.
+affine map to 1..255, ``np.rint`` (half-to-even).  Bit-exact by construction (tests/ compare it with the CPU restatement).
 """
 import numpy as np
 
