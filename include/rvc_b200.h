@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 4
+#define RVC_ABI_VERSION 5
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -80,12 +80,16 @@ typedef struct {
     float* y;        int64_t y_bs, y_cs;
     int32_t B, Cin, Cout, Lin, k, u, kn, sn, pn;
     float pre_slope;
+    /* optional: input = (x + x2 + x3) / in_div — the `xs / num_kernels` of the previous stage (synthesizers.py:157-159)
+     * fused at load; x2/x3 share x's strides. */
+    const float* x2; const float* x3; float in_div;
 } rvc_convtr1d_desc;
 int rvc_convtr1d_f32(const rvc_convtr1d_desc* d, void* stream);
 
-/* y[b,0,l] = tanh( sum_{ci,k} w[ci*7+k] * leaky_relu(x[b,ci,l-3+k], slope) ), no bias — conv_post (synthesizers.py:161). */
-int rvc_conv_post_f32(const float* x, int64_t x_bs, int64_t x_cs, const float* w, float* y, int64_t y_bs,
-                      int32_t B, int32_t C, int32_t L, float slope, void* stream);
+/* y[b,0,l] = tanh( sum_{ci,k} w[ci*7+k] * leaky_relu(in[b,ci,l-3+k], slope) ), no bias — conv_post (synthesizers.py:161);
+ * in = x, or (x + x2 + x3) / in_div when x2/x3 are given. */
+int rvc_conv_post_f32(const float* x, const float* x2, const float* x3, float in_div, int64_t x_bs, int64_t x_cs, const float* w,
+                      float* y, int64_t y_bs, int32_t B, int32_t C, int32_t L, float slope, void* stream);
 
 /*
  * TextEncoder front end (synthesizers.py:367-368): x[b,c,t] = leaky_relu((phone[b,t,:].W[c,:] + bias[c] + E[pitch[b,t],c])

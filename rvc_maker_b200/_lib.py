@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 DT_BF16, DT_TF32 = 0, 1
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -43,6 +43,7 @@ class ConvTr1dDesc(C.Structure):
         ("y", _vp), ("y_bs", _i64), ("y_cs", _i64),
         ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("Lin", _i32), ("k", _i32), ("u", _i32), ("kn", _i32), ("sn", _i32), ("pn", _i32),
         ("pre_slope", _f32),
+        ("x2", _vp), ("x3", _vp), ("in_div", _f32),
     ]
 
 
@@ -66,7 +67,7 @@ SIGNATURES = {
     "rvc_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "rvc_conv1d_f32": (C.c_int, [C.POINTER(Conv1dDesc), _vp]),
     "rvc_convtr1d_f32": (C.c_int, [C.POINTER(ConvTr1dDesc), _vp]),
-    "rvc_conv_post_f32": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp]),
+    "rvc_conv_post_f32": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp]),
     "rvc_embed_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_layernorm_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp]),
     "rvc_rel_attention_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -43,7 +43,12 @@ __global__ void __launch_bounds__(256) convtr1d_f32_kernel(const rvc_convtr1d_de
             const int ci = idx / XW, j = idx - ci * XW;
             const int q = q0 - (M - 1) + j;
             float v = 0.f;
-            if (ci0 + ci < d.Cin && q >= 0 && q < d.Lin) v = rvc::lrelu(xb[(int64_t)(ci0 + ci) * d.x_cs + q], d.pre_slope);
+            if (ci0 + ci < d.Cin && q >= 0 && q < d.Lin) {
+                const int64_t off = (int64_t)(ci0 + ci) * d.x_cs + q;
+                v = xb[off];
+                if (d.x2) v = ((v + d.x2[(int64_t)b * d.x_bs + off]) + d.x3[(int64_t)b * d.x_bs + off]) / d.in_div;
+                v = rvc::lrelu(v, d.pre_slope);
+            }
             x_s[idx] = v;
         }
         for (int idx = tid; idx < CI_T * KR * CO_T; idx += nthreads) {
@@ -108,7 +113,8 @@ __global__ void __launch_bounds__(256) convtr1d_f32_kernel(const rvc_convtr1d_de
 }
 
 // conv_post: Cout = 1, k = 7, pad 3, no bias, pre-leaky_relu(slope), tanh.  One thread = 4 consecutive outputs.
-__global__ void __launch_bounds__(256) conv_post_f32_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_cs,
+__global__ void __launch_bounds__(256) conv_post_f32_kernel(const float* __restrict__ x, const float* __restrict__ x2,
+                                                            const float* __restrict__ x3, float in_div, int64_t x_bs, int64_t x_cs,
                                                             const float* __restrict__ w, float* __restrict__ y, int64_t y_bs,
                                                             int C, int L, float slope) {
     extern __shared__ float w_s[];  // [C][7]
@@ -119,11 +125,19 @@ __global__ void __launch_bounds__(256) conv_post_f32_kernel(const float* __restr
     if (l0 >= L) return;
     const float* xb = x + (int64_t)b * x_bs;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool interior = (l0 >= 4) && (l0 + 8 <= L) && ((x_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0);
+    const bool interior = !x2 && (l0 >= 4) && (l0 + 8 <= L) && ((x_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0);
     for (int c = 0; c < C; ++c) {
         const float* xr = xb + (int64_t)c * x_cs;
         float win[12];  // x[l0-4 .. l0+7]
-        if (interior) {
+        if (x2) {
+            const float* xr2 = x2 + (int64_t)b * x_bs + (int64_t)c * x_cs;
+            const float* xr3 = x3 + (int64_t)b * x_bs + (int64_t)c * x_cs;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const int l = l0 - 4 + j;
+                win[j] = (l >= 0 && l < L) ? ((xr[l] + xr2[l]) + xr3[l]) / in_div : 0.f;
+            }
+        } else if (interior) {
             const float4 a = *reinterpret_cast<const float4*>(xr + l0 - 4);
             const float4 bq = *reinterpret_cast<const float4*>(xr + l0);
             const float4 cq = *reinterpret_cast<const float4*>(xr + l0 + 4);
@@ -162,6 +176,7 @@ RVC_API int rvc_convtr1d_f32(const rvc_convtr1d_desc* dp, void* stream) {
     if (d.k < d.u || ((d.k - d.u) & 1) || d.u > 64)
         return rvc::fail(RVC_ESHAPE, "rvc_convtr1d_f32: needs k >= u, (k-u) even, u <= 64 (k=%d u=%d)", d.k, d.u);
     if (d.har && (!d.nw || d.kn <= 0 || d.sn <= 0)) return rvc::fail(RVC_EINVAL, "rvc_convtr1d_f32: noise conv arguments");
+    if ((d.x2 == nullptr) != (d.x3 == nullptr)) return rvc::fail(RVC_EINVAL, "rvc_convtr1d_f32: x2 and x3 go together");
     if (d.Lin == 0) return 0;
     const int QG = 128 / d.u > 0 ? 128 / d.u : 1;
     const int M = rvc::cdiv(d.k, d.u);
@@ -179,12 +194,13 @@ RVC_API int rvc_convtr1d_f32(const rvc_convtr1d_desc* dp, void* stream) {
     return rvc::check_launch("rvc_convtr1d_f32");
 }
 
-RVC_API int rvc_conv_post_f32(const float* x, int64_t x_bs, int64_t x_cs, const float* w, float* y, int64_t y_bs,
-                                 int32_t B, int32_t C, int32_t L, float slope, void* stream) {
+RVC_API int rvc_conv_post_f32(const float* x, const float* x2, const float* x3, float in_div, int64_t x_bs, int64_t x_cs, const float* w,
+                                 float* y, int64_t y_bs, int32_t B, int32_t C, int32_t L, float slope, void* stream) {
     if (!x || !w || !y) return rvc::fail(RVC_EINVAL, "rvc_conv_post_f32: null pointer");
+    if ((x2 == nullptr) != (x3 == nullptr)) return rvc::fail(RVC_EINVAL, "rvc_conv_post_f32: x2 and x3 go together");
     if (B <= 0 || B > 65535 || C <= 0 || C > 1024 || L < 0) return rvc::fail(RVC_ESHAPE, "rvc_conv_post_f32: bad shape");
     if (L == 0) return 0;
     dim3 grid(rvc::cdiv(rvc::cdiv(L, 4), 256), B);
-    conv_post_f32_kernel<<<grid, 256, C * 7 * sizeof(float), (cudaStream_t)stream>>>(x, x_bs, x_cs, w, y, y_bs, C, L, slope);
+    conv_post_f32_kernel<<<grid, 256, C * 7 * sizeof(float), (cudaStream_t)stream>>>(x, x2, x3, in_div, x_bs, x_cs, w, y, y_bs, C, L, slope);
     return rvc::check_launch("rvc_conv_post_f32");
 }

@@ -12,7 +12,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, Conv1dDesc, ConvTr1dDesc
+from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_TF32, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc
 
 LRELU_SLOPE = 0.1
 WINDOW = 10
@@ -103,6 +103,9 @@ class Engine:
                         U=m.upsample_initial_channel, G=m.gin_channels, D=m.text_enc_hidden_dim, rates=m.upsample_rates,
                         uks=m.upsample_kernel_sizes, rks=m.resblock_kernel_sizes, rds=m.resblock_dilation_sizes, sr=float(m.sr),
                         upp=m.upp, f0=m.use_f0)
+        self.precision = getattr(m, "precision", "tc")
+        if self.precision not in ("tc", "fp32"):
+            raise ValueError(f"precision must be 'tc' or 'fp32', got {self.precision!r}")
         self._fold(m)
         self.plans = {}
 
@@ -161,6 +164,19 @@ class Engine:
         d = m.dec
         W["pre_w"], W["pre_b"] = _pack_conv(_f(d.conv_pre.weight)), _f(d.conv_pre.bias)
         nk = len(c["rks"])
+        # ResBlock stage precision: bf16 tensor cores for C >= 128, tf32 tensor cores for C in {32, 64} (SURVEY 7 hard part 2:
+        # bf16 on the narrow stages breaks the 1e-3 bar), fp32 CUDA cores otherwise / when precision == "fp32".
+        self.stage_dt = []
+        tc_w = {}
+        for i in range(len(c["rates"])):
+            ch = c["U"] // (2 ** (i + 1))
+            dt = None
+            if self.precision == "tc" and nk == 3 and len({len(dl) for dl in c["rds"]}) == 1 and all(k % 2 == 1 and (k - 1) // 2 * max(dl) <= 64 for k, dl in zip(c["rks"], c["rds"])):
+                if ch >= 128 and ch % 128 == 0 and ch <= 256:
+                    dt = DT_BF16
+                elif ch in (32, 64):
+                    dt = DT_TF32
+            self.stage_dt.append(dt)
         for i in range(len(c["rates"])):
             up = d.ups[i] if c["f0"] else d.ups_and_resblocks[i * (nk + 1)]
             W[f"up_w{i}"] = _fold_wn(up).permute(0, 2, 1).contiguous()  # [Cin][k][Cout]
@@ -171,13 +187,26 @@ class Engine:
             for j in range(nk):
                 rb = d.resblocks[i * nk + j] if c["f0"] else d.ups_and_resblocks[i * (nk + 1) + 1 + j]
                 for mm in range(len(c["rds"][j])):
-                    W[f"rb{i}_{j}_c1w{mm}"], W[f"rb{i}_{j}_c1b{mm}"] = _pack_conv(_fold_wn(rb.convs1[mm])), _f(rb.convs1[mm].bias)
-                    W[f"rb{i}_{j}_c2w{mm}"], W[f"rb{i}_{j}_c2b{mm}"] = _pack_conv(_fold_wn(rb.convs2[mm])), _f(rb.convs2[mm].bias)
+                    w1, w2 = _fold_wn(rb.convs1[mm]), _fold_wn(rb.convs2[mm])
+                    W[f"rb{i}_{j}_c1b{mm}"], W[f"rb{i}_{j}_c2b{mm}"] = _f(rb.convs1[mm].bias), _f(rb.convs2[mm].bias)
+                    if self.stage_dt[i] is None:
+                        W[f"rb{i}_{j}_c1w{mm}"], W[f"rb{i}_{j}_c2w{mm}"] = _pack_conv(w1), _pack_conv(w2)
+                    else:
+                        tc_w[f"rb{i}_{j}_c1w{mm}"], tc_w[f"rb{i}_{j}_c2w{mm}"] = (w1, self.stage_dt[i]), (w2, self.stage_dt[i])
         W["post_w"] = _f(d.conv_post.weight)[0].contiguous()
         if c["f0"]:
             W["lin_w"], W["lin_b"] = _f(d.m_source.l_linear.weight).view(1), _f(d.m_source.l_linear.bias).view(1)
         W["emb_g"] = _f(m.emb_g.weight)
         self.W = {k: (v.to(self.dev) if v is not None else None) for k, v in W.items()}
+        # tensor-core weights: [Cout][Cin][K] fp32 -> packed [K][Cin/CK][Cout][CK] in bf16 / tf32 (device-side pack kernel)
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        with torch.cuda.device(self.dev):
+            for k, (w, dt) in tc_w.items():
+                wd = w.to(self.dev).contiguous()
+                out = torch.empty(wd.numel() * (2 if dt == DT_BF16 else 4), dtype=torch.uint8, device=self.dev)
+                _lib.check(self.lib.rvc_pack_weight(wd.data_ptr(), out.data_ptr(), wd.shape[0], wd.shape[1], wd.shape[2], dt, st), "pack_weight")
+                self.W[k] = out
+            torch.cuda.synchronize(self.dev)
 
     # ------------------------------------------------------------------ descriptor helpers
     def _conv(self, plan, name, x, w, y, *, B, Cin, Cout, L, K=1, dil=1, pad=0, bias=None, bias_b=None, bias_b_bs=0, mask=None,
@@ -202,6 +231,11 @@ class Engine:
         flops = 2.0 * B * Cin * Cout * g2 * K * L
         bytes_ = 4.0 * (B * Cin * L + B * Cout * L * (1 + (res is not None) + (beta != 0.0)) + Cin * K * Cout * g2)
         plan.add(name, self.lib.rvc_conv1d_f32, C.byref(d), flops=flops, bytes_=bytes_, kind=f"conv1d_f32[C{Cout}k{K}]")
+
+    def _zbuf(self, plan, nbytes):
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
+        plan.keep.append(t)
+        return t
 
     def _buf(self, plan, *shape, dtype=torch.float32):
         t = torch.empty(*shape, dtype=dtype, device=self.dev)
@@ -297,12 +331,15 @@ class Engine:
             lens.append(L)
         big = max(ch * ln for ch, ln in zip(chans, lens))
         S = [self._buf(p, B * big) for _ in range(4)]
-        cur, curC, curL = xpre, U, T
+        cur, curC, curL = (xpre, None, None), U, T   # cur = (x, x2, x3): the stage input is (x + x2 + x3) / nk when x2 is set
         for i, (u, k) in enumerate(zip(rates, uks)):
             Ci, Li = chans[i], lens[i]
+            dt = self.stage_dt[i]
             d = ConvTr1dDesc()
-            vx = V(cur, curC, curL)
+            vx = V(cur[0], curC, curL)
             d.x, d.x_bs, d.x_cs = vx.ptr, vx.bs, vx.cs
+            if cur[1] is not None:
+                d.x2, d.x3, d.in_div = cur[1].data_ptr(), cur[2].data_ptr(), float(nk)
             d.w, d.bias = W[f"up_w{i}"].data_ptr(), W[f"up_b{i}"].data_ptr()
             if c["f0"]:
                 sn = int(math.prod(rates[i + 1:])) if i + 1 < len(rates) else 1
@@ -317,25 +354,75 @@ class Engine:
             p.keep.append(d)
             p.add(f"ups{i}", lib.rvc_convtr1d_f32, C.byref(d), flops=2.0 * B * curC * Ci * k * curL, bytes_=4.0 * B * (curC * curL + Ci * Li),
                   kind="convtr1d_f32")
-            vs1, vs2, vs3 = V(S[1], Ci, Li), V(S[2], Ci, Li), V(S[3], Ci, Li)
-            for j, (kk, dils) in enumerate(zip(rks, rds)):
-                src = vs0
-                for mm, dl in enumerate(dils):
-                    last = mm == len(dils) - 1
-                    self._conv(p, f"rb{i}_{j}_c1_{mm}", src, W[f"rb{i}_{j}_c1w{mm}"], vs1, B=B, Cin=Ci, Cout=Ci, L=Li, K=kk, dil=dl,
-                               pad=(kk * dl - dl) // 2, bias=W[f"rb{i}_{j}_c1b{mm}"], pre_slope=LRELU_SLOPE)
-                    if not last:
-                        self._conv(p, f"rb{i}_{j}_c2_{mm}", vs1, W[f"rb{i}_{j}_c2w{mm}"], vs2, B=B, Cin=Ci, Cout=Ci, L=Li, K=kk,
-                                   pad=(kk - 1) // 2, bias=W[f"rb{i}_{j}_c2b{mm}"], pre_slope=LRELU_SLOPE, res=src)
-                        src = vs2
-                    else:
-                        self._conv(p, f"rb{i}_{j}_c2_{mm}", vs1, W[f"rb{i}_{j}_c2w{mm}"], vs3, B=B, Cin=Ci, Cout=Ci, L=Li, K=kk,
-                                   pad=(kk - 1) // 2, bias=W[f"rb{i}_{j}_c2b{mm}"], pre_slope=LRELU_SLOPE, res=src,
-                                   out_scale=1.0 / nk, beta=0.0 if j == 0 else 1.0)
-            cur, curC, curL = S[3], Ci, Li
+            if dt is None:
+                # ---- fp32 CUDA-core ResBlocks, sequential, accumulated into S[3]
+                vs1, vs2, vs3 = V(S[1], Ci, Li), V(S[2], Ci, Li), V(S[3], Ci, Li)
+                for j, (kk, dils) in enumerate(zip(rks, rds)):
+                    src = vs0
+                    for mm, dl in enumerate(dils):
+                        last = mm == len(dils) - 1
+                        self._conv(p, f"rb{i}_{j}_c1_{mm}", src, W[f"rb{i}_{j}_c1w{mm}"], vs1, B=B, Cin=Ci, Cout=Ci, L=Li, K=kk, dil=dl,
+                                   pad=(kk * dl - dl) // 2, bias=W[f"rb{i}_{j}_c1b{mm}"], pre_slope=LRELU_SLOPE)
+                        if not last:
+                            self._conv(p, f"rb{i}_{j}_c2_{mm}", vs1, W[f"rb{i}_{j}_c2w{mm}"], vs2, B=B, Cin=Ci, Cout=Ci, L=Li, K=kk,
+                                       pad=(kk - 1) // 2, bias=W[f"rb{i}_{j}_c2b{mm}"], pre_slope=LRELU_SLOPE, res=src)
+                            src = vs2
+                        else:
+                            self._conv(p, f"rb{i}_{j}_c2_{mm}", vs1, W[f"rb{i}_{j}_c2w{mm}"], vs3, B=B, Cin=Ci, Cout=Ci, L=Li, K=kk,
+                                       pad=(kk - 1) // 2, bias=W[f"rb{i}_{j}_c2b{mm}"], pre_slope=LRELU_SLOPE, res=src,
+                                       out_scale=1.0 / nk, beta=0.0 if j == 0 else 1.0)
+                cur, curC, curL = (S[3], None, None), Ci, Li
+            else:
+                # ---- tensor-core ResBlocks: the nk blocks advance in lock-step, one persistent launch per conv step
+                esz = 2 if dt == DT_BF16 else 4
+                rows = int(lib.rvc_packed_rows(Li))
+                pk = lambda: self._zbuf(p, B * Ci * rows * esz)          # packed activations (pad rows stay zero)
+                xa = pk()
+                ta, pa = [pk() for _ in range(nk)], [pk() for _ in range(nk)]
+                P = [S[1 + j] for j in range(nk)]                        # fp32 residual streams / block outputs
+                p.add(f"pack{i}", lib.rvc_pack_act, S[0].data_ptr(), Ci * Li, Li, xa.data_ptr(), B, Ci, Li, dt, LRELU_SLOPE,
+                      bytes_=B * Ci * Li * (4.0 + esz), kind="pack_act")
+                order = sorted(range(nk), key=lambda j: -rks[j])          # heavy kernels first (static round-robin tiles)
+                nsteps = len(rds[0])
+                assert all(len(dl) == nsteps for dl in rds)
+                for mm in range(nsteps):
+                    last = mm == nsteps - 1
+                    for half in (1, 2):
+                        d = Conv1dTcDesc()
+                        d.njobs, d.B, d.C, d.L, d.dtype = nk, B, Ci, Li, dt
+                        fl = 0.0
+                        for slot, j in enumerate(order):
+                            jb = d.jobs[slot]
+                            kk = rks[j]
+                            if half == 1:   # t = conv1_d(lrelu(x));  store lrelu(t) packed
+                                jb.a = (xa if mm == 0 else pa[j]).data_ptr()
+                                jb.w, jb.bias = W[f"rb{i}_{j}_c1w{mm}"].data_ptr(), W[f"rb{i}_{j}_c1b{mm}"].data_ptr()
+                                jb.y_act = ta[j].data_ptr()
+                                jb.K, jb.dil = kk, rds[j][mm]
+                            else:           # x = conv2(lrelu(t)) + x;  store x (fp32) and lrelu(x) packed for the next pair
+                                jb.a = ta[j].data_ptr()
+                                jb.w, jb.bias = W[f"rb{i}_{j}_c2w{mm}"].data_ptr(), W[f"rb{i}_{j}_c2b{mm}"].data_ptr()
+                                jb.res = (S[0] if mm == 0 else P[j]).data_ptr()
+                                jb.y_f32 = P[j].data_ptr()
+                                if not last:
+                                    jb.y_act = pa[j].data_ptr()
+                                jb.K, jb.dil = kk, 1
+                            jb.act_slope, jb.out_scale, jb.beta = LRELU_SLOPE, 1.0, 0.0
+                            fl += 2.0 * B * Ci * Ci * kk * Li
+                        p.keep.append(d)
+                        by = nk * B * Ci * Li * (2.0 * esz if half == 1 else (esz + 8.0 + (0 if last else esz)))
+                        p.add(f"rbtc{i}_s{mm}_c{half}", lib.rvc_conv1d_tc, C.byref(d), flops=fl, bytes_=by,
+                              kind=f"conv1d_tc_{'bf16' if dt == DT_BF16 else 'tf32'}[C{Ci}]")
+                if nk == 3:
+                    cur, curC, curL = (P[0], P[1], P[2]), Ci, Li
+                else:
+                    raise NotImplementedError("tensor-core path expects 3 ResBlocks per stage")
         p.o = self._buf(p, B, 1, Lfin)
-        p.add("conv_post", lib.rvc_conv_post_f32, cur.data_ptr(), curC * curL, curL, W["post_w"].data_ptr(), p.o.data_ptr(), Lfin, B, curC, curL, 0.01,
-              flops=2.0 * B * curC * 7 * curL, bytes_=4.0 * B * (curC + 1) * curL, kind="conv_post_f32")
+        x2 = cur[1].data_ptr() if cur[1] is not None else None
+        x3 = cur[2].data_ptr() if cur[2] is not None else None
+        p.add("conv_post", lib.rvc_conv_post_f32, cur[0].data_ptr(), x2, x3, float(nk), curC * curL, curL, W["post_w"].data_ptr(), p.o.data_ptr(),
+              Lfin, B, curC, curL, 0.01, flops=2.0 * B * curC * 7 * curL, bytes_=4.0 * B * (curC * (3 if x2 else 1) + 1) * curL,
+              kind="conv_post_f32")
         return p
 
     def plan(self, kind, B, T):

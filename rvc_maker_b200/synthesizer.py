@@ -17,6 +17,7 @@ module whose parameters are not on a CUDA device, or without the built library, 
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 from torch import nn
@@ -168,6 +169,8 @@ class Synthesizer(nn.Module):
         self.flow = fl
         self.emb_g = nn.Embedding(spk_embed_dim, G)
 
+        # "tc": ResBlocks on tcgen05 tensor cores (bf16 for C >= 128, tf32 for C in {32, 64}); "fp32": CUDA-core fp32 everywhere
+        self.precision = kwargs.get("precision", os.environ.get("RVC_B200_PRECISION", "tc"))
         self._engine = None
         self._noise_override = None  # tests: (eps_z [B,I,T], eps_src [B,T*upp,1] or None)
 

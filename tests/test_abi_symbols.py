@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.rvc_abi_version() == 4
+    assert lib.rvc_abi_version() == 5
     # argument validation happens before any CUDA call, so it is checkable without a GPU
     rc = lib.rvc_conv1d_f32(None, None)
     assert rc == -1
@@ -46,7 +46,7 @@ def test_desc_struct_layout_matches_header():
     from rvc_maker_b200._lib import Conv1dDesc, ConvTr1dDesc
 
     assert ctypes.sizeof(Conv1dDesc) == 176
-    assert ctypes.sizeof(ConvTr1dDesc) == 136
+    assert ctypes.sizeof(ConvTr1dDesc) == 160
     from rvc_maker_b200._lib import Conv1dTcDesc, TcJob
 
     assert ctypes.sizeof(TcJob) == 80 and ctypes.sizeof(Conv1dTcDesc) == 264

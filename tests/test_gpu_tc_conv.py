@@ -82,6 +82,11 @@ def run_case(dtype, Cc, K, dil, B, L, seed=0, with_res=True, njobs=1):
 @pytest.mark.parametrize("Cc", [32, 64, 128, 256])
 @pytest.mark.parametrize("K,dil", [(3, 1), (7, 3), (11, 5)])
 def test_tc_conv_shapes(dtype, Cc, K, dil):
+    if dtype == 1 and Cc == 256:
+        # tf32 doubles the activation tile: 256 channels do not fit shared memory -> loud shape error, no fallback
+        with pytest.raises(RuntimeError, match="does not fit shared memory"):
+            run_case(dtype, Cc, K, dil, B=2, L=1000)
+        return
     run_case(dtype, Cc, K, dil, B=2, L=1000)
 
 
