@@ -234,7 +234,7 @@ def main():
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "tc" else "f32", "data": "synthetic",
-        "config": {"workload": workload, "precision": ("bf16 tcgen05 (C>=128) + tf32 tcgen05 (C=64/32) ResBlocks, fp32 elsewhere"
+        "config": {"workload": workload, "precision": ("bf16 tcgen05 (C>=128) + fp16 tcgen05 (C=64/32) ResBlocks, fp32 elsewhere"
                                                        if args.precision == "tc" else "fp32 CUDA cores"), "l2": "256 MiB memset between steps (untimed); per-step working set > L2",
                    "parallelism": f"{world} replica(s), independent chunks, no data-path collective"},
         "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -262,7 +262,7 @@ def main():
         if top.startswith(("conv1d", "convtr1d", "rel_attention", "embed")):
             # contraction kernels: tensor roofline (tf32 runs at half the bf16 rate; CUDA-core fp32 kernels are still reported
             # against the tensor peak because that is the bound the north star sets for them)
-            peak = bf16_peak / 2 if "tf32" in top else bf16_peak
+            peak = bf16_peak
             ach = f["flops"] / (f["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None}
         else:

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 5
+#define RVC_ABI_VERSION 6
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -127,35 +127,47 @@ int rvc_sine_source_f32(const float* f0, const float* noise, const float* lin_w,
                         float* har, int32_t B, int32_t T, int32_t upp, float sr, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Tensor-core (tcgen05) path for the ResBlock convolutions (residuals.py:32-36), C -> C, odd K, "same" padding.
+ * Tensor-core (tcgen05) Conv1d: Cin -> Cout, odd K, dilation, "same" padding, stride 1, fp32 accumulation in TMEM.
+ * Used for the ResBlocks (residuals.py:32-36), the TextEncoder 1x1 / FFN convs (synthesizers.py:222,302-305,369), the flow's
+ * pre / WaveNet / post convs (residuals.py:129, modules.py:43-45) and conv_pre (synthesizers.py:146).
  *
- * Packed activation layout: act[b][c / CK][rvc_packed_rows(L)][CK] with CK = 8 (bf16) or 4 (tf32-rounded fp32), i.e.
- * 16-byte units of CK channels per position; position l lives at row 64 + l and every other row is ZERO (allocate
- * zero-filled; kernels never write pad rows).  Packed weights: [K][Cin / CK][Cout][CK].
+ * Packed activation layout: act[b][c / 8][rvc_packed_rows(L)][8] in bf16 or fp16, i.e. 16-byte units of 8 channels per
+ * position; position l lives at row 64 + l and every other row is ZERO (allocate zero-filled; kernels never write pad
+ * rows).  Packed weights: [K][Cin / 8][Cout][8].
  */
 #define RVC_DT_BF16 0
-#define RVC_DT_TF32 1
+#define RVC_DT_FP16 2
 int64_t rvc_packed_rows(int32_t L);
-/* y_packed = DT(leaky_relu(x, slope)) for fp32 x[B,C,L] (slope = 1 -> identity) */
-int rvc_pack_act(const float* x, int64_t x_bs, int64_t x_cs, void* y, int32_t B, int32_t C, int32_t L, int32_t dtype, float slope,
-                 void* stream);
-/* folded fp32 [Cout][Cin][K] -> packed [K][Cin/CK][Cout][CK] */
+/* y_packed = DT(leaky_relu(x, slope) * mask) for fp32 x[B,C,L] with element strides (slope = 1 -> identity, mask may be NULL) */
+int rvc_pack_act(const float* x, int64_t x_bs, int64_t x_cs, const float* mask, void* y, int32_t B, int32_t C, int32_t L,
+                 int32_t dtype, float slope, void* stream);
+/* folded fp32 [Cout][Cin][K] -> packed [K][Cin/8][Cout][8] */
 int rvc_pack_weight(const float* w, void* y, int32_t Cout, int32_t Cin, int32_t K, int32_t dtype, void* stream);
 
 /*
- * One conv job:  v = conv(a) + bias (+ res);  y_f32 = v;  y_act = DT(leaky_relu(v, act_slope));
- *                acc_out = (beta != 0 ? beta * acc_out : 0) + out_scale * v.      res / y_f32 / acc_out: contiguous fp32 [B,C,L].
- * Up to three independent jobs (the three ResBlocks of a generator stage) share one persistent launch.
+ * One conv job.  With acc = conv(a) (weight-column order):
+ *   gated == 0:  v[co] = acc[co] + bias[co] + bias_b[b][co]
+ *   gated == 1:  v[c]  = tanh(acc[t] + bias[t] + bias_b[b][t]) * sigmoid(acc[s] + bias[s] + bias_b[b][s]), where within every
+ *                N tile of `nt` weight columns the first nt/2 are the tanh columns of output channels [tile*nt/2, ...) and
+ *                the last nt/2 the matching sigmoid columns (the caller packs weights / biases in that order)  [commons.py:35-41]
+ *   relu: v = max(v, 0);   res: v = res[b][c][l] + alpha * v;   mask: v *= mask[b][l]
+ *   y_f32[b][c][l] = v (element strides y_bs / y_cs);   y_act = DT(leaky_relu(v, act_slope)) in the packed layout.
+ * Up to three jobs sharing (B, Cin, Cout, L, dtype) run in one persistent launch.  nt / mt = 0 let the library pick the tile.
  */
 typedef struct {
-    const void* a; const void* w; const float* bias;
-    const float* res; float* y_f32; void* y_act; float* acc_out;
-    int32_t K, dil;
-    float act_slope, out_scale, beta;
+    const void* a; const void* w;
+    const float* bias;
+    const float* bias_b; int64_t bias_b_bs;
+    const float* mask;
+    const float* res; int64_t res_bs, res_cs;
+    float* y_f32; int64_t y_bs, y_cs;
+    void* y_act;
+    int32_t K, dil, gated, relu;
+    float alpha, act_slope;
 } rvc_tc_job;
 typedef struct {
     rvc_tc_job jobs[3];
-    int32_t njobs, B, C, L, dtype;
+    int32_t njobs, B, Cin, Cout, L, dtype, nt, mt;
 } rvc_conv1d_tc_desc;
 int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);
 

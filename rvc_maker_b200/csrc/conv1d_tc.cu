@@ -1,61 +1,73 @@
-// ResBlock Conv1d (C -> C, kernel K, dilation d, "same" padding) as an implicit GEMM on the 5th-gen tensor cores.
+// Conv1d (Cin -> Cout, odd kernel K, dilation d, "same" padding, stride 1) as an implicit GEMM on the 5th-gen tensor cores.
 //
-//   D[128 positions, NT out-channels] += A_tap[128 positions, 16|8 in-channels] * W_tap[NT, 16|8]^T   (tcgen05.mma, fp32 in TMEM)
+//   D[128 positions, NT out-channels] += A_tap[128 positions, 16 in-channels] * W_tap[NT, 16]^T     (tcgen05.mma kind::f16,
+//                                                                                                    fp32 accumulators in TMEM)
+// Data layout ("C8 packed", DT = bf16 or fp16):  act[b][c / 8][64 + l][8].  One 16-byte unit holds 8 consecutive channels of
+// ONE position and consecutive positions are 16 B apart — exactly the K-major no-swizzle UMMA core-matrix layout (8 rows x
+// 16 B contiguous).  A conv tap that reads position l + j*dil - pad is therefore the SAME shared-memory tile with the
+// descriptor start address advanced by 16*j*dil bytes: the activation tile (TM + halo positions x a stage of input
+// channels) is staged once with plain 1-D bulk async copies (one per 16-byte channel chunk; the zero rows around the
+// sequence live in the global buffer, so there is no boundary logic) and reused by every tap.  Weights, pre-packed
+// [K][Cin/8][Cout][8], stream through a 4-slot ring.
 //
-// Data layout ("C8/C4 packed", DT = bf16 or tf32-rounded fp32):  act[b][c / CK][PADL + l][CK],  CK = 16 B / sizeof(DT).
-// One 16-byte unit therefore holds CK consecutive channels of ONE position, and consecutive positions are 16 B apart,
-// which is exactly the K-major no-swizzle UMMA core-matrix layout (8 rows x 16 B contiguous).  A conv tap that reads
-// position l + j*dil - pad is the SAME shared-memory tile with the descriptor start address advanced by 16*j*dil bytes,
-// so the activation tile (256 + halo positions, all input channels) is staged ONCE per CTA tile with plain 1-D bulk
-// async copies (one per 16-byte channel chunk; zero rows around the sequence live in the global buffer, so there is no
-// boundary logic) and reused by every tap.  Weights, pre-packed [K][C/CK][Cout][CK], stream through a 4-slot ring.
-//
-// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (+TMEM owner), warps 2-5 = epilogue
-// (TMEM -> registers -> bias / residual / leaky_relu -> fp32 NCL and packed-DT stores, coalesced along positions).
-// Accumulators are double-buffered in TMEM (2 groups x 2 sub-tiles x NT columns) so the epilogue of tile t overlaps
-// the MMAs of tile t+1; CTAs are persistent over a static round-robin tile list spanning up to three independent
-// conv jobs (the three ResBlocks of a stage).
+// Warp roles (224 threads): warp 0 = activation producer, warp 6 = weight producer, warp 1 = MMA issuer (+TMEM owner),
+// warps 2-5 = epilogue (TMEM -> registers -> bias / gate / relu / residual / mask -> fp32 NCL and packed-DT stores, all
+// coalesced along positions).  Accumulators are double-buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile
+// t+1; CTAs are persistent over a static round-robin tile list spanning up to three independent jobs (the three ResBlocks
+// of a generator stage, or the res/skip halves of a WaveNet layer).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
 constexpr int BM = 128;          // positions per accumulator (TMEM lanes)
-constexpr int MT = 2;            // accumulators (sub-tiles) per CTA tile
-constexpr int TM = BM * MT;      // positions per CTA tile
 constexpr int PADL = 64;         // zero rows in front of position 0 in packed buffers
 constexpr int PADR = 64;
+constexpr int ROWQ = 256;        // packed row count is rounded up to this
 constexpr int NSTAGE = 4;        // weight ring slots
 constexpr int STAGE_BYTES = 16384;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 224;
 constexpr int MAXJOBS = 3;
 
-__host__ __device__ inline int packed_rows(int L) { return PADL + ((L + TM - 1) / TM) * TM + PADR; }
+__host__ __device__ inline int packed_rows(int L) { return PADL + ((L + ROWQ - 1) / ROWQ) * ROWQ + PADR; }
 
 struct Params {
     rvc_tc_job jobs[MAXJOBS];
-    int njobs, B, C, L, Lp;
-    int nch;          // C / CK: 16-byte channel chunks
-    int rows_max;     // A-tile rows allocated per chunk (TM + max halo)
+    int njobs, B, Cin, Cout, L, Lp;
+    int nch;          // Cin / 8: 16-byte input-channel chunks
+    int nch_out;      // packed output chunks (Cout/8, or Cout/16 when gated)
+    int ach;          // chunks per activation stage
+    int ncs;          // activation stages per tile
+    int rows_max;     // rows allocated per chunk in an activation stage (TM + max halo)
     int n_lt, n_nt;   // tiles along L and along Cout
     int tiles_per_job, total_tiles;
-    int abuf;         // number of A buffers (1 or 2)
+    int fp16;         // operand format: 0 = bf16, 1 = fp16
 };
 
-template <bool TF32, int NT>
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
+    if (fp16) {
+        a = fminf(fmaxf(a, -65504.f), 65504.f);
+        b = fminf(fmaxf(b, -65504.f), 65504.f);
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    return tc::pack_bf16x2(a, b);
+}
+
+template <int NT, int MT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) {
-    constexpr int SCH = STAGE_BYTES / (NT * 16);          // 16-byte chunks per weight stage
-    constexpr uint32_t IDESC = tc::make_idesc(TF32 ? 2u : 1u, NT);
-    constexpr int TMEM_COLS = 2 * MT * NT;                // two accumulator groups
-    static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
-    constexpr int CK = TF32 ? 4 : 8;
+    constexpr int TM = BM * MT;
+    constexpr int SCH = (STAGE_BYTES / (NT * 16)) & ~1;    // 16-byte chunks per weight stage (even)
+    constexpr int ACC_COLS = 2 * MT * NT;                   // two accumulator groups
+    constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+    static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
 
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t a_bytes = (uint32_t)p.nch * p.rows_max * 16;
-    uint8_t* a_smem = smem;                                         // [abuf][nch][rows_max][16]
-    uint8_t* w_smem = smem + (size_t)p.abuf * a_bytes;              // [NSTAGE][STAGE_BYTES]
+    const uint32_t a_bytes = (uint32_t)p.ach * p.rows_max * 16;
+    uint8_t* a_smem = smem;                                         // [2][ach][rows_max][16]
+    uint8_t* w_smem = smem + 2 * (size_t)a_bytes;                   // [NSTAGE][STAGE_BYTES]
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + NSTAGE * STAGE_BYTES);
-    // barrier map: w_full[4] w_empty[4] a_full[2] a_empty[2] acc_full[2] acc_empty[2]
     const uint32_t bar0 = tc::smem_u32(bars);
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
     auto W_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
@@ -81,8 +93,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int spt = (p.nch + SCH - 1) / SCH;   // weight stages per tap
-
     auto decode = [&](int tile, int& j, int& b, int& lt, int& nt) {
         j = tile / p.tiles_per_job;
         int r = tile - j * p.tiles_per_job;
@@ -92,102 +102,104 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     };
 
     if (warp == 0) {
-        // ======================= producer: A tiles + weight stages via bulk async copies =======================
-        uint32_t wst = 0, wph = 0;
-        int it = 0;
-        // stage the activation tile of local iteration `i` (tile id `t`) into buffer i % abuf
-        auto issue_a = [&](int i, int t) {
-            int j, b, lt, nt;
-            decode(t, j, b, lt, nt);
-            const rvc_tc_job& jb = p.jobs[j];
-            const int pad = (jb.K - 1) / 2 * jb.dil;
-            const int rows = TM + 2 * pad;
-            const int ab = i % p.abuf;
-            const uint32_t aph = (i / p.abuf) & 1;
-            if (lane == 0) {
-                tc::mbar_wait(A_EMPTY(ab), aph ^ 1);
-                tc::mbar_arrive_expect_tx(A_FULL(ab), (uint32_t)p.nch * rows * 16);
-            }
-            __syncwarp();
-            const uint8_t* asrc = reinterpret_cast<const uint8_t*>(jb.a) +
-                                  ((size_t)b * p.nch * p.Lp + (size_t)(PADL + lt * TM - pad)) * 16;
-            for (int c = lane; c < p.nch; c += 32)
-                tc::bulk_g2s(tc::smem_u32(a_smem + (size_t)ab * a_bytes + (size_t)c * p.rows_max * 16), asrc + (size_t)c * p.Lp * 16,
-                             (uint32_t)rows * 16, A_FULL(ab));
-        };
-        if ((int)blockIdx.x < p.total_tiles) issue_a(0, blockIdx.x);
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        // ======================= activation producer =======================
+        uint32_t ast = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int j, b, lt, nt;
             decode(tile, j, b, lt, nt);
             const rvc_tc_job& jb = p.jobs[j];
-            const int next = tile + gridDim.x;
-            bool next_issued = next >= p.total_tiles;
+            const int pad = (jb.K - 1) / 2 * jb.dil;
+            const int rows = TM + 2 * pad;
+            for (int cs = 0; cs < p.ncs; ++cs) {
+                const int c0 = cs * p.ach;
+                const int nc = min(p.ach, p.nch - c0);
+                if (lane == 0) {
+                    tc::mbar_wait(A_EMPTY(ast), aph ^ 1);
+                    tc::mbar_arrive_expect_tx(A_FULL(ast), (uint32_t)nc * rows * 16);
+                }
+                __syncwarp();
+                const uint8_t* asrc = reinterpret_cast<const uint8_t*>(jb.a) +
+                                      (((size_t)b * p.nch + c0) * p.Lp + (size_t)(PADL + lt * TM - pad)) * 16;
+                for (int c = lane; c < nc; c += 32)
+                    tc::bulk_g2s(tc::smem_u32(a_smem + (size_t)ast * a_bytes + (size_t)c * p.rows_max * 16), asrc + (size_t)c * p.Lp * 16,
+                                 (uint32_t)rows * 16, A_FULL(ast));
+                if (++ast == 2) { ast = 0; aph ^= 1; }
+            }
+        }
+    } else if (warp == 6) {
+        // ======================= weight producer =======================
+        uint32_t wst = 0, wph = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int j, b, lt, nt;
+            decode(tile, j, b, lt, nt);
+            const rvc_tc_job& jb = p.jobs[j];
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(jb.w);
-            int sidx = 0;
-            for (int tap = 0; tap < jb.K; ++tap) {
-                for (int s = 0; s < spt; ++s, ++sidx) {
-                    // prefetch the next tile's activations once this tile's MMAs are known to be running (double-buffered A only)
-                    if (!next_issued && p.abuf == 2 && sidx == NSTAGE) { issue_a(it + 1, next); next_issued = true; }
-                    const int c0 = s * SCH;
-                    const int nc = min(SCH, p.nch - c0);
-                    if (lane == 0) {
-                        tc::mbar_wait(W_EMPTY(wst), wph ^ 1);
-                        tc::mbar_arrive_expect_tx(W_FULL(wst), (uint32_t)nc * NT * 16);
+            for (int cs = 0; cs < p.ncs; ++cs) {
+                const int ca = cs * p.ach;
+                const int na = min(p.ach, p.nch - ca);
+                for (int tap = 0; tap < jb.K; ++tap) {
+                    for (int c0 = 0; c0 < na; c0 += SCH) {
+                        const int nc = min(SCH, na - c0);
+                        if (lane == 0) {
+                            tc::mbar_wait(W_EMPTY(wst), wph ^ 1);
+                            tc::mbar_arrive_expect_tx(W_FULL(wst), (uint32_t)nc * NT * 16);
+                        }
+                        __syncwarp();
+                        const uint32_t dst = tc::smem_u32(w_smem + wst * STAGE_BYTES);
+                        const uint8_t* src = wsrc + (((size_t)tap * p.nch + ca + c0) * p.Cout + (size_t)nt * NT) * 16;
+                        if (NT == p.Cout) {
+                            if (lane == 0) tc::bulk_g2s(dst, src, (uint32_t)nc * NT * 16, W_FULL(wst));
+                        } else {
+                            for (int c = lane; c < nc; c += 32) tc::bulk_g2s(dst + c * NT * 16, src + (size_t)c * p.Cout * 16, NT * 16, W_FULL(wst));
+                        }
+                        if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                     }
-                    __syncwarp();
-                    const uint32_t dst = tc::smem_u32(w_smem + wst * STAGE_BYTES);
-                    if (NT == p.C) {
-                        if (lane == 0)
-                            tc::bulk_g2s(dst, wsrc + ((size_t)(tap * p.nch + c0) * p.C) * 16, (uint32_t)nc * NT * 16, W_FULL(wst));
-                    } else {
-                        for (int c = lane; c < nc; c += 32)
-                            tc::bulk_g2s(dst + c * NT * 16, wsrc + ((size_t)(tap * p.nch + c0 + c) * p.C + nt * NT) * 16, NT * 16, W_FULL(wst));
-                    }
-                    if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                 }
             }
-            if (!next_issued) issue_a(it + 1, next);
         }
     } else if (warp == 1) {
         // ======================= MMA issuer (single thread) =======================
         if (lane == 0) {
-            uint32_t wst = 0, wph = 0;
+            const uint32_t idesc = tc::make_idesc(p.fp16 ? 0u : 1u, NT);
+            uint32_t wst = 0, wph = 0, ast = 0, aph = 0;
             int it = 0;
             const uint32_t lbo_a = (uint32_t)p.rows_max * 16, lbo_b = NT * 16;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 int j, b, lt, nt;
                 decode(tile, j, b, lt, nt);
                 const rvc_tc_job& jb = p.jobs[j];
-                const int ab = it % p.abuf;
-                const uint32_t aph = (it / p.abuf) & 1;
                 const int g = it & 1;
                 const uint32_t gph = (it >> 1) & 1;
                 tc::mbar_wait(ACC_EMPTY(g), gph ^ 1);
-                tc::mbar_wait(A_FULL(ab), aph);
                 tc::fence_after_sync();
-                const uint32_t a_base = tc::smem_u32(a_smem + (size_t)ab * a_bytes);
-                for (int tap = 0; tap < jb.K; ++tap) {
-                    for (int s = 0; s < spt; ++s) {
-                        const int c0 = s * SCH;
-                        const int nc = min(SCH, p.nch - c0);
-                        tc::mbar_wait(W_FULL(wst), wph);
-                        tc::fence_after_sync();
-                        const uint32_t w_base = tc::smem_u32(w_smem + wst * STAGE_BYTES);
+                for (int cs = 0; cs < p.ncs; ++cs) {
+                    const int na = min(p.ach, p.nch - cs * p.ach);
+                    tc::mbar_wait(A_FULL(ast), aph);
+                    tc::fence_after_sync();
+                    const uint32_t a_base = tc::smem_u32(a_smem + (size_t)ast * a_bytes);
+                    for (int tap = 0; tap < jb.K; ++tap) {
+                        for (int c0 = 0; c0 < na; c0 += SCH) {
+                            const int nc = min(SCH, na - c0);
+                            tc::mbar_wait(W_FULL(wst), wph);
+                            tc::fence_after_sync();
+                            const uint32_t w_base = tc::smem_u32(w_smem + wst * STAGE_BYTES);
 #pragma unroll
-                        for (int m = 0; m < MT; ++m) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((g * MT + m) * NT);
-                            for (int kk = 0; kk < nc; kk += 2) {
-                                const uint32_t a_addr = a_base + (uint32_t)((c0 + kk) * p.rows_max + m * BM + tap * jb.dil) * 16;
-                                const uint32_t b_addr = w_base + (uint32_t)(kk * NT) * 16;
-                                tc::umma<TF32>(d_tmem, tc::make_desc(a_addr, lbo_a, 128), tc::make_desc(b_addr, lbo_b, 128), IDESC,
-                                               (tap | s | kk) != 0);
+                            for (int m = 0; m < MT; ++m) {
+                                const uint32_t d_tmem = tmem_base + (uint32_t)((g * MT + m) * NT);
+                                for (int kk = 0; kk < nc; kk += 2) {
+                                    const uint32_t a_addr = a_base + (uint32_t)((c0 + kk) * p.rows_max + m * BM + tap * jb.dil) * 16;
+                                    const uint32_t b_addr = w_base + (uint32_t)(kk * NT) * 16;
+                                    tc::umma<false>(d_tmem, tc::make_desc(a_addr, lbo_a, 128), tc::make_desc(b_addr, lbo_b, 128), idesc,
+                                                    (cs | tap | c0 | kk) != 0);
+                                }
                             }
+                            tc::umma_commit(W_EMPTY(wst));
+                            if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                         }
-                        tc::umma_commit(W_EMPTY(wst));
-                        if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                     }
+                    tc::umma_commit(A_EMPTY(ast));
+                    if (++ast == 2) { ast = 0; aph ^= 1; }
                 }
-                tc::umma_commit(A_EMPTY(ab));
                 tc::umma_commit(ACC_FULL(g));
             }
         }
@@ -201,62 +213,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             const rvc_tc_job& jb = p.jobs[j];
             const int g = it & 1;
             const uint32_t gph = (it >> 1) & 1;
+            const float* bb = jb.bias_b ? jb.bias_b + (size_t)b * jb.bias_b_bs : nullptr;
             tc::mbar_wait(ACC_FULL(g), gph);
             tc::fence_after_sync();
 #pragma unroll 1
             for (int m = 0; m < MT; ++m) {
                 const int l = lt * TM + m * BM + q * 32 + lane;
                 const bool ok = l < p.L;
+                const float mk = (jb.mask && ok) ? jb.mask[(size_t)b * p.L + l] : 1.f;
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * MT + m) * NT);
+                constexpr int NBLK = NT / 32;
+                const int nblk = jb.gated ? NBLK / 2 : NBLK;
 #pragma unroll 1
-                for (int cb = 0; cb < NT / 32; ++cb) {
+                for (int cb = 0; cb < nblk; ++cb) {
                     uint32_t r[32];
-                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * MT + m) * NT + cb * 32), r);
-                    tc::tmem_ld_wait();
-                    const int co0 = nt * NT + cb * 32;
                     float v[32];
+                    tc::tmem_ld32(t_row + cb * 32, r);
+                    tc::tmem_ld_wait();
+                    const int col0 = nt * NT + cb * 32;       // weight-column index (bias order)
+                    int co0;                                  // output-channel index
+                    if (jb.gated) {
+                        uint32_t r2[32];
+                        tc::tmem_ld32(t_row + (cb + NBLK / 2) * 32, r2);
+                        tc::tmem_ld_wait();
+                        const int col1 = col0 + (NBLK / 2) * 32;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __ldg(jb.bias + co0 + i);
-                    if (ok) {
-                        const size_t nbase = ((size_t)b * p.C + co0) * p.L + l;
-                        if (jb.res) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] += jb.res[nbase + (size_t)i * p.L];
+                        for (int i = 0; i < 32; ++i) {
+                            float t = __uint_as_float(r[i]) + __ldg(jb.bias + col0 + i);
+                            float s = __uint_as_float(r2[i]) + __ldg(jb.bias + col1 + i);
+                            if (bb) { t += __ldg(bb + col0 + i); s += __ldg(bb + col1 + i); }
+                            v[i] = tanhf(t) * rvc::sigmoidf_acc(s);
                         }
-                        if (jb.y_f32) {
+                        co0 = nt * (NT / 2) + cb * 32;
+                    } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) jb.y_f32[nbase + (size_t)i * p.L] = v[i];
+                        for (int i = 0; i < 32; ++i) {
+                            v[i] = __uint_as_float(r[i]) + (jb.bias ? __ldg(jb.bias + col0 + i) : 0.f);
+                            if (bb) v[i] += __ldg(bb + col0 + i);
                         }
-                        if (jb.acc_out) {
-                            if (jb.beta != 0.f) {
+                        co0 = col0;
+                    }
+                    if (!ok) continue;
+                    if (jb.relu) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    float* o = jb.acc_out + nbase + (size_t)i * p.L;
-                                    *o = jb.beta * (*o) + jb.out_scale * v[i];
-                                }
-                            } else {
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (jb.res) {
+                        const float* rp = jb.res + (size_t)b * jb.res_bs + (size_t)co0 * jb.res_cs + l;
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) jb.acc_out[nbase + (size_t)i * p.L] = jb.out_scale * v[i];
-                            }
-                        }
-                        if (jb.y_act) {
-                            uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) +
-                                          (((size_t)b * p.nch + co0 / CK) * p.Lp + PADL + l) * 16;
+                        for (int i = 0; i < 32; ++i) v[i] = rp[(size_t)i * jb.res_cs] + jb.alpha * v[i];
+                    }
+                    if (jb.mask) {
 #pragma unroll
-                            for (int u = 0; u < 32 / CK; ++u) {
-                                uint4 pk;
-                                if constexpr (TF32) {
-                                    pk.x = __float_as_uint(tc::round_tf32(rvc::lrelu(v[4 * u + 0], jb.act_slope)));
-                                    pk.y = __float_as_uint(tc::round_tf32(rvc::lrelu(v[4 * u + 1], jb.act_slope)));
-                                    pk.z = __float_as_uint(tc::round_tf32(rvc::lrelu(v[4 * u + 2], jb.act_slope)));
-                                    pk.w = __float_as_uint(tc::round_tf32(rvc::lrelu(v[4 * u + 3], jb.act_slope)));
-                                } else {
-                                    pk.x = tc::pack_bf16x2(rvc::lrelu(v[8 * u + 0], jb.act_slope), rvc::lrelu(v[8 * u + 1], jb.act_slope));
-                                    pk.y = tc::pack_bf16x2(rvc::lrelu(v[8 * u + 2], jb.act_slope), rvc::lrelu(v[8 * u + 3], jb.act_slope));
-                                    pk.z = tc::pack_bf16x2(rvc::lrelu(v[8 * u + 4], jb.act_slope), rvc::lrelu(v[8 * u + 5], jb.act_slope));
-                                    pk.w = tc::pack_bf16x2(rvc::lrelu(v[8 * u + 6], jb.act_slope), rvc::lrelu(v[8 * u + 7], jb.act_slope));
-                                }
-                                *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp * 16) = pk;
-                            }
+                        for (int i = 0; i < 32; ++i) v[i] *= mk;
+                    }
+                    if (jb.y_f32) {
+                        float* yp = jb.y_f32 + (size_t)b * jb.y_bs + (size_t)co0 * jb.y_cs + l;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) yp[(size_t)i * jb.y_cs] = v[i];
+                    }
+                    if (jb.y_act) {
+                        uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (((size_t)b * p.nch_out + co0 / 8) * p.Lp + PADL + l) * 16;
+                        const float sl = jb.act_slope;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            uint4 pk;
+                            pk.x = pack2(rvc::lrelu(v[8 * u + 0], sl), rvc::lrelu(v[8 * u + 1], sl), p.fp16);
+                            pk.y = pack2(rvc::lrelu(v[8 * u + 2], sl), rvc::lrelu(v[8 * u + 3], sl), p.fp16);
+                            pk.z = pack2(rvc::lrelu(v[8 * u + 4], sl), rvc::lrelu(v[8 * u + 5], sl), p.fp16);
+                            pk.w = pack2(rvc::lrelu(v[8 * u + 6], sl), rvc::lrelu(v[8 * u + 7], sl), p.fp16);
+                            *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp * 16) = pk;
                         }
                     }
                 }
@@ -276,89 +302,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
 }
 
 // ------------------------------------------------------------------------------------------------ packing kernels
-template <bool TF32>
-__global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_cs, uint8_t* __restrict__ y,
-                                                       int nch, int L, int Lp, float slope) {
-    constexpr int CK = TF32 ? 4 : 8;
+// fp32 [B, C, L] (strided) -> packed [B][C/8][Lp][8]; value = lrelu(x, slope) * mask
+__global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_cs, const float* __restrict__ mask,
+                                                       uint8_t* __restrict__ y, int nch, int L, int Lp, float slope, int fp16) {
     const int l = blockIdx.x * 256 + threadIdx.x;
     const int c = blockIdx.y, b = blockIdx.z;
     if (l >= L) return;
-    const float* xp = x + (int64_t)b * x_bs + (int64_t)c * CK * x_cs + l;
-    float v[CK];
+    const float* xp = x + (int64_t)b * x_bs + (int64_t)c * 8 * x_cs + l;
+    const float mk = mask ? mask[(int64_t)b * L + l] : 1.f;
+    float v[8];
 #pragma unroll
-    for (int i = 0; i < CK; ++i) v[i] = rvc::lrelu(xp[(int64_t)i * x_cs], slope);
+    for (int i = 0; i < 8; ++i) v[i] = rvc::lrelu(xp[(int64_t)i * x_cs], slope) * mk;
     uint4 pk;
-    if constexpr (TF32) {
-        pk.x = __float_as_uint(tc::round_tf32(v[0])); pk.y = __float_as_uint(tc::round_tf32(v[1]));
-        pk.z = __float_as_uint(tc::round_tf32(v[2])); pk.w = __float_as_uint(tc::round_tf32(v[3]));
-    } else {
-        pk.x = tc::pack_bf16x2(v[0], v[1]); pk.y = tc::pack_bf16x2(v[2], v[3]);
-        pk.z = tc::pack_bf16x2(v[4], v[5]); pk.w = tc::pack_bf16x2(v[6], v[7]);
-    }
+    pk.x = pack2(v[0], v[1], fp16); pk.y = pack2(v[2], v[3], fp16);
+    pk.z = pack2(v[4], v[5], fp16); pk.w = pack2(v[6], v[7], fp16);
     *reinterpret_cast<uint4*>(y + (((size_t)b * nch + c) * Lp + PADL + l) * 16) = pk;
 }
 
-// folded fp32 [Cout][Cin][K] -> packed [K][Cin/CK][Cout][CK]
-template <bool TF32>
-__global__ void pack_weight_kernel(const float* __restrict__ w, uint8_t* __restrict__ y, int Cout, int Cin, int K) {
-    constexpr int CK = TF32 ? 4 : 8;
-    const int nch = Cin / CK;
+// folded fp32 [Cout][Cin][K] -> packed [K][Cin/8][Cout][8]
+__global__ void pack_weight_kernel(const float* __restrict__ w, uint8_t* __restrict__ y, int Cout, int Cin, int K, int fp16) {
+    const int nch = Cin / 8;
     const int64_t n = (int64_t)K * nch * Cout;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
     const int co = (int)(idx % Cout);
     const int c = (int)((idx / Cout) % nch);
     const int tap = (int)(idx / ((int64_t)Cout * nch));
-    float v[CK];
+    float v[8];
 #pragma unroll
-    for (int i = 0; i < CK; ++i) v[i] = w[((int64_t)co * Cin + c * CK + i) * K + tap];
+    for (int i = 0; i < 8; ++i) v[i] = w[((int64_t)co * Cin + c * 8 + i) * K + tap];
     uint4 pk;
-    if constexpr (TF32) {
-        pk.x = __float_as_uint(tc::round_tf32(v[0])); pk.y = __float_as_uint(tc::round_tf32(v[1]));
-        pk.z = __float_as_uint(tc::round_tf32(v[2])); pk.w = __float_as_uint(tc::round_tf32(v[3]));
-    } else {
-        pk.x = tc::pack_bf16x2(v[0], v[1]); pk.y = tc::pack_bf16x2(v[2], v[3]);
-        pk.z = tc::pack_bf16x2(v[4], v[5]); pk.w = tc::pack_bf16x2(v[6], v[7]);
-    }
+    pk.x = pack2(v[0], v[1], fp16); pk.y = pack2(v[2], v[3], fp16);
+    pk.z = pack2(v[4], v[5], fp16); pk.w = pack2(v[6], v[7], fp16);
     *reinterpret_cast<uint4*>(y + idx * 16) = pk;
 }
 
-template <bool TF32, int NT>
+template <int NT, int MT>
 int launch_tc(const Params& p, size_t smem, int grid, cudaStream_t stream) {
-    auto kern = conv1d_tc_kernel<TF32, NT>;
+    auto kern = conv1d_tc_kernel<NT, MT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return rvc::fail((int)e, "rvc_conv1d_tc: smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
     kern<<<grid, NTHREADS, smem, stream>>>(p);
     return rvc::check_launch("rvc_conv1d_tc");
 }
 
+template <int NT>
+int launch_tc_mt(int mt, const Params& p, size_t smem, int grid, cudaStream_t stream) {
+    return mt == 1 ? launch_tc<NT, 1>(p, smem, grid, stream) : launch_tc<NT, 2>(p, smem, grid, stream);
+}
+
 }  // namespace
 
 RVC_API int64_t rvc_packed_rows(int32_t L) { return packed_rows(L); }
 
-RVC_API int rvc_pack_act(const float* x, int64_t x_bs, int64_t x_cs, void* y, int32_t B, int32_t C, int32_t L, int32_t dtype, float slope,
-                         void* stream) {
+RVC_API int rvc_pack_act(const float* x, int64_t x_bs, int64_t x_cs, const float* mask, void* y, int32_t B, int32_t C, int32_t L,
+                         int32_t dtype, float slope, void* stream) {
     if (!x || !y) return rvc::fail(RVC_EINVAL, "rvc_pack_act: null pointer");
-    const int CK = dtype == RVC_DT_TF32 ? 4 : 8;
-    if (B <= 0 || B > 65535 || C <= 0 || C % CK || L < 0) return rvc::fail(RVC_ESHAPE, "rvc_pack_act: bad shape (C=%d must be a multiple of %d)", C, CK);
+    if (dtype != RVC_DT_BF16 && dtype != RVC_DT_FP16) return rvc::fail(RVC_EINVAL, "rvc_pack_act: dtype must be RVC_DT_BF16 or RVC_DT_FP16");
+    if (B <= 0 || B > 65535 || C <= 0 || C % 8 || L < 0) return rvc::fail(RVC_ESHAPE, "rvc_pack_act: bad shape (C=%d must be a multiple of 8)", C);
     if (L == 0) return 0;
-    dim3 grid(rvc::cdiv(L, 256), C / CK, B);
-    if (dtype == RVC_DT_TF32)
-        pack_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_cs, (uint8_t*)y, C / CK, L, packed_rows(L), slope);
-    else
-        pack_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_cs, (uint8_t*)y, C / CK, L, packed_rows(L), slope);
+    dim3 grid(rvc::cdiv(L, 256), C / 8, B);
+    pack_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_cs, mask, (uint8_t*)y, C / 8, L, packed_rows(L), slope, dtype == RVC_DT_FP16);
     return rvc::check_launch("rvc_pack_act");
 }
 
 RVC_API int rvc_pack_weight(const float* w, void* y, int32_t Cout, int32_t Cin, int32_t K, int32_t dtype, void* stream) {
     if (!w || !y) return rvc::fail(RVC_EINVAL, "rvc_pack_weight: null pointer");
-    const int CK = dtype == RVC_DT_TF32 ? 4 : 8;
-    if (Cout <= 0 || Cin <= 0 || Cin % CK || K <= 0) return rvc::fail(RVC_ESHAPE, "rvc_pack_weight: bad shape");
-    const int64_t n = (int64_t)K * (Cin / CK) * Cout;
-    if (dtype == RVC_DT_TF32)
-        pack_weight_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)y, Cout, Cin, K);
-    else
-        pack_weight_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)y, Cout, Cin, K);
+    if (dtype != RVC_DT_BF16 && dtype != RVC_DT_FP16) return rvc::fail(RVC_EINVAL, "rvc_pack_weight: dtype must be RVC_DT_BF16 or RVC_DT_FP16");
+    if (Cout <= 0 || Cin <= 0 || Cin % 8 || K <= 0) return rvc::fail(RVC_ESHAPE, "rvc_pack_weight: bad shape");
+    const int64_t n = (int64_t)K * (Cin / 8) * Cout;
+    pack_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)y, Cout, Cin, K, dtype == RVC_DT_FP16);
     return rvc::check_launch("rvc_pack_weight");
 }
 
@@ -366,47 +379,65 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     if (!dp) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: null descriptor");
     const rvc_conv1d_tc_desc& d = *dp;
     if (d.njobs < 1 || d.njobs > MAXJOBS) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: njobs must be 1..3");
-    const bool tf32 = d.dtype == RVC_DT_TF32;
-    const int CK = tf32 ? 4 : 8;
-    if (d.B <= 0 || d.L <= 0 || d.C <= 0 || d.C % (2 * CK)) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: C=%d must be a multiple of %d", d.C, 2 * CK);
-    const int NT = d.C >= 128 ? 128 : d.C;
-    if (NT != 128 && NT != 64 && NT != 32) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: C=%d unsupported (32, 64 or a multiple of 128)", d.C);
-    if (d.C % NT) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: C=%d must be a multiple of 128", d.C);
+    if (d.dtype != RVC_DT_BF16 && d.dtype != RVC_DT_FP16) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: dtype must be RVC_DT_BF16 or RVC_DT_FP16");
+    if (d.B <= 0 || d.L <= 0 || d.Cin <= 0 || d.Cout <= 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: bad shape");
+    if (d.Cin % 16) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: Cin=%d must be a multiple of 16", d.Cin);
+    if (d.Cout % 32) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: Cout=%d must be a multiple of 32", d.Cout);
     Params p;
-    int maxpad = 0;
+    int maxpad = 0, gated = d.jobs[0].gated ? 1 : 0;
     for (int j = 0; j < d.njobs; ++j) {
         const rvc_tc_job& jb = d.jobs[j];
-        if (!jb.a || !jb.w || !jb.bias) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: job %d has null a/w/bias", j);
+        if (!jb.a || !jb.w) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: job %d has null a/w", j);
         if (jb.K <= 0 || !(jb.K & 1) || jb.dil <= 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: job %d needs odd K, dil > 0", j);
+        if ((jb.gated ? 1 : 0) != gated) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: jobs of one launch must agree on `gated`");
+        if (jb.gated && !jb.bias) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: gated job needs a bias");
         const int pad = (jb.K - 1) / 2 * jb.dil;
         if (pad > PADL) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: halo %d exceeds the %d zero rows of the packed layout", pad, PADL);
         maxpad = pad > maxpad ? pad : maxpad;
         p.jobs[j] = jb;
     }
-    p.njobs = d.njobs; p.B = d.B; p.C = d.C; p.L = d.L; p.Lp = packed_rows(d.L);
-    p.nch = d.C / CK;
-    p.rows_max = TM + 2 * maxpad;
-    p.n_lt = rvc::cdiv(d.L, TM);
-    p.n_nt = d.C / NT;
-    p.tiles_per_job = d.B * p.n_lt * p.n_nt;
-    p.total_tiles = p.tiles_per_job * d.njobs;
-    const size_t a_bytes = (size_t)p.nch * p.rows_max * 16;
-    const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 256;
-    const size_t limit = 227 * 1024;
-    p.abuf = (2 * a_bytes + fixed <= limit) ? 2 : 1;
-    const size_t smem = p.abuf * a_bytes + fixed;
-    if (smem > limit) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: activation tile (%zu B) does not fit shared memory", a_bytes);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // tile shape: the widest N tile (and 2 sub-tiles) that still yields >= one wave of CTAs; gated needs NT % 64 == 0
+    int mt = d.mt, NT = d.nt;
+    auto ntiles = [&](int nt_, int mt_) { return (long)d.njobs * d.B * rvc::cdiv(d.L, BM * mt_) * (d.Cout / nt_); };
+    if (NT == 0) {
+        const int cands[3] = {128, 64, 32};
+        for (int i = 0; i < 3; ++i) {
+            const int c = cands[i];
+            if (d.Cout % c || (gated && c % 64)) continue;
+            NT = c;
+            if (ntiles(c, 1) >= sms) break;
+        }
+        if (NT == 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: no N tile for Cout=%d (gated=%d)", d.Cout, gated);
+    }
+    if (NT != 128 && NT != 64 && NT != 32) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt must be 32, 64 or 128");
+    if (d.Cout % NT || (gated && NT % 64)) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt=%d does not tile Cout=%d (gated=%d)", NT, d.Cout, gated);
+    if (mt == 0) mt = ntiles(NT, 2) >= 2L * sms ? 2 : 1;
+    if (mt != 1 && mt != 2) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: mt must be 1 or 2");
+    const int TM = BM * mt;
+    p.njobs = d.njobs; p.B = d.B; p.Cin = d.Cin; p.Cout = d.Cout; p.L = d.L; p.Lp = packed_rows(d.L);
+    p.nch = d.Cin / 8;
+    p.nch_out = (gated ? d.Cout / 2 : d.Cout) / 8;
+    p.rows_max = TM + 2 * maxpad;
+    p.n_lt = rvc::cdiv(d.L, TM);
+    p.n_nt = d.Cout / NT;
+    p.tiles_per_job = d.B * p.n_lt * p.n_nt;
+    p.total_tiles = p.tiles_per_job * d.njobs;
+    p.fp16 = d.dtype == RVC_DT_FP16;
+    const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 256;
+    const size_t limit = 227 * 1024;
+    // activation stage: as many channel chunks as fit twice (double buffer); even count
+    int ach = p.nch;
+    while (2 * (size_t)ach * p.rows_max * 16 + fixed > limit && ach > 2) ach = ((ach + 1) / 2 + 1) & ~1;
+    if (2 * (size_t)ach * p.rows_max * 16 + fixed > limit) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: activation stage does not fit shared memory");
+    p.ach = ach;
+    p.ncs = rvc::cdiv(p.nch, ach);
+    const size_t smem = 2 * (size_t)ach * p.rows_max * 16 + fixed;
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     cudaStream_t st = (cudaStream_t)stream;
-    if (tf32) {
-        if (NT == 128) return launch_tc<true, 128>(p, smem, grid, st);
-        if (NT == 64) return launch_tc<true, 64>(p, smem, grid, st);
-        return launch_tc<true, 32>(p, smem, grid, st);
-    }
-    if (NT == 128) return launch_tc<false, 128>(p, smem, grid, st);
-    if (NT == 64) return launch_tc<false, 64>(p, smem, grid, st);
-    return launch_tc<false, 32>(p, smem, grid, st);
+    if (NT == 128) return launch_tc_mt<128>(mt, p, smem, grid, st);
+    if (NT == 64) return launch_tc_mt<64>(mt, p, smem, grid, st);
+    return launch_tc_mt<32>(mt, p, smem, grid, st);
 }

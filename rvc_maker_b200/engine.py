@@ -12,7 +12,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_TF32, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc
+from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc
 
 LRELU_SLOPE = 0.1
 WINDOW = 10
@@ -164,8 +164,9 @@ class Engine:
         d = m.dec
         W["pre_w"], W["pre_b"] = _pack_conv(_f(d.conv_pre.weight)), _f(d.conv_pre.bias)
         nk = len(c["rks"])
-        # ResBlock stage precision: bf16 tensor cores for C >= 128, tf32 tensor cores for C in {32, 64} (SURVEY 7 hard part 2:
-        # bf16 on the narrow stages breaks the 1e-3 bar), fp32 CUDA cores otherwise / when precision == "fp32".
+        # ResBlock stage precision: bf16 tensor cores for C >= 128, fp16 tensor cores (10-bit mantissa, as tf32, at twice the
+        # rate) for C in {32, 64} — bf16 on the narrow stages breaks the 1e-3 bar (SURVEY 7 hard part 2) — and fp32 CUDA cores
+        # otherwise / when precision == "fp32".
         self.stage_dt = []
         tc_w = {}
         for i in range(len(c["rates"])):
@@ -175,7 +176,7 @@ class Engine:
                 if ch >= 128 and ch % 128 == 0 and ch <= 256:
                     dt = DT_BF16
                 elif ch in (32, 64):
-                    dt = DT_TF32
+                    dt = DT_FP16
             self.stage_dt.append(dt)
         for i in range(len(c["rates"])):
             up = d.ups[i] if c["f0"] else d.ups_and_resblocks[i * (nk + 1)]
@@ -203,7 +204,7 @@ class Engine:
         with torch.cuda.device(self.dev):
             for k, (w, dt) in tc_w.items():
                 wd = w.to(self.dev).contiguous()
-                out = torch.empty(wd.numel() * (2 if dt == DT_BF16 else 4), dtype=torch.uint8, device=self.dev)
+                out = torch.empty(wd.numel() * 2, dtype=torch.uint8, device=self.dev)
                 _lib.check(self.lib.rvc_pack_weight(wd.data_ptr(), out.data_ptr(), wd.shape[0], wd.shape[1], wd.shape[2], dt, st), "pack_weight")
                 self.W[k] = out
             torch.cuda.synchronize(self.dev)
@@ -374,13 +375,13 @@ class Engine:
                 cur, curC, curL = (S[3], None, None), Ci, Li
             else:
                 # ---- tensor-core ResBlocks: the nk blocks advance in lock-step, one persistent launch per conv step
-                esz = 2 if dt == DT_BF16 else 4
+                esz = 2
                 rows = int(lib.rvc_packed_rows(Li))
                 pk = lambda: self._zbuf(p, B * Ci * rows * esz)          # packed activations (pad rows stay zero)
                 xa = pk()
                 ta, pa = [pk() for _ in range(nk)], [pk() for _ in range(nk)]
                 P = [S[1 + j] for j in range(nk)]                        # fp32 residual streams / block outputs
-                p.add(f"pack{i}", lib.rvc_pack_act, S[0].data_ptr(), Ci * Li, Li, xa.data_ptr(), B, Ci, Li, dt, LRELU_SLOPE,
+                p.add(f"pack{i}", lib.rvc_pack_act, S[0].data_ptr(), Ci * Li, Li, None, xa.data_ptr(), B, Ci, Li, dt, LRELU_SLOPE,
                       bytes_=B * Ci * Li * (4.0 + esz), kind="pack_act")
                 order = sorted(range(nk), key=lambda j: -rks[j])          # heavy kernels first (static round-robin tiles)
                 nsteps = len(rds[0])
@@ -389,7 +390,7 @@ class Engine:
                     last = mm == nsteps - 1
                     for half in (1, 2):
                         d = Conv1dTcDesc()
-                        d.njobs, d.B, d.C, d.L, d.dtype = nk, B, Ci, Li, dt
+                        d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype = nk, B, Ci, Ci, Li, dt
                         fl = 0.0
                         for slot, j in enumerate(order):
                             jb = d.jobs[slot]
@@ -402,17 +403,17 @@ class Engine:
                             else:           # x = conv2(lrelu(t)) + x;  store x (fp32) and lrelu(x) packed for the next pair
                                 jb.a = ta[j].data_ptr()
                                 jb.w, jb.bias = W[f"rb{i}_{j}_c2w{mm}"].data_ptr(), W[f"rb{i}_{j}_c2b{mm}"].data_ptr()
-                                jb.res = (S[0] if mm == 0 else P[j]).data_ptr()
-                                jb.y_f32 = P[j].data_ptr()
+                                jb.res, jb.res_bs, jb.res_cs = (S[0] if mm == 0 else P[j]).data_ptr(), Ci * Li, Li
+                                jb.y_f32, jb.y_bs, jb.y_cs = P[j].data_ptr(), Ci * Li, Li
                                 if not last:
                                     jb.y_act = pa[j].data_ptr()
                                 jb.K, jb.dil = kk, 1
-                            jb.act_slope, jb.out_scale, jb.beta = LRELU_SLOPE, 1.0, 0.0
+                            jb.act_slope, jb.alpha = LRELU_SLOPE, 1.0
                             fl += 2.0 * B * Ci * Ci * kk * Li
                         p.keep.append(d)
                         by = nk * B * Ci * Li * (2.0 * esz if half == 1 else (esz + 8.0 + (0 if last else esz)))
                         p.add(f"rbtc{i}_s{mm}_c{half}", lib.rvc_conv1d_tc, C.byref(d), flops=fl, bytes_=by,
-                              kind=f"conv1d_tc_{'bf16' if dt == DT_BF16 else 'tf32'}[C{Ci}]")
+                              kind=f"conv1d_tc_{'bf16' if dt == DT_BF16 else 'fp16'}[C{Ci}]")
                 if nk == 3:
                     cur, curC, curL = (P[0], P[1], P[2]), Ci, Li
                 else:

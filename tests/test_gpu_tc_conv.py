@@ -1,7 +1,7 @@
-"""Op-level parity of the tcgen05 ResBlock conv (rvc_conv1d_tc) through the C ABI.
+"""Op-level parity of the tcgen05 Conv1d (rvc_conv1d_tc) through the C ABI.
 
-Reference = fp64 torch conv1d on operands rounded exactly as the kernel rounds them (bf16 RN / tf32 RNA), so the only
-difference left is fp32 accumulation order: tolerance 2e-4 * max|ref| (K*C up to 2816 products per output).
+Reference = fp64 torch conv1d on operands rounded exactly as the kernel rounds them (bf16 / fp16, round-to-nearest), so the
+only difference left is fp32 accumulation order: tolerance 2e-4 * max|ref| (up to 2816 products per output).
 """
 import ctypes as C
 
@@ -11,91 +11,146 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+BF16, FP16 = 0, 2
+DEV = "cuda:0"
+
 
 def rnd(x, dtype):
-    if dtype == 0:
-        return x.to(torch.bfloat16).to(torch.float32)
-    i = x.contiguous().view(torch.int32)
-    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    return x.to(torch.bfloat16 if dtype == BF16 else torch.float16).to(torch.float32)
 
 
-def unpack(buf, B, C, L, dtype, rows):
-    CK = 8 if dtype == 0 else 4
-    t = buf.view(torch.bfloat16 if dtype == 0 else torch.float32).view(B, C // CK, rows, CK)
-    return t[:, :, 64:64 + L, :].permute(0, 1, 3, 2).reshape(B, C, L).float()
+def unpack(buf, B, C_, L, dtype, rows):
+    t = buf.view(torch.bfloat16 if dtype == BF16 else torch.float16).view(B, C_ // 8, rows, 8)
+    return t[:, :, 64:64 + L, :].permute(0, 1, 3, 2).reshape(B, C_, L).float()
 
 
-def run_case(dtype, Cc, K, dil, B, L, seed=0, with_res=True, njobs=1):
+def pad_rows_zero(buf, B, C_, L, dtype, rows):
+    t = buf.view(torch.bfloat16 if dtype == BF16 else torch.float16).view(B, C_ // 8, rows, 8)
+    return float(t[:, :, :64].abs().max()) == 0.0 and float(t[:, :, 64 + L:].abs().max()) == 0.0
+
+
+def gate_perm(H, nt):
+    """weight-column order for a gated conv: per N tile, nt/2 tanh rows then the matching nt/2 sigmoid rows."""
+    idx = []
+    for t in range(2 * H // nt):
+        idx += list(range(t * nt // 2, (t + 1) * nt // 2)) + list(range(H + t * nt // 2, H + (t + 1) * nt // 2))
+    return torch.tensor(idx)
+
+
+def run_case(dtype, Cin, Cout, K, dil, B, L, seed=0, njobs=1, gated=False, relu=False, use_mask=False, use_res=True, alpha=1.0,
+             slope=0.1, nt=0, mt=0, use_bias_b=False):
     from rvc_maker_b200 import _lib
 
     lib = _lib.load()
-    dev = "cuda:0"
     g = torch.Generator(device="cpu").manual_seed(seed)
     st = torch.cuda.current_stream().cuda_stream
     rows = lib.rvc_packed_rows(L)
-    CK = 8 if dtype == 0 else 4
-    esz = 2 if dtype == 0 else 4
+    esz = 2
     d = _lib.Conv1dTcDesc()
-    d.njobs, d.B, d.C, d.L, d.dtype = njobs, B, Cc, L, dtype
+    d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.nt, d.mt = njobs, B, Cin, Cout, L, dtype, nt, mt
+    Ceff = Cout // 2 if gated else Cout
     keep, checks = [], []
+    mask = (torch.rand(B, L, generator=g) > 0.2).float().to(DEV) if use_mask else None
     for j in range(njobs):
         Kj, dj = (K, dil) if j == 0 else ((3, 1) if j == 1 else (7, 3))
-        x = torch.randn(B, Cc, L, generator=g).to(dev)
-        w = (torch.randn(Cc, Cc, Kj, generator=g) / (Cc * Kj) ** 0.5).to(dev)
-        bias = torch.randn(Cc, generator=g).to(dev)
-        res = torch.randn(B, Cc, L, generator=g).to(dev) if with_res else None
-        a = torch.zeros(B * (Cc // CK) * rows * CK * esz, dtype=torch.uint8, device=dev)
-        wp = torch.zeros(Kj * Cc * Cc * esz, dtype=torch.uint8, device=dev)
-        y_act = torch.zeros_like(a)
-        y = torch.empty(B, Cc, L, device=dev)
-        acc = torch.randn(B, Cc, L, generator=g).to(dev)
-        acc0 = acc.clone()
-        _lib.check(lib.rvc_pack_act(x.data_ptr(), Cc * L, L, a.data_ptr(), B, Cc, L, dtype, 0.1, st), "pack_act")
-        _lib.check(lib.rvc_pack_weight(w.data_ptr(), wp.data_ptr(), Cc, Cc, Kj, dtype, st), "pack_weight")
+        x = torch.randn(B, Cin, L, generator=g).to(DEV)
+        w = (torch.randn(Cout, Cin, Kj, generator=g) / (Cin * Kj) ** 0.5).to(DEV)
+        bias = torch.randn(Cout, generator=g).to(DEV)
+        bias_b = torch.randn(B, Cout + 5, generator=g).to(DEV) if use_bias_b else None
+        res_full = torch.randn(B, Ceff + 3, L, generator=g).to(DEV) if use_res else None   # strided residual (channel slice)
+        a = torch.zeros(B * Cin * rows * esz, dtype=torch.uint8, device=DEV)
+        wp = torch.zeros(Kj * Cin * Cout * esz, dtype=torch.uint8, device=DEV)
+        y_act = torch.zeros(B * Ceff * rows * esz, dtype=torch.uint8, device=DEV)
+        y_full = torch.zeros(B, Ceff + 2, L, device=DEV)                                    # strided output (channel slice)
+        _lib.check(lib.rvc_pack_act(x.data_ptr(), Cin * L, L, None, a.data_ptr(), B, Cin, L, dtype, slope, st), "pack_act")
+        if gated:
+            perm = gate_perm(Cout // 2, nt).to(DEV)
+            wk, bk = w[perm].contiguous(), bias[perm].contiguous()
+            bbk = torch.cat([bias_b[:, :Cout][:, perm], bias_b[:, Cout:]], 1).contiguous() if use_bias_b else None
+        else:
+            wk, bk, bbk = w, bias, bias_b
+        _lib.check(lib.rvc_pack_weight(wk.data_ptr(), wp.data_ptr(), Cout, Cin, Kj, dtype, st), "pack_weight")
         jb = d.jobs[j]
-        jb.a, jb.w, jb.bias = a.data_ptr(), wp.data_ptr(), bias.data_ptr()
-        jb.res = res.data_ptr() if with_res else None
-        jb.y_f32, jb.y_act, jb.acc_out = y.data_ptr(), y_act.data_ptr(), acc.data_ptr()
-        jb.K, jb.dil, jb.act_slope, jb.out_scale, jb.beta = Kj, dj, 0.1, 1.0 / 3.0, 1.0
-        keep += [x, w, bias, res, a, wp, y_act, y, acc]
-        checks.append((x, w, bias, res, a, y_act, y, acc, acc0, Kj, dj))
+        jb.a, jb.w, jb.bias = a.data_ptr(), wp.data_ptr(), bk.data_ptr()
+        if use_bias_b:
+            jb.bias_b, jb.bias_b_bs = bbk.data_ptr(), Cout + 5
+        if use_mask:
+            jb.mask = mask.data_ptr()
+        if use_res:
+            jb.res, jb.res_bs, jb.res_cs = res_full.data_ptr() + 4 * L, (Ceff + 3) * L, L   # channels 1..Ceff
+        jb.y_f32, jb.y_bs, jb.y_cs = y_full.data_ptr() + 4 * L, (Ceff + 2) * L, L           # channels 1..Ceff
+        jb.y_act = y_act.data_ptr()
+        jb.K, jb.dil, jb.gated, jb.relu, jb.alpha, jb.act_slope = Kj, dj, int(gated), int(relu), alpha, slope
+        keep += [x, w, bias, bias_b, res_full, a, wp, y_act, y_full, wk, bk, bbk]
+        checks.append((x, w, bias, bias_b, res_full, a, y_act, y_full, Kj, dj))
     _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "conv1d_tc")
     torch.cuda.synchronize()
-    for x, w, bias, res, a, y_act, y, acc, acc0, Kj, dj in checks:
-        xa = rnd(F.leaky_relu(x, 0.1), dtype)
-        assert torch.equal(unpack(a, B, Cc, L, dtype, rows), xa), "pack_act mismatch"
+    for x, w, bias, bias_b, res_full, a, y_act, y_full, Kj, dj in checks:
+        xa = rnd(F.leaky_relu(x, slope), dtype)
+        assert torch.equal(unpack(a, B, Cin, L, dtype, rows), xa), "pack_act mismatch"
         ref = F.conv1d(xa.double(), rnd(w, dtype).double(), bias.double(), dilation=dj, padding=(Kj - 1) // 2 * dj)
-        if res is not None:
-            ref = ref + res.double()
-        scale = float(ref.abs().max())
+        if use_bias_b:
+            ref = ref + bias_b[:, :Cout].double().unsqueeze(-1)
+        if gated:
+            H = Cout // 2
+            ref = torch.tanh(ref[:, :H]) * torch.sigmoid(ref[:, H:])
+        if relu:
+            ref = torch.relu(ref)
+        if use_res:
+            ref = res_full[:, 1:1 + Ceff].double() + alpha * ref
+        if use_mask:
+            ref = ref * mask.double().unsqueeze(1)
+        y = y_full[:, 1:1 + Ceff]
+        scale = max(1.0, float(ref.abs().max()))
         err = float((y.double() - ref).abs().max())
-        assert err <= 2e-4 * scale, (dtype, Cc, Kj, dj, B, L, err, scale)
-        assert torch.equal(unpack(y_act, B, Cc, L, dtype, rows), rnd(F.leaky_relu(y, 0.1), dtype)), "y_act mismatch"
-        assert float((acc - (acc0 + y / 3.0)).abs().max()) <= 1e-5 * max(1.0, scale)
-        # pad rows of the packed output stay zero
-        CK = 8 if dtype == 0 else 4
-        t = y_act.view(torch.bfloat16 if dtype == 0 else torch.float32).view(B, Cc // CK, rows, CK)
-        assert float(t[:, :, :64].abs().max()) == 0.0 and float(t[:, :, 64 + L:].abs().max()) == 0.0
+        assert err <= 2e-4 * scale, (dtype, Cin, Cout, Kj, dj, B, L, err, scale)
+        assert float(y_full[:, 0].abs().max()) == 0.0 and float(y_full[:, -1].abs().max()) == 0.0, "wrote outside the channel slice"
+        assert torch.equal(unpack(y_act, B, Ceff, L, dtype, rows), rnd(F.leaky_relu(y, slope), dtype)), "y_act mismatch"
+        assert pad_rows_zero(y_act, B, Ceff, L, dtype, rows)
 
 
-@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("dtype", [BF16, FP16])
 @pytest.mark.parametrize("Cc", [32, 64, 128, 256])
 @pytest.mark.parametrize("K,dil", [(3, 1), (7, 3), (11, 5)])
-def test_tc_conv_shapes(dtype, Cc, K, dil):
-    if dtype == 1 and Cc == 256:
-        # tf32 doubles the activation tile: 256 channels do not fit shared memory -> loud shape error, no fallback
-        with pytest.raises(RuntimeError, match="does not fit shared memory"):
-            run_case(dtype, Cc, K, dil, B=2, L=1000)
-        return
-    run_case(dtype, Cc, K, dil, B=2, L=1000)
+def test_resblock_shapes(dtype, Cc, K, dil):
+    run_case(dtype, Cc, Cc, K, dil, B=2, L=1000)
 
 
-@pytest.mark.parametrize("L", [1, 255, 256, 257, 777, 5000])
-def test_tc_conv_ragged_lengths(L):
-    run_case(0, 128, 7, 1, B=1, L=L, with_res=False)
-    run_case(1, 64, 11, 5, B=3, L=L)
+@pytest.mark.parametrize("L", [1, 127, 128, 129, 255, 256, 257, 777, 5000])
+def test_ragged_lengths(L):
+    run_case(BF16, 128, 128, 7, 1, B=1, L=L, use_res=False)
+    run_case(FP16, 64, 64, 11, 5, B=3, L=L)
 
 
-def test_tc_conv_three_jobs_many_tiles():
-    run_case(0, 128, 11, 5, B=2, L=40000, njobs=3)
-    run_case(1, 32, 11, 1, B=1, L=100000, njobs=3)
+@pytest.mark.parametrize("nt,mt", [(32, 1), (32, 2), (64, 1), (64, 2), (128, 1), (128, 2)])
+def test_forced_tiles(nt, mt):
+    run_case(FP16, 128, 128, 5, 2, B=2, L=1500, nt=nt, mt=mt)
+
+
+def test_three_jobs_many_tiles():
+    run_case(BF16, 128, 128, 11, 5, B=2, L=40000, njobs=3)
+    run_case(FP16, 32, 32, 11, 1, B=1, L=100000, njobs=3)
+
+
+@pytest.mark.parametrize("Cin,Cout,K", [(192, 576, 1), (192, 768, 3), (768, 192, 3), (192, 384, 1), (96, 192, 1), (192, 96, 1), (192, 512, 7)])
+def test_encoder_flow_shapes(Cin, Cout, K):
+    """TextEncoder / flow / conv_pre shapes: Cin != Cout, streamed input-channel stages (Cin = 768), mask, relu, alpha."""
+    run_case(FP16, Cin, Cout, K, 1, B=2, L=1000, relu=(Cout == 768), use_mask=True, alpha=-1.0, slope=1.0, use_bias_b=(Cout == 512))
+
+
+@pytest.mark.parametrize("nt", [64, 128])
+def test_gated_wavenet_conv(nt):
+    """WaveNet in_layer: 192 -> 2*192, k = 5, tanh * sigmoid gate with per-batch conditioning bias (modules.py:43-45)."""
+    run_case(FP16, 192, 384, 5, 1, B=2, L=1000, gated=True, use_res=False, slope=1.0, nt=nt, use_bias_b=True)
+
+
+def test_shape_errors_are_loud():
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    d = _lib.Conv1dTcDesc()
+    d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype = 1, 1, 24, 64, 100, FP16
+    d.jobs[0].a = d.jobs[0].w = 1
+    d.jobs[0].K, d.jobs[0].dil = 3, 1
+    assert lib.rvc_conv1d_tc(C.byref(d), None) == -2
+    assert b"multiple of 16" in lib.rvc_last_error()
