@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 6
+#define RVC_ABI_VERSION 7
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -100,9 +100,10 @@ int rvc_embed_f32(const float* phone, const int64_t* pitch, const int64_t* lengt
                   const float* emb_pitch, float* x, float* mask, int32_t B, int32_t T, int32_t D, int32_t H, void* stream);
 
 /* y = LayerNorm_C(x + r) * gamma + beta over the channel axis of [B,C,T] (synthesizers.py:179-181, :346-347);
- * out_mask multiplies by mask[b,t] (the final `x * x_mask`, :348). */
+ * out_mask multiplies by mask[b,t] (the final `x * x_mask`, :348).  y_act (optional): the MASKED result in the packed
+ * bf16/fp16 layout of the tensor-core convs (see below), act_dtype = RVC_DT_BF16 / RVC_DT_FP16. */
 int rvc_layernorm_f32(const float* x, const float* r, const float* gamma, const float* beta, const float* mask, float* y,
-                      int32_t B, int32_t C, int32_t T, float eps, int32_t out_mask, void* stream);
+                      int32_t B, int32_t C, int32_t T, float eps, int32_t out_mask, void* y_act, int32_t act_dtype, void* stream);
 
 /*
  * Relative-position multi-head attention core (synthesizers.py:221-250), heads share the [2w+1, dk] tables:

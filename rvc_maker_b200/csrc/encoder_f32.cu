@@ -1,5 +1,7 @@
 // TextEncoder-side fp32 kernels: phone/pitch embedding, channel LayerNorm, relative-position attention, z_p sampling.
 #include "common.cuh"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace {
@@ -67,24 +69,36 @@ __global__ void __launch_bounds__(128) embed_f32_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm over channels of [B,C,T]; blockDim (32 t, 8 channel groups)
+// LayerNorm over channels of [B,C,T]; blockDim (32 t, 8 channel groups).  Group ty owns the 8-channel chunks
+// ty, ty+8, ... so that it can also emit the packed (16 B = 8 channels) fp16/bf16 copy the tensor-core convs read.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ln_pack2(float a, float b, int fp16) {
+    if (fp16) {
+        __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ r,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mask, float* __restrict__ y, int C, int T,
-                                                            float eps, int out_mask) {
+                                                            float eps, int out_mask, uint8_t* __restrict__ y_act, int Lp, int fp16) {
     __shared__ float red[8][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int t = blockIdx.x * 32 + tx, b = blockIdx.y;
     const bool ok = t < T;
     const int64_t base = (int64_t)b * C * T + t;
+    const int nchunk = (C + 7) / 8;
     float s = 0.f;
     if (ok)
-        for (int c = ty; c < C; c += 8) {
-            float v = x[base + (int64_t)c * T];
-            if (r) v += r[base + (int64_t)c * T];
-            s += v;
-        }
+        for (int ch = ty; ch < nchunk; ch += 8)
+            for (int c = ch * 8; c < min(C, ch * 8 + 8); ++c) {
+                float v = x[base + (int64_t)c * T];
+                if (r) v += r[base + (int64_t)c * T];
+                s += v;
+            }
     red[ty][tx] = s;
     __syncthreads();
     float mean = 0.f;
@@ -94,12 +108,13 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
     __syncthreads();
     float q = 0.f;
     if (ok)
-        for (int c = ty; c < C; c += 8) {
-            float v = x[base + (int64_t)c * T];
-            if (r) v += r[base + (int64_t)c * T];
-            v -= mean;
-            q = fmaf(v, v, q);
-        }
+        for (int ch = ty; ch < nchunk; ch += 8)
+            for (int c = ch * 8; c < min(C, ch * 8 + 8); ++c) {
+                float v = x[base + (int64_t)c * T];
+                if (r) v += r[base + (int64_t)c * T];
+                v -= mean;
+                q = fmaf(v, v, q);
+            }
     red[ty][tx] = q;
     __syncthreads();
     float var = 0.f;
@@ -108,11 +123,27 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
     var /= (float)C;
     const float rstd = rsqrtf(var + eps);
     if (!ok) return;
-    const float m = out_mask ? mask[(int64_t)b * T + t] : 1.f;
-    for (int c = ty; c < C; c += 8) {
-        float v = x[base + (int64_t)c * T];
-        if (r) v += r[base + (int64_t)c * T];
-        y[base + (int64_t)c * T] = ((v - mean) * rstd * gamma[c] + beta[c]) * m;
+    const float mk = mask ? mask[(int64_t)b * T + t] : 1.f;
+    const float m = out_mask ? mk : 1.f;
+    for (int ch = ty; ch < nchunk; ch += 8) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = ch * 8 + i;
+            o[i] = 0.f;
+            if (c < C) {
+                float v = x[base + (int64_t)c * T];
+                if (r) v += r[base + (int64_t)c * T];
+                o[i] = (v - mean) * rstd * gamma[c] + beta[c];
+                y[base + (int64_t)c * T] = o[i] * m;
+            }
+        }
+        if (y_act) {  // packed copy is always masked: it only ever feeds convs whose input the reference masks (or 1x1 convs)
+            uint4 pk;
+            pk.x = ln_pack2(o[0] * mk, o[1] * mk, fp16); pk.y = ln_pack2(o[2] * mk, o[3] * mk, fp16);
+            pk.z = ln_pack2(o[4] * mk, o[5] * mk, fp16); pk.w = ln_pack2(o[6] * mk, o[7] * mk, fp16);
+            *reinterpret_cast<uint4*>(y_act + (((size_t)b * nchunk + ch) * Lp + 64 + t) * 16) = pk;
+        }
     }
 }
 
@@ -269,12 +300,15 @@ RVC_API int rvc_embed_f32(const float* phone, const int64_t* pitch, const int64_
 }
 
 RVC_API int rvc_layernorm_f32(const float* x, const float* r, const float* gamma, const float* beta, const float* mask, float* y,
-                                 int32_t B, int32_t C, int32_t T, float eps, int32_t out_mask, void* stream) {
+                                 int32_t B, int32_t C, int32_t T, float eps, int32_t out_mask, void* y_act, int32_t act_dtype, void* stream) {
     if (!x || !gamma || !beta || !y || (out_mask && !mask)) return rvc::fail(RVC_EINVAL, "rvc_layernorm_f32: null pointer");
     if (B <= 0 || B > 65535 || C <= 0 || T < 0) return rvc::fail(RVC_ESHAPE, "rvc_layernorm_f32: bad shape");
+    if (y_act && (C % 8 || !mask || (act_dtype != RVC_DT_BF16 && act_dtype != RVC_DT_FP16)))
+        return rvc::fail(RVC_EINVAL, "rvc_layernorm_f32: packed output needs C %% 8 == 0, a mask and a bf16/fp16 dtype");
     if (T == 0) return 0;
     dim3 grid(rvc::cdiv(T, 32), B);
-    layernorm_f32_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, r, gamma, beta, mask, y, C, T, eps, out_mask);
+    layernorm_f32_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, r, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act,
+                                                                       (int)rvc_packed_rows(T), act_dtype == RVC_DT_FP16);
     return rvc::check_launch("rvc_layernorm_f32");
 }
 

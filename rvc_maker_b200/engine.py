@@ -198,6 +198,50 @@ class Engine:
         if c["f0"]:
             W["lin_w"], W["lin_b"] = _f(d.m_source.l_linear.weight).view(1), _f(d.m_source.l_linear.bias).view(1)
         W["emb_g"] = _f(m.emb_g.weight)
+        # ---- TextEncoder / flow / conv_pre on tensor cores (fp16 operands, fp32 accumulate) when every shape tiles
+        half = I // 2
+        dims_ok = all(v % 16 == 0 for v in (H, c["Fc"], half, I)) and all(v % 32 == 0 for v in (H, 3 * H, c["Fc"], 2 * I, half, c["U"])) \
+            and H % 64 == 0 and c["ks"] % 2 == 1
+        self.enc_tc = self.precision == "tc" and dims_ok
+        if self.enc_tc:
+            dt = DT_FP16
+            e = m.enc_p
+            for i in range(c["nl"]):
+                a = e.encoder.attn_layers[i]
+                tc_w[f"t_qkv_w{i}"] = (torch.cat([_f(a.conv_q.weight), _f(a.conv_k.weight), _f(a.conv_v.weight)], 0), dt)
+                tc_w[f"t_o_w{i}"] = (_f(a.conv_o.weight), dt)
+                f = e.encoder.ffn_layers[i]
+                tc_w[f"t_f1_w{i}"], tc_w[f"t_f2_w{i}"] = (_f(f.conv_1.weight), dt), (_f(f.conv_2.weight), dt)
+            tc_w["t_proj_w"] = (_f(e.proj.weight), dt)
+            # gated in_layers: weight columns ordered per 64-wide N tile as [32 tanh | 32 sigmoid] (see include/rvc_b200.h)
+            perm = []
+            for t in range(2 * H // 64):
+                perm += list(range(t * 32, t * 32 + 32)) + list(range(H + t * 32, H + t * 32 + 32))
+            perm = torch.tensor(perm)
+            cond_w2, cond_b2 = [], []
+            for f in range(4):
+                cp = m.flow.flows[2 * f]
+                flipped = f in (3, 1)
+                pre_w, post_w = _f(cp.pre.weight), _f(cp.post.weight)
+                if flipped:
+                    pre_w, post_w = pre_w.flip(1), post_w.flip(0)
+                tc_w[f"t_fl{f}_pre_w"], tc_w[f"t_fl{f}_post_w"] = (pre_w.contiguous(), dt), (post_w.contiguous(), dt)
+                cw, cb = _fold_wn(cp.enc.cond_layer), _f(cp.enc.cond_layer.bias)
+                for l in range(3):
+                    tc_w[f"t_fl{f}_in_w{l}"] = (_fold_wn(cp.enc.in_layers[l])[perm].contiguous(), dt)
+                    W[f"t_fl{f}_in_b{l}"] = _f(cp.enc.in_layers[l].bias)[perm].contiguous()
+                    rs_w = _fold_wn(cp.enc.res_skip_layers[l])
+                    if l < 2:
+                        tc_w[f"t_fl{f}_res_w{l}"], tc_w[f"t_fl{f}_skip_w{l}"] = (rs_w[:H].contiguous(), dt), (rs_w[H:].contiguous(), dt)
+                    else:
+                        tc_w[f"t_fl{f}_skip_w{l}"] = (rs_w.contiguous(), dt)
+                    cond_w2.append(cw[l * 2 * H:(l + 1) * 2 * H][perm])
+                    cond_b2.append(cb[l * 2 * H:(l + 1) * 2 * H][perm])
+            cond_w2.append(_f(m.dec.cond.weight))
+            cond_b2.append(_f(m.dec.cond.bias))
+            W["cond_w"] = _pack_conv(torch.cat(cond_w2, 0))      # same layout as before, gate-permuted rows
+            W["cond_b"] = torch.cat(cond_b2, 0).contiguous()
+            tc_w["t_pre_w"] = (_f(m.dec.conv_pre.weight), dt)
         self.W = {k: (v.to(self.dev) if v is not None else None) for k, v in W.items()}
         # tensor-core weights: [Cout][Cin][K] fp32 -> packed [K][Cin/CK][Cout][CK] in bf16 / tf32 (device-side pack kernel)
         st = torch.cuda.current_stream(self.dev).cuda_stream
@@ -233,6 +277,39 @@ class Engine:
         bytes_ = 4.0 * (B * Cin * L + B * Cout * L * (1 + (res is not None) + (beta != 0.0)) + Cin * K * Cout * g2)
         plan.add(name, self.lib.rvc_conv1d_f32, C.byref(d), flops=flops, bytes_=bytes_, kind=f"conv1d_f32[C{Cout}k{K}]")
 
+    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag=""):
+        """One persistent tcgen05 launch over up to three jobs (dicts of rvc_tc_job fields; V views for res / y)."""
+        d = Conv1dTcDesc()
+        d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.nt, d.mt = len(jobs), B, Cin, Cout, L, dtype, nt, mt
+        fl = by = 0.0
+        for slot, j in enumerate(jobs):
+            jb = d.jobs[slot]
+            jb.a, jb.w = j["a"].data_ptr(), j["w"].data_ptr()
+            jb.bias = j["bias"].data_ptr() if j.get("bias") is not None else None
+            if j.get("bias_b") is not None:
+                jb.bias_b, jb.bias_b_bs = j["bias_b"], j["bias_b_bs"]
+            if j.get("mask") is not None:
+                jb.mask = j["mask"].data_ptr()
+            if j.get("res") is not None:
+                jb.res, jb.res_bs, jb.res_cs = j["res"].ptr, j["res"].bs, j["res"].cs
+            if j.get("y") is not None:
+                jb.y_f32, jb.y_bs, jb.y_cs = j["y"].ptr, j["y"].bs, j["y"].cs
+            if j.get("y_act") is not None:
+                jb.y_act = j["y_act"].data_ptr()
+            jb.K, jb.dil = j.get("K", 1), j.get("dil", 1)
+            jb.gated, jb.relu = int(j.get("gated", False)), int(j.get("relu", False))
+            jb.alpha, jb.act_slope = j.get("alpha", 1.0), j.get("act_slope", 1.0)
+            ce = Cout // 2 if jb.gated else Cout
+            fl += 2.0 * B * Cin * Cout * jb.K * L
+            by += B * L * (2.0 * Cin + ce * (4.0 * (j.get("res") is not None) + 4.0 * (j.get("y") is not None) + 2.0 * (j.get("y_act") is not None)))
+        plan.keep.append(d)
+        plan.keep.append(jobs)
+        plan.add(name, self.lib.rvc_conv1d_tc, C.byref(d), flops=fl, bytes_=by,
+                 kind=f"conv1d_tc_{'bf16' if dtype == DT_BF16 else 'fp16'}[{tag or 'C%d' % Cout}]")
+
+    def _packed(self, plan, B, Cch, L):
+        return self._zbuf(plan, B * Cch * int(self.lib.rvc_packed_rows(L)) * 2)
+
     def _zbuf(self, plan, nbytes):
         t = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
         plan.keep.append(t)
@@ -262,19 +339,42 @@ class Engine:
               W["emb_wT"].data_ptr(), W["emb_b"].data_ptr(), W["emb_pitch"].data_ptr() if c["f0"] else None, x.data_ptr(),
               p.mask.data_ptr(), B, T, D, H, flops=2.0 * B * T * D * H, bytes_=4.0 * B * T * (D + H), kind="embed_f32")
         padl = (ks - 1) // 2
+        if self.enc_tc:
+            dt = DT_FP16
+            xa, atta, ha = self._packed(p, B, H, T), self._packed(p, B, H, T), self._packed(p, B, Fc, T)
+            p.add("pack_x", lib.rvc_pack_act, x.data_ptr(), H * T, T, None, xa.data_ptr(), B, H, T, dt, 1.0, kind="pack_act", bytes_=6.0 * B * H * T)
+            for i in range(c["nl"]):
+                self._tc(p, f"qkv{i}", [dict(a=xa, w=W[f"t_qkv_w{i}"], bias=W[f"qkv_b{i}"], y=vqkv)], B=B, Cin=H, Cout=3 * H, L=T, dtype=dt, tag="enc")
+                p.add(f"attn{i}", lib.rvc_rel_attention_f32, qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(), W[f"ev{i}"].data_ptr(),
+                      att.data_ptr(), B, H, c["nh"], T, WINDOW, flops=4.0 * B * H * T * T, bytes_=16.0 * B * H * T, kind="rel_attention_f32")
+                p.add(f"pack_att{i}", lib.rvc_pack_act, att.data_ptr(), H * T, T, None, atta.data_ptr(), B, H, T, dt, 1.0, kind="pack_act",
+                      bytes_=6.0 * B * H * T)
+                self._tc(p, f"attn_o{i}", [dict(a=atta, w=W[f"t_o_w{i}"], bias=W[f"o_b{i}"], y=vy)], B=B, Cin=H, Cout=H, L=T, dtype=dt, tag="enc")
+                p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
+                      p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0, xa.data_ptr(), dt, kind="layernorm_f32", bytes_=14.0 * B * H * T)
+                self._tc(p, f"ffn1_{i}", [dict(a=xa, w=W[f"t_f1_w{i}"], bias=W[f"f1_b{i}"], relu=True, mask=p.mask, y_act=ha, K=ks)],
+                         B=B, Cin=H, Cout=Fc, L=T, dtype=dt, tag="enc")
+                self._tc(p, f"ffn2_{i}", [dict(a=ha, w=W[f"t_f2_w{i}"], bias=W[f"f2_b{i}"], mask=p.mask, y=vy, K=ks)],
+                         B=B, Cin=Fc, Cout=H, L=T, dtype=dt, tag="enc")
+                p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln2_g{i}"].data_ptr(), W[f"ln2_b{i}"].data_ptr(),
+                      p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 1 if i == c["nl"] - 1 else 0, xa.data_ptr(), dt, kind="layernorm_f32",
+                      bytes_=14.0 * B * H * T)
+            self._tc(p, "proj", [dict(a=xa, w=W["t_proj_w"], bias=W["proj_b"], mask=p.mask, y=vst)], B=B, Cin=H, Cout=2 * I, L=T, dtype=dt, tag="enc")
+            p.add("sample_zp", lib.rvc_sample_zp_f32, p.stats.data_ptr(), p.eps_z.data_ptr(), p.mask.data_ptr(), p.zp.data_ptr(), B, I, T)
+            return p
         for i in range(c["nl"]):
             self._conv(p, f"qkv{i}", vx, W[f"qkv_w{i}"], vqkv, B=B, Cin=H, Cout=3 * H, L=T, bias=W[f"qkv_b{i}"])
             p.add(f"attn{i}", lib.rvc_rel_attention_f32, qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(), W[f"ev{i}"].data_ptr(),
                   att.data_ptr(), B, H, c["nh"], T, WINDOW, flops=4.0 * B * H * T * T, bytes_=16.0 * B * H * T, kind="rel_attention_f32")
             self._conv(p, f"attn_o{i}", vatt, W[f"o_w{i}"], vy, B=B, Cin=H, Cout=H, L=T, bias=W[f"o_b{i}"])
             p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
-                  p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0)
+                  p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0, None, 0)
             self._conv(p, f"ffn1_{i}", vx, W[f"f1_w{i}"], vh, B=B, Cin=H, Cout=Fc, L=T, K=ks, pad=padl, bias=W[f"f1_b{i}"], mask=p.mask,
                        in_mask=True, act=ACT_RELU)
             self._conv(p, f"ffn2_{i}", vh, W[f"f2_w{i}"], vy, B=B, Cin=Fc, Cout=H, L=T, K=ks, pad=padl, bias=W[f"f2_b{i}"], mask=p.mask,
                        in_mask=True, out_mask=True)
             p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln2_g{i}"].data_ptr(), W[f"ln2_b{i}"].data_ptr(),
-                  p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 1 if i == c["nl"] - 1 else 0)
+                  p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 1 if i == c["nl"] - 1 else 0, None, 0)
         self._conv(p, "proj", vx, W["proj_w"], vst, B=B, Cin=H, Cout=2 * I, L=T, bias=W["proj_b"], mask=p.mask, out_mask=True)
         p.add("sample_zp", lib.rvc_sample_zp_f32, p.stats.data_ptr(), p.eps_z.data_ptr(), p.mask.data_ptr(), p.zp.data_ptr(), B, I, T)
         return p
@@ -295,7 +395,31 @@ class Engine:
         # speaker conditioning: cond_layer(g) x4 + dec.cond(g) in one launch (modules.py:39, synthesizers.py:147)
         self._conv(p, "cond", V(p.g, G, 1), W["cond_w"], V(gc, self.cond_total, 1), B=B, Cin=G, Cout=self.cond_total, L=1, bias=W["cond_b"])
         p.add_py(lambda: p.z.copy_(p.zp))
-        for f in (3, 2, 1, 0):
+        for f in ((3, 2, 1, 0) if self.enc_tc else ()):
+            dt = DT_FP16
+            if f == 3:
+                x0a, hpa, acta, oa = self._packed(p, B, half, T), self._packed(p, B, H, T), self._packed(p, B, H, T), self._packed(p, B, H, T)
+                # x0 of the first coupling = (flipped) second half of z_p, not masked (residuals.py:128,137)
+                p.add("pack_x0", lib.rvc_pack_act, p.z.data_ptr() + half * T * 4, I * T, T, None, x0a.data_ptr(), B, half, T, dt, 1.0,
+                      kind="pack_act", bytes_=6.0 * B * half * T)
+            flipped = f in (3, 1)
+            dst = V(p.z, I, T, 0 if flipped else half)
+            self._tc(p, f"fl{f}_pre", [dict(a=x0a, w=W[f"t_fl{f}_pre_w"], bias=W[f"fl{f}_pre_b"], mask=p.mask, y=vh, y_act=hpa)],
+                     B=B, Cin=half, Cout=H, L=T, dtype=dt, tag="flow")
+            for l in range(3):
+                self._tc(p, f"fl{f}_in{l}", [dict(a=hpa, w=W[f"t_fl{f}_in_w{l}"], bias=W[f"t_fl{f}_in_b{l}"], K=5, gated=True, y_act=acta,
+                                                  bias_b=gc.data_ptr() + (self.cond_off[f] + l * 2 * H) * 4, bias_b_bs=self.cond_total)],
+                         B=B, Cin=H, Cout=2 * H, L=T, dtype=dt, nt=64, tag="flow")
+                if l < 2:
+                    jobs = [dict(a=acta, w=W[f"t_fl{f}_res_w{l}"], bias=W[f"fl{f}_res_b{l}"], res=vh, mask=p.mask, y=vh, y_act=hpa),
+                            dict(a=acta, w=W[f"t_fl{f}_skip_w{l}"], bias=W[f"fl{f}_skip_b{l}"], res=(vo if l > 0 else None), y=vo)]
+                else:  # last layer: all channels are skip; output*mask feeds `post` directly in packed form (modules.py:49-51)
+                    jobs = [dict(a=acta, w=W[f"t_fl{f}_skip_w{l}"], bias=W[f"fl{f}_skip_b{l}"], res=vo, mask=p.mask, y_act=oa)]
+                self._tc(p, f"fl{f}_rs{l}", jobs, B=B, Cin=H, Cout=H, L=T, dtype=dt, tag="flow")
+            # x1 <- (x1 - post(...)*mask)*mask; its packed copy is the next coupling's x0
+            self._tc(p, f"fl{f}_post", [dict(a=oa, w=W[f"t_fl{f}_post_w"], bias=W[f"fl{f}_post_b"], res=dst, alpha=-1.0, mask=p.mask, y=dst,
+                                             y_act=(x0a if f > 0 else None))], B=B, Cin=H, Cout=half, L=T, dtype=dt, tag="flow")
+        for f in (() if self.enc_tc else (3, 2, 1, 0)):
             flipped = f in (3, 1)
             src = V(p.z, I, T, half if flipped else 0)
             dst = V(p.z, I, T, 0 if flipped else half)
@@ -321,8 +445,16 @@ class Engine:
             p.add("sine_source", lib.rvc_sine_source_f32, p.f0.data_ptr(), p.eps_src.data_ptr(), W["lin_w"].data_ptr(), W["lin_b"].data_ptr(),
                   scratch.data_ptr(), har.data_ptr(), B, T, upp, c["sr"], launches=2, bytes_=8.0 * B * Lfin, kind="sine_source_f32")
         xpre = self._buf(p, B, U, T)
-        self._conv(p, "conv_pre", V(p.z, I, T), W["pre_w"], V(xpre, U, T), B=B, Cin=I, Cout=U, L=T, K=7, pad=3, bias=W["pre_b"],
-                   bias_b=gc.data_ptr() + self.cond_off[4] * 4, bias_b_bs=self.cond_total, mask=p.mask, in_mask=True)
+        if self.enc_tc:
+            za = self._packed(p, B, I, T)
+            p.add("pack_z", lib.rvc_pack_act, p.z.data_ptr(), I * T, T, p.mask.data_ptr(), za.data_ptr(), B, I, T, DT_FP16, 1.0, kind="pack_act",
+                  bytes_=6.0 * B * I * T)
+            self._tc(p, "conv_pre", [dict(a=za, w=W["t_pre_w"], bias=W["pre_b"], K=7, y=V(xpre, U, T),
+                                          bias_b=gc.data_ptr() + self.cond_off[4] * 4, bias_b_bs=self.cond_total)],
+                     B=B, Cin=I, Cout=U, L=T, dtype=DT_FP16, tag="conv_pre")
+        else:
+            self._conv(p, "conv_pre", V(p.z, I, T), W["pre_w"], V(xpre, U, T), B=B, Cin=I, Cout=U, L=T, K=7, pad=3, bias=W["pre_b"],
+                       bias_b=gc.data_ptr() + self.cond_off[4] * 4, bias_b_bs=self.cond_total, mask=p.mask, in_mask=True)
         rates, uks, rks, rds = c["rates"], c["uks"], c["rks"], c["rds"]
         nk = len(rks)
         chans = [U // (2 ** (i + 1)) for i in range(len(rates))]

@@ -21,10 +21,15 @@ TC_TOL = 1e-3
 TC_SNR = 40.0
 
 
+# latent tensors (z, z_p, m_p, logs_p) on the tensor-core path: fp16 operands (10-bit mantissa) through 6 encoder layers and
+# 4 couplings; bar = 5e-3 * max|ref| and SNR >= 50 dB (measured: see profiles/ parity table)
+TC_LATENT_TOL = 5e-3
+TC_LATENT_SNR = 50.0
+
+
 def tol_for(precision, key):
-    """The tensor-core path only touches the decoder: z, z_p, m_p, logs_p keep the fp32 bar."""
-    if precision == "tc" and key == "o":
-        return TC_TOL, TC_SNR
+    if precision == "tc":
+        return (TC_TOL, TC_SNR) if key == "o" else (TC_LATENT_TOL, TC_LATENT_SNR)
     return FP32_TOL, FP32_SNR
 
 
@@ -96,9 +101,10 @@ def test_cuda_matches_oracle_midsize(cname, use_f0, B, T, ragged, precision):
     ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
                                                       eps_z=inp["eps_z"], eps_src=inp["eps_src"], use_f0=use_f0)
     ref = dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl)
+    for k in ("o", "z", "m_p", "logs_p"):
+        m = cases.metrics(out[k].float().cpu(), ref[k])
+        print(f"[{cname} {precision}] {k}: max_abs={m['max_abs']:.3e} (max|ref|={float(ref[k].abs().max()):.2f}) snr={m['snr_db']:.1f} dB")
     assert_close(out, ref, precision, tag=cname)
-    m = cases.metrics(out["o"].float().cpu(), ro)
-    print(f"\n[{cname} {precision}] o: max_abs={m['max_abs']:.3e} snr={m['snr_db']:.1f} dB ac_snr={m['snr_ac_db']:.1f} dB")
 
 
 def test_half_module_protocol():
