@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 7
+#define RVC_ABI_VERSION 8
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -139,9 +139,10 @@ int rvc_sine_source_f32(const float* f0, const float* noise, const float* lin_w,
 #define RVC_DT_BF16 0
 #define RVC_DT_FP16 2
 int64_t rvc_packed_rows(int32_t L);
-/* y_packed = DT(leaky_relu(x, slope) * mask) for fp32 x[B,C,L] with element strides (slope = 1 -> identity, mask may be NULL) */
-int rvc_pack_act(const float* x, int64_t x_bs, int64_t x_cs, const float* mask, void* y, int32_t B, int32_t C, int32_t L,
-                 int32_t dtype, float slope, void* stream);
+/* y_packed = DT(leaky_relu(in, slope) * mask) for fp32 x[B,C,L] with element strides (slope = 1 -> identity, mask may be NULL);
+ * in = x, or (x + x2 + x3) / in_div when x2/x3 are given (the `xs / num_kernels` of a generator stage). */
+int rvc_pack_act(const float* x, const float* x2, const float* x3, float in_div, int64_t x_bs, int64_t x_cs, const float* mask, void* y,
+                 int32_t B, int32_t C, int32_t L, int32_t dtype, float slope, void* stream);
 /* folded fp32 [Cout][Cin][K] -> packed [K][Cin/8][Cout][8] */
 int rvc_pack_weight(const float* w, void* y, int32_t Cout, int32_t Cin, int32_t K, int32_t dtype, void* stream);
 
@@ -163,12 +164,18 @@ typedef struct {
     const float* res; int64_t res_bs, res_cs;
     float* y_f32; int64_t y_bs, y_cs;
     void* y_act;
-    int32_t K, dil, gated, relu;
+    int32_t K, dil, pad, gated, relu;   /* pad = zero rows left of position 0 seen by tap 0 ("same": (K-1)/2*dil) */
     float alpha, act_slope;
 } rvc_tc_job;
+/*
+ * up > 1 selects the ConvTranspose1d phase mode (GeneratorNSF.ups, synthesizers.py:133,156): the packed weights hold `up`
+ * phase blocks [up][K][Cin/8][Cout][8] with K = ceil(k/up) taps, block r tap t = w_T[:, :, r + (K-1-t)*up] (zero past k), every
+ * job uses pad = K-1, and the result of input position q, phase r lands at output position q*up + r - pshift
+ * (pshift = (k-up)/2); res / mask / y_f32 / y_act are indexed at OUTPUT positions (length L*up).
+ */
 typedef struct {
     rvc_tc_job jobs[3];
-    int32_t njobs, B, Cin, Cout, L, dtype, nt, mt;
+    int32_t njobs, B, Cin, Cout, L, dtype, nt, mt, up, pshift;
 } rvc_conv1d_tc_desc;
 int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);
 

@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 DT_BF16, DT_FP16 = 0, 2
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -56,14 +56,14 @@ class TcJob(C.Structure):
         ("res", _vp), ("res_bs", _i64), ("res_cs", _i64),
         ("y_f32", _vp), ("y_bs", _i64), ("y_cs", _i64),
         ("y_act", _vp),
-        ("K", _i32), ("dil", _i32), ("gated", _i32), ("relu", _i32),
+        ("K", _i32), ("dil", _i32), ("pad", _i32), ("gated", _i32), ("relu", _i32),
         ("alpha", _f32), ("act_slope", _f32),
     ]
 
 
 class Conv1dTcDesc(C.Structure):
     _fields_ = [("jobs", TcJob * 3), ("njobs", _i32), ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("L", _i32), ("dtype", _i32),
-                ("nt", _i32), ("mt", _i32)]
+                ("nt", _i32), ("mt", _i32), ("up", _i32), ("pshift", _i32)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
@@ -80,7 +80,7 @@ SIGNATURES = {
     "rvc_sample_zp_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rvc_sine_source_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "rvc_packed_rows": (_i64, [_i32]),
-    "rvc_pack_act": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "rvc_pack_act": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_conv1d_tc": (C.c_int, [C.POINTER(Conv1dTcDesc), _vp]),
 }

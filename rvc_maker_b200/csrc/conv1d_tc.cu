@@ -43,6 +43,8 @@ struct Params {
     int n_lt, n_nt;   // tiles along L and along Cout
     int tiles_per_job, total_tiles;
     int fp16;         // operand format: 0 = bf16, 1 = fp16
+    int up, pshift;   // transposed-conv phase mode: output position = l * up + phase - pshift (up = 1: plain conv)
+    int Lout, Lp_out; // output length and packed rows of the output
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
@@ -93,9 +95,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    auto decode = [&](int tile, int& j, int& b, int& lt, int& nt) {
+    // tile id -> (job, batch, L tile, N tile, phase); phase is the fastest index so that the u phases of one input tile run on
+    // neighbouring CTAs at the same time and share the activation tile through L2
+    auto decode = [&](int tile, int& j, int& b, int& lt, int& nt, int& ph) {
         j = tile / p.tiles_per_job;
         int r = tile - j * p.tiles_per_job;
+        ph = r % p.up; r /= p.up;
         nt = r % p.n_nt; r /= p.n_nt;
         lt = r % p.n_lt;
         b = r / p.n_lt;
@@ -105,11 +110,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         // ======================= activation producer =======================
         uint32_t ast = 0, aph = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            int j, b, lt, nt;
-            decode(tile, j, b, lt, nt);
+            int j, b, lt, nt, ph;
+            decode(tile, j, b, lt, nt, ph);
             const rvc_tc_job& jb = p.jobs[j];
-            const int pad = (jb.K - 1) / 2 * jb.dil;
-            const int rows = TM + 2 * pad;
+            const int pad = jb.pad;
+            const int rows = TM + (jb.K - 1) * jb.dil;
             for (int cs = 0; cs < p.ncs; ++cs) {
                 const int c0 = cs * p.ach;
                 const int nc = min(p.ach, p.nch - c0);
@@ -130,10 +135,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         // ======================= weight producer =======================
         uint32_t wst = 0, wph = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            int j, b, lt, nt;
-            decode(tile, j, b, lt, nt);
+            int j, b, lt, nt, ph;
+            decode(tile, j, b, lt, nt, ph);
             const rvc_tc_job& jb = p.jobs[j];
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(jb.w);
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(jb.w) + (size_t)ph * jb.K * p.nch * p.Cout * 16;
             for (int cs = 0; cs < p.ncs; ++cs) {
                 const int ca = cs * p.ach;
                 const int na = min(p.ach, p.nch - ca);
@@ -165,8 +170,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             int it = 0;
             const uint32_t lbo_a = (uint32_t)p.rows_max * 16, lbo_b = NT * 16;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                int j, b, lt, nt;
-                decode(tile, j, b, lt, nt);
+                int j, b, lt, nt, ph;
+                decode(tile, j, b, lt, nt, ph);
                 const rvc_tc_job& jb = p.jobs[j];
                 const int g = it & 1;
                 const uint32_t gph = (it >> 1) & 1;
@@ -208,8 +213,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         const int q = warp & 3;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            int j, b, lt, nt;
-            decode(tile, j, b, lt, nt);
+            int j, b, lt, nt, ph;
+            decode(tile, j, b, lt, nt, ph);
             const rvc_tc_job& jb = p.jobs[j];
             const int g = it & 1;
             const uint32_t gph = (it >> 1) & 1;
@@ -218,9 +223,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             tc::fence_after_sync();
 #pragma unroll 1
             for (int m = 0; m < MT; ++m) {
-                const int l = lt * TM + m * BM + q * 32 + lane;
-                const bool ok = l < p.L;
-                const float mk = (jb.mask && ok) ? jb.mask[(size_t)b * p.L + l] : 1.f;
+                const int lin = lt * TM + m * BM + q * 32 + lane;
+                const int l = lin * p.up + ph - p.pshift;          // output position
+                const bool ok = lin < p.L && l >= 0 && l < p.Lout;
+                const float mk = (jb.mask && ok) ? jb.mask[(size_t)b * p.Lout + l] : 1.f;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * MT + m) * NT);
                 constexpr int NBLK = NT / 32;
                 const int nblk = jb.gated ? NBLK / 2 : NBLK;
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                         for (int i = 0; i < 32; ++i) yp[(size_t)i * jb.y_cs] = v[i];
                     }
                     if (jb.y_act) {
-                        uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (((size_t)b * p.nch_out + co0 / 8) * p.Lp + PADL + l) * 16;
+                        uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (((size_t)b * p.nch_out + co0 / 8) * p.Lp_out + PADL + l) * 16;
                         const float sl = jb.act_slope;
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                             pk.y = pack2(rvc::lrelu(v[8 * u + 2], sl), rvc::lrelu(v[8 * u + 3], sl), p.fp16);
                             pk.z = pack2(rvc::lrelu(v[8 * u + 4], sl), rvc::lrelu(v[8 * u + 5], sl), p.fp16);
                             pk.w = pack2(rvc::lrelu(v[8 * u + 6], sl), rvc::lrelu(v[8 * u + 7], sl), p.fp16);
-                            *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp * 16) = pk;
+                            *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp_out * 16) = pk;
                         }
                     }
                 }
@@ -303,16 +309,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
 
 // ------------------------------------------------------------------------------------------------ packing kernels
 // fp32 [B, C, L] (strided) -> packed [B][C/8][Lp][8]; value = lrelu(x, slope) * mask
-__global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_cs, const float* __restrict__ mask,
+__global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, const float* __restrict__ x2, const float* __restrict__ x3,
+                                                       float in_div, int64_t x_bs, int64_t x_cs, const float* __restrict__ mask,
                                                        uint8_t* __restrict__ y, int nch, int L, int Lp, float slope, int fp16) {
     const int l = blockIdx.x * 256 + threadIdx.x;
     const int c = blockIdx.y, b = blockIdx.z;
     if (l >= L) return;
-    const float* xp = x + (int64_t)b * x_bs + (int64_t)c * 8 * x_cs + l;
+    const int64_t off = (int64_t)b * x_bs + (int64_t)c * 8 * x_cs + l;
     const float mk = mask ? mask[(int64_t)b * L + l] : 1.f;
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = rvc::lrelu(xp[(int64_t)i * x_cs], slope) * mk;
+    for (int i = 0; i < 8; ++i) {
+        float t = x[off + (int64_t)i * x_cs];
+        if (x2) t = ((t + x2[off + (int64_t)i * x_cs]) + x3[off + (int64_t)i * x_cs]) / in_div;
+        v[i] = rvc::lrelu(t, slope) * mk;
+    }
     uint4 pk;
     pk.x = pack2(v[0], v[1], fp16); pk.y = pack2(v[2], v[3], fp16);
     pk.z = pack2(v[4], v[5], fp16); pk.w = pack2(v[6], v[7], fp16);
@@ -355,14 +366,16 @@ int launch_tc_mt(int mt, const Params& p, size_t smem, int grid, cudaStream_t st
 
 RVC_API int64_t rvc_packed_rows(int32_t L) { return packed_rows(L); }
 
-RVC_API int rvc_pack_act(const float* x, int64_t x_bs, int64_t x_cs, const float* mask, void* y, int32_t B, int32_t C, int32_t L,
-                         int32_t dtype, float slope, void* stream) {
+RVC_API int rvc_pack_act(const float* x, const float* x2, const float* x3, float in_div, int64_t x_bs, int64_t x_cs, const float* mask, void* y,
+                         int32_t B, int32_t C, int32_t L, int32_t dtype, float slope, void* stream) {
     if (!x || !y) return rvc::fail(RVC_EINVAL, "rvc_pack_act: null pointer");
+    if ((x2 == nullptr) != (x3 == nullptr)) return rvc::fail(RVC_EINVAL, "rvc_pack_act: x2 and x3 go together");
     if (dtype != RVC_DT_BF16 && dtype != RVC_DT_FP16) return rvc::fail(RVC_EINVAL, "rvc_pack_act: dtype must be RVC_DT_BF16 or RVC_DT_FP16");
     if (B <= 0 || B > 65535 || C <= 0 || C % 8 || L < 0) return rvc::fail(RVC_ESHAPE, "rvc_pack_act: bad shape (C=%d must be a multiple of 8)", C);
     if (L == 0) return 0;
     dim3 grid(rvc::cdiv(L, 256), C / 8, B);
-    pack_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_cs, mask, (uint8_t*)y, C / 8, L, packed_rows(L), slope, dtype == RVC_DT_FP16);
+    pack_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x2, x3, in_div, x_bs, x_cs, mask, (uint8_t*)y, C / 8, L, packed_rows(L), slope,
+                                                            dtype == RVC_DT_FP16);
     return rvc::check_launch("rvc_pack_act");
 }
 
@@ -388,12 +401,14 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     for (int j = 0; j < d.njobs; ++j) {
         const rvc_tc_job& jb = d.jobs[j];
         if (!jb.a || !jb.w) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: job %d has null a/w", j);
-        if (jb.K <= 0 || !(jb.K & 1) || jb.dil <= 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: job %d needs odd K, dil > 0", j);
+        if (jb.K <= 0 || jb.dil <= 0 || jb.pad < 0 || jb.pad > (jb.K - 1) * jb.dil)
+            return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: job %d needs K > 0, dil > 0, 0 <= pad <= (K-1)*dil", j);
         if ((jb.gated ? 1 : 0) != gated) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: jobs of one launch must agree on `gated`");
         if (jb.gated && !jb.bias) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: gated job needs a bias");
-        const int pad = (jb.K - 1) / 2 * jb.dil;
-        if (pad > PADL) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: halo %d exceeds the %d zero rows of the packed layout", pad, PADL);
-        maxpad = pad > maxpad ? pad : maxpad;
+        const int halo = (jb.K - 1) * jb.dil;
+        if (jb.pad > PADL || halo - jb.pad > PADR)
+            return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: halo %d/%d exceeds the %d zero rows of the packed layout", jb.pad, halo - jb.pad, PADL);
+        maxpad = halo > maxpad ? halo : maxpad;
         p.jobs[j] = jb;
     }
     int dev = 0, sms = 148;
@@ -401,7 +416,12 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // tile shape: the widest N tile (and 2 sub-tiles) that still yields >= one wave of CTAs; gated needs NT % 64 == 0
     int mt = d.mt, NT = d.nt;
-    auto ntiles = [&](int nt_, int mt_) { return (long)d.njobs * d.B * rvc::cdiv(d.L, BM * mt_) * (d.Cout / nt_); };
+    const int up = d.up > 0 ? d.up : 1;
+    if (up > 1 && (d.pshift < 0 || d.pshift >= up + PADR)) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: bad pshift");
+    // transposed mode: input positions q in [0, L + ceil(pshift/up)) reach valid outputs (rows past L are zero in the packed buffer)
+    const int Lq = up > 1 ? d.L + rvc::cdiv(d.pshift, up) : d.L;
+    const int Lout = up > 1 ? d.L * up : d.L;
+    auto ntiles = [&](int nt_, int mt_) { return (long)d.njobs * d.B * rvc::cdiv(Lq, BM * mt_) * (d.Cout / nt_) * up; };
     if (NT == 0) {
         const int cands[3] = {128, 64, 32};
         for (int i = 0; i < 3; ++i) {
@@ -417,13 +437,14 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     if (mt == 0) mt = ntiles(NT, 2) >= 2L * sms ? 2 : 1;
     if (mt != 1 && mt != 2) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: mt must be 1 or 2");
     const int TM = BM * mt;
-    p.njobs = d.njobs; p.B = d.B; p.Cin = d.Cin; p.Cout = d.Cout; p.L = d.L; p.Lp = packed_rows(d.L);
+    p.njobs = d.njobs; p.B = d.B; p.Cin = d.Cin; p.Cout = d.Cout; p.L = Lq; p.Lp = packed_rows(d.L);
+    p.up = up; p.pshift = up > 1 ? d.pshift : 0; p.Lout = Lout; p.Lp_out = packed_rows(Lout);
     p.nch = d.Cin / 8;
     p.nch_out = (gated ? d.Cout / 2 : d.Cout) / 8;
-    p.rows_max = TM + 2 * maxpad;
-    p.n_lt = rvc::cdiv(d.L, TM);
+    p.rows_max = TM + maxpad;
+    p.n_lt = rvc::cdiv(Lq, TM);
     p.n_nt = d.Cout / NT;
-    p.tiles_per_job = d.B * p.n_lt * p.n_nt;
+    p.tiles_per_job = d.B * p.n_lt * p.n_nt * up;
     p.total_tiles = p.tiles_per_job * d.njobs;
     p.fp16 = d.dtype == RVC_DT_FP16;
     const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 256;

@@ -297,6 +297,7 @@ class Engine:
             if j.get("y_act") is not None:
                 jb.y_act = j["y_act"].data_ptr()
             jb.K, jb.dil = j.get("K", 1), j.get("dil", 1)
+            jb.pad = j.get("pad", (jb.K - 1) // 2 * jb.dil)
             jb.gated, jb.relu = int(j.get("gated", False)), int(j.get("relu", False))
             jb.alpha, jb.act_slope = j.get("alpha", 1.0), j.get("act_slope", 1.0)
             ce = Cout // 2 if jb.gated else Cout
@@ -342,12 +343,12 @@ class Engine:
         if self.enc_tc:
             dt = DT_FP16
             xa, atta, ha = self._packed(p, B, H, T), self._packed(p, B, H, T), self._packed(p, B, Fc, T)
-            p.add("pack_x", lib.rvc_pack_act, x.data_ptr(), H * T, T, None, xa.data_ptr(), B, H, T, dt, 1.0, kind="pack_act", bytes_=6.0 * B * H * T)
+            p.add("pack_x", lib.rvc_pack_act, x.data_ptr(), None, None, 1.0, H * T, T, None, xa.data_ptr(), B, H, T, dt, 1.0, kind="pack_act", bytes_=6.0 * B * H * T)
             for i in range(c["nl"]):
                 self._tc(p, f"qkv{i}", [dict(a=xa, w=W[f"t_qkv_w{i}"], bias=W[f"qkv_b{i}"], y=vqkv)], B=B, Cin=H, Cout=3 * H, L=T, dtype=dt, tag="enc")
                 p.add(f"attn{i}", lib.rvc_rel_attention_f32, qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(), W[f"ev{i}"].data_ptr(),
                       att.data_ptr(), B, H, c["nh"], T, WINDOW, flops=4.0 * B * H * T * T, bytes_=16.0 * B * H * T, kind="rel_attention_f32")
-                p.add(f"pack_att{i}", lib.rvc_pack_act, att.data_ptr(), H * T, T, None, atta.data_ptr(), B, H, T, dt, 1.0, kind="pack_act",
+                p.add(f"pack_att{i}", lib.rvc_pack_act, att.data_ptr(), None, None, 1.0, H * T, T, None, atta.data_ptr(), B, H, T, dt, 1.0, kind="pack_act",
                       bytes_=6.0 * B * H * T)
                 self._tc(p, f"attn_o{i}", [dict(a=atta, w=W[f"t_o_w{i}"], bias=W[f"o_b{i}"], y=vy)], B=B, Cin=H, Cout=H, L=T, dtype=dt, tag="enc")
                 p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
@@ -400,7 +401,7 @@ class Engine:
             if f == 3:
                 x0a, hpa, acta, oa = self._packed(p, B, half, T), self._packed(p, B, H, T), self._packed(p, B, H, T), self._packed(p, B, H, T)
                 # x0 of the first coupling = (flipped) second half of z_p, not masked (residuals.py:128,137)
-                p.add("pack_x0", lib.rvc_pack_act, p.z.data_ptr() + half * T * 4, I * T, T, None, x0a.data_ptr(), B, half, T, dt, 1.0,
+                p.add("pack_x0", lib.rvc_pack_act, p.z.data_ptr() + half * T * 4, None, None, 1.0, I * T, T, None, x0a.data_ptr(), B, half, T, dt, 1.0,
                       kind="pack_act", bytes_=6.0 * B * half * T)
             flipped = f in (3, 1)
             dst = V(p.z, I, T, 0 if flipped else half)
@@ -447,7 +448,7 @@ class Engine:
         xpre = self._buf(p, B, U, T)
         if self.enc_tc:
             za = self._packed(p, B, I, T)
-            p.add("pack_z", lib.rvc_pack_act, p.z.data_ptr(), I * T, T, p.mask.data_ptr(), za.data_ptr(), B, I, T, DT_FP16, 1.0, kind="pack_act",
+            p.add("pack_z", lib.rvc_pack_act, p.z.data_ptr(), None, None, 1.0, I * T, T, p.mask.data_ptr(), za.data_ptr(), B, I, T, DT_FP16, 1.0, kind="pack_act",
                   bytes_=6.0 * B * I * T)
             self._tc(p, "conv_pre", [dict(a=za, w=W["t_pre_w"], bias=W["pre_b"], K=7, y=V(xpre, U, T),
                                           bias_b=gc.data_ptr() + self.cond_off[4] * 4, bias_b_bs=self.cond_total)],
@@ -513,7 +514,7 @@ class Engine:
                 xa = pk()
                 ta, pa = [pk() for _ in range(nk)], [pk() for _ in range(nk)]
                 P = [S[1 + j] for j in range(nk)]                        # fp32 residual streams / block outputs
-                p.add(f"pack{i}", lib.rvc_pack_act, S[0].data_ptr(), Ci * Li, Li, None, xa.data_ptr(), B, Ci, Li, dt, LRELU_SLOPE,
+                p.add(f"pack{i}", lib.rvc_pack_act, S[0].data_ptr(), None, None, 1.0, Ci * Li, Li, None, xa.data_ptr(), B, Ci, Li, dt, LRELU_SLOPE,
                       bytes_=B * Ci * Li * (4.0 + esz), kind="pack_act")
                 order = sorted(range(nk), key=lambda j: -rks[j])          # heavy kernels first (static round-robin tiles)
                 nsteps = len(rds[0])
@@ -531,7 +532,7 @@ class Engine:
                                 jb.a = (xa if mm == 0 else pa[j]).data_ptr()
                                 jb.w, jb.bias = W[f"rb{i}_{j}_c1w{mm}"].data_ptr(), W[f"rb{i}_{j}_c1b{mm}"].data_ptr()
                                 jb.y_act = ta[j].data_ptr()
-                                jb.K, jb.dil = kk, rds[j][mm]
+                                jb.K, jb.dil, jb.pad = kk, rds[j][mm], (kk - 1) // 2 * rds[j][mm]
                             else:           # x = conv2(lrelu(t)) + x;  store x (fp32) and lrelu(x) packed for the next pair
                                 jb.a = ta[j].data_ptr()
                                 jb.w, jb.bias = W[f"rb{i}_{j}_c2w{mm}"].data_ptr(), W[f"rb{i}_{j}_c2b{mm}"].data_ptr()
@@ -539,7 +540,7 @@ class Engine:
                                 jb.y_f32, jb.y_bs, jb.y_cs = P[j].data_ptr(), Ci * Li, Li
                                 if not last:
                                     jb.y_act = pa[j].data_ptr()
-                                jb.K, jb.dil = kk, 1
+                                jb.K, jb.dil, jb.pad = kk, 1, (kk - 1) // 2
                             jb.act_slope, jb.alpha = LRELU_SLOPE, 1.0
                             fl += 2.0 * B * Ci * Ci * kk * Li
                         p.keep.append(d)

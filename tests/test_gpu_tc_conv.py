@@ -62,7 +62,7 @@ def run_case(dtype, Cin, Cout, K, dil, B, L, seed=0, njobs=1, gated=False, relu=
         wp = torch.zeros(Kj * Cin * Cout * esz, dtype=torch.uint8, device=DEV)
         y_act = torch.zeros(B * Ceff * rows * esz, dtype=torch.uint8, device=DEV)
         y_full = torch.zeros(B, Ceff + 2, L, device=DEV)                                    # strided output (channel slice)
-        _lib.check(lib.rvc_pack_act(x.data_ptr(), Cin * L, L, None, a.data_ptr(), B, Cin, L, dtype, slope, st), "pack_act")
+        _lib.check(lib.rvc_pack_act(x.data_ptr(), None, None, 1.0, Cin * L, L, None, a.data_ptr(), B, Cin, L, dtype, slope, st), "pack_act")
         if gated:
             perm = gate_perm(Cout // 2, nt).to(DEV)
             wk, bk = w[perm].contiguous(), bias[perm].contiguous()
@@ -80,7 +80,7 @@ def run_case(dtype, Cin, Cout, K, dil, B, L, seed=0, njobs=1, gated=False, relu=
             jb.res, jb.res_bs, jb.res_cs = res_full.data_ptr() + 4 * L, (Ceff + 3) * L, L   # channels 1..Ceff
         jb.y_f32, jb.y_bs, jb.y_cs = y_full.data_ptr() + 4 * L, (Ceff + 2) * L, L           # channels 1..Ceff
         jb.y_act = y_act.data_ptr()
-        jb.K, jb.dil, jb.gated, jb.relu, jb.alpha, jb.act_slope = Kj, dj, int(gated), int(relu), alpha, slope
+        jb.K, jb.dil, jb.pad, jb.gated, jb.relu, jb.alpha, jb.act_slope = Kj, dj, (Kj - 1) // 2 * dj, int(gated), int(relu), alpha, slope
         keep += [x, w, bias, bias_b, res_full, a, wp, y_act, y_full, wk, bk, bbk]
         checks.append((x, w, bias, bias_b, res_full, a, y_act, y_full, Kj, dj))
     _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "conv1d_tc")
@@ -144,6 +144,55 @@ def test_gated_wavenet_conv(nt):
     run_case(FP16, 192, 384, 5, 1, B=2, L=1000, gated=True, use_res=False, slope=1.0, nt=nt, use_bias_b=True)
 
 
+@pytest.mark.parametrize("Cin,Cout,k,u,Lin,dtype", [(512, 256, 24, 12, 1000, BF16), (256, 128, 20, 10, 3000, BF16), (128, 64, 4, 2, 5001, FP16),
+                                                    (64, 32, 4, 2, 777, FP16), (512, 256, 16, 10, 300, FP16), (256, 128, 16, 4, 500, FP16)])
+def test_conv_transpose_phase_mode(Cin, Cout, k, u, Lin, dtype):
+    """ConvTranspose1d(k, stride u, pad (k-u)/2) as u phase GEMMs, with pre-lrelu input, residual (noise conv) and packed output."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    B = 2
+    g = torch.Generator(device="cpu").manual_seed(5)
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(B, Cin, Lin, generator=g).to(DEV)
+    w = (torch.randn(Cin, Cout, k, generator=g) / (Cin * k / u) ** 0.5).to(DEV)   # ConvTranspose1d weight layout
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    Lout = Lin * u
+    res = torch.randn(B, Cout, Lout, generator=g).to(DEV)
+    M = -(-k // u)
+    # phase-major conv weight [Cout][Cin][u*M]: block r, tap t = w[:, :, r + (M-1-t)*u]
+    wk = torch.zeros(Cout, Cin, u * M, device=DEV)
+    for r in range(u):
+        for t in range(M):
+            kk = r + (M - 1 - t) * u
+            if kk < k:
+                wk[:, :, r * M + t] = w[:, :, kk].t()
+    rows_in, rows_out = lib.rvc_packed_rows(Lin), lib.rvc_packed_rows(Lout)
+    a = torch.zeros(B * Cin * rows_in * 2, dtype=torch.uint8, device=DEV)
+    wp = torch.zeros(u * M * Cin * Cout * 2, dtype=torch.uint8, device=DEV)
+    y_act = torch.zeros(B * Cout * rows_out * 2, dtype=torch.uint8, device=DEV)
+    y = torch.zeros(B, Cout, Lout, device=DEV)
+    _lib.check(lib.rvc_pack_act(x.data_ptr(), None, None, 1.0, Cin * Lin, Lin, None, a.data_ptr(), B, Cin, Lin, dtype, 0.1, st), "pack_act")
+    _lib.check(lib.rvc_pack_weight(wk.data_ptr(), wp.data_ptr(), Cout, Cin, u * M, dtype, st), "pack_weight")
+    d = _lib.Conv1dTcDesc()
+    d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.up, d.pshift = 1, B, Cin, Cout, Lin, dtype, u, (k - u) // 2
+    jb = d.jobs[0]
+    jb.a, jb.w, jb.bias = a.data_ptr(), wp.data_ptr(), bias.data_ptr()
+    jb.res, jb.res_bs, jb.res_cs = res.data_ptr(), Cout * Lout, Lout
+    jb.y_f32, jb.y_bs, jb.y_cs = y.data_ptr(), Cout * Lout, Lout
+    jb.y_act = y_act.data_ptr()
+    jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = M, 1, M - 1, 1.0, 0.1
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "conv1d_tc(up)")
+    torch.cuda.synchronize()
+    xa = rnd(F.leaky_relu(x, 0.1), dtype)
+    ref = F.conv_transpose1d(xa.double(), rnd(w, dtype).double(), bias.double(), stride=u, padding=(k - u) // 2) + res.double()
+    scale = max(1.0, float(ref.abs().max()))
+    err = float((y.double() - ref).abs().max())
+    assert err <= 2e-4 * scale, (err, scale)
+    assert torch.equal(unpack(y_act, B, Cout, Lout, dtype, rows_out), rnd(F.leaky_relu(y, 0.1), dtype))
+    assert pad_rows_zero(y_act, B, Cout, Lout, dtype, rows_out)
+
+
 def test_shape_errors_are_loud():
     from rvc_maker_b200 import _lib
 
@@ -151,6 +200,6 @@ def test_shape_errors_are_loud():
     d = _lib.Conv1dTcDesc()
     d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype = 1, 1, 24, 64, 100, FP16
     d.jobs[0].a = d.jobs[0].w = 1
-    d.jobs[0].K, d.jobs[0].dil = 3, 1
+    d.jobs[0].K, d.jobs[0].dil, d.jobs[0].pad = 3, 1, 1
     assert lib.rvc_conv1d_tc(C.byref(d), None) == -2
     assert b"multiple of 16" in lib.rvc_last_error()
