@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 8
+#define RVC_ABI_VERSION 9
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -85,6 +85,12 @@ typedef struct {
     const float* x2; const float* x3; float in_div;
 } rvc_convtr1d_desc;
 int rvc_convtr1d_f32(const rvc_convtr1d_desc* d, void* stream);
+
+/* NSF noise conv alone (synthesizers.py:134-136, :156): y[b,co,l] = bias[co] + sum_j w[co][j] * har[b, l*sn - pn + j]; har has
+ * Lout*sn samples per batch row (har_bs apart), y is contiguous [B,C,Lout] with batch stride y_bs.  Used as the residual input
+ * of the tensor-core ConvTranspose1d. */
+int rvc_noise_conv_f32(const float* har, int64_t har_bs, const float* w, const float* bias, float* y, int64_t y_bs, int32_t B,
+                       int32_t C, int32_t Lout, int32_t kn, int32_t sn, int32_t pn, void* stream);
 
 /* y[b,0,l] = tanh( sum_{ci,k} w[ci*7+k] * leaky_relu(in[b,ci,l-3+k], slope) ), no bias — conv_post (synthesizers.py:161);
  * in = x, or (x + x2 + x3) / in_div when x2/x3 are given. */

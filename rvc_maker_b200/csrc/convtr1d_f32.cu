@@ -204,3 +204,56 @@ RVC_API int rvc_conv_post_f32(const float* x, const float* x2, const float* x3, 
     conv_post_f32_kernel<<<grid, 256, C * 7 * sizeof(float), (cudaStream_t)stream>>>(x, x2, x3, in_div, x_bs, x_cs, w, y, y_bs, C, L, slope);
     return rvc::check_launch("rvc_conv_post_f32");
 }
+
+// ------------------------------------------------------------------------------------------------
+// NSF noise convs (synthesizers.py:134-136): y[b,co,l] = bias[co] + sum_j w[co][j] * har[b, l*sn - pn + j], Cin = 1.
+// One thread = one output position; its har window sits in registers (16 taps at a time) and is reused by 32 channels.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __restrict__ har, int64_t har_bs, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ y, int64_t y_bs, int C,
+                                                             int Lout, int kn, int sn, int pn) {
+    extern __shared__ float w_s[];  // [32][kn]
+    const int co0 = blockIdx.y * 32, b = blockIdx.z;
+    for (int i = threadIdx.x; i < 32 * kn; i += 128) {
+        const int c = i / kn;
+        w_s[i] = (co0 + c < C) ? w[(int64_t)(co0 + c) * kn + (i - c * kn)] : 0.f;
+    }
+    __syncthreads();
+    const int l = blockIdx.x * 128 + threadIdx.x;
+    if (l >= Lout) return;
+    const int64_t hlen = (int64_t)Lout * sn;
+    const float* hb = har + (int64_t)b * har_bs;
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = (co0 + c < C && bias) ? bias[co0 + c] : 0.f;
+    for (int j0 = 0; j0 < kn; j0 += 16) {
+        float h[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int64_t idx = (int64_t)l * sn - pn + j0 + j;
+            h[j] = (j0 + j < kn && idx >= 0 && idx < hlen) ? hb[idx] : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float* wr = w_s + c * kn + j0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j0 + j < kn) acc[c] = fmaf(wr[j], h[j], acc[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+        if (co0 + c < C) y[(int64_t)b * y_bs + (int64_t)(co0 + c) * Lout + l] = acc[c];
+}
+}  // namespace
+
+RVC_API int rvc_noise_conv_f32(const float* har, int64_t har_bs, const float* w, const float* bias, float* y, int64_t y_bs, int32_t B,
+                               int32_t C, int32_t Lout, int32_t kn, int32_t sn, int32_t pn, void* stream) {
+    if (!har || !w || !y) return rvc::fail(RVC_EINVAL, "rvc_noise_conv_f32: null pointer");
+    if (B <= 0 || B > 65535 || C <= 0 || Lout < 0 || kn <= 0 || kn > 1024 || sn <= 0 || pn < 0) return rvc::fail(RVC_ESHAPE, "rvc_noise_conv_f32: bad shape");
+    if (Lout == 0) return 0;
+    dim3 grid(rvc::cdiv(Lout, 128), rvc::cdiv(C, 32), B);
+    noise_conv_f32_kernel<<<grid, 128, 32 * kn * sizeof(float), (cudaStream_t)stream>>>(har, har_bs, w, bias, y, y_bs, C, Lout, kn, sn, pn);
+    return rvc::check_launch("rvc_noise_conv_f32");
+}

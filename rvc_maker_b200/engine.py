@@ -178,10 +178,25 @@ class Engine:
                 elif ch in (32, 64):
                     dt = DT_FP16
             self.stage_dt.append(dt)
+        self.up_dt = []
         for i in range(len(c["rates"])):
             up = d.ups[i] if c["f0"] else d.ups_and_resblocks[i * (nk + 1)]
-            W[f"up_w{i}"] = _fold_wn(up).permute(0, 2, 1).contiguous()  # [Cin][k][Cout]
+            wt = _fold_wn(up)                                           # [Cin][Cout][k]
+            W[f"up_w{i}"] = wt.permute(0, 2, 1).contiguous()            # [Cin][k][Cout]
             W[f"up_b{i}"] = _f(up.bias)
+            cin_i, cout_i, k_i, u_i = wt.shape[0], wt.shape[1], wt.shape[2], c["rates"][i]
+            self.up_dt.append(None)
+            if self.precision == "tc" and cin_i % 16 == 0 and cout_i % 32 == 0 and (k_i - u_i) % 2 == 0:
+                # phase-major conv weight [Cout][Cin][u*M]: block r, tap t = w_T[:, :, r + (M-1-t)*u] (include/rvc_b200.h)
+                M = -(-k_i // u_i)
+                wk = torch.zeros(cout_i, cin_i, u_i * M)
+                for r in range(u_i):
+                    for t in range(M):
+                        kk = r + (M - 1 - t) * u_i
+                        if kk < k_i:
+                            wk[:, :, r * M + t] = wt[:, :, kk].t()
+                self.up_dt[i] = self.stage_dt[i] if self.stage_dt[i] is not None else DT_FP16
+                tc_w[f"t_up_w{i}"] = (wk, self.up_dt[i])
             if c["f0"]:
                 W[f"nz_w{i}"] = _f(d.noise_convs[i].weight)[:, 0, :].contiguous()
                 W[f"nz_b{i}"] = _f(d.noise_convs[i].bias)
@@ -277,10 +292,11 @@ class Engine:
         bytes_ = 4.0 * (B * Cin * L + B * Cout * L * (1 + (res is not None) + (beta != 0.0)) + Cin * K * Cout * g2)
         plan.add(name, self.lib.rvc_conv1d_f32, C.byref(d), flops=flops, bytes_=bytes_, kind=f"conv1d_f32[C{Cout}k{K}]")
 
-    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag=""):
+    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag="", up=1, pshift=0, flops=None):
         """One persistent tcgen05 launch over up to three jobs (dicts of rvc_tc_job fields; V views for res / y)."""
         d = Conv1dTcDesc()
         d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.nt, d.mt = len(jobs), B, Cin, Cout, L, dtype, nt, mt
+        d.up, d.pshift = up, pshift
         fl = by = 0.0
         for slot, j in enumerate(jobs):
             jb = d.jobs[slot]
@@ -302,10 +318,10 @@ class Engine:
             jb.alpha, jb.act_slope = j.get("alpha", 1.0), j.get("act_slope", 1.0)
             ce = Cout // 2 if jb.gated else Cout
             fl += 2.0 * B * Cin * Cout * jb.K * L
-            by += B * L * (2.0 * Cin + ce * (4.0 * (j.get("res") is not None) + 4.0 * (j.get("y") is not None) + 2.0 * (j.get("y_act") is not None)))
+            by += B * L * (2.0 * Cin + up * ce * (4.0 * (j.get("res") is not None) + 4.0 * (j.get("y") is not None) + 2.0 * (j.get("y_act") is not None)))
         plan.keep.append(d)
         plan.keep.append(jobs)
-        plan.add(name, self.lib.rvc_conv1d_tc, C.byref(d), flops=fl, bytes_=by,
+        plan.add(name, self.lib.rvc_conv1d_tc, C.byref(d), flops=fl if flops is None else flops, bytes_=by,
                  kind=f"conv1d_tc_{'bf16' if dtype == DT_BF16 else 'fp16'}[{tag or 'C%d' % Cout}]")
 
     def _packed(self, plan, B, Cch, L):
@@ -446,11 +462,13 @@ class Engine:
             p.add("sine_source", lib.rvc_sine_source_f32, p.f0.data_ptr(), p.eps_src.data_ptr(), W["lin_w"].data_ptr(), W["lin_b"].data_ptr(),
                   scratch.data_ptr(), har.data_ptr(), B, T, upp, c["sr"], launches=2, bytes_=8.0 * B * Lfin, kind="sine_source_f32")
         xpre = self._buf(p, B, U, T)
+        xpre_a = None
         if self.enc_tc:
             za = self._packed(p, B, I, T)
             p.add("pack_z", lib.rvc_pack_act, p.z.data_ptr(), None, None, 1.0, I * T, T, p.mask.data_ptr(), za.data_ptr(), B, I, T, DT_FP16, 1.0, kind="pack_act",
                   bytes_=6.0 * B * I * T)
-            self._tc(p, "conv_pre", [dict(a=za, w=W["t_pre_w"], bias=W["pre_b"], K=7, y=V(xpre, U, T),
+            xpre_a = self._packed(p, B, U, T) if self.up_dt[0] == DT_FP16 else None
+            self._tc(p, "conv_pre", [dict(a=za, w=W["t_pre_w"], bias=W["pre_b"], K=7, y=V(xpre, U, T), y_act=xpre_a, act_slope=LRELU_SLOPE,
                                           bias_b=gc.data_ptr() + self.cond_off[4] * 4, bias_b_bs=self.cond_total)],
                      B=B, Cin=I, Cout=U, L=T, dtype=DT_FP16, tag="conv_pre")
         else:
@@ -469,25 +487,50 @@ class Engine:
         for i, (u, k) in enumerate(zip(rates, uks)):
             Ci, Li = chans[i], lens[i]
             dt = self.stage_dt[i]
-            d = ConvTr1dDesc()
-            vx = V(cur[0], curC, curL)
-            d.x, d.x_bs, d.x_cs = vx.ptr, vx.bs, vx.cs
-            if cur[1] is not None:
-                d.x2, d.x3, d.in_div = cur[1].data_ptr(), cur[2].data_ptr(), float(nk)
-            d.w, d.bias = W[f"up_w{i}"].data_ptr(), W[f"up_b{i}"].data_ptr()
-            if c["f0"]:
-                sn = int(math.prod(rates[i + 1:])) if i + 1 < len(rates) else 1
-                kn = 1 if sn == 1 else sn * 2 - sn % 2
-                d.har, d.har_bs = har.data_ptr(), Lfin
-                d.nw, d.nbias = W[f"nz_w{i}"].data_ptr(), W[f"nz_b{i}"].data_ptr()
-                d.kn, d.sn, d.pn = kn, sn, (0 if sn == 1 else (kn - sn) // 2)
             vs0 = V(S[0], Ci, Li)
-            d.y, d.y_bs, d.y_cs = vs0.ptr, vs0.bs, vs0.cs
-            d.B, d.Cin, d.Cout, d.Lin, d.k, d.u = B, curC, Ci, curL, k, u
-            d.pre_slope = LRELU_SLOPE
-            p.keep.append(d)
-            p.add(f"ups{i}", lib.rvc_convtr1d_f32, C.byref(d), flops=2.0 * B * curC * Ci * k * curL, bytes_=4.0 * B * (curC * curL + Ci * Li),
-                  kind="convtr1d_f32")
+            sn = int(math.prod(rates[i + 1:])) if i + 1 < len(rates) else 1
+            kn = 1 if sn == 1 else sn * 2 - sn % 2
+            pn = 0 if sn == 1 else (kn - sn) // 2
+            xa = None   # packed lrelu(x) of this stage's input to the ResBlocks, produced by the ups epilogue when possible
+            if self.up_dt[i] is not None:
+                # ---- ConvTranspose1d on tensor cores: u phase GEMMs; the noise conv result is the epilogue's residual input
+                udt = self.up_dt[i]
+                if i == 0 and xpre_a is not None:
+                    ua = xpre_a
+                else:
+                    ua = self._packed(p, B, curC, curL)
+                    x2 = cur[1].data_ptr() if cur[1] is not None else None
+                    x3 = cur[2].data_ptr() if cur[2] is not None else None
+                    p.add(f"pack_up{i}", lib.rvc_pack_act, cur[0].data_ptr(), x2, x3, float(nk), curC * curL, curL, None, ua.data_ptr(), B, curC,
+                          curL, udt, LRELU_SLOPE, bytes_=B * curC * curL * (2.0 + (12.0 if x2 else 4.0)), kind="pack_act")
+                if c["f0"]:
+                    p.add(f"noise{i}", lib.rvc_noise_conv_f32, har.data_ptr(), Lfin, W[f"nz_w{i}"].data_ptr(), W[f"nz_b{i}"].data_ptr(),
+                          S[0].data_ptr(), Ci * Li, B, Ci, Li, kn, sn, pn, flops=2.0 * B * Ci * Li * kn, bytes_=4.0 * B * (Ci * Li + Li * sn),
+                          kind="noise_conv_f32")
+                if dt is not None and dt == udt:
+                    xa = self._packed(p, B, Ci, Li)
+                M = -(-k // u)
+                self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(vs0 if c["f0"] else None), y=vs0, y_act=xa,
+                                             act_slope=LRELU_SLOPE, K=M, pad=M - 1)],
+                         B=B, Cin=curC, Cout=Ci, L=curL, dtype=udt, up=u, pshift=(k - u) // 2, tag=f"ups",
+                         flops=2.0 * B * curC * Ci * k * curL)
+            else:
+                d = ConvTr1dDesc()
+                vx = V(cur[0], curC, curL)
+                d.x, d.x_bs, d.x_cs = vx.ptr, vx.bs, vx.cs
+                if cur[1] is not None:
+                    d.x2, d.x3, d.in_div = cur[1].data_ptr(), cur[2].data_ptr(), float(nk)
+                d.w, d.bias = W[f"up_w{i}"].data_ptr(), W[f"up_b{i}"].data_ptr()
+                if c["f0"]:
+                    d.har, d.har_bs = har.data_ptr(), Lfin
+                    d.nw, d.nbias = W[f"nz_w{i}"].data_ptr(), W[f"nz_b{i}"].data_ptr()
+                    d.kn, d.sn, d.pn = kn, sn, pn
+                d.y, d.y_bs, d.y_cs = vs0.ptr, vs0.bs, vs0.cs
+                d.B, d.Cin, d.Cout, d.Lin, d.k, d.u = B, curC, Ci, curL, k, u
+                d.pre_slope = LRELU_SLOPE
+                p.keep.append(d)
+                p.add(f"ups{i}", lib.rvc_convtr1d_f32, C.byref(d), flops=2.0 * B * curC * Ci * k * curL, bytes_=4.0 * B * (curC * curL + Ci * Li),
+                      kind="convtr1d_f32")
             if dt is None:
                 # ---- fp32 CUDA-core ResBlocks, sequential, accumulated into S[3]
                 vs1, vs2, vs3 = V(S[1], Ci, Li), V(S[2], Ci, Li), V(S[3], Ci, Li)
@@ -511,11 +554,12 @@ class Engine:
                 esz = 2
                 rows = int(lib.rvc_packed_rows(Li))
                 pk = lambda: self._zbuf(p, B * Ci * rows * esz)          # packed activations (pad rows stay zero)
-                xa = pk()
                 ta, pa = [pk() for _ in range(nk)], [pk() for _ in range(nk)]
                 P = [S[1 + j] for j in range(nk)]                        # fp32 residual streams / block outputs
-                p.add(f"pack{i}", lib.rvc_pack_act, S[0].data_ptr(), None, None, 1.0, Ci * Li, Li, None, xa.data_ptr(), B, Ci, Li, dt, LRELU_SLOPE,
-                      bytes_=B * Ci * Li * (4.0 + esz), kind="pack_act")
+                if xa is None:
+                    xa = pk()
+                    p.add(f"pack{i}", lib.rvc_pack_act, S[0].data_ptr(), None, None, 1.0, Ci * Li, Li, None, xa.data_ptr(), B, Ci, Li, dt,
+                          LRELU_SLOPE, bytes_=B * Ci * Li * (4.0 + esz), kind="pack_act")
                 order = sorted(range(nk), key=lambda j: -rks[j])          # heavy kernels first (static round-robin tiles)
                 nsteps = len(rds[0])
                 assert all(len(dl) == nsteps for dl in rds)
