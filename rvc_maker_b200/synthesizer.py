@@ -169,7 +169,8 @@ class Synthesizer(nn.Module):
         self.flow = fl
         self.emb_g = nn.Embedding(spk_embed_dim, G)
 
-        # "tc": ResBlocks on tcgen05 tensor cores (bf16 for C >= 128, tf32 for C in {32, 64}); "fp32": CUDA-core fp32 everywhere
+        # "tc": every conv on tcgen05 tensor cores with fp16 operands / fp32 accumulation; "tc-bf16": same with bf16 operands in the
+        # C >= 128 ResBlocks; "fp32": CUDA-core fp32 everywhere
         self.precision = kwargs.get("precision", os.environ.get("RVC_B200_PRECISION", "tc"))
         self._engine = None
         self._noise_override = None  # tests: (eps_z [B,I,T], eps_src [B,T*upp,1] or None)

@@ -28,7 +28,7 @@ TC_LATENT_SNR = 50.0
 
 
 def tol_for(precision, key):
-    if precision == "tc":
+    if precision.startswith("tc"):
         return (TC_TOL, TC_SNR) if key == "o" else (TC_LATENT_TOL, TC_LATENT_SNR)
     return FP32_TOL, FP32_SNR
 
@@ -72,7 +72,7 @@ def assert_close(out, ref, precision="fp32", tag=""):
             assert m["snr_db"] >= snr, (tag, k, m)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("precision", ["fp32", "tc", "tc-bf16"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_cuda_matches_reference_golden(name, precision, golden_dir):
     cname, use_f0, heated, disk, B, T, ragged, rate, wseed, iseed, _ = CASES[name]
@@ -86,7 +86,7 @@ def test_cuda_matches_reference_golden(name, precision, golden_dir):
     assert_close(out, gold, precision, tag=name)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("precision", ["fp32", "tc", "tc-bf16"])
 @pytest.mark.parametrize("cname,use_f0,B,T,ragged", [
     ("v2_40k", True, 1, 300, False),
     ("v2_48k", True, 2, 250, True),
