@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 9
+#define RVC_ABI_VERSION 10
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -171,7 +171,12 @@ typedef struct {
     float* y_f32; int64_t y_bs, y_cs;
     void* y_act;
     int32_t K, dil, pad, gated, relu;   /* pad = zero rows left of position 0 seen by tap 0 ("same": (K-1)/2*dil) */
-    float alpha, act_slope;
+    float alpha, act_slope;             /* without res: v *= alpha */
+    /* optional layout overrides (0 = default), used when one operand is itself an activation (attention: S = q.k^T, O = P.v):
+     * a_bs / y_act_bs = bytes between batch items of a / y_act; w_bs = bytes between per-batch weight sets (0: shared
+     * weights); w_cs = rows between consecutive 16-byte weight chunks (default Cout). */
+    int64_t a_bs, w_bs, y_act_bs;
+    int32_t w_cs, reserved;
 } rvc_tc_job;
 /*
  * up > 1 selects the ConvTranspose1d phase mode (GeneratorNSF.ups, synthesizers.py:133,156): the packed weights hold `up`
@@ -184,6 +189,19 @@ typedef struct {
     int32_t njobs, B, Cin, Cout, L, dtype, nt, mt, up, pshift;
 } rvc_conv1d_tc_desc;
 int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);
+
+/*
+ * Softmax stage of the tensor-core attention (MultiHeadAttention.attention, synthesizers.py:221-250).  The contractions run
+ * through rvc_conv1d_tc: S[b][h][j][i] = q_i . k_j (fp32, Tk >= T key rows per head, Tk % 8 == 0; rows >= T ignored) and
+ * O = P . v (+ R).  This call computes, per (b, head, query i):
+ *   s[i,j] = S[j][i] / sqrt(dk) + [|j-i| <= w] (q_i / sqrt(dk)) . emb_k[j-i+w];   s = -1e4 where mask_i * mask_j == 0
+ *   P = softmax_j(s) -> packed fp16 [b][h][Tk/8][rvc_packed_rows(T)][8] (positions = queries, channels = keys)
+ *   R[b][h*dk + d][i] = sum_{|j-i|<=w} P[i,j] emb_v[j-i+w][d]                        (fp32 [B,H,T])
+ *   vw = v^T packed over keys: fp16 [b][h][Tk/8][dk][8]                              (weights of the P.v GEMM)
+ * qkv is the fp32 [B, 3H, T] projection (q, k, v row blocks).
+ */
+int rvc_attn_softmax(const float* S, const float* qkv, const float* mask, const float* emb_k, const float* emb_v, void* P, float* R,
+                     void* vw, int32_t B, int32_t H, int32_t n_heads, int32_t T, int32_t Tk, int32_t window, void* stream);
 
 #ifdef __cplusplus
 }

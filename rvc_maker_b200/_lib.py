@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 DT_BF16, DT_FP16 = 0, 2
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -58,6 +58,8 @@ class TcJob(C.Structure):
         ("y_act", _vp),
         ("K", _i32), ("dil", _i32), ("pad", _i32), ("gated", _i32), ("relu", _i32),
         ("alpha", _f32), ("act_slope", _f32),
+        ("a_bs", _i64), ("w_bs", _i64), ("y_act_bs", _i64),
+        ("w_cs", _i32), ("reserved", _i32),
     ]
 
 
@@ -84,6 +86,7 @@ SIGNATURES = {
     "rvc_pack_act": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_conv1d_tc": (C.c_int, [C.POINTER(Conv1dTcDesc), _vp]),
+    "rvc_attn_softmax": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,167 @@
+// Softmax stage of the tensor-core attention path (MultiHeadAttention.attention, synthesizers.py:221-250).
+//
+// The two contractions run on the tcgen05 GEMM engine (conv1d_tc.cu): S = q.k^T as a 1x1 "conv" whose weights are the packed
+// k activations, and O = P.v with the v^T tile as weights.  This kernel sits between them:
+//   s[i,j] = S[j][i] / sqrt(dk) + [|j-i| <= w] (q_i / sqrt(dk)).Ek[j-i+w];   s = -1e4 where mask_i * mask_j == 0
+//   P[i,j] = softmax_j(s)            -> packed fp16 [b][h][j/8][64 + i][8]   (the A operand of the P.v GEMM)
+//   R[i,:] = sum_{|j-i|<=w} P[i,j] Ev[j-i+w]                                  (fp32, the residual input of the P.v GEMM)
+//   vw     = v^T packed over keys   -> fp16 [b][h][j/8][d][8]                (the weights of the P.v GEMM)
+// CTA = 64 queries x 8 key groups (512 threads); S is read coalesced along queries, twice (online max/sum, then probabilities).
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <math.h>
+
+namespace {
+
+constexpr int AQ = 64, AG = 8, ANT = AQ * AG;
+
+__device__ __forceinline__ uint32_t h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restrict__ S, const float* __restrict__ qkv, const float* __restrict__ mask,
+                                                           const float* __restrict__ emb_k, const float* __restrict__ emb_v, uint8_t* __restrict__ P,
+                                                           float* __restrict__ R, uint8_t* __restrict__ vw, int H, int nh, int T, int Tk, int Lp,
+                                                           int W, int nqb) {
+    extern __shared__ float sm[];
+    const int dk = H / nh, NR = 2 * W + 1;
+    const int h = blockIdx.y % nh, b = blockIdx.y / nh;
+    const int nchunk = Tk / 8;
+    const int tid = threadIdx.x;
+    const float* vb = qkv + ((int64_t)b * 3 * H + 2 * H + h * dk) * T;
+
+    if ((int)blockIdx.x >= nqb) {
+        // ---- v^T pack: vw[b][h][c][d][8] = v[d][8c .. 8c+7]
+        const int idx = (blockIdx.x - nqb) * ANT + tid;
+        if (idx >= dk * nchunk) return;
+        const int d = idx / nchunk, c = idx - d * nchunk;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (8 * c + i < T) ? vb[(int64_t)d * T + 8 * c + i] : 0.f;
+        uint4 pk = make_uint4(h2(v[0], v[1]), h2(v[2], v[3]), h2(v[4], v[5]), h2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(vw + ((((int64_t)b * nh + h) * nchunk + c) * dk + d) * 16) = pk;
+        return;
+    }
+
+    float* qe_s = sm;                    // [AQ][NR]
+    float* ev_s = qe_s + AQ * NR;        // [NR][dk]
+    float* m_s = ev_s + NR * dk;         // [AG][AQ]
+    float* l_s = m_s + AG * AQ;          // [AG][AQ]
+    const int ti = tid % AQ, g = tid / AQ;
+    const int i0 = blockIdx.x * AQ, i = i0 + ti;
+    const float* qb = qkv + ((int64_t)b * 3 * H + h * dk) * T;
+    const float* mb = mask + (int64_t)b * T;
+    const float* Sb = S + ((int64_t)b * nh + h) * Tk * T;
+    const float rs = sqrtf((float)dk);
+
+    for (int idx = tid; idx < NR * dk; idx += ANT) ev_s[idx] = emb_v[idx];
+    for (int idx = tid; idx < AQ * NR; idx += ANT) {
+        const int q = idx % AQ, r = idx / AQ;   // consecutive threads -> consecutive queries (coalesced q reads)
+        float acc = 0.f;
+        if (i0 + q < T)
+            for (int d = 0; d < dk; ++d) acc = fmaf(qb[(int64_t)d * T + i0 + q] / rs, emb_k[r * dk + d], acc);
+        qe_s[q * NR + r] = acc;
+    }
+    __syncthreads();
+
+    const bool qok = i < T;
+    const float mq = qok ? mb[i] : 0.f;
+    const float inv = 1.f / rs;
+    auto score = [&](int j) -> float {
+        float s = Sb[(int64_t)j * T + i] * inv;
+        const int rel = j - i + W;
+        if (rel >= 0 && rel < NR) s += qe_s[ti * NR + rel];
+        if (mq * mb[j] == 0.f) s = -1e4f;
+        return s;
+    };
+
+    // ---- pass 1: online max / sum over this group's key chunks (chunk c belongs to group c % AG)
+    float m = -INFINITY, l = 0.f;
+    if (qok)
+        for (int c = g; c < nchunk; c += AG) {
+            float s8[8];
+            float cm = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = 8 * c + u;
+                s8[u] = j < T ? score(j) : -INFINITY;
+                cm = fmaxf(cm, s8[u]);
+            }
+            if (cm == -INFINITY) continue;
+            const float mn = fmaxf(m, cm);
+            float acc = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += expf(s8[u] - mn);
+            l = l * expf(m - mn) + acc;
+            m = mn;
+        }
+    m_s[g * AQ + ti] = m;
+    l_s[g * AQ + ti] = l;
+    __syncthreads();
+    float M = -INFINITY, Lsum = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < AG; ++gg) M = fmaxf(M, m_s[gg * AQ + ti]);
+#pragma unroll
+    for (int gg = 0; gg < AG; ++gg) {
+        const float mg = m_s[gg * AQ + ti];
+        if (mg != -INFINITY) Lsum += l_s[gg * AQ + ti] * expf(mg - M);
+    }
+    if (!qok) return;
+    const float rl = 1.f / Lsum;
+
+    // ---- pass 2: probabilities, packed fp16
+    uint8_t* Pb = P + (((int64_t)b * nh + h) * nchunk * Lp + 64 + i) * 16;
+    for (int c = g; c < nchunk; c += AG) {
+        float p8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = 8 * c + u;
+            p8[u] = j < T ? expf(score(j) - M) * rl : 0.f;
+        }
+        *reinterpret_cast<uint4*>(Pb + (int64_t)c * Lp * 16) = make_uint4(h2(p8[0], p8[1]), h2(p8[2], p8[3]), h2(p8[4], p8[5]), h2(p8[6], p8[7]));
+    }
+
+    // ---- relative-value term: group g owns output dims [g*dk/8, (g+1)*dk/8)
+    const int dpg = dk / AG, d0 = g * dpg;
+    float acc[16];
+#pragma unroll
+    for (int dd = 0; dd < 16; ++dd) acc[dd] = 0.f;
+    for (int r = 0; r < NR; ++r) {
+        const int j = i + r - W;
+        if (j < 0 || j >= T) continue;
+        const float pv = expf(score(j) - M) * rl;
+#pragma unroll
+        for (int dd = 0; dd < 16; ++dd)
+            if (dd < dpg) acc[dd] = fmaf(pv, ev_s[r * dk + d0 + dd], acc[dd]);
+    }
+    float* Rb = R + ((int64_t)b * H + h * dk + d0) * T + i;
+#pragma unroll
+    for (int dd = 0; dd < 16; ++dd)
+        if (dd < dpg) Rb[(int64_t)dd * T] = acc[dd];
+}
+
+}  // namespace
+
+RVC_API int rvc_attn_softmax(const float* S, const float* qkv, const float* mask, const float* emb_k, const float* emb_v, void* P, float* R,
+                             void* vw, int32_t B, int32_t H, int32_t n_heads, int32_t T, int32_t Tk, int32_t window, void* stream) {
+    if (!S || !qkv || !mask || !emb_k || !emb_v || !P || !R || !vw) return rvc::fail(RVC_EINVAL, "rvc_attn_softmax: null pointer");
+    if (B <= 0 || H <= 0 || n_heads <= 0 || H % n_heads || T <= 0 || Tk < T || Tk % 8 || window < 0)
+        return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: bad shape");
+    const int dk = H / n_heads;
+    if (dk % AG || dk / AG > 16) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: head dim %d must be a multiple of 8 and <= 128", dk);
+    if ((int64_t)B * n_heads > 65535) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: B*heads > 65535");
+    const int NR = 2 * window + 1;
+    const size_t smem = (size_t)(AQ * NR + NR * dk + 2 * AG * AQ) * sizeof(float);
+    if (smem > 200 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: window too large");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return rvc::fail((int)e, "rvc_attn_softmax: smem opt-in: %s", cudaGetErrorString(e));
+    }
+    const int nqb = rvc::cdiv(T, AQ);
+    const int nvb = rvc::cdiv(dk * (Tk / 8), ANT);
+    dim3 grid(nqb + nvb, B * n_heads);
+    attn_softmax_kernel<<<grid, ANT, smem, (cudaStream_t)stream>>>(S, qkv, mask, emb_k, emb_v, (uint8_t*)P, R, (uint8_t*)vw, H, n_heads, T, Tk,
+                                                                   (int)rvc_packed_rows(T), window, nqb);
+    return rvc::check_launch("rvc_attn_softmax");
+}

@@ -123,8 +123,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     tc::mbar_arrive_expect_tx(A_FULL(ast), (uint32_t)nc * rows * 16);
                 }
                 __syncwarp();
-                const uint8_t* asrc = reinterpret_cast<const uint8_t*>(jb.a) +
-                                      (((size_t)b * p.nch + c0) * p.Lp + (size_t)(PADL + lt * TM - pad)) * 16;
+                const size_t a_bs = jb.a_bs ? (size_t)jb.a_bs : (size_t)p.nch * p.Lp * 16;
+                const uint8_t* asrc = reinterpret_cast<const uint8_t*>(jb.a) + (size_t)b * a_bs +
+                                      ((size_t)c0 * p.Lp + (size_t)(PADL + lt * TM - pad)) * 16;
                 for (int c = lane; c < nc; c += 32)
                     tc::bulk_g2s(tc::smem_u32(a_smem + (size_t)ast * a_bytes + (size_t)c * p.rows_max * 16), asrc + (size_t)c * p.Lp * 16,
                                  (uint32_t)rows * 16, A_FULL(ast));
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             int j, b, lt, nt, ph;
             decode(tile, j, b, lt, nt, ph);
             const rvc_tc_job& jb = p.jobs[j];
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(jb.w) + (size_t)ph * jb.K * p.nch * p.Cout * 16;
+            const size_t w_cs = jb.w_cs ? (size_t)jb.w_cs : (size_t)p.Cout;      // rows between consecutive weight chunks
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(jb.w) + (size_t)b * jb.w_bs + (size_t)ph * jb.K * p.nch * w_cs * 16;
             for (int cs = 0; cs < p.ncs; ++cs) {
                 const int ca = cs * p.ach;
                 const int na = min(p.ach, p.nch - ca);
@@ -151,11 +153,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                         }
                         __syncwarp();
                         const uint32_t dst = tc::smem_u32(w_smem + wst * STAGE_BYTES);
-                        const uint8_t* src = wsrc + (((size_t)tap * p.nch + ca + c0) * p.Cout + (size_t)nt * NT) * 16;
-                        if (NT == p.Cout) {
+                        const uint8_t* src = wsrc + (((size_t)tap * p.nch + ca + c0) * w_cs + (size_t)nt * NT) * 16;
+                        if (NT == p.Cout && w_cs == (size_t)p.Cout) {
                             if (lane == 0) tc::bulk_g2s(dst, src, (uint32_t)nc * NT * 16, W_FULL(wst));
                         } else {
-                            for (int c = lane; c < nc; c += 32) tc::bulk_g2s(dst + c * NT * 16, src + (size_t)c * p.Cout * 16, NT * 16, W_FULL(wst));
+                            for (int c = lane; c < nc; c += 32) tc::bulk_g2s(dst + c * NT * 16, src + (size_t)c * w_cs * 16, NT * 16, W_FULL(wst));
                         }
                         if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                     }
@@ -268,6 +270,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                         const float* rp = jb.res + (size_t)b * jb.res_bs + (size_t)co0 * jb.res_cs + l;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = rp[(size_t)i * jb.res_cs] + jb.alpha * v[i];
+                } else if (jb.alpha != 1.f) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= jb.alpha;
                     }
                     if (jb.mask) {
 #pragma unroll
@@ -279,7 +284,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                         for (int i = 0; i < 32; ++i) yp[(size_t)i * jb.y_cs] = v[i];
                     }
                     if (jb.y_act) {
-                        uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (((size_t)b * p.nch_out + co0 / 8) * p.Lp_out + PADL + l) * 16;
+                        const size_t ya_bs = jb.y_act_bs ? (size_t)jb.y_act_bs : (size_t)p.nch_out * p.Lp_out * 16;
+                        uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (size_t)b * ya_bs + (((size_t)co0 / 8) * p.Lp_out + PADL + l) * 16;
                         const float sl = jb.act_slope;
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {

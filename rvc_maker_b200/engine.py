@@ -301,7 +301,8 @@ class Engine:
         fl = by = 0.0
         for slot, j in enumerate(jobs):
             jb = d.jobs[slot]
-            jb.a, jb.w = j["a"].data_ptr(), j["w"].data_ptr()
+            jb.a = j["a"] if isinstance(j["a"], int) else j["a"].data_ptr()
+            jb.w = j["w"] if isinstance(j["w"], int) else j["w"].data_ptr()
             jb.bias = j["bias"].data_ptr() if j.get("bias") is not None else None
             if j.get("bias_b") is not None:
                 jb.bias_b, jb.bias_b_bs = j["bias_b"], j["bias_b_bs"]
@@ -312,11 +313,12 @@ class Engine:
             if j.get("y") is not None:
                 jb.y_f32, jb.y_bs, jb.y_cs = j["y"].ptr, j["y"].bs, j["y"].cs
             if j.get("y_act") is not None:
-                jb.y_act = j["y_act"].data_ptr()
+                jb.y_act = j["y_act"] if isinstance(j["y_act"], int) else j["y_act"].data_ptr()
             jb.K, jb.dil = j.get("K", 1), j.get("dil", 1)
             jb.pad = j.get("pad", (jb.K - 1) // 2 * jb.dil)
             jb.gated, jb.relu = int(j.get("gated", False)), int(j.get("relu", False))
             jb.alpha, jb.act_slope = j.get("alpha", 1.0), j.get("act_slope", 1.0)
+            jb.a_bs, jb.w_bs, jb.y_act_bs, jb.w_cs = j.get("a_bs", 0), j.get("w_bs", 0), j.get("y_act_bs", 0), j.get("w_cs", 0)
             ce = Cout // 2 if jb.gated else Cout
             fl += 2.0 * B * Cin * Cout * jb.K * L
             by += B * L * (2.0 * Cin + up * ce * (4.0 * (j.get("res") is not None) + 4.0 * (j.get("y") is not None) + 2.0 * (j.get("y_act") is not None)))
@@ -361,12 +363,41 @@ class Engine:
             dt = DT_FP16
             xa, atta, ha = self._packed(p, B, H, T), self._packed(p, B, H, T), self._packed(p, B, Fc, T)
             p.add("pack_x", lib.rvc_pack_act, x.data_ptr(), None, None, 1.0, H * T, T, None, xa.data_ptr(), B, H, T, dt, 1.0, kind="pack_act", bytes_=6.0 * B * H * T)
+            nh = c["nh"]
+            dk = H // nh
+            tc_attn = nh <= 3 and dk % 32 == 0
+            if tc_attn:
+                Lp = int(lib.rvc_packed_rows(T))
+                Tk = (T + 127) // 128 * 128
+                qkva = self._packed(p, B, 3 * H, T)
+                Sb = self._buf(p, B, nh, Tk, T)
+                Pb = self._zbuf(p, B * nh * (Tk // 8) * Lp * 16)
+                Rb = self._buf(p, B, H, T)
+                vwb = self._buf(p, B * nh * (Tk // 8) * dk * 4, dtype=torch.int32)
+                qkv_bs = (3 * H // 8) * Lp * 16
             for i in range(c["nl"]):
-                self._tc(p, f"qkv{i}", [dict(a=xa, w=W[f"t_qkv_w{i}"], bias=W[f"qkv_b{i}"], y=vqkv)], B=B, Cin=H, Cout=3 * H, L=T, dtype=dt, tag="enc")
-                p.add(f"attn{i}", lib.rvc_rel_attention_f32, qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(), W[f"ev{i}"].data_ptr(),
-                      att.data_ptr(), B, H, c["nh"], T, WINDOW, flops=4.0 * B * H * T * T, bytes_=16.0 * B * H * T, kind="rel_attention_f32")
-                p.add(f"pack_att{i}", lib.rvc_pack_act, att.data_ptr(), None, None, 1.0, H * T, T, None, atta.data_ptr(), B, H, T, dt, 1.0, kind="pack_act",
-                      bytes_=6.0 * B * H * T)
+                self._tc(p, f"qkv{i}", [dict(a=xa, w=W[f"t_qkv_w{i}"], bias=W[f"qkv_b{i}"], y=vqkv, y_act=(qkva if tc_attn else None))],
+                         B=B, Cin=H, Cout=3 * H, L=T, dtype=dt, tag="enc")
+                if tc_attn:
+                    # S[b][h][key][query] = q . k^T : the packed k activations of each batch item are the GEMM's weights
+                    jobs = [dict(a=qkva.data_ptr() + (h * dk // 8) * Lp * 16, a_bs=qkv_bs,
+                                 w=qkva.data_ptr() + (((H + h * dk) // 8) * Lp + 64) * 16, w_bs=qkv_bs, w_cs=Lp,
+                                 y=V(Sb, nh * Tk, T, h * Tk)) for h in range(nh)]
+                    self._tc(p, f"attn_qk{i}", jobs, B=B, Cin=dk, Cout=Tk, L=T, dtype=dt, tag="attn", flops=2.0 * B * H * T * T)
+                    p.add(f"attn_sm{i}", lib.rvc_attn_softmax, Sb.data_ptr(), qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(),
+                          W[f"ev{i}"].data_ptr(), Pb.data_ptr(), Rb.data_ptr(), vwb.data_ptr(), B, H, nh, T, Tk, WINDOW,
+                          bytes_=B * nh * Tk * T * 10.0, kind="attn_softmax")
+                    # O = P . v + R, written straight into the packed input of conv_o
+                    jobs = [dict(a=Pb.data_ptr() + h * (Tk // 8) * Lp * 16, a_bs=nh * (Tk // 8) * Lp * 16,
+                                 w=vwb.data_ptr() + h * (Tk // 8) * dk * 16, w_bs=nh * (Tk // 8) * dk * 16,
+                                 res=V(Rb, H, T, h * dk), y_act=atta.data_ptr() + (h * dk // 8) * Lp * 16, y_act_bs=(H // 8) * Lp * 16)
+                            for h in range(nh)]
+                    self._tc(p, f"attn_pv{i}", jobs, B=B, Cin=Tk, Cout=dk, L=T, dtype=dt, tag="attn", flops=2.0 * B * H * T * T)
+                else:
+                    p.add(f"attn{i}", lib.rvc_rel_attention_f32, qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(), W[f"ev{i}"].data_ptr(),
+                          att.data_ptr(), B, H, nh, T, WINDOW, flops=4.0 * B * H * T * T, bytes_=16.0 * B * H * T, kind="rel_attention_f32")
+                    p.add(f"pack_att{i}", lib.rvc_pack_act, att.data_ptr(), None, None, 1.0, H * T, T, None, atta.data_ptr(), B, H, T, dt, 1.0,
+                          kind="pack_act", bytes_=6.0 * B * H * T)
                 self._tc(p, f"attn_o{i}", [dict(a=atta, w=W[f"t_o_w{i}"], bias=W[f"o_b{i}"], y=vy)], B=B, Cin=H, Cout=H, L=T, dtype=dt, tag="enc")
                 p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
                       p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0, xa.data_ptr(), dt, kind="layernorm_f32", bytes_=14.0 * B * H * T)
