@@ -10,9 +10,9 @@
 // sequence live in the global buffer, so there is no boundary logic) and reused by every tap.  Weights, pre-packed
 // [K][Cin/8][Cout][8], stream through a 4-slot ring.
 //
-// Warp roles (224 threads): warp 0 = activation producer, warp 6 = weight producer, warp 1 = MMA issuer (+TMEM owner),
-// warps 2-5 = epilogue (TMEM -> registers -> bias / gate / relu / residual / mask -> fp32 NCL and packed-DT stores, all
-// coalesced along positions).  Accumulators are double-buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile
+// Warp roles (384 threads): warp 0 = activation producer, warp 2 = weight producer, warp 1 = MMA issuer (+TMEM owner),
+// warps 4-11 = epilogue, two warpgroups (TMEM -> registers -> bias / gate / relu / residual / mask -> fp32 NCL and packed-DT
+// stores, all coalesced along positions).  Accumulators are double-buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile
 // t+1; CTAs are persistent over a static round-robin tile list spanning up to three independent jobs (the three ResBlocks
 // of a generator stage, or the res/skip halves of a WaveNet layer).
 #include "common.cuh"
@@ -27,7 +27,7 @@ constexpr int PADR = 64;
 constexpr int ROWQ = 256;        // packed row count is rounded up to this
 constexpr int NSTAGE = 4;        // weight ring slots
 constexpr int STAGE_BYTES = 16384;
-constexpr int NTHREADS = 224;
+constexpr int NTHREADS = 384;      // 12 warps: A producer, MMA issuer, W producer, (idle), 8 epilogue warps
 constexpr int MAXJOBS = 3;
 
 __host__ __device__ inline int packed_rows(int L) { return PADL + ((L + ROWQ - 1) / ROWQ) * ROWQ + PADR; }
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(W_FULL(s), 1); tc::mbar_init(W_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(A_FULL(s), 1); tc::mbar_init(A_EMPTY(s), 1);
-            tc::mbar_init(ACC_FULL(s), 1); tc::mbar_init(ACC_EMPTY(s), 4);
+            tc::mbar_init(ACC_FULL(s), 1); tc::mbar_init(ACC_EMPTY(s), 8);
         }
         tc::fence_barrier_init();
     }
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 if (++ast == 2) { ast = 0; aph ^= 1; }
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 2) {
         // ======================= weight producer =======================
         uint32_t wst = 0, wph = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -144,23 +144,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             for (int cs = 0; cs < p.ncs; ++cs) {
                 const int ca = cs * p.ach;
                 const int na = min(p.ach, p.nch - ca);
-                for (int tap = 0; tap < jb.K; ++tap) {
-                    for (int c0 = 0; c0 < na; c0 += SCH) {
-                        const int nc = min(SCH, na - c0);
-                        if (lane == 0) {
-                            tc::mbar_wait(W_EMPTY(wst), wph ^ 1);
-                            tc::mbar_arrive_expect_tx(W_FULL(wst), (uint32_t)nc * NT * 16);
-                        }
-                        __syncwarp();
-                        const uint32_t dst = tc::smem_u32(w_smem + wst * STAGE_BYTES);
-                        const uint8_t* src = wsrc + (((size_t)tap * p.nch + ca + c0) * w_cs + (size_t)nt * NT) * 16;
-                        if (NT == p.Cout && w_cs == (size_t)p.Cout) {
-                            if (lane == 0) tc::bulk_g2s(dst, src, (uint32_t)nc * NT * 16, W_FULL(wst));
-                        } else {
-                            for (int c = lane; c < nc; c += 32) tc::bulk_g2s(dst + c * NT * 16, src + (size_t)c * w_cs * 16, NT * 16, W_FULL(wst));
-                        }
-                        if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
+                // flat unit index f = tap * na + chunk; a ring slot holds SCH consecutive units (several taps when C is small)
+                const int nflat = jb.K * na;
+                const bool contiguous = (NT == p.Cout) && (w_cs == (size_t)p.Cout) && (na == p.nch);
+                for (int f0 = 0; f0 < nflat; f0 += SCH) {
+                    const int nu = min(SCH, nflat - f0);
+                    if (lane == 0) {
+                        tc::mbar_wait(W_EMPTY(wst), wph ^ 1);
+                        tc::mbar_arrive_expect_tx(W_FULL(wst), (uint32_t)nu * NT * 16);
                     }
+                    __syncwarp();
+                    const uint32_t dst = tc::smem_u32(w_smem + wst * STAGE_BYTES);
+                    if (contiguous) {
+                        if (lane == 0) tc::bulk_g2s(dst, wsrc + (size_t)f0 * NT * 16, (uint32_t)nu * NT * 16, W_FULL(wst));
+                    } else {
+                        for (int u = lane; u < nu; u += 32) {
+                            const int f = f0 + u, tap = f / na, ch = f - tap * na;
+                            tc::bulk_g2s(dst + u * NT * 16, wsrc + (((size_t)tap * p.nch + ca + ch) * w_cs + (size_t)nt * NT) * 16, NT * 16, W_FULL(wst));
+                        }
+                    }
+                    if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                 }
             }
         }
@@ -184,25 +187,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     tc::mbar_wait(A_FULL(ast), aph);
                     tc::fence_after_sync();
                     const uint32_t a_base = tc::smem_u32(a_smem + (size_t)ast * a_bytes);
-                    for (int tap = 0; tap < jb.K; ++tap) {
-                        for (int c0 = 0; c0 < na; c0 += SCH) {
-                            const int nc = min(SCH, na - c0);
-                            tc::mbar_wait(W_FULL(wst), wph);
-                            tc::fence_after_sync();
-                            const uint32_t w_base = tc::smem_u32(w_smem + wst * STAGE_BYTES);
+                    const int nflat = jb.K * na;
+                    for (int f0 = 0; f0 < nflat; f0 += SCH) {
+                        const int nu = min(SCH, nflat - f0);
+                        tc::mbar_wait(W_FULL(wst), wph);
+                        tc::fence_after_sync();
+                        const uint32_t w_base = tc::smem_u32(w_smem + wst * STAGE_BYTES);
 #pragma unroll
-                            for (int m = 0; m < MT; ++m) {
-                                const uint32_t d_tmem = tmem_base + (uint32_t)((g * MT + m) * NT);
-                                for (int kk = 0; kk < nc; kk += 2) {
-                                    const uint32_t a_addr = a_base + (uint32_t)((c0 + kk) * p.rows_max + m * BM + tap * jb.dil) * 16;
-                                    const uint32_t b_addr = w_base + (uint32_t)(kk * NT) * 16;
-                                    tc::umma<false>(d_tmem, tc::make_desc(a_addr, lbo_a, 128), tc::make_desc(b_addr, lbo_b, 128), idesc,
-                                                    (cs | tap | c0 | kk) != 0);
-                                }
+                        for (int m = 0; m < MT; ++m) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((g * MT + m) * NT);
+                            int tap = f0 / na, ch = f0 - tap * na;
+                            for (int u = 0; u < nu; u += 2) {
+                                const uint32_t a_addr = a_base + (uint32_t)(ch * p.rows_max + m * BM + tap * jb.dil) * 16;
+                                const uint32_t b_addr = w_base + (uint32_t)(u * NT) * 16;
+                                tc::umma<false>(d_tmem, tc::make_desc(a_addr, lbo_a, 128), tc::make_desc(b_addr, lbo_b, 128), idesc,
+                                                (cs | f0 | u) != 0);
+                                ch += 2;
+                                if (ch >= na) { ch = 0; ++tap; }
                             }
-                            tc::umma_commit(W_EMPTY(wst));
-                            if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                         }
+                        tc::umma_commit(W_EMPTY(wst));
+                        if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                     }
                     tc::umma_commit(A_EMPTY(ast));
                     if (++ast == 2) { ast = 0; aph ^= 1; }
@@ -210,9 +215,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 tc::umma_commit(ACC_FULL(g));
             }
         }
-    } else {
-        // ======================= epilogue: 4 warps, warp%4 selects the TMEM lane quarter =======================
+    } else if (warp >= 4) {
+        // ======================= epilogue: 2 warpgroups x 4 warps; warp%4 selects the TMEM lane quarter, the warpgroup
+        // takes every other (sub-tile, 32-column block) work item =======================
         const int q = warp & 3;
+        const int eg = (warp - 4) >> 2;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             int j, b, lt, nt, ph;
@@ -221,81 +228,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             const int g = it & 1;
             const uint32_t gph = (it >> 1) & 1;
             const float* bb = jb.bias_b ? jb.bias_b + (size_t)b * jb.bias_b_bs : nullptr;
+            constexpr int NBLK = NT / 32;
+            const int nblk = jb.gated ? NBLK / 2 : NBLK;
             tc::mbar_wait(ACC_FULL(g), gph);
             tc::fence_after_sync();
 #pragma unroll 1
-            for (int m = 0; m < MT; ++m) {
+            for (int item = eg; item < MT * nblk; item += 2) {
+                const int m = item / nblk, cb = item - m * nblk;
                 const int lin = lt * TM + m * BM + q * 32 + lane;
                 const int l = lin * p.up + ph - p.pshift;          // output position
                 const bool ok = lin < p.L && l >= 0 && l < p.Lout;
-                const float mk = (jb.mask && ok) ? jb.mask[(size_t)b * p.Lout + l] : 1.f;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * MT + m) * NT);
-                constexpr int NBLK = NT / 32;
-                const int nblk = jb.gated ? NBLK / 2 : NBLK;
-#pragma unroll 1
-                for (int cb = 0; cb < nblk; ++cb) {
-                    uint32_t r[32];
-                    float v[32];
-                    tc::tmem_ld32(t_row + cb * 32, r);
+                const int col0 = nt * NT + cb * 32;               // weight-column index (bias order)
+                const int co0 = jb.gated ? nt * (NT / 2) + cb * 32 : col0;   // output-channel index
+                uint32_t r[32];
+                float v[32];
+                // residual loads first: they do not depend on the accumulator and overlap the TMEM read
+                if (jb.res && ok) {
+                    const float* rp = jb.res + (size_t)b * jb.res_bs + (size_t)co0 * jb.res_cs + l;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = rp[(size_t)i * jb.res_cs];
+                }
+                const float mk = (jb.mask && ok) ? jb.mask[(size_t)b * p.Lout + l] : 1.f;
+                tc::tmem_ld32(t_row + cb * 32, r);
+                tc::tmem_ld_wait();
+                if (jb.gated) {
+                    uint32_t r2[32];
+                    tc::tmem_ld32(t_row + (cb + NBLK / 2) * 32, r2);
                     tc::tmem_ld_wait();
-                    const int col0 = nt * NT + cb * 32;       // weight-column index (bias order)
-                    int co0;                                  // output-channel index
-                    if (jb.gated) {
-                        uint32_t r2[32];
-                        tc::tmem_ld32(t_row + (cb + NBLK / 2) * 32, r2);
-                        tc::tmem_ld_wait();
-                        const int col1 = col0 + (NBLK / 2) * 32;
+                    const int col1 = col0 + (NBLK / 2) * 32;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float t = __uint_as_float(r[i]) + __ldg(jb.bias + col0 + i);
-                            float s = __uint_as_float(r2[i]) + __ldg(jb.bias + col1 + i);
-                            if (bb) { t += __ldg(bb + col0 + i); s += __ldg(bb + col1 + i); }
-                            v[i] = tanhf(t) * rvc::sigmoidf_acc(s);
-                        }
-                        co0 = nt * (NT / 2) + cb * 32;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            v[i] = __uint_as_float(r[i]) + (jb.bias ? __ldg(jb.bias + col0 + i) : 0.f);
-                            if (bb) v[i] += __ldg(bb + col0 + i);
-                        }
-                        co0 = col0;
+                    for (int i = 0; i < 32; ++i) {
+                        float t = __uint_as_float(r[i]) + __ldg(jb.bias + col0 + i);
+                        float sg = __uint_as_float(r2[i]) + __ldg(jb.bias + col1 + i);
+                        if (bb) { t += __ldg(bb + col0 + i); sg += __ldg(bb + col1 + i); }
+                        r[i] = __float_as_uint(tanhf(t) * rvc::sigmoidf_acc(sg));
                     }
-                    if (!ok) continue;
-                    if (jb.relu) {
+                } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    for (int i = 0; i < 32; ++i) {
+                        float t = __uint_as_float(r[i]) + (jb.bias ? __ldg(jb.bias + col0 + i) : 0.f);
+                        if (bb) t += __ldg(bb + col0 + i);
+                        r[i] = __float_as_uint(t);
                     }
-                    if (jb.res) {
-                        const float* rp = jb.res + (size_t)b * jb.res_bs + (size_t)co0 * jb.res_cs + l;
+                }
+                if (!ok) continue;
+                if (jb.relu) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = rp[(size_t)i * jb.res_cs] + jb.alpha * v[i];
-                } else if (jb.alpha != 1.f) {
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
+                }
+                if (jb.res) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= jb.alpha;
-                    }
-                    if (jb.mask) {
+                    for (int i = 0; i < 32; ++i) v[i] = v[i] + jb.alpha * __uint_as_float(r[i]);
+                } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] *= mk;
-                    }
-                    if (jb.y_f32) {
-                        float* yp = jb.y_f32 + (size_t)b * jb.y_bs + (size_t)co0 * jb.y_cs + l;
+                    for (int i = 0; i < 32; ++i) v[i] = jb.alpha * __uint_as_float(r[i]);
+                }
+                if (jb.mask) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) yp[(size_t)i * jb.y_cs] = v[i];
-                    }
-                    if (jb.y_act) {
-                        const size_t ya_bs = jb.y_act_bs ? (size_t)jb.y_act_bs : (size_t)p.nch_out * p.Lp_out * 16;
-                        uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (size_t)b * ya_bs + (((size_t)co0 / 8) * p.Lp_out + PADL + l) * 16;
-                        const float sl = jb.act_slope;
+                    for (int i = 0; i < 32; ++i) v[i] *= mk;
+                }
+                if (jb.y_f32) {
+                    float* yp = jb.y_f32 + (size_t)b * jb.y_bs + (size_t)co0 * jb.y_cs + l;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            uint4 pk;
-                            pk.x = pack2(rvc::lrelu(v[8 * u + 0], sl), rvc::lrelu(v[8 * u + 1], sl), p.fp16);
-                            pk.y = pack2(rvc::lrelu(v[8 * u + 2], sl), rvc::lrelu(v[8 * u + 3], sl), p.fp16);
-                            pk.z = pack2(rvc::lrelu(v[8 * u + 4], sl), rvc::lrelu(v[8 * u + 5], sl), p.fp16);
-                            pk.w = pack2(rvc::lrelu(v[8 * u + 6], sl), rvc::lrelu(v[8 * u + 7], sl), p.fp16);
-                            *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp_out * 16) = pk;
-                        }
+                    for (int i = 0; i < 32; ++i) yp[(size_t)i * jb.y_cs] = v[i];
+                }
+                if (jb.y_act) {
+                    const size_t ya_bs = jb.y_act_bs ? (size_t)jb.y_act_bs : (size_t)p.nch_out * p.Lp_out * 16;
+                    uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (size_t)b * ya_bs + (((size_t)co0 / 8) * p.Lp_out + PADL + l) * 16;
+                    const float sl = jb.act_slope;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 pk;
+                        pk.x = pack2(rvc::lrelu(v[8 * u + 0], sl), rvc::lrelu(v[8 * u + 1], sl), p.fp16);
+                        pk.y = pack2(rvc::lrelu(v[8 * u + 2], sl), rvc::lrelu(v[8 * u + 3], sl), p.fp16);
+                        pk.z = pack2(rvc::lrelu(v[8 * u + 4], sl), rvc::lrelu(v[8 * u + 5], sl), p.fp16);
+                        pk.w = pack2(rvc::lrelu(v[8 * u + 6], sl), rvc::lrelu(v[8 * u + 7], sl), p.fp16);
+                        *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp_out * 16) = pk;
                     }
                 }
             }
