@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 10
+#define RVC_ABI_VERSION 11
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -119,6 +119,10 @@ int rvc_layernorm_f32(const float* x, const float* r, const float* gamma, const 
  */
 int rvc_rel_attention_f32(const float* qkv, const float* mask, const float* emb_k, const float* emb_v, float* out,
                           int32_t B, int32_t H, int32_t n_heads, int32_t T, int32_t window, void* stream);
+
+/* Speaker conditioning on a length-1 sequence (modules.py:39 cond_layer(g), synthesizers.py:147 cond(g)):
+ * y[b][co] = bias[co] + sum_ci w[ci][co] * x[b][ci], w packed [Cin][Cout]. */
+int rvc_cond_gemv_f32(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Cout, void* stream);
 
 /* z_p = (m + exp(logs) * eps * 0.66666) * mask, stats = [B, 2*C, T] (m rows then logs rows) — synthesizers.py:449. */
 int rvc_sample_zp_f32(const float* stats, const float* eps, const float* mask, float* zp, int32_t B, int32_t C, int32_t T,

@@ -29,6 +29,8 @@ constexpr int NSTAGE = 4;        // weight ring slots
 constexpr int STAGE_BYTES = 16384;
 constexpr int NTHREADS = 384;      // 12 warps: A producer, MMA issuer, W producer, (idle), 8 epilogue warps
 constexpr int MAXJOBS = 3;
+constexpr int MAXABUF = 8;        // activation ring slots (as many as fit next to the weight ring)
+constexpr int MAXNG = 4;          // TMEM accumulator groups
 
 __host__ __device__ inline int packed_rows(int L) { return PADL + ((L + ROWQ - 1) / ROWQ) * ROWQ + PADR; }
 
@@ -43,6 +45,7 @@ struct Params {
     int n_lt, n_nt;   // tiles along L and along Cout
     int tiles_per_job, total_tiles;
     int fp16;         // operand format: 0 = bf16, 1 = fp16
+    int nabuf;        // activation ring depth (2..MAXABUF)
     int up, pshift;   // transposed-conv phase mode: output position = l * up + phase - pshift (up = 1: plain conv)
     int Lout, Lp_out; // output length and packed rows of the output
 };
@@ -61,32 +64,32 @@ template <int NT, int MT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) {
     constexpr int TM = BM * MT;
     constexpr int SCH = (STAGE_BYTES / (NT * 16)) & ~1;    // 16-byte chunks per weight stage (even)
-    constexpr int ACC_COLS = 2 * MT * NT;                   // two accumulator groups
+    constexpr int NG = (512 / (MT * NT)) >= MAXNG ? MAXNG : (512 / (MT * NT));   // accumulator groups (>= 2)
+    static_assert(NG >= 2, "need at least two accumulator groups");
+    constexpr int ACC_COLS = NG * MT * NT;
     constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
     static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t a_bytes = (uint32_t)p.ach * p.rows_max * 16;
-    uint8_t* a_smem = smem;                                         // [2][ach][rows_max][16]
-    uint8_t* w_smem = smem + 2 * (size_t)a_bytes;                   // [NSTAGE][STAGE_BYTES]
+    uint8_t* a_smem = smem;                                         // [nabuf][ach][rows_max][16]
+    uint8_t* w_smem = smem + (size_t)p.nabuf * a_bytes;             // [NSTAGE][STAGE_BYTES]
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + NSTAGE * STAGE_BYTES);
     const uint32_t bar0 = tc::smem_u32(bars);
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
     auto W_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
     auto A_FULL = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
-    auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 + s); };
-    auto ACC_FULL = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 4 + s); };
-    auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 6 + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 8);
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + MAXABUF + s); };
+    auto ACC_FULL = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * MAXABUF + s); };
+    auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * MAXABUF + MAXNG + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * MAXABUF + 2 * MAXNG);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(W_FULL(s), 1); tc::mbar_init(W_EMPTY(s), 1); }
-        for (int s = 0; s < 2; ++s) {
-            tc::mbar_init(A_FULL(s), 1); tc::mbar_init(A_EMPTY(s), 1);
-            tc::mbar_init(ACC_FULL(s), 1); tc::mbar_init(ACC_EMPTY(s), 8);
-        }
+        for (int s = 0; s < MAXABUF; ++s) { tc::mbar_init(A_FULL(s), 1); tc::mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < MAXNG; ++s) { tc::mbar_init(ACC_FULL(s), 1); tc::mbar_init(ACC_EMPTY(s), 8); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 for (int c = lane; c < nc; c += 32)
                     tc::bulk_g2s(tc::smem_u32(a_smem + (size_t)ast * a_bytes + (size_t)c * p.rows_max * 16), asrc + (size_t)c * p.Lp * 16,
                                  (uint32_t)rows * 16, A_FULL(ast));
-                if (++ast == 2) { ast = 0; aph ^= 1; }
+                if (++ast == (uint32_t)p.nabuf) { ast = 0; aph ^= 1; }
             }
         }
     } else if (warp == 2) {
@@ -178,8 +181,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 int j, b, lt, nt, ph;
                 decode(tile, j, b, lt, nt, ph);
                 const rvc_tc_job& jb = p.jobs[j];
-                const int g = it & 1;
-                const uint32_t gph = (it >> 1) & 1;
+                const int g = it % NG;
+                const uint32_t gph = (it / NG) & 1;
                 tc::mbar_wait(ACC_EMPTY(g), gph ^ 1);
                 tc::fence_after_sync();
                 for (int cs = 0; cs < p.ncs; ++cs) {
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                         if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                     }
                     tc::umma_commit(A_EMPTY(ast));
-                    if (++ast == 2) { ast = 0; aph ^= 1; }
+                    if (++ast == (uint32_t)p.nabuf) { ast = 0; aph ^= 1; }
                 }
                 tc::umma_commit(ACC_FULL(g));
             }
@@ -225,8 +228,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             int j, b, lt, nt, ph;
             decode(tile, j, b, lt, nt, ph);
             const rvc_tc_job& jb = p.jobs[j];
-            const int g = it & 1;
-            const uint32_t gph = (it >> 1) & 1;
+            const int g = it % NG;
+            const uint32_t gph = (it / NG) & 1;
             const float* bb = jb.bias_b ? jb.bias_b + (size_t)b * jb.bias_b_bs : nullptr;
             constexpr int NBLK = NT / 32;
             const int nblk = jb.gated ? NBLK / 2 : NBLK;
@@ -462,7 +465,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     p.tiles_per_job = d.B * p.n_lt * p.n_nt * up;
     p.total_tiles = p.tiles_per_job * d.njobs;
     p.fp16 = d.dtype == RVC_DT_FP16;
-    const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 256;
+    const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512;
     const size_t limit = 227 * 1024;
     // activation stage: as many channel chunks as fit twice (double buffer); even count
     int ach = p.nch;
@@ -470,7 +473,11 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     if (2 * (size_t)ach * p.rows_max * 16 + fixed > limit) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: activation stage does not fit shared memory");
     p.ach = ach;
     p.ncs = rvc::cdiv(p.nch, ach);
-    const size_t smem = 2 * (size_t)ach * p.rows_max * 16 + fixed;
+    const size_t a_stage = (size_t)ach * p.rows_max * 16;
+    int nabuf = (int)((limit - fixed) / a_stage);
+    nabuf = nabuf > MAXABUF ? MAXABUF : nabuf;
+    p.nabuf = nabuf;
+    const size_t smem = (size_t)nabuf * a_stage + fixed;
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     cudaStream_t st = (cudaStream_t)stream;
     if (NT == 128) return launch_tc_mt<128>(mt, p, smem, grid, st);

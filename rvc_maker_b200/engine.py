@@ -442,7 +442,8 @@ class Engine:
         hb, acts, outb = self._buf(p, B, H, T), self._buf(p, B, H, T), self._buf(p, B, H, T)
         vh, va, vo = V(hb, H, T), V(acts, H, T), V(outb, H, T)
         # speaker conditioning: cond_layer(g) x4 + dec.cond(g) in one launch (modules.py:39, synthesizers.py:147)
-        self._conv(p, "cond", V(p.g, G, 1), W["cond_w"], V(gc, self.cond_total, 1), B=B, Cin=G, Cout=self.cond_total, L=1, bias=W["cond_b"])
+        p.add("cond", lib.rvc_cond_gemv_f32, p.g.data_ptr(), W["cond_w"].data_ptr(), W["cond_b"].data_ptr(), gc.data_ptr(), B, G, self.cond_total,
+              flops=2.0 * B * G * self.cond_total, bytes_=4.0 * G * self.cond_total, kind="cond_gemv_f32")
         p.add_py(lambda: p.z.copy_(p.zp))
         for f in ((3, 2, 1, 0) if self.enc_tc else ()):
             dt = DT_FP16
