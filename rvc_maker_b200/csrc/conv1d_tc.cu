@@ -10,7 +10,8 @@
 // sequence live in the global buffer, so there is no boundary logic) and reused by every tap.  Weights, pre-packed
 // [K][Cin/8][Cout][8], stream through a 4-slot ring.
 //
-// Warp roles (384 threads): warp 0 = activation producer, warp 2 = weight producer, warp 1 = MMA issuer (+TMEM owner),
+// Warp roles (384 threads): warp 0 = activation producer, warp 2 = weight producer, warps 1 and 3 = MMA issuers (one per
+// 128-position sub-tile; warp 1 also owns the TMEM allocation),
 // warps 4-11 = epilogue, two warpgroups (TMEM -> registers -> bias / gate / relu / residual / mask -> fp32 NCL and packed-DT
 // stores, all coalesced along positions).  Accumulators are double-buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile
 // t+1; CTAs are persistent over a static round-robin tile list spanning up to three independent jobs (the three ResBlocks
@@ -84,12 +85,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * MAXABUF + MAXNG + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * MAXABUF + 2 * MAXNG);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+    const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(W_FULL(s), 1); tc::mbar_init(W_EMPTY(s), 1); }
-        for (int s = 0; s < MAXABUF; ++s) { tc::mbar_init(A_FULL(s), 1); tc::mbar_init(A_EMPTY(s), 1); }
-        for (int s = 0; s < MAXNG; ++s) { tc::mbar_init(ACC_FULL(s), 1); tc::mbar_init(ACC_EMPTY(s), 8); }
+        // one MMA issuer warp per sub-tile: every "consumed" barrier collects MT commits
+        for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(W_FULL(s), 1); tc::mbar_init(W_EMPTY(s), MT); }
+        for (int s = 0; s < MAXABUF; ++s) { tc::mbar_init(A_FULL(s), 1); tc::mbar_init(A_EMPTY(s), MT); }
+        for (int s = 0; s < MAXNG; ++s) { tc::mbar_init(ACC_FULL(s), MT); tc::mbar_init(ACC_EMPTY(s), 8); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
@@ -170,53 +173,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 }
             }
         }
-    } else if (warp == 1) {
-        // ======================= MMA issuer (single thread) =======================
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc(p.fp16 ? 0u : 1u, NT);
-            uint32_t wst = 0, wph = 0, ast = 0, aph = 0;
-            int it = 0;
-            const uint32_t lbo_a = (uint32_t)p.rows_max * 16, lbo_b = NT * 16;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                int j, b, lt, nt, ph;
-                decode(tile, j, b, lt, nt, ph);
-                const rvc_tc_job& jb = p.jobs[j];
-                const int g = it % NG;
-                const uint32_t gph = (it / NG) & 1;
-                tc::mbar_wait(ACC_EMPTY(g), gph ^ 1);
+    } else if (warp == 1 || (MT == 2 && warp == 3)) {
+        // ======================= MMA issuers: warp 1 -> sub-tile 0, warp 3 -> sub-tile 1.  The whole warp runs the (uniform)
+        // loop so that descriptors live in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.
+        // Descriptors are updated incrementally: +2*rows_max (16-B units) per k-step, +dil per tap for A; +2*NT for W. =====
+        const int m = (warp == 1) ? 0 : 1;
+        const uint32_t idesc = tc::make_idesc(p.fp16 ? 0u : 1u, NT);
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                  // SBO = 128 B, descriptor version 1, no swizzle
+        const uint32_t a_lo_hi = ((uint32_t)p.rows_max & 0x3FFFu) << 16;   // LBO(A) = rows_max * 16 B
+        const uint32_t b_lo_hi = ((uint32_t)NT & 0x3FFFu) << 16;           // LBO(W) = NT * 16 B
+        const uint32_t rows2 = 2u * (uint32_t)p.rows_max;
+        uint32_t wst = 0, wph = 0, ast = 0, aph = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            int j, b, lt, nt, ph;
+            decode(tile, j, b, lt, nt, ph);
+            const int K = p.jobs[j].K;
+            const uint32_t dil = (uint32_t)p.jobs[j].dil;
+            const int g = it % NG;
+            const uint32_t gph = (it / NG) & 1;
+            tc::mbar_wait(ACC_EMPTY(g), gph ^ 1);
+            tc::fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)((g * MT + m) * NT);
+            uint32_t accumulate = 0;
+            for (int cs = 0; cs < p.ncs; ++cs) {
+                const int na = min(p.ach, p.nch - cs * p.ach);
+                tc::mbar_wait(A_FULL(ast), aph);
                 tc::fence_after_sync();
-                for (int cs = 0; cs < p.ncs; ++cs) {
-                    const int na = min(p.ach, p.nch - cs * p.ach);
-                    tc::mbar_wait(A_FULL(ast), aph);
+                const uint32_t a_base16 = (tc::smem_u32(a_smem + (size_t)ast * a_bytes) >> 4) + (uint32_t)(m * BM);
+                const int nflat = K * na;
+                int ch = 0;
+                uint32_t tap_off = 0, a_off = 0;       // a_off = ch * rows_max + tap * dil, in 16-byte rows
+                for (int f0 = 0; f0 < nflat; f0 += SCH) {
+                    const int nu = min(SCH, nflat - f0);
+                    tc::mbar_wait(W_FULL(wst), wph);
                     tc::fence_after_sync();
-                    const uint32_t a_base = tc::smem_u32(a_smem + (size_t)ast * a_bytes);
-                    const int nflat = jb.K * na;
-                    for (int f0 = 0; f0 < nflat; f0 += SCH) {
-                        const int nu = min(SCH, nflat - f0);
-                        tc::mbar_wait(W_FULL(wst), wph);
-                        tc::fence_after_sync();
-                        const uint32_t w_base = tc::smem_u32(w_smem + wst * STAGE_BYTES);
-#pragma unroll
-                        for (int m = 0; m < MT; ++m) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((g * MT + m) * NT);
-                            int tap = f0 / na, ch = f0 - tap * na;
-                            for (int u = 0; u < nu; u += 2) {
-                                const uint32_t a_addr = a_base + (uint32_t)(ch * p.rows_max + m * BM + tap * jb.dil) * 16;
-                                const uint32_t b_addr = w_base + (uint32_t)(u * NT) * 16;
-                                tc::umma<false>(d_tmem, tc::make_desc(a_addr, lbo_a, 128), tc::make_desc(b_addr, lbo_b, 128), idesc,
-                                                (cs | f0 | u) != 0);
-                                ch += 2;
-                                if (ch >= na) { ch = 0; ++tap; }
-                            }
-                        }
-                        tc::umma_commit(W_EMPTY(wst));
-                        if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
+                    uint32_t b16 = tc::smem_u32(w_smem + wst * STAGE_BYTES) >> 4;
+                    for (int u = 0; u < nu; u += 2) {
+                        const uint64_t da = ((uint64_t)desc_hi << 32) | (a_lo_hi | ((a_base16 + a_off) & 0x3FFFu));
+                        const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo_hi | (b16 & 0x3FFFu));
+                        if (tc::elect_one()) tc::umma<false>(d_tmem, da, db, idesc, accumulate);
+                        accumulate = 1;
+                        b16 += 2u * NT;
+                        ch += 2;
+                        a_off += rows2;
+                        if (ch >= na) { ch = 0; tap_off += dil; a_off = tap_off; }
                     }
-                    tc::umma_commit(A_EMPTY(ast));
-                    if (++ast == (uint32_t)p.nabuf) { ast = 0; aph ^= 1; }
+                    if (tc::elect_one()) tc::umma_commit(W_EMPTY(wst));
+                    if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                 }
-                tc::umma_commit(ACC_FULL(g));
+                if (tc::elect_one()) tc::umma_commit(A_EMPTY(ast));
+                if (++ast == (uint32_t)p.nabuf) { ast = 0; aph ^= 1; }
             }
+            if (tc::elect_one()) tc::umma_commit(ACC_FULL(g));
         }
     } else if (warp >= 4) {
         // ======================= epilogue: 2 warpgroups x 4 warps; warp%4 selects the TMEM lane quarter, the warpgroup
