@@ -47,6 +47,7 @@ struct Params {
     int tiles_per_job, total_tiles;
     int fp16;         // operand format: 0 = bf16, 1 = fp16
     int nabuf;        // activation ring depth (2..MAXABUF)
+    int dbg;          // timing experiments only: 1 = epilogue skips global I/O, 2 = skip MMA issue, 4 = skip operand loads
     int up, pshift;   // transposed-conv phase mode: output position = l * up + phase - pshift (up = 1: plain conv)
     int Lout, Lp_out; // output length and packed rows of the output
 };
@@ -126,9 +127,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 const int nc = min(p.ach, p.nch - c0);
                 if (lane == 0) {
                     tc::mbar_wait(A_EMPTY(ast), aph ^ 1);
-                    tc::mbar_arrive_expect_tx(A_FULL(ast), (uint32_t)nc * rows * 16);
+                    if (p.dbg & 4) tc::mbar_arrive(A_FULL(ast));
+                    else tc::mbar_arrive_expect_tx(A_FULL(ast), (uint32_t)nc * rows * 16);
                 }
                 __syncwarp();
+                if (p.dbg & 4) { if (++ast == (uint32_t)p.nabuf) { ast = 0; aph ^= 1; } continue; }
                 const size_t a_bs = jb.a_bs ? (size_t)jb.a_bs : (size_t)p.nch * p.Lp * 16;
                 const uint8_t* asrc = reinterpret_cast<const uint8_t*>(jb.a) + (size_t)b * a_bs +
                                       ((size_t)c0 * p.Lp + (size_t)(PADL + lt * TM - pad)) * 16;
@@ -157,9 +160,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     const int nu = min(SCH, nflat - f0);
                     if (lane == 0) {
                         tc::mbar_wait(W_EMPTY(wst), wph ^ 1);
-                        tc::mbar_arrive_expect_tx(W_FULL(wst), (uint32_t)nu * NT * 16);
+                        if (p.dbg & 4) tc::mbar_arrive(W_FULL(wst));
+                        else tc::mbar_arrive_expect_tx(W_FULL(wst), (uint32_t)nu * NT * 16);
                     }
                     __syncwarp();
+                    if (p.dbg & 4) { if (++wst == NSTAGE) { wst = 0; wph ^= 1; } continue; }
                     const uint32_t dst = tc::smem_u32(w_smem + wst * STAGE_BYTES);
                     if (contiguous) {
                         if (lane == 0) tc::bulk_g2s(dst, wsrc + (size_t)f0 * NT * 16, (uint32_t)nu * NT * 16, W_FULL(wst));
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     for (int u = 0; u < nu; u += 2) {
                         const uint64_t da = ((uint64_t)desc_hi << 32) | (a_lo_hi | ((a_base16 + a_off) & 0x3FFFu));
                         const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo_hi | (b16 & 0x3FFFu));
-                        if (tc::elect_one()) tc::umma<false>(d_tmem, da, db, idesc, accumulate);
+                        if (!(p.dbg & 2) && tc::elect_one()) tc::umma<false>(d_tmem, da, db, idesc, accumulate);
                         accumulate = 1;
                         b16 += 2u * NT;
                         ch += 2;
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 const int m = item / nblk, cb = item - m * nblk;
                 const int lin = lt * TM + m * BM + q * 32 + lane;
                 const int l = lin * p.up + ph - p.pshift;          // output position
-                const bool ok = lin < p.L && l >= 0 && l < p.Lout;
+                const bool ok = lin < p.L && l >= 0 && l < p.Lout && !(p.dbg & 1);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * MT + m) * NT);
                 const int col0 = nt * NT + cb * 32;               // weight-column index (bias order)
                 const int co0 = jb.gated ? nt * (NT / 2) + cb * 32 : col0;   // output-channel index
@@ -474,6 +479,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     p.tiles_per_job = d.B * p.n_lt * p.n_nt * up;
     p.total_tiles = p.tiles_per_job * d.njobs;
     p.fp16 = d.dtype == RVC_DT_FP16;
+    p.dbg = d.jobs[0].reserved;
     const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512;
     const size_t limit = 227 * 1024;
     // activation stage: as many channel chunks as fit twice (double buffer); even count

@@ -1,76 +1,61 @@
-// Microbenchmark: tcgen05.mma (M=128, K=16, fp16) cycles per instruction for different shared-memory operand layouts.
-// Operands are whatever is in shared memory (values do not matter for timing).   nvcc -arch=sm_100a -O3 -o mma_bench tools/mma_layout_bench.cu
+// Microbenchmark: tcgen05.mma (K=16, fp16, SS mode) cycles per instruction vs. N, M, number of issuing warps and operand layout.
+// Operands are whatever is in shared memory (values do not matter for timing).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mma_bench tools/mma_layout_bench.cu
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../rvc_maker_b200/csrc/tc_common.cuh"
 
-__device__ __forceinline__ uint64_t desc_sw(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
-    const uint32_t lo = ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
-    const uint32_t hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
-    return ((uint64_t)hi << 32) | lo;
-}
+__host__ __device__ constexpr uint32_t idesc_mn(uint32_t m, uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24); }
 
-template <int NT>
-__global__ void __launch_bounds__(128, 1) bench(int variant, int iters, int rows_a, long long* out) {
+// variant 0: interleaved rows@16B (LBO = rows*16, SBO = 128);  1: 128B swizzle (SBO = 1024)
+__global__ void __launch_bounds__(128, 1) bench(int variant, int M, int N, int nissue, int iters, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[2];
     __shared__ uint32_t slot;
-    const int warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { tc::mbar_init(tc::smem_u32(&bar), 1); tc::fence_barrier_init(); }
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    if (threadIdx.x == 0) { tc::mbar_init(tc::smem_u32(&bar[0]), 1); tc::mbar_init(tc::smem_u32(&bar[1]), 1); tc::fence_barrier_init(); }
     if (warp == 0) tc::tmem_alloc(tc::smem_u32(&slot), 512);
     tc::fence_before_sync(); __syncthreads(); tc::fence_after_sync();
     const uint32_t tmem = slot;
-    if (threadIdx.x == 32) {
-        const uint32_t a0 = tc::smem_u32(smem), b0 = a0 + 96 * 1024;
-        const uint32_t idesc = tc::make_idesc(0u, NT);
+    if (warp >= 1 && warp <= nissue) {
+        const int w = warp - 1;
+        const uint32_t a16 = tc::smem_u32(smem) >> 4, b16 = (tc::smem_u32(smem) + 96 * 1024) >> 4;
+        const uint32_t idesc = idesc_mn(M, N);
+        const uint32_t hi = variant == 0 ? ((128u >> 4) | (1u << 14)) : ((1024u >> 4) | (1u << 14) | (2u << 29));
+        const uint32_t lo_hi = variant == 0 ? (306u << 16) : (1u << 16);
+        const uint32_t d = tmem + (uint32_t)(w * 256);
         long long t0 = clock64();
+        uint32_t off = 0;
         for (int i = 0; i < iters; ++i) {
-            const int ks = i & 7;   // 8 k-steps per "tap"
-            const int tap = (i >> 3) % 5;
-            uint64_t da, db;
-            if (variant == 0) {        // interleaved, rows 16 B apart (shift-friendly): LBO = rows*16, SBO = 128
-                da = desc_sw(a0 + (2 * ks * rows_a + tap * 3) * 16, rows_a * 16, 128, 0);
-                db = desc_sw(b0 + (2 * ks * NT) * 16, NT * 16, 128, 0);
-            } else if (variant == 1) { // interleaved canonical dense: K chunks adjacent (LBO = 128), SBO = 256
-                da = desc_sw(a0 + ks * 128 * 32, 128, 256, 0);
-                db = desc_sw(b0 + ks * NT * 32, 128, 256, 0);
-            } else if (variant == 2) { // 128B swizzle, rows of 128 B: SBO = 1024, k-step = +32 B, row shift = +128 B * tap
-                da = desc_sw(a0 + ks * 32 + tap * 3 * 128, 16, 1024, 2);
-                db = desc_sw(b0 + ks * 32, 16, 1024, 2);
-            } else {                   // variant 0 for A, but accumulators alternate between 4 TMEM tiles
-                da = desc_sw(a0 + (2 * ks * rows_a + tap * 3) * 16, rows_a * 16, 128, 0);
-                db = desc_sw(b0 + (2 * ks * NT) * 16, NT * 16, 128, 0);
-            }
-            const uint32_t d = tmem + ((variant == 3) ? (uint32_t)((i & 3) * NT) : 0u);
-            tc::umma<false>(d, da, db, idesc, 1u);
+            const uint64_t da = ((uint64_t)hi << 32) | (lo_hi | ((a16 + off) & 0x3FFFu));
+            const uint64_t db = ((uint64_t)hi << 32) | (lo_hi | ((b16 + off) & 0x3FFFu));
+            if (tc::elect_one()) tc::umma<false>(d, da, db, idesc, 1u);
+            off = (off + 2) & 63;
         }
-        tc::umma_commit(tc::smem_u32(&bar));
-        tc::mbar_wait(tc::smem_u32(&bar), 0);
+        if (tc::elect_one()) tc::umma_commit(tc::smem_u32(&bar[w]));
+        tc::mbar_wait(tc::smem_u32(&bar[w]), 0);
         long long t1 = clock64();
-        if (blockIdx.x == 0) out[0] = t1 - t0;
+        if (blockIdx.x == 0 && threadIdx.x == 32) out[0] = t1 - t0;
     }
     tc::fence_before_sync(); __syncthreads();
     if (warp == 0) { tc::fence_after_sync(); tc::tmem_dealloc(tmem, 512); }
 }
 
-template <int NT> void run(long long* d_out) {
-    cudaFuncSetAttribute(bench<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    const char* names[4] = {"interleave rows@16B (current)", "interleave dense (LBO=128)", "swizzle-128B rows@128B", "current, 4 accumulators"};
-    for (int v = 0; v < 4; ++v) {
-        for (int grid : {1, 148}) {
-            long long h = 0;
-            const int iters = 4000;
-            bench<NT><<<grid, 128, 200 * 1024>>>(v, iters, 306, d_out);
-            cudaError_t e = cudaDeviceSynchronize();
-            cudaMemcpy(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
-            printf("N=%3d  %-32s grid=%3d  %7.1f cycles/MMA  (%s)\n", NT, names[v], grid, (double)h / iters, cudaGetErrorString(e));
-        }
-    }
-}
-
 int main() {
     long long* d_out; cudaMalloc(&d_out, 8);
-    run<32>(d_out); run<64>(d_out); run<128>(d_out); run<256>(d_out);
+    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int iters = 4000;
+    for (int variant = 0; variant < 2; ++variant)
+        for (int M : {128, 64})
+            for (int N : {32, 64, 128, 256})
+                for (int nissue : {1, 2}) {
+                    long long h = 0;
+                    bench<<<148, 128, 200 * 1024>>>(variant, M, N, nissue, iters, d_out);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    cudaMemcpy(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+                    printf("%-12s M=%3d N=%3d issuers=%d  %6.1f cycles per MMA per issuer, %6.1f per MMA overall (%s)\n",
+                           variant ? "swizzle128" : "interleave", M, N, nissue, (double)h / iters, (double)h / iters / nissue, cudaGetErrorString(e));
+                }
     return 0;
 }
