@@ -35,6 +35,20 @@ constexpr int MAXNG = 4;          // TMEM accumulator groups
 
 __host__ __device__ inline int packed_rows(int L) { return PADL + ((L + ROWQ - 1) / ROWQ) * ROWQ + PADR; }
 
+// Granlund-Montgomery division by an invariant (n < 2^31): q = (umulhi(m, n) + n) >> l.  The role loops decode a tile id per
+// iteration; hardware integer division costs the single issuing warp ~130 cycles each (tools/mma_layout_bench.cu).
+struct FastDiv {
+    uint32_t m, l, d;
+    __host__ void init(uint32_t div) {
+        d = div;
+        l = 0;
+        while ((1ull << l) < div) ++l;
+        m = (uint32_t)(((1ull << 32) * ((1ull << l) - div)) / div + 1);
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return (uint32_t)(((uint64_t)__umulhi(m, n) + n) >> l); }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 struct Params {
     rvc_tc_job jobs[MAXJOBS];
     int njobs, B, Cin, Cout, L, Lp;
@@ -45,6 +59,7 @@ struct Params {
     int rows_max;     // rows allocated per chunk in an activation stage (TM + max halo)
     int n_lt, n_nt;   // tiles along L and along Cout
     int tiles_per_job, total_tiles;
+    FastDiv fd_tpj, fd_up, fd_nnt, fd_nlt;
     int fp16;         // operand format: 0 = bf16, 1 = fp16
     int nabuf;        // activation ring depth (2..MAXABUF)
     int dbg;          // timing experiments only: 1 = epilogue skips global I/O, 2 = skip MMA issue, 4 = skip operand loads
@@ -105,12 +120,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     // tile id -> (job, batch, L tile, N tile, phase); phase is the fastest index so that the u phases of one input tile run on
     // neighbouring CTAs at the same time and share the activation tile through L2
     auto decode = [&](int tile, int& j, int& b, int& lt, int& nt, int& ph) {
-        j = tile / p.tiles_per_job;
-        int r = tile - j * p.tiles_per_job;
-        ph = r % p.up; r /= p.up;
-        nt = r % p.n_nt; r /= p.n_nt;
-        lt = r % p.n_lt;
-        b = r / p.n_lt;
+        uint32_t q, r, t;
+        p.fd_tpj.divmod((uint32_t)tile, q, r);
+        j = (int)q;
+        p.fd_up.divmod(r, q, t);
+        ph = (int)t;
+        p.fd_nnt.divmod(q, r, t);
+        nt = (int)t;
+        p.fd_nlt.divmod(r, q, t);
+        lt = (int)t;
+        b = (int)q;
     };
 
     if (warp == 0) {
@@ -120,6 +139,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             int j, b, lt, nt, ph;
             decode(tile, j, b, lt, nt, ph);
             const rvc_tc_job& jb = p.jobs[j];
+            if (jb.res && p.up == 1) {
+                // pull this tile's residual rows (NT channels x TM positions, fp32) into L2 ahead of the epilogue
+                const int l0 = lt * TM;
+                const int n = min(TM, p.L - l0);
+                if (n > 0) {
+                    const float* rp = jb.res + (size_t)b * jb.res_bs + (size_t)(nt * NT) * jb.res_cs + l0;
+                    for (int c = lane; c < NT; c += 32) {
+                        const float* q = rp + (size_t)c * jb.res_cs;
+                        const uint32_t bytes = (uint32_t)(((reinterpret_cast<uintptr_t>(q) & 15) + (size_t)n * 4 + 15) & ~(size_t)15);
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)15), "r"(bytes) : "memory");
+                    }
+                }
+            }
             const int pad = jb.pad;
             const int rows = TM + (jb.K - 1) * jb.dil;
             for (int cs = 0; cs < p.ncs; ++cs) {
@@ -205,24 +237,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 const int na = min(p.ach, p.nch - cs * p.ach);
                 tc::mbar_wait(A_FULL(ast), aph);
                 tc::fence_after_sync();
-                const uint32_t a_base16 = (tc::smem_u32(a_smem + (size_t)ast * a_bytes) >> 4) + (uint32_t)(m * BM);
+                // descriptor low words: [13:0] start address / 16, [29:16] LBO / 16.  Per k-step: A += 2 chunks (2*rows_max rows),
+                // W += 2 chunks (2*NT rows); per tap: A restarts at the tap's row shift.  No field overflows: smem < 256 KB.
+                const uint32_t da_base = a_lo_hi | (((tc::smem_u32(a_smem + (size_t)ast * a_bytes) >> 4) + (uint32_t)(m * BM)) & 0x3FFFu);
                 const int nflat = K * na;
                 int ch = 0;
-                uint32_t tap_off = 0, a_off = 0;       // a_off = ch * rows_max + tap * dil, in 16-byte rows
+                uint32_t tap_off = 0, da_lo = da_base;
                 for (int f0 = 0; f0 < nflat; f0 += SCH) {
                     const int nu = min(SCH, nflat - f0);
                     tc::mbar_wait(W_FULL(wst), wph);
                     tc::fence_after_sync();
-                    uint32_t b16 = tc::smem_u32(w_smem + wst * STAGE_BYTES) >> 4;
-                    for (int u = 0; u < nu; u += 2) {
-                        const uint64_t da = ((uint64_t)desc_hi << 32) | (a_lo_hi | ((a_base16 + a_off) & 0x3FFFu));
-                        const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo_hi | (b16 & 0x3FFFu));
-                        if (!(p.dbg & 2) && tc::elect_one()) tc::umma<false>(d_tmem, da, db, idesc, accumulate);
-                        accumulate = 1;
-                        b16 += 2u * NT;
-                        ch += 2;
-                        a_off += rows2;
-                        if (ch >= na) { ch = 0; tap_off += dil; a_off = tap_off; }
+                    uint32_t db_lo = b_lo_hi | ((tc::smem_u32(w_smem + wst * STAGE_BYTES) >> 4) & 0x3FFFu);
+                    int u = 0;
+                    while (u < nu) {
+                        const int run = min(nu - u, na - ch);   // k-steps until the stage ends or the tap wraps (even)
+                        for (int r = 0; r < run; r += 2) {
+                            if (!(p.dbg & 2) && tc::elect_one())
+                                tc::umma<false>(d_tmem, ((uint64_t)desc_hi << 32) | da_lo, ((uint64_t)desc_hi << 32) | db_lo, idesc, accumulate);
+                            accumulate = 1;
+                            da_lo += rows2;
+                            db_lo += 2u * NT;
+                        }
+                        u += run;
+                        ch += run;
+                        if (ch == na) { ch = 0; tap_off += dil; da_lo = da_base + tap_off; }
                     }
                     if (tc::elect_one()) tc::umma_commit(W_EMPTY(wst));
                     if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
@@ -478,6 +516,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     p.n_nt = d.Cout / NT;
     p.tiles_per_job = d.B * p.n_lt * p.n_nt * up;
     p.total_tiles = p.tiles_per_job * d.njobs;
+    p.fd_tpj.init((uint32_t)p.tiles_per_job); p.fd_up.init((uint32_t)up); p.fd_nnt.init((uint32_t)p.n_nt); p.fd_nlt.init((uint32_t)p.n_lt);
     p.fp16 = d.dtype == RVC_DT_FP16;
     p.dbg = d.jobs[0].reserved;
     const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512;
