@@ -418,11 +418,32 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, uint8_t* __restr
     *reinterpret_cast<uint4*>(y + idx * 16) = pk;
 }
 
+// per-device SM count, queried once (idempotent cache; no other global state)
+int sm_count_cached() {
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev] = sms;
+    }
+    return cache[dev];
+}
+
 template <int NT, int MT>
 int launch_tc(const Params& p, size_t smem, int grid, cudaStream_t stream) {
     auto kern = conv1d_tc_kernel<NT, MT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return rvc::fail((int)e, "rvc_conv1d_tc: smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+    // opt in to the maximum dynamic shared memory once per device and instantiation (the attribute is sticky)
+    static bool opted[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !opted[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return rvc::fail((int)e, "rvc_conv1d_tc: smem opt-in: %s", cudaGetErrorString(e));
+        if (dev >= 0 && dev < 64) opted[dev] = true;
+    }
     kern<<<grid, NTHREADS, smem, stream>>>(p);
     return rvc::check_launch("rvc_conv1d_tc");
 }
@@ -481,9 +502,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
         maxpad = halo > maxpad ? halo : maxpad;
         p.jobs[j] = jb;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count_cached();
     // tile shape: the widest N tile (and 2 sub-tiles) that still yields >= one wave of CTAs; gated needs NT % 64 == 0
     int mt = d.mt, NT = d.nt;
     const int up = d.up > 0 ? d.up : 1;

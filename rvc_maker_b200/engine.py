@@ -109,6 +109,9 @@ class Engine:
         self.tc = self.precision != "fp32"
         self._fold(m)
         self.plans = {}
+        self.graphs = {}
+        self._warm = set()
+        self.use_graph = bool(getattr(m, "use_cuda_graph", True))
 
     # ------------------------------------------------------------------ weight folding / packing
     def _fold(self, m):
@@ -640,8 +643,10 @@ class Engine:
         key = (kind, B, T)
         pl = self.plans.get(key)
         if pl is None:
-            if len(self.plans) >= 8:  # bound the workspace arena: drop the oldest shape
+            if len(self.plans) >= 8:  # bound the workspace arena: drop the oldest shape (and every graph built on it)
                 self.plans.pop(next(iter(self.plans)))
+                self.graphs.clear()
+                self._warm.clear()
             pl = self._enc_plan(B, T) if kind == "enc" else self._dec_plan(B, T)
             self.plans[key] = pl
         return pl
@@ -684,13 +689,9 @@ class Engine:
                 pe.eps_z.copy_(noise[0], non_blocking=True)
             else:
                 pe.eps_z.normal_()  # randn_like(m_p), synthesizers.py:449
-            pe.run(stream)
-
             head = int(T * (1.0 - rate)) if rate is not None else 0
             T2 = T - head
             pd = self.plan("dec", B, T2)
-            pd.zp.copy_(pe.zp[:, :, head:])
-            pd.mask.copy_(pe.mask[:, head:])
             pd.g.copy_(self.W["emb_g"][sid.to(self.dev)])  # emb_g(sid), :447
             if c["f0"]:
                 pd.f0.copy_(nsff0[:, head:], non_blocking=True)
@@ -699,7 +700,30 @@ class Engine:
                 else:
                     torch.rand(1, 1, 1, device=self.dev)  # rand_ini (:87) — drawn to keep the generator stream aligned, value unused (:88)
                     pd.eps_src.normal_()                  # randn_like(sine_waves), :98
-            pd.run(stream)
+
+            def body(st):
+                pe.run(st)
+                pd.zp.copy_(pe.zp[:, :, head:])
+                pd.mask.copy_(pe.mask[:, head:])
+                pd.run(st)
+
+            # the kernel sequence of a (B, T, head) shape is static: capture it once into a CUDA graph and replay it
+            # (inputs / noise were copied into the plans' persistent buffers above; RNG draws stay outside the graph)
+            key = (B, T, head)
+            gr = self.graphs.get(key) if self.use_graph else None
+            if self.use_graph and gr is None and key in self._warm:
+                if len(self.graphs) >= 8:
+                    self.graphs.pop(next(iter(self.graphs)))
+                gr = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(self.dev)
+                with torch.cuda.graph(gr):
+                    body(torch.cuda.current_stream(self.dev).cuda_stream)
+                self.graphs[key] = gr
+            if gr is not None:
+                gr.replay()
+            else:
+                body(stream)
+                self._warm.add(key)
 
             I = c["I"]
             o = pd.o.to(out_dtype, copy=True)

@@ -154,3 +154,26 @@ def test_inputs_not_mutated_and_errors():
         net.infer(ph[:, :, :5], inp["phone_lengths"].cuda(), inp["pitch"].cuda(), inp["nsff0"].cuda(), inp["sid"].cuda())
     with pytest.raises(RuntimeError):
         build_net(cfg, sd, True).cpu().infer(inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_cuda_graph_replay_matches_eager(precision):
+    """The second and later calls of a shape replay a captured CUDA graph; results must be bit-identical to the eager launch."""
+    cfg = cases.CONFIGS["v2_40k"]
+    sd = cases.synth_state_dict(cfg, seed=8, heated=True)
+    inp = cases.synth_inputs(cfg, 2, 96, seed=3, ragged=True)
+    net = build_net(cfg, sd, True, precision=precision)
+    eager = run_net(net, inp)
+    assert not net._engine.graphs
+    g1 = run_net(net, inp)
+    assert len(net._engine.graphs) == 1
+    g2 = run_net(net, inp)
+    for k in eager:
+        assert torch.equal(eager[k], g1[k]) and torch.equal(eager[k], g2[k]), k
+    # new inputs through the same graph
+    inp2 = cases.synth_inputs(cfg, 2, 96, seed=4, ragged=True)
+    a = run_net(net, inp2)
+    net2 = build_net(cfg, sd, True, precision=precision)
+    b = run_net(net2, inp2)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
