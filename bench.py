@@ -238,7 +238,7 @@ def main():
                                  "tc-bf16": "as tc, bf16 operands in the C>=128 ResBlocks", "fp32": "fp32 CUDA cores"}[args.precision], "l2": "256 MiB memset between steps (untimed); per-step working set > L2",
                    "parallelism": f"{world} replica(s), independent chunks, no data-path collective"},
         "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": net._engine.launches_per_infer(B, T) * args.steps,
+        "gpu_launches": net._engine.launches_per_infer(B, T) * args.steps * world,
         "clocks": clocks,
     }
 
