@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 11
+#define RVC_ABI_VERSION 12
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -105,6 +105,14 @@ int rvc_conv_post_f32(const float* x, const float* x2, const float* x3, float in
 int rvc_embed_f32(const float* phone, const int64_t* pitch, const int64_t* lengths, const float* wT, const float* bias,
                   const float* emb_pitch, float* x, float* mask, int32_t B, int32_t T, int32_t D, int32_t H, void* stream);
 
+/* Tensor-core variant of the front end: rvc_embed_prep writes mask[b,t] = t < lengths[b] and, when pitch != NULL, the exact
+ * gather pb[b,c,t] = emb_pitch[pitch[b,t]][c] * scale (fp32 [B,H,T]); rvc_pack_rows converts the channels-last phone features
+ * [B,T,D] into the packed operand layout; the Linear itself then runs through rvc_conv1d_tc with res = pb, alpha = sqrt(H),
+ * relu = 2 (leaky_relu on the final value) and the mask. */
+int rvc_embed_prep(const int64_t* pitch, const int64_t* lengths, const float* emb_pitch, float scale, float* pb, float* mask,
+                   int32_t B, int32_t T, int32_t H, void* stream);
+int rvc_pack_rows(const float* x, void* y, int32_t B, int32_t T, int32_t D, int32_t dtype, void* stream);
+
 /* y = LayerNorm_C(x + r) * gamma + beta over the channel axis of [B,C,T] (synthesizers.py:179-181, :346-347);
  * out_mask multiplies by mask[b,t] (the final `x * x_mask`, :348).  y_act (optional): the MASKED result in the packed
  * bf16/fp16 layout of the tensor-core convs (see below), act_dtype = RVC_DT_BF16 / RVC_DT_FP16. */
@@ -162,7 +170,8 @@ int rvc_pack_weight(const float* w, void* y, int32_t Cout, int32_t Cin, int32_t 
  *   gated == 1:  v[c]  = tanh(acc[t] + bias[t] + bias_b[b][t]) * sigmoid(acc[s] + bias[s] + bias_b[b][s]), where within every
  *                N tile of `nt` weight columns the first nt/2 are the tanh columns of output channels [tile*nt/2, ...) and
  *                the last nt/2 the matching sigmoid columns (the caller packs weights / biases in that order)  [commons.py:35-41]
- *   relu: v = max(v, 0);   res: v = res[b][c][l] + alpha * v;   mask: v *= mask[b][l]
+ *   relu == 1: v = max(v, 0);   res: v = res[b][c][l] + alpha * v;   relu == 2: v = leaky_relu(v, act_slope) (then y_act adds none);
+ *   mask: v *= mask[b][l]
  *   y_f32[b][c][l] = v (element strides y_bs / y_cs);   y_act = DT(leaky_relu(v, act_slope)) in the packed layout.
  * Up to three jobs sharing (B, Cin, Cout, L, dtype) run in one persistent launch.  nt / mt = 0 let the library pick the tile.
  */

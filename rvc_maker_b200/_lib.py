@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 DT_BF16, DT_FP16 = 0, 2
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -77,6 +77,8 @@ SIGNATURES = {
     "rvc_convtr1d_f32": (C.c_int, [C.POINTER(ConvTr1dDesc), _vp]),
     "rvc_conv_post_f32": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp]),
     "rvc_embed_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "rvc_embed_prep": (C.c_int, [_vp, _vp, _vp, _f32, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "rvc_pack_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_layernorm_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _i32, _vp]),
     "rvc_rel_attention_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rvc_cond_gemv_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),

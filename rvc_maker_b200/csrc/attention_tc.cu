@@ -76,10 +76,15 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
         return s;
     };
 
-    // ---- pass 1: online max / sum over this group's key chunks (chunk c belongs to group c % AG)
+    // ---- pass 1: online max / sum over this group's key chunks (chunk c belongs to group c % AG).  When a thread's share
+    // of the row fits (<= CACHE chunks) the scores stay in registers and S is read from memory only once.
+    constexpr int CACHE = 8;
+    const bool cached = (nchunk + AG - 1) / AG <= CACHE;
+    float sc[CACHE][8];
     float m = -INFINITY, l = 0.f;
-    if (qok)
-        for (int c = g; c < nchunk; c += AG) {
+    if (qok) {
+        int k = 0;
+        for (int c = g; c < nchunk; c += AG, ++k) {
             float s8[8];
             float cm = -INFINITY;
 #pragma unroll
@@ -87,6 +92,14 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
                 const int j = 8 * c + u;
                 s8[u] = j < T ? score(j) : -INFINITY;
                 cm = fmaxf(cm, s8[u]);
+            }
+            if (cached) {
+#pragma unroll
+                for (int kk = 0; kk < CACHE; ++kk)
+                    if (kk == k) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) sc[kk][u] = s8[u];
+                    }
             }
             if (cm == -INFINITY) continue;
             const float mn = fmaxf(m, cm);
@@ -96,6 +109,7 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
             l = l * expf(m - mn) + acc;
             m = mn;
         }
+    }
     m_s[g * AQ + ti] = m;
     l_s[g * AQ + ti] = l;
     __syncthreads();
@@ -112,14 +126,27 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
 
     // ---- pass 2: probabilities, packed fp16
     uint8_t* Pb = P + (((int64_t)b * nh + h) * nchunk * Lp + 64 + i) * 16;
-    for (int c = g; c < nchunk; c += AG) {
-        float p8[8];
+    if (cached) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int j = 8 * c + u;
-            p8[u] = j < T ? expf(score(j) - M) * rl : 0.f;
+        for (int k = 0; k < CACHE; ++k) {
+            const int c = g + k * AG;
+            if (c < nchunk) {
+                float p8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) p8[u] = expf(sc[k][u] - M) * rl;   // exp(-inf) = 0 for keys >= T
+                *reinterpret_cast<uint4*>(Pb + (int64_t)c * Lp * 16) = make_uint4(h2(p8[0], p8[1]), h2(p8[2], p8[3]), h2(p8[4], p8[5]), h2(p8[6], p8[7]));
+            }
         }
-        *reinterpret_cast<uint4*>(Pb + (int64_t)c * Lp * 16) = make_uint4(h2(p8[0], p8[1]), h2(p8[2], p8[3]), h2(p8[4], p8[5]), h2(p8[6], p8[7]));
+    } else {
+        for (int c = g; c < nchunk; c += AG) {
+            float p8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = 8 * c + u;
+                p8[u] = j < T ? expf(score(j) - M) * rl : 0.f;
+            }
+            *reinterpret_cast<uint4*>(Pb + (int64_t)c * Lp * 16) = make_uint4(h2(p8[0], p8[1]), h2(p8[2], p8[3]), h2(p8[4], p8[5]), h2(p8[6], p8[7]));
+        }
     }
 
     // ---- relative-value term: group g owns output dims [g*dk/AG, (g+1)*dk/AG)

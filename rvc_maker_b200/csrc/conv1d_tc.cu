@@ -139,19 +139,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             int j, b, lt, nt, ph;
             decode(tile, j, b, lt, nt, ph);
             const rvc_tc_job& jb = p.jobs[j];
-            if (jb.res && p.up == 1) {
-                // pull this tile's residual rows (NT channels x TM positions, fp32) into L2 ahead of the epilogue
-                const int l0 = lt * TM;
-                const int n = min(TM, p.L - l0);
-                if (n > 0) {
-                    const float* rp = jb.res + (size_t)b * jb.res_bs + (size_t)(nt * NT) * jb.res_cs + l0;
-                    for (int c = lane; c < NT; c += 32) {
-                        const float* q = rp + (size_t)c * jb.res_cs;
-                        const uint32_t bytes = (uint32_t)(((reinterpret_cast<uintptr_t>(q) & 15) + (size_t)n * 4 + 15) & ~(size_t)15);
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)15), "r"(bytes) : "memory");
-                    }
-                }
-            }
             const int pad = jb.pad;
             const int rows = TM + (jb.K - 1) * jb.dil;
             for (int cs = 0; cs < p.ncs; ++cs) {
@@ -328,7 +315,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     }
                 }
                 if (!ok) continue;
-                if (jb.relu) {
+                if (jb.relu == 1) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
                 }
@@ -338,6 +325,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = jb.alpha * __uint_as_float(r[i]);
+                }
+                float sl = jb.act_slope;
+                if (jb.relu == 2) {   // leaky_relu on the final value itself (both outputs carry it)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = rvc::lrelu(v[i], sl);
+                    sl = 1.f;
                 }
                 if (jb.mask) {
 #pragma unroll
@@ -351,7 +344,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 if (jb.y_act) {
                     const size_t ya_bs = jb.y_act_bs ? (size_t)jb.y_act_bs : (size_t)p.nch_out * p.Lp_out * 16;
                     uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (size_t)b * ya_bs + (((size_t)co0 / 8) * p.Lp_out + PADL + l) * 16;
-                    const float sl = jb.act_slope;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         uint4 pk;

@@ -227,20 +227,12 @@ __global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __rest
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = (co0 + c < C && bias) ? bias[co0 + c] : 0.f;
-    for (int j0 = 0; j0 < kn; j0 += 16) {
-        float h[16];
+    const int64_t h0 = (int64_t)l * sn - pn;
+    for (int j = 0; j < kn; ++j) {
+        const int64_t idx = h0 + j;
+        const float hv = (idx >= 0 && idx < hlen) ? hb[idx] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int64_t idx = (int64_t)l * sn - pn + j0 + j;
-            h[j] = (j0 + j < kn && idx >= 0 && idx < hlen) ? hb[idx] : 0.f;
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float* wr = w_s + c * kn + j0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (j0 + j < kn) acc[c] = fmaf(wr[j], h[j], acc[c]);
-        }
+        for (int c = 0; c < 32; ++c) acc[c] = fmaf(w_s[c * kn + j], hv, acc[c]);
     }
 #pragma unroll
     for (int c = 0; c < 32; ++c)

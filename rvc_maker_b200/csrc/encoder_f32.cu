@@ -322,6 +322,55 @@ RVC_API int rvc_cond_gemv_f32(const float* x, const float* w, const float* bias,
 namespace {
 }  // namespace
 
+namespace {
+// TextEncoder front end for the tensor-core path: mask[b,t] = t < len[b]; pb[b,c,t] = E[pitch[b,t]][c] * scale (exact gather)
+__global__ void __launch_bounds__(256) embed_prep_kernel(const int64_t* __restrict__ pitch, const int64_t* __restrict__ lengths,
+                                                         const float* __restrict__ emb_pitch, float scale, float* __restrict__ pb,
+                                                         float* __restrict__ mask, int T, int H) {
+    const int t = blockIdx.x * 256 + threadIdx.x, b = blockIdx.z;
+    if (t >= T) return;
+    if (blockIdx.y == 0) mask[(int64_t)b * T + t] = t < lengths[b] ? 1.f : 0.f;
+    if (!pitch) return;
+    const int64_t pi = pitch[(int64_t)b * T + t];
+    const int c0 = blockIdx.y * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (c0 + i < H) pb[((int64_t)b * H + c0 + i) * T + t] = emb_pitch[pi * H + c0 + i] * scale;
+}
+
+// channels-last fp32 [B, T, D] -> packed fp16/bf16 [B][D/8][Lp][8]
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int T, int D, int Lp, int fp16) {
+    const int t = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    const float4* xp = reinterpret_cast<const float4*>(x + ((int64_t)b * T + t) * D + c * 8);
+    const float4 a = xp[0], d = xp[1];
+    uint4 pk;
+    pk.x = ln_pack2(a.x, a.y, fp16); pk.y = ln_pack2(a.z, a.w, fp16);
+    pk.z = ln_pack2(d.x, d.y, fp16); pk.w = ln_pack2(d.z, d.w, fp16);
+    *reinterpret_cast<uint4*>(y + (((int64_t)b * (D / 8) + c) * Lp + 64 + t) * 16) = pk;
+}
+}  // namespace
+
+RVC_API int rvc_embed_prep(const int64_t* pitch, const int64_t* lengths, const float* emb_pitch, float scale, float* pb, float* mask,
+                           int32_t B, int32_t T, int32_t H, void* stream) {
+    if (!lengths || !mask || (pitch && (!emb_pitch || !pb))) return rvc::fail(RVC_EINVAL, "rvc_embed_prep: null pointer");
+    if (B <= 0 || B > 65535 || T < 0 || H <= 0) return rvc::fail(RVC_ESHAPE, "rvc_embed_prep: bad shape");
+    if (T == 0) return 0;
+    dim3 grid(rvc::cdiv(T, 256), pitch ? rvc::cdiv(H, 16) : 1, B);
+    embed_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pitch, lengths, emb_pitch, scale, pb, mask, T, H);
+    return rvc::check_launch("rvc_embed_prep");
+}
+
+RVC_API int rvc_pack_rows(const float* x, void* y, int32_t B, int32_t T, int32_t D, int32_t dtype, void* stream) {
+    if (!x || !y) return rvc::fail(RVC_EINVAL, "rvc_pack_rows: null pointer");
+    if (dtype != RVC_DT_BF16 && dtype != RVC_DT_FP16) return rvc::fail(RVC_EINVAL, "rvc_pack_rows: dtype must be RVC_DT_BF16 or RVC_DT_FP16");
+    if (B <= 0 || B > 65535 || T < 0 || D <= 0 || D % 8 || (reinterpret_cast<uintptr_t>(x) & 15)) return rvc::fail(RVC_ESHAPE, "rvc_pack_rows: bad shape / alignment");
+    if (T == 0) return 0;
+    dim3 grid(rvc::cdiv(T, 256), D / 8, B);
+    pack_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (uint8_t*)y, T, D, (int)rvc_packed_rows(T), dtype == RVC_DT_FP16);
+    return rvc::check_launch("rvc_pack_rows");
+}
+
 RVC_API int rvc_embed_f32(const float* phone, const int64_t* pitch, const int64_t* lengths, const float* wT, const float* bias,
                              const float* emb_pitch, float* x, float* mask, int32_t B, int32_t T, int32_t D, int32_t H, void* stream) {
     if (!phone || !lengths || !wT || !bias || !x || !mask) return rvc::fail(RVC_EINVAL, "rvc_embed_f32: null pointer");

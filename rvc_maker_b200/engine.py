@@ -232,6 +232,8 @@ class Engine:
                 f = e.encoder.ffn_layers[i]
                 tc_w[f"t_f1_w{i}"], tc_w[f"t_f2_w{i}"] = (_f(f.conv_1.weight), dt), (_f(f.conv_2.weight), dt)
             tc_w["t_proj_w"] = (_f(e.proj.weight), dt)
+            if c["D"] % 16 == 0:
+                tc_w["t_emb_w"] = (_f(e.emb_phone.weight).unsqueeze(-1).contiguous(), dt)   # Linear as a 1x1 conv [H, D, 1]
             # gated in_layers: weight columns ordered per 64-wide N tile as [32 tanh | 32 sigmoid] (see include/rvc_b200.h)
             perm = []
             for t in range(2 * H // 64):
@@ -319,7 +321,7 @@ class Engine:
                 jb.y_act = j["y_act"] if isinstance(j["y_act"], int) else j["y_act"].data_ptr()
             jb.K, jb.dil = j.get("K", 1), j.get("dil", 1)
             jb.pad = j.get("pad", (jb.K - 1) // 2 * jb.dil)
-            jb.gated, jb.relu = int(j.get("gated", False)), int(j.get("relu", False))
+            jb.gated, jb.relu = int(j.get("gated", False)), int(j.get("relu", 0))
             jb.alpha, jb.act_slope = j.get("alpha", 1.0), j.get("act_slope", 1.0)
             jb.a_bs, jb.w_bs, jb.y_act_bs, jb.w_cs = j.get("a_bs", 0), j.get("w_bs", 0), j.get("y_act_bs", 0), j.get("w_cs", 0)
             ce = Cout // 2 if jb.gated else Cout
@@ -358,14 +360,29 @@ class Engine:
         p.stats = self._buf(p, B, 2 * I, T)
         p.zp = self._buf(p, B, I, T)
         vx, vqkv, vatt, vy, vh, vst = V(x, H, T), V(qkv, 3 * H, T), V(att, H, T), V(y, H, T), V(h, Fc, T), V(p.stats, 2 * I, T)
-        p.add("embed", lib.rvc_embed_f32, p.phone.data_ptr(), p.pitch.data_ptr() if c["f0"] else None, p.lengths.data_ptr(),
-              W["emb_wT"].data_ptr(), W["emb_b"].data_ptr(), W["emb_pitch"].data_ptr() if c["f0"] else None, x.data_ptr(),
-              p.mask.data_ptr(), B, T, D, H, flops=2.0 * B * T * D * H, bytes_=4.0 * B * T * (D + H), kind="embed_f32")
         padl = (ks - 1) // 2
+        tc_embed = self.enc_tc and "t_emb_w" in W
+        if not tc_embed:
+            p.add("embed", lib.rvc_embed_f32, p.phone.data_ptr(), p.pitch.data_ptr() if c["f0"] else None, p.lengths.data_ptr(),
+                  W["emb_wT"].data_ptr(), W["emb_b"].data_ptr(), W["emb_pitch"].data_ptr() if c["f0"] else None, x.data_ptr(),
+                  p.mask.data_ptr(), B, T, D, H, flops=2.0 * B * T * D * H, bytes_=4.0 * B * T * (D + H), kind="embed_f32")
         if self.enc_tc:
             dt = DT_FP16
             xa, atta, ha = self._packed(p, B, H, T), self._packed(p, B, H, T), self._packed(p, B, Fc, T)
-            p.add("pack_x", lib.rvc_pack_act, x.data_ptr(), None, None, 1.0, H * T, T, None, xa.data_ptr(), B, H, T, dt, 1.0, kind="pack_act", bytes_=6.0 * B * H * T)
+            if tc_embed:
+                # x = lrelu((phone.W^T + b + E[pitch]) * sqrt(H), 0.1) * mask  (synthesizers.py:367): exact gather + tensor-core Linear
+                pha = self._packed(p, B, D, T)
+                pbias = self._buf(p, B, H, T) if c["f0"] else None
+                sq = math.sqrt(H)
+                p.add("embed_prep", lib.rvc_embed_prep, p.pitch.data_ptr() if c["f0"] else None, p.lengths.data_ptr(),
+                      W["emb_pitch"].data_ptr() if c["f0"] else None, sq, pbias.data_ptr() if c["f0"] else None, p.mask.data_ptr(), B, T, H,
+                      bytes_=8.0 * B * H * T, kind="embed_prep")
+                p.add("pack_phone", lib.rvc_pack_rows, p.phone.data_ptr(), pha.data_ptr(), B, T, D, dt, bytes_=6.0 * B * T * D, kind="pack_act")
+                self._tc(p, "embed", [dict(a=pha, w=W["t_emb_w"], bias=W["emb_b"], res=(V(pbias, H, T) if c["f0"] else None), alpha=sq,
+                                           relu=2, act_slope=0.1, mask=p.mask, y=vx, y_act=xa)], B=B, Cin=D, Cout=H, L=T, dtype=dt, tag="enc")
+            else:
+                p.add("pack_x", lib.rvc_pack_act, x.data_ptr(), None, None, 1.0, H * T, T, None, xa.data_ptr(), B, H, T, dt, 1.0, kind="pack_act",
+                      bytes_=6.0 * B * H * T)
             nh = c["nh"]
             dk = H // nh
             tc_attn = nh <= 3 and dk % 32 == 0
