@@ -6,14 +6,14 @@
 //   P[i,j] = softmax_j(s)            -> packed fp16 [b][h][j/8][64 + i][8]   (the A operand of the P.v GEMM)
 //   R[i,:] = sum_{|j-i|<=w} P[i,j] Ev[j-i+w]                                  (fp32, the residual input of the P.v GEMM)
 //   vw     = v^T packed over keys   -> fp16 [b][h][j/8][d][8]                (the weights of the P.v GEMM)
-// CTA = 32 queries x 16 key groups (512 threads); S is read coalesced along queries, twice (online max/sum, then probabilities).
+// CTA = 16 queries x 32 key groups (512 threads); S is read coalesced along queries, twice (online max/sum, then probabilities).
 #include "common.cuh"
 #include <cuda_fp16.h>
 #include <math.h>
 
 namespace {
 
-constexpr int AQ = 32, AG = 16, ANT = AQ * AG;
+constexpr int AQ = 16, AG = 32, ANT = AQ * AG;
 
 __device__ __forceinline__ uint32_t h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -176,7 +176,7 @@ RVC_API int rvc_attn_softmax(const float* S, const float* qkv, const float* mask
     if (B <= 0 || H <= 0 || n_heads <= 0 || H % n_heads || T <= 0 || Tk < T || Tk % 8 || window < 0)
         return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: bad shape");
     const int dk = H / n_heads;
-    if (dk % AG || dk / AG > 16) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: head dim %d must be a multiple of 16 and <= 256", dk);
+    if (dk % AG || dk / AG > 16) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: head dim %d must be a multiple of 32 and <= 512", dk);
     if ((int64_t)B * n_heads > 65535) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: B*heads > 65535");
     const int NR = 2 * window + 1;
     const size_t smem = (size_t)(AQ * NR + NR * dk + 2 * AG * AQ) * sizeof(float);

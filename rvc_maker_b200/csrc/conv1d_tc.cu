@@ -80,6 +80,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
 template <int NT, int MT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) {
     constexpr int TM = BM * MT;
+    constexpr int NI = MT >= 2 ? 2 : 1;                     // MMA issuer warps
+    constexpr int MPI = MT / NI;                            // sub-tiles per issuer
     constexpr int SCH = (STAGE_BYTES / (NT * 16)) & ~1;    // 16-byte chunks per weight stage (even)
     constexpr int NG = (512 / (MT * NT)) >= MAXNG ? MAXNG : (512 / (MT * NT));   // accumulator groups (>= 2)
     static_assert(NG >= 2, "need at least two accumulator groups");
@@ -105,10 +107,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        // one MMA issuer warp per sub-tile: every "consumed" barrier collects MT commits
-        for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(W_FULL(s), 1); tc::mbar_init(W_EMPTY(s), MT); }
-        for (int s = 0; s < MAXABUF; ++s) { tc::mbar_init(A_FULL(s), 1); tc::mbar_init(A_EMPTY(s), MT); }
-        for (int s = 0; s < MAXNG; ++s) { tc::mbar_init(ACC_FULL(s), MT); tc::mbar_init(ACC_EMPTY(s), 8); }
+        // NI MMA issuer warps (sub-tiles split between them): every "consumed" barrier collects NI commits
+        for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(W_FULL(s), 1); tc::mbar_init(W_EMPTY(s), NI); }
+        for (int s = 0; s < MAXABUF; ++s) { tc::mbar_init(A_FULL(s), 1); tc::mbar_init(A_EMPTY(s), NI); }
+        for (int s = 0; s < MAXNG; ++s) { tc::mbar_init(ACC_FULL(s), NI); tc::mbar_init(ACC_EMPTY(s), 8); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
@@ -197,8 +199,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 }
             }
         }
-    } else if (warp == 1 || (MT == 2 && warp == 3)) {
-        // ======================= MMA issuers: warp 1 -> sub-tile 0, warp 3 -> sub-tile 1.  The whole warp runs the (uniform)
+    } else if (warp == 1 || (NI == 2 && warp == 3)) {
+        // ======================= MMA issuers: warp 1 -> sub-tiles 0 (and 2), warp 3 -> sub-tiles 1 (and 3).  The whole warp runs the (uniform)
         // loop so that descriptors live in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.
         // Descriptors are updated incrementally: +2*rows_max (16-B units) per k-step, +dil per tap for A; +2*NT for W. =====
         const int m = (warp == 1) ? 0 : 1;
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             const uint32_t gph = (it / NG) & 1;
             tc::mbar_wait(ACC_EMPTY(g), gph ^ 1);
             tc::fence_after_sync();
-            const uint32_t d_tmem = tmem_base + (uint32_t)((g * MT + m) * NT);
+            const uint32_t d_tmem = tmem_base + (uint32_t)((g * MT + m) * NT);   // + 2*NT for this issuer's second sub-tile
             uint32_t accumulate = 0;
             for (int cs = 0; cs < p.ncs; ++cs) {
                 const int na = min(p.ach, p.nch - cs * p.ach);
@@ -239,8 +241,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     while (u < nu) {
                         const int run = min(nu - u, na - ch);   // k-steps until the stage ends or the tap wraps (even)
                         for (int r = 0; r < run; r += 2) {
-                            if (!(p.dbg & 2) && tc::elect_one())
+                            if (!(p.dbg & 2) && tc::elect_one()) {
                                 tc::umma<false>(d_tmem, ((uint64_t)desc_hi << 32) | da_lo, ((uint64_t)desc_hi << 32) | db_lo, idesc, accumulate);
+                                if constexpr (MPI == 2)   // sub-tile m + 2: same weights, activation rows 2*128 further down
+                                    tc::umma<false>(d_tmem + 2u * NT, ((uint64_t)desc_hi << 32) | (da_lo + 2u * BM), ((uint64_t)desc_hi << 32) | db_lo,
+                                                    idesc, accumulate);
+                            }
                             accumulate = 1;
                             da_lo += rows2;
                             db_lo += 2u * NT;
@@ -442,6 +448,9 @@ int launch_tc(const Params& p, size_t smem, int grid, cudaStream_t stream) {
 
 template <int NT>
 int launch_tc_mt(int mt, const Params& p, size_t smem, int grid, cudaStream_t stream) {
+    if constexpr (NT <= 64) {
+        if (mt == 4) return launch_tc<NT, 4>(p, smem, grid, stream);
+    }
     return mt == 1 ? launch_tc<NT, 1>(p, smem, grid, stream) : launch_tc<NT, 2>(p, smem, grid, stream);
 }
 
@@ -515,8 +524,11 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     }
     if (NT != 128 && NT != 64 && NT != 32) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt must be 32, 64 or 128");
     if (d.Cout % NT || (gated && NT % 64)) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt=%d does not tile Cout=%d (gated=%d)", NT, d.Cout, gated);
-    if (mt == 0) mt = ntiles(NT, 2) >= 2L * sms ? 2 : 1;
-    if (mt != 1 && mt != 2) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: mt must be 1 or 2");
+    // sub-tiles per CTA tile: as many as still leave >= 2 waves of tiles (fewer, larger tiles amortise the per-tile handshakes);
+    // 4 sub-tiles need NT <= 64 (TMEM: 2 groups x 4 x NT columns)
+    if (mt == 0) mt = (NT <= 64 && up == 1 && ntiles(NT, 4) >= 2L * sms) ? 4 : (ntiles(NT, 2) >= 2L * sms ? 2 : 1);
+    if (mt != 1 && mt != 2 && mt != 4) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: mt must be 1, 2 or 4");
+    if (mt == 4 && NT > 64) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: mt = 4 needs nt <= 64");
     const int TM = BM * mt;
     p.njobs = d.njobs; p.B = d.B; p.Cin = d.Cin; p.Cout = d.Cout; p.L = Lq; p.Lp = packed_rows(d.L);
     p.up = up; p.pshift = up > 1 ? d.pshift : 0; p.Lout = Lout; p.Lp_out = packed_rows(Lout);

@@ -288,25 +288,23 @@ __global__ void sample_zp_f32_kernel(const float* __restrict__ stats, const floa
 
 
 
-// y[b][co] = bias[co] + sum_ci w[ci][co] * x[b][ci]   (w packed [Cin][Cout]: consecutive threads -> consecutive co, coalesced)
-__global__ void __launch_bounds__(128) cond_gemv_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+// y[b][co] = bias[co] + sum_ci w[ci][co] * x[b][ci]   (w packed [Cin][Cout]); block = 32 output columns x 8 ci slices
+__global__ void __launch_bounds__(256) cond_gemv_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                             float* __restrict__ y, int Cin, int Cout) {
-    extern __shared__ float x_s[];
-    const int b = blockIdx.y;
-    for (int i = threadIdx.x; i < Cin; i += 128) x_s[i] = x[(int64_t)b * Cin + i];
+    __shared__ float red[8][33];
+    const int b = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int co = blockIdx.x * 32 + tx;
+    float a = 0.f;
+    if (co < Cout)
+        for (int ci = ty; ci < Cin; ci += 8) a = fmaf(w[(int64_t)ci * Cout + co], x[(int64_t)b * Cin + ci], a);
+    red[ty][tx] = a;
     __syncthreads();
-    const int co = blockIdx.x * 128 + threadIdx.x;
-    if (co >= Cout) return;
-    float a0 = bias ? bias[co] : 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int ci = 0;
-    for (; ci + 4 <= Cin; ci += 4) {
-        a0 = fmaf(w[(int64_t)(ci + 0) * Cout + co], x_s[ci + 0], a0);
-        a1 = fmaf(w[(int64_t)(ci + 1) * Cout + co], x_s[ci + 1], a1);
-        a2 = fmaf(w[(int64_t)(ci + 2) * Cout + co], x_s[ci + 2], a2);
-        a3 = fmaf(w[(int64_t)(ci + 3) * Cout + co], x_s[ci + 3], a3);
+    if (ty == 0 && co < Cout) {
+        float s = bias ? bias[co] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][tx];
+        y[(int64_t)b * Cout + co] = s;
     }
-    for (; ci < Cin; ++ci) a0 = fmaf(w[(int64_t)ci * Cout + co], x_s[ci], a0);
-    y[(int64_t)b * Cout + co] = (a0 + a1) + (a2 + a3);
 }
 
 }  // namespace
@@ -314,8 +312,8 @@ __global__ void __launch_bounds__(128) cond_gemv_f32_kernel(const float* __restr
 RVC_API int rvc_cond_gemv_f32(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Cout, void* stream) {
     if (!x || !w || !y) return rvc::fail(RVC_EINVAL, "rvc_cond_gemv_f32: null pointer");
     if (B <= 0 || B > 65535 || Cin <= 0 || Cin > 8192 || Cout <= 0) return rvc::fail(RVC_ESHAPE, "rvc_cond_gemv_f32: bad shape");
-    dim3 grid(rvc::cdiv(Cout, 128), B);
-    cond_gemv_f32_kernel<<<grid, 128, Cin * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, y, Cin, Cout);
+    dim3 grid(rvc::cdiv(Cout, 32), B);
+    cond_gemv_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, Cin, Cout);
     return rvc::check_launch("rvc_cond_gemv_f32");
 }
 

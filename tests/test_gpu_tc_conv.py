@@ -122,14 +122,15 @@ def test_ragged_lengths(L):
     run_case(FP16, 64, 64, 11, 5, B=3, L=L)
 
 
-@pytest.mark.parametrize("nt,mt", [(32, 1), (32, 2), (64, 1), (64, 2), (128, 1), (128, 2)])
+@pytest.mark.parametrize("nt,mt", [(32, 1), (32, 2), (32, 4), (64, 1), (64, 2), (64, 4), (128, 1), (128, 2)])
 def test_forced_tiles(nt, mt):
     run_case(FP16, 128, 128, 5, 2, B=2, L=1500, nt=nt, mt=mt)
 
 
 def test_three_jobs_many_tiles():
     run_case(BF16, 128, 128, 11, 5, B=2, L=40000, njobs=3)
-    run_case(FP16, 32, 32, 11, 1, B=1, L=100000, njobs=3)
+    run_case(FP16, 32, 32, 11, 1, B=1, L=100000, njobs=3)          # auto-selects 4 sub-tiles per CTA tile
+    run_case(FP16, 64, 64, 11, 5, B=1, L=300001, njobs=3)
 
 
 @pytest.mark.parametrize("Cin,Cout,K", [(192, 576, 1), (192, 768, 3), (768, 192, 3), (192, 384, 1), (96, 192, 1), (192, 96, 1), (192, 512, 7)])
