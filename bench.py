@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--config", default="v2_48k")
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--batch", type=int, default=1)
-    ap.add_argument("--precision", default="tc", choices=["tc", "tc-bf16", "fp32"], help="tc = fp16 tcgen05 operands, tc-bf16 = bf16 in the C>=128 ResBlocks, fp32 = CUDA cores")
+    ap.add_argument("--precision", default="tc", choices=["tc", "tc-bf16", "fp32"], help="tc = fp16 tcgen05 operands, tc-bf16 = bf16 in the C=256 ResBlocks, fp32 = CUDA cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-json", default=None, help="write the per-kernel timing table here")
     args = ap.parse_args()
@@ -235,7 +235,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"tc": "f16", "tc-bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": workload, "precision": {"tc": "fp16 operands / fp32 accumulate on tcgen05 for every conv, fp32 residual streams + attention + norms",
-                                 "tc-bf16": "as tc, bf16 operands in the C>=128 ResBlocks", "fp32": "fp32 CUDA cores"}[args.precision], "l2": "256 MiB memset between steps (untimed); per-step working set > L2",
+                                 "tc-bf16": "as tc, bf16 operands in the C=256 ResBlocks", "fp32": "fp32 CUDA cores"}[args.precision], "l2": "256 MiB memset between steps (untimed); per-step working set > L2",
                    "parallelism": f"{world} replica(s), independent chunks, no data-path collective"},
         "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": net._engine.launches_per_infer(B, T) * args.steps * world,

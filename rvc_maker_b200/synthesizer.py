@@ -170,7 +170,7 @@ class Synthesizer(nn.Module):
         self.emb_g = nn.Embedding(spk_embed_dim, G)
 
         # "tc": every conv on tcgen05 tensor cores with fp16 operands / fp32 accumulation; "tc-bf16": same with bf16 operands in the
-        # C >= 128 ResBlocks; "fp32": CUDA-core fp32 everywhere
+        # C = 256 ResBlocks; "fp32": CUDA-core fp32 everywhere
         self.precision = kwargs.get("precision", os.environ.get("RVC_B200_PRECISION", "tc"))
         # replay the static kernel sequence of a (B, T) shape as a CUDA graph from its second call on
         self.use_cuda_graph = bool(kwargs.get("use_cuda_graph", True))
