@@ -68,14 +68,16 @@ struct Params {
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
-    if (fp16) {
-        a = fminf(fmaxf(a, -65504.f), 65504.f);
-        b = fminf(fmaxf(b, -65504.f), 65504.f);
-        __half2 h = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t r;
+    if (fp16) {   // saturating: values beyond +-65504 clamp instead of becoming inf
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    } else {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     }
-    return tc::pack_bf16x2(a, b);
+    return r;
 }
+// leaky_relu for 0 <= slope <= 1 as max(v, slope*v): two instructions, no select
+__device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
 
 template <int NT, int MT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) {
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     auto ACC_FULL = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * MAXABUF + s); };
     auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * MAXABUF + MAXNG + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * MAXABUF + 2 * MAXNG);
+    float* bias_s = reinterpret_cast<float*>(bars + 2 * NSTAGE + 2 * MAXABUF + 2 * MAXNG + 2);   // [njobs][Cout], 16-byte aligned
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
     const int lane = threadIdx.x & 31;
@@ -114,6 +117,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
+    if (warp >= 4)   // biases of all jobs -> shared memory (read back with broadcast LDS.128 in the epilogue)
+        for (int i = threadIdx.x - 128; i < p.njobs * p.Cout; i += NTHREADS - 128) {
+            const int j = i / p.Cout;
+            bias_s[i] = p.jobs[j].bias ? p.jobs[j].bias[i - j * p.Cout] : 0.f;
+        }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -300,24 +308,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 const float mk = (jb.mask && ok) ? jb.mask[(size_t)b * p.Lout + l] : 1.f;
                 tc::tmem_ld32(t_row + cb * 32, r);
                 tc::tmem_ld_wait();
+                const float4* bs4 = reinterpret_cast<const float4*>(bias_s + j * p.Cout + col0);
                 if (jb.gated) {
                     uint32_t r2[32];
                     tc::tmem_ld32(t_row + (cb + NBLK / 2) * 32, r2);
                     tc::tmem_ld_wait();
                     const int col1 = col0 + (NBLK / 2) * 32;
+                    const float* bs1 = bias_s + j * p.Cout + col1;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        float t = __uint_as_float(r[i]) + __ldg(jb.bias + col0 + i);
-                        float sg = __uint_as_float(r2[i]) + __ldg(jb.bias + col1 + i);
+                        float t = __uint_as_float(r[i]) + bias_s[j * p.Cout + col0 + i];
+                        float sg = __uint_as_float(r2[i]) + bs1[i];
                         if (bb) { t += __ldg(bb + col0 + i); sg += __ldg(bb + col1 + i); }
                         r[i] = __float_as_uint(tanhf(t) * rvc::sigmoidf_acc(sg));
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float t = __uint_as_float(r[i]) + (jb.bias ? __ldg(jb.bias + col0 + i) : 0.f);
-                        if (bb) t += __ldg(bb + col0 + i);
-                        r[i] = __float_as_uint(t);
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const float4 b4 = bs4[i4];
+                        r[4 * i4 + 0] = __float_as_uint(__uint_as_float(r[4 * i4 + 0]) + b4.x);
+                        r[4 * i4 + 1] = __float_as_uint(__uint_as_float(r[4 * i4 + 1]) + b4.y);
+                        r[4 * i4 + 2] = __float_as_uint(__uint_as_float(r[4 * i4 + 2]) + b4.z);
+                        r[4 * i4 + 3] = __float_as_uint(__uint_as_float(r[4 * i4 + 3]) + b4.w);
+                    }
+                    if (bb) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(bb + col0 + i));
                     }
                 }
                 if (!ok) continue;
@@ -325,17 +341,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
                 }
+                const float alpha = jb.alpha;
                 if (jb.res) {
+                    if (alpha == 1.f) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = v[i] + jb.alpha * __uint_as_float(r[i]);
+                        for (int i = 0; i < 32; ++i) v[i] = v[i] + __uint_as_float(r[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaf(alpha, __uint_as_float(r[i]), v[i]);
+                    }
+                } else if (alpha == 1.f) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = jb.alpha * __uint_as_float(r[i]);
+                    for (int i = 0; i < 32; ++i) v[i] = alpha * __uint_as_float(r[i]);
                 }
                 float sl = jb.act_slope;
                 if (jb.relu == 2) {   // leaky_relu on the final value itself (both outputs carry it)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = rvc::lrelu(v[i], sl);
+                    for (int i = 0; i < 32; ++i) v[i] = lrelu_max(v[i], sl);
                     sl = 1.f;
                 }
                 if (jb.mask) {
@@ -353,10 +378,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         uint4 pk;
-                        pk.x = pack2(rvc::lrelu(v[8 * u + 0], sl), rvc::lrelu(v[8 * u + 1], sl), p.fp16);
-                        pk.y = pack2(rvc::lrelu(v[8 * u + 2], sl), rvc::lrelu(v[8 * u + 3], sl), p.fp16);
-                        pk.z = pack2(rvc::lrelu(v[8 * u + 4], sl), rvc::lrelu(v[8 * u + 5], sl), p.fp16);
-                        pk.w = pack2(rvc::lrelu(v[8 * u + 6], sl), rvc::lrelu(v[8 * u + 7], sl), p.fp16);
+                        pk.x = pack2(lrelu_max(v[8 * u + 0], sl), lrelu_max(v[8 * u + 1], sl), p.fp16);
+                        pk.y = pack2(lrelu_max(v[8 * u + 2], sl), lrelu_max(v[8 * u + 3], sl), p.fp16);
+                        pk.z = pack2(lrelu_max(v[8 * u + 4], sl), lrelu_max(v[8 * u + 5], sl), p.fp16);
+                        pk.w = pack2(lrelu_max(v[8 * u + 6], sl), lrelu_max(v[8 * u + 7], sl), p.fp16);
                         *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp_out * 16) = pk;
                     }
                 }
@@ -497,6 +522,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
             return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: job %d needs K > 0, dil > 0, 0 <= pad <= (K-1)*dil", j);
         if ((jb.gated ? 1 : 0) != gated) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: jobs of one launch must agree on `gated`");
         if (jb.gated && !jb.bias) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: gated job needs a bias");
+        if (!(jb.act_slope >= 0.f && jb.act_slope <= 1.f)) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: act_slope must be in [0, 1]");
         const int halo = (jb.K - 1) * jb.dil;
         if (jb.pad > PADL || halo - jb.pad > PADR)
             return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: halo %d/%d exceeds the %d zero rows of the packed layout", jb.pad, halo - jb.pad, PADL);
@@ -542,7 +568,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     p.fd_tpj.init((uint32_t)p.tiles_per_job); p.fd_up.init((uint32_t)up); p.fd_nnt.init((uint32_t)p.n_nt); p.fd_nlt.init((uint32_t)p.n_lt);
     p.fp16 = d.dtype == RVC_DT_FP16;
     p.dbg = d.jobs[0].reserved;
-    const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512;
+    const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512 + (size_t)d.njobs * d.Cout * sizeof(float);
     const size_t limit = 227 * 1024;
     // activation stage: as many channel chunks as fit twice (double buffer); even count
     int ach = p.nch;
