@@ -10,10 +10,10 @@
 // sequence live in the global buffer, so there is no boundary logic) and reused by every tap.  Weights, pre-packed
 // [K][Cin/8][Cout][8], stream through a 4-slot ring.
 //
-// Warp roles (384 threads): warp 0 = activation producer, warp 2 = weight producer, warps 1 and 3 = MMA issuers (one per
-// 128-position sub-tile; warp 1 also owns the TMEM allocation),
-// warps 4-11 = epilogue, two warpgroups (TMEM -> registers -> bias / gate / relu / residual / mask -> fp32 NCL and packed-DT
-// stores, all coalesced along positions).  Accumulators are double-buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile
+// Warp roles (512 threads): warp 0 = activation producer, warp 2 = weight producer, warps 1 and 3 = MMA issuers (sub-tiles
+// split between them; warp 1 also owns the TMEM allocation), warps 4-15 = epilogue, three warpgroups (TMEM -> registers ->
+// bias / gate / relu / residual / mask -> fp32 NCL and packed-DT stores, all coalesced along positions).  setmaxnreg moves
+// registers from warpgroup 0 (56) to the epilogue warpgroups (152): the epilogue is instruction-issue bound (ncu).  Accumulators are double-buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile
 // t+1; CTAs are persistent over a static round-robin tile list spanning up to three independent jobs (the three ResBlocks
 // of a generator stage, or the res/skip halves of a WaveNet layer).
 #include "common.cuh"
@@ -28,7 +28,8 @@ constexpr int PADR = 64;
 constexpr int ROWQ = 256;        // packed row count is rounded up to this
 constexpr int NSTAGE = 4;        // weight ring slots
 constexpr int STAGE_BYTES = 16384;
-constexpr int NTHREADS = 384;      // 12 warps: A producer, MMA issuer, W producer, (idle), 8 epilogue warps
+constexpr int NTHREADS = 512;      // 16 warps: warpgroup 0 = A producer, MMA issuers, W producer; warpgroups 1-3 = epilogue
+constexpr int NEG = 3;             // epilogue warpgroups
 constexpr int MAXJOBS = 3;
 constexpr int MAXABUF = 8;        // activation ring slots (as many as fit next to the weight ring)
 constexpr int MAXNG = 4;          // TMEM accumulator groups
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         // NI MMA issuer warps (sub-tiles split between them): every "consumed" barrier collects NI commits
         for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(W_FULL(s), 1); tc::mbar_init(W_EMPTY(s), NI); }
         for (int s = 0; s < MAXABUF; ++s) { tc::mbar_init(A_FULL(s), 1); tc::mbar_init(A_EMPTY(s), NI); }
-        for (int s = 0; s < MAXNG; ++s) { tc::mbar_init(ACC_FULL(s), NI); tc::mbar_init(ACC_EMPTY(s), 8); }
+        for (int s = 0; s < MAXNG; ++s) { tc::mbar_init(ACC_FULL(s), NI); tc::mbar_init(ACC_EMPTY(s), 4 * NEG); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
@@ -142,6 +143,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         b = (int)q;
     };
 
+    // register rebalancing (setmaxnreg): the producer / issuer warpgroup needs few registers, the epilogue warpgroups many
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ======================= activation producer =======================
         uint32_t ast = 0, aph = 0;
@@ -271,11 +275,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             }
             if (tc::elect_one()) tc::umma_commit(ACC_FULL(g));
         }
-    } else if (warp >= 4) {
-        // ======================= epilogue: 2 warpgroups x 4 warps; warp%4 selects the TMEM lane quarter, the warpgroup
-        // takes every other (sub-tile, 32-column block) work item =======================
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        // ======================= epilogue: NEG warpgroups x 4 warps; warp%4 selects the TMEM lane quarter, the warpgroup
+        // takes every NEG-th (sub-tile, 32-column block) work item =======================
         const int q = warp & 3;
-        const int eg = (warp - 4) >> 2;
+        const int eg = (warp - 4) >> 2;   // 0 .. NEG-1
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             int j, b, lt, nt, ph;
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             tc::mbar_wait(ACC_FULL(g), gph);
             tc::fence_after_sync();
 #pragma unroll 1
-            for (int item = eg; item < MT * nblk; item += 2) {
+            for (int item = eg; item < MT * nblk; item += NEG) {
                 const int m = item / nblk, cb = item - m * nblk;
                 const int lin = lt * TM + m * BM + q * 32 + lane;
                 const int l = lin * p.up + ph - p.pshift;          // output position
