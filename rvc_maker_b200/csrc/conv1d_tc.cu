@@ -558,7 +558,8 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     if (d.Cout % NT || (gated && NT % 64)) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt=%d does not tile Cout=%d (gated=%d)", NT, d.Cout, gated);
     // sub-tiles per CTA tile: as many as still leave >= 2 waves of tiles (fewer, larger tiles amortise the per-tile handshakes);
     // 4 sub-tiles need NT <= 64 (TMEM: 2 groups x 4 x NT columns)
-    if (mt == 0) mt = (NT <= 64 && up == 1 && ntiles(NT, 4) >= 2L * sms) ? 4 : (ntiles(NT, 2) >= 2L * sms ? 2 : 1);
+    // (weight bytes streamed per output halve with every doubling, so 2 sub-tiles are preferred as soon as they fill the GPU once)
+    if (mt == 0) mt = (NT <= 64 && up == 1 && ntiles(NT, 4) >= 2L * sms) ? 4 : (ntiles(NT, 2) >= (long)sms ? 2 : 1);
     if (mt != 1 && mt != 2 && mt != 4) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: mt must be 1, 2 or 4");
     if (mt == 4 && NT > 64) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: mt = 4 needs nt <= 64");
     const int TM = BM * mt;
