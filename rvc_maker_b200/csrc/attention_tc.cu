@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
     float* ev_s = qe_s + AQ * NR;        // [NR][dk]
     float* m_s = ev_s + NR * dk;         // [AG][AQ]
     float* l_s = m_s + AG * AQ;          // [AG][AQ]
+    float* q_s = l_s + AG * AQ;          // [dk][AQ]   q / sqrt(dk)
+    float* ek_s = q_s + dk * AQ;         // [NR][dk]
     const int ti = tid % AQ, g = tid / AQ;
     const int i0 = blockIdx.x * AQ, i = i0 + ti;
     const float* qb = qkv + ((int64_t)b * 3 * H + h * dk) * T;
@@ -55,13 +57,22 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
     const float* Sb = S + ((int64_t)b * nh + h) * Tk * T;
     const float rs = sqrtf((float)dk);
 
-    for (int idx = tid; idx < NR * dk; idx += ANT) ev_s[idx] = emb_v[idx];
+    // stage the query tile and both relative tables (parallel, coalesced), then the banded q.Ek terms from shared memory
+    for (int idx = tid; idx < NR * dk; idx += ANT) { ev_s[idx] = emb_v[idx]; ek_s[idx] = emb_k[idx]; }
+    for (int idx = tid; idx < dk * AQ; idx += ANT) {
+        const int q = idx % AQ, d = idx / AQ;
+        q_s[idx] = (i0 + q < T) ? qb[(int64_t)d * T + i0 + q] / rs : 0.f;
+    }
+    __syncthreads();
     for (int idx = tid; idx < AQ * NR; idx += ANT) {
-        const int q = idx % AQ, r = idx / AQ;   // consecutive threads -> consecutive queries (coalesced q reads)
-        float acc = 0.f;
-        if (i0 + q < T)
-            for (int d = 0; d < dk; ++d) acc = fmaf(qb[(int64_t)d * T + i0 + q] / rs, emb_k[r * dk + d], acc);
-        qe_s[q * NR + r] = acc;
+        const int q = idx % AQ, r = idx / AQ;
+        float a0 = 0.f, a1 = 0.f;
+        for (int d = 0; d + 1 < dk; d += 2) {
+            a0 = fmaf(q_s[d * AQ + q], ek_s[r * dk + d], a0);
+            a1 = fmaf(q_s[(d + 1) * AQ + q], ek_s[r * dk + d + 1], a1);
+        }
+        if (dk & 1) a0 = fmaf(q_s[(dk - 1) * AQ + q], ek_s[r * dk + dk - 1], a0);
+        qe_s[q * NR + r] = a0 + a1;
     }
     __syncthreads();
 
@@ -179,7 +190,7 @@ RVC_API int rvc_attn_softmax(const float* S, const float* qkv, const float* mask
     if (dk % AG || dk / AG > 16) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: head dim %d must be a multiple of 32 and <= 512", dk);
     if ((int64_t)B * n_heads > 65535) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: B*heads > 65535");
     const int NR = 2 * window + 1;
-    const size_t smem = (size_t)(AQ * NR + NR * dk + 2 * AG * AQ) * sizeof(float);
+    const size_t smem = (size_t)(AQ * NR + 2 * NR * dk + 2 * AG * AQ + dk * AQ) * sizeof(float);
     if (smem > 200 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: window too large");
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
