@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 12
+#define RVC_ABI_VERSION 13
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -196,10 +196,13 @@ typedef struct {
  * phase blocks [up][K][Cin/8][Cout][8] with K = ceil(k/up) taps, block r tap t = w_T[:, :, r + (K-1-t)*up] (zero past k), every
  * job uses pad = K-1, and the result of input position q, phase r lands at output position q*up + r - pshift
  * (pshift = (k-up)/2); res / mask / y_f32 / y_act are indexed at OUTPUT positions (length L*up).
+ *
+ * sum_jobs = 1 (stage average of the ResBlocks, synthesizers.py:157-159): every tile runs ALL jobs into one accumulator and
+ * the epilogue of job 0 receives v = alpha * (sum_j conv_j + sum_j bias_j + sum_j res_j); outputs / mask / act_slope of job 0.
  */
 typedef struct {
     rvc_tc_job jobs[3];
-    int32_t njobs, B, Cin, Cout, L, dtype, nt, mt, up, pshift;
+    int32_t njobs, B, Cin, Cout, L, dtype, nt, mt, up, pshift, sum_jobs, reserved;
 } rvc_conv1d_tc_desc;
 int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);
 

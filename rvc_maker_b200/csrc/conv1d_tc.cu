@@ -63,6 +63,7 @@ struct Params {
     FastDiv fd_tpj, fd_up, fd_nnt, fd_nlt;
     int fp16;         // operand format: 0 = bf16, 1 = fp16
     int nabuf;        // activation ring depth (2..MAXABUF)
+    int sum_jobs;     // 1: every tile runs ALL jobs into one accumulator (stage average of the ResBlocks)
     int dbg;          // timing experiments only: 1 = epilogue skips global I/O, 2 = skip MMA issue, 4 = skip operand loads
     int up, pshift;   // transposed-conv phase mode: output position = l * up + phase - pshift (up = 1: plain conv)
     int Lout, Lp_out; // output length and packed rows of the output
@@ -120,8 +121,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
     if (warp >= 4)   // biases of all jobs -> shared memory (read back with broadcast LDS.128 in the epilogue)
         for (int i = threadIdx.x - 128; i < p.njobs * p.Cout; i += NTHREADS - 128) {
-            const int j = i / p.Cout;
-            bias_s[i] = p.jobs[j].bias ? p.jobs[j].bias[i - j * p.Cout] : 0.f;
+            const int j = i / p.Cout, c = i - j * p.Cout;
+            float v = p.jobs[j].bias ? p.jobs[j].bias[c] : 0.f;
+            if (p.sum_jobs && j == 0)
+                for (int jj = 1; jj < p.njobs; ++jj) v += p.jobs[jj].bias ? p.jobs[jj].bias[c] : 0.f;
+            bias_s[i] = v;
         }
     tc::fence_before_sync();
     __syncthreads();
@@ -152,7 +156,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int j, b, lt, nt, ph;
             decode(tile, j, b, lt, nt, ph);
-            const rvc_tc_job& jb = p.jobs[j];
+            for (int jj = 0; jj < (p.sum_jobs ? p.njobs : 1); ++jj) {
+            const rvc_tc_job& jb = p.jobs[p.sum_jobs ? jj : j];
             const int pad = jb.pad;
             const int rows = TM + (jb.K - 1) * jb.dil;
             for (int cs = 0; cs < p.ncs; ++cs) {
@@ -173,6 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                                  (uint32_t)rows * 16, A_FULL(ast));
                 if (++ast == (uint32_t)p.nabuf) { ast = 0; aph ^= 1; }
             }
+            }
         }
     } else if (warp == 2) {
         // ======================= weight producer =======================
@@ -180,7 +186,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int j, b, lt, nt, ph;
             decode(tile, j, b, lt, nt, ph);
-            const rvc_tc_job& jb = p.jobs[j];
+            for (int jj = 0; jj < (p.sum_jobs ? p.njobs : 1); ++jj) {
+            const rvc_tc_job& jb = p.jobs[p.sum_jobs ? jj : j];
             const size_t w_cs = jb.w_cs ? (size_t)jb.w_cs : (size_t)p.Cout;      // rows between consecutive weight chunks
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(jb.w) + (size_t)b * jb.w_bs + (size_t)ph * jb.K * p.nch * w_cs * 16;
             for (int cs = 0; cs < p.ncs; ++cs) {
@@ -210,6 +217,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
                 }
             }
+            }
         }
     } else if (warp == 1 || (NI == 2 && warp == 3)) {
         // ======================= MMA issuers: warp 1 -> sub-tiles 0 (and 2), warp 3 -> sub-tiles 1 (and 3).  The whole warp runs the (uniform)
@@ -226,14 +234,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             int j, b, lt, nt, ph;
             decode(tile, j, b, lt, nt, ph);
-            const int K = p.jobs[j].K;
-            const uint32_t dil = (uint32_t)p.jobs[j].dil;
             const int g = it % NG;
             const uint32_t gph = (it / NG) & 1;
             tc::mbar_wait(ACC_EMPTY(g), gph ^ 1);
             tc::fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)((g * MT + m) * NT);   // + 2*NT for this issuer's second sub-tile
             uint32_t accumulate = 0;
+            for (int jj = 0; jj < (p.sum_jobs ? p.njobs : 1); ++jj) {
+            const int K = p.jobs[p.sum_jobs ? jj : j].K;
+            const uint32_t dil = (uint32_t)p.jobs[p.sum_jobs ? jj : j].dil;
             for (int cs = 0; cs < p.ncs; ++cs) {
                 const int na = min(p.ach, p.nch - cs * p.ach);
                 tc::mbar_wait(A_FULL(ast), aph);
@@ -273,6 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 if (tc::elect_one()) tc::umma_commit(A_EMPTY(ast));
                 if (++ast == (uint32_t)p.nabuf) { ast = 0; aph ^= 1; }
             }
+            }
             if (tc::elect_one()) tc::umma_commit(ACC_FULL(g));
         }
     }
@@ -310,6 +320,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     const float* rp = jb.res + (size_t)b * jb.res_bs + (size_t)co0 * jb.res_cs + l;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = rp[(size_t)i * jb.res_cs];
+                    if (p.sum_jobs)
+                        for (int jj = 1; jj < p.njobs; ++jj) {
+                            const rvc_tc_job& j2 = p.jobs[jj];
+                            const float* rp2 = j2.res + (size_t)b * j2.res_bs + (size_t)co0 * j2.res_cs + l;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] += rp2[(size_t)i * j2.res_cs];
+                        }
                 }
                 const float mk = (jb.mask && ok) ? jb.mask[(size_t)b * p.Lout + l] : 1.f;
                 tc::tmem_ld32(t_row + cb * 32, r);
@@ -348,7 +365,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
                 }
                 const float alpha = jb.alpha;
-                if (jb.res) {
+                if (p.sum_jobs) {   // v = alpha * (sum_j conv_j + sum_j bias_j + sum_j res_j)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = alpha * ((jb.res ? v[i] : 0.f) + __uint_as_float(r[i]));
+                } else if (jb.res) {
                     if (alpha == 1.f) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = v[i] + __uint_as_float(r[i]);
@@ -543,7 +563,13 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     // transposed mode: input positions q in [0, L + ceil(pshift/up)) reach valid outputs (rows past L are zero in the packed buffer)
     const int Lq = up > 1 ? d.L + rvc::cdiv(d.pshift, up) : d.L;
     const int Lout = up > 1 ? d.L * up : d.L;
-    auto ntiles = [&](int nt_, int mt_) { return (long)d.njobs * d.B * rvc::cdiv(Lq, BM * mt_) * (d.Cout / nt_) * up; };
+    const int njt = d.sum_jobs ? 1 : d.njobs;   // jobs that multiply the tile count
+    if (d.sum_jobs) {
+        if (gated || up > 1) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs excludes gated / transposed mode");
+        for (int j = 1; j < d.njobs; ++j)
+            if ((d.jobs[j].res == nullptr) != (d.jobs[0].res == nullptr)) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs needs res on all jobs or none");
+    }
+    auto ntiles = [&](int nt_, int mt_) { return (long)njt * d.B * rvc::cdiv(Lq, BM * mt_) * (d.Cout / nt_) * up; };
     if (NT == 0) {
         const int cands[3] = {128, 64, 32};
         for (int i = 0; i < 3; ++i) {
@@ -571,9 +597,10 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     p.n_lt = rvc::cdiv(Lq, TM);
     p.n_nt = d.Cout / NT;
     p.tiles_per_job = d.B * p.n_lt * p.n_nt * up;
-    p.total_tiles = p.tiles_per_job * d.njobs;
+    p.total_tiles = p.tiles_per_job * njt;
     p.fd_tpj.init((uint32_t)p.tiles_per_job); p.fd_up.init((uint32_t)up); p.fd_nnt.init((uint32_t)p.n_nt); p.fd_nlt.init((uint32_t)p.n_lt);
     p.fp16 = d.dtype == RVC_DT_FP16;
+    p.sum_jobs = d.sum_jobs ? 1 : 0;
     p.dbg = d.jobs[0].reserved;
     const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512 + (size_t)d.njobs * d.Cout * sizeof(float);
     const size_t limit = 227 * 1024;

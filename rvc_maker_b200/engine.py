@@ -538,6 +538,7 @@ class Engine:
         big = max(ch * ln for ch, ln in zip(chans, lens))
         S = [self._buf(p, B * big) for _ in range(4)]
         cur, curC, curL = (xpre, None, None), U, T   # cur = (x, x2, x3): the stage input is (x + x2 + x3) / nk when x2 is set
+        prev_ua = None
         for i, (u, k) in enumerate(zip(rates, uks)):
             Ci, Li = chans[i], lens[i]
             dt = self.stage_dt[i]
@@ -551,6 +552,8 @@ class Engine:
                 udt = self.up_dt[i]
                 if i == 0 and xpre_a is not None:
                     ua = xpre_a
+                elif prev_ua is not None:
+                    ua = prev_ua          # written by the previous stage's fused last conv2
                 else:
                     ua = self._packed(p, B, curC, curL)
                     x2 = cur[1].data_ptr() if cur[1] is not None else None
@@ -603,6 +606,7 @@ class Engine:
                                        pad=(kk - 1) // 2, bias=W[f"rb{i}_{j}_c2b{mm}"], pre_slope=LRELU_SLOPE, res=src,
                                        out_scale=1.0 / nk, beta=0.0 if j == 0 else 1.0)
                 cur, curC, curL = (S[3], None, None), Ci, Li
+                prev_ua = None
             else:
                 # ---- tensor-core ResBlocks: the nk blocks advance in lock-step, one persistent launch per conv step
                 esz = 2
@@ -615,6 +619,10 @@ class Engine:
                     p.add(f"pack{i}", lib.rvc_pack_act, S[0].data_ptr(), None, None, 1.0, Ci * Li, Li, None, xa.data_ptr(), B, Ci, Li, dt,
                           LRELU_SLOPE, bytes_=B * Ci * Li * (4.0 + esz), kind="pack_act")
                 order = sorted(range(nk), key=lambda j: -rks[j])          # heavy kernels first (static round-robin tiles)
+                nxt = i + 1
+                next_tc_ups = nxt < len(rates) and self.up_dt[nxt] is not None and self.up_dt[nxt] == dt
+                next_ua = self._packed(p, B, Ci, Li) if next_tc_ups else None   # packed lrelu(stage average) for the next ups
+                need_f32 = not next_tc_ups                                         # conv_post / fp32 ups read the fp32 average
                 nsteps = len(rds[0])
                 assert all(len(dl) == nsteps for dl in rds)
                 for mm in range(nsteps):
@@ -622,6 +630,11 @@ class Engine:
                     for half in (1, 2):
                         d = Conv1dTcDesc()
                         d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype = nk, B, Ci, Ci, Li, dt
+                        # last conv2 of the stage: all three blocks accumulate into one tile and the stage average
+                        # (x0' + x1' + x2') / nk is written once — fp32 for conv_post / an fp32 ups, and (or) directly as
+                        # the packed leaky_relu input of the next tensor-core ups (synthesizers.py:150,157-159)
+                        fused = last and half == 2
+                        d.sum_jobs = int(fused)
                         fl = 0.0
                         for slot, j in enumerate(order):
                             jb = d.jobs[slot]
@@ -635,20 +648,24 @@ class Engine:
                                 jb.a = ta[j].data_ptr()
                                 jb.w, jb.bias = W[f"rb{i}_{j}_c2w{mm}"].data_ptr(), W[f"rb{i}_{j}_c2b{mm}"].data_ptr()
                                 jb.res, jb.res_bs, jb.res_cs = (S[0] if mm == 0 else P[j]).data_ptr(), Ci * Li, Li
-                                jb.y_f32, jb.y_bs, jb.y_cs = P[j].data_ptr(), Ci * Li, Li
-                                if not last:
+                                if not fused:
+                                    jb.y_f32, jb.y_bs, jb.y_cs = P[j].data_ptr(), Ci * Li, Li
                                     jb.y_act = pa[j].data_ptr()
+                                elif slot == 0:
+                                    if need_f32:
+                                        jb.y_f32, jb.y_bs, jb.y_cs = S[0].data_ptr(), Ci * Li, Li
+                                    if next_ua is not None:
+                                        jb.y_act = next_ua.data_ptr()
                                 jb.K, jb.dil, jb.pad = kk, 1, (kk - 1) // 2
-                            jb.act_slope, jb.alpha = LRELU_SLOPE, 1.0
+                            jb.act_slope, jb.alpha = LRELU_SLOPE, (1.0 / nk if fused else 1.0)
                             fl += 2.0 * B * Ci * Ci * kk * Li
                         p.keep.append(d)
-                        by = nk * B * Ci * Li * (2.0 * esz if half == 1 else (esz + 8.0 + (0 if last else esz)))
+                        by = nk * B * Ci * Li * (2.0 * esz if half == 1 else (esz + 8.0 + esz)) if not fused else \
+                            B * Ci * Li * (nk * (esz + 4.0) + (4.0 if need_f32 else 0.0) + (esz if next_ua is not None else 0.0))
                         p.add(f"rbtc{i}_s{mm}_c{half}", lib.rvc_conv1d_tc, C.byref(d), flops=fl, bytes_=by,
                               kind=f"conv1d_tc_{'bf16' if dt == DT_BF16 else 'fp16'}[C{Ci}]")
-                if nk == 3:
-                    cur, curC, curL = (P[0], P[1], P[2]), Ci, Li
-                else:
-                    raise NotImplementedError("tensor-core path expects 3 ResBlocks per stage")
+                cur, curC, curL = (S[0], None, None), Ci, Li      # stage average (fp32), valid when need_f32
+                prev_ua = next_ua
         p.o = self._buf(p, B, 1, Lfin)
         x2 = cur[1].data_ptr() if cur[1] is not None else None
         x3 = cur[2].data_ptr() if cur[2] is not None else None

@@ -194,6 +194,45 @@ def test_conv_transpose_phase_mode(Cin, Cout, k, u, Lin, dtype):
     assert pad_rows_zero(y_act, B, Cout, Lout, dtype, rows_out)
 
 
+def test_sum_jobs_stage_average():
+    """sum_jobs: three convs (k = 11/7/3) accumulate into one tile; v = alpha * (sum conv + sum bias + sum res)."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    B, Cc, L, dtype = 2, 64, 3001, FP16
+    g = torch.Generator(device="cpu").manual_seed(9)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(L)
+    d = _lib.Conv1dTcDesc()
+    d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.sum_jobs = 3, B, Cc, Cc, L, dtype, 1
+    y = torch.zeros(B, Cc, L, device=DEV)
+    y_act = torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+    keep, ref = [], 0.0
+    for j, (k, dil) in enumerate(((11, 5), (7, 3), (3, 1))):
+        x = torch.randn(B, Cc, L, generator=g).to(DEV)
+        w = (torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+        bias = torch.randn(Cc, generator=g).to(DEV)
+        res = torch.randn(B, Cc, L, generator=g).to(DEV)
+        a = torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+        wp = torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+        _lib.check(lib.rvc_pack_act(x.data_ptr(), None, None, 1.0, Cc * L, L, None, a.data_ptr(), B, Cc, L, dtype, 0.1, st), "pack_act")
+        _lib.check(lib.rvc_pack_weight(w.data_ptr(), wp.data_ptr(), Cc, Cc, k, dtype, st), "pack_weight")
+        jb = d.jobs[j]
+        jb.a, jb.w, jb.bias = a.data_ptr(), wp.data_ptr(), bias.data_ptr()
+        jb.res, jb.res_bs, jb.res_cs = res.data_ptr(), Cc * L, L
+        jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = k, dil, (k - 1) // 2 * dil, 1.0 / 3.0, 0.1
+        if j == 0:
+            jb.y_f32, jb.y_bs, jb.y_cs, jb.y_act = y.data_ptr(), Cc * L, L, y_act.data_ptr()
+        keep += [x, w, bias, res, a, wp]
+        ref = ref + F.conv1d(rnd(F.leaky_relu(x, 0.1), dtype).double(), rnd(w, dtype).double(), bias.double(), dilation=dil,
+                             padding=(k - 1) // 2 * dil) + res.double()
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "conv1d_tc(sum)")
+    torch.cuda.synchronize()
+    ref = ref / 3.0
+    assert float((y.double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
+    assert torch.equal(unpack(y_act, B, Cc, L, dtype, rows), rnd(F.leaky_relu(y, 0.1), dtype))
+
+
 def test_shape_errors_are_loud():
     from rvc_maker_b200 import _lib
 
