@@ -652,8 +652,8 @@ class Engine:
                                     jb.y_f32, jb.y_bs, jb.y_cs = P[j].data_ptr(), Ci * Li, Li
                                     jb.y_act = pa[j].data_ptr()
                                 elif slot == 0:
-                                    if need_f32:
-                                        jb.y_f32, jb.y_bs, jb.y_cs = S[0].data_ptr(), Ci * Li, Li
+                                    if need_f32:   # into P[0]'s buffer: every thread reads its residuals before it writes (in-place safe)
+                                        jb.y_f32, jb.y_bs, jb.y_cs = S[1].data_ptr(), Ci * Li, Li
                                     if next_ua is not None:
                                         jb.y_act = next_ua.data_ptr()
                                 jb.K, jb.dil, jb.pad = kk, 1, (kk - 1) // 2
@@ -664,7 +664,7 @@ class Engine:
                             B * Ci * Li * (nk * (esz + 4.0) + (4.0 if need_f32 else 0.0) + (esz if next_ua is not None else 0.0))
                         p.add(f"rbtc{i}_s{mm}_c{half}", lib.rvc_conv1d_tc, C.byref(d), flops=fl, bytes_=by,
                               kind=f"conv1d_tc_{'bf16' if dt == DT_BF16 else 'fp16'}[C{Ci}]")
-                cur, curC, curL = (S[0], None, None), Ci, Li      # stage average (fp32), valid when need_f32
+                cur, curC, curL = (S[1], None, None), Ci, Li      # stage average (fp32), valid when need_f32
                 prev_ua = next_ua
         p.o = self._buf(p, B, 1, Lfin)
         x2 = cur[1].data_ptr() if cur[1] is not None else None
