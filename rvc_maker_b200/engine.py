@@ -30,64 +30,26 @@ class V:
         self.cs = L
 
 
-JOIN = "__join_side_stream__"
-
-
 class Plan:
-    """Flat launch list.  `side=True` ops form an independent branch (SineGen, noise convs: they depend only on the inputs)
-    that is forked onto a second stream at the start of run() and joined at the JOIN marker — inside a CUDA-graph capture this
-    becomes a parallel graph branch that fills the SMs the small encoder / flow launches leave idle."""
-
     def __init__(self):
         self.ops = []
         self.meta = []
         self.keep = []
         self.launches = 0
-        self.side_ops = []
-        self.side_stream = None
-        self._side_running = False
 
-    def add(self, name, fn, *args, launches=1, flops=0.0, bytes_=0.0, kind="other", side=False):
-        meta = dict(name=name, kind=kind, flops=float(flops), bytes=float(bytes_), launches=launches)
-        if side:
-            self.side_ops.append((name, fn, args, meta))
-        else:
-            self.ops.append((name, fn, args))
-            self.meta.append(meta)
+    def add(self, name, fn, *args, launches=1, flops=0.0, bytes_=0.0, kind="other"):
+        self.ops.append((name, fn, args))
+        self.meta.append(dict(name=name, kind=kind, flops=float(flops), bytes=float(bytes_), launches=launches))
         self.launches += launches
-
-    def add_join(self):
-        self.ops.append((JOIN, None, ()))
-        self.meta.append(None)
 
     def add_py(self, fn):
         self.ops.append((None, fn, ()))
         self.meta.append(None)
 
-    def start_side(self):
-        """Fork the side branch off the current stream (call as early as its inputs are in place)."""
-        if not self.side_ops or self._side_running:
-            return
-        if self.side_stream is None:
-            self.side_stream = torch.cuda.Stream()
-        side = self.side_stream
-        side.wait_stream(torch.cuda.current_stream())
-        for name, fn, args, _ in self.side_ops:
-            rc = fn(*args, side.cuda_stream)
-            if rc != 0:
-                _lib.check(rc, name)
-        self._side_running = True
-
     def run(self, stream):
-        self.start_side()
-        cur, side = torch.cuda.current_stream(), (self.side_stream if self._side_running else None)
-        self._side_running = False
         for name, fn, args in self.ops:
             if name is None:
                 fn()
-            elif name is JOIN:
-                if side is not None:
-                    cur.wait_stream(side)  # join
             else:
                 rc = fn(*args, stream)
                 if rc != 0:
@@ -96,12 +58,9 @@ class Plan:
     def run_timed(self, stream):
         """Replay with a CUDA-event pair around every C-ABI call (profiling aid; not used for headline numbers)."""
         evs = []
-        seq = [((n, f, a), m) for n, f, a, m in self.side_ops] + list(zip(self.ops, self.meta))   # profiling: side branch inline
-        for (name, fn, args), meta in seq:
+        for (name, fn, args), meta in zip(self.ops, self.meta):
             if name is None:
                 fn()
-                continue
-            if name is JOIN:
                 continue
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -555,7 +514,7 @@ class Engine:
             har = self._buf(p, B, Lfin)
             scratch = self._buf(p, B, T)
             p.add("sine_source", lib.rvc_sine_source_f32, p.f0.data_ptr(), p.eps_src.data_ptr(), W["lin_w"].data_ptr(), W["lin_b"].data_ptr(),
-                  scratch.data_ptr(), har.data_ptr(), B, T, upp, c["sr"], launches=2, bytes_=8.0 * B * Lfin, kind="sine_source_f32", side=True)
+                  scratch.data_ptr(), har.data_ptr(), B, T, upp, c["sr"], launches=2, bytes_=8.0 * B * Lfin, kind="sine_source_f32")
         xpre = self._buf(p, B, U, T)
         xpre_a = None
         if self.enc_tc:
@@ -580,7 +539,6 @@ class Engine:
         S = [self._buf(p, B * big) for _ in range(4)]
         cur, curC, curL = (xpre, None, None), U, T   # cur = (x, x2, x3): the stage input is (x + x2 + x3) / nk when x2 is set
         prev_ua = None
-        p.add_join()   # SineGen / noise-conv branch must be complete before the first ups
         for i, (u, k) in enumerate(zip(rates, uks)):
             Ci, Li = chans[i], lens[i]
             dt = self.stage_dt[i]
@@ -602,17 +560,14 @@ class Engine:
                     x3 = cur[2].data_ptr() if cur[2] is not None else None
                     p.add(f"pack_up{i}", lib.rvc_pack_act, cur[0].data_ptr(), x2, x3, float(nk), curC * curL, curL, None, ua.data_ptr(), B, curC,
                           curL, udt, LRELU_SLOPE, bytes_=B * curC * curL * (2.0 + (12.0 if x2 else 4.0)), kind="pack_act")
-                nz = None
                 if c["f0"]:
-                    # noise conv of this stage: side branch, own buffer (the ups epilogue adds it as its residual input)
-                    nz = self._buf(p, B, Ci, Li)
                     p.add(f"noise{i}", lib.rvc_noise_conv_f32, har.data_ptr(), Lfin, W[f"nz_w{i}"].data_ptr(), W[f"nz_b{i}"].data_ptr(),
-                          nz.data_ptr(), Ci * Li, B, Ci, Li, kn, sn, pn, flops=2.0 * B * Ci * Li * kn, bytes_=4.0 * B * (Ci * Li + Li * sn),
-                          kind="noise_conv_f32", side=True)
+                          S[0].data_ptr(), Ci * Li, B, Ci, Li, kn, sn, pn, flops=2.0 * B * Ci * Li * kn, bytes_=4.0 * B * (Ci * Li + Li * sn),
+                          kind="noise_conv_f32")
                 if dt is not None and dt == udt:
                     xa = self._packed(p, B, Ci, Li)
                 M = -(-k // u)
-                self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(V(nz, Ci, Li) if nz is not None else None), y=vs0, y_act=xa,
+                self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(vs0 if c["f0"] else None), y=vs0, y_act=xa,
                                              act_slope=LRELU_SLOPE, K=M, pad=M - 1)],
                          B=B, Cin=curC, Cout=Ci, L=curL, dtype=udt, up=u, pshift=(k - u) // 2, tag=f"ups",
                          flops=2.0 * B * curC * Ci * k * curL)
@@ -782,7 +737,6 @@ class Engine:
                     pd.eps_src.normal_()                  # randn_like(sine_waves), :98
 
             def body(st):
-                pd.start_side()    # SineGen + noise convs overlap the encoder and the flow
                 pe.run(st)
                 pd.zp.copy_(pe.zp[:, :, head:])
                 pd.mask.copy_(pe.mask[:, head:])
