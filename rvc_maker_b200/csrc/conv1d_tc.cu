@@ -131,6 +131,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: everything above (barrier init, TMEM allocation, bias staging — constant data only)
+    // may overlap the tail of the previous kernel in the stream; activations are only touched after the wait.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // tile id -> (job, batch, L tile, N tile, phase); phase is the fastest index so that the u phases of one input tile run on
     // neighbouring CTAs at the same time and share the activation tile through L2
@@ -493,7 +497,18 @@ int launch_tc(const Params& p, size_t smem, int grid, cudaStream_t stream) {
         if (e != cudaSuccess) return rvc::fail((int)e, "rvc_conv1d_tc: smem opt-in: %s", cudaGetErrorString(e));
         if (dev >= 0 && dev < 64) opted[dev] = true;
     }
-    kern<<<grid, NTHREADS, smem, stream>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+    if (le != cudaSuccess) return rvc::fail((int)le, "rvc_conv1d_tc: launch: %s", cudaGetErrorString(le));
     return rvc::check_launch("rvc_conv1d_tc");
 }
 
