@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
                                                            const float* __restrict__ emb_k, const float* __restrict__ emb_v, uint8_t* __restrict__ P,
                                                            float* __restrict__ R, uint8_t* __restrict__ vw, int H, int nh, int T, int Tk, int Lp,
                                                            int W, int nqb) {
+    rvc::pdl_prologue();
     extern __shared__ float sm[];
     const int dk = H / nh, NR = 2 * W + 1;
     const int h = blockIdx.y % nh, b = blockIdx.y / nh;
@@ -199,7 +200,7 @@ RVC_API int rvc_attn_softmax(const float* S, const float* qkv, const float* mask
     const int nqb = rvc::cdiv(T, AQ);
     const int nvb = rvc::cdiv(dk * (Tk / 8), ANT);
     dim3 grid(nqb + nvb, B * n_heads);
-    attn_softmax_kernel<<<grid, ANT, smem, (cudaStream_t)stream>>>(S, qkv, mask, emb_k, emb_v, (uint8_t*)P, R, (uint8_t*)vw, H, n_heads, T, Tk,
+    rvc::launch_pdl(attn_softmax_kernel, dim3(grid), dim3(ANT), (size_t)(smem), (cudaStream_t)stream, S, qkv, mask, emb_k, emb_v, (uint8_t*)P, R, (uint8_t*)vw, H, n_heads, T, Tk,
                                                                    (int)rvc_packed_rows(T), window, nqb);
     return rvc::check_launch("rvc_attn_softmax");
 }

@@ -35,4 +35,26 @@ __device__ __forceinline__ float sigmoidf_acc(float v) { return 1.f / (1.f + exp
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch: kernels call pdl_prologue() first (lets the next kernel in the stream be scheduled early, then
+// waits until every prerequisite grid has completed and its writes are visible); hosts launch through launch_pdl().
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace rvc

@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
 __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, const float* __restrict__ x2, const float* __restrict__ x3,
                                                        float in_div, int64_t x_bs, int64_t x_cs, const float* __restrict__ mask,
                                                        uint8_t* __restrict__ y, int nch, int L, int Lp, float slope, int fp16) {
+    rvc::pdl_prologue();
     const int l = blockIdx.x * 256 + threadIdx.x;
     const int c = blockIdx.y, b = blockIdx.z;
     if (l >= L) return;
@@ -532,7 +533,7 @@ RVC_API int rvc_pack_act(const float* x, const float* x2, const float* x3, float
     if (B <= 0 || B > 65535 || C <= 0 || C % 8 || L < 0) return rvc::fail(RVC_ESHAPE, "rvc_pack_act: bad shape (C=%d must be a multiple of 8)", C);
     if (L == 0) return 0;
     dim3 grid(rvc::cdiv(L, 256), C / 8, B);
-    pack_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x2, x3, in_div, x_bs, x_cs, mask, (uint8_t*)y, C / 8, L, packed_rows(L), slope,
+    rvc::launch_pdl(pack_act_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, x, x2, x3, in_div, x_bs, x_cs, mask, (uint8_t*)y, C / 8, L, packed_rows(L), slope,
                                                             dtype == RVC_DT_FP16);
     return rvc::check_launch("rvc_pack_act");
 }

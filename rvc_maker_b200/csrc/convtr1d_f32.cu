@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(256) conv_post_f32_kernel(const float* __restr
                                                             const float* __restrict__ x3, float in_div, int64_t x_bs, int64_t x_cs,
                                                             const float* __restrict__ w, float* __restrict__ y, int64_t y_bs,
                                                             int C, int L, float slope) {
+    rvc::pdl_prologue();
     extern __shared__ float w_s[];  // [C][7]
     for (int i = threadIdx.x; i < C * 7; i += blockDim.x) w_s[i] = w[i];
     __syncthreads();
@@ -201,7 +202,7 @@ RVC_API int rvc_conv_post_f32(const float* x, const float* x2, const float* x3, 
     if (B <= 0 || B > 65535 || C <= 0 || C > 1024 || L < 0) return rvc::fail(RVC_ESHAPE, "rvc_conv_post_f32: bad shape");
     if (L == 0) return 0;
     dim3 grid(rvc::cdiv(rvc::cdiv(L, 4), 256), B);
-    conv_post_f32_kernel<<<grid, 256, C * 7 * sizeof(float), (cudaStream_t)stream>>>(x, x2, x3, in_div, x_bs, x_cs, w, y, y_bs, C, L, slope);
+    rvc::launch_pdl(conv_post_f32_kernel, dim3(grid), dim3(256), (size_t)(C * 7 * sizeof(float)), (cudaStream_t)stream, x, x2, x3, in_div, x_bs, x_cs, w, y, y_bs, C, L, slope);
     return rvc::check_launch("rvc_conv_post_f32");
 }
 
@@ -213,6 +214,7 @@ namespace {
 __global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __restrict__ har, int64_t har_bs, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y, int64_t y_bs, int C,
                                                              int Lout, int kn, int sn, int pn) {
+    rvc::pdl_prologue();
     extern __shared__ float w_s[];  // [32][kn]
     const int co0 = blockIdx.y * 32, b = blockIdx.z;
     for (int i = threadIdx.x; i < 32 * kn; i += 128) {
@@ -246,6 +248,6 @@ RVC_API int rvc_noise_conv_f32(const float* har, int64_t har_bs, const float* w,
     if (B <= 0 || B > 65535 || C <= 0 || Lout < 0 || kn <= 0 || kn > 1024 || sn <= 0 || pn < 0) return rvc::fail(RVC_ESHAPE, "rvc_noise_conv_f32: bad shape");
     if (Lout == 0) return 0;
     dim3 grid(rvc::cdiv(Lout, 128), rvc::cdiv(C, 32), B);
-    noise_conv_f32_kernel<<<grid, 128, 32 * kn * sizeof(float), (cudaStream_t)stream>>>(har, har_bs, w, bias, y, y_bs, C, Lout, kn, sn, pn);
+    rvc::launch_pdl(noise_conv_f32_kernel, dim3(grid), dim3(128), (size_t)(32 * kn * sizeof(float)), (cudaStream_t)stream, har, har_bs, w, bias, y, y_bs, C, Lout, kn, sn, pn);
     return rvc::check_launch("rvc_noise_conv_f32");
 }

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mask, float* __restrict__ y, int C, int T,
                                                             float eps, int out_mask, uint8_t* __restrict__ y_act, int Lp, int fp16) {
+    rvc::pdl_prologue();
     __shared__ float red[8][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int t = blockIdx.x * 32 + tx, b = blockIdx.y;
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(128) rel_attention_f32_kernel(const float* __r
 
 __global__ void sample_zp_f32_kernel(const float* __restrict__ stats, const float* __restrict__ eps, const float* __restrict__ mask,
                                      float* __restrict__ zp, int C, int T, int64_t n) {
+    rvc::pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int t = (int)(i % T);
@@ -291,6 +293,7 @@ __global__ void sample_zp_f32_kernel(const float* __restrict__ stats, const floa
 // y[b][co] = bias[co] + sum_ci w[ci][co] * x[b][ci]   (w packed [Cin][Cout]); block = 32 output columns x 8 ci slices
 __global__ void __launch_bounds__(256) cond_gemv_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                             float* __restrict__ y, int Cin, int Cout) {
+    rvc::pdl_prologue();
     __shared__ float red[8][33];
     const int b = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int co = blockIdx.x * 32 + tx;
@@ -313,7 +316,7 @@ RVC_API int rvc_cond_gemv_f32(const float* x, const float* w, const float* bias,
     if (!x || !w || !y) return rvc::fail(RVC_EINVAL, "rvc_cond_gemv_f32: null pointer");
     if (B <= 0 || B > 65535 || Cin <= 0 || Cin > 8192 || Cout <= 0) return rvc::fail(RVC_ESHAPE, "rvc_cond_gemv_f32: bad shape");
     dim3 grid(rvc::cdiv(Cout, 32), B);
-    cond_gemv_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, Cin, Cout);
+    rvc::launch_pdl(cond_gemv_f32_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, x, w, bias, y, Cin, Cout);
     return rvc::check_launch("rvc_cond_gemv_f32");
 }
 
@@ -325,6 +328,7 @@ namespace {
 __global__ void __launch_bounds__(256) embed_prep_kernel(const int64_t* __restrict__ pitch, const int64_t* __restrict__ lengths,
                                                          const float* __restrict__ emb_pitch, float scale, float* __restrict__ pb,
                                                          float* __restrict__ mask, int T, int H) {
+    rvc::pdl_prologue();
     const int t = blockIdx.x * 256 + threadIdx.x, b = blockIdx.z;
     if (t >= T) return;
     if (blockIdx.y == 0) mask[(int64_t)b * T + t] = t < lengths[b] ? 1.f : 0.f;
@@ -338,6 +342,7 @@ __global__ void __launch_bounds__(256) embed_prep_kernel(const int64_t* __restri
 
 // channels-last fp32 [B, T, D] -> packed fp16/bf16 [B][D/8][Lp][8]
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int T, int D, int Lp, int fp16) {
+    rvc::pdl_prologue();
     const int t = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
     if (t >= T) return;
     const float4* xp = reinterpret_cast<const float4*>(x + ((int64_t)b * T + t) * D + c * 8);
@@ -355,7 +360,7 @@ RVC_API int rvc_embed_prep(const int64_t* pitch, const int64_t* lengths, const f
     if (B <= 0 || B > 65535 || T < 0 || H <= 0) return rvc::fail(RVC_ESHAPE, "rvc_embed_prep: bad shape");
     if (T == 0) return 0;
     dim3 grid(rvc::cdiv(T, 256), pitch ? rvc::cdiv(H, 16) : 1, B);
-    embed_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pitch, lengths, emb_pitch, scale, pb, mask, T, H);
+    rvc::launch_pdl(embed_prep_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, pitch, lengths, emb_pitch, scale, pb, mask, T, H);
     return rvc::check_launch("rvc_embed_prep");
 }
 
@@ -365,7 +370,7 @@ RVC_API int rvc_pack_rows(const float* x, void* y, int32_t B, int32_t T, int32_t
     if (B <= 0 || B > 65535 || T < 0 || D <= 0 || D % 8 || (reinterpret_cast<uintptr_t>(x) & 15)) return rvc::fail(RVC_ESHAPE, "rvc_pack_rows: bad shape / alignment");
     if (T == 0) return 0;
     dim3 grid(rvc::cdiv(T, 256), D / 8, B);
-    pack_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (uint8_t*)y, T, D, (int)rvc_packed_rows(T), dtype == RVC_DT_FP16);
+    rvc::launch_pdl(pack_rows_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, x, (uint8_t*)y, T, D, (int)rvc_packed_rows(T), dtype == RVC_DT_FP16);
     return rvc::check_launch("rvc_pack_rows");
 }
 
@@ -388,7 +393,7 @@ RVC_API int rvc_layernorm_f32(const float* x, const float* r, const float* gamma
         return rvc::fail(RVC_EINVAL, "rvc_layernorm_f32: packed output needs C %% 8 == 0, a mask and a bf16/fp16 dtype");
     if (T == 0) return 0;
     dim3 grid(rvc::cdiv(T, 32), B);
-    layernorm_f32_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, r, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act,
+    rvc::launch_pdl(layernorm_f32_kernel, dim3(grid), dim3(32, 8), (size_t)0, (cudaStream_t)stream, x, r, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act,
                                                                        (int)rvc_packed_rows(T), act_dtype == RVC_DT_FP16);
     return rvc::check_launch("rvc_layernorm_f32");
 }
@@ -419,6 +424,6 @@ RVC_API int rvc_sample_zp_f32(const float* stats, const float* eps, const float*
     if (B <= 0 || C <= 0 || T < 0) return rvc::fail(RVC_ESHAPE, "rvc_sample_zp_f32: bad shape");
     const int64_t n = (int64_t)B * C * T;
     if (n == 0) return 0;
-    sample_zp_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(stats, eps, mask, zp, C, T, n);
+    rvc::launch_pdl(sample_zp_f32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, stats, eps, mask, zp, C, T, n);
     return rvc::check_launch("rvc_sample_zp_f32");
 }

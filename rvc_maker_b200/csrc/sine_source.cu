@@ -12,6 +12,7 @@ constexpr int SCAN_NT = 256;
 
 __global__ void __launch_bounds__(SCAN_NT) sine_phase_scan_kernel(const float* __restrict__ f0, float* __restrict__ phase, int T,
                                                                   int upp, float sr) {
+    rvc::pdl_prologue();
     __shared__ double warp_tot[SCAN_NT / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
     const float* fb = f0 + (int64_t)b * T;
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(256) sine_synth_kernel(const float* __restrict
                                                          const float* __restrict__ noise, const float* __restrict__ lin_w,
                                                          const float* __restrict__ lin_b, float* __restrict__ har, int T, int upp,
                                                          float sr, int64_t n) {
+    rvc::pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t frame = i / upp;              // b*T + t
@@ -69,10 +71,10 @@ RVC_API int rvc_sine_source_f32(const float* f0, const float* noise, const float
     if (!f0 || !noise || !lin_w || !lin_b || !scratch || !har) return rvc::fail(RVC_EINVAL, "rvc_sine_source_f32: null pointer");
     if (B <= 0 || T < 0 || upp <= 0 || !(sr > 0.f)) return rvc::fail(RVC_ESHAPE, "rvc_sine_source_f32: bad shape");
     if (T == 0) return 0;
-    sine_phase_scan_kernel<<<B, SCAN_NT, 0, (cudaStream_t)stream>>>(f0, scratch, T, upp, sr);
+    rvc::launch_pdl(sine_phase_scan_kernel, dim3(B), dim3(SCAN_NT), (size_t)(0), (cudaStream_t)stream, f0, scratch, T, upp, sr);
     int rc = rvc::check_launch("rvc_sine_source_f32(scan)");
     if (rc) return rc;
     const int64_t n = (int64_t)B * T * upp;
-    sine_synth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(f0, scratch, noise, lin_w, lin_b, har, T, upp, sr, n);
+    rvc::launch_pdl(sine_synth_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, f0, scratch, noise, lin_w, lin_b, har, T, upp, sr, n);
     return rvc::check_launch("rvc_sine_source_f32(synth)");
 }
