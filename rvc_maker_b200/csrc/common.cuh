@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/rvc_b200.h"
 
@@ -53,7 +54,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    // measured on B200 (bench.py, same box): PDL on these small / many-block kernels is 3 % SLOWER end to end (their early-scheduled
+    // blocks occupy SMs while they wait), so it is off unless RVC_B200_PDL=1; the tcgen05 conv kernel always uses it (+3 %).
+    static const bool enabled = [] { const char* e = getenv("RVC_B200_PDL"); return e && e[0] == '1'; }();
+    cfg.numAttrs = enabled ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
