@@ -86,11 +86,11 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
-def build_net(cfg, device, precision="tc"):
+def build_net(cfg, device, precision="tc", use_f0=True):
     from rvc_maker_b200 import Synthesizer, configs
 
     torch.manual_seed(1234)  # the reference's own training seed (main/configs/v2/48000.json:4)
-    net = Synthesizer(*configs.ctor_args(cfg), use_f0=True, text_enc_hidden_dim=cfg["text_enc_hidden_dim"], precision=precision)
+    net = Synthesizer(*configs.ctor_args(cfg), use_f0=use_f0, text_enc_hidden_dim=cfg["text_enc_hidden_dim"], precision=precision)
     # zero-initialised flow `post` convs would make the flow a no-op for timing purposes only in value, not in work;
     # give them small random weights so outputs are non-trivial.
     for i in range(0, 8, 2):
@@ -127,6 +127,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--precision", default="tc", choices=["tc", "tc-bf16", "fp32"], help="tc = fp16 tcgen05 operands, tc-bf16 = bf16 in the C=256 ResBlocks, fp32 = CUDA cores")
+    ap.add_argument("--non-f0", action="store_true", help="plain HiFi-GAN generator (BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-json", default=None, help="write the per-kernel timing table here")
     args = ap.parse_args()
@@ -141,7 +142,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"RVC {args.config} f0 Synthesizer.infer, B={B} x T={T} frames ({audio_s:.1f} s of audio per step), random-init"
+    workload = f"RVC {args.config} {'non-f0' if args.non_f0 else 'f0'} Synthesizer.infer, B={B} x T={T} frames ({audio_s:.1f} s of audio per step), random-init"
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -176,12 +177,14 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    net, sd = build_net(cfg, dev, args.precision)
+    net, sd = build_net(cfg, dev, args.precision, use_f0=not args.non_f0)
     host = {k: v.pin_memory() for k, v in synth_inputs(cfg, B, T, seed=rank).items()}
     devin = {k: v.to(dev) for k, v in host.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(inp):
+        if args.non_f0:
+            return net.infer(inp["phone"], inp["phone_lengths"], None, None, inp["sid"])[0]
         return net.infer(inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"])[0]
 
     for _ in range(args.warmup):
@@ -269,6 +272,14 @@ def main():
             peak = peaks.get("hbm_gbs", 6650.0)
             ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
+        try:   # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/), per launch
+            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(top)
+            if tr:
+                roof["traffic"] = tr["dram_bytes_per_launch"]
+                roof["traffic_source"] = tr["source"]
+        except Exception:
+            pass
+        roof["algorithmic_bytes_per_launch"] = f["bytes"] / max(f["launches"], 1)
         roof.update({"kernel": top, "launches_per_step": f["launches"], "share_of_step": f["ms"] / total_ms,
                      "peak_source": "MEASURED_PEAKS.json (sustained)" if peaks else "fallback"})
         out["roofline"] = roof
