@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             const int g = it % NG;
             const uint32_t gph = (it / NG) & 1;
             const float* bb = jb.bias_b ? jb.bias_b + (size_t)b * jb.bias_b_bs : nullptr;
-            constexpr int NBLK = NT / 32;
+            constexpr int EB = NT < 32 ? 16 : 32;     // accumulator columns handled per work item
+            constexpr int NBLK = NT / EB;
             const int nblk = jb.gated ? NBLK / 2 : NBLK;
             tc::mbar_wait(ACC_FULL(g), gph);
             tc::fence_after_sync();
@@ -315,35 +316,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 const int l = lin * p.up + ph - p.pshift;          // output position
                 const bool ok = lin < p.L && l >= 0 && l < p.Lout && !(p.dbg & 1);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * MT + m) * NT);
-                const int col0 = nt * NT + cb * 32;               // weight-column index (bias order)
-                const int co0 = jb.gated ? nt * (NT / 2) + cb * 32 : col0;   // output-channel index
-                uint32_t r[32];
-                float v[32];
+                const int col0 = nt * NT + cb * EB;               // weight-column index (bias order)
+                const int co0 = jb.gated ? nt * (NT / 2) + cb * EB : col0;   // output-channel index
+                uint32_t r[EB];
+                float v[EB];
                 // residual loads first: they do not depend on the accumulator and overlap the TMEM read
                 if (jb.res && ok) {
                     const float* rp = jb.res + (size_t)b * jb.res_bs + (size_t)co0 * jb.res_cs + l;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = rp[(size_t)i * jb.res_cs];
+                    for (int i = 0; i < EB; ++i) v[i] = rp[(size_t)i * jb.res_cs];
                     if (p.sum_jobs)
                         for (int jj = 1; jj < p.njobs; ++jj) {
                             const rvc_tc_job& j2 = p.jobs[jj];
                             const float* rp2 = j2.res + (size_t)b * j2.res_bs + (size_t)co0 * j2.res_cs + l;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] += rp2[(size_t)i * j2.res_cs];
+                            for (int i = 0; i < EB; ++i) v[i] += rp2[(size_t)i * j2.res_cs];
                         }
                 }
                 const float mk = (jb.mask && ok) ? jb.mask[(size_t)b * p.Lout + l] : 1.f;
-                tc::tmem_ld32(t_row + cb * 32, r);
+                tc::tmem_ld<EB>(t_row + cb * EB, r);
                 tc::tmem_ld_wait();
                 const float4* bs4 = reinterpret_cast<const float4*>(bias_s + j * p.Cout + col0);
                 if (jb.gated) {
-                    uint32_t r2[32];
-                    tc::tmem_ld32(t_row + (cb + NBLK / 2) * 32, r2);
+                    uint32_t r2[EB];
+                    tc::tmem_ld<EB>(t_row + (cb + NBLK / 2) * 32, r2);
                     tc::tmem_ld_wait();
-                    const int col1 = col0 + (NBLK / 2) * 32;
+                    const int col1 = col0 + (NBLK / 2) * EB;
                     const float* bs1 = bias_s + j * p.Cout + col1;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
+                    for (int i = 0; i < EB; ++i) {
                         float t = __uint_as_float(r[i]) + bias_s[j * p.Cout + col0 + i];
                         float sg = __uint_as_float(r2[i]) + bs1[i];
                         if (bb) { t += __ldg(bb + col0 + i); sg += __ldg(bb + col1 + i); }
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     }
                 } else {
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
+                    for (int i4 = 0; i4 < EB / 4; ++i4) {
                         const float4 b4 = bs4[i4];
                         r[4 * i4 + 0] = __float_as_uint(__uint_as_float(r[4 * i4 + 0]) + b4.x);
                         r[4 * i4 + 1] = __float_as_uint(__uint_as_float(r[4 * i4 + 1]) + b4.y);
@@ -360,53 +361,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     }
                     if (bb) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(bb + col0 + i));
+                        for (int i = 0; i < EB; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(bb + col0 + i));
                     }
                 }
                 if (!ok) continue;
                 if (jb.relu == 1) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
+                    for (int i = 0; i < EB; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
                 }
                 const float alpha = jb.alpha;
                 if (p.sum_jobs) {   // v = alpha * (sum_j conv_j + sum_j bias_j + sum_j res_j)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = alpha * ((jb.res ? v[i] : 0.f) + __uint_as_float(r[i]));
+                    for (int i = 0; i < EB; ++i) v[i] = alpha * ((jb.res ? v[i] : 0.f) + __uint_as_float(r[i]));
                 } else if (jb.res) {
                     if (alpha == 1.f) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = v[i] + __uint_as_float(r[i]);
+                        for (int i = 0; i < EB; ++i) v[i] = v[i] + __uint_as_float(r[i]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaf(alpha, __uint_as_float(r[i]), v[i]);
+                        for (int i = 0; i < EB; ++i) v[i] = fmaf(alpha, __uint_as_float(r[i]), v[i]);
                     }
                 } else if (alpha == 1.f) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    for (int i = 0; i < EB; ++i) v[i] = __uint_as_float(r[i]);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = alpha * __uint_as_float(r[i]);
+                    for (int i = 0; i < EB; ++i) v[i] = alpha * __uint_as_float(r[i]);
                 }
                 float sl = jb.act_slope;
                 if (jb.relu == 2) {   // leaky_relu on the final value itself (both outputs carry it)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = lrelu_max(v[i], sl);
+                    for (int i = 0; i < EB; ++i) v[i] = lrelu_max(v[i], sl);
                     sl = 1.f;
                 }
                 if (jb.mask) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= mk;
+                    for (int i = 0; i < EB; ++i) v[i] *= mk;
                 }
                 if (jb.y_f32) {
                     float* yp = jb.y_f32 + (size_t)b * jb.y_bs + (size_t)co0 * jb.y_cs + l;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) yp[(size_t)i * jb.y_cs] = v[i];
+                    for (int i = 0; i < EB; ++i) yp[(size_t)i * jb.y_cs] = v[i];
                 }
                 if (jb.y_act) {
                     const size_t ya_bs = jb.y_act_bs ? (size_t)jb.y_act_bs : (size_t)p.nch_out * p.Lp_out * 16;
                     uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (size_t)b * ya_bs + (((size_t)co0 / 8) * p.Lp_out + PADL + l) * 16;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < EB / 8; ++u) {
                         uint4 pk;
                         pk.x = pack2(lrelu_max(v[8 * u + 0], sl), lrelu_max(v[8 * u + 1], sl), p.fp16);
                         pk.y = pack2(lrelu_max(v[8 * u + 2], sl), lrelu_max(v[8 * u + 3], sl), p.fp16);
@@ -554,7 +555,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     if (d.dtype != RVC_DT_BF16 && d.dtype != RVC_DT_FP16) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: dtype must be RVC_DT_BF16 or RVC_DT_FP16");
     if (d.B <= 0 || d.L <= 0 || d.Cin <= 0 || d.Cout <= 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: bad shape");
     if (d.Cin % 16) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: Cin=%d must be a multiple of 16", d.Cin);
-    if (d.Cout % 32) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: Cout=%d must be a multiple of 32", d.Cout);
+    if (d.Cout % 16) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: Cout=%d must be a multiple of 16", d.Cout);
     Params p;
     int maxpad = 0, gated = d.jobs[0].gated ? 1 : 0;
     for (int j = 0; j < d.njobs; ++j) {
@@ -587,8 +588,8 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     }
     auto ntiles = [&](int nt_, int mt_) { return (long)njt * d.B * rvc::cdiv(Lq, BM * mt_) * (d.Cout / nt_) * up; };
     if (NT == 0) {
-        const int cands[3] = {128, 64, 32};
-        for (int i = 0; i < 3; ++i) {
+        const int cands[4] = {128, 64, 32, 16};
+        for (int i = 0; i < 4; ++i) {
             const int c = cands[i];
             if (d.Cout % c || (gated && c % 64)) continue;
             NT = c;
@@ -596,7 +597,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
         }
         if (NT == 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: no N tile for Cout=%d (gated=%d)", d.Cout, gated);
     }
-    if (NT != 128 && NT != 64 && NT != 32) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt must be 32, 64 or 128");
+    if (NT != 128 && NT != 64 && NT != 32 && NT != 16) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt must be 16, 32, 64 or 128");
     if (d.Cout % NT || (gated && NT % 64)) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt=%d does not tile Cout=%d (gated=%d)", NT, d.Cout, gated);
     // sub-tiles per CTA tile: as many as still leave >= 2 waves of tiles (fewer, larger tiles amortise the per-tile handshakes);
     // 4 sub-tiles need NT <= 64 (TMEM: 2 groups x 4 x NT columns)
@@ -635,5 +636,6 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (NT == 128) return launch_tc_mt<128>(mt, p, smem, grid, st);
     if (NT == 64) return launch_tc_mt<64>(mt, p, smem, grid, st);
-    return launch_tc_mt<32>(mt, p, smem, grid, st);
+    if (NT == 32) return launch_tc_mt<32>(mt, p, smem, grid, st);
+    return launch_tc_mt<16>(mt, p, smem, grid, st);
 }

@@ -180,7 +180,7 @@ class Engine:
                 if ch in (128, 256):
                     # bf16 only where the 1e-3 budget allows it: C = 256 (6.8e-5 per SURVEY 7.2); bf16 at C = 128 measured 1.0e-3
                     dt = DT_BF16 if (self.precision == "tc-bf16" and ch == 256) else DT_FP16
-                elif ch in (32, 64):
+                elif ch in (16, 32, 64):
                     dt = DT_FP16
             self.stage_dt.append(dt)
         self.up_dt = []
@@ -191,7 +191,7 @@ class Engine:
             W[f"up_b{i}"] = _f(up.bias)
             cin_i, cout_i, k_i, u_i = wt.shape[0], wt.shape[1], wt.shape[2], c["rates"][i]
             self.up_dt.append(None)
-            if self.tc and cin_i % 16 == 0 and cout_i % 32 == 0 and (k_i - u_i) % 2 == 0:
+            if self.tc and cin_i % 16 == 0 and cout_i % 16 == 0 and (k_i - u_i) % 2 == 0:
                 # phase-major conv weight [Cout][Cin][u*M]: block r, tap t = w_T[:, :, r + (M-1-t)*u] (include/rvc_b200.h)
                 M = -(-k_i // u_i)
                 wk = torch.zeros(cout_i, cin_i, u_i * M)

@@ -110,7 +110,7 @@ def run_case(dtype, Cin, Cout, K, dil, B, L, seed=0, njobs=1, gated=False, relu=
 
 
 @pytest.mark.parametrize("dtype", [BF16, FP16])
-@pytest.mark.parametrize("Cc", [32, 64, 128, 256])
+@pytest.mark.parametrize("Cc", [16, 32, 64, 128, 256])
 @pytest.mark.parametrize("K,dil", [(3, 1), (7, 3), (11, 5)])
 def test_resblock_shapes(dtype, Cc, K, dil):
     run_case(dtype, Cc, Cc, K, dil, B=2, L=1000)
@@ -131,6 +131,7 @@ def test_three_jobs_many_tiles():
     run_case(BF16, 128, 128, 11, 5, B=2, L=40000, njobs=3)
     run_case(FP16, 32, 32, 11, 1, B=1, L=100000, njobs=3)          # auto-selects 4 sub-tiles per CTA tile
     run_case(FP16, 64, 64, 11, 5, B=1, L=300001, njobs=3)
+    run_case(FP16, 16, 16, 11, 5, B=2, L=160000, njobs=3)           # v1-32k last stage
 
 
 @pytest.mark.parametrize("Cin,Cout,K", [(192, 576, 1), (192, 768, 3), (768, 192, 3), (192, 384, 1), (96, 192, 1), (192, 96, 1), (192, 512, 7)])
@@ -146,7 +147,7 @@ def test_gated_wavenet_conv(nt):
 
 
 @pytest.mark.parametrize("Cin,Cout,k,u,Lin,dtype", [(512, 256, 24, 12, 1000, BF16), (256, 128, 20, 10, 3000, BF16), (128, 64, 4, 2, 5001, FP16),
-                                                    (64, 32, 4, 2, 777, FP16), (512, 256, 16, 10, 300, FP16), (256, 128, 16, 4, 500, FP16)])
+                                                    (64, 32, 4, 2, 777, FP16), (32, 16, 4, 2, 100000, FP16), (512, 256, 16, 10, 300, FP16), (256, 128, 16, 4, 500, FP16)])
 def test_conv_transpose_phase_mode(Cin, Cout, k, u, Lin, dtype):
     """ConvTranspose1d(k, stride u, pad (k-u)/2) as u phase GEMMs, with pre-lrelu input, residual (noise conv) and packed output."""
     from rvc_maker_b200 import _lib
