@@ -592,6 +592,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
         for (int i = 0; i < 4; ++i) {
             const int c = cands[i];
             if (d.Cout % c || (gated && c % 64)) continue;
+            if (c == 16 && NT != 0) break;          // N = 16 MMAs waste 60 % of the pipe: only when nothing wider divides Cout
             NT = c;
             if (ntiles(c, 1) >= sms) break;
         }
