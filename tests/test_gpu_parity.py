@@ -177,3 +177,30 @@ def test_cuda_graph_replay_matches_eager(precision):
     b = run_net(net2, inp2)
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+def test_bench_workload_full_size(precision):
+    """BASELINE configs[1] at its real size (v2-48k f0, B = 1, T = 1000 frames -> 480 000 samples) against the oracle."""
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=1234, heated=True)
+    inp = cases.synth_inputs(cfg, 1, 1000, seed=0)
+    out = run_net(build_net(cfg, sd, True, precision=precision), inp)
+    ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
+                                                      eps_z=inp["eps_z"], eps_src=inp["eps_src"])
+    assert tuple(out["o"].shape) == (1, 1, 480000)
+    ref = dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl)
+    m = cases.metrics(out["o"].float().cpu(), ro)
+    print(f"\n[config 2 full size, {precision}] o: max_abs={m['max_abs']:.3e} snr={m['snr_db']:.1f} dB ac_snr={m['snr_ac_db']:.1f} dB")
+    assert_close(out, ref, precision, tag="config2")
+
+
+def test_cold_weights_full_batch_tc():
+    """Reference-like initialisation statistics (DC-dominated output), ragged batch of 4, tensor-core path."""
+    cfg = cases.CONFIGS["v2_40k"]
+    sd = cases.synth_state_dict(cfg, seed=99, heated=False)
+    inp = cases.synth_inputs(cfg, 4, 257, seed=5, ragged=True)
+    out = run_net(build_net(cfg, sd, True, precision="tc"), inp)
+    ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
+                                                      eps_z=inp["eps_z"], eps_src=inp["eps_src"])
+    assert_close(out, dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl), "tc", tag="cold")
