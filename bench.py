@@ -53,7 +53,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -117,6 +117,77 @@ def cpu_baseline(cfg, sd, inp, steps, warmup):
     return times, cores
 
 
+def bench_stream(args, cfg, net, dev, dist, rank, world, local_rank):
+    """BASELINE config 5: `--stream-seconds` of synthetic features, chunked as convert.py:403-447 does (x_pad, x_center = 1, 38 s),
+    chunks sharded longest-first over the ranks, waveform pieces trimmed and gathered on the host.  A step = the whole stream."""
+    from rvc_maker_b200 import chunks as ch
+
+    n = args.stream_seconds * ch.SAMPLE_RATE
+    spans = ch.chunk_spans(n, ch.uniform_split_points(n))
+    owner = ch.shard_chunks(spans, world)
+    mine = [c for c in spans if owner[c.index] == rank]
+    total_frames = spans[-1].frame_end
+    full = synth_inputs(cfg, 1, total_frames, seed=0)
+    host = {k: (v.pin_memory() if v.dim() > 1 else v) for k, v in full.items()}
+    devfull = {k: v.to(dev) for k, v in full.items()}
+    sr = cfg["sr"]
+
+    def run_chunk(src, c):
+        sl = slice(c.frame_start, c.frame_end)
+        ln = torch.tensor([c.frames])
+        o = net.infer(src["phone"][:, sl], ln, src["pitch"][:, sl], src["nsff0"][:, sl], src["sid"])[0]
+        return ch.trim(o[0, 0], sr)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        for c in mine:
+            run_chunk(devfull, c)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_w0 = time.perf_counter()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        for c in mine:
+            run_chunk(devfull, c)
+    b.record()
+    barrier()
+    dev_ms = a.elapsed_time(b)
+    # end to end: pinned host features per chunk -> device -> waveform pieces -> host -> gathered + concatenated on rank 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        parts = {c.index: run_chunk(host, c).float().cpu().numpy() for c in mine}
+        wave = ch.gather_stream(parts, len(spans), rank, world)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop(t_w0, time.perf_counter()) if sampler else None
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        assert wave.shape[0] == args.stream_seconds * sr
+        launches = sum(net._engine.launches_per_infer(1, c.frames) for c in spans) * args.steps
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        print(json.dumps({
+            "metric": "audio_seconds_per_second", "value": args.stream_seconds * args.steps / (dev_ms / 1e3), "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": {"tc": "f16", "tc-bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "config": {"workload": f"RVC {args.config} f0, {args.stream_seconds} s synthetic stream -> {len(spans)} chunks "
+                                   f"({', '.join(str(c.frames) for c in spans[:2])}, ... frames incl. 2 x 100 pad), sharded longest-first over {world} rank(s)",
+                       "l2": "per-chunk working set > L2", "parallelism": f"{world} rank(s), independent chunks, host-side gather, no data-path collective"},
+            "e2e": {"value": args.stream_seconds * args.steps / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(wave.shape[0]) * 4},
+            "gpu_launches": launches, "clocks": clocks}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -128,6 +199,10 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--precision", default="tc", choices=["tc", "tc-bf16", "fp32"], help="tc = fp16 tcgen05 operands, tc-bf16 = bf16 in the C=256 ResBlocks, fp32 = CUDA cores")
     ap.add_argument("--non-f0", action="store_true", help="plain HiFi-GAN generator (BASELINE config 4)")
+    ap.add_argument("--workload", default="clip", choices=["clip", "stream"],
+                    help="clip = one B x T batch per step (default, configs[1]); stream = BASELINE config 5: a long stream cut by the reference's "
+                         "chunk plan and sharded over the ranks (strong scaling)")
+    ap.add_argument("--stream-seconds", type=int, default=600)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-json", default=None, help="write the per-kernel timing table here")
     args = ap.parse_args()
@@ -178,6 +253,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     net, sd = build_net(cfg, dev, args.precision, use_f0=not args.non_f0)
+    if args.workload == "stream":
+        return bench_stream(args, cfg, net, dev, dist, rank, world, local_rank)
     host = {k: v.pin_memory() for k, v in synth_inputs(cfg, B, T, seed=rank).items()}
     devin = {k: v.to(dev) for k, v in host.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
