@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 15
+#define RVC_ABI_VERSION 14
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -190,11 +190,6 @@ typedef struct {
      * weights); w_cs = rows between consecutive 16-byte weight chunks (default Cout). */
     int64_t a_bs, w_bs, y_act_bs;
     int32_t w_cs, reserved;
-    /* optional fused residual + LayerNorm over the channel axis (LayerNorm.forward, synthesizers.py:179-181; Encoder.forward
-     * :346-347): needs Cout = 192 (one N tile), one job, bias and res.  u = res + [mask if ln_flags & 1] * (conv + bias);
-     * y_f32 = (LN(u) * gamma + beta) * [mask if ln_flags & 2];  y_act = packed (LN(u) * gamma + beta) * mask. */
-    const float* ln_gamma; const float* ln_beta;
-    float ln_eps; int32_t ln_flags;
 } rvc_tc_job;
 /*
  * up > 1 selects the ConvTranspose1d phase mode (GeneratorNSF.ups, synthesizers.py:133,156): the packed weights hold `up`

@@ -309,70 +309,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             const int nblk = jb.gated ? NBLK / 2 : NBLK;
             tc::mbar_wait(ACC_FULL(g), gph);
             tc::fence_after_sync();
-            if (jb.ln_gamma) {
-                // ---- fused residual + LayerNorm over the NT (= Cout) channels of each position (synthesizers.py:179-181,
-                // :346-347): u = res + [mask] (acc + bias); y = LN(u) * gamma + beta.  One thread owns one position; two passes
-                // over TMEM (sum / sum of squares, then normalise).  Only epilogue warpgroup 0 works (MT = 1: 128 rows).
-                if (eg == 0) {
-                    const int lin = lt * TM + q * 32 + lane;
-                    const bool ok = lin < p.L;
-                    const int l = lin;
-                    const float mk = (jb.mask && ok) ? jb.mask[(size_t)b * p.Lout + l] : 1.f;
-                    const float pre = (jb.ln_flags & 1) ? mk : 1.f;
-                    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * MT) * NT);
-                    const float* rp = jb.res + (size_t)b * jb.res_bs + (ok ? l : 0);
-                    float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-                    for (int cb = 0; cb < NBLK; ++cb) {
-                        uint32_t r[EB];
-                        tc::tmem_ld<EB>(t_row + cb * EB, r);
-                        tc::tmem_ld_wait();
-                        if (ok) {
-#pragma unroll
-                            for (int i = 0; i < EB; ++i) {
-                                const float u = rp[(size_t)(cb * EB + i) * jb.res_cs] + pre * (__uint_as_float(r[i]) + bias_s[j * p.Cout + cb * EB + i]);
-                                sum += u;
-                                sq = fmaf(u, u, sq);
-                            }
-                        }
-                    }
-                    const float mean = sum / (float)NT;
-                    const float rstd = rsqrtf(fmaxf(sq / (float)NT - mean * mean, 0.f) + jb.ln_eps);
-                    const float om = (jb.ln_flags & 2) ? mk : 1.f;
-#pragma unroll 1
-                    for (int cb = 0; cb < NBLK; ++cb) {
-                        uint32_t r[EB];
-                        tc::tmem_ld<EB>(t_row + cb * EB, r);
-                        tc::tmem_ld_wait();
-                        if (!ok) continue;
-                        float v[EB];
-#pragma unroll
-                        for (int i = 0; i < EB; ++i) {
-                            const int c = cb * EB + i;
-                            const float u = rp[(size_t)c * jb.res_cs] + pre * (__uint_as_float(r[i]) + bias_s[j * p.Cout + c]);
-                            v[i] = (u - mean) * rstd * __ldg(jb.ln_gamma + c) + __ldg(jb.ln_beta + c);
-                        }
-                        if (jb.y_f32) {
-                            float* yp = jb.y_f32 + (size_t)b * jb.y_bs + (size_t)(cb * EB) * jb.y_cs + l;
-#pragma unroll
-                            for (int i = 0; i < EB; ++i) yp[(size_t)i * jb.y_cs] = v[i] * om;
-                        }
-                        if (jb.y_act) {
-                            const size_t ya_bs = jb.y_act_bs ? (size_t)jb.y_act_bs : (size_t)p.nch_out * p.Lp_out * 16;
-                            uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (size_t)b * ya_bs + (((size_t)(cb * EB) / 8) * p.Lp_out + PADL + l) * 16;
-#pragma unroll
-                            for (int u8 = 0; u8 < EB / 8; ++u8) {
-                                uint4 pk;
-                                pk.x = pack2(v[8 * u8 + 0] * mk, v[8 * u8 + 1] * mk, p.fp16);
-                                pk.y = pack2(v[8 * u8 + 2] * mk, v[8 * u8 + 3] * mk, p.fp16);
-                                pk.z = pack2(v[8 * u8 + 4] * mk, v[8 * u8 + 5] * mk, p.fp16);
-                                pk.w = pack2(v[8 * u8 + 6] * mk, v[8 * u8 + 7] * mk, p.fp16);
-                                *reinterpret_cast<uint4*>(yb + (size_t)u8 * p.Lp_out * 16) = pk;
-                            }
-                        }
-                    }
-                }
-            } else
 #pragma unroll 1
             for (int item = eg; item < MT * nblk; item += NEG) {
                 const int m = item / nblk, cb = item - m * nblk;
@@ -662,15 +598,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
         }
         if (NT == 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: no N tile for Cout=%d (gated=%d)", d.Cout, gated);
     }
-    const bool ln = d.jobs[0].ln_gamma != nullptr;
-    if (ln) {   // fused LayerNorm: one N tile spans all output channels, one job, 128-position tiles
-        const rvc_tc_job& jb = d.jobs[0];
-        if (d.njobs != 1 || d.Cout != 192 || gated || up > 1 || d.sum_jobs || !jb.res || !jb.ln_beta || !jb.bias)
-            return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: fused LayerNorm needs one job, Cout = 192, bias, res and gamma/beta");
-        NT = 192;
-        mt = 1;
-    }
-    if (NT != 192 && NT != 128 && NT != 64 && NT != 32 && NT != 16) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt must be 16, 32, 64 or 128");
+    if (NT != 128 && NT != 64 && NT != 32 && NT != 16) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt must be 16, 32, 64 or 128");
     if (d.Cout % NT || (gated && NT % 64)) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: nt=%d does not tile Cout=%d (gated=%d)", NT, d.Cout, gated);
     // sub-tiles per CTA tile: as many as still leave >= 2 waves of tiles (fewer, larger tiles amortise the per-tile handshakes);
     // 4 sub-tiles need NT <= 64 (TMEM: 2 groups x 4 x NT columns)
@@ -707,7 +635,6 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     const size_t smem = (size_t)nabuf * a_stage + fixed;
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     cudaStream_t st = (cudaStream_t)stream;
-    if (NT == 192) return launch_tc<192, 1>(p, smem, grid, st);
     if (NT == 128) return launch_tc_mt<128>(mt, p, smem, grid, st);
     if (NT == 64) return launch_tc_mt<64>(mt, p, smem, grid, st);
     if (NT == 32) return launch_tc_mt<32>(mt, p, smem, grid, st);

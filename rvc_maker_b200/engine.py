@@ -325,9 +325,6 @@ class Engine:
             jb.gated, jb.relu = int(j.get("gated", False)), int(j.get("relu", 0))
             jb.alpha, jb.act_slope = j.get("alpha", 1.0), j.get("act_slope", 1.0)
             jb.a_bs, jb.w_bs, jb.y_act_bs, jb.w_cs = j.get("a_bs", 0), j.get("w_bs", 0), j.get("y_act_bs", 0), j.get("w_cs", 0)
-            if j.get("ln_gamma") is not None:
-                jb.ln_gamma, jb.ln_beta = j["ln_gamma"].data_ptr(), j["ln_beta"].data_ptr()
-                jb.ln_eps, jb.ln_flags = 1e-5, j.get("ln_flags", 0)
             ce = Cout // 2 if jb.gated else Cout
             fl += 2.0 * B * Cin * Cout * jb.K * L
             by += B * L * (2.0 * Cin + up * ce * (4.0 * (j.get("res") is not None) + 4.0 * (j.get("y") is not None) + 2.0 * (j.get("y_act") is not None)))
@@ -422,29 +419,16 @@ class Engine:
                           att.data_ptr(), B, H, nh, T, WINDOW, flops=4.0 * B * H * T * T, bytes_=16.0 * B * H * T, kind="rel_attention_f32")
                     p.add(f"pack_att{i}", lib.rvc_pack_act, att.data_ptr(), None, None, 1.0, H * T, T, None, atta.data_ptr(), B, H, T, dt, 1.0,
                           kind="pack_act", bytes_=6.0 * B * H * T)
-                if H == 192:
-                    # conv_o + residual + LayerNorm in one launch (192-wide N tile: a thread sees its whole position); x updated in place
-                    self._tc(p, f"attn_o_ln{i}", [dict(a=atta, w=W[f"t_o_w{i}"], bias=W[f"o_b{i}"], res=vx, y=vx, y_act=xa, mask=p.mask,
-                                                       ln_gamma=W[f"ln1_g{i}"], ln_beta=W[f"ln1_b{i}"], ln_flags=0)],
-                             B=B, Cin=H, Cout=H, L=T, dtype=dt, tag="enc")
-                else:
-                    self._tc(p, f"attn_o{i}", [dict(a=atta, w=W[f"t_o_w{i}"], bias=W[f"o_b{i}"], y=vy)], B=B, Cin=H, Cout=H, L=T, dtype=dt, tag="enc")
-                    p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
-                          p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0, xa.data_ptr(), dt, kind="layernorm_f32", bytes_=14.0 * B * H * T)
+                self._tc(p, f"attn_o{i}", [dict(a=atta, w=W[f"t_o_w{i}"], bias=W[f"o_b{i}"], y=vy)], B=B, Cin=H, Cout=H, L=T, dtype=dt, tag="enc")
+                p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
+                      p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0, xa.data_ptr(), dt, kind="layernorm_f32", bytes_=14.0 * B * H * T)
                 self._tc(p, f"ffn1_{i}", [dict(a=xa, w=W[f"t_f1_w{i}"], bias=W[f"f1_b{i}"], relu=True, mask=p.mask, y_act=ha, K=ks)],
                          B=B, Cin=H, Cout=Fc, L=T, dtype=dt, tag="enc")
-                if H == 192:
-                    # ffn conv_2 (* mask) + residual + LayerNorm (+ the final `x * x_mask` of the encoder on the last layer)
-                    self._tc(p, f"ffn2_ln{i}", [dict(a=ha, w=W[f"t_f2_w{i}"], bias=W[f"f2_b{i}"], K=ks, res=vx, y=vx, y_act=xa, mask=p.mask,
-                                                     ln_gamma=W[f"ln2_g{i}"], ln_beta=W[f"ln2_b{i}"],
-                                                     ln_flags=1 | (2 if i == c["nl"] - 1 else 0))],
-                             B=B, Cin=Fc, Cout=H, L=T, dtype=dt, tag="enc")
-                else:
-                    self._tc(p, f"ffn2_{i}", [dict(a=ha, w=W[f"t_f2_w{i}"], bias=W[f"f2_b{i}"], mask=p.mask, y=vy, K=ks)],
-                             B=B, Cin=Fc, Cout=H, L=T, dtype=dt, tag="enc")
-                    p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln2_g{i}"].data_ptr(), W[f"ln2_b{i}"].data_ptr(),
-                          p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 1 if i == c["nl"] - 1 else 0, xa.data_ptr(), dt, kind="layernorm_f32",
-                          bytes_=14.0 * B * H * T)
+                self._tc(p, f"ffn2_{i}", [dict(a=ha, w=W[f"t_f2_w{i}"], bias=W[f"f2_b{i}"], mask=p.mask, y=vy, K=ks)],
+                         B=B, Cin=Fc, Cout=H, L=T, dtype=dt, tag="enc")
+                p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln2_g{i}"].data_ptr(), W[f"ln2_b{i}"].data_ptr(),
+                      p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 1 if i == c["nl"] - 1 else 0, xa.data_ptr(), dt, kind="layernorm_f32",
+                      bytes_=14.0 * B * H * T)
             self._tc(p, "proj", [dict(a=xa, w=W["t_proj_w"], bias=W["proj_b"], mask=p.mask, y=vst)], B=B, Cin=H, Cout=2 * I, L=T, dtype=dt, tag="enc")
             p.add("sample_zp", lib.rvc_sample_zp_f32, p.stats.data_ptr(), p.eps_z.data_ptr(), p.mask.data_ptr(), p.zp.data_ptr(), B, I, T)
             return p
