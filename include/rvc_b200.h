@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 14
+#define RVC_ABI_VERSION 15
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -88,9 +88,9 @@ int rvc_convtr1d_f32(const rvc_convtr1d_desc* d, void* stream);
 
 /* NSF noise conv alone (synthesizers.py:134-136, :156): y[b,co,l] = bias[co] + sum_j w[co][j] * har[b, l*sn - pn + j]; har has
  * Lout*sn samples per batch row (har_bs apart), y is contiguous [B,C,Lout] with batch stride y_bs.  Used as the residual input
- * of the tensor-core ConvTranspose1d. */
+ * of the tensor-core ConvTranspose1d.  blocked = 1 writes y channel-blocked, [b][c/8][l][8] (C % 8 == 0), see rvc_conv1d_tc_desc. */
 int rvc_noise_conv_f32(const float* har, int64_t har_bs, const float* w, const float* bias, float* y, int64_t y_bs, int32_t B,
-                       int32_t C, int32_t Lout, int32_t kn, int32_t sn, int32_t pn, void* stream);
+                       int32_t C, int32_t Lout, int32_t kn, int32_t sn, int32_t pn, int32_t blocked, void* stream);
 
 /* y[b,0,l] = tanh( sum_{ci,k} w[ci*7+k] * leaky_relu(in[b,ci,l-3+k], slope) ), no bias — conv_post (synthesizers.py:161);
  * in = x, or (x + x2 + x3) / in_div when x2/x3 are given. */
@@ -199,10 +199,15 @@ typedef struct {
  *
  * sum_jobs = 1 (stage average of the ResBlocks, synthesizers.py:157-159): every tile runs ALL jobs into one accumulator and
  * the epilogue of job 0 receives v = alpha * (sum_j conv_j + sum_j bias_j + sum_j res_j); outputs / mask / act_slope of job 0.
+ *
+ * f32_blocked (bit 0: res, bit 1: y_f32 of every job): the fp32 tensor is channel-blocked, [b][c/8][l][8] — element (b, c, l)
+ * at b*bs + (c/8)*cs + l*8 + c%8 with cs = the stride between 8-channel blocks (8*L when dense).  The epilogue then moves
+ * 32 contiguous bytes per thread and 1 KB per warp instead of 32 scattered 128-byte lines; the generator's residual streams
+ * use it (measured: 5.5 vs 4.4 TB/s for the conv2 epilogue's traffic, tools/epilogue_pattern_bench.cu).
  */
 typedef struct {
     rvc_tc_job jobs[3];
-    int32_t njobs, B, Cin, Cout, L, dtype, nt, mt, up, pshift, sum_jobs, reserved;
+    int32_t njobs, B, Cin, Cout, L, dtype, nt, mt, up, pshift, sum_jobs, f32_blocked;
 } rvc_conv1d_tc_desc;
 int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);
 

@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 DT_BF16, DT_FP16 = 0, 2
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -65,7 +65,7 @@ class TcJob(C.Structure):
 
 class Conv1dTcDesc(C.Structure):
     _fields_ = [("jobs", TcJob * 3), ("njobs", _i32), ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("L", _i32), ("dtype", _i32),
-                ("nt", _i32), ("mt", _i32), ("up", _i32), ("pshift", _i32), ("sum_jobs", _i32), ("reserved", _i32)]
+                ("nt", _i32), ("mt", _i32), ("up", _i32), ("pshift", _i32), ("sum_jobs", _i32), ("f32_blocked", _i32)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
@@ -84,7 +84,7 @@ SIGNATURES = {
     "rvc_cond_gemv_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rvc_sample_zp_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rvc_sine_source_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
-    "rvc_noise_conv_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "rvc_noise_conv_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rvc_packed_rows": (_i64, [_i32]),
     "rvc_pack_act": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

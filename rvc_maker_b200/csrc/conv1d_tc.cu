@@ -64,7 +64,10 @@ struct Params {
     int fp16;         // operand format: 0 = bf16, 1 = fp16
     int nabuf;        // activation ring depth (2..MAXABUF)
     int sum_jobs;     // 1: every tile runs ALL jobs into one accumulator (stage average of the ResBlocks)
-    int dbg;          // timing experiments only: 1 = epilogue skips global I/O, 2 = skip MMA issue, 4 = skip operand loads
+    int has_res;      // some job carries a residual (enables the epilogue's residual prefetch)
+    int blocked;      // bit 0: res is channel-blocked fp32 [b][c/8][l][8]; bit 1: y_f32 is
+    int dbg;          // timing experiments only: 1 = epilogue skips global I/O, 2 = skip MMA issue, 4 = skip operand loads,
+                      // 8 = skip residual loads, 16 = skip fp32 stores, 32 = skip packed stores, 64 = no residual prefetch
     int up, pshift;   // transposed-conv phase mode: output position = l * up + phase - pshift (up = 1: plain conv)
     int Lout, Lp_out; // output length and packed rows of the output
 };
@@ -81,7 +84,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
 // leaky_relu for 0 <= slope <= 1 as max(v, slope*v): two instructions, no select
 __device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
 
-template <int NT, int MT>
+// PF: the launch has residual inputs and the epilogue prefetches them one work item ahead
+template <int NT, int MT, bool PF>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) {
     constexpr int TM = BM * MT;
     constexpr int NI = MT >= 2 ? 2 : 1;                     // MMA issuer warps
@@ -297,21 +301,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         const int q = warp & 3;
         const int eg = (warp - 4) >> 2;   // 0 .. NEG-1
         constexpr int EBP = NT < 32 ? 16 : 32;
-        // Residual prefetch, one work item ahead (also across tiles): the fp32 residual loads of item n+1 are in flight while
-        // item n waits for its accumulator, does its math and stores — without it each warp exposed the full load latency per
-        // item and the conv2 launches sat at < 50 % of DRAM peak (ncu).
-        float vn[EBP];
-        auto prefetch_res = [&](int tile_, int item_) {
-            int j_, b_, lt_, nt_, ph_;
-            decode(tile_, j_, b_, lt_, nt_, ph_);
-            const rvc_tc_job& jn = p.jobs[j_];
-            if (!jn.res) return;
+        // Residual prefetch (PF instantiation), one work item ahead, also across tiles: the fp32 residual loads of item n+1 are
+        // in flight while item n waits for its accumulator, does its math and stores (3-6 % on the conv2 launches).  Launches
+        // without residuals use the PF = false instantiation: the 32 extra live registers cost the conv1 epilogue ~10 %.
+        float vn[PF ? EBP : 1];
+        auto load_res = [&](const rvc_tc_job& jn, int b_, int lt_, int nt_, int ph_, int item_, float* vn) {
             const int nblk_ = jn.gated ? (NT / EBP) / 2 : NT / EBP;
             const int m_ = item_ / nblk_, cb_ = item_ - m_ * nblk_;
             const int lin_ = lt_ * TM + m_ * BM + q * 32 + lane;
             const int l_ = lin_ * p.up + ph_ - p.pshift;
-            if (!(lin_ < p.L && l_ >= 0 && l_ < p.Lout) || (p.dbg & 1)) return;
+            if (!(lin_ < p.L && l_ >= 0 && l_ < p.Lout) || (p.dbg & 9)) return;
             const int co_ = jn.gated ? nt_ * (NT / 2) + cb_ * EBP : nt_ * NT + cb_ * EBP;
+            if (p.blocked & 1) {   // channel-blocked fp32: 32 contiguous bytes per 8 channels
+                const float* rp = jn.res + (size_t)b_ * jn.res_bs + (size_t)(co_ >> 3) * jn.res_cs + (size_t)l_ * 8;
+#pragma unroll
+                for (int u = 0; u < EBP / 8; ++u) tc::ldg256(rp + (size_t)u * jn.res_cs, vn + 8 * u);
+                if (p.sum_jobs)
+                    for (int jj = 1; jj < p.njobs; ++jj) {
+                        const rvc_tc_job& j2 = p.jobs[jj];
+                        const float* rp2 = j2.res + (size_t)b_ * j2.res_bs + (size_t)(co_ >> 3) * j2.res_cs + (size_t)l_ * 8;
+#pragma unroll
+                        for (int u = 0; u < EBP / 8; ++u) {
+                            float t8[8];
+                            tc::ldg256(rp2 + (size_t)u * j2.res_cs, t8);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) vn[8 * u + i] += t8[i];
+                        }
+                    }
+                return;
+            }
             const float* rp = jn.res + (size_t)b_ * jn.res_bs + (size_t)co_ * jn.res_cs + l_;
 #pragma unroll
             for (int i = 0; i < EBP; ++i) vn[i] = rp[(size_t)i * jn.res_cs];
@@ -323,14 +341,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     for (int i = 0; i < EBP; ++i) vn[i] += rp2[(size_t)i * j2.res_cs];
                 }
         };
-        auto nitems_of = [&](int tile_) {
+        // first item of a tile (for the very first tile and, from the last item of a tile, for the next one)
+        auto prefetch_tile = [&](int tile_) {
+            if (tile_ >= p.total_tiles) return;
             int j_, b_, lt_, nt_, ph_;
             decode(tile_, j_, b_, lt_, nt_, ph_);
-            return MT * (p.jobs[j_].gated ? (NT / EBP) / 2 : NT / EBP);
+            const rvc_tc_job& jn = p.jobs[j_];
+            if (jn.res && eg < MT * (jn.gated ? (NT / EBP) / 2 : NT / EBP)) load_res(jn, b_, lt_, nt_, ph_, eg, vn);
         };
+        if constexpr (PF) {
 #pragma unroll
-        for (int i = 0; i < EBP; ++i) vn[i] = 0.f;
-        if ((int)blockIdx.x < p.total_tiles && eg < nitems_of(blockIdx.x)) prefetch_res(blockIdx.x, eg);
+            for (int i = 0; i < EBP; ++i) vn[i] = 0.f;
+            prefetch_tile(blockIdx.x);
+        }
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             int j, b, lt, nt, ph;
@@ -356,10 +379,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 uint32_t r[EB];
                 float v[EB];
                 // this item's residual was prefetched one item ago; start the next item's loads before touching the accumulator
+                if constexpr (PF) {   // this item's residual was requested one item ago; request the next one before the accumulator
 #pragma unroll
-                for (int i = 0; i < EB; ++i) v[i] = vn[i];
-                if (item + NEG < MT * nblk) prefetch_res(tile, item + NEG);
-                else if (tile + (int)gridDim.x < p.total_tiles && eg < nitems_of(tile + gridDim.x)) prefetch_res(tile + gridDim.x, eg);
+                    for (int i = 0; i < EB; ++i) v[i] = vn[i];
+                    if (item + NEG < MT * nblk) { if (jb.res) load_res(jb, b, lt, nt, ph, item + NEG, vn); }
+                    else prefetch_tile(tile + gridDim.x);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < EB; ++i) v[i] = 0.f;
+                    if (jb.res) load_res(jb, b, lt, nt, ph, item, v);
+                }
                 const float mk = (jb.mask && ok) ? jb.mask[(size_t)b * p.Lout + l] : 1.f;
                 tc::tmem_ld<EB>(t_row + cb * EB, r);
                 tc::tmem_ld_wait();
@@ -425,12 +454,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
 #pragma unroll
                     for (int i = 0; i < EB; ++i) v[i] *= mk;
                 }
-                if (jb.y_f32) {
-                    float* yp = jb.y_f32 + (size_t)b * jb.y_bs + (size_t)co0 * jb.y_cs + l;
+                if (jb.y_f32 && !(p.dbg & 16)) {
+                    if (p.blocked & 2) {
+                        float* yp = jb.y_f32 + (size_t)b * jb.y_bs + (size_t)(co0 >> 3) * jb.y_cs + (size_t)l * 8;
 #pragma unroll
-                    for (int i = 0; i < EB; ++i) yp[(size_t)i * jb.y_cs] = v[i];
+                        for (int u = 0; u < EB / 8; ++u) tc::stg256(yp + (size_t)u * jb.y_cs, v + 8 * u);
+                    } else {
+                        float* yp = jb.y_f32 + (size_t)b * jb.y_bs + (size_t)co0 * jb.y_cs + l;
+#pragma unroll
+                        for (int i = 0; i < EB; ++i) yp[(size_t)i * jb.y_cs] = v[i];
+                    }
                 }
-                if (jb.y_act) {
+                if (jb.y_act && !(p.dbg & 32)) {
                     const size_t ya_bs = jb.y_act_bs ? (size_t)jb.y_act_bs : (size_t)p.nch_out * p.Lp_out * 16;
                     uint8_t* yb = reinterpret_cast<uint8_t*>(jb.y_act) + (size_t)b * ya_bs + (((size_t)co0 / 8) * p.Lp_out + PADL + l) * 16;
 #pragma unroll
@@ -514,9 +549,17 @@ int sm_count_cached() {
     return cache[dev];
 }
 
+template <int NT, int MT, bool PF>
+int launch_tc_pf(const Params& p, size_t smem, int grid, cudaStream_t stream);
+
 template <int NT, int MT>
 int launch_tc(const Params& p, size_t smem, int grid, cudaStream_t stream) {
-    auto kern = conv1d_tc_kernel<NT, MT>;
+    return (p.has_res && !(p.dbg & 64)) ? launch_tc_pf<NT, MT, true>(p, smem, grid, stream) : launch_tc_pf<NT, MT, false>(p, smem, grid, stream);
+}
+
+template <int NT, int MT, bool PF>
+int launch_tc_pf(const Params& p, size_t smem, int grid, cudaStream_t stream) {
+    auto kern = conv1d_tc_kernel<NT, MT, PF>;
     // opt in to the maximum dynamic shared memory once per device and instantiation (the attribute is sticky)
     static bool opted[64] = {false};
     int dev = 0;
@@ -631,6 +674,14 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     // 4 sub-tiles need NT <= 64 (TMEM: 2 groups x 4 x NT columns)
     // (weight bytes streamed per output halve with every doubling, so 2 sub-tiles are preferred as soon as they fill the GPU once)
     if (mt == 0) mt = (NT <= 64 && up == 1 && ntiles(NT, 4) >= 2L * sms) ? 4 : (ntiles(NT, 2) >= (long)sms ? 2 : 1);
+    if (d.f32_blocked & ~3) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: f32_blocked must be 0..3");
+    for (int j = 0; j < d.njobs && d.f32_blocked; ++j) {
+        const rvc_tc_job& jb = d.jobs[j];
+        if ((d.f32_blocked & 1) && jb.res && (((uintptr_t)jb.res & 31) || (jb.res_bs & 7) || (jb.res_cs & 7)))
+            return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: blocked res needs a 32-byte aligned pointer and strides in multiples of 8");
+        if ((d.f32_blocked & 2) && jb.y_f32 && (((uintptr_t)jb.y_f32 & 31) || (jb.y_bs & 7) || (jb.y_cs & 7)))
+            return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: blocked y_f32 needs a 32-byte aligned pointer and strides in multiples of 8");
+    }
     if (mt != 1 && mt != 2 && mt != 4) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: mt must be 1, 2 or 4");
     if (mt == 4 && NT > 64) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: mt = 4 needs nt <= 64");
     const int TM = BM * mt;
@@ -647,6 +698,9 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     p.fp16 = d.dtype == RVC_DT_FP16;
     p.sum_jobs = d.sum_jobs ? 1 : 0;
     p.dbg = d.jobs[0].reserved;
+    p.blocked = d.f32_blocked;
+    p.has_res = 0;
+    for (int j = 0; j < d.njobs; ++j) p.has_res |= d.jobs[j].res != nullptr;
     const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512 + (size_t)d.njobs * d.Cout * sizeof(float);
     const size_t limit = 227 * 1024;
     // activation stage: as many channel chunks as fit twice (double buffer); even count

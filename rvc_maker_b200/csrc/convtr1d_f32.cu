@@ -213,7 +213,7 @@ RVC_API int rvc_conv_post_f32(const float* x, const float* x2, const float* x3, 
 namespace {
 __global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __restrict__ har, int64_t har_bs, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y, int64_t y_bs, int C,
-                                                             int Lout, int kn, int sn, int pn) {
+                                                             int Lout, int kn, int sn, int pn, int blocked) {
     rvc::pdl_prologue();
     extern __shared__ float w_s[];  // [32][kn]
     const int co0 = blockIdx.y * 32, b = blockIdx.z;
@@ -236,6 +236,16 @@ __global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __rest
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] = fmaf(w_s[c * kn + j], hv, acc[c]);
     }
+    if (blocked) {   // [b][c/8][l][8]: one 32-byte sector per 8 channels
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            if (co0 + 8 * g < C) {
+                float4* yp = reinterpret_cast<float4*>(y + (int64_t)b * y_bs + ((int64_t)(co0 / 8 + g) * Lout + l) * 8);
+                yp[0] = make_float4(acc[8 * g], acc[8 * g + 1], acc[8 * g + 2], acc[8 * g + 3]);
+                yp[1] = make_float4(acc[8 * g + 4], acc[8 * g + 5], acc[8 * g + 6], acc[8 * g + 7]);
+            }
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < 32; ++c)
         if (co0 + c < C) y[(int64_t)b * y_bs + (int64_t)(co0 + c) * Lout + l] = acc[c];
@@ -243,11 +253,12 @@ __global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __rest
 }  // namespace
 
 RVC_API int rvc_noise_conv_f32(const float* har, int64_t har_bs, const float* w, const float* bias, float* y, int64_t y_bs, int32_t B,
-                               int32_t C, int32_t Lout, int32_t kn, int32_t sn, int32_t pn, void* stream) {
+                               int32_t C, int32_t Lout, int32_t kn, int32_t sn, int32_t pn, int32_t blocked, void* stream) {
     if (!har || !w || !y) return rvc::fail(RVC_EINVAL, "rvc_noise_conv_f32: null pointer");
+    if (blocked && ((C & 7) || ((uintptr_t)y & 31) || (y_bs & 7))) return rvc::fail(RVC_ESHAPE, "rvc_noise_conv_f32: blocked output needs C %% 8 == 0 and 32-byte alignment");
     if (B <= 0 || B > 65535 || C <= 0 || Lout < 0 || kn <= 0 || kn > 1024 || sn <= 0 || pn < 0) return rvc::fail(RVC_ESHAPE, "rvc_noise_conv_f32: bad shape");
     if (Lout == 0) return 0;
     dim3 grid(rvc::cdiv(Lout, 128), rvc::cdiv(C, 32), B);
-    rvc::launch_pdl(noise_conv_f32_kernel, dim3(grid), dim3(128), (size_t)(32 * kn * sizeof(float)), (cudaStream_t)stream, har, har_bs, w, bias, y, y_bs, C, Lout, kn, sn, pn);
+    rvc::launch_pdl(noise_conv_f32_kernel, dim3(grid), dim3(128), (size_t)(32 * kn * sizeof(float)), (cudaStream_t)stream, har, har_bs, w, bias, y, y_bs, C, Lout, kn, sn, pn, (int)blocked);
     return rvc::check_launch("rvc_noise_conv_f32");
 }

@@ -23,11 +23,11 @@ class V:
 
     __slots__ = ("t", "ptr", "bs", "cs")
 
-    def __init__(self, t, ctot, L, coff=0):
+    def __init__(self, t, ctot, L, coff=0, cs=None):
         self.t = t
         self.ptr = t.data_ptr() + coff * L * 4
         self.bs = ctot * L
-        self.cs = L
+        self.cs = L if cs is None else cs   # cs = 8 * L: channel-blocked [b][c/8][l][8] (stride between 8-channel blocks)
 
 
 class Plan:
@@ -299,11 +299,11 @@ class Engine:
         bytes_ = 4.0 * (B * Cin * L + B * Cout * L * (1 + (res is not None) + (beta != 0.0)) + Cin * K * Cout * g2)
         plan.add(name, self.lib.rvc_conv1d_f32, C.byref(d), flops=flops, bytes_=bytes_, kind=f"conv1d_f32[C{Cout}k{K}]")
 
-    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag="", up=1, pshift=0, flops=None):
+    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag="", up=1, pshift=0, flops=None, blocked=0):
         """One persistent tcgen05 launch over up to three jobs (dicts of rvc_tc_job fields; V views for res / y)."""
         d = Conv1dTcDesc()
         d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.nt, d.mt = len(jobs), B, Cin, Cout, L, dtype, nt, mt
-        d.up, d.pshift = up, pshift
+        d.up, d.pshift, d.f32_blocked = up, pshift, blocked
         fl = by = 0.0
         for slot, j in enumerate(jobs):
             jb = d.jobs[slot]
@@ -547,6 +547,11 @@ class Engine:
             kn = 1 if sn == 1 else sn * 2 - sn % 2
             pn = 0 if sn == 1 else (kn - sn) // 2
             xa = None   # packed lrelu(x) of this stage's input to the ResBlocks, produced by the ups epilogue when possible
+            # a stage that runs entirely on the tensor-core kernel keeps its fp32 residual streams (S[0], P[j]) channel-blocked,
+            # [b][c/8][l][8]: the epilogues then move whole 32-byte sectors per thread (rvc_conv1d_tc_desc.f32_blocked)
+            blk = self.up_dt[i] is not None and dt is not None and dt == self.up_dt[i] and Ci % 8 == 0
+            if blk:
+                vs0 = V(S[0], Ci, Li, cs=8 * Li)
             if self.up_dt[i] is not None:
                 # ---- ConvTranspose1d on tensor cores: u phase GEMMs; the noise conv result is the epilogue's residual input
                 udt = self.up_dt[i]
@@ -562,7 +567,7 @@ class Engine:
                           curL, udt, LRELU_SLOPE, bytes_=B * curC * curL * (2.0 + (12.0 if x2 else 4.0)), kind="pack_act")
                 if c["f0"]:
                     p.add(f"noise{i}", lib.rvc_noise_conv_f32, har.data_ptr(), Lfin, W[f"nz_w{i}"].data_ptr(), W[f"nz_b{i}"].data_ptr(),
-                          S[0].data_ptr(), Ci * Li, B, Ci, Li, kn, sn, pn, flops=2.0 * B * Ci * Li * kn, bytes_=4.0 * B * (Ci * Li + Li * sn),
+                          S[0].data_ptr(), Ci * Li, B, Ci, Li, kn, sn, pn, int(blk), flops=2.0 * B * Ci * Li * kn, bytes_=4.0 * B * (Ci * Li + Li * sn),
                           kind="noise_conv_f32")
                 if dt is not None and dt == udt:
                     xa = self._packed(p, B, Ci, Li)
@@ -570,7 +575,7 @@ class Engine:
                 self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(vs0 if c["f0"] else None), y=vs0, y_act=xa,
                                              act_slope=LRELU_SLOPE, K=M, pad=M - 1)],
                          B=B, Cin=curC, Cout=Ci, L=curL, dtype=udt, up=u, pshift=(k - u) // 2, tag=f"ups",
-                         flops=2.0 * B * curC * Ci * k * curL)
+                         flops=2.0 * B * curC * Ci * k * curL, blocked=3 if blk else 0)
             else:
                 d = ConvTr1dDesc()
                 vx = V(cur[0], curC, curL)
@@ -623,6 +628,8 @@ class Engine:
                 next_tc_ups = nxt < len(rates) and self.up_dt[nxt] is not None and self.up_dt[nxt] == dt
                 next_ua = self._packed(p, B, Ci, Li) if next_tc_ups else None   # packed lrelu(stage average) for the next ups
                 need_f32 = not next_tc_ups                                         # conv_post / fp32 ups read the fp32 average
+                # blocked residuals -> plain [B, C, L] average cannot be written in place over P[0]
+                avg = (self._buf(p, B * Ci * Li) if blk else S[1]) if need_f32 else None
                 nsteps = len(rds[0])
                 assert all(len(dl) == nsteps for dl in rds)
                 for mm in range(nsteps):
@@ -635,6 +642,9 @@ class Engine:
                         # the packed leaky_relu input of the next tensor-core ups (synthesizers.py:150,157-159)
                         fused = last and half == 2
                         d.sum_jobs = int(fused)
+                        rcs = 8 * Li if blk else Li     # channel(-block) stride of the fp32 streams
+                        # the fused stage average leaves the blocked domain: conv_post / an fp32 ups read plain [B, C, L]
+                        d.f32_blocked = (1 if fused else 3) if (blk and half == 2) else 0
                         fl = 0.0
                         for slot, j in enumerate(order):
                             jb = d.jobs[slot]
@@ -647,13 +657,13 @@ class Engine:
                             else:           # x = conv2(lrelu(t)) + x;  store x (fp32) and lrelu(x) packed for the next pair
                                 jb.a = ta[j].data_ptr()
                                 jb.w, jb.bias = W[f"rb{i}_{j}_c2w{mm}"].data_ptr(), W[f"rb{i}_{j}_c2b{mm}"].data_ptr()
-                                jb.res, jb.res_bs, jb.res_cs = (S[0] if mm == 0 else P[j]).data_ptr(), Ci * Li, Li
+                                jb.res, jb.res_bs, jb.res_cs = (S[0] if mm == 0 else P[j]).data_ptr(), Ci * Li, rcs
                                 if not fused:
-                                    jb.y_f32, jb.y_bs, jb.y_cs = P[j].data_ptr(), Ci * Li, Li
+                                    jb.y_f32, jb.y_bs, jb.y_cs = P[j].data_ptr(), Ci * Li, rcs
                                     jb.y_act = pa[j].data_ptr()
                                 elif slot == 0:
-                                    if need_f32:   # into P[0]'s buffer: every thread reads its residuals before it writes (in-place safe)
-                                        jb.y_f32, jb.y_bs, jb.y_cs = S[1].data_ptr(), Ci * Li, Li
+                                    if need_f32:   # NCL: into P[0]'s buffer (every thread reads its residuals before it writes)
+                                        jb.y_f32, jb.y_bs, jb.y_cs = avg.data_ptr(), Ci * Li, Li
                                     if next_ua is not None:
                                         jb.y_act = next_ua.data_ptr()
                                 jb.K, jb.dil, jb.pad = kk, 1, (kk - 1) // 2
@@ -664,7 +674,7 @@ class Engine:
                             B * Ci * Li * (nk * (esz + 4.0) + (4.0 if need_f32 else 0.0) + (esz if next_ua is not None else 0.0))
                         p.add(f"rbtc{i}_s{mm}_c{half}", lib.rvc_conv1d_tc, C.byref(d), flops=fl, bytes_=by,
                               kind=f"conv1d_tc_{'bf16' if dt == DT_BF16 else 'fp16'}[C{Ci}]")
-                cur, curC, curL = (S[1], None, None), Ci, Li      # stage average (fp32), valid when need_f32
+                cur, curC, curL = (avg, None, None), Ci, Li       # stage average (fp32, plain layout), None when the next ups is fused
                 prev_ua = next_ua
         p.o = self._buf(p, B, 1, Lfin)
         x2 = cur[1].data_ptr() if cur[1] is not None else None

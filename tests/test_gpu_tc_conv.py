@@ -244,3 +244,148 @@ def test_shape_errors_are_loud():
     d.jobs[0].K, d.jobs[0].dil, d.jobs[0].pad = 3, 1, 1
     assert lib.rvc_conv1d_tc(C.byref(d), None) == -2
     assert b"multiple of 16" in lib.rvc_last_error()
+
+
+def to_blocked(x):
+    """[B, C, L] -> channel-blocked [B, C/8, L, 8] (rvc_conv1d_tc_desc.f32_blocked)."""
+    B, C_, L = x.shape
+    return x.view(B, C_ // 8, 8, L).permute(0, 1, 3, 2).contiguous()
+
+
+def from_blocked(xb):
+    B, nb, L, _ = xb.shape
+    return xb.permute(0, 1, 3, 2).reshape(B, nb * 8, L)
+
+
+@pytest.mark.parametrize("Cc,K,L,blocked", [(128, 7, 3001, 3), (32, 11, 20000, 3), (16, 3, 5000, 3), (64, 3, 777, 1), (256, 7, 1200, 2)])
+def test_blocked_fp32_streams(Cc, K, L, blocked):
+    """Channel-blocked residual / output (the generator's residual streams): same numbers as the plain layout, bit for bit."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    B, dtype = 2, FP16
+    g = torch.Generator(device="cpu").manual_seed(21)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(L)
+    x = torch.randn(B, Cc, L, generator=g).to(DEV)
+    w = (torch.randn(Cc, Cc, K, generator=g) / (Cc * K) ** 0.5).to(DEV)
+    bias = torch.randn(Cc, generator=g).to(DEV)
+    res = torch.randn(B, Cc, L, generator=g).to(DEV)
+    a = torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+    wp = torch.zeros(K * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.rvc_pack_act(x.data_ptr(), None, None, 1.0, Cc * L, L, None, a.data_ptr(), B, Cc, L, dtype, 0.1, st), "pack_act")
+    _lib.check(lib.rvc_pack_weight(w.data_ptr(), wp.data_ptr(), Cc, Cc, K, dtype, st), "pack_weight")
+    outs = []
+    for blk in (0, blocked):
+        d = _lib.Conv1dTcDesc()
+        d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.f32_blocked = 1, B, Cc, Cc, L, dtype, blk
+        r_in = to_blocked(res) if blk & 1 else res
+        y = torch.zeros(B, Cc // 8, L, 8, device=DEV) if blk & 2 else torch.zeros(B, Cc, L, device=DEV)
+        y_act = torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+        jb = d.jobs[0]
+        jb.a, jb.w, jb.bias = a.data_ptr(), wp.data_ptr(), bias.data_ptr()
+        jb.res, jb.res_bs, jb.res_cs = r_in.data_ptr(), Cc * L, (8 * L if blk & 1 else L)
+        jb.y_f32, jb.y_bs, jb.y_cs = y.data_ptr(), Cc * L, (8 * L if blk & 2 else L)
+        jb.y_act = y_act.data_ptr()
+        jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = K, 1, (K - 1) // 2, 1.0, 0.1
+        _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "conv1d_tc")
+        torch.cuda.synchronize()
+        outs.append((from_blocked(y) if blk & 2 else y, y_act))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    ref = F.conv1d(rnd(F.leaky_relu(x, 0.1), dtype).double(), rnd(w, dtype).double(), bias.double(), padding=(K - 1) // 2) + res.double()
+    assert float((outs[1][0].double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_blocked_phase_mode_and_stage_average():
+    """Blocked residual + output through the ConvTranspose1d phase mode, then blocked residuals into a plain sum_jobs average."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    B, Cin, Cout, k, u, Lin, dtype = 2, 128, 64, 4, 2, 2501, FP16
+    g = torch.Generator(device="cpu").manual_seed(22)
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(B, Cin, Lin, generator=g).to(DEV)
+    w = (torch.randn(Cin, Cout, k, generator=g) / (Cin * k / u) ** 0.5).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    Lout = Lin * u
+    res = torch.randn(B, Cout, Lout, generator=g).to(DEV)
+    M = -(-k // u)
+    wk = torch.zeros(Cout, Cin, u * M, device=DEV)
+    for r in range(u):
+        for t in range(M):
+            kk = r + (M - 1 - t) * u
+            if kk < k:
+                wk[:, :, r * M + t] = w[:, :, kk].t()
+    rows_in, rows_out = lib.rvc_packed_rows(Lin), lib.rvc_packed_rows(Lout)
+    a = torch.zeros(B * Cin * rows_in * 2, dtype=torch.uint8, device=DEV)
+    wp = torch.zeros(u * M * Cin * Cout * 2, dtype=torch.uint8, device=DEV)
+    y_act = torch.zeros(B * Cout * rows_out * 2, dtype=torch.uint8, device=DEV)
+    yb = to_blocked(res)                      # in place: residual in, result out (as the engine does with the noise conv)
+    _lib.check(lib.rvc_pack_act(x.data_ptr(), None, None, 1.0, Cin * Lin, Lin, None, a.data_ptr(), B, Cin, Lin, dtype, 0.1, st), "pack_act")
+    _lib.check(lib.rvc_pack_weight(wk.data_ptr(), wp.data_ptr(), Cout, Cin, u * M, dtype, st), "pack_weight")
+    d = _lib.Conv1dTcDesc()
+    d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.up, d.pshift, d.f32_blocked = 1, B, Cin, Cout, Lin, dtype, u, (k - u) // 2, 3
+    jb = d.jobs[0]
+    jb.a, jb.w, jb.bias = a.data_ptr(), wp.data_ptr(), bias.data_ptr()
+    jb.res, jb.res_bs, jb.res_cs = yb.data_ptr(), Cout * Lout, 8 * Lout
+    jb.y_f32, jb.y_bs, jb.y_cs = yb.data_ptr(), Cout * Lout, 8 * Lout
+    jb.y_act = y_act.data_ptr()
+    jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = M, 1, M - 1, 1.0, 0.1
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "conv1d_tc(up, blocked)")
+    torch.cuda.synchronize()
+    y = from_blocked(yb)
+    ref = F.conv_transpose1d(rnd(F.leaky_relu(x, 0.1), dtype).double(), rnd(w, dtype).double(), bias.double(), stride=u, padding=(k - u) // 2) + res.double()
+    assert float((y.double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
+    assert torch.equal(unpack(y_act, B, Cout, Lout, dtype, rows_out), rnd(F.leaky_relu(y, 0.1), dtype))
+
+    # stage average: blocked residuals in, plain [B, C, L] average out
+    Cc, L = Cout, Lout
+    d = _lib.Conv1dTcDesc()
+    d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.sum_jobs, d.f32_blocked = 3, B, Cc, Cc, L, dtype, 1, 1
+    avg = torch.zeros(B, Cc, L, device=DEV)
+    keep, ref = [], 0.0
+    for j, (kk, dil) in enumerate(((11, 1), (7, 1), (3, 1))):
+        xj = torch.randn(B, Cc, L, generator=g).to(DEV)
+        wj = (torch.randn(Cc, Cc, kk, generator=g) / (Cc * kk) ** 0.5).to(DEV)
+        bj = torch.randn(Cc, generator=g).to(DEV)
+        rj = torch.randn(B, Cc, L, generator=g).to(DEV)
+        rjb = to_blocked(rj)
+        aj = torch.zeros(B * Cc * rows_out * 2, dtype=torch.uint8, device=DEV)
+        wpj = torch.zeros(kk * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+        _lib.check(lib.rvc_pack_act(xj.data_ptr(), None, None, 1.0, Cc * L, L, None, aj.data_ptr(), B, Cc, L, dtype, 0.1, st), "pack_act")
+        _lib.check(lib.rvc_pack_weight(wj.data_ptr(), wpj.data_ptr(), Cc, Cc, kk, dtype, st), "pack_weight")
+        jb = d.jobs[j]
+        jb.a, jb.w, jb.bias = aj.data_ptr(), wpj.data_ptr(), bj.data_ptr()
+        jb.res, jb.res_bs, jb.res_cs = rjb.data_ptr(), Cc * L, 8 * L
+        jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = kk, dil, (kk - 1) // 2, 1.0 / 3.0, 0.1
+        if j == 0:
+            jb.y_f32, jb.y_bs, jb.y_cs = avg.data_ptr(), Cc * L, L
+        keep += [xj, wj, bj, rj, rjb, aj, wpj]
+        ref = ref + F.conv1d(rnd(F.leaky_relu(xj, 0.1), dtype).double(), rnd(wj, dtype).double(), bj.double(), padding=(kk - 1) // 2) + rj.double()
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "conv1d_tc(sum, blocked res)")
+    torch.cuda.synchronize()
+    ref = ref / 3.0
+    assert float((avg.double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_noise_conv_blocked_output():
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    B, Cc, Lout, sn = 2, 64, 3000, 4
+    kn, pn = sn * 2, sn // 2
+    g = torch.Generator(device="cpu").manual_seed(23)
+    st = torch.cuda.current_stream().cuda_stream
+    har = torch.randn(B, Lout * sn, generator=g).to(DEV)
+    w = torch.randn(Cc, kn, generator=g).to(DEV)
+    bias = torch.randn(Cc, generator=g).to(DEV)
+    y0 = torch.zeros(B, Cc, Lout, device=DEV)
+    y1 = torch.zeros(B, Cc // 8, Lout, 8, device=DEV)
+    _lib.check(lib.rvc_noise_conv_f32(har.data_ptr(), Lout * sn, w.data_ptr(), bias.data_ptr(), y0.data_ptr(), Cc * Lout, B, Cc, Lout, kn, sn, pn, 0, st), "noise")
+    _lib.check(lib.rvc_noise_conv_f32(har.data_ptr(), Lout * sn, w.data_ptr(), bias.data_ptr(), y1.data_ptr(), Cc * Lout, B, Cc, Lout, kn, sn, pn, 1, st), "noise")
+    torch.cuda.synchronize()
+    assert torch.equal(y0, from_blocked(y1))
+    ref = F.conv1d(har.unsqueeze(1), w.unsqueeze(1), bias, stride=sn, padding=pn)
+    assert float((y0 - ref).abs().max()) <= 1e-4
+    assert lib.rvc_noise_conv_f32(har.data_ptr(), Lout * sn, w.data_ptr(), bias.data_ptr(), y1.data_ptr(), Cc * Lout, B, 12, Lout, kn, sn, pn, 1, st) != 0

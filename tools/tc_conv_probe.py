@@ -12,10 +12,11 @@ dev = "cuda:0"
 st = torch.cuda.current_stream().cuda_stream
 
 
-def probe(Cc, L, conv2, dbg, nt=0, mt=0, reps=5):
+def probe(Cc, L, conv2, dbg, nt=0, mt=0, reps=5, blocked=0):
     rows = lib.rvc_packed_rows(L)
     d = _lib.Conv1dTcDesc()
     d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.nt, d.mt = 3, 1, Cc, Cc, L, 2, nt, mt
+    d.f32_blocked = blocked if conv2 else 0
     keep = []
     for j, (k, dil) in enumerate(((11, 5), (7, 3), (3, 1))):
         a = torch.zeros(Cc * rows * 2, dtype=torch.uint8, device=dev)
@@ -29,8 +30,8 @@ def probe(Cc, L, conv2, dbg, nt=0, mt=0, reps=5):
         if conv2:
             res = torch.zeros(Cc, L, device=dev)
             y = torch.zeros(Cc, L, device=dev)
-            jb.res, jb.res_bs, jb.res_cs = res.data_ptr(), Cc * L, L
-            jb.y_f32, jb.y_bs, jb.y_cs = y.data_ptr(), Cc * L, L
+            jb.res, jb.res_bs, jb.res_cs = res.data_ptr(), Cc * L, (8 * L if blocked & 1 else L)
+            jb.y_f32, jb.y_bs, jb.y_cs = y.data_ptr(), Cc * L, (8 * L if blocked & 2 else L)
             keep += [res, y]
     d.jobs[0].reserved = dbg
     best = 1e9
@@ -44,6 +45,8 @@ def probe(Cc, L, conv2, dbg, nt=0, mt=0, reps=5):
     return best * 1e3
 
 
+if __name__ != "__main__":
+    raise SystemExit
 names = {0: "full", 1: "no epilogue I/O", 2: "no MMA issue", 4: "no operand loads", 3: "no epi I/O + no MMA", 5: "no epi I/O + no loads", 6: "no MMA + no loads",
          7: "barriers only"}
 for Cc, L in ((32, 480000), (64, 240000), (128, 120000)):
