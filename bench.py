@@ -118,25 +118,32 @@ def cpu_baseline(cfg, sd, inp, steps, warmup):
 
 
 def bench_stream(args, cfg, net, dev, dist, rank, world, local_rank):
-    """BASELINE config 5: `--stream-seconds` of synthetic features, chunked as convert.py:403-447 does (x_pad, x_center = 1, 38 s),
-    chunks sharded longest-first over the ranks, waveform pieces trimmed and gathered on the host.  A step = the whole stream."""
+    """BASELINE config 5: `--stream-seconds` of synthetic 50 fps features + f0, cut by the reference's chunk plan (convert.py:403-447,
+    x_pad / x_center = 1 / 38 s), chunks sharded longest-first over the ranks, run through rvc_maker_b200.pipeline.StreamConverter
+    (x2 up-sampling + protect blend, batched infer, trim, peak normalisation, stitched on rank 0).  A step = the whole stream."""
     from rvc_maker_b200 import chunks as ch
+    from rvc_maker_b200 import pipeline as pl
 
     n = args.stream_seconds * ch.SAMPLE_RATE
-    spans = ch.chunk_spans(n, ch.uniform_split_points(n))
-    owner = ch.shard_chunks(spans, world)
-    mine = [c for c in spans if owner[c.index] == rank]
+    opt_ts = ch.uniform_split_points(n)
+    spans = ch.chunk_spans(n, opt_ts)
     total_frames = spans[-1].frame_end
     full = synth_inputs(cfg, 1, total_frames, seed=0)
-    host = {k: (v.pin_memory() if v.dim() > 1 else v) for k, v in full.items()}
-    devfull = {k: v.to(dev) for k, v in full.items()}
-    sr = cfg["sr"]
+    sr, upp = cfg["sr"], int(np.prod(cfg["upsample_rates"]))
+    feats_h = full["phone"][0, ::2].contiguous().pin_memory()          # 50 fps embedder output
+    pitch_h, pitchf_h = full["pitch"][0].pin_memory(), full["nsff0"][0].pin_memory()
+    feats_d, pitch_d, pitchf_d, sid_d = feats_h.to(dev), pitch_h.to(dev), pitchf_h.to(dev), full["sid"].to(dev)
+    conv = pl.StreamConverter(net, sr, upp, max_batch=args.stream_batch)
+    half = lambda c: slice(c.frame_start // 2, c.frame_start // 2 + c.frames // 2)
+    protect = 0.33                                                       # the reference's default; feats0 = feats (no retrieval index)
 
-    def run_chunk(src, c):
-        sl = slice(c.frame_start, c.frame_end)
-        ln = torch.tensor([c.frames])
-        o = net.infer(src["phone"][:, sl], ln, src["pitch"][:, sl], src["nsff0"][:, sl], src["sid"])[0]
-        return ch.trim(o[0, 0], sr)
+    def embed_d(c):
+        f = feats_d[half(c)]
+        return f, f
+
+    def embed_h(c):
+        f = feats_h[half(c)]
+        return f, f
 
     def barrier():
         if dist is not None:
@@ -144,46 +151,51 @@ def bench_stream(args, cfg, net, dev, dist, rank, world, local_rank):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        for c in mine:
-            run_chunk(devfull, c)
+        conv.convert(n, opt_ts, embed_d, pitch_d, pitchf_d, sid_d, protect=protect, rank=rank, world=world, to_host=False)
+        wave = conv.convert(n, opt_ts, embed_h, pitch_h, pitchf_h, full["sid"], protect=protect, rank=rank, world=world)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_w0 = time.perf_counter()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.steps):
-        for c in mine:
-            run_chunk(devfull, c)
+        conv.convert(n, opt_ts, embed_d, pitch_d, pitchf_d, sid_d, protect=protect, rank=rank, world=world, to_host=False)
     b.record()
     barrier()
     dev_ms = a.elapsed_time(b)
-    # end to end: pinned host features per chunk -> device -> waveform pieces -> host -> gathered + concatenated on rank 0
+    # end to end: pinned host features -> device -> waveform pieces -> one pinned host stream on rank 0 (peak-normalised)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        parts = {c.index: run_chunk(host, c).float().cpu().numpy() for c in mine}
-        wave = ch.gather_stream(parts, len(spans), rank, world)
+        wave = conv.convert(n, opt_ts, embed_h, pitch_h, pitchf_h, full["sid"], protect=protect, rank=rank, world=world)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop(t_w0, time.perf_counter()) if sampler else None
+    h2d = torch.tensor([float(conv.last_stats["h2d_bytes"])], device=dev, dtype=torch.float64)
     if dist is not None:
         t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
         dev_ms, e2e_s = float(t[0]), float(t[1])
     if rank == 0:
         assert wave.shape[0] == args.stream_seconds * sr
-        launches = sum(net._engine.launches_per_infer(1, c.frames) for c in spans) * args.steps
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        owner = ch.shard_chunks(spans, world)
+        launches = 0
+        for r in range(world):
+            for grp in pl.batch_chunks([c for c in spans if owner[c.index] == r], args.stream_batch):
+                launches += net._engine.launches_per_infer(len(grp), grp[0].frames) + 1 + len(grp)    # + feature prep + abs-max per piece
         print(json.dumps({
             "metric": "audio_seconds_per_second", "value": args.stream_seconds * args.steps / (dev_ms / 1e3), "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": {"tc": "f16", "tc-bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"RVC {args.config} f0, {args.stream_seconds} s synthetic stream -> {len(spans)} chunks "
-                                   f"({', '.join(str(c.frames) for c in spans[:2])}, ... frames incl. 2 x 100 pad), sharded longest-first over {world} rank(s)",
-                       "l2": "per-chunk working set > L2", "parallelism": f"{world} rank(s), independent chunks, host-side gather, no data-path collective"},
-            "e2e": {"value": args.stream_seconds * args.steps / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+                                   f"({', '.join(str(c.frames) for c in spans[:2])}, ... frames incl. 2 x 100 pad), batches of <= {args.stream_batch} equal "
+                                   f"chunks, sharded longest-first over {world} rank(s)",
+                       "l2": "per-chunk working set > L2", "parallelism": f"{world} rank(s), independent chunks, one NCCL gather of the finished "
+                       "pieces when ranks > 1, no data-path collective"},
+            "e2e": {"value": args.stream_seconds * args.steps / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d.item()),
                     "d2h_bytes_per_step": int(wave.shape[0]) * 4},
-            "gpu_launches": launches, "clocks": clocks}))
+            "gpu_launches": launches * args.steps, "clocks": clocks}))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -203,6 +215,7 @@ def main():
                     help="clip = one B x T batch per step (default, configs[1]); stream = BASELINE config 5: a long stream cut by the reference's "
                          "chunk plan and sharded over the ranks (strong scaling)")
     ap.add_argument("--stream-seconds", type=int, default=600)
+    ap.add_argument("--stream-batch", type=int, default=2, help="stream workload: equal-length chunks batched per infer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-json", default=None, help="write the per-kernel timing table here")
     args = ap.parse_args()

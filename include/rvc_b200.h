@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 15
+#define RVC_ABI_VERSION 16
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -223,6 +223,22 @@ int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);
  */
 int rvc_attn_softmax(const float* S, const float* qkv, const float* mask, const float* emb_k, const float* emb_v, void* P, float* R,
                      void* vw, int32_t B, int32_t H, int32_t n_heads, int32_t T, int32_t Tk, int32_t window, void* stream);
+
+/*
+ * Caller side of the path: the feature preparation VC.voice_conversion performs between the embedder and
+ * Synthesizer.infer (main/inference/convert.py:361-378).
+ *   out[b,t,:] = feats[b,t/2,:]                                    (feats0 == NULL: F.interpolate(scale_factor=2), :361)
+ *   out[b,t,:] = feats[b,t/2,:]*pf + feats0[b,t/2,:]*(1-pf),  pf = protect where pitchf[b,t] < 1, else 1   (:372-378)
+ * feats / feats0 are [B,Th,D] fp32 at 50 frames/s, pitchf is [B,>=T] fp32 (Hz) with row stride pitchf_bs, out is [B,T,D] with
+ * T <= 2*Th (the p_len clamp of :365-370).  Each product and the sum are rounded separately: bit-identical to the reference's
+ * elementwise ops.
+ */
+int rvc_feature_prep_f32(const float* feats, const float* feats0, const float* pitchf, int64_t pitchf_bs, float protect, float* out,
+                         int32_t B, int32_t Th, int32_t T, int32_t D, void* stream);
+
+/* result[b] = max(result[b], max_i |x[b*x_bs + i]|), i < n — the peak the pipeline normalises by (`np.abs(audio_opt).max()`,
+ * convert.py:451), accumulated chunk by chunk on the device; the caller zeroes `result` first. */
+int rvc_absmax_f32(const float* x, int64_t x_bs, int64_t n, float* result, int32_t B, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 DT_BF16, DT_FP16 = 0, 2
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -85,6 +85,8 @@ SIGNATURES = {
     "rvc_sample_zp_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rvc_sine_source_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "rvc_noise_conv_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "rvc_feature_prep_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "rvc_absmax_f32": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp]),
     "rvc_packed_rows": (_i64, [_i32]),
     "rvc_pack_act": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

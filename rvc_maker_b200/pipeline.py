@@ -1,0 +1,251 @@
+"""Chunk pipeline around ``Synthesizer.infer`` — the caller on both sides of the hot path.
+
+Mirrors ``VC.voice_conversion`` from the embedder output on (main/inference/convert.py:361-381) and the chunk loop of
+``VC.pipeline`` (:403-452).  The reference converts one chunk at a time: features -> ``F.interpolate(x2)`` -> protect blend ->
+``infer`` -> ``.cpu().numpy()`` -> ``empty_cache()``, then ``np.concatenate`` and a peak normalisation.  Here
+
+* chunks with the same shape are batched into one ``infer`` (the 38 s chunks of a long stream all have T = 4000);
+* up-sampling + protect blend are one kernel (``rvc_feature_prep_f32``), bit-identical to the reference's elementwise ops;
+* inputs of batch i+1 are staged host->device on a copy stream while batch i computes, finished pieces are trimmed on the
+  device and copied into ONE pinned host buffer at their final offsets on a second copy stream (no per-chunk sync, no concatenate);
+* the peak (``np.abs(audio_opt).max()``, :451) is accumulated on the device (``rvc_absmax_f32``) and applied once on the host;
+* with several ranks every rank synthesises the chunks ``shard_chunks`` gives it; the pieces are gathered once over NCCL
+  (the only collective, after the data path) and rank 0 assembles the stream.
+
+Out of scope (hooks instead): the embedder and FAISS retrieval that produce ``feats`` / ``feats0`` (:336-359), f0
+extraction (:431, 8f-2), the high-pass filter (:402) and ``change_rms`` (:450, only when volume_envelope != 1).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .chunks import WINDOW, ChunkConfig, chunk_spans, shard_chunks
+
+
+def feature_prep(feats, feats0, pitchf, protect, T=None):
+    """``F.interpolate(feats, scale_factor=2)`` + protect blend on the device (convert.py:361-378).
+
+    feats, feats0 (or None): [B, Th, D] fp32 CUDA tensors; pitchf: [B, >=T] fp32 (Hz) or None; returns [B, T, D] (T defaults
+    to 2*Th).  The blend runs only ``if protect < 0.5 and pitch_guidance`` (:362, :372), as in the reference.
+    """
+    if feats.device.type != "cuda":
+        raise RuntimeError("rvc_maker_b200.pipeline.feature_prep needs CUDA tensors (no CPU fallback)")
+    lib = _lib.load()
+    feats = feats.float().contiguous()
+    B, Th, D = feats.shape
+    T = 2 * Th if T is None else int(T)
+    blend = feats0 is not None and pitchf is not None and protect < 0.5
+    f0p = pfp = None
+    pbs = 0
+    if blend:
+        feats0 = feats0.float().contiguous()
+        pitchf = pitchf.float()
+        if pitchf.stride(-1) != 1:
+            pitchf = pitchf.contiguous()
+        if pitchf.shape[1] < T:
+            raise ValueError(f"pitchf has {pitchf.shape[1]} frames, features need {T}")
+        f0p, pfp, pbs = feats0.data_ptr(), pitchf.data_ptr(), pitchf.stride(0)
+    out = torch.empty(B, T, D, device=feats.device, dtype=torch.float32)
+    st = torch.cuda.current_stream(feats.device).cuda_stream
+    _lib.check(lib.rvc_feature_prep_f32(feats.data_ptr(), f0p, pfp, pbs, float(protect), out.data_ptr(), B, Th, T, D, st), "rvc_feature_prep_f32")
+    return out
+
+
+def voice_conversion(net_g, feats, p_len, pitch, pitchf, sid, protect=0.5, feats0=None):
+    """convert.py:361-381 for a batch of equal-shape chunks: returns the waveforms ``infer(...)[0][:, 0]`` ([B, T*upp], on device).
+
+    feats / feats0: [B, Th, D] embedder output (after / before the retrieval blend), p_len = chunk samples // window (:363),
+    pitch / pitchf: [B, frames] (None for a model without pitch guidance).
+    """
+    guided = pitch is not None and pitchf is not None
+    T = 2 * feats.shape[1]
+    if T < p_len:                       # :365-369
+        p_len = T
+        if guided:
+            pitch, pitchf = pitch[:, :p_len], pitchf[:, :p_len]
+    if guided and pitch.shape[1] != T:   # the reference fails inside TextEncoder with a broadcast error here
+        raise ValueError(f"features have {T} frames after up-sampling but pitch has {pitch.shape[1]}")
+    phone = feature_prep(feats, feats0 if guided else None, pitchf if guided else None, protect, T)
+    lengths = torch.full((feats.shape[0],), p_len, dtype=torch.long, device=feats.device)   # :380
+    o = net_g.infer(phone, lengths, pitch if guided else None, pitchf.float() if guided else None, sid)[0]
+    return o[:, 0]
+
+
+def batch_chunks(chunks, max_batch):
+    """Group chunks of identical length (frames and samples) into batches of at most ``max_batch``, longest first."""
+    groups, cur = [], []
+    for c in sorted(chunks, key=lambda c: (-c.frames, -(c.sample_end - c.sample_start), c.index)):
+        if cur and (len(cur) == max_batch or (c.frames, c.sample_end - c.sample_start) != (cur[0].frames, cur[0].sample_end - cur[0].sample_start)):
+            groups.append(cur)
+            cur = []
+        cur.append(c)
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def piece_layout(spans, upp, tgt_sr, cfg=ChunkConfig()):
+    """Offset and length (target-rate samples) of every chunk's trimmed piece in the stitched stream (convert.py:444-448)."""
+    t_pad_tgt = tgt_sr * cfg.x_pad
+    lens = [max(c.frames * upp - 2 * t_pad_tgt, 0) for c in spans]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    return [int(o) for o in offs[:-1]], lens, int(offs[-1])
+
+
+class StreamConverter:
+    """``VC.pipeline`` from the chunk plan on (convert.py:403-452), batched and overlapped.  One instance per process / GPU."""
+
+    def __init__(self, net_g, tgt_sr, upp, *, cfg=ChunkConfig(), max_batch=2, device=None):
+        self.net, self.sr, self.upp, self.cfg, self.max_batch = net_g, int(tgt_sr), int(upp), cfg, int(max_batch)
+        self.dev = torch.device(device) if device is not None else next(net_g.parameters()).device
+        if self.dev.type != "cuda":
+            raise RuntimeError("rvc_maker_b200.pipeline.StreamConverter needs the model on a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.h2d = torch.cuda.Stream(self.dev)
+        self.d2h = torch.cuda.Stream(self.dev)
+        self._host = None       # pinned output stream, reused between calls
+        self._peak = torch.zeros(1, device=self.dev)
+        self.last_stats = {}
+
+    # ------------------------------------------------------------------ staging
+    def _stage(self, group, embed, pitch, pitchf, sid):
+        """Issue the host->device copies of one batch on the copy stream; returns the device tensors and the event to wait on."""
+        with torch.cuda.stream(self.h2d):
+            fl, f0l = [], []
+            for c in group:
+                f, f0 = embed(c)
+                fl.append(f)
+                f0l.append(f0)
+            if any(f.shape != fl[0].shape for f in fl):
+                raise ValueError("chunks of one batch must give features of one shape")
+            feats = torch.stack([f.to(self.dev, non_blocking=True) for f in fl])
+            if any(f is None for f in f0l):
+                feats0 = None
+            elif all(f0 is f for f, f0 in zip(fl, f0l)):
+                feats0 = feats      # no retrieval blend happened (index_rate = 0): feats0 = feats.clone(), one copy is enough
+            else:
+                feats0 = torch.stack([f.to(self.dev, non_blocking=True) for f in f0l])
+            pi = pf = None
+            if pitch is not None:
+                pi = torch.stack([pitch[c.frame_start:c.frame_end].to(self.dev, non_blocking=True) for c in group])
+                pf = torch.stack([pitchf[c.frame_start:c.frame_end].to(self.dev, non_blocking=True) for c in group])
+            sd = sid.to(self.dev, non_blocking=True).reshape(-1)[:1].expand(len(group)).contiguous()
+            ev = torch.cuda.Event()
+            ev.record(self.h2d)
+        nbytes = sum(t.numel() * t.element_size() for t in (feats, None if feats0 is feats else feats0, pi, pf) if t is not None)
+        return dict(group=group, feats=feats, feats0=feats0, pitch=pi, pitchf=pf, sid=sd, ev=ev, bytes=nbytes)
+
+    # ------------------------------------------------------------------ convert
+    def convert(self, n_samples, opt_ts, embed, pitch, pitchf, sid, *, protect=0.5, rank=0, world=1, noise_fn=None, to_host=True):
+        """Synthesise the stream of ``n_samples`` 16 kHz samples cut at ``opt_ts`` (chunks.split_points).
+
+        embed(chunk) -> (feats [Th, D], feats0 [Th, D] or None): fp32 tensors (pinned host or device) for the chunk's audio slice
+        ``audio_pad[chunk.sample_start:chunk.sample_end]``; pitch (int64) / pitchf (fp32): [frames of the padded stream] or None;
+        sid: 0-d or 1-element int64 tensor.  noise_fn(chunk) -> (eps_z [1, I, T], eps_src [1, T*upp, 1]) pins the model's two
+        noise draws (tests).  Returns the stitched float32 waveform as a numpy view of the pinned buffer on rank 0 (valid until the
+        next call; None on other ranks), or the per-chunk device pieces when ``to_host`` is False.
+        """
+        if pitch is not None:
+            pitch, pitchf = pitch.reshape(-1), pitchf.reshape(-1)
+        spans = chunk_spans(n_samples, opt_ts, self.cfg)
+        owner = shard_chunks(spans, world)
+        mine = [c for c in spans if owner[c.index] == rank]
+        offs, lens, total = piece_layout(spans, self.upp, self.sr, self.cfg)
+        t_pad_tgt = self.sr * self.cfg.x_pad
+        groups = batch_chunks(mine, self.max_batch)
+        comp = torch.cuda.current_stream(self.dev)
+        st = comp.cuda_stream
+        if to_host and rank == 0 and (self._host is None or self._host.numel() < total):
+            self._host = torch.empty(total, dtype=torch.float32).pin_memory()
+        self._peak.zero_()
+        self.h2d.wait_stream(comp)
+        self.d2h.wait_stream(comp)
+        pieces, keep, short, h2d_bytes = {}, [], False, 0
+        staged = self._stage(groups[0], embed, pitch, pitchf, sid) if groups else None
+        for gi, group in enumerate(groups):
+            cur = staged
+            comp.wait_event(cur["ev"])
+            staged = self._stage(groups[gi + 1], embed, pitch, pitchf, sid) if gi + 1 < len(groups) else None   # overlaps this batch
+            h2d_bytes += cur["bytes"]
+            c0 = group[0]
+            if noise_fn is not None:
+                nz = [noise_fn(c) for c in group]
+                self.net._noise_override = (torch.cat([a for a, _ in nz]), torch.cat([b for _, b in nz]))
+            wav = voice_conversion(self.net, cur["feats"], (c0.sample_end - c0.sample_start) // WINDOW, cur["pitch"], cur["pitchf"], cur["sid"],
+                                   protect, cur["feats0"])
+            for t in (cur["feats"], cur["feats0"], cur["pitch"], cur["pitchf"], cur["sid"]):
+                if t is not None:
+                    t.record_stream(comp)
+            L = wav.shape[1]
+            n_keep = L - 2 * t_pad_tgt
+            if n_keep <= 0:
+                raise ValueError(f"chunk of {c0.frames} frames is shorter than its 2 x {self.cfg.x_pad} s of context")
+            body = wav[:, t_pad_tgt:L - t_pad_tgt]                                    # [t_pad_tgt : -t_pad_tgt], :444
+            for b in range(len(group)):   # one running peak for the whole stream
+                _lib.check(self.lib.rvc_absmax_f32(body[b].data_ptr(), 0, n_keep, self._peak.data_ptr(), 1, st), "rvc_absmax_f32")
+            ev = torch.cuda.Event()
+            ev.record(comp)
+            for b, c in enumerate(group):
+                short |= n_keep != lens[c.index]
+                pieces[c.index] = body[b]
+                if to_host and world == 1:
+                    self.d2h.wait_event(ev)
+                    with torch.cuda.stream(self.d2h):
+                        self._host[offs[c.index]: offs[c.index] + min(n_keep, lens[c.index])].copy_(body[b, :lens[c.index]], non_blocking=True)
+            wav.record_stream(self.d2h)
+            keep.append(wav)
+        self.last_stats = {"chunks": len(spans), "batches": len(groups), "h2d_bytes": h2d_bytes, "d2h_bytes": 4 * total if rank == 0 else 0}
+        if not to_host:
+            return pieces
+        if world > 1:
+            return self._gather(pieces, spans, owner, offs, lens, total, rank, world, short)
+        self.d2h.synchronize()
+        comp.synchronize()
+        return self._finish(pieces, spans, offs, lens, total, short, float(self._peak.item()))
+
+    def _finish(self, pieces, spans, offs, lens, total, short, peak):
+        out = self._host[:total].numpy()
+        if short:   # an embedder that returned fewer frames than the pitch grid: pieces are shorter, stitch what exists (:448)
+            out = np.concatenate([out[offs[c.index]: offs[c.index] + min(int(pieces[c.index].shape[0]), lens[c.index])] for c in spans])
+        audio_max = np.float32(peak) / 0.99                                            # :451-452 (float32 peak, as np.abs(x).max())
+        if audio_max > 1:
+            out /= audio_max
+        return out
+
+    def _gather(self, pieces, spans, owner, offs, lens, total, rank, world, short):
+        if short:
+            raise NotImplementedError("multi-rank stitching needs chunks whose features cover the pitch grid")
+        peak = gather_pieces(pieces, self._peak, spans, owner, offs, lens, rank, world, self._host, self.dev)
+        torch.cuda.current_stream(self.dev).synchronize()
+        if rank != 0:
+            return None
+        return self._finish(pieces, spans, offs, lens, total, False, peak)
+
+
+def gather_pieces(pieces, peak, spans, owner, offs, lens, rank, world, host, device):
+    """Every rank packs the pieces it owns into one buffer (+ its running peak as the last element); ONE ``dist.gather`` to rank 0
+    (NCCL over NVLink for CUDA tensors; the only collective of the stream workload, after the data path); rank 0 copies each piece
+    to its offset in ``host`` and returns the global peak.  Device-agnostic so that the layout logic is testable under gloo."""
+    import torch.distributed as dist
+
+    per_rank = [sum(lens[c.index] for c in spans if owner[c.index] == r) for r in range(world)]
+    cap = max(per_rank) + 1
+    buf = torch.zeros(cap, device=device)
+    o = 0
+    for c in spans:
+        if owner[c.index] == rank:
+            buf[o:o + lens[c.index]].copy_(pieces[c.index][:lens[c.index]])
+            o += lens[c.index]
+    buf[cap - 1:cap].copy_(peak.reshape(-1)[:1])
+    dst = [torch.empty(cap, device=device) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, dst, dst=0)
+    if rank != 0:
+        return None
+    cursor = [0] * world
+    for c in spans:
+        r = owner[c.index]
+        host[offs[c.index]: offs[c.index] + lens[c.index]].copy_(dst[r][cursor[r]: cursor[r] + lens[c.index]], non_blocking=True)
+        cursor[r] += lens[c.index]
+    return float(torch.stack([d[cap - 1] for d in dst]).max().item())
