@@ -23,18 +23,24 @@ __device__ __forceinline__ uint32_t h2(float a, float b) {
 __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restrict__ S, const float* __restrict__ qkv, const float* __restrict__ mask,
                                                            const float* __restrict__ emb_k, const float* __restrict__ emb_v, uint8_t* __restrict__ P,
                                                            float* __restrict__ R, uint8_t* __restrict__ vw, int H, int nh, int T, int Tk, int Lp,
-                                                           int W, int nqb) {
+                                                           int W, int nqb, int nvb, int BH) {
     rvc::pdl_prologue();
     extern __shared__ float sm[];
     const int dk = H / nh, NR = 2 * W + 1;
-    const int h = blockIdx.y % nh, b = blockIdx.y / nh;
+    // 1-D grid: the query blocks of every (b, head) first, the short v^T-pack blocks last — with T = 1000 the 126 softmax CTAs
+    // then start together in one wave instead of queueing behind the pack blocks of the previous head
+    const int nsm = nqb * BH;
+    const bool is_pack = (int)blockIdx.x >= nsm;
+    const int bh = is_pack ? ((int)blockIdx.x - nsm) / nvb : (int)blockIdx.x / nqb;
+    const int bx = is_pack ? ((int)blockIdx.x - nsm) % nvb : (int)blockIdx.x % nqb;
+    const int h = bh % nh, b = bh / nh;
     const int nchunk = Tk / 8;
     const int tid = threadIdx.x;
     const float* vb = qkv + ((int64_t)b * 3 * H + 2 * H + h * dk) * T;
 
-    if ((int)blockIdx.x >= nqb) {
+    if (is_pack) {
         // ---- v^T pack: vw[b][h][c][d][8] = v[d][8c .. 8c+7]
-        const int idx = (blockIdx.x - nqb) * ANT + tid;
+        const int idx = bx * ANT + tid;
         if (idx >= dk * nchunk) return;
         const int d = idx / nchunk, c = idx - d * nchunk;
         float v[8];
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
     float* q_s = l_s + AG * AQ;          // [dk][AQ]   q / sqrt(dk)
     float* ek_s = q_s + dk * AQ;         // [NR][dk]
     const int ti = tid % AQ, g = tid / AQ;
-    const int i0 = blockIdx.x * AQ, i = i0 + ti;
+    const int i0 = bx * AQ, i = i0 + ti;
     const float* qb = qkv + ((int64_t)b * 3 * H + h * dk) * T;
     const float* mb = mask + (int64_t)b * T;
     const float* Sb = S + ((int64_t)b * nh + h) * Tk * T;
@@ -117,8 +123,8 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
             const float mn = fmaxf(m, cm);
             float acc = 0.f;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc += expf(s8[u] - mn);
-            l = l * expf(m - mn) + acc;
+            for (int u = 0; u < 8; ++u) acc += __expf(s8[u] - mn);
+            l = l * __expf(m - mn) + acc;
             m = mn;
         }
     }
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
 #pragma unroll
     for (int gg = 0; gg < AG; ++gg) {
         const float mg = m_s[gg * AQ + ti];
-        if (mg != -INFINITY) Lsum += l_s[gg * AQ + ti] * expf(mg - M);
+        if (mg != -INFINITY) Lsum += l_s[gg * AQ + ti] * __expf(mg - M);
     }
     if (!qok) return;
     const float rl = 1.f / Lsum;
@@ -145,7 +151,7 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
             if (c < nchunk) {
                 float p8[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) p8[u] = expf(sc[k][u] - M) * rl;   // exp(-inf) = 0 for keys >= T
+                for (int u = 0; u < 8; ++u) p8[u] = __expf(sc[k][u] - M) * rl;   // exp(-inf) = 0 for keys >= T
                 *reinterpret_cast<uint4*>(Pb + (int64_t)c * Lp * 16) = make_uint4(h2(p8[0], p8[1]), h2(p8[2], p8[3]), h2(p8[4], p8[5]), h2(p8[6], p8[7]));
             }
         }
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int j = 8 * c + u;
-                p8[u] = j < T ? expf(score(j) - M) * rl : 0.f;
+                p8[u] = j < T ? __expf(score(j) - M) * rl : 0.f;
             }
             *reinterpret_cast<uint4*>(Pb + (int64_t)c * Lp * 16) = make_uint4(h2(p8[0], p8[1]), h2(p8[2], p8[3]), h2(p8[4], p8[5]), h2(p8[6], p8[7]));
         }
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(ANT) attn_softmax_kernel(const float* __restri
     for (int r = 0; r < NR; ++r) {
         const int j = i + r - W;
         if (j < 0 || j >= T) continue;
-        const float pv = expf(score(j) - M) * rl;
+        const float pv = __expf(score(j) - M) * rl;
 #pragma unroll
         for (int dd = 0; dd < 16; ++dd)
             if (dd < dpg) acc[dd] = fmaf(pv, ev_s[r * dk + d0 + dd], acc[dd]);
@@ -199,8 +205,8 @@ RVC_API int rvc_attn_softmax(const float* S, const float* qkv, const float* mask
     }
     const int nqb = rvc::cdiv(T, AQ);
     const int nvb = rvc::cdiv(dk * (Tk / 8), ANT);
-    dim3 grid(nqb + nvb, B * n_heads);
+    dim3 grid((unsigned)((nqb + nvb) * B * n_heads));
     rvc::launch_pdl(attn_softmax_kernel, dim3(grid), dim3(ANT), (size_t)(smem), (cudaStream_t)stream, S, qkv, mask, emb_k, emb_v, (uint8_t*)P, R, (uint8_t*)vw, H, n_heads, T, Tk,
-                                                                   (int)rvc_packed_rows(T), window, nqb);
+                                                                   (int)rvc_packed_rows(T), window, nqb, nvb, B * n_heads);
     return rvc::check_launch("rvc_attn_softmax");
 }
