@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 16
+#define RVC_ABI_VERSION 17
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -210,6 +210,28 @@ typedef struct {
     int32_t njobs, B, Cin, Cout, L, dtype, nt, mt, up, pshift, sum_jobs, f32_blocked;
 } rvc_conv1d_tc_desc;
 int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);
+
+/*
+ * One ResBlock step  x' = c2(lrelu(c1_d(lrelu(x)) + b1)) + b2 + x  (ResBlockBase.forward, residuals.py:32-36) in ONE kernel for
+ * the narrow generator stages (C = 32 or 64): the intermediate stays in shared memory as the second conv's tensor-core operand.
+ * Up to three jobs (the three ResBlocks of a stage) per persistent launch.  Per job: a = packed lrelu(x) [B][C/8][rows][8];
+ * w1 / w2 packed [K][C/8][C][8] (rvc_pack_weight), odd K1 / K2, conv1 dilation dil1, conv2 dilation 1, "same" padding;
+ * res, y: fp32 CHANNEL-BLOCKED [B][C/8][L][8] (see rvc_conv1d_tc_desc.f32_blocked; y may alias res); y_act = packed
+ * lrelu(x').  Results are bit-identical to the two rvc_conv1d_tc launches they replace.
+ */
+typedef struct {
+    const void* a;
+    const void* w1; const float* b1;
+    const void* w2; const float* b2;
+    const float* res; float* y; void* y_act;
+    int32_t K1, dil1, K2, reserved;
+} rvc_pair_job;
+typedef struct {
+    rvc_pair_job jobs[3];
+    int32_t njobs, B, C, L, dtype;
+    float slope;        /* leaky_relu slope of both activations (0.1) */
+} rvc_resblock_pair_desc;
+int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* d, void* stream);
 
 /*
  * Softmax stage of the tensor-core attention (MultiHeadAttention.attention, synthesizers.py:221-250).  The contractions run

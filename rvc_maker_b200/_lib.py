@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 DT_BF16, DT_FP16 = 0, 2
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -68,6 +68,17 @@ class Conv1dTcDesc(C.Structure):
                 ("nt", _i32), ("mt", _i32), ("up", _i32), ("pshift", _i32), ("sum_jobs", _i32), ("f32_blocked", _i32)]
 
 
+class PairJob(C.Structure):
+    """rvc_pair_job (include/rvc_b200.h)."""
+    _fields_ = [("a", _vp), ("w1", _vp), ("b1", _vp), ("w2", _vp), ("b2", _vp), ("res", _vp), ("y", _vp), ("y_act", _vp),
+                ("K1", _i32), ("dil1", _i32), ("K2", _i32), ("reserved", _i32)]
+
+
+class ResblockPairDesc(C.Structure):
+    """rvc_resblock_pair_desc."""
+    _fields_ = [("jobs", PairJob * 3), ("njobs", _i32), ("B", _i32), ("C", _i32), ("L", _i32), ("dtype", _i32), ("slope", _f32)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
 SIGNATURES = {
     "rvc_abi_version": (C.c_int, []),
@@ -87,6 +98,7 @@ SIGNATURES = {
     "rvc_noise_conv_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rvc_feature_prep_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_absmax_f32": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp]),
+    "rvc_resblock_pair_tc": (C.c_int, [C.POINTER(ResblockPairDesc), _vp]),
     "rvc_packed_rows": (_i64, [_i32]),
     "rvc_pack_act": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

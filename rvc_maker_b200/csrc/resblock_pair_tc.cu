@@ -1,0 +1,445 @@
+// One ResBlock step  x <- c2(lrelu(c1_d(lrelu(x)))) + x  (residuals.py:32-36) as ONE persistent tcgen05 kernel for the narrow
+// generator stages (C = 32, 64), where the two separate conv launches are bound by the epilogue's HBM traffic, not the tensor pipe.
+//
+// Per tile of 256 rows the intermediate t = lrelu(c1(lrelu(x)) + b1) never leaves the SM: phase 1 accumulates c1 into TMEM, the
+// epilogue rounds t to fp16 straight into a shared-memory tile in the packed operand layout ([c/8][row][8], the K-major
+// no-swizzle core-matrix layout), and phase 2 reads that tile as its A operand — a conv2 tap is again just a descriptor start
+// address 16 B further down.  Saved against two launches: the packed write of t, its read back, one launch.  The tile computes
+// t on rows [l0 - h2, l0 - h2 + 256) and keeps the 256 - (K2-1) outputs that see only real t rows, so consecutive tiles overlap
+// by K2-1 rows (4 % recompute at k = 11).  t rows outside [0, L) are written as zeros: conv2's "same" padding.
+//
+// Roles as in conv1d_tc.cu (512 threads): warp 0 activation producer, warp 2 weight producer (w1 and w2 stream through one ring),
+// warps 1/3 MMA issuers (one 128-row sub-tile each), warps 4-15 epilogue.  Everything is double-buffered (activation tile, t tile,
+// both accumulators) and the two phases are skewed by one tile — every role walks  P1(0), P1(1), P2(0), P1(2), P2(1), ... — so that
+// the tensor pipe works on tile i+1's conv1 while the epilogue still stores tile i.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int TMR = 256;          // rows per tile (two sub-tiles)
+constexpr int PADL = 64;          // zero rows in front of position 0 in packed buffers
+constexpr int ROWQ = 256;
+constexpr int PADR = 64;
+constexpr int RT = 272;           // rows of the t tile: 256 + (K2max - 1), rounded up
+constexpr int NSTAGE = 4;
+constexpr int STAGE_BYTES = 16384;
+constexpr int NTHREADS = 512;
+constexpr int NEG = 3;
+constexpr int MAXJOBS = 3;
+
+inline int packed_rows(int L) { return PADL + ((L + ROWQ - 1) / ROWQ) * ROWQ + PADR; }
+
+struct PParams {
+    rvc_pair_job jobs[MAXJOBS];
+    int njobs, B, C, L, Lp, fp16;
+    int ra;                          // rows per chunk of an activation stage: 256 + max_j (K1-1)*dil1
+    int tiles_before[MAXJOBS + 1];   // prefix sums of the tiles per job
+    int n_lt[MAXJOBS];
+    int tmo[MAXJOBS];                // outputs kept per tile: 256 - (K2-1)
+    int total_tiles;
+    float slope;
+};
+
+__device__ __forceinline__ uint32_t pack2h(float a, float b, int fp16) {
+    uint32_t r;
+    if (fp16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
+
+template <int C>
+__global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParams p) {
+    constexpr int NCH = C / 8;                          // 16-byte channel chunks
+    constexpr int SCH = STAGE_BYTES / (C * 16);         // chunk-rows per weight stage (even)
+    constexpr int EB = 32;                              // accumulator columns per epilogue work item
+    constexpr int NBLK = C / EB;
+    constexpr int NITEM = 2 * NBLK;                     // work items per phase and tile
+    constexpr int TMEM_COLS = 8 * C;                    // 2 phases x 2 buffers x 2 sub-tiles x C columns
+    static_assert(TMEM_COLS <= 512 && (SCH % 2) == 0, "tile shape");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t a_bytes = (uint32_t)NCH * p.ra * 16;
+    constexpr uint32_t t_bytes = (uint32_t)NCH * RT * 16;
+    uint8_t* a_smem = smem;                             // [2][NCH][ra][16]
+    uint8_t* t_smem = smem + 2 * (size_t)a_bytes;       // [2][NCH][RT][16]
+    uint8_t* w_smem = t_smem + 2 * (size_t)t_bytes;     // [NSTAGE][STAGE_BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + NSTAGE * STAGE_BYTES);
+    const uint32_t bar0 = tc::smem_u32(bars);
+    auto W_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto W_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+    auto A_FULL = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 + s); };
+    auto ACC1_FULL = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 4 + s); };
+    auto ACC1_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 6 + s); };
+    auto T_FULL = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 8 + s); };
+    auto T_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 10 + s); };
+    auto ACC2_FULL = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 12 + s); };
+    auto ACC2_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 14 + s); };
+    constexpr int NBAR = 2 * NSTAGE + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+    float* bias_s = reinterpret_cast<float*>(bars + NBAR + 2);     // [njobs][2][C]
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(W_FULL(s), 1); tc::mbar_init(W_EMPTY(s), 2); }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(A_FULL(s), 1);      tc::mbar_init(A_EMPTY(s), 2);
+            tc::mbar_init(ACC1_FULL(s), 2);   tc::mbar_init(ACC1_EMPTY(s), 4 * NEG);
+            tc::mbar_init(T_FULL(s), 4 * NEG); tc::mbar_init(T_EMPTY(s), 2);
+            tc::mbar_init(ACC2_FULL(s), 2);   tc::mbar_init(ACC2_EMPTY(s), 4 * NEG);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
+    if (warp >= 4) {
+        for (int i = threadIdx.x - 128; i < p.njobs * 2 * C; i += NTHREADS - 128) {
+            const int j = i / (2 * C), r = i - j * 2 * C;
+            const float* src = r < C ? p.jobs[j].b1 : p.jobs[j].b2;
+            bias_s[i] = src ? src[r < C ? r : r - C] : 0.f;
+        }
+        // rows 256.. of both t tiles are never written by the epilogue: keep them finite (they only reach discarded outputs)
+        for (int i = threadIdx.x - 128; i < 2 * NCH * (RT - TMR); i += NTHREADS - 128) {
+            const int buf = i / (NCH * (RT - TMR)), r = i - buf * NCH * (RT - TMR);
+            const int ch = r / (RT - TMR), row = TMR + r - ch * (RT - TMR);
+            *reinterpret_cast<uint4*>(t_smem + (size_t)buf * t_bytes + ((size_t)ch * RT + row) * 16) = make_uint4(0, 0, 0, 0);
+        }
+        tc::fence_proxy_async();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    auto decode = [&](int tile, int& j, int& b, int& lt) {
+        j = 0;
+        while (j + 1 < p.njobs && tile >= p.tiles_before[j + 1]) ++j;
+        const int r = tile - p.tiles_before[j];
+        if (p.B == 1) { b = 0; lt = r; }
+        else { b = r / p.n_lt[j]; lt = r - b * p.n_lt[j]; }
+    };
+    const int n_my = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
+
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+        // ======================= activation producer: rows [l0 - h2 - pad1, + 256 + (K1-1)*dil1) of packed lrelu(x) =======================
+        for (int it = 0; it < n_my; ++it) {
+            int j, b, lt;
+            decode(tile_of(it), j, b, lt);
+            const rvc_pair_job& jb = p.jobs[j];
+            const int ast = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int h2 = (jb.K2 - 1) / 2, pad1 = (jb.K1 - 1) / 2 * jb.dil1;
+            const int row0 = PADL + lt * p.tmo[j] - h2 - pad1;                       // >= 0 (host checks h2 + pad1 <= PADL)
+            int rows = TMR + (jb.K1 - 1) * jb.dil1;
+            rows = min(rows, p.Lp - row0);                                           // the last tile must not read past the buffer
+            if (lane == 0) {
+                tc::mbar_wait(A_EMPTY(ast), aph ^ 1);
+                tc::mbar_arrive_expect_tx(A_FULL(ast), (uint32_t)NCH * rows * 16);
+            }
+            __syncwarp();
+            const uint8_t* asrc = reinterpret_cast<const uint8_t*>(jb.a) + (size_t)b * NCH * p.Lp * 16 + (size_t)row0 * 16;
+            for (int c = lane; c < NCH; c += 32)
+                tc::bulk_g2s(tc::smem_u32(a_smem + (size_t)ast * a_bytes + (size_t)c * p.ra * 16), asrc + (size_t)c * p.Lp * 16, (uint32_t)rows * 16,
+                             A_FULL(ast));
+        }
+    } else if (warp == 2) {
+        // ======================= weight producer: w1(0), w1(1), w2(0), w1(2), w2(1), ... through one ring =======================
+        uint32_t wst = 0, wph = 0;
+        auto stream = [&](const void* w, int K) {
+            const int nflat = K * NCH;
+            for (int f0 = 0; f0 < nflat; f0 += SCH) {
+                const int nu = min(SCH, nflat - f0);
+                if (lane == 0) {
+                    tc::mbar_wait(W_EMPTY(wst), wph ^ 1);
+                    tc::mbar_arrive_expect_tx(W_FULL(wst), (uint32_t)nu * C * 16);
+                    tc::bulk_g2s(tc::smem_u32(w_smem + wst * STAGE_BYTES), reinterpret_cast<const uint8_t*>(w) + (size_t)f0 * C * 16, (uint32_t)nu * C * 16,
+                                 W_FULL(wst));
+                }
+                __syncwarp();
+                if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
+            }
+        };
+        for (int it = 0; it <= n_my; ++it) {
+            int j, b, lt;
+            if (it < n_my) { decode(tile_of(it), j, b, lt); stream(p.jobs[j].w1, p.jobs[j].K1); }
+            if (it > 0) { decode(tile_of(it - 1), j, b, lt); stream(p.jobs[j].w2, p.jobs[j].K2); }
+        }
+    } else {
+        // ======================= MMA issuers: warp 1 -> rows 0..127, warp 3 -> rows 128..255 of the tile =======================
+        const int m = (warp == 1) ? 0 : 1;
+        const uint32_t idesc = tc::make_idesc(p.fp16 ? 0u : 1u, C);
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+        const uint32_t b_lo_hi = ((uint32_t)C & 0x3FFFu) << 16;
+        uint32_t wst = 0, wph = 0;
+        // one conv phase: K taps x NCH/2 k-steps; A rows advance by `dil` per tap and 2*lbo_rows per k-step
+        auto run_phase = [&](uint32_t d_tmem, uint32_t a_addr16, uint32_t lbo_rows, int K, uint32_t dil) {
+            const uint32_t a_lo_hi = (lbo_rows & 0x3FFFu) << 16;
+            const uint32_t da_base = a_lo_hi | ((a_addr16 + (uint32_t)(m * BM)) & 0x3FFFu);
+            const int nflat = K * NCH;
+            int ch = 0;
+            uint32_t tap_off = 0, da_lo = da_base, accumulate = 0;
+            for (int f0 = 0; f0 < nflat; f0 += SCH) {
+                const int nu = min(SCH, nflat - f0);
+                tc::mbar_wait(W_FULL(wst), wph);
+                tc::fence_after_sync();
+                uint32_t db_lo = b_lo_hi | ((tc::smem_u32(w_smem + wst * STAGE_BYTES) >> 4) & 0x3FFFu);
+                int u = 0;
+                while (u < nu) {
+                    const int run = min(nu - u, NCH - ch);
+                    for (int r = 0; r < run; r += 2) {
+                        if (tc::elect_one())
+                            tc::umma<false>(d_tmem, ((uint64_t)desc_hi << 32) | da_lo, ((uint64_t)desc_hi << 32) | db_lo, idesc, accumulate);
+                        accumulate = 1;
+                        da_lo += 2u * lbo_rows;
+                        db_lo += 2u * C;
+                    }
+                    u += run;
+                    ch += run;
+                    if (ch == NCH) { ch = 0; tap_off += dil; da_lo = da_base + tap_off; }
+                }
+                if (tc::elect_one()) tc::umma_commit(W_EMPTY(wst));
+                if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
+            }
+        };
+        for (int it = 0; it <= n_my; ++it) {
+            int j, b, lt;
+            if (it < n_my) {   // ---- phase 1 of tile it
+                decode(tile_of(it), j, b, lt);
+                const int g = it & 1;
+                const uint32_t gph = (it >> 1) & 1;
+                tc::mbar_wait(ACC1_EMPTY(g), gph ^ 1);
+                tc::mbar_wait(A_FULL(g), gph);
+                tc::fence_after_sync();
+                run_phase(tmem_base + (uint32_t)((g * 2 + m) * C), tc::smem_u32(a_smem + (size_t)g * a_bytes) >> 4, (uint32_t)p.ra, p.jobs[j].K1,
+                          (uint32_t)p.jobs[j].dil1);
+                if (tc::elect_one()) { tc::umma_commit(A_EMPTY(g)); tc::umma_commit(ACC1_FULL(g)); }
+                __syncwarp();
+            }
+            if (it > 0) {      // ---- phase 2 of tile it - 1
+                decode(tile_of(it - 1), j, b, lt);
+                const int g = (it - 1) & 1;
+                const uint32_t gph = ((it - 1) >> 1) & 1;
+                tc::mbar_wait(ACC2_EMPTY(g), gph ^ 1);
+                tc::mbar_wait(T_FULL(g), gph);
+                tc::fence_after_sync();
+                run_phase(tmem_base + (uint32_t)(4 * C + (g * 2 + m) * C), tc::smem_u32(t_smem + (size_t)g * t_bytes) >> 4, (uint32_t)RT, p.jobs[j].K2, 1u);
+                if (tc::elect_one()) { tc::umma_commit(T_EMPTY(g)); tc::umma_commit(ACC2_FULL(g)); }
+                __syncwarp();
+            }
+        }
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        // ======================= epilogue warps =======================
+        // Step `it` holds the work items of epilogue 1 of tile it (k = 0 .. NITEM-1) and of epilogue 2 of tile it-1
+        // (k = NITEM .. 2*NITEM-1) in ONE list shared round-robin by the three warpgroups (k = eg, eg+3, ...): 8 items over 3
+        // warpgroups cost 3 item times, two separate 4-item phases would cost 4.  The residual of a warp's next epilogue-2 item is
+        // requested before it turns to its epilogue-1 items (and before the accumulator wait), so its latency is hidden.
+        const int q = warp & 3;
+        const int eg = (warp - 4) >> 2;
+        const size_t cs = (size_t)p.L * 8;                               // stride between 8-channel blocks of the fp32 streams
+        const int first2 = eg + NEG * ((NITEM - eg + NEG - 1) / NEG);    // this warpgroup's first epilogue-2 item index (>= NITEM)
+        float vn[EB];
+        for (int it = 0; it <= n_my; ++it) {
+            const bool has1 = it < n_my, has2 = it > 0;
+            int j1 = 0, b1 = 0, lt1 = 0, j2 = 0, b2 = 0, lt2 = 0;
+            if (has1) decode(tile_of(it), j1, b1, lt1);
+            if (has2) decode(tile_of(it - 1), j2, b2, lt2);
+            const rvc_pair_job& jb2 = p.jobs[j2];
+            const int l02 = lt2 * p.tmo[j2];
+            auto res_load = [&](int k, float* dst) {        // residual of epilogue-2 item k - NITEM of tile it-1
+                const int item = k - NITEM;
+                const int m = item / NBLK, cb = item - m * NBLK;
+                const int r2 = m * BM + q * 32 + lane;
+                const int l = l02 + r2;
+                if (!(r2 < p.tmo[j2] && l < p.L)) return;
+                const float* rp = jb2.res + (size_t)b2 * C * p.L + (size_t)(cb * (EB / 8)) * cs + (size_t)l * 8;
+#pragma unroll
+                for (int u = 0; u < EB / 8; ++u) tc::ldg256(rp + (size_t)u * cs, dst + 8 * u);
+            };
+            if (has2 && first2 < 2 * NITEM) res_load(first2, vn);
+            if (has1) {
+                // ---- epilogue 1 of tile it: t = lrelu(acc1 + b1) -> fp16 -> shared-memory operand tile (zeros outside [0, L))
+                const rvc_pair_job& jb = p.jobs[j1];
+                const int g = it & 1;
+                const uint32_t gph = (it >> 1) & 1;
+                const int l0 = lt1 * p.tmo[j1] - (jb.K2 - 1) / 2;        // position of t row 0
+                tc::mbar_wait(ACC1_FULL(g), gph);
+                tc::mbar_wait(T_EMPTY(g), gph ^ 1);
+                tc::fence_after_sync();
+                uint8_t* tb = t_smem + (size_t)g * t_bytes;
+#pragma unroll 1
+                for (int item = eg; item < NITEM; item += NEG) {
+                    const int m = item / NBLK, cb = item - m * NBLK;
+                    const int row = m * BM + q * 32 + lane;
+                    const int pos = l0 + row;
+                    const bool inside = pos >= 0 && pos < p.L;
+                    uint32_t r[EB];
+                    tc::tmem_ld<EB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * 2 + m) * C + cb * EB), r);
+                    tc::tmem_ld_wait();
+                    const float4* bs4 = reinterpret_cast<const float4*>(bias_s + (j1 * 2) * C + cb * EB);
+#pragma unroll
+                    for (int u = 0; u < EB / 8; ++u) {
+                        const float4 c0 = bs4[2 * u], c1 = bs4[2 * u + 1];
+                        uint4 pk;
+                        pk.x = pack2h(lrelu_max(__uint_as_float(r[8 * u + 0]) + c0.x, p.slope), lrelu_max(__uint_as_float(r[8 * u + 1]) + c0.y, p.slope), p.fp16);
+                        pk.y = pack2h(lrelu_max(__uint_as_float(r[8 * u + 2]) + c0.z, p.slope), lrelu_max(__uint_as_float(r[8 * u + 3]) + c0.w, p.slope), p.fp16);
+                        pk.z = pack2h(lrelu_max(__uint_as_float(r[8 * u + 4]) + c1.x, p.slope), lrelu_max(__uint_as_float(r[8 * u + 5]) + c1.y, p.slope), p.fp16);
+                        pk.w = pack2h(lrelu_max(__uint_as_float(r[8 * u + 6]) + c1.z, p.slope), lrelu_max(__uint_as_float(r[8 * u + 7]) + c1.w, p.slope), p.fp16);
+                        if (!inside) pk = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4*>(tb + ((size_t)(cb * (EB / 8) + u) * RT + row) * 16) = pk;
+                    }
+                }
+                tc::fence_before_sync();
+                tc::fence_proxy_async();          // the t tile is read by the tensor core through the async proxy
+                __syncwarp();
+                if (lane == 0) { tc::mbar_arrive(T_FULL(g)); tc::mbar_arrive(ACC1_EMPTY(g)); }
+            }
+            if (has2) {
+                // ---- epilogue 2 of tile it - 1: x' = acc2 + b2 + x  ->  fp32 (channel-blocked) and packed lrelu(x')
+                const int g = (it - 1) & 1;
+                const uint32_t gph = ((it - 1) >> 1) & 1;
+                tc::mbar_wait(ACC2_FULL(g), gph);
+                tc::fence_after_sync();
+#pragma unroll 1
+                for (int k = first2; k < 2 * NITEM; k += NEG) {
+                    const int item = k - NITEM;
+                    const int m = item / NBLK, cb = item - m * NBLK;
+                    const int r2 = m * BM + q * 32 + lane;
+                    const int l = l02 + r2;
+                    const bool ok = r2 < p.tmo[j2] && l < p.L;
+                    float v[EB];
+#pragma unroll
+                    for (int i = 0; i < EB; ++i) v[i] = vn[i];
+                    if (k + NEG < 2 * NITEM) res_load(k + NEG, vn);
+                    uint32_t r[EB];
+                    tc::tmem_ld<EB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(4 * C + (g * 2 + m) * C + cb * EB), r);
+                    tc::tmem_ld_wait();
+                    if (!ok) continue;
+                    const float4* bs4 = reinterpret_cast<const float4*>(bias_s + (j2 * 2 + 1) * C + cb * EB);
+#pragma unroll
+                    for (int i4 = 0; i4 < EB / 4; ++i4) {
+                        const float4 b4 = bs4[i4];
+                        v[4 * i4 + 0] += __uint_as_float(r[4 * i4 + 0]) + b4.x;
+                        v[4 * i4 + 1] += __uint_as_float(r[4 * i4 + 1]) + b4.y;
+                        v[4 * i4 + 2] += __uint_as_float(r[4 * i4 + 2]) + b4.z;
+                        v[4 * i4 + 3] += __uint_as_float(r[4 * i4 + 3]) + b4.w;
+                    }
+                    float* yp = jb2.y + (size_t)b2 * C * p.L + (size_t)(cb * (EB / 8)) * cs + (size_t)l * 8;
+#pragma unroll
+                    for (int u = 0; u < EB / 8; ++u) tc::stg256(yp + (size_t)u * cs, v + 8 * u);
+                    uint8_t* yb = reinterpret_cast<uint8_t*>(jb2.y_act) + (size_t)b2 * NCH * p.Lp * 16 + (((size_t)cb * (EB / 8)) * p.Lp + PADL + l) * 16;
+#pragma unroll
+                    for (int u = 0; u < EB / 8; ++u) {
+                        uint4 pk;
+                        pk.x = pack2h(lrelu_max(v[8 * u + 0], p.slope), lrelu_max(v[8 * u + 1], p.slope), p.fp16);
+                        pk.y = pack2h(lrelu_max(v[8 * u + 2], p.slope), lrelu_max(v[8 * u + 3], p.slope), p.fp16);
+                        pk.z = pack2h(lrelu_max(v[8 * u + 4], p.slope), lrelu_max(v[8 * u + 5], p.slope), p.fp16);
+                        pk.w = pack2h(lrelu_max(v[8 * u + 6], p.slope), lrelu_max(v[8 * u + 7], p.slope), p.fp16);
+                        *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp * 16) = pk;
+                    }
+                }
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(ACC2_EMPTY(g));
+            }
+        }
+    }
+
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+int sm_count() {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return sms[dev] > 0 ? sms[dev] : 148;
+}
+
+template <int C>
+int launch_pair(const PParams& p, size_t smem, int grid, cudaStream_t stream) {
+    auto kern = resblock_pair_kernel<C>;
+    static bool opted[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !opted[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return rvc::fail((int)e, "rvc_resblock_pair_tc: smem opt-in: %s", cudaGetErrorString(e));
+        if (dev >= 0 && dev < 64) opted[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+    if (le != cudaSuccess) return rvc::fail((int)le, "rvc_resblock_pair_tc: launch: %s", cudaGetErrorString(le));
+    return rvc::check_launch("rvc_resblock_pair_tc");
+}
+
+}  // namespace
+
+RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream) {
+    if (!dp) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: null descriptor");
+    const rvc_resblock_pair_desc& d = *dp;
+    if (d.njobs < 1 || d.njobs > MAXJOBS) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: njobs must be 1..3");
+    if (d.dtype != RVC_DT_BF16 && d.dtype != RVC_DT_FP16) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: dtype must be RVC_DT_BF16 or RVC_DT_FP16");
+    if (d.C != 32 && d.C != 64) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: C=%d (the fused pair covers C = 32 and 64)", d.C);
+    if (d.B <= 0 || d.L <= 0) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: bad shape");
+    if (!(d.slope >= 0.f && d.slope <= 1.f)) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: slope must be in [0, 1]");
+    PParams p;
+    p.njobs = d.njobs; p.B = d.B; p.C = d.C; p.L = d.L; p.Lp = packed_rows(d.L); p.fp16 = d.dtype == RVC_DT_FP16; p.slope = d.slope;
+    int halo1 = 0;
+    long total = 0;
+    for (int j = 0; j < d.njobs; ++j) {
+        const rvc_pair_job& jb = d.jobs[j];
+        if (!jb.a || !jb.w1 || !jb.w2 || !jb.res || !jb.y || !jb.y_act) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d has a null pointer", j);
+        if (jb.a == jb.y_act) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: y_act must not alias a (tiles read a with halos while others write y_act)", j);
+        if (jb.K1 <= 0 || !(jb.K1 & 1) || jb.K2 <= 0 || !(jb.K2 & 1) || jb.dil1 <= 0)
+            return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: job %d needs odd kernel sizes and dil1 > 0", j);
+        if (jb.K2 - 1 > RT - TMR) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: K2=%d exceeds %d", jb.K2, RT - TMR + 1);
+        if ((jb.K1 - 1) / 2 * jb.dil1 + (jb.K2 - 1) / 2 > PADL)
+            return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: halo %d exceeds the %d zero rows of the packed layout", (jb.K1 - 1) / 2 * jb.dil1 + (jb.K2 - 1) / 2, PADL);
+        if ((((uintptr_t)jb.res | (uintptr_t)jb.y) & 31) || (((uintptr_t)jb.a | (uintptr_t)jb.w1 | (uintptr_t)jb.w2 | (uintptr_t)jb.y_act) & 15))
+            return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: fp32 streams need 32-byte, packed buffers 16-byte alignment", j);
+        halo1 = (jb.K1 - 1) * jb.dil1 > halo1 ? (jb.K1 - 1) * jb.dil1 : halo1;
+        p.tmo[j] = TMR - (jb.K2 - 1);
+        p.n_lt[j] = rvc::cdiv(d.L, p.tmo[j]);
+        p.tiles_before[j] = (int)total;
+        total += (long)d.B * p.n_lt[j];
+        p.jobs[j] = jb;
+    }
+    if (total > 0x7fffffffL) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: too many tiles");
+    for (int j = d.njobs; j <= MAXJOBS; ++j) p.tiles_before[j] = (int)total;
+    p.total_tiles = (int)total;
+    p.ra = TMR + halo1;
+    const int nch = d.C / 8;
+    const size_t smem = 2 * (size_t)nch * p.ra * 16 + 2 * (size_t)nch * RT * 16 + (size_t)NSTAGE * STAGE_BYTES + 512 + (size_t)d.njobs * 2 * d.C * sizeof(float);
+    if (smem > 227 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: tile does not fit shared memory (%zu bytes)", smem);
+    const int sms = sm_count();
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    if (d.C == 64) return launch_pair<64>(p, smem, grid, (cudaStream_t)stream);
+    return launch_pair<32>(p, smem, grid, (cudaStream_t)stream);
+}

@@ -8,11 +8,12 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc
+from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc, ResblockPairDesc
 
 LRELU_SLOPE = 0.1
 WINDOW = 10
@@ -112,6 +113,7 @@ class Engine:
         self.graphs = {}
         self._warm = set()
         self.use_graph = bool(getattr(m, "use_cuda_graph", True))
+        self.pair_fusion = os.environ.get("RVC_B200_PAIR_FUSION", "1") != "0"   # fused ResBlock steps in the C = 32 / 64 stages
 
     # ------------------------------------------------------------------ weight folding / packing
     def _fold(self, m):
@@ -632,8 +634,32 @@ class Engine:
                 avg = (self._buf(p, B * Ci * Li) if blk else S[1]) if need_f32 else None
                 nsteps = len(rds[0])
                 assert all(len(dl) == nsteps for dl in rds)
+                # narrow, fully blocked stages: one fused launch per ResBlock step (conv1 -> lrelu -> conv2 + x, the intermediate
+                # stays in shared memory, rvc_resblock_pair_tc) for every step but the last, whose conv2 is the fused stage average
+                use_pair = blk and Ci in (32, 64) and self.pair_fusion
+                src_a = {j: xa for j in range(nk)}     # packed lrelu(x_j) read by the next conv1
+                t_of = {}
                 for mm in range(nsteps):
                     last = mm == nsteps - 1
+                    if use_pair and not last:
+                        pd = ResblockPairDesc()
+                        pd.njobs, pd.B, pd.C, pd.L, pd.dtype, pd.slope = nk, B, Ci, Li, dt, LRELU_SLOPE
+                        fl = 0.0
+                        for slot, j in enumerate(order):
+                            pj = pd.jobs[slot]
+                            kk = rks[j]
+                            dst_a = pa[j] if src_a[j] is not pa[j] else ta[j]     # ping-pong: tiles read `a` with halos while others write y_act
+                            pj.a = src_a[j].data_ptr()
+                            pj.w1, pj.b1 = W[f"rb{i}_{j}_c1w{mm}"].data_ptr(), W[f"rb{i}_{j}_c1b{mm}"].data_ptr()
+                            pj.w2, pj.b2 = W[f"rb{i}_{j}_c2w{mm}"].data_ptr(), W[f"rb{i}_{j}_c2b{mm}"].data_ptr()
+                            pj.res, pj.y, pj.y_act = (S[0] if mm == 0 else P[j]).data_ptr(), P[j].data_ptr(), dst_a.data_ptr()
+                            pj.K1, pj.dil1, pj.K2 = kk, rds[j][mm], kk
+                            src_a[j] = dst_a
+                            fl += 4.0 * B * Ci * Ci * kk * Li
+                        p.keep.append(pd)
+                        p.add(f"rbpair{i}_s{mm}", lib.rvc_resblock_pair_tc, C.byref(pd), flops=fl, bytes_=nk * B * Ci * Li * (esz + 8.0 + esz),
+                              kind=f"resblock_pair_tc_{'bf16' if dt == DT_BF16 else 'fp16'}[C{Ci}]")
+                        continue
                     for half in (1, 2):
                         d = Conv1dTcDesc()
                         d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype = nk, B, Ci, Ci, Li, dt
@@ -650,17 +676,21 @@ class Engine:
                             jb = d.jobs[slot]
                             kk = rks[j]
                             if half == 1:   # t = conv1_d(lrelu(x));  store lrelu(t) packed
-                                jb.a = (xa if mm == 0 else pa[j]).data_ptr()
+                                tdst = ta[j] if src_a[j] is not ta[j] else pa[j]
+                                jb.a = src_a[j].data_ptr()
                                 jb.w, jb.bias = W[f"rb{i}_{j}_c1w{mm}"].data_ptr(), W[f"rb{i}_{j}_c1b{mm}"].data_ptr()
-                                jb.y_act = ta[j].data_ptr()
+                                jb.y_act = tdst.data_ptr()
+                                t_of[j] = tdst
                                 jb.K, jb.dil, jb.pad = kk, rds[j][mm], (kk - 1) // 2 * rds[j][mm]
                             else:           # x = conv2(lrelu(t)) + x;  store x (fp32) and lrelu(x) packed for the next pair
-                                jb.a = ta[j].data_ptr()
+                                jb.a = t_of[j].data_ptr()
                                 jb.w, jb.bias = W[f"rb{i}_{j}_c2w{mm}"].data_ptr(), W[f"rb{i}_{j}_c2b{mm}"].data_ptr()
                                 jb.res, jb.res_bs, jb.res_cs = (S[0] if mm == 0 else P[j]).data_ptr(), Ci * Li, rcs
                                 if not fused:
                                     jb.y_f32, jb.y_bs, jb.y_cs = P[j].data_ptr(), Ci * Li, rcs
-                                    jb.y_act = pa[j].data_ptr()
+                                    ndst = pa[j] if t_of[j] is not pa[j] else ta[j]    # (conv1 of this step has consumed src_a[j])
+                                    jb.y_act = ndst.data_ptr()
+                                    src_a[j] = ndst
                                 elif slot == 0:
                                     if need_f32:   # NCL: into P[0]'s buffer (every thread reads its residuals before it writes)
                                         jb.y_f32, jb.y_bs, jb.y_cs = avg.data_ptr(), Ci * Li, Li

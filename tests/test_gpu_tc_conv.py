@@ -389,3 +389,73 @@ def test_noise_conv_blocked_output():
     ref = F.conv1d(har.unsqueeze(1), w.unsqueeze(1), bias, stride=sn, padding=pn)
     assert float((y0 - ref).abs().max()) <= 1e-4
     assert lib.rvc_noise_conv_f32(har.data_ptr(), Lout * sn, w.data_ptr(), bias.data_ptr(), y1.data_ptr(), Cc * Lout, B, 12, Lout, kn, sn, pn, 1, st) != 0
+
+
+@pytest.mark.parametrize("Cc,L,B", [(64, 3001, 2), (32, 20000, 1), (64, 246, 1), (32, 1, 1), (64, 50000, 1), (32, 777, 3)])
+def test_fused_resblock_pair_equals_two_launches(Cc, L, B):
+    """rvc_resblock_pair_tc (conv1 -> lrelu -> conv2 + residual in one kernel, intermediate in shared memory) against the two
+    rvc_conv1d_tc launches it replaces: same operands, same accumulation order -> bit-identical fp32 and packed outputs."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    dtype = FP16
+    g = torch.Generator(device="cpu").manual_seed(31 + Cc + L)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(L)
+    pd = _lib.ResblockPairDesc()
+    pd.njobs, pd.B, pd.C, pd.L, pd.dtype, pd.slope = 3, B, Cc, L, dtype, 0.1
+    d1, d2 = _lib.Conv1dTcDesc(), _lib.Conv1dTcDesc()
+    for d in (d1, d2):
+        d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype = 3, B, Cc, Cc, L, dtype
+    d2.f32_blocked = 3
+    keep, outs = [], []
+    for j, (k, dil) in enumerate(((11, 5), (7, 3), (3, 1))):
+        x = torch.randn(B, Cc, L, generator=g).to(DEV)
+        w1 = (torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+        w2 = (torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+        b1, b2 = torch.randn(Cc, generator=g).to(DEV), torch.randn(Cc, generator=g).to(DEV)
+        xb = to_blocked(x)
+        a = torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+        w1p = torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+        w2p = torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+        _lib.check(lib.rvc_pack_act(x.data_ptr(), None, None, 1.0, Cc * L, L, None, a.data_ptr(), B, Cc, L, dtype, 0.1, st), "pack_act")
+        _lib.check(lib.rvc_pack_weight(w1.data_ptr(), w1p.data_ptr(), Cc, Cc, k, dtype, st), "pack_weight")
+        _lib.check(lib.rvc_pack_weight(w2.data_ptr(), w2p.data_ptr(), Cc, Cc, k, dtype, st), "pack_weight")
+        ta = torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+        y_ref, ya_ref = torch.zeros_like(xb), torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+        y_fused, ya_fused = torch.zeros_like(xb), torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+        jb = d1.jobs[j]
+        jb.a, jb.w, jb.bias, jb.y_act = a.data_ptr(), w1p.data_ptr(), b1.data_ptr(), ta.data_ptr()
+        jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = k, dil, (k - 1) // 2 * dil, 1.0, 0.1
+        jb = d2.jobs[j]
+        jb.a, jb.w, jb.bias, jb.y_act = ta.data_ptr(), w2p.data_ptr(), b2.data_ptr(), ya_ref.data_ptr()
+        jb.res, jb.res_bs, jb.res_cs = xb.data_ptr(), Cc * L, 8 * L
+        jb.y_f32, jb.y_bs, jb.y_cs = y_ref.data_ptr(), Cc * L, 8 * L
+        jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = k, 1, (k - 1) // 2, 1.0, 0.1
+        pj = pd.jobs[j]
+        pj.a, pj.w1, pj.b1, pj.w2, pj.b2 = a.data_ptr(), w1p.data_ptr(), b1.data_ptr(), w2p.data_ptr(), b2.data_ptr()
+        pj.res, pj.y, pj.y_act = xb.data_ptr(), y_fused.data_ptr(), ya_fused.data_ptr()
+        pj.K1, pj.dil1, pj.K2 = k, dil, k
+        keep += [x, w1, w2, b1, b2, xb, a, w1p, w2p, ta]
+        outs.append((y_ref, ya_ref, y_fused, ya_fused, x, w1, w2, b1, b2, dil, k))
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d1), st), "conv1")
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d2), st), "conv2")
+    _lib.check(lib.rvc_resblock_pair_tc(C.byref(pd), st), "pair")
+    torch.cuda.synchronize()
+    for y_ref, ya_ref, y_fused, ya_fused, x, w1, w2, b1, b2, dil, k in outs:
+        assert torch.equal(y_fused, y_ref)
+        assert torch.equal(ya_fused, ya_ref)
+        t = rnd(F.leaky_relu(F.conv1d(rnd(F.leaky_relu(x, 0.1), dtype).double(), rnd(w1, dtype).double(), b1.double(), dilation=dil,
+                                      padding=(k - 1) // 2 * dil).float(), 0.1), dtype)
+        ref = F.conv1d(t.double(), rnd(w2, dtype).double(), b2.double(), padding=(k - 1) // 2) + x.double()
+        assert float((from_blocked(y_fused).double() - ref).abs().max()) <= 3e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_fused_resblock_pair_rejects_wide_stages():
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    pd = _lib.ResblockPairDesc()
+    pd.njobs, pd.B, pd.C, pd.L, pd.dtype, pd.slope = 1, 1, 128, 1000, FP16, 0.1
+    assert lib.rvc_resblock_pair_tc(C.byref(pd), None) == -2
+    assert b"C = 32 and 64" in lib.rvc_last_error()
