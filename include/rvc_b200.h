@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 17
+#define RVC_ABI_VERSION 19
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -113,11 +113,14 @@ int rvc_embed_prep(const int64_t* pitch, const int64_t* lengths, const float* em
                    int32_t B, int32_t T, int32_t H, void* stream);
 int rvc_pack_rows(const float* x, void* y, int32_t B, int32_t T, int32_t D, int32_t dtype, void* stream);
 
-/* y = LayerNorm_C(x + r) * gamma + beta over the channel axis of [B,C,T] (synthesizers.py:179-181, :346-347);
- * out_mask multiplies by mask[b,t] (the final `x * x_mask`, :348).  y_act (optional): the MASKED result in the packed
- * bf16/fp16 layout of the tensor-core convs (see below), act_dtype = RVC_DT_BF16 / RVC_DT_FP16. */
-int rvc_layernorm_f32(const float* x, const float* r, const float* gamma, const float* beta, const float* mask, float* y,
-                      int32_t B, int32_t C, int32_t T, float eps, int32_t out_mask, void* y_act, int32_t act_dtype, void* stream);
+/* y = LayerNorm_C(x + r [+ r2 + r3]) * gamma + beta over the channel axis of [B,C,T] (synthesizers.py:179-181, :346-347);
+ * r2 / r3 (both or neither) are further partial sums of the residual branch — the FFN's second conv runs as three
+ * input-channel slices in one launch when the sequence is short.  out_mask multiplies by mask[b,t] (the final `x * x_mask`,
+ * :348).  y_act (optional): the MASKED result in the packed bf16/fp16 layout of the tensor-core convs (see below),
+ * act_dtype = RVC_DT_BF16 / RVC_DT_FP16. */
+int rvc_layernorm_f32(const float* x, const float* r, const float* r2, const float* r3, const float* gamma, const float* beta,
+                      const float* mask, float* y, int32_t B, int32_t C, int32_t T, float eps, int32_t out_mask, void* y_act,
+                      int32_t act_dtype, void* stream);
 
 /*
  * Relative-position multi-head attention core (synthesizers.py:221-250), heads share the [2w+1, dk] tables:
@@ -230,6 +233,12 @@ typedef struct {
     rvc_pair_job jobs[3];
     int32_t njobs, B, C, L, dtype;
     float slope;        /* leaky_relu slope of both activations (0.1) */
+    /* sum_jobs = 1: the last step of a stage (synthesizers.py:157-159).  Every tile runs all jobs, their conv2 accumulate into one
+     * tile and job 0's outputs receive alpha * sum_j (c2_j(...) + b2_j + res_j): y (optional; channel-blocked, or plain [B,C,L]
+     * when y_ncl = 1) and y_act (optional; packed lrelu of it). */
+    int32_t sum_jobs, y_ncl;
+    float alpha;
+    int32_t reserved;
 } rvc_resblock_pair_desc;
 int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* d, void* stream);
 

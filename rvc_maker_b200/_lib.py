@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 17
+ABI_VERSION = 19
 DT_BF16, DT_FP16 = 0, 2
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -76,7 +76,8 @@ class PairJob(C.Structure):
 
 class ResblockPairDesc(C.Structure):
     """rvc_resblock_pair_desc."""
-    _fields_ = [("jobs", PairJob * 3), ("njobs", _i32), ("B", _i32), ("C", _i32), ("L", _i32), ("dtype", _i32), ("slope", _f32)]
+    _fields_ = [("jobs", PairJob * 3), ("njobs", _i32), ("B", _i32), ("C", _i32), ("L", _i32), ("dtype", _i32), ("slope", _f32),
+                ("sum_jobs", _i32), ("y_ncl", _i32), ("alpha", _f32), ("reserved", _i32)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
@@ -90,7 +91,7 @@ SIGNATURES = {
     "rvc_embed_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_embed_prep": (C.c_int, [_vp, _vp, _vp, _f32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rvc_pack_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    "rvc_layernorm_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _i32, _vp]),
+    "rvc_layernorm_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _i32, _vp]),
     "rvc_rel_attention_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rvc_cond_gemv_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rvc_sample_zp_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),

@@ -663,8 +663,12 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
             const int c = cands[i];
             if (d.Cout % c || (gated && c % 64)) continue;
             if (c == 16 && NT != 0) break;          // N = 16 MMAs waste 60 % of the pipe: only when nothing wider divides Cout
+            const long t = ntiles(c, 1);
+            // one wave of wider tiles on >= 60 % of the SMs beats 1.x waves of narrower ones (192 -> 768, k = 3, T = 1000:
+            // 96 tiles of 64 columns 7.0 us, 192 tiles of 32 columns 8.9 us)
+            if (NT != 0 && t >= sms && 2 * t < 3L * sms && 5 * ntiles(NT, 1) >= 3L * sms) break;
             NT = c;
-            if (ntiles(c, 1) >= sms) break;
+            if (t >= sms) break;
         }
         if (NT == 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: no N tile for Cout=%d (gated=%d)", d.Cout, gated);
     }

@@ -82,6 +82,7 @@ __device__ __forceinline__ uint32_t ln_pack2(float a, float b, int fp16) {
 }
 
 __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ r,
+                                                            const float* __restrict__ r2, const float* __restrict__ r3,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mask, float* __restrict__ y, int C, int T,
                                                             float eps, int out_mask, uint8_t* __restrict__ y_act, int Lp, int fp16) {
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
             for (int c = ch * 8; c < min(C, ch * 8 + 8); ++c) {
                 float v = x[base + (int64_t)c * T];
                 if (r) v += r[base + (int64_t)c * T];
+                if (r2) v += r2[base + (int64_t)c * T] + r3[base + (int64_t)c * T];
                 s += v;
             }
     red[ty][tx] = s;
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
             for (int c = ch * 8; c < min(C, ch * 8 + 8); ++c) {
                 float v = x[base + (int64_t)c * T];
                 if (r) v += r[base + (int64_t)c * T];
+                if (r2) v += r2[base + (int64_t)c * T] + r3[base + (int64_t)c * T];
                 v -= mean;
                 q = fmaf(v, v, q);
             }
@@ -135,6 +138,7 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
             if (c < C) {
                 float v = x[base + (int64_t)c * T];
                 if (r) v += r[base + (int64_t)c * T];
+                if (r2) v += r2[base + (int64_t)c * T] + r3[base + (int64_t)c * T];
                 o[i] = (v - mean) * rstd * gamma[c] + beta[c];
                 y[base + (int64_t)c * T] = o[i] * m;
             }
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
 // trip instead of three (11.9 -> ~4 us at [192, 1000]: the launch is latency-bound, 32 CTAs).
 template <int NCH>
 __global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ r,
+                                                            const float* __restrict__ r2, const float* __restrict__ r3,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mask, float* __restrict__ y, int C, int T,
                                                             float eps, int out_mask, uint8_t* __restrict__ y_act, int Lp, int fp16) {
@@ -178,6 +183,15 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restr
             for (int i = 0; i < 8; ++i) {
                 const int c = (ty + 8 * k) * 8 + i;
                 if (ok && c < C) v[k][i] += r[base + (int64_t)c * T];
+            }
+    }
+    if (r2) {   // split-K partial sums of the producing conv (the FFN's second conv runs as three input-channel slices)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = (ty + 8 * k) * 8 + i;
+                if (ok && c < C) v[k][i] += r2[base + (int64_t)c * T] + r3[base + (int64_t)c * T];
             }
     }
     float s = 0.f;
@@ -470,9 +484,11 @@ RVC_API int rvc_embed_f32(const float* phone, const int64_t* pitch, const int64_
     return rvc::check_launch("rvc_embed_f32");
 }
 
-RVC_API int rvc_layernorm_f32(const float* x, const float* r, const float* gamma, const float* beta, const float* mask, float* y,
-                                 int32_t B, int32_t C, int32_t T, float eps, int32_t out_mask, void* y_act, int32_t act_dtype, void* stream) {
+RVC_API int rvc_layernorm_f32(const float* x, const float* r, const float* r2, const float* r3, const float* gamma, const float* beta,
+                                 const float* mask, float* y, int32_t B, int32_t C, int32_t T, float eps, int32_t out_mask, void* y_act,
+                                 int32_t act_dtype, void* stream) {
     if (!x || !gamma || !beta || !y || (out_mask && !mask)) return rvc::fail(RVC_EINVAL, "rvc_layernorm_f32: null pointer");
+    if ((r2 == nullptr) != (r3 == nullptr) || (r2 && !r)) return rvc::fail(RVC_EINVAL, "rvc_layernorm_f32: r2 and r3 go together (and need r)");
     if (B <= 0 || B > 65535 || C <= 0 || T < 0) return rvc::fail(RVC_ESHAPE, "rvc_layernorm_f32: bad shape");
     if (y_act && (C % 8 || !mask || (act_dtype != RVC_DT_BF16 && act_dtype != RVC_DT_FP16)))
         return rvc::fail(RVC_EINVAL, "rvc_layernorm_f32: packed output needs C %% 8 == 0, a mask and a bf16/fp16 dtype");
@@ -481,11 +497,11 @@ RVC_API int rvc_layernorm_f32(const float* x, const float* r, const float* gamma
     const int Lp = (int)rvc_packed_rows(T), f16 = act_dtype == RVC_DT_FP16;
     cudaStream_t st = (cudaStream_t)stream;
     const int nper = rvc::cdiv(C, 64);   // 8-channel chunks per thread
-    if (nper == 1) rvc::launch_pdl(layernorm_reg_kernel<1>, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);
-    else if (nper == 2) rvc::launch_pdl(layernorm_reg_kernel<2>, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);
-    else if (nper == 3) rvc::launch_pdl(layernorm_reg_kernel<3>, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);
-    else if (nper == 4) rvc::launch_pdl(layernorm_reg_kernel<4>, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);
-    else rvc::launch_pdl(layernorm_f32_kernel, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);
+    if (nper == 1) rvc::launch_pdl(layernorm_reg_kernel<1>, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, r2, r3, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);
+    else if (nper == 2) rvc::launch_pdl(layernorm_reg_kernel<2>, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, r2, r3, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);
+    else if (nper == 3) rvc::launch_pdl(layernorm_reg_kernel<3>, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, r2, r3, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);
+    else if (nper == 4) rvc::launch_pdl(layernorm_reg_kernel<4>, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, r2, r3, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);
+    else rvc::launch_pdl(layernorm_f32_kernel, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, r2, r3, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);
     return rvc::check_launch("rvc_layernorm_f32");
 }
 

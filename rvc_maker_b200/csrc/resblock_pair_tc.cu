@@ -40,7 +40,9 @@ struct PParams {
     int n_lt[MAXJOBS];
     int tmo[MAXJOBS];                // outputs kept per tile: 256 - (K2-1)
     int total_tiles;
-    float slope;
+    int sum_jobs;                    // every tile runs ALL jobs; conv2 of all jobs accumulates into one tile (stage average)
+    int y_ncl;                       // sum mode: y is plain [B, C, L] instead of channel-blocked
+    float slope, alpha;
 };
 
 __device__ __forceinline__ uint32_t pack2h(float a, float b, int fp16) {
@@ -101,7 +103,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
         for (int i = threadIdx.x - 128; i < p.njobs * 2 * C; i += NTHREADS - 128) {
             const int j = i / (2 * C), r = i - j * 2 * C;
             const float* src = r < C ? p.jobs[j].b1 : p.jobs[j].b2;
-            bias_s[i] = src ? src[r < C ? r : r - C] : 0.f;
+            float v = src ? src[r < C ? r : r - C] : 0.f;
+            if (p.sum_jobs && j == 0 && r >= C)       // the stage average adds every job's conv2 bias
+                for (int jj = 1; jj < p.njobs; ++jj) v += p.jobs[jj].b2 ? p.jobs[jj].b2[r - C] : 0.f;
+            bias_s[i] = v;
         }
         // rows 256.. of both t tiles are never written by the epilogue: keep them finite (they only reach discarded outputs)
         for (int i = threadIdx.x - 128; i < 2 * NCH * (RT - TMR); i += NTHREADS - 128) {
@@ -127,17 +132,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
     };
     const int n_my = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
+    // a *unit* is one (tile, job) conv pair: in the plain mode every tile is one unit of its own job; with sum_jobs a tile is
+    // njobs consecutive units whose phase 2 accumulates into the same accumulator
+    const int J = p.sum_jobs ? p.njobs : 1;
+    const int n_units = n_my * J;
+    auto unit = [&](int n, int& it, int& jj, int& j, int& b, int& lt) {
+        it = J == 1 ? n : n / J;
+        jj = n - it * J;
+        decode(tile_of(it), j, b, lt);
+        if (p.sum_jobs) j = jj;
+    };
 
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ======================= activation producer: rows [l0 - h2 - pad1, + 256 + (K1-1)*dil1) of packed lrelu(x) =======================
-        for (int it = 0; it < n_my; ++it) {
-            int j, b, lt;
-            decode(tile_of(it), j, b, lt);
+        for (int n = 0; n < n_units; ++n) {
+            int it, jj, j, b, lt;
+            unit(n, it, jj, j, b, lt);
             const rvc_pair_job& jb = p.jobs[j];
-            const int ast = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
+            const int ast = n & 1;
+            const uint32_t aph = (n >> 1) & 1;
             const int h2 = (jb.K2 - 1) / 2, pad1 = (jb.K1 - 1) / 2 * jb.dil1;
             const int row0 = PADL + lt * p.tmo[j] - h2 - pad1;                       // >= 0 (host checks h2 + pad1 <= PADL)
             int rows = TMR + (jb.K1 - 1) * jb.dil1;
@@ -169,10 +184,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
             }
         };
-        for (int it = 0; it <= n_my; ++it) {
-            int j, b, lt;
-            if (it < n_my) { decode(tile_of(it), j, b, lt); stream(p.jobs[j].w1, p.jobs[j].K1); }
-            if (it > 0) { decode(tile_of(it - 1), j, b, lt); stream(p.jobs[j].w2, p.jobs[j].K2); }
+        for (int n = 0; n <= n_units; ++n) {
+            int it, jj, j, b, lt;
+            if (n < n_units) { unit(n, it, jj, j, b, lt); stream(p.jobs[j].w1, p.jobs[j].K1); }
+            if (n > 0) { unit(n - 1, it, jj, j, b, lt); stream(p.jobs[j].w2, p.jobs[j].K2); }
         }
     } else {
         // ======================= MMA issuers: warp 1 -> rows 0..127, warp 3 -> rows 128..255 of the tile =======================
@@ -182,12 +197,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
         const uint32_t b_lo_hi = ((uint32_t)C & 0x3FFFu) << 16;
         uint32_t wst = 0, wph = 0;
         // one conv phase: K taps x NCH/2 k-steps; A rows advance by `dil` per tap and 2*lbo_rows per k-step
-        auto run_phase = [&](uint32_t d_tmem, uint32_t a_addr16, uint32_t lbo_rows, int K, uint32_t dil) {
+        auto run_phase = [&](uint32_t d_tmem, uint32_t a_addr16, uint32_t lbo_rows, int K, uint32_t dil, uint32_t accumulate) {
             const uint32_t a_lo_hi = (lbo_rows & 0x3FFFu) << 16;
             const uint32_t da_base = a_lo_hi | ((a_addr16 + (uint32_t)(m * BM)) & 0x3FFFu);
             const int nflat = K * NCH;
             int ch = 0;
-            uint32_t tap_off = 0, da_lo = da_base, accumulate = 0;
+            uint32_t tap_off = 0, da_lo = da_base;
             for (int f0 = 0; f0 < nflat; f0 += SCH) {
                 const int nu = min(SCH, nflat - f0);
                 tc::mbar_wait(W_FULL(wst), wph);
@@ -211,29 +226,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
             }
         };
-        for (int it = 0; it <= n_my; ++it) {
-            int j, b, lt;
-            if (it < n_my) {   // ---- phase 1 of tile it
-                decode(tile_of(it), j, b, lt);
-                const int g = it & 1;
-                const uint32_t gph = (it >> 1) & 1;
+        for (int n = 0; n <= n_units; ++n) {
+            int it, jj, j, b, lt;
+            if (n < n_units) {   // ---- phase 1 of unit n
+                unit(n, it, jj, j, b, lt);
+                const int g = n & 1;
+                const uint32_t gph = (n >> 1) & 1;
                 tc::mbar_wait(ACC1_EMPTY(g), gph ^ 1);
                 tc::mbar_wait(A_FULL(g), gph);
                 tc::fence_after_sync();
                 run_phase(tmem_base + (uint32_t)((g * 2 + m) * C), tc::smem_u32(a_smem + (size_t)g * a_bytes) >> 4, (uint32_t)p.ra, p.jobs[j].K1,
-                          (uint32_t)p.jobs[j].dil1);
+                          (uint32_t)p.jobs[j].dil1, 0u);
                 if (tc::elect_one()) { tc::umma_commit(A_EMPTY(g)); tc::umma_commit(ACC1_FULL(g)); }
                 __syncwarp();
             }
-            if (it > 0) {      // ---- phase 2 of tile it - 1
-                decode(tile_of(it - 1), j, b, lt);
-                const int g = (it - 1) & 1;
-                const uint32_t gph = ((it - 1) >> 1) & 1;
-                tc::mbar_wait(ACC2_EMPTY(g), gph ^ 1);
+            if (n > 0) {         // ---- phase 2 of unit n - 1 (accumulates over the jobs of a tile with sum_jobs)
+                unit(n - 1, it, jj, j, b, lt);
+                const int g = (n - 1) & 1;
+                const uint32_t gph = ((n - 1) >> 1) & 1;
+                const int g2 = it & 1;
+                if (jj == 0) tc::mbar_wait(ACC2_EMPTY(g2), ((it >> 1) & 1) ^ 1);
                 tc::mbar_wait(T_FULL(g), gph);
                 tc::fence_after_sync();
-                run_phase(tmem_base + (uint32_t)(4 * C + (g * 2 + m) * C), tc::smem_u32(t_smem + (size_t)g * t_bytes) >> 4, (uint32_t)RT, p.jobs[j].K2, 1u);
-                if (tc::elect_one()) { tc::umma_commit(T_EMPTY(g)); tc::umma_commit(ACC2_FULL(g)); }
+                run_phase(tmem_base + (uint32_t)(4 * C + (g2 * 2 + m) * C), tc::smem_u32(t_smem + (size_t)g * t_bytes) >> 4, (uint32_t)RT, p.jobs[j].K2, 1u,
+                          jj ? 1u : 0u);
+                if (tc::elect_one()) {
+                    tc::umma_commit(T_EMPTY(g));
+                    if (jj == J - 1) tc::umma_commit(ACC2_FULL(g2));
+                }
                 __syncwarp();
             }
         }
@@ -250,29 +270,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
         const size_t cs = (size_t)p.L * 8;                               // stride between 8-channel blocks of the fp32 streams
         const int first2 = eg + NEG * ((NITEM - eg + NEG - 1) / NEG);    // this warpgroup's first epilogue-2 item index (>= NITEM)
         float vn[EB];
-        for (int it = 0; it <= n_my; ++it) {
-            const bool has1 = it < n_my, has2 = it > 0;
-            int j1 = 0, b1 = 0, lt1 = 0, j2 = 0, b2 = 0, lt2 = 0;
-            if (has1) decode(tile_of(it), j1, b1, lt1);
-            if (has2) decode(tile_of(it - 1), j2, b2, lt2);
+        for (int n = 0; n <= n_units; ++n) {
+            const bool has1 = n < n_units;
+            int it1 = 0, jj1 = 0, j1 = 0, b1 = 0, lt1 = 0, it2 = 0, jj2 = 0, j2 = 0, b2 = 0, lt2 = 0;
+            if (has1) unit(n, it1, jj1, j1, b1, lt1);
+            if (n > 0) unit(n - 1, it2, jj2, j2, b2, lt2);
+            const bool has2 = n > 0 && jj2 == J - 1;      // unit n-1 closed its tile: the accumulator of tile it2 is complete
+            if (p.sum_jobs) j2 = 0;                       // outputs / summed bias of the stage average live in job 0
             const rvc_pair_job& jb2 = p.jobs[j2];
             const int l02 = lt2 * p.tmo[j2];
-            auto res_load = [&](int k, float* dst) {        // residual of epilogue-2 item k - NITEM of tile it-1
+            auto res_load = [&](int k, float* dst) {      // residual(s) of epilogue-2 item k - NITEM of tile it2
                 const int item = k - NITEM;
                 const int m = item / NBLK, cb = item - m * NBLK;
                 const int r2 = m * BM + q * 32 + lane;
                 const int l = l02 + r2;
                 if (!(r2 < p.tmo[j2] && l < p.L)) return;
-                const float* rp = jb2.res + (size_t)b2 * C * p.L + (size_t)(cb * (EB / 8)) * cs + (size_t)l * 8;
+                const size_t off = (size_t)b2 * C * p.L + (size_t)(cb * (EB / 8)) * cs + (size_t)l * 8;
 #pragma unroll
-                for (int u = 0; u < EB / 8; ++u) tc::ldg256(rp + (size_t)u * cs, dst + 8 * u);
+                for (int u = 0; u < EB / 8; ++u) tc::ldg256(jb2.res + off + (size_t)u * cs, dst + 8 * u);
+                if (p.sum_jobs)
+                    for (int jx = 1; jx < p.njobs; ++jx) {
+#pragma unroll
+                        for (int u = 0; u < EB / 8; ++u) {
+                            float t8[8];
+                            tc::ldg256(p.jobs[jx].res + off + (size_t)u * cs, t8);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) dst[8 * u + i] += t8[i];
+                        }
+                    }
             };
             if (has2 && first2 < 2 * NITEM) res_load(first2, vn);
             if (has1) {
-                // ---- epilogue 1 of tile it: t = lrelu(acc1 + b1) -> fp16 -> shared-memory operand tile (zeros outside [0, L))
+                // ---- epilogue 1 of unit n: t = lrelu(acc1 + b1) -> fp16 -> shared-memory operand tile (zeros outside [0, L))
                 const rvc_pair_job& jb = p.jobs[j1];
-                const int g = it & 1;
-                const uint32_t gph = (it >> 1) & 1;
+                const int g = n & 1;
+                const uint32_t gph = (n >> 1) & 1;
                 const int l0 = lt1 * p.tmo[j1] - (jb.K2 - 1) / 2;        // position of t row 0
                 tc::mbar_wait(ACC1_FULL(g), gph);
                 tc::mbar_wait(T_EMPTY(g), gph ^ 1);
@@ -306,9 +338,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 if (lane == 0) { tc::mbar_arrive(T_FULL(g)); tc::mbar_arrive(ACC1_EMPTY(g)); }
             }
             if (has2) {
-                // ---- epilogue 2 of tile it - 1: x' = acc2 + b2 + x  ->  fp32 (channel-blocked) and packed lrelu(x')
-                const int g = (it - 1) & 1;
-                const uint32_t gph = ((it - 1) >> 1) & 1;
+                // ---- epilogue 2 of tile it2: x' = alpha * (acc2 + b2 + x)  ->  fp32 and packed lrelu(x')
+                const int g = it2 & 1;
+                const uint32_t gph = (it2 >> 1) & 1;
                 tc::mbar_wait(ACC2_FULL(g), gph);
                 tc::fence_after_sync();
 #pragma unroll 1
@@ -335,18 +367,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                         v[4 * i4 + 2] += __uint_as_float(r[4 * i4 + 2]) + b4.z;
                         v[4 * i4 + 3] += __uint_as_float(r[4 * i4 + 3]) + b4.w;
                     }
-                    float* yp = jb2.y + (size_t)b2 * C * p.L + (size_t)(cb * (EB / 8)) * cs + (size_t)l * 8;
+                    if (p.sum_jobs) {
 #pragma unroll
-                    for (int u = 0; u < EB / 8; ++u) tc::stg256(yp + (size_t)u * cs, v + 8 * u);
-                    uint8_t* yb = reinterpret_cast<uint8_t*>(jb2.y_act) + (size_t)b2 * NCH * p.Lp * 16 + (((size_t)cb * (EB / 8)) * p.Lp + PADL + l) * 16;
+                        for (int i = 0; i < EB; ++i) v[i] *= p.alpha;
+                    }
+                    if (jb2.y) {
+                        if (p.y_ncl) {
+                            float* yp = jb2.y + (size_t)b2 * C * p.L + (size_t)(cb * EB) * p.L + l;
 #pragma unroll
-                    for (int u = 0; u < EB / 8; ++u) {
-                        uint4 pk;
-                        pk.x = pack2h(lrelu_max(v[8 * u + 0], p.slope), lrelu_max(v[8 * u + 1], p.slope), p.fp16);
-                        pk.y = pack2h(lrelu_max(v[8 * u + 2], p.slope), lrelu_max(v[8 * u + 3], p.slope), p.fp16);
-                        pk.z = pack2h(lrelu_max(v[8 * u + 4], p.slope), lrelu_max(v[8 * u + 5], p.slope), p.fp16);
-                        pk.w = pack2h(lrelu_max(v[8 * u + 6], p.slope), lrelu_max(v[8 * u + 7], p.slope), p.fp16);
-                        *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp * 16) = pk;
+                            for (int i = 0; i < EB; ++i) yp[(size_t)i * p.L] = v[i];
+                        } else {
+                            float* yp = jb2.y + (size_t)b2 * C * p.L + (size_t)(cb * (EB / 8)) * cs + (size_t)l * 8;
+#pragma unroll
+                            for (int u = 0; u < EB / 8; ++u) tc::stg256(yp + (size_t)u * cs, v + 8 * u);
+                        }
+                    }
+                    if (jb2.y_act) {
+                        uint8_t* yb = reinterpret_cast<uint8_t*>(jb2.y_act) + (size_t)b2 * NCH * p.Lp * 16 + (((size_t)cb * (EB / 8)) * p.Lp + PADL + l) * 16;
+#pragma unroll
+                        for (int u = 0; u < EB / 8; ++u) {
+                            uint4 pk;
+                            pk.x = pack2h(lrelu_max(v[8 * u + 0], p.slope), lrelu_max(v[8 * u + 1], p.slope), p.fp16);
+                            pk.y = pack2h(lrelu_max(v[8 * u + 2], p.slope), lrelu_max(v[8 * u + 3], p.slope), p.fp16);
+                            pk.z = pack2h(lrelu_max(v[8 * u + 4], p.slope), lrelu_max(v[8 * u + 5], p.slope), p.fp16);
+                            pk.w = pack2h(lrelu_max(v[8 * u + 6], p.slope), lrelu_max(v[8 * u + 7], p.slope), p.fp16);
+                            *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp * 16) = pk;
+                        }
                     }
                 }
                 tc::fence_before_sync();
@@ -411,28 +457,39 @@ RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream)
     if (!(d.slope >= 0.f && d.slope <= 1.f)) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: slope must be in [0, 1]");
     PParams p;
     p.njobs = d.njobs; p.B = d.B; p.C = d.C; p.L = d.L; p.Lp = packed_rows(d.L); p.fp16 = d.dtype == RVC_DT_FP16; p.slope = d.slope;
-    int halo1 = 0;
+    p.sum_jobs = d.sum_jobs ? 1 : 0; p.y_ncl = d.y_ncl ? 1 : 0; p.alpha = d.sum_jobs ? d.alpha : 1.f;
+    int halo1 = 0, k2max = 1;
     long total = 0;
     for (int j = 0; j < d.njobs; ++j) {
         const rvc_pair_job& jb = d.jobs[j];
-        if (!jb.a || !jb.w1 || !jb.w2 || !jb.res || !jb.y || !jb.y_act) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d has a null pointer", j);
-        if (jb.a == jb.y_act) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: y_act must not alias a (tiles read a with halos while others write y_act)", j);
+        const bool outs = !d.sum_jobs || j == 0;      // the stage average writes through job 0 only
+        if (!jb.a || !jb.w1 || !jb.w2 || !jb.res) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d has a null pointer", j);
+        if (!d.sum_jobs && (!jb.y || !jb.y_act)) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d needs y and y_act", j);
+        if (d.sum_jobs && j == 0 && !jb.y && !jb.y_act) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: sum_jobs needs y or y_act on job 0");
+        if (outs && jb.a == jb.y_act)
+            return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: y_act must not alias a (tiles read a with halos while others write y_act)", j);
         if (jb.K1 <= 0 || !(jb.K1 & 1) || jb.K2 <= 0 || !(jb.K2 & 1) || jb.dil1 <= 0)
             return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: job %d needs odd kernel sizes and dil1 > 0", j);
         if (jb.K2 - 1 > RT - TMR) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: K2=%d exceeds %d", jb.K2, RT - TMR + 1);
         if ((jb.K1 - 1) / 2 * jb.dil1 + (jb.K2 - 1) / 2 > PADL)
             return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: halo %d exceeds the %d zero rows of the packed layout", (jb.K1 - 1) / 2 * jb.dil1 + (jb.K2 - 1) / 2, PADL);
-        if ((((uintptr_t)jb.res | (uintptr_t)jb.y) & 31) || (((uintptr_t)jb.a | (uintptr_t)jb.w1 | (uintptr_t)jb.w2 | (uintptr_t)jb.y_act) & 15))
+        if ((((uintptr_t)jb.res | (uintptr_t)(outs ? jb.y : nullptr)) & 31) ||
+            (((uintptr_t)jb.a | (uintptr_t)jb.w1 | (uintptr_t)jb.w2 | (uintptr_t)(outs ? jb.y_act : nullptr)) & 15))
             return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: fp32 streams need 32-byte, packed buffers 16-byte alignment", j);
         halo1 = (jb.K1 - 1) * jb.dil1 > halo1 ? (jb.K1 - 1) * jb.dil1 : halo1;
-        p.tmo[j] = TMR - (jb.K2 - 1);
+        k2max = jb.K2 > k2max ? jb.K2 : k2max;
+        p.jobs[j] = jb;
+    }
+    for (int j = 0; j < d.njobs; ++j) {
+        p.tmo[j] = TMR - ((d.sum_jobs ? k2max : d.jobs[j].K2) - 1);     // with sum_jobs every job shares the tile grid of the widest conv2
         p.n_lt[j] = rvc::cdiv(d.L, p.tmo[j]);
         p.tiles_before[j] = (int)total;
-        total += (long)d.B * p.n_lt[j];
-        p.jobs[j] = jb;
+        if (!d.sum_jobs || j == 0) total += (long)d.B * p.n_lt[j];
     }
     if (total > 0x7fffffffL) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: too many tiles");
     for (int j = d.njobs; j <= MAXJOBS; ++j) p.tiles_before[j] = (int)total;
+    if (d.sum_jobs)
+        for (int j = 1; j <= MAXJOBS; ++j) p.tiles_before[j] = (int)total;   // decode() then always lands on job 0
     p.total_tiles = (int)total;
     p.ra = TMR + halo1;
     const int nch = d.C / 8;

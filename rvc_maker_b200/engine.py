@@ -234,6 +234,10 @@ class Engine:
                 tc_w[f"t_o_w{i}"] = (_f(a.conv_o.weight), dt)
                 f = e.encoder.ffn_layers[i]
                 tc_w[f"t_f1_w{i}"], tc_w[f"t_f2_w{i}"] = (_f(f.conv_1.weight), dt), (_f(f.conv_2.weight), dt)
+                if c["Fc"] % 48 == 0:   # three input-channel slices of conv_2 for the split-K launch of short sequences
+                    fs = c["Fc"] // 3
+                    for sp in range(3):
+                        tc_w[f"t_f2_w{i}_k{sp}"] = (_f(f.conv_2.weight)[:, sp * fs:(sp + 1) * fs].contiguous(), dt)
             tc_w["t_proj_w"] = (_f(e.proj.weight), dt)
             if c["D"] % 16 == 0:
                 tc_w["t_emb_w"] = (_f(e.emb_phone.weight).unsqueeze(-1).contiguous(), dt)   # Linear as a 1x1 conv [H, D, 1]
@@ -372,6 +376,8 @@ class Engine:
         if self.enc_tc:
             dt = DT_FP16
             xa, atta, ha = self._packed(p, B, H, T), self._packed(p, B, H, T), self._packed(p, B, Fc, T)
+            y2, y3 = self._buf(p, B, H, T), self._buf(p, B, H, T)      # split-K partial sums of the FFN's second conv
+            Lp = int(lib.rvc_packed_rows(T))
             if tc_embed:
                 # x = lrelu((phone.W^T + b + E[pitch]) * sqrt(H), 0.1) * mask  (synthesizers.py:367): exact gather + tensor-core Linear
                 pha = self._packed(p, B, D, T)
@@ -422,13 +428,24 @@ class Engine:
                     p.add(f"pack_att{i}", lib.rvc_pack_act, att.data_ptr(), None, None, 1.0, H * T, T, None, atta.data_ptr(), B, H, T, dt, 1.0,
                           kind="pack_act", bytes_=6.0 * B * H * T)
                 self._tc(p, f"attn_o{i}", [dict(a=atta, w=W[f"t_o_w{i}"], bias=W[f"o_b{i}"], y=vy)], B=B, Cin=H, Cout=H, L=T, dtype=dt, tag="enc")
-                p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
+                p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), None, None, W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
                       p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0, xa.data_ptr(), dt, kind="layernorm_f32", bytes_=14.0 * B * H * T)
                 self._tc(p, f"ffn1_{i}", [dict(a=xa, w=W[f"t_f1_w{i}"], bias=W[f"f1_b{i}"], relu=True, mask=p.mask, y_act=ha, K=ks)],
                          B=B, Cin=H, Cout=Fc, L=T, dtype=dt, tag="enc")
-                self._tc(p, f"ffn2_{i}", [dict(a=ha, w=W[f"t_f2_w{i}"], bias=W[f"f2_b{i}"], mask=p.mask, y=vy, K=ks)],
-                         B=B, Cin=Fc, Cout=H, L=T, dtype=dt, tag="enc")
-                p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln2_g{i}"].data_ptr(), W[f"ln2_b{i}"].data_ptr(),
+                # conv_2 (Fc -> H, Fc = 4H input channels): with few position tiles the launch is a handful of CTAs streaming long K
+                # loops (14.5 us at T = 1000).  Three input-channel slices as three jobs fill the GPU (7.2 us); LayerNorm adds the
+                # three partial sums.
+                split = f"t_f2_w{i}_k0" in W and B * (-(-T // 128)) * (H // 32) < 100
+                if split:
+                    fs = Fc // 3
+                    jobs = [dict(a=ha.data_ptr() + sp * (fs // 8) * Lp * 16, a_bs=(Fc // 8) * Lp * 16, w=W[f"t_f2_w{i}_k{sp}"],
+                                 bias=(W[f"f2_b{i}"] if sp == 0 else None), mask=p.mask, y=(vy, V(y2, H, T), V(y3, H, T))[sp], K=ks) for sp in range(3)]
+                    self._tc(p, f"ffn2_{i}", jobs, B=B, Cin=fs, Cout=H, L=T, dtype=dt, tag="enc")
+                else:
+                    self._tc(p, f"ffn2_{i}", [dict(a=ha, w=W[f"t_f2_w{i}"], bias=W[f"f2_b{i}"], mask=p.mask, y=vy, K=ks)],
+                             B=B, Cin=Fc, Cout=H, L=T, dtype=dt, tag="enc")
+                p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), y2.data_ptr() if split else None, y3.data_ptr() if split else None,
+                      W[f"ln2_g{i}"].data_ptr(), W[f"ln2_b{i}"].data_ptr(),
                       p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 1 if i == c["nl"] - 1 else 0, xa.data_ptr(), dt, kind="layernorm_f32",
                       bytes_=14.0 * B * H * T)
             self._tc(p, "proj", [dict(a=xa, w=W["t_proj_w"], bias=W["proj_b"], mask=p.mask, y=vst)], B=B, Cin=H, Cout=2 * I, L=T, dtype=dt, tag="enc")
@@ -439,13 +456,13 @@ class Engine:
             p.add(f"attn{i}", lib.rvc_rel_attention_f32, qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(), W[f"ev{i}"].data_ptr(),
                   att.data_ptr(), B, H, c["nh"], T, WINDOW, flops=4.0 * B * H * T * T, bytes_=16.0 * B * H * T, kind="rel_attention_f32")
             self._conv(p, f"attn_o{i}", vatt, W[f"o_w{i}"], vy, B=B, Cin=H, Cout=H, L=T, bias=W[f"o_b{i}"])
-            p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
+            p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), None, None, W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
                   p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0, None, 0)
             self._conv(p, f"ffn1_{i}", vx, W[f"f1_w{i}"], vh, B=B, Cin=H, Cout=Fc, L=T, K=ks, pad=padl, bias=W[f"f1_b{i}"], mask=p.mask,
                        in_mask=True, act=ACT_RELU)
             self._conv(p, f"ffn2_{i}", vh, W[f"f2_w{i}"], vy, B=B, Cin=Fc, Cout=H, L=T, K=ks, pad=padl, bias=W[f"f2_b{i}"], mask=p.mask,
                        in_mask=True, out_mask=True)
-            p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), W[f"ln2_g{i}"].data_ptr(), W[f"ln2_b{i}"].data_ptr(),
+            p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), None, None, W[f"ln2_g{i}"].data_ptr(), W[f"ln2_b{i}"].data_ptr(),
                   p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 1 if i == c["nl"] - 1 else 0, None, 0)
         self._conv(p, "proj", vx, W["proj_w"], vst, B=B, Cin=H, Cout=2 * I, L=T, bias=W["proj_b"], mask=p.mask, out_mask=True)
         p.add("sample_zp", lib.rvc_sample_zp_f32, p.stats.data_ptr(), p.eps_z.data_ptr(), p.mask.data_ptr(), p.zp.data_ptr(), B, I, T)
@@ -641,23 +658,33 @@ class Engine:
                 t_of = {}
                 for mm in range(nsteps):
                     last = mm == nsteps - 1
-                    if use_pair and not last:
+                    if use_pair:
+                        # the last step runs in sum mode: the three conv2 accumulate into one tile and the stage average is written
+                        # once — plain fp32 for conv_post / an fp32 ups and (or) packed for the next tensor-core ups
                         pd = ResblockPairDesc()
                         pd.njobs, pd.B, pd.C, pd.L, pd.dtype, pd.slope = nk, B, Ci, Li, dt, LRELU_SLOPE
+                        pd.sum_jobs, pd.y_ncl, pd.alpha = int(last), int(last), 1.0 / nk
                         fl = 0.0
                         for slot, j in enumerate(order):
                             pj = pd.jobs[slot]
                             kk = rks[j]
-                            dst_a = pa[j] if src_a[j] is not pa[j] else ta[j]     # ping-pong: tiles read `a` with halos while others write y_act
                             pj.a = src_a[j].data_ptr()
                             pj.w1, pj.b1 = W[f"rb{i}_{j}_c1w{mm}"].data_ptr(), W[f"rb{i}_{j}_c1b{mm}"].data_ptr()
                             pj.w2, pj.b2 = W[f"rb{i}_{j}_c2w{mm}"].data_ptr(), W[f"rb{i}_{j}_c2b{mm}"].data_ptr()
-                            pj.res, pj.y, pj.y_act = (S[0] if mm == 0 else P[j]).data_ptr(), P[j].data_ptr(), dst_a.data_ptr()
+                            pj.res = (S[0] if mm == 0 else P[j]).data_ptr()
                             pj.K1, pj.dil1, pj.K2 = kk, rds[j][mm], kk
-                            src_a[j] = dst_a
+                            if not last:
+                                dst_a = pa[j] if src_a[j] is not pa[j] else ta[j]     # ping-pong: tiles read `a` with halos while others write y_act
+                                pj.y, pj.y_act = P[j].data_ptr(), dst_a.data_ptr()
+                                src_a[j] = dst_a
+                            elif slot == 0:
+                                pj.y = avg.data_ptr() if need_f32 else None
+                                pj.y_act = next_ua.data_ptr() if next_ua is not None else None
                             fl += 4.0 * B * Ci * Ci * kk * Li
                         p.keep.append(pd)
-                        p.add(f"rbpair{i}_s{mm}", lib.rvc_resblock_pair_tc, C.byref(pd), flops=fl, bytes_=nk * B * Ci * Li * (esz + 8.0 + esz),
+                        by = nk * B * Ci * Li * (esz + 8.0 + esz) if not last else \
+                            B * Ci * Li * (nk * (esz + 4.0) + (4.0 if need_f32 else 0.0) + (esz if next_ua is not None else 0.0))
+                        p.add(f"rbpair{i}_s{mm}", lib.rvc_resblock_pair_tc, C.byref(pd), flops=fl, bytes_=by,
                               kind=f"resblock_pair_tc_{'bf16' if dt == DT_BF16 else 'fp16'}[C{Ci}]")
                         continue
                     for half in (1, 2):

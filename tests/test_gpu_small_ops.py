@@ -32,7 +32,7 @@ def test_layernorm_matches_torch(C_, T, with_res):
     for out_mask in (0, 1):
         y = torch.empty_like(x)
         ya = torch.zeros(B * C_ * rows * 2, dtype=torch.uint8, device=DEV)
-        _lib.check(lib.rvc_layernorm_f32(x.data_ptr(), r.data_ptr() if with_res else None, gamma.data_ptr(), beta.data_ptr(), mask.data_ptr(),
+        _lib.check(lib.rvc_layernorm_f32(x.data_ptr(), r.data_ptr() if with_res else None, None, None, gamma.data_ptr(), beta.data_ptr(), mask.data_ptr(),
                                          y.data_ptr(), B, C_, T, 1e-5, out_mask, ya.data_ptr(), 2, st), "layernorm")
         torch.cuda.synchronize()
         xin = (x + r) if with_res else x
@@ -41,9 +41,19 @@ def test_layernorm_matches_torch(C_, T, with_res):
         assert float((y.double() - want).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
         packed = unpack16(ya, B, C_, T, rows)
         assert float((packed.double() - ref * mask.double().unsqueeze(1)).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+    if with_res:   # split-K partial sums r + r2 + r3
+        r2, r3 = torch.randn(B, C_, T, generator=g).to(DEV), torch.randn(B, C_, T, generator=g).to(DEV)
+        y3 = torch.empty_like(x)
+        _lib.check(lib.rvc_layernorm_f32(x.data_ptr(), r.data_ptr(), r2.data_ptr(), r3.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mask.data_ptr(),
+                                         y3.data_ptr(), B, C_, T, 1e-5, 0, None, 0, st), "layernorm r2 r3")
+        torch.cuda.synchronize()
+        ref3 = F.layer_norm((x + r + r2 + r3).double().transpose(1, 2), (C_,), gamma.double(), beta.double(), 1e-5).transpose(1, 2)
+        assert float((y3.double() - ref3).abs().max()) <= 2e-5 * max(1.0, float(ref3.abs().max()))
+        assert lib.rvc_layernorm_f32(x.data_ptr(), r.data_ptr(), r2.data_ptr(), None, gamma.data_ptr(), beta.data_ptr(), mask.data_ptr(),
+                                     y3.data_ptr(), B, C_, T, 1e-5, 0, None, 0, st) != 0
     # in place (how the encoder calls it)
     x2 = x.clone()
-    _lib.check(lib.rvc_layernorm_f32(x2.data_ptr(), r.data_ptr() if with_res else None, gamma.data_ptr(), beta.data_ptr(), mask.data_ptr(),
+    _lib.check(lib.rvc_layernorm_f32(x2.data_ptr(), r.data_ptr() if with_res else None, None, None, gamma.data_ptr(), beta.data_ptr(), mask.data_ptr(),
                                      x2.data_ptr(), B, C_, T, 1e-5, 1, None, 0, st), "layernorm in place")
     torch.cuda.synchronize()
     assert torch.equal(x2, y)

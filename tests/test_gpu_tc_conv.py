@@ -459,3 +459,62 @@ def test_fused_resblock_pair_rejects_wide_stages():
     pd.njobs, pd.B, pd.C, pd.L, pd.dtype, pd.slope = 1, 1, 128, 1000, FP16, 0.1
     assert lib.rvc_resblock_pair_tc(C.byref(pd), None) == -2
     assert b"C = 32 and 64" in lib.rvc_last_error()
+
+
+@pytest.mark.parametrize("Cc,L,B,y_ncl", [(64, 3001, 2, 1), (32, 20000, 1, 0), (64, 246, 1, 0), (32, 5, 2, 1), (64, 30011, 1, 1)])
+def test_fused_resblock_pair_stage_average(Cc, L, B, y_ncl):
+    """sum_jobs mode of rvc_resblock_pair_tc (last ResBlock step + stage average in one kernel) against conv1 x3 followed by the
+    sum_jobs conv2 launch of rvc_conv1d_tc: bit-identical average (plain or channel-blocked) and packed copy."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    dtype = FP16
+    g = torch.Generator(device="cpu").manual_seed(57 + Cc + L)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(L)
+    pd = _lib.ResblockPairDesc()
+    pd.njobs, pd.B, pd.C, pd.L, pd.dtype, pd.slope, pd.sum_jobs, pd.y_ncl, pd.alpha = 3, B, Cc, L, dtype, 0.1, 1, y_ncl, 1.0 / 3.0
+    d1, d2 = _lib.Conv1dTcDesc(), _lib.Conv1dTcDesc()
+    for d in (d1, d2):
+        d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype = 3, B, Cc, Cc, L, dtype
+    d2.sum_jobs, d2.f32_blocked = 1, (1 if y_ncl else 3)
+    shape = (B, Cc, L) if y_ncl else (B, Cc // 8, L, 8)
+    y_ref, y_fused = torch.zeros(shape, device=DEV), torch.zeros(shape, device=DEV)
+    ya_ref = torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+    ya_fused = torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+    keep = []
+    for j, (k, dil) in enumerate(((11, 5), (7, 5), (3, 5))):
+        x = torch.randn(B, Cc, L, generator=g).to(DEV)
+        xin = torch.randn(B, Cc, L, generator=g).to(DEV)
+        w1 = (torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+        w2 = (torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+        b1, b2 = torch.randn(Cc, generator=g).to(DEV), torch.randn(Cc, generator=g).to(DEV)
+        xb = to_blocked(x)
+        a = torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+        w1p = torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+        w2p = torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+        _lib.check(lib.rvc_pack_act(xin.data_ptr(), None, None, 1.0, Cc * L, L, None, a.data_ptr(), B, Cc, L, dtype, 0.1, st), "pack_act")
+        _lib.check(lib.rvc_pack_weight(w1.data_ptr(), w1p.data_ptr(), Cc, Cc, k, dtype, st), "pack_weight")
+        _lib.check(lib.rvc_pack_weight(w2.data_ptr(), w2p.data_ptr(), Cc, Cc, k, dtype, st), "pack_weight")
+        ta = torch.zeros(B * Cc * rows * 2, dtype=torch.uint8, device=DEV)
+        jb = d1.jobs[j]
+        jb.a, jb.w, jb.bias, jb.y_act = a.data_ptr(), w1p.data_ptr(), b1.data_ptr(), ta.data_ptr()
+        jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = k, dil, (k - 1) // 2 * dil, 1.0, 0.1
+        jb = d2.jobs[j]
+        jb.a, jb.w, jb.bias = ta.data_ptr(), w2p.data_ptr(), b2.data_ptr()
+        jb.res, jb.res_bs, jb.res_cs = xb.data_ptr(), Cc * L, 8 * L
+        jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = k, 1, (k - 1) // 2, 1.0 / 3.0, 0.1
+        pj = pd.jobs[j]
+        pj.a, pj.w1, pj.b1, pj.w2, pj.b2, pj.res = a.data_ptr(), w1p.data_ptr(), b1.data_ptr(), w2p.data_ptr(), b2.data_ptr(), xb.data_ptr()
+        pj.K1, pj.dil1, pj.K2 = k, dil, k
+        if j == 0:
+            jb.y_f32, jb.y_bs, jb.y_cs, jb.y_act = y_ref.data_ptr(), Cc * L, (L if y_ncl else 8 * L), ya_ref.data_ptr()
+            pj.y, pj.y_act = y_fused.data_ptr(), ya_fused.data_ptr()
+        keep += [x, xin, w1, w2, b1, b2, xb, a, w1p, w2p, ta]
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d1), st), "conv1")
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d2), st), "conv2 sum")
+    _lib.check(lib.rvc_resblock_pair_tc(C.byref(pd), st), "pair sum")
+    torch.cuda.synchronize()
+    assert float(y_ref.abs().max()) > 0.1
+    assert torch.equal(y_fused, y_ref)
+    assert torch.equal(ya_fused, ya_ref)
