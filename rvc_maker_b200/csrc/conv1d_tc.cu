@@ -657,6 +657,14 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
             if ((d.jobs[j].res == nullptr) != (d.jobs[0].res == nullptr)) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs needs res on all jobs or none");
     }
     auto ntiles = [&](int nt_, int mt_) { return (long)njt * d.B * rvc::cdiv(Lq, BM * mt_) * (d.Cout / nt_) * up; };
+    // wide layers on short sequences (the C = 256 generator stage: L = 10-12 k) are bound by streaming the weights of each tile
+    // from L2, not by the tensor pipe: 512-row x 64-column tiles re-use a weight stage four times and win even below one wave
+    // (measured, 3 jobs k = 11/7/3, L = 12000: conv 50 -> 45 us, stage-average launch 101 -> 54 us)
+    if (NT == 0 && mt == 0 && up == 1 && !gated && d.Cin >= 256 && d.Cout >= 256 && d.Cout % 64 == 0 && 2 * ntiles(64, 4) >= sms &&
+        ntiles(128, 2) < 4L * sms) {
+        NT = 64;
+        mt = 4;
+    }
     if (NT == 0) {
         const int cands[4] = {128, 64, 32, 16};
         for (int i = 0; i < 4; ++i) {
