@@ -215,26 +215,41 @@ __global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __rest
                                                              const float* __restrict__ bias, float* __restrict__ y, int64_t y_bs, int C,
                                                              int Lout, int kn, int sn, int pn, int blocked) {
     rvc::pdl_prologue();
-    extern __shared__ float w_s[];  // [32][kn]
+    // w_s [kn][32]: one tap's 32 channel weights are 8 broadcast LDS.128; h_s: the CTA's window of the harmonic source
+    // (128 positions * sn + kn samples, loaded coalesced once instead of kn stride-sn global loads per thread)
+    extern __shared__ __align__(16) float w_s[];
+    float* h_s = w_s + 32 * kn;
     const int co0 = blockIdx.y * 32, b = blockIdx.z;
+    const int64_t hlen = (int64_t)Lout * sn;
+    const float* hb = har + (int64_t)b * har_bs;
+    const int64_t g0 = (int64_t)blockIdx.x * 128 * sn - pn;       // source index of h_s[0]
+    const int span = 127 * sn + kn;
     for (int i = threadIdx.x; i < 32 * kn; i += 128) {
-        const int c = i / kn;
-        w_s[i] = (co0 + c < C) ? w[(int64_t)(co0 + c) * kn + (i - c * kn)] : 0.f;
+        const int c = i / kn, j = i - c * kn;
+        w_s[j * 32 + c] = (co0 + c < C) ? w[(int64_t)(co0 + c) * kn + j] : 0.f;
+    }
+    for (int i = threadIdx.x; i < span; i += 128) {
+        const int64_t idx = g0 + i;
+        h_s[i] = (idx >= 0 && idx < hlen) ? hb[idx] : 0.f;
     }
     __syncthreads();
     const int l = blockIdx.x * 128 + threadIdx.x;
     if (l >= Lout) return;
-    const int64_t hlen = (int64_t)Lout * sn;
-    const float* hb = har + (int64_t)b * har_bs;
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = (co0 + c < C && bias) ? bias[co0 + c] : 0.f;
-    const int64_t h0 = (int64_t)l * sn - pn;
+    const float* hp = h_s + threadIdx.x * sn;
     for (int j = 0; j < kn; ++j) {
-        const int64_t idx = h0 + j;
-        const float hv = (idx >= 0 && idx < hlen) ? hb[idx] : 0.f;
+        const float hv = hp[j];
+        const float4* wj = reinterpret_cast<const float4*>(w_s + j * 32);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = fmaf(w_s[c * kn + j], hv, acc[c]);
+        for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 wv = wj[c4];
+            acc[4 * c4 + 0] = fmaf(wv.x, hv, acc[4 * c4 + 0]);
+            acc[4 * c4 + 1] = fmaf(wv.y, hv, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(wv.z, hv, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(wv.w, hv, acc[4 * c4 + 3]);
+        }
     }
     if (blocked) {   // [b][c/8][l][8]: one 32-byte sector per 8 channels
 #pragma unroll
@@ -259,6 +274,8 @@ RVC_API int rvc_noise_conv_f32(const float* har, int64_t har_bs, const float* w,
     if (B <= 0 || B > 65535 || C <= 0 || Lout < 0 || kn <= 0 || kn > 1024 || sn <= 0 || pn < 0) return rvc::fail(RVC_ESHAPE, "rvc_noise_conv_f32: bad shape");
     if (Lout == 0) return 0;
     dim3 grid(rvc::cdiv(Lout, 128), rvc::cdiv(C, 32), B);
-    rvc::launch_pdl(noise_conv_f32_kernel, dim3(grid), dim3(128), (size_t)(32 * kn * sizeof(float)), (cudaStream_t)stream, har, har_bs, w, bias, y, y_bs, C, Lout, kn, sn, pn, (int)blocked);
+    const size_t smem = (size_t)(32 * kn + 127 * sn + kn) * sizeof(float);
+    if (smem > 48 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_noise_conv_f32: kn = %d, sn = %d need %zu bytes of shared memory (> 48 KB)", kn, sn, smem);
+    rvc::launch_pdl(noise_conv_f32_kernel, dim3(grid), dim3(128), smem, (cudaStream_t)stream, har, har_bs, w, bias, y, y_bs, C, Lout, kn, sn, pn, (int)blocked);
     return rvc::check_launch("rvc_noise_conv_f32");
 }
