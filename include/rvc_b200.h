@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 19
+#define RVC_ABI_VERSION 20
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -193,6 +193,13 @@ typedef struct {
      * weights); w_cs = rows between consecutive 16-byte weight chunks (default Cout). */
     int64_t a_bs, w_bs, y_act_bs;
     int32_t w_cs, reserved;
+    /* optional, in place of `res`: the NSF noise conv of a generator stage (synthesizers.py:134-136, :156) computed in the
+     * epilogue — v += nz_b[c] + sum_{j < nz_kn} nz_w[c*nz_kn + j] * nz_har[b*nz_har_bs + l*nz_sn - nz_pn + j] at output
+     * position l (source samples outside [0, Lout*nz_sn) read as 0), nz_kn <= 4.  Same arithmetic as rvc_noise_conv_f32
+     * followed by res: bit-identical, without the extra launch and the fp32 round trip. */
+    const float* nz_har; const float* nz_w; const float* nz_b;
+    int64_t nz_har_bs;
+    int32_t nz_kn, nz_sn, nz_pn, reserved2;
 } rvc_tc_job;
 /*
  * up > 1 selects the ConvTranspose1d phase mode (GeneratorNSF.ups, synthesizers.py:133,156): the packed weights hold `up`

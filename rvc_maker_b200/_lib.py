@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 DT_BF16, DT_FP16 = 0, 2
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -60,6 +60,7 @@ class TcJob(C.Structure):
         ("alpha", _f32), ("act_slope", _f32),
         ("a_bs", _i64), ("w_bs", _i64), ("y_act_bs", _i64),
         ("w_cs", _i32), ("reserved", _i32),
+        ("nz_har", _vp), ("nz_w", _vp), ("nz_b", _vp), ("nz_har_bs", _i64), ("nz_kn", _i32), ("nz_sn", _i32), ("nz_pn", _i32), ("reserved2", _i32),
     ]
 
 

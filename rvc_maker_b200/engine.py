@@ -331,6 +331,9 @@ class Engine:
             jb.gated, jb.relu = int(j.get("gated", False)), int(j.get("relu", 0))
             jb.alpha, jb.act_slope = j.get("alpha", 1.0), j.get("act_slope", 1.0)
             jb.a_bs, jb.w_bs, jb.y_act_bs, jb.w_cs = j.get("a_bs", 0), j.get("w_bs", 0), j.get("y_act_bs", 0), j.get("w_cs", 0)
+            if j.get("nz_har"):
+                jb.nz_har, jb.nz_w, jb.nz_b, jb.nz_har_bs = j["nz_har"], j["nz_w"], j["nz_b"], j["nz_har_bs"]
+                jb.nz_kn, jb.nz_sn, jb.nz_pn = j["nz_kn"], j["nz_sn"], j["nz_pn"]
             ce = Cout // 2 if jb.gated else Cout
             fl += 2.0 * B * Cin * Cout * jb.K * L
             by += B * L * (2.0 * Cin + up * ce * (4.0 * (j.get("res") is not None) + 4.0 * (j.get("y") is not None) + 2.0 * (j.get("y_act") is not None)))
@@ -584,15 +587,20 @@ class Engine:
                     x3 = cur[2].data_ptr() if cur[2] is not None else None
                     p.add(f"pack_up{i}", lib.rvc_pack_act, cur[0].data_ptr(), x2, x3, float(nk), curC * curL, curL, None, ua.data_ptr(), B, curC,
                           curL, udt, LRELU_SLOPE, bytes_=B * curC * curL * (2.0 + (12.0 if x2 else 4.0)), kind="pack_act")
-                if c["f0"]:
+                # short noise convs (kernel <= 4: the last two stages) are computed inside the ups epilogue instead of a launch of
+                # their own followed by an fp32 round trip (rvc_tc_job.nz_*); the long ones keep their kernel
+                nz_fused = bool(c["f0"]) and blk and kn <= 4
+                if c["f0"] and not nz_fused:
                     p.add(f"noise{i}", lib.rvc_noise_conv_f32, har.data_ptr(), Lfin, W[f"nz_w{i}"].data_ptr(), W[f"nz_b{i}"].data_ptr(),
                           S[0].data_ptr(), Ci * Li, B, Ci, Li, kn, sn, pn, int(blk), flops=2.0 * B * Ci * Li * kn, bytes_=4.0 * B * (Ci * Li + Li * sn),
                           kind="noise_conv_f32")
                 if dt is not None and dt == udt:
                     xa = self._packed(p, B, Ci, Li)
                 M = -(-k // u)
-                self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(vs0 if c["f0"] else None), y=vs0, y_act=xa,
-                                             act_slope=LRELU_SLOPE, K=M, pad=M - 1)],
+                nz = dict(nz_har=har.data_ptr(), nz_w=W[f"nz_w{i}"].data_ptr(), nz_b=W[f"nz_b{i}"].data_ptr(), nz_har_bs=Lfin, nz_kn=kn, nz_sn=sn,
+                          nz_pn=pn) if nz_fused else {}
+                self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(vs0 if c["f0"] and not nz_fused else None), y=vs0, y_act=xa,
+                                             act_slope=LRELU_SLOPE, K=M, pad=M - 1, **nz)],
                          B=B, Cin=curC, Cout=Ci, L=curL, dtype=udt, up=u, pshift=(k - u) // 2, tag=f"ups",
                          flops=2.0 * B * curC * Ci * k * curL, blocked=3 if blk else 0)
             else:

@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.rvc_abi_version() == 19
+    assert lib.rvc_abi_version() == 20
     # argument validation happens before any CUDA call, so it is checkable without a GPU
     rc = lib.rvc_conv1d_f32(None, None)
     assert rc == -1
@@ -49,7 +49,7 @@ def test_desc_struct_layout_matches_header():
     assert ctypes.sizeof(ConvTr1dDesc) == 160
     from rvc_maker_b200._lib import Conv1dTcDesc, TcJob
 
-    assert ctypes.sizeof(TcJob) == 168 and ctypes.sizeof(Conv1dTcDesc) == 552
+    assert ctypes.sizeof(TcJob) == 216 and ctypes.sizeof(Conv1dTcDesc) == 696
     assert lib_rows(1000) == 64 + 1024 + 64
 
 

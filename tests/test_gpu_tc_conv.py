@@ -518,3 +518,58 @@ def test_fused_resblock_pair_stage_average(Cc, L, B, y_ncl):
     assert float(y_ref.abs().max()) > 0.1
     assert torch.equal(y_fused, y_ref)
     assert torch.equal(ya_fused, ya_ref)
+
+
+@pytest.mark.parametrize("Cin,Cout,k,u,Lin,sn", [(128, 64, 4, 2, 5001, 2), (64, 32, 4, 2, 7777, 1), (32, 16, 4, 2, 3000, 1)])
+def test_fused_noise_conv_in_ups_epilogue(Cin, Cout, k, u, Lin, sn):
+    """rvc_tc_job.nz_*: the short NSF noise conv computed in the ConvTranspose epilogue equals rvc_noise_conv_f32 + res, bit for bit."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    B, dtype = 2, FP16
+    g = torch.Generator(device="cpu").manual_seed(77 + Cin)
+    st = torch.cuda.current_stream().cuda_stream
+    Lout = Lin * u
+    kn = 1 if sn == 1 else 2 * sn
+    pn = 0 if sn == 1 else (kn - sn) // 2
+    x = torch.randn(B, Cin, Lin, generator=g).to(DEV)
+    w = (torch.randn(Cin, Cout, k, generator=g) / (Cin * k / u) ** 0.5).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    har = torch.randn(B, Lout * sn, generator=g).to(DEV)
+    nzw, nzb = torch.randn(Cout, 1, kn, generator=g).to(DEV), torch.randn(Cout, generator=g).to(DEV)
+    M = -(-k // u)
+    wk = torch.zeros(Cout, Cin, u * M, device=DEV)
+    for r in range(u):
+        for t in range(M):
+            kk = r + (M - 1 - t) * u
+            if kk < k:
+                wk[:, :, r * M + t] = w[:, :, kk].t()
+    rows_in, rows_out = lib.rvc_packed_rows(Lin), lib.rvc_packed_rows(Lout)
+    a = torch.zeros(B * Cin * rows_in * 2, dtype=torch.uint8, device=DEV)
+    wp = torch.zeros(u * M * Cin * Cout * 2, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.rvc_pack_act(x.data_ptr(), None, None, 1.0, Cin * Lin, Lin, None, a.data_ptr(), B, Cin, Lin, dtype, 0.1, st), "pack_act")
+    _lib.check(lib.rvc_pack_weight(wk.data_ptr(), wp.data_ptr(), Cout, Cin, u * M, dtype, st), "pack_weight")
+    outs = []
+    for fused in (False, True):
+        yb = torch.zeros(B, Cout // 8, Lout, 8, device=DEV)
+        y_act = torch.zeros(B * Cout * rows_out * 2, dtype=torch.uint8, device=DEV)
+        d = _lib.Conv1dTcDesc()
+        d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.up, d.pshift, d.f32_blocked = 1, B, Cin, Cout, Lin, dtype, u, (k - u) // 2, 3
+        jb = d.jobs[0]
+        jb.a, jb.w, jb.bias = a.data_ptr(), wp.data_ptr(), bias.data_ptr()
+        jb.y_f32, jb.y_bs, jb.y_cs, jb.y_act = yb.data_ptr(), Cout * Lout, 8 * Lout, y_act.data_ptr()
+        jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = M, 1, M - 1, 1.0, 0.1
+        if fused:
+            jb.nz_har, jb.nz_w, jb.nz_b, jb.nz_har_bs, jb.nz_kn, jb.nz_sn, jb.nz_pn = har.data_ptr(), nzw.data_ptr(), nzb.data_ptr(), Lout * sn, kn, sn, pn
+        else:
+            _lib.check(lib.rvc_noise_conv_f32(har.data_ptr(), Lout * sn, nzw.data_ptr(), nzb.data_ptr(), yb.data_ptr(), Cout * Lout, B, Cout, Lout, kn, sn, pn,
+                                              1, st), "noise")
+            jb.res, jb.res_bs, jb.res_cs = yb.data_ptr(), Cout * Lout, 8 * Lout
+        _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "conv1d_tc(up)")
+        torch.cuda.synchronize()
+        outs.append((yb, y_act))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    ref = F.conv_transpose1d(rnd(F.leaky_relu(x, 0.1), dtype).double(), rnd(w, dtype).double(), bias.double(), stride=u, padding=(k - u) // 2) \
+        + F.conv1d(har.unsqueeze(1).double(), nzw.double(), nzb.double(), stride=sn, padding=pn)
+    assert float((from_blocked(outs[1][0]).double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
