@@ -340,7 +340,7 @@ def main():
         rows = net._engine.profile(B, T)
         fam = {}
         for r in rows:
-            k = r["kind"] if r["kind"].startswith("conv1d_tc") else r["kind"].split("[")[0]
+            k = r["kind"] if r["kind"].startswith(("conv1d_tc", "resblock_pair_tc")) else r["kind"].split("[")[0]   # per-stage tags for the tcgen05 kernels
             f = fam.setdefault(k, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
             f["ms"] += r["ms"]; f["flops"] += r["flops"]; f["bytes"] += r["bytes"]; f["launches"] += r["launches"]
         top = max(fam, key=lambda k: fam[k]["ms"])
@@ -352,7 +352,7 @@ def main():
         f = fam[top]
         total_ms = sum(v["ms"] for v in fam.values())
         bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        if top.startswith(("conv1d", "convtr1d", "rel_attention", "embed")):
+        if top.startswith(("conv1d", "convtr1d", "rel_attention", "embed")) or (top.startswith("resblock_pair") and f["flops"] / max(f["bytes"], 1.0) > 210.0):
             # contraction kernels: tensor roofline (tf32 runs at half the bf16 rate; CUDA-core fp32 kernels are still reported
             # against the tensor peak because that is the bound the north star sets for them)
             peak = bf16_peak
