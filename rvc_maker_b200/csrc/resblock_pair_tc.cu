@@ -15,6 +15,9 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
+#ifndef RVC_PAIR_NSTAGE
+#define RVC_PAIR_NSTAGE 4
+#endif
 
 namespace {
 
@@ -24,7 +27,7 @@ constexpr int PADL = 64;          // zero rows in front of position 0 in packed 
 constexpr int ROWQ = 256;
 constexpr int PADR = 64;
 constexpr int RT = 272;           // rows of the t tile: 256 + (K2max - 1), rounded up
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = RVC_PAIR_NSTAGE;
 constexpr int STAGE_BYTES = 16384;
 constexpr int NTHREADS = 512;
 constexpr int NEG = 3;

@@ -12,10 +12,11 @@ dev = "cuda:0"
 st = torch.cuda.current_stream().cuda_stream
 
 
-def probe(Cc, L, reps=6):
+def probe(Cc, L, reps=6, sum_jobs=0):
     rows = lib.rvc_packed_rows(L)
     d = _lib.ResblockPairDesc()
     d.njobs, d.B, d.C, d.L, d.dtype, d.slope = 3, 1, Cc, L, 2, 0.1
+    d.sum_jobs, d.y_ncl, d.alpha = sum_jobs, 0, 1.0 / 3.0
     keep = []
     for j, (k, dil) in enumerate(((11, 5), (7, 3), (3, 1))):
         a = torch.zeros(Cc * rows * 2, dtype=torch.uint8, device=dev)
@@ -26,7 +27,7 @@ def probe(Cc, L, reps=6):
         x = torch.zeros(Cc, L, device=dev)
         pj = d.jobs[j]
         pj.a, pj.w1, pj.b1, pj.w2, pj.b2 = a.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
-        pj.res, pj.y, pj.y_act = x.data_ptr(), x.data_ptr(), ya.data_ptr()
+        pj.res, pj.y, pj.y_act = x.data_ptr(), (None if sum_jobs else x.data_ptr()), (ya.data_ptr() if (not sum_jobs or j == 0) else None)
         pj.K1, pj.dil1, pj.K2 = k, dil, k
         keep += [a, w1, w2, ya, b1, b2, x]
     best = 1e9
@@ -41,5 +42,8 @@ def probe(Cc, L, reps=6):
 
 
 if __name__ == "__main__":
-    for Cc, L in ((64, 240000), (32, 480000), (64, 200000), (32, 400000)):
-        print(f"C={Cc} L={L}: fused pair {probe(Cc, L):7.1f} us")
+    for Cc, L in ((64, 240000), (32, 480000)):
+        try:
+            print(f"C={Cc} L={L}: fused pair {probe(Cc, L):7.1f} us   stage-average mode {probe(Cc, L, sum_jobs=1):7.1f} us")
+        except Exception as e:
+            print(f"C={Cc} L={L}: {e}")
