@@ -81,6 +81,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
     }
     return r;
 }
+// tanh(t) * sigmoid(s) = (e^{2t} - 1) / ((e^{2t} + 1) (1 + e^{-s})) with the fast exponential and one fast division: ~14 instructions
+// instead of ~60 for tanhf * 1/(1+expf) — the gated epilogue of a WaveNet in_layer runs on 4 warps per tile and was a third of
+// that launch.  Absolute error <= ~2e-7 (the result is rounded to fp16 right after); arguments clamped where the functions
+// are saturated to 1e-13 anyway so that no intermediate overflows.
+__device__ __forceinline__ float gate_fast(float t, float s) {
+    const float e2 = __expf(2.f * fminf(fmaxf(t, -15.f), 15.f));
+    const float es = __expf(-fmaxf(s, -30.f));
+    return __fdividef(e2 - 1.f, (e2 + 1.f) * (1.f + es));
+}
 // leaky_relu for 0 <= slope <= 1 as max(v, slope*v): two instructions, no select
 __device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
 
@@ -434,7 +443,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                         float t = __uint_as_float(r[i]) + bias_s[j * p.Cout + col0 + i];
                         float sg = __uint_as_float(r2[i]) + bs1[i];
                         if (bb) { t += __ldg(bb + col0 + i); sg += __ldg(bb + col1 + i); }
-                        r[i] = __float_as_uint(tanhf(t) * rvc::sigmoidf_acc(sg));
+                        r[i] = __float_as_uint(gate_fast(t, sg));
                     }
                 } else {
 #pragma unroll
