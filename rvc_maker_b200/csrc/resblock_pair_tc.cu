@@ -22,11 +22,10 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int TMR = 256;          // rows per tile (two sub-tiles)
 constexpr int PADL = 64;          // zero rows in front of position 0 in packed buffers
 constexpr int ROWQ = 256;
 constexpr int PADR = 64;
-constexpr int RT = 272;           // rows of the t tile: 256 + (K2max - 1), rounded up
+constexpr int RTX = 16;           // extra rows of the t tile: >= K2max - 1
 constexpr int NSTAGE = RVC_PAIR_NSTAGE;
 constexpr int STAGE_BYTES = 16384;
 constexpr int NTHREADS = 512;
@@ -45,6 +44,7 @@ struct PParams {
     int total_tiles;
     int sum_jobs;                    // every tile runs ALL jobs; conv2 of all jobs accumulates into one tile (stage average)
     int y_ncl;                       // sum mode: y is plain [B, C, L] instead of channel-blocked
+    int dbg;                         // timing experiments only: 1 = no MMA issue, 2 = no epilogue-2 global I/O, 4 = no residual loads
     float slope, alpha;
 };
 
@@ -56,14 +56,19 @@ __device__ __forceinline__ uint32_t pack2h(float a, float b, int fp16) {
 }
 __device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
 
-template <int C>
+// MT = 128-row sub-tiles per tile: 2, or 4 for C = 32 where TMEM holds twice the rows and the per-tile handshakes (about 2.3 us
+// of barrier round trips per tile with no MMA and no stores at all) were the bound rather than HBM
+template <int C, int MT>
 __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParams p) {
+    constexpr int TMR = BM * MT;                        // rows per tile
+    constexpr int RT = TMR + RTX;                       // rows of the t tile
+    constexpr int MPI = MT / 2;                         // sub-tiles per issuer warp
     constexpr int NCH = C / 8;                          // 16-byte channel chunks
     constexpr int SCH = STAGE_BYTES / (C * 16);         // chunk-rows per weight stage (even)
     constexpr int EB = 32;                              // accumulator columns per epilogue work item
     constexpr int NBLK = C / EB;
-    constexpr int NITEM = 2 * NBLK;                     // work items per phase and tile
-    constexpr int TMEM_COLS = 8 * C;                    // 2 phases x 2 buffers x 2 sub-tiles x C columns
+    constexpr int NITEM = MT * NBLK;                    // work items per phase and tile
+    constexpr int TMEM_COLS = 4 * MT * C;               // 2 phases x 2 buffers x MT sub-tiles x C columns
     static_assert(TMEM_COLS <= 512 && (SCH % 2) == 0, "tile shape");
 
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -215,8 +220,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 while (u < nu) {
                     const int run = min(nu - u, NCH - ch);
                     for (int r = 0; r < run; r += 2) {
-                        if (tc::elect_one())
+                        if (!(p.dbg & 1) && tc::elect_one()) {
                             tc::umma<false>(d_tmem, ((uint64_t)desc_hi << 32) | da_lo, ((uint64_t)desc_hi << 32) | db_lo, idesc, accumulate);
+                            if constexpr (MPI == 2)   // sub-tile m + 2: same weights, rows 2*128 further down
+                                tc::umma<false>(d_tmem + 2u * C, ((uint64_t)desc_hi << 32) | (da_lo + 2u * BM), ((uint64_t)desc_hi << 32) | db_lo, idesc, accumulate);
+                        }
                         accumulate = 1;
                         da_lo += 2u * lbo_rows;
                         db_lo += 2u * C;
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 tc::mbar_wait(ACC1_EMPTY(g), gph ^ 1);
                 tc::mbar_wait(A_FULL(g), gph);
                 tc::fence_after_sync();
-                run_phase(tmem_base + (uint32_t)((g * 2 + m) * C), tc::smem_u32(a_smem + (size_t)g * a_bytes) >> 4, (uint32_t)p.ra, p.jobs[j].K1,
+                run_phase(tmem_base + (uint32_t)((g * MT + m) * C), tc::smem_u32(a_smem + (size_t)g * a_bytes) >> 4, (uint32_t)p.ra, p.jobs[j].K1,
                           (uint32_t)p.jobs[j].dil1, 0u);
                 if (tc::elect_one()) { tc::umma_commit(A_EMPTY(g)); tc::umma_commit(ACC1_FULL(g)); }
                 __syncwarp();
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 if (jj == 0) tc::mbar_wait(ACC2_EMPTY(g2), ((it >> 1) & 1) ^ 1);
                 tc::mbar_wait(T_FULL(g), gph);
                 tc::fence_after_sync();
-                run_phase(tmem_base + (uint32_t)(4 * C + (g2 * 2 + m) * C), tc::smem_u32(t_smem + (size_t)g * t_bytes) >> 4, (uint32_t)RT, p.jobs[j].K2, 1u,
+                run_phase(tmem_base + (uint32_t)(2 * MT * C + (g2 * MT + m) * C), tc::smem_u32(t_smem + (size_t)g * t_bytes) >> 4, (uint32_t)RT, p.jobs[j].K2, 1u,
                           jj ? 1u : 0u);
                 if (tc::elect_one()) {
                     tc::umma_commit(T_EMPTY(g));
@@ -287,20 +295,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 const int m = item / NBLK, cb = item - m * NBLK;
                 const int r2 = m * BM + q * 32 + lane;
                 const int l = l02 + r2;
-                if (!(r2 < p.tmo[j2] && l < p.L)) return;
+                if (!(r2 < p.tmo[j2] && l < p.L) || (p.dbg & 6)) return;
                 const size_t off = (size_t)b2 * C * p.L + (size_t)(cb * (EB / 8)) * cs + (size_t)l * 8;
 #pragma unroll
                 for (int u = 0; u < EB / 8; ++u) tc::ldg256(jb2.res + off + (size_t)u * cs, dst + 8 * u);
-                if (p.sum_jobs)
-                    for (int jx = 1; jx < p.njobs; ++jx) {
+                if (p.sum_jobs) {
+                    // the other jobs' residuals: all loads of a chunk are issued before the first add (a per-job loop serialised
+                    // three DRAM round trips per item and made the stage-average epilogue the critical path)
+                    const float* r1 = p.jobs[1 < p.njobs ? 1 : 0].res + off;
+                    const float* r2 = p.jobs[2 < p.njobs ? 2 : 0].res + off;
+                    const float s1 = p.njobs > 1 ? 1.f : 0.f, s2 = p.njobs > 2 ? 1.f : 0.f;
 #pragma unroll
-                        for (int u = 0; u < EB / 8; ++u) {
-                            float t8[8];
-                            tc::ldg256(p.jobs[jx].res + off + (size_t)u * cs, t8);
+                    for (int u = 0; u < EB / 8; ++u) {
+                        float a8[8], b8[8];
+                        tc::ldg256(r1 + (size_t)u * cs, a8);
+                        tc::ldg256(r2 + (size_t)u * cs, b8);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) dst[8 * u + i] += t8[i];
-                        }
+                        for (int i = 0; i < 8; ++i) dst[8 * u + i] = (dst[8 * u + i] + s1 * a8[i]) + s2 * b8[i];
                     }
+                }
             };
             if (has2 && first2 < 2 * NITEM) res_load(first2, vn);
             if (has1) {
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                     const int pos = l0 + row;
                     const bool inside = pos >= 0 && pos < p.L;
                     uint32_t r[EB];
-                    tc::tmem_ld<EB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * 2 + m) * C + cb * EB), r);
+                    tc::tmem_ld<EB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * MT + m) * C + cb * EB), r);
                     tc::tmem_ld_wait();
                     const float4* bs4 = reinterpret_cast<const float4*>(bias_s + (j1 * 2) * C + cb * EB);
 #pragma unroll
@@ -352,13 +365,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                     const int m = item / NBLK, cb = item - m * NBLK;
                     const int r2 = m * BM + q * 32 + lane;
                     const int l = l02 + r2;
-                    const bool ok = r2 < p.tmo[j2] && l < p.L;
+                    const bool ok = r2 < p.tmo[j2] && l < p.L && !(p.dbg & 2);
                     float v[EB];
 #pragma unroll
                     for (int i = 0; i < EB; ++i) v[i] = vn[i];
                     if (k + NEG < 2 * NITEM) res_load(k + NEG, vn);
                     uint32_t r[EB];
-                    tc::tmem_ld<EB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(4 * C + (g * 2 + m) * C + cb * EB), r);
+                    tc::tmem_ld<EB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * MT * C + (g * MT + m) * C + cb * EB), r);
                     tc::tmem_ld_wait();
                     if (!ok) continue;
                     const float4* bs4 = reinterpret_cast<const float4*>(bias_s + (j2 * 2 + 1) * C + cb * EB);
@@ -422,9 +435,9 @@ int sm_count() {
     return sms[dev] > 0 ? sms[dev] : 148;
 }
 
-template <int C>
+template <int C, int MT>
 int launch_pair(const PParams& p, size_t smem, int grid, cudaStream_t stream) {
-    auto kern = resblock_pair_kernel<C>;
+    auto kern = resblock_pair_kernel<C, MT>;
     static bool opted[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -458,9 +471,11 @@ RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream)
     if (d.C != 32 && d.C != 64) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: C=%d (the fused pair covers C = 32 and 64)", d.C);
     if (d.B <= 0 || d.L <= 0) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: bad shape");
     if (!(d.slope >= 0.f && d.slope <= 1.f)) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: slope must be in [0, 1]");
+    const int TMR = BM * (d.C == 32 ? 4 : 2), RT = TMR + RTX;     // C = 32: four sub-tiles per tile (TMEM: 4 * MT * C columns)
     PParams p;
     p.njobs = d.njobs; p.B = d.B; p.C = d.C; p.L = d.L; p.Lp = packed_rows(d.L); p.fp16 = d.dtype == RVC_DT_FP16; p.slope = d.slope;
     p.sum_jobs = d.sum_jobs ? 1 : 0; p.y_ncl = d.y_ncl ? 1 : 0; p.alpha = d.sum_jobs ? d.alpha : 1.f;
+    p.dbg = d.reserved;
     int halo1 = 0, k2max = 1;
     long total = 0;
     for (int j = 0; j < d.njobs; ++j) {
@@ -473,7 +488,7 @@ RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream)
             return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: y_act must not alias a (tiles read a with halos while others write y_act)", j);
         if (jb.K1 <= 0 || !(jb.K1 & 1) || jb.K2 <= 0 || !(jb.K2 & 1) || jb.dil1 <= 0)
             return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: job %d needs odd kernel sizes and dil1 > 0", j);
-        if (jb.K2 - 1 > RT - TMR) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: K2=%d exceeds %d", jb.K2, RT - TMR + 1);
+        if (jb.K2 - 1 > RTX) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: K2=%d exceeds %d", jb.K2, RTX + 1);
         if ((jb.K1 - 1) / 2 * jb.dil1 + (jb.K2 - 1) / 2 > PADL)
             return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: halo %d exceeds the %d zero rows of the packed layout", (jb.K1 - 1) / 2 * jb.dil1 + (jb.K2 - 1) / 2, PADL);
         if ((((uintptr_t)jb.res | (uintptr_t)(outs ? jb.y : nullptr)) & 31) ||
@@ -500,6 +515,6 @@ RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream)
     if (smem > 227 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: tile does not fit shared memory (%zu bytes)", smem);
     const int sms = sm_count();
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-    if (d.C == 64) return launch_pair<64>(p, smem, grid, (cudaStream_t)stream);
-    return launch_pair<32>(p, smem, grid, (cudaStream_t)stream);
+    if (d.C == 64) return launch_pair<64, 2>(p, smem, grid, (cudaStream_t)stream);
+    return launch_pair<32, 4>(p, smem, grid, (cudaStream_t)stream);
 }

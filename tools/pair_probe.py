@@ -12,11 +12,11 @@ dev = "cuda:0"
 st = torch.cuda.current_stream().cuda_stream
 
 
-def probe(Cc, L, reps=6, sum_jobs=0, ks=((11, 5), (7, 3), (3, 1))):
+def probe(Cc, L, reps=6, sum_jobs=0, ks=((11, 5), (7, 3), (3, 1)), dbg=0):
     rows = lib.rvc_packed_rows(L)
     d = _lib.ResblockPairDesc()
     d.njobs, d.B, d.C, d.L, d.dtype, d.slope = 3, 1, Cc, L, 2, 0.1
-    d.sum_jobs, d.y_ncl, d.alpha = sum_jobs, 0, 1.0 / 3.0
+    d.sum_jobs, d.y_ncl, d.alpha, d.reserved = sum_jobs, 0, 1.0 / 3.0, dbg
     keep = []
     for j, (k, dil) in enumerate(ks):
         a = torch.zeros(Cc * rows * 2, dtype=torch.uint8, device=dev)
@@ -41,7 +41,11 @@ def probe(Cc, L, reps=6, sum_jobs=0, ks=((11, 5), (7, 3), (3, 1))):
     return best * 1e3
 
 
-if __name__ == "__main__" and len(sys.argv) > 1:
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dbg":
+    for Cc, L in ((64, 240000), (32, 480000)):
+        for sm in (0, 1):
+            print(f"C={Cc} {'stage-average' if sm else 'pair'}: " + "  ".join(f"{nm} {probe(Cc, L, sum_jobs=sm, dbg=dv):6.1f}" for nm, dv in (("full", 0), ("no-MMA", 1), ("no-res-loads", 4), ("no-e2-I/O", 2), ("no-MMA+no-e2-I/O", 3))))
+elif __name__ == "__main__" and len(sys.argv) > 1:
     for ks in (((3, 1),) * 3, ((7, 1),) * 3, ((11, 1),) * 3, ((11, 5), (7, 3), (3, 1))):
         print(ks, "C64 pair %.1f  avg %.1f | C32 pair %.1f  avg %.1f" % (probe(64, 240000, ks=ks), probe(64, 240000, sum_jobs=1, ks=ks),
                                                                     probe(32, 480000, ks=ks), probe(32, 480000, sum_jobs=1, ks=ks)))
