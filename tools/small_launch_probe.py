@@ -1,3 +1,4 @@
+"""Per-launch cost of small rvc_conv1d_tc launches inside a CUDA graph (back-to-back dependent launches): the numbers quoted in DESIGN.md section 4 for the short-sequence encoder / flow layers."""
 import ctypes as C, sys, torch
 sys.path.insert(0, ".")
 from rvc_maker_b200 import _lib
