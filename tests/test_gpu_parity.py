@@ -204,3 +204,25 @@ def test_cold_weights_full_batch_tc():
     ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
                                                       eps_z=inp["eps_z"], eps_src=inp["eps_src"])
     assert_close(out, dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl), "tc", tag="cold")
+
+
+def test_infer_to_host_matches_infer():
+    """Pinned read-back helper: same waveform as infer()[0], float32 on the host, complete on return, also for a half module."""
+    from rvc_maker_b200 import Synthesizer
+
+    cfg = cases.CONFIGS["tiny"]
+    sd = cases.synth_state_dict(cfg, seed=7, heated=True)
+    inp = cases.synth_inputs(cfg, 2, 48, seed=3)
+    net = Synthesizer(*cases.ctor_args(cfg), use_f0=True, text_enc_hidden_dim=cfg["text_enc_hidden_dim"])
+    del net.enc_q
+    net.load_state_dict(sd, strict=True)
+    net = net.eval().to("cuda:0")
+    args = (inp["phone"].cuda(), inp["phone_lengths"].cuda(), inp["pitch"].cuda(), inp["nsff0"].cuda(), inp["sid"].cuda())
+    for half in (False, True):
+        net = net.half() if half else net.float()
+        a = tuple(t.half() if (half and t.is_floating_point()) else t for t in args)
+        net._noise_override = (inp["eps_z"], inp["eps_src"])
+        want = net.infer(*a)[0]
+        got = net.infer_to_host(*a)
+        assert got.device.type == "cpu" and got.is_pinned() and got.dtype == torch.float32 and got.shape == want.shape
+        assert torch.equal(got, want.float().cpu())
