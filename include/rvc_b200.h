@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 20
+#define RVC_ABI_VERSION 21
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -251,7 +251,8 @@ int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* d, void* stream);
 
 /*
  * Softmax stage of the tensor-core attention (MultiHeadAttention.attention, synthesizers.py:221-250).  The contractions run
- * through rvc_conv1d_tc: S[b][h][j][i] = q_i . k_j (fp32, Tk >= T key rows per head, Tk % 8 == 0; rows >= T ignored) and
+ * through rvc_conv1d_tc: S[b][h][j/8][i][j%8] = q_i . k_j (fp32, channel-blocked over the keys — f32_blocked output of the
+ * GEMM; Tk >= T key rows per head, Tk % 8 == 0; rows >= T ignored) and
  * O = P . v (+ R).  This call computes, per (b, head, query i):
  *   s[i,j] = S[j][i] / sqrt(dk) + [|j-i| <= w] (q_i / sqrt(dk)) . emb_k[j-i+w];   s = -1e4 where mask_i * mask_j == 0
  *   P = softmax_j(s) -> packed fp16 [b][h][Tk/8][rvc_packed_rows(T)][8] (positions = queries, channels = keys)

@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 20
+ABI_VERSION = 21
 DT_BF16, DT_FP16 = 0, 2
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2

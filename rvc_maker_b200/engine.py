@@ -411,11 +411,11 @@ class Engine:
                 self._tc(p, f"qkv{i}", [dict(a=xa, w=W[f"t_qkv_w{i}"], bias=W[f"qkv_b{i}"], y=vqkv, y_act=(qkva if tc_attn else None))],
                          B=B, Cin=H, Cout=3 * H, L=T, dtype=dt, tag="enc")
                 if tc_attn:
-                    # S[b][h][key][query] = q . k^T : the packed k activations of each batch item are the GEMM's weights
+                    # S[b][h][key/8][query][8] = q . k^T (channel-blocked over the keys): the packed k activations of each batch item are the GEMM's weights
                     jobs = [dict(a=qkva.data_ptr() + (h * dk // 8) * Lp * 16, a_bs=qkv_bs,
                                  w=qkva.data_ptr() + (((H + h * dk) // 8) * Lp + 64) * 16, w_bs=qkv_bs, w_cs=Lp,
-                                 y=V(Sb, nh * Tk, T, h * Tk)) for h in range(nh)]
-                    self._tc(p, f"attn_qk{i}", jobs, B=B, Cin=dk, Cout=Tk, L=T, dtype=dt, tag="attn", flops=2.0 * B * H * T * T)
+                                 y=V(Sb, nh * Tk, T, h * Tk, cs=8 * T)) for h in range(nh)]
+                    self._tc(p, f"attn_qk{i}", jobs, B=B, Cin=dk, Cout=Tk, L=T, dtype=dt, tag="attn", flops=2.0 * B * H * T * T, blocked=2)
                     p.add(f"attn_sm{i}", lib.rvc_attn_softmax, Sb.data_ptr(), qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(),
                           W[f"ev{i}"].data_ptr(), Pb.data_ptr(), Rb.data_ptr(), vwb.data_ptr(), B, H, nh, T, Tk, WINDOW,
                           bytes_=B * nh * Tk * T * 10.0, kind="attn_softmax")

@@ -78,11 +78,12 @@ def test_attn_softmax_stage(B, T):
     # S[b,h,j,i] = q_i . k_j (what the QK^T launch produces); rows >= T are never read
     S = torch.zeros(B, nh, Tk, T, device=DEV)
     S[:, :, :T] = torch.einsum("bhdi,bhdj->bhji", q, k).float()
+    S_blocked = S.view(B, nh, Tk // 8, 8, T).permute(0, 1, 2, 4, 3).contiguous()      # [b][h][key/8][query][8], as the GEMM writes it
     rows = lib.rvc_packed_rows(T)
     P = torch.zeros(B * nh * (Tk // 8) * rows * 16, dtype=torch.uint8, device=DEV)
     R = torch.zeros(B, H, T, device=DEV)
     vw = torch.zeros(B * nh * (Tk // 8) * dk * 16, dtype=torch.uint8, device=DEV)
-    _lib.check(lib.rvc_attn_softmax(S.data_ptr(), qkv.data_ptr(), mask.data_ptr(), emb_k.data_ptr(), emb_v.data_ptr(), P.data_ptr(), R.data_ptr(),
+    _lib.check(lib.rvc_attn_softmax(S_blocked.data_ptr(), qkv.data_ptr(), mask.data_ptr(), emb_k.data_ptr(), emb_v.data_ptr(), P.data_ptr(), R.data_ptr(),
                                     vw.data_ptr(), B, H, nh, T, Tk, W, st), "attn_softmax")
     torch.cuda.synchronize()
     # reference (synthesizers.py:226-248 in closed form)
