@@ -245,7 +245,7 @@ typedef struct {
      * when y_ncl = 1) and y_act (optional; packed lrelu of it). */
     int32_t sum_jobs, y_ncl;
     float alpha;
-    int32_t reserved;
+    int32_t reserved;   /* 0 (timing experiments: 1 = no MMA issue, 2 = no epilogue-2 global I/O, 4 = no residual loads) */
 } rvc_resblock_pair_desc;
 int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* d, void* stream);
 

@@ -1,15 +1,15 @@
 // One ResBlock step  x <- c2(lrelu(c1_d(lrelu(x)))) + x  (residuals.py:32-36) as ONE persistent tcgen05 kernel for the narrow
 // generator stages (C = 32, 64), where the two separate conv launches are bound by the epilogue's HBM traffic, not the tensor pipe.
 //
-// Per tile of 256 rows the intermediate t = lrelu(c1(lrelu(x)) + b1) never leaves the SM: phase 1 accumulates c1 into TMEM, the
+// Per tile of R = 256 rows (512 at C = 32) the intermediate t = lrelu(c1(lrelu(x)) + b1) never leaves the SM: phase 1 accumulates c1 into TMEM, the
 // epilogue rounds t to fp16 straight into a shared-memory tile in the packed operand layout ([c/8][row][8], the K-major
 // no-swizzle core-matrix layout), and phase 2 reads that tile as its A operand — a conv2 tap is again just a descriptor start
 // address 16 B further down.  Saved against two launches: the packed write of t, its read back, one launch.  The tile computes
-// t on rows [l0 - h2, l0 - h2 + 256) and keeps the 256 - (K2-1) outputs that see only real t rows, so consecutive tiles overlap
-// by K2-1 rows (4 % recompute at k = 11).  t rows outside [0, L) are written as zeros: conv2's "same" padding.
+// t on rows [l0 - h2, l0 - h2 + R) and keeps the R - (K2-1) outputs that see only real t rows, so consecutive tiles overlap
+// by K2-1 rows (4 % recompute at k = 11, R = 256).  t rows outside [0, L) are written as zeros: conv2's "same" padding.
 //
 // Roles as in conv1d_tc.cu (512 threads): warp 0 activation producer, warp 2 weight producer (w1 and w2 stream through one ring),
-// warps 1/3 MMA issuers (one 128-row sub-tile each), warps 4-15 epilogue.  Everything is double-buffered (activation tile, t tile,
+// warps 1/3 MMA issuers (one or two 128-row sub-tiles each), warps 4-15 epilogue.  Everything is double-buffered (activation tile, t tile,
 // both accumulators) and the two phases are skewed by one tile — every role walks  P1(0), P1(1), P2(0), P1(2), P2(1), ... — so that
 // the tensor pipe works on tile i+1's conv1 while the epilogue still stores tile i.
 #include "common.cuh"
