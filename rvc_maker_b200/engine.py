@@ -802,7 +802,7 @@ class Engine:
             head = int(T * (1.0 - rate)) if rate is not None else 0
             T2 = T - head
             pd = self.plan("dec", B, T2)
-            pd.g.copy_(self.W["emb_g"][sid.to(self.dev)])  # emb_g(sid), :447
+            pd.g.copy_(self.W["emb_g"][sid.to(self.dev, non_blocking=True)])  # emb_g(sid), :447 (no host sync for a pinned sid)
             if c["f0"]:
                 pd.f0.copy_(nsff0[:, head:], non_blocking=True)
                 if noise is not None:
