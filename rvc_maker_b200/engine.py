@@ -477,10 +477,17 @@ class Engine:
         half = I // 2
         upp = c["upp"]
         p = Plan()
-        p.zp = self._buf(p, B, I, T)
-        p.mask = self._buf(p, B, T)
+        # the four results the decoder plan hands back (o, mask, z, z_p) share one arena, so infer() clones them with a single copy
+        Lfin_ = T * c["upp"]
+        seg = lambda n: -(-n // 64) * 64                       # segments start 256-byte aligned
+        n_o, n_m, n_z = seg(B * Lfin_), seg(B * T), seg(B * I * T)
+        p.out_arena = self._buf(p, n_o + n_m + 2 * n_z)
+        p.o = p.out_arena[:B * Lfin_].view(B, 1, Lfin_)
+        p.mask = p.out_arena[n_o:n_o + B * T].view(B, T)
+        p.z = p.out_arena[n_o + n_m:n_o + n_m + B * I * T].view(B, I, T)
+        p.zp = p.out_arena[n_o + n_m + n_z:n_o + n_m + n_z + B * I * T].view(B, I, T)
+        p.out_offsets = (n_o, n_m, n_z)
         p.g = self._buf(p, B, G)
-        p.z = self._buf(p, B, I, T)
         gc = self._buf(p, B, self.cond_total)
         hb, acts, outb = self._buf(p, B, H, T), self._buf(p, B, H, T), self._buf(p, B, H, T)
         vh, va, vo = V(hb, H, T), V(acts, H, T), V(outb, H, T)
@@ -741,7 +748,6 @@ class Engine:
                               kind=f"conv1d_tc_{'bf16' if dt == DT_BF16 else 'fp16'}[C{Ci}]")
                 cur, curC, curL = (avg, None, None), Ci, Li       # stage average (fp32, plain layout), None when the next ups is fused
                 prev_ua = next_ua
-        p.o = self._buf(p, B, 1, Lfin)
         x2 = cur[1].data_ptr() if cur[1] is not None else None
         x3 = cur[2].data_ptr() if cur[2] is not None else None
         p.add("conv_post", lib.rvc_conv_post_f32, cur[0].data_ptr(), x2, x3, float(nk), curC * curL, curL, W["post_w"].data_ptr(), p.o.data_ptr(),
@@ -835,11 +841,15 @@ class Engine:
                 body(stream)
                 self._warm.add(key)
 
+            # fresh tensors for the caller: one copy of the decoder plan's result arena, one of the encoder statistics
             I = c["I"]
-            o = pd.o.to(out_dtype, copy=True)
-            x_mask = pd.mask.view(B, 1, T2).to(out_dtype, copy=True)
-            z = pd.z.to(out_dtype, copy=True)
-            z_p = pd.zp.to(out_dtype, copy=True)
-            m_p = pe.stats[:, :I].to(out_dtype, copy=True)
-            logs_p = pe.stats[:, I:].to(out_dtype, copy=True)
+            res = pd.out_arena.to(out_dtype, copy=True)
+            n_o, n_m, n_z = pd.out_offsets
+            Lfin = T2 * c["upp"]
+            o = res[:B * Lfin].view(B, 1, Lfin)
+            x_mask = res[n_o:n_o + B * T2].view(B, 1, T2)
+            z = res[n_o + n_m:n_o + n_m + B * I * T2].view(B, I, T2)
+            z_p = res[n_o + n_m + n_z:n_o + n_m + n_z + B * I * T2].view(B, I, T2)
+            stats = pe.stats.to(out_dtype, copy=True)
+            m_p, logs_p = stats[:, :I], stats[:, I:]
         return o, x_mask, (z, z_p, m_p, logs_p)
