@@ -117,6 +117,38 @@ def cpu_baseline(cfg, sd, inp, steps, warmup):
     return times, cores
 
 
+def gpu_eager_baseline(cfg, sd, inp, dev, audio_s, steps=5, warmup=2):
+    """Same-box library baseline: the reference algorithm (oracle port, weight-norm already folded — which the reference
+    does not do) executed by PyTorch eager on this GPU, i.e. cuDNN / cuBLAS kernels, fp32 with TF32 off and on.  Part of the baseline
+    leg only (`--gpu-eager-baseline`); nothing of the product runs here."""
+    from oracle import synth_oracle
+
+    res = {"kind": "port", "what": "oracle port under PyTorch eager on cuda (cuDNN/cuBLAS), device-resident inputs, weight-norm pre-folded"}
+    try:
+        folded = {k: v.to(dev) for k, v in synth_oracle.fold_state_dict(sd).items()}
+        di = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
+        for tag, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            ts = []
+            with torch.device(dev):
+                for i in range(warmup + steps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    synth_oracle.infer(sd, cfg, di["phone"], di["phone_lengths"], di["pitch"], di["nsff0"], di["sid"], folded=folded)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if i >= warmup:
+                        ts.append(e0.elapsed_time(e1))
+            res[tag] = {"value": audio_s / (min(ts) * 1e-3), "unit": "audio-s/s", "ms_per_step": min(ts)}
+    except Exception as e:   # a baseline that cannot run must not take the bench line with it
+        res["error"] = f"{type(e).__name__}: {e}"[:300]
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = False
+    return res
+
+
 def bench_stream(args, cfg, net, dev, dist, rank, world, local_rank):
     """BASELINE config 5: `--stream-seconds` of synthetic 50 fps features + f0, cut by the reference's chunk plan (convert.py:403-447,
     x_pad / x_center = 1 / 38 s), chunks sharded longest-first over the ranks, run through rvc_maker_b200.pipeline.StreamConverter
@@ -218,6 +250,8 @@ def main():
     ap.add_argument("--stream-batch", type=int, default=2, help="stream workload: equal-length chunks batched per infer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-json", default=None, help="write the per-kernel timing table here")
+    ap.add_argument("--gpu-eager-baseline", action="store_true",
+                    help="also time the oracle port under PyTorch eager on this GPU (cuDNN/cuBLAS; the same-box library baseline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -378,9 +412,18 @@ def main():
         roof.update({"kernel": top, "launches_per_step": f["launches"], "share_of_step": f["ms"] / total_ms,
                      "peak_source": "MEASURED_PEAKS.json (sustained)" if peaks else "fallback"})
         out["roofline"] = roof
-        out["kernels"] = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4),
-                              "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2), "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
-                              "launches": v["launches"]} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+        # per-stage fraction of roofline: the bound is the side of the ridge (sustained tensor peak / HBM peak, flop per byte) the
+        # family's algorithmic intensity falls on; launch-latency-bound families (short sequences) show up as small fractions of either
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        ridge = bf16_peak * 1e3 / hbm_peak
+
+        def stage_row(v):
+            tf, gb = v["flops"] / max(v["ms"], 1e-9) / 1e9, v["bytes"] / max(v["ms"], 1e-9) / 1e6
+            tensor = v["flops"] / max(v["bytes"], 1.0) > ridge
+            return {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4), "tflops": round(tf, 2), "gbs": round(gb, 1),
+                    "bound": "tensor" if tensor else "hbm", "frac": round(tf / bf16_peak if tensor else gb / hbm_peak, 4), "launches": v["launches"]}
+
+        out["kernels"] = {k: stage_row(v) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         if args.ops_json:
             json.dump(rows, open(args.ops_json, "w"), indent=0)
         if world == 1 and not args.no_cpu_baseline:
@@ -388,6 +431,8 @@ def main():
             times, cores = cpu_baseline(cfg, sd, inp, 2, 1)
             out["cpu_baseline"] = {"value": audio_s / min(times), "unit": "audio-s/s", "cores": cores, "kind": "port",
                                    "sample": f"best of 2 after 1 warm-up of the same step (B={B}, T={T}), torch CPU fp32 oracle port"}
+        if world == 1 and args.gpu_eager_baseline:
+            out["gpu_eager_baseline"] = gpu_eager_baseline(cfg, sd, synth_inputs(cfg, B, T), dev, audio_s)
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
