@@ -195,6 +195,21 @@ def test_bench_workload_full_size(precision):
     assert_close(out, ref, precision, tag="config2")
 
 
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+@pytest.mark.parametrize("T", [1, 2, 9, 127, 129, 1001])
+def test_edge_lengths(T, precision):
+    """Lengths around the kernels' tile edges (128-position MMA tiles, 8-key chunks, 64-row pads), a single frame, and a ragged batch
+    whose second item can be empty (T = 1 draws lengths [1, 0]: every key masked, softmax over a row of -1e4)."""
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=777, heated=True)
+    inp = cases.synth_inputs(cfg, 2, T, seed=T, ragged=True)
+    out = run_net(build_net(cfg, sd, True, precision=precision), inp)
+    ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
+                                                      eps_z=inp["eps_z"], eps_src=inp["eps_src"])
+    assert tuple(out["o"].shape) == (2, 1, T * 480)
+    assert_close(out, dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl), precision, tag=f"T={T}")
+
+
 def test_cold_weights_full_batch_tc():
     """Reference-like initialisation statistics (DC-dominated output), ragged batch of 4, tensor-core path."""
     cfg = cases.CONFIGS["v2_40k"]
