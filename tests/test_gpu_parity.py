@@ -210,6 +210,19 @@ def test_edge_lengths(T, precision):
     assert_close(out, dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl), precision, tag=f"T={T}")
 
 
+@pytest.mark.parametrize("B,T,rate", [(1, 1024, None), (1, 1025, None), (40, 64, None), (2, 300, 0.5)])
+def test_softmax_variant_boundary_wide_batch_and_rate_tc(B, T, rate):
+    """T = 1024 / 1025 sit on either side of the short- and long-sequence softmax kernels; B = 40 is wider than any BASELINE batch;
+    `rate` (synthesizers.py:451-456) trims the head frames before the flow on the real architecture."""
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=778, heated=True)
+    inp = cases.synth_inputs(cfg, B, T, seed=B + T, ragged=B > 1)
+    out = run_net(build_net(cfg, sd, True, precision="tc"), inp, rate)
+    ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
+                                                      rate=rate, eps_z=inp["eps_z"], eps_src=inp["eps_src"])
+    assert_close(out, dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl), "tc", tag=f"B={B} T={T} rate={rate}")
+
+
 def test_cold_weights_full_batch_tc():
     """Reference-like initialisation statistics (DC-dominated output), ragged batch of 4, tensor-core path."""
     cfg = cases.CONFIGS["v2_40k"]
