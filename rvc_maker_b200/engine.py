@@ -110,6 +110,7 @@ class Engine:
         self.tc = self.precision != "fp32"
         self._fold(m)
         self.plans = {}
+        self.max_plans = 16   # encoder + decoder plans of the 8 most recently used (B, T) shapes (a bucketed stream needs 3-6)
         self.graphs = {}
         self._warm = set()
         self.use_graph = bool(getattr(m, "use_cuda_graph", True))
@@ -757,14 +758,14 @@ class Engine:
 
     def plan(self, kind, B, T):
         key = (kind, B, T)
-        pl = self.plans.get(key)
+        pl = self.plans.pop(key, None)
         if pl is None:
-            if len(self.plans) >= 8:  # bound the workspace arena: drop the oldest shape (and every graph built on it)
+            if len(self.plans) >= self.max_plans:  # bound the workspace arena: drop the least recently used shape (and every graph built on it)
                 self.plans.pop(next(iter(self.plans)))
                 self.graphs.clear()
                 self._warm.clear()
             pl = self._enc_plan(B, T) if kind == "enc" else self._dec_plan(B, T)
-            self.plans[key] = pl
+        self.plans[key] = pl   # most recently used last
         return pl
 
     def profile(self, B, T, repeats=3):
@@ -828,7 +829,7 @@ class Engine:
             key = (B, T, head)
             gr = self.graphs.get(key) if self.use_graph else None
             if self.use_graph and gr is None and key in self._warm:
-                if len(self.graphs) >= 8:
+                if len(self.graphs) >= self.max_plans // 2:
                     self.graphs.pop(next(iter(self.graphs)))
                 gr = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize(self.dev)

@@ -5,6 +5,12 @@ Mirrors ``VC.voice_conversion`` from the embedder output on (main/inference/conv
 ``infer`` -> ``.cpu().numpy()`` -> ``empty_cache()``, then ``np.concatenate`` and a peak normalisation.  Here
 
 * chunks with the same shape are batched into one ``infer`` (the 38 s chunks of a long stream all have T = 4000);
+* ``bucket=N`` (optional): the reference cuts real audio at energy minima (:403-420), so every chunk has its own length and each
+  would need its own launch plan / CUDA graph.  With a bucket, chunks are zero-padded to the next multiple of N frames and run
+  with their true ``phone_lengths`` — exactly what the reference computes for the shorter items of a ragged batch — so a few
+  shapes serve the whole stream and unequal chunks batch together.  Encoder and flow are masked at every layer (identical
+  values); the generator's tail sees the padding only within its receptive field (~10 frames), far inside the ``x_pad`` = 1 s of
+  context that is trimmed from every piece;
 * up-sampling + protect blend are one kernel (``rvc_feature_prep_f32``), bit-identical to the reference's elementwise ops;
 * inputs of batch i+1 are staged host->device on a copy stream while batch i computes, finished pieces are trimmed on the
   device and copied into ONE pinned host buffer at their final offsets on a second copy stream (no per-chunk sync, no concatenate);
@@ -73,11 +79,26 @@ def voice_conversion(net_g, feats, p_len, pitch, pitchf, sid, protect=0.5, feats
     return o[:, 0]
 
 
-def batch_chunks(chunks, max_batch):
-    """Group chunks of identical length (frames and samples) into batches of at most ``max_batch``, longest first."""
+def voice_conversion_padded(net_g, feats, lengths, pitch, pitchf, sid, protect=0.5, feats0=None):
+    """``voice_conversion`` for a bucketed batch: feats / feats0 [B, Tb/2, D], pitch / pitchf [B, Tb] are zero-padded (pitch index 1)
+    behind every item's own frames and ``lengths`` [B] holds each item's p_len (settled per item by the caller, :363-369).
+    Returns [B, Tb*upp]; item b is valid up to its own ``T_b * upp`` samples."""
+    guided = pitch is not None and pitchf is not None
+    phone = feature_prep(feats, feats0 if guided else None, pitchf if guided else None, protect, 2 * feats.shape[1])
+    o = net_g.infer(phone, lengths, pitch if guided else None, pitchf.float() if guided else None, sid)[0]
+    return o[:, 0]
+
+
+def batch_chunks(chunks, max_batch, bucket=0):
+    """Group chunks of identical length (frames and samples) — or, with ``bucket``, of the same length rounded up to a multiple of
+    ``bucket`` frames — into batches of at most ``max_batch``, longest first."""
+    if bucket:
+        key = lambda c: -(-c.frames // bucket)
+    else:
+        key = lambda c: (c.frames, c.sample_end - c.sample_start)
     groups, cur = [], []
     for c in sorted(chunks, key=lambda c: (-c.frames, -(c.sample_end - c.sample_start), c.index)):
-        if cur and (len(cur) == max_batch or (c.frames, c.sample_end - c.sample_start) != (cur[0].frames, cur[0].sample_end - cur[0].sample_start)):
+        if cur and (len(cur) == max_batch or key(c) != key(cur[0])):
             groups.append(cur)
             cur = []
         cur.append(c)
@@ -97,8 +118,11 @@ def piece_layout(spans, upp, tgt_sr, cfg=ChunkConfig()):
 class StreamConverter:
     """``VC.pipeline`` from the chunk plan on (convert.py:403-452), batched and overlapped.  One instance per process / GPU."""
 
-    def __init__(self, net_g, tgt_sr, upp, *, cfg=ChunkConfig(), max_batch=2, device=None):
+    def __init__(self, net_g, tgt_sr, upp, *, cfg=ChunkConfig(), max_batch=2, device=None, bucket=0):
         self.net, self.sr, self.upp, self.cfg, self.max_batch = net_g, int(tgt_sr), int(upp), cfg, int(max_batch)
+        self.bucket = int(bucket)
+        if self.bucket < 0 or self.bucket % 2:
+            raise ValueError("bucket must be an even number of frames (0 = exact shapes)")
         self.dev = torch.device(device) if device is not None else next(net_g.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("rvc_maker_b200.pipeline.StreamConverter needs the model on a CUDA device (no CPU fallback)")
@@ -118,6 +142,8 @@ class StreamConverter:
                 f, f0 = embed(c)
                 fl.append(f)
                 f0l.append(f0)
+            if self.bucket:
+                return self._stage_padded(group, fl, f0l, pitch, pitchf, sid)
             if any(f.shape != fl[0].shape for f in fl):
                 raise ValueError("chunks of one batch must give features of one shape")
             feats = torch.stack([f.to(self.dev, non_blocking=True) for f in fl])
@@ -135,7 +161,44 @@ class StreamConverter:
             ev = torch.cuda.Event()
             ev.record(self.h2d)
         nbytes = sum(t.numel() * t.element_size() for t in (feats, None if feats0 is feats else feats0, pi, pf) if t is not None)
-        return dict(group=group, feats=feats, feats0=feats0, pitch=pi, pitchf=pf, sid=sd, ev=ev, bytes=nbytes)
+        return dict(group=group, feats=feats, feats0=feats0, pitch=pi, pitchf=pf, sid=sd, ev=ev, bytes=nbytes, lengths=None,
+                    T_items=[2 * int(feats.shape[1])] * len(group))
+
+    def _stage_padded(self, group, fl, f0l, pitch, pitchf, sid):
+        """Bucketed batch (called on the copy stream): every item keeps its own frames, the rest of the bucket is zeros / pitch index 1."""
+        B, D = len(group), int(fl[0].shape[1])
+        guided = pitch is not None
+        T_items, p_lens = [], []
+        for c, f in zip(group, fl):
+            T, p_len, n_pitch = 2 * int(f.shape[0]), (c.sample_end - c.sample_start) // WINDOW, c.frame_end - c.frame_start
+            if T < p_len:                                         # convert.py:365-369
+                p_len, n_pitch = T, min(n_pitch, T)
+            if guided and n_pitch != T:
+                raise ValueError(f"features have {T} frames after up-sampling but pitch has {n_pitch}")
+            T_items.append(T)
+            p_lens.append(p_len)
+        Tb = -(-max(T_items) // self.bucket) * self.bucket
+        feats = torch.zeros(B, Tb // 2, D, device=self.dev)
+        same = all(f0 is f for f, f0 in zip(fl, f0l))
+        feats0 = None if any(f0 is None for f0 in f0l) else (feats if same else torch.zeros(B, Tb // 2, D, device=self.dev))
+        pi = torch.ones(B, Tb, dtype=torch.long, device=self.dev) if guided else None
+        pf = torch.zeros(B, Tb, device=self.dev) if guided else None
+        nbytes = 0
+        for b, (c, f, f0) in enumerate(zip(group, fl, f0l)):
+            feats[b, :f.shape[0]].copy_(f, non_blocking=True)
+            nbytes += f.numel() * 4
+            if feats0 is not None and feats0 is not feats:
+                feats0[b, :f0.shape[0]].copy_(f0, non_blocking=True)
+                nbytes += f0.numel() * 4
+            if guided:
+                pi[b, :T_items[b]].copy_(pitch[c.frame_start:c.frame_start + T_items[b]], non_blocking=True)
+                pf[b, :T_items[b]].copy_(pitchf[c.frame_start:c.frame_start + T_items[b]], non_blocking=True)
+                nbytes += T_items[b] * 12
+        lengths = torch.tensor(p_lens, dtype=torch.long).to(self.dev)
+        sd = sid.to(self.dev, non_blocking=True).reshape(-1)[:1].expand(B).contiguous()
+        ev = torch.cuda.Event()
+        ev.record(self.h2d)
+        return dict(group=group, feats=feats, feats0=feats0, pitch=pi, pitchf=pf, sid=sd, ev=ev, bytes=nbytes, lengths=lengths, T_items=T_items)
 
     # ------------------------------------------------------------------ convert
     def convert(self, n_samples, opt_ts, embed, pitch, pitchf, sid, *, protect=0.5, rank=0, world=1, noise_fn=None, to_host=True):
@@ -154,7 +217,7 @@ class StreamConverter:
         mine = [c for c in spans if owner[c.index] == rank]
         offs, lens, total = piece_layout(spans, self.upp, self.sr, self.cfg)
         t_pad_tgt = self.sr * self.cfg.x_pad
-        groups = batch_chunks(mine, self.max_batch)
+        groups = batch_chunks(mine, self.max_batch, self.bucket)
         comp = torch.cuda.current_stream(self.dev)
         st = comp.cuda_stream
         if to_host and rank == 0 and (self._host is None or self._host.numel() < total):
@@ -162,7 +225,7 @@ class StreamConverter:
         self._peak.zero_()
         self.h2d.wait_stream(comp)
         self.d2h.wait_stream(comp)
-        pieces, keep, short, h2d_bytes = {}, [], False, 0
+        pieces, keep, short, h2d_bytes, shapes = {}, [], False, 0, set()
         staged = self._stage(groups[0], embed, pitch, pitchf, sid) if groups else None
         for gi, group in enumerate(groups):
             cur = staged
@@ -170,33 +233,42 @@ class StreamConverter:
             staged = self._stage(groups[gi + 1], embed, pitch, pitchf, sid) if gi + 1 < len(groups) else None   # overlaps this batch
             h2d_bytes += cur["bytes"]
             c0 = group[0]
+            T_items = cur["T_items"]
+            shapes.add((len(group), 2 * int(cur["feats"].shape[1])))
             if noise_fn is not None:
                 nz = [noise_fn(c) for c in group]
+                if cur["lengths"] is not None:   # bucketed: the pinned draws cover each item's own frames, zeros behind them
+                    Tb = cur["pitch"].shape[1] if cur["pitch"] is not None else 2 * cur["feats"].shape[1]
+                    nz = [(torch.nn.functional.pad(a, (0, Tb - a.shape[2])), torch.nn.functional.pad(b, (0, 0, 0, Tb * self.upp - b.shape[1])))
+                          for a, b in nz]
                 self.net._noise_override = (torch.cat([a for a, _ in nz]), torch.cat([b for _, b in nz]))
-            wav = voice_conversion(self.net, cur["feats"], (c0.sample_end - c0.sample_start) // WINDOW, cur["pitch"], cur["pitchf"], cur["sid"],
-                                   protect, cur["feats0"])
-            for t in (cur["feats"], cur["feats0"], cur["pitch"], cur["pitchf"], cur["sid"]):
+            if cur["lengths"] is not None:
+                wav = voice_conversion_padded(self.net, cur["feats"], cur["lengths"], cur["pitch"], cur["pitchf"], cur["sid"], protect, cur["feats0"])
+            else:
+                wav = voice_conversion(self.net, cur["feats"], (c0.sample_end - c0.sample_start) // WINDOW, cur["pitch"], cur["pitchf"], cur["sid"],
+                                       protect, cur["feats0"])
+            for t in (cur["feats"], cur["feats0"], cur["pitch"], cur["pitchf"], cur["sid"], cur["lengths"]):
                 if t is not None:
                     t.record_stream(comp)
-            L = wav.shape[1]
-            n_keep = L - 2 * t_pad_tgt
-            if n_keep <= 0:
-                raise ValueError(f"chunk of {c0.frames} frames is shorter than its 2 x {self.cfg.x_pad} s of context")
-            body = wav[:, t_pad_tgt:L - t_pad_tgt]                                    # [t_pad_tgt : -t_pad_tgt], :444
+            keeps = [T * self.upp - 2 * t_pad_tgt for T in T_items]
+            if min(keeps) <= 0:
+                raise ValueError(f"chunk of {min(T_items)} frames is shorter than its 2 x {self.cfg.x_pad} s of context")
+            bodies = [wav[b, t_pad_tgt:t_pad_tgt + keeps[b]] for b in range(len(group))]   # [t_pad_tgt : -t_pad_tgt], :444
             for b in range(len(group)):   # one running peak for the whole stream
-                _lib.check(self.lib.rvc_absmax_f32(body[b].data_ptr(), 0, n_keep, self._peak.data_ptr(), 1, st), "rvc_absmax_f32")
+                _lib.check(self.lib.rvc_absmax_f32(bodies[b].data_ptr(), 0, keeps[b], self._peak.data_ptr(), 1, st), "rvc_absmax_f32")
             ev = torch.cuda.Event()
             ev.record(comp)
             for b, c in enumerate(group):
-                short |= n_keep != lens[c.index]
-                pieces[c.index] = body[b]
+                short |= keeps[b] != lens[c.index]
+                pieces[c.index] = bodies[b]
                 if to_host and world == 1:
                     self.d2h.wait_event(ev)
                     with torch.cuda.stream(self.d2h):
-                        self._host[offs[c.index]: offs[c.index] + min(n_keep, lens[c.index])].copy_(body[b, :lens[c.index]], non_blocking=True)
+                        self._host[offs[c.index]: offs[c.index] + min(keeps[b], lens[c.index])].copy_(bodies[b][:lens[c.index]], non_blocking=True)
             wav.record_stream(self.d2h)
             keep.append(wav)
-        self.last_stats = {"chunks": len(spans), "batches": len(groups), "h2d_bytes": h2d_bytes, "d2h_bytes": 4 * total if rank == 0 else 0}
+        self.last_stats = {"chunks": len(spans), "batches": len(groups), "h2d_bytes": h2d_bytes, "d2h_bytes": 4 * total if rank == 0 else 0,
+                           "shapes": len(shapes)}
         if not to_host:
             return pieces
         if world > 1:

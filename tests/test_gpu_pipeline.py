@@ -76,8 +76,9 @@ class PatternNet(torch.nn.Module):
         return (o.unsqueeze(1),)
 
 
-@pytest.mark.parametrize("seconds,max_batch,silent", [(100, 2, False), (100, 1, False), (30, 2, False), (200, 3, True), (125, 2, True)])
-def test_stream_converter_plumbing_is_bit_exact(seconds, max_batch, silent):
+@pytest.mark.parametrize("seconds,max_batch,silent,bucket", [(100, 2, False, 0), (100, 1, False, 0), (30, 2, False, 0), (200, 3, True, 0), (125, 2, True, 0),
+                                                             (100, 2, False, 512), (200, 3, False, 1024), (125, 2, True, 256), (30, 2, False, 64)])
+def test_stream_converter_plumbing_is_bit_exact(seconds, max_batch, silent, bucket):
     upp, sr, D = 480, 48000, 16
     rng = np.random.Generator(np.random.PCG64(seconds))
     n = seconds * ch.SAMPLE_RATE
@@ -97,7 +98,7 @@ def test_stream_converter_plumbing_is_bit_exact(seconds, max_batch, silent):
         audio, lambda a, f0, f1: (feats[None, half_rate(f0, f1)], feats0[None, half_rate(f0, f1)]), ref_net.infer, pitch[None], pitchf[None], sid, sr, protect)
 
     net = PatternNet(upp).to(DEV)
-    conv = pl.StreamConverter(net, sr, upp, max_batch=max_batch)
+    conv = pl.StreamConverter(net, sr, upp, max_batch=max_batch, bucket=bucket)
     fh, f0h = feats.pin_memory(), feats0.pin_memory()
     got = conv.convert(n, ch.split_points(audio), lambda c: (fh[half_rate(c.frame_start, c.frame_end)], f0h[half_rate(c.frame_start, c.frame_end)]),
                        pitch.pin_memory(), pitchf.pin_memory(), sid, protect=protect)
@@ -112,6 +113,54 @@ def test_stream_converter_plumbing_is_bit_exact(seconds, max_batch, silent):
     assert conv.last_stats["chunks"] == len(opt_ts) + 1
     if silent:
         assert conv.last_stats["batches"] < conv.last_stats["chunks"]
+    if bucket >= 512 and not silent:   # energy-split chunks all differ in length: buckets bring them back to a few shapes
+        exact = len({c.frames for c in ch.chunk_spans(n, opt_ts)})
+        assert conv.last_stats["shapes"] < exact, (conv.last_stats, exact)
+
+
+def test_bucketed_stream_equals_exact_shapes_with_the_model():
+    """Three chunks of unequal length (1130 / 1280 / 1190 frames) through the real Synthesizer (fp32 kernel set, pinned noise): padding them
+    to one 1280-frame bucket with their true lengths gives the waveform of the exact-shape runs — the generator's tail sees the
+    padding only inside the 1 s of context that is trimmed."""
+    from rvc_maker_b200 import Synthesizer
+
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=1234, heated=True)
+    upp, sr, D, I = cases.upp_of(cfg), cfg["sr"], cfg["text_enc_hidden_dim"], cfg["inter_channels"]
+    n = 30 * ch.SAMPLE_RATE
+    opt_ts = [int(9.3 * ch.SAMPLE_RATE), int(20.1 * ch.SAMPLE_RATE)]
+    spans = ch.chunk_spans(n, opt_ts)
+    assert [c.frames for c in spans] == [1130, 1280, 1190]
+    total_frames = spans[-1].frame_end
+    inp = cases.synth_inputs(cfg, 1, total_frames, seed=9)
+    g = torch.Generator().manual_seed(12)
+    feats = torch.randn(total_frames // 2, D, generator=g)
+    feats0 = feats + 0.3 * torch.randn(total_frames // 2, D, generator=g)
+    pitch, pitchf, sid = inp["pitch"][0], inp["nsff0"][0], inp["sid"]
+
+    def noise(c):
+        T = 2 * (c.frames // 2)
+        ez = torch.from_numpy(np.random.Generator(np.random.PCG64(300 + c.index)).standard_normal((1, I, T), dtype=np.float32))
+        es = torch.from_numpy(np.random.Generator(np.random.PCG64(400 + c.index)).standard_normal((1, T * upp, 1), dtype=np.float32))
+        return ez, es
+
+    net = Synthesizer(*cases.ctor_args(cfg), use_f0=True, text_enc_hidden_dim=D, precision="fp32")
+    del net.enc_q
+    net.load_state_dict(sd, strict=True)
+    net = net.eval().to(DEV)
+    fh, f0h = feats.pin_memory(), feats0.pin_memory()
+    emb = lambda c: (fh[half_rate(c.frame_start, c.frame_end)], f0h[half_rate(c.frame_start, c.frame_end)])
+    outs, stats = {}, {}
+    for bucket in (0, 256):
+        conv = pl.StreamConverter(net, sr, upp, max_batch=2, bucket=bucket)
+        outs[bucket] = conv.convert(n, opt_ts, emb, pitch, pitchf, sid, protect=0.33, noise_fn=noise).copy()
+        stats[bucket] = dict(conv.last_stats)
+    assert outs[0].shape == outs[256].shape == (30 * sr,)
+    assert stats[0]["shapes"] == 3 and stats[0]["batches"] == 3
+    assert stats[256]["shapes"] == 2 and stats[256]["batches"] == 2      # (2, 1280) + (1, 1280)
+    m = cases.metrics(torch.from_numpy(outs[256]), torch.from_numpy(outs[0]))
+    print(f"\n[bucketed vs exact shapes, fp32] max_abs={m['max_abs']:.3e} snr={m['snr_db']:.1f} dB")
+    assert m["max_abs"] <= 2e-5 and m["snr_db"] >= 80.0, m
 
 
 def test_stream_converter_with_the_model_matches_the_reference_loop():

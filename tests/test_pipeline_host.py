@@ -20,6 +20,31 @@ def test_batch_chunks_groups_equal_shapes():
     assert pl.batch_chunks([], 2) == []
 
 
+def test_batch_chunks_buckets_energy_split_plans():
+    """The reference moves every split point to the quietest sample within +-6 s (convert.py:406-412): on real audio no two chunks
+    share a length.  Buckets of 512 frames bring a 10-minute stream back to a handful of shapes and let unequal chunks share a batch."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    n = 600 * ch.SAMPLE_RATE
+    audio = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    spans = ch.chunk_spans(n, ch.split_points(audio))
+    assert len({c.frames for c in spans}) >= len(spans) - 2
+    exact = pl.batch_chunks(spans, 2)
+    assert len(exact) >= len(spans) - 2
+    groups = pl.batch_chunks(spans, 2, bucket=512)
+    assert sorted(c.index for g in groups for c in g) == list(range(len(spans)))
+    assert all(len({-(-c.frames // 512) for c in g}) == 1 and len(g) <= 2 for g in groups)
+    assert len(groups) < len(exact)
+    shapes = {(len(g), -(-g[0].frames // 512) * 512) for g in groups}
+    assert len(shapes) <= 8        # fits the engine's plan cache (8 most recently used shapes)
+    pad = sum(-(-g[0].frames // 512) * 512 * len(g) for g in groups) / sum(c.frames for c in spans)
+    assert pad < 1.12              # padded work stays within 12 % of the real frames
+
+
+def test_stream_converter_rejects_odd_bucket():
+    with pytest.raises((ValueError, RuntimeError)):
+        pl.StreamConverter(torch.nn.Linear(1, 1), 48000, 480, bucket=3)
+
+
 def test_piece_layout_covers_the_stream():
     for seconds in (10, 45, 600):
         n = seconds * ch.SAMPLE_RATE
