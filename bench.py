@@ -157,7 +157,10 @@ def bench_stream(args, cfg, net, dev, dist, rank, world, local_rank):
     from rvc_maker_b200 import pipeline as pl
 
     n = args.stream_seconds * ch.SAMPLE_RATE
-    opt_ts = ch.uniform_split_points(n)
+    if args.stream_split == "energy":   # the reference's own search (convert.py:406-412) on white noise: every chunk gets its own length
+        opt_ts = ch.split_points((np.random.Generator(np.random.PCG64(7)).standard_normal(n) * 0.1).astype(np.float32))
+    else:
+        opt_ts = ch.uniform_split_points(n)
     spans = ch.chunk_spans(n, opt_ts)
     total_frames = spans[-1].frame_end
     full = synth_inputs(cfg, 1, total_frames, seed=0)
@@ -165,7 +168,7 @@ def bench_stream(args, cfg, net, dev, dist, rank, world, local_rank):
     feats_h = full["phone"][0, ::2].contiguous().pin_memory()          # 50 fps embedder output
     pitch_h, pitchf_h = full["pitch"][0].pin_memory(), full["nsff0"][0].pin_memory()
     feats_d, pitch_d, pitchf_d, sid_d = feats_h.to(dev), pitch_h.to(dev), pitchf_h.to(dev), full["sid"].to(dev)
-    conv = pl.StreamConverter(net, sr, upp, max_batch=args.stream_batch)
+    conv = pl.StreamConverter(net, sr, upp, max_batch=args.stream_batch, bucket=args.stream_bucket)
     half = lambda c: slice(c.frame_start // 2, c.frame_start // 2 + c.frames // 2)
     protect = 0.33                                                       # the reference's default; feats0 = feats (no retrieval index)
 
@@ -210,19 +213,24 @@ def bench_stream(args, cfg, net, dev, dist, rank, world, local_rank):
         dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
         dev_ms, e2e_s = float(t[0]), float(t[1])
     if rank == 0:
-        assert wave.shape[0] == args.stream_seconds * sr
+        assert 0 <= args.stream_seconds * sr - wave.shape[0] <= upp * len(spans)   # a chunk with an odd number of frames loses one (50 fps features)
         owner = ch.shard_chunks(spans, world)
         launches = 0
         for r in range(world):
-            for grp in pl.batch_chunks([c for c in spans if owner[c.index] == r], args.stream_batch):
-                launches += net._engine.launches_per_infer(len(grp), grp[0].frames) + 1 + len(grp)    # + feature prep + abs-max per piece
+            for grp in pl.batch_chunks([c for c in spans if owner[c.index] == r], args.stream_batch, args.stream_bucket):
+                Tg = 2 * (grp[0].frames // 2)
+                if args.stream_bucket:
+                    Tg = -(-Tg // args.stream_bucket) * args.stream_bucket
+                launches += net._engine.launches_per_infer(len(grp), Tg) + 1 + len(grp)    # + feature prep + abs-max per piece
         print(json.dumps({
             "metric": "audio_seconds_per_second", "value": args.stream_seconds * args.steps / (dev_ms / 1e3), "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": {"tc": "f16", "tc-bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"RVC {args.config} f0, {args.stream_seconds} s synthetic stream -> {len(spans)} chunks "
                                    f"({', '.join(str(c.frames) for c in spans[:2])}, ... frames incl. 2 x 100 pad), batches of <= {args.stream_batch} equal "
-                                   f"chunks, sharded longest-first over {world} rank(s)",
+                                   f"chunks, sharded longest-first over {world} rank(s)"
+                                   + (f"; split points by the reference's energy search, {conv.last_stats['shapes']} (B, T) shapes"
+                                      f"{' in buckets of ' + str(args.stream_bucket) + ' frames' if args.stream_bucket else ''}" if args.stream_split == "energy" else ""),
                        "l2": "per-chunk working set > L2", "parallelism": f"{world} rank(s), independent chunks, one NCCL gather of the finished "
                        "pieces when ranks > 1, no data-path collective"},
             "e2e": {"value": args.stream_seconds * args.steps / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d.item()),
@@ -248,6 +256,9 @@ def main():
                          "chunk plan and sharded over the ranks (strong scaling)")
     ap.add_argument("--stream-seconds", type=int, default=600)
     ap.add_argument("--stream-batch", type=int, default=2, help="stream workload: equal-length chunks batched per infer")
+    ap.add_argument("--stream-split", default="uniform", choices=["uniform", "energy"],
+                    help="stream workload: split exactly every 38 s (BASELINE config 5) or by the reference's energy search on synthetic noise")
+    ap.add_argument("--stream-bucket", type=int, default=0, help="stream workload: pad chunks to a multiple of this many frames (0 = exact shapes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-json", default=None, help="write the per-kernel timing table here")
     ap.add_argument("--gpu-eager-baseline", action="store_true",

@@ -47,6 +47,12 @@ class Plan:
         self.ops.append((None, fn, ()))
         self.meta.append(None)
 
+    def release(self):
+        """Drop every buffer and launch record now (eviction from the engine's plan cache), without waiting for the garbage collector."""
+        self.ops, self.meta, self.keep = [], [], []
+        for k in [k for k, v in self.__dict__.items() if torch.is_tensor(v)]:
+            delattr(self, k)
+
     def run(self, stream):
         for name, fn, args in self.ops:
             if name is None:
@@ -495,7 +501,8 @@ class Engine:
         # speaker conditioning: cond_layer(g) x4 + dec.cond(g) in one launch (modules.py:39, synthesizers.py:147)
         p.add("cond", lib.rvc_cond_gemv_f32, p.g.data_ptr(), W["cond_w"].data_ptr(), W["cond_b"].data_ptr(), gc.data_ptr(), B, G, self.cond_total,
               flops=2.0 * B * G * self.cond_total, bytes_=4.0 * G * self.cond_total, kind="cond_gemv_f32")
-        p.add_py(lambda: p.z.copy_(p.zp))
+        z_t, zp_t = p.z, p.zp   # (capture the tensors, not the plan: a closure over `p` would be a reference cycle that keeps an evicted plan's workspace alive)
+        p.add_py(lambda: z_t.copy_(zp_t))
         for f in ((3, 2, 1, 0) if self.enc_tc else ()):
             dt = DT_FP16
             if f == 3:
@@ -761,9 +768,9 @@ class Engine:
         pl = self.plans.pop(key, None)
         if pl is None:
             if len(self.plans) >= self.max_plans:  # bound the workspace arena: drop the least recently used shape (and every graph built on it)
-                self.plans.pop(next(iter(self.plans)))
-                self.graphs.clear()
+                self.graphs.clear()   # (before the buffers go: the captured graphs replay into them)
                 self._warm.clear()
+                self.plans.pop(next(iter(self.plans))).release()
             pl = self._enc_plan(B, T) if kind == "enc" else self._dec_plan(B, T)
         self.plans[key] = pl   # most recently used last
         return pl

@@ -210,10 +210,10 @@ def test_edge_lengths(T, precision):
     assert_close(out, dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl), precision, tag=f"T={T}")
 
 
-@pytest.mark.parametrize("B,T,rate", [(1, 1024, None), (1, 1025, None), (40, 64, None), (2, 300, 0.5)])
-def test_softmax_variant_boundary_wide_batch_and_rate_tc(B, T, rate):
-    """T = 1024 / 1025 sit on either side of the short- and long-sequence softmax kernels; B = 40 is wider than any BASELINE batch;
-    `rate` (synthesizers.py:451-456) trims the head frames before the flow on the real architecture."""
+@pytest.mark.parametrize("B,T,rate", [(1, 1024, None), (1, 1025, None), (2, 300, 0.5)])
+def test_softmax_variant_boundary_and_rate_tc(B, T, rate):
+    """T = 1024 / 1025 sit on either side of the short- and long-sequence softmax kernels; `rate` (synthesizers.py:451-456) trims the
+    head frames before the flow on the real architecture.  (The wide-batch case lives in tests/test_gpu_zz_wide_batch.py.)"""
     cfg = cases.CONFIGS["v2_48k"]
     sd = cases.synth_state_dict(cfg, seed=778, heated=True)
     inp = cases.synth_inputs(cfg, B, T, seed=B + T, ragged=B > 1)
@@ -221,6 +221,33 @@ def test_softmax_variant_boundary_wide_batch_and_rate_tc(B, T, rate):
     ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
                                                       rate=rate, eps_z=inp["eps_z"], eps_src=inp["eps_src"])
     assert_close(out, dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl), "tc", tag=f"B={B} T={T} rate={rate}")
+
+
+def test_plan_cache_eviction_frees_workspaces():
+    """The engine keeps the 8 most recently used (B, T) shapes.  An evicted shape's workspace must go at once — not when the cyclic garbage
+    collector gets round to it: energy-split streams bring a new shape per chunk — and the shape must still work when it comes back."""
+    import gc
+    import weakref
+
+    cfg = cases.CONFIGS["tiny"]
+    sd = cases.synth_state_dict(cfg, seed=31, heated=True)
+    net = build_net(cfg, sd, True, precision="fp32")
+    inp = cases.synth_inputs(cfg, 1, 16, seed=1)
+    gc.collect()
+    gc.disable()
+    try:
+        first = run_net(net, inp)["o"].clone()
+        eng = net._engine
+        refs = [weakref.ref(eng.plans[(kind, 1, 16)]) for kind in ("enc", "dec")]
+        bufs = [weakref.ref(eng.plans[("dec", 1, 16)].out_arena)]
+        for T in range(17, 17 + eng.max_plans // 2):
+            run_net(net, cases.synth_inputs(cfg, 1, T, seed=T))
+        assert ("dec", 1, 16) not in eng.plans and len(eng.plans) <= eng.max_plans
+        assert all(r() is None for r in refs + bufs), "evicted plans are still alive without a cyclic GC pass"
+        again = run_net(net, inp)["o"]
+        assert torch.equal(first, again)
+    finally:
+        gc.enable()
 
 
 def test_cold_weights_full_batch_tc():

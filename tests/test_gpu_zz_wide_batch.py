@@ -1,0 +1,29 @@
+"""A batch wider than any BASELINE configuration (B = 40 ragged items of <= 64 frames) on the tensor-core kernel set.
+
+Kept in its own file, last in collection order, on purpose: this case passed in three isolated runs on B200 and failed once in the
+middle of a full-suite run (round 1, cause not found before the GPU budget ran out).  tools/poison_probe.py shows the case is
+bit-identical over eager / captured / replayed calls and unaffected by NaN-poisoning of the allocator's free blocks, with
+o max_abs 8.9e-4 (bar 1e-3), latents <= 6.6e-3 * max|ref| (bar 1e-2) and SNR >= 52.9 dB (bar 50) — so an uninitialised-workspace read
+is ruled out; a timing-dependent hazard at many small tiles is not.  DESIGN.md section 8 lists it as the first item of the next round.
+"""
+import pytest
+
+from oracle import cases, synth_oracle
+from test_gpu_parity import assert_close, build_net, run_net
+
+pytestmark = pytest.mark.gpu
+
+
+def test_wide_ragged_batch_tc():
+    B, T = 40, 64
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=778, heated=True)
+    inp = cases.synth_inputs(cfg, B, T, seed=B + T, ragged=True)
+    out = run_net(build_net(cfg, sd, True, precision="tc"), inp)
+    ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
+                                                      eps_z=inp["eps_z"], eps_src=inp["eps_src"])
+    ref = dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl)
+    for k in ("o", "z", "m_p", "logs_p"):
+        m = cases.metrics(out[k].float().cpu(), ref[k])
+        print(f"[B=40 T=64 tc] {k}: max_abs={m['max_abs']:.3e} (max|ref|={float(ref[k].abs().max()):.2f}) snr={m['snr_db']:.1f} dB")
+    assert_close(out, ref, "tc", tag="B=40 T=64")
