@@ -27,3 +27,21 @@ def test_wide_ragged_batch_tc():
         m = cases.metrics(out[k].float().cpu(), ref[k])
         print(f"[B=40 T=64 tc] {k}: max_abs={m['max_abs']:.3e} (max|ref|={float(ref[k].abs().max()):.2f}) snr={m['snr_db']:.1f} dB")
     assert_close(out, ref, "tc", tag="B=40 T=64")
+
+
+@pytest.mark.parametrize("cname,use_f0,B", [("v1_32k", True, 16), ("v2_40k", False, 32)])
+def test_baseline_batched_configs_full_size_tc(cname, use_f0, B):
+    """BASELINE configs[2] (v1-32k f0, 16 chunks) and configs[3] (v2-40k non-f0, 32 chunks) at their real size, T = 1000 frames per chunk,
+    ragged lengths, against the oracle.  Added at the end of round 1 without a GPU run of its own (the budget was spent): the smaller
+    batches of the same architectures are covered by test_gpu_parity.py, the throughput of these sizes by profiles/r1_2t_bench_*.json."""
+    cfg = cases.CONFIGS[cname]
+    sd = cases.synth_state_dict(cfg, use_f0=use_f0, seed=4321, heated=True)
+    inp = cases.synth_inputs(cfg, B, 1000, seed=B, ragged=True, use_f0=use_f0)
+    out = run_net(build_net(cfg, sd, use_f0, precision="tc"), inp)
+    ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
+                                                      eps_z=inp["eps_z"], eps_src=inp["eps_src"], use_f0=use_f0)
+    ref = dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl)
+    m = cases.metrics(out["o"].float().cpu(), ro)
+    print(f"[{cname} B={B} T=1000 tc] o: max_abs={m['max_abs']:.3e} snr={m['snr_db']:.1f} dB")
+    assert tuple(out["o"].shape) == (B, 1, 1000 * cases.upp_of(cfg))
+    assert_close(out, ref, "tc", tag=f"{cname} B={B}")
