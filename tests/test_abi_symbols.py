@@ -60,8 +60,18 @@ def lib_rows(L):
 
 
 def test_no_oracle_import_in_product():
-    pkg = os.path.join(ROOT, "rvc_maker_b200")
-    for fn in os.listdir(pkg):
-        if fn.endswith(".py"):
-            src = open(os.path.join(pkg, fn)).read()
-            assert "import oracle" not in src and "from oracle" not in src, fn
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and the baseline legs of bench.py may import it."""
+    for sub in ("rvc_maker_b200", "tools"):
+        pkg = os.path.join(ROOT, sub)
+        for fn in os.listdir(pkg):
+            if fn.endswith(".py"):
+                src = open(os.path.join(pkg, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src, (sub, fn)
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    # in bench.py the oracle may only appear inside cpu_baseline() / gpu_eager_baseline() (the reported baselines, `--impl reference` included)
+    import ast
+    for node in ast.parse(bench).body:
+        uses = "oracle" in (ast.get_source_segment(bench, node) or "") and any(
+            isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n) for n in ast.walk(node))
+        if uses:
+            assert isinstance(node, ast.FunctionDef) and node.name in ("cpu_baseline", "gpu_eager_baseline"), getattr(node, "name", node)
