@@ -287,21 +287,29 @@ class StreamConverter:
         return out
 
     def _gather(self, pieces, spans, owner, offs, lens, total, rank, world, short):
-        if short:
-            raise NotImplementedError("multi-rank stitching needs chunks whose features cover the pitch grid")
-        peak = gather_pieces(pieces, self._peak, spans, owner, offs, lens, rank, world, self._host, self.dev)
+        peak, total = gather_pieces(pieces, self._peak, spans, owner, offs, lens, rank, world, self._host, self.dev)
         torch.cuda.current_stream(self.dev).synchronize()
         if rank != 0:
             return None
-        return self._finish(pieces, spans, offs, lens, total, False, peak)
+        return self._finish(pieces, spans, offs, lens, total, False, peak)   # (already laid out back to back)
 
 
 def gather_pieces(pieces, peak, spans, owner, offs, lens, rank, world, host, device):
     """Every rank packs the pieces it owns into one buffer (+ its running peak as the last element); ONE ``dist.gather`` to rank 0
     (NCCL over NVLink for CUDA tensors; the only collective of the stream workload, after the data path); rank 0 copies each piece
-    to its offset in ``host`` and returns the global peak.  Device-agnostic so that the layout logic is testable under gloo."""
+    to its offset in ``host`` and returns ``(global peak, stream length)`` (``(None, None)`` elsewhere).  Pieces may be shorter than
+    planned (an embedder that returns fewer frames than the pitch grid, e.g. a chunk with an odd number of frames loses one,
+    convert.py:365-369): the ranks first agree on the actual lengths (one all-reduce of n_chunks integers) and the pieces are laid out
+    back to back, as the reference's ``np.concatenate`` does (:448).  Device-agnostic so that the layout logic is testable under gloo."""
     import torch.distributed as dist
 
+    act = torch.tensor([min(int(pieces[c.index].shape[0]), lens[c.index]) if owner[c.index] == rank else 0 for c in spans],
+                       dtype=torch.int64).to(device)
+    dist.all_reduce(act)
+    lens = [int(v) for v in act.tolist()]
+    offs = [0] * len(spans)
+    for i in range(1, len(spans)):
+        offs[i] = offs[i - 1] + lens[i - 1]
     per_rank = [sum(lens[c.index] for c in spans if owner[c.index] == r) for r in range(world)]
     cap = max(per_rank) + 1
     buf = torch.zeros(cap, device=device)
@@ -314,10 +322,10 @@ def gather_pieces(pieces, peak, spans, owner, offs, lens, rank, world, host, dev
     dst = [torch.empty(cap, device=device) for _ in range(world)] if rank == 0 else None
     dist.gather(buf, dst, dst=0)
     if rank != 0:
-        return None
+        return None, None
     cursor = [0] * world
     for c in spans:
         r = owner[c.index]
         host[offs[c.index]: offs[c.index] + lens[c.index]].copy_(dst[r][cursor[r]: cursor[r] + lens[c.index]], non_blocking=True)
         cursor[r] += lens[c.index]
-    return float(torch.stack([d[cap - 1] for d in dst]).max().item())
+    return float(torch.stack([d[cap - 1] for d in dst]).max().item()), sum(lens)
