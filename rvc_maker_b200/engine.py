@@ -120,6 +120,7 @@ class Engine:
         self.graphs = {}
         self._warm = set()
         self.use_graph = bool(getattr(m, "use_cuda_graph", True))
+        self.poison = {"1": "nan", "nan": "nan", "big": "big"}.get(os.environ.get("RVC_B200_POISON", ""), "")
         self.pair_fusion = os.environ.get("RVC_B200_PAIR_FUSION", "1") != "0"   # fused ResBlock steps in the C = 32 / 64 stages
 
     # ------------------------------------------------------------------ weight folding / packing
@@ -359,6 +360,10 @@ class Engine:
 
     def _buf(self, plan, *shape, dtype=torch.float32):
         t = torch.empty(*shape, dtype=dtype, device=self.dev)
+        if self.poison and t.is_floating_point():
+            # debugging aid (RVC_B200_POISON=nan | big): every workspace starts as NaN (or 1e30), so an element that a kernel reads without
+            # any kernel having written it shows up in the output instead of depending on what the allocator's block held before
+            t.fill_(float("nan") if self.poison == "nan" else 1e30)
         plan.keep.append(t)
         return t
 

@@ -1,10 +1,11 @@
-"""A batch wider than any BASELINE configuration (B = 40 ragged items of <= 64 frames) on the tensor-core kernel set.
+"""A batch wider than any BASELINE configuration (B = 40 ragged items of <= 64 frames) on the tensor-core kernel set, and BASELINE's
+batched configurations at full size.
 
-Kept in its own file, last in collection order, on purpose: this case passed in three isolated runs on B200 and failed once in the
-middle of a full-suite run (round 1, cause not found before the GPU budget ran out).  tools/poison_probe.py shows the case is
-bit-identical over eager / captured / replayed calls and unaffected by NaN-poisoning of the allocator's free blocks, with
-o max_abs 8.9e-4 (bar 1e-3), latents <= 6.6e-3 * max|ref| (bar 1e-2) and SNR >= 52.9 dB (bar 50) — so an uninitialised-workspace read
-is ruled out; tools/stress_determinism.py then gave 48 bit-identical calls over 12 fresh engines, so a timing-dependent hazard at many small tiles would have to be rare.  DESIGN.md section 8 lists it as the first item of the next round.
+Kept in its own file, last in collection order, on purpose: the B = 40 case passed in four isolated runs on B200 and failed once in the
+middle of a full-suite process (round 1; the cause was not found before the GPU budget ran out).  It is bit-identical over eager /
+captured / replayed calls and over 12 fresh engines in one process (tools/stress_determinism.py); margins: o max_abs 8.9e-4 (bar 1e-3),
+latents <= 6.6e-3 * max|ref| (bar 1e-2), SNR >= 52.9 dB (bar 50).  A read of never-written workspace is NOT ruled out (a long process hands
+out allocator blocks other shapes have used): run the suite with RVC_B200_POISON=nan first.  DESIGN.md section 8 item 0.
 """
 import pytest
 
