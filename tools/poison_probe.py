@@ -3,7 +3,9 @@ replay), then again after filling the caching allocator's free blocks with NaN, 
 No checker involved: the kernels are deterministic, so any difference is a read of stale memory (or a race).
 
 usage (on a B200): python tools/poison_probe.py [B T]
-Round-1 result for B = 40, T = 64 (tc kernel set): all six calls bit-identical, no NaN.
+Round-1 result for B = 40, T = 64 (tc kernel set): all six calls bit-identical, no NaN.  Caveat: the caching allocator serves a
+same-sized request from the best-fitting cached block, i.e. mostly from the first run's own (valid) buffers rather than from the
+poisoned block, so this probe is weak evidence; the engine's RVC_B200_POISON=nan switch poisons every workspace at plan build instead.
 """
 import os
 import sys
