@@ -187,7 +187,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             for (int jj = 0; jj < (p.sum_jobs ? p.njobs : 1); ++jj) {
             const rvc_tc_job& jb = p.jobs[p.sum_jobs ? jj : j];
             const int pad = jb.pad;
-            const int rows = TM + (jb.K - 1) * jb.dil;
+            const int row0 = PADL + lt * TM - pad;                           // >= 0 (host checks pad <= PADL)
+            // the last tile must not read past the chunk's Lp rows (ragged L, TM = 512, the extra tile of the transposed mode):
+            // rows of the stage that are not loaded only reach outputs the epilogue discards (lin >= L)
+            const int rows = min(TM + (jb.K - 1) * jb.dil, p.Lp - row0);
             for (int cs = 0; cs < p.ncs; ++cs) {
                 const int c0 = cs * p.ach;
                 const int nc = min(p.ach, p.nch - c0);
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 if (p.dbg & 4) { if (++ast == (uint32_t)p.nabuf) { ast = 0; aph ^= 1; } continue; }
                 const size_t a_bs = jb.a_bs ? (size_t)jb.a_bs : (size_t)p.nch * p.Lp * 16;
                 const uint8_t* asrc = reinterpret_cast<const uint8_t*>(jb.a) + (size_t)b * a_bs +
-                                      ((size_t)c0 * p.Lp + (size_t)(PADL + lt * TM - pad)) * 16;
+                                      ((size_t)c0 * p.Lp + (size_t)row0) * 16;
                 for (int c = lane; c < nc; c += 32)
                     tc::bulk_g2s(tc::smem_u32(a_smem + (size_t)ast * a_bytes + (size_t)c * p.rows_max * 16), asrc + (size_t)c * p.Lp * 16,
                                  (uint32_t)rows * 16, A_FULL(ast));

@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import threading
 
 import torch
 
@@ -37,6 +38,7 @@ class Plan:
         self.meta = []
         self.keep = []
         self.launches = 0
+        self.last_stream = None   # torch stream of the last use (plan build included): a use on another stream waits for it first
 
     def add(self, name, fn, *args, launches=1, flops=0.0, bytes_=0.0, kind="other"):
         self.ops.append((name, fn, args))
@@ -117,8 +119,9 @@ class Engine:
         self._fold(m)
         self.plans = {}
         self.max_plans = 16   # encoder + decoder plans of the 8 most recently used (B, T) shapes (a bucketed stream needs 3-6)
-        self.graphs = {}
+        self.graphs = {}          # (B, T, head) -> (CUDAGraph, plan keys it replays into), most recently used last
         self._warm = set()
+        self._lock = threading.RLock()   # infer() is serialised per engine: plans, workspaces and graphs are shared per (B, T)
         self.use_graph = bool(getattr(m, "use_cuda_graph", True))
         self.poison = {"1": "nan", "nan": "nan", "big": "big"}.get(os.environ.get("RVC_B200_POISON", ""), "")
         self.pair_fusion = os.environ.get("RVC_B200_PAIR_FUSION", "1") != "0"   # fused ResBlock steps in the C = 32 / 64 stages
@@ -353,18 +356,36 @@ class Engine:
     def _packed(self, plan, B, Cch, L):
         return self._zbuf(plan, B * Cch * int(self.lib.rvc_packed_rows(L)) * 2)
 
+    GUARD = 1 << 16   # poison mode: bytes of 0x7e (fp16 / bf16 / fp32 NaN-or-huge patterns) behind every workspace
+
+    def _alloc(self, plan, nbytes):
+        """Raw workspace bytes.  With RVC_B200_POISON set every workspace is followed by GUARD bytes of 0x7e, so a read past the end
+        of a buffer (or of a packed chunk's last rows) meets a NaN / 1e38 pattern instead of whatever the allocator placed there."""
+        if not self.poison:
+            t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.dev)
+            plan.keep.append(t)
+            return t
+        full = torch.empty(nbytes + self.GUARD, dtype=torch.uint8, device=self.dev)
+        full[nbytes:].fill_(0x7E)
+        plan.keep.append(full)
+        return full[:nbytes]
+
     def _zbuf(self, plan, nbytes):
-        t = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
-        plan.keep.append(t)
+        t = self._alloc(plan, nbytes)
+        t.zero_()
         return t
 
     def _buf(self, plan, *shape, dtype=torch.float32):
-        t = torch.empty(*shape, dtype=dtype, device=self.dev)
-        if self.poison and t.is_floating_point():
-            # debugging aid (RVC_B200_POISON=nan | big): every workspace starts as NaN (or 1e30), so an element that a kernel reads without
-            # any kernel having written it shows up in the output instead of depending on what the allocator's block held before
-            t.fill_(float("nan") if self.poison == "nan" else 1e30)
-        plan.keep.append(t)
+        n = int(math.prod(shape)) if shape else 1
+        t = self._alloc(plan, n * torch.empty((), dtype=dtype).element_size())[: n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+        if self.poison:
+            # debugging aid (RVC_B200_POISON=nan | big): every workspace starts as NaN (or 1e30) — integer / byte workspaces as 0x7e bytes
+            # (fp16 NaN) — so an element that a kernel reads without any kernel having written it shows up in the output instead of
+            # depending on what the allocator's block held before
+            if t.is_floating_point():
+                t.fill_(float("nan") if self.poison == "nan" else 1e30)
+            else:
+                t.view(torch.uint8).fill_(0x7E)
         return t
 
     # ------------------------------------------------------------------ plans
@@ -771,12 +792,19 @@ class Engine:
     def plan(self, kind, B, T):
         key = (kind, B, T)
         pl = self.plans.pop(key, None)
+        cur = torch.cuda.current_stream(self.dev) if self.dev.type == "cuda" else None
         if pl is None:
-            if len(self.plans) >= self.max_plans:  # bound the workspace arena: drop the least recently used shape (and every graph built on it)
-                self.graphs.clear()   # (before the buffers go: the captured graphs replay into them)
-                self._warm.clear()
-                self.plans.pop(next(iter(self.plans))).release()
+            if len(self.plans) >= self.max_plans:  # bound the workspace arena: drop the least recently used shape
+                old = next(iter(self.plans))
+                # ... and the graphs that replay into its buffers (before the buffers go); graphs of other shapes stay
+                for gk in [gk for gk, (_, pkeys) in self.graphs.items() if old in pkeys]:
+                    del self.graphs[gk]
+                    self._warm.discard(gk)
+                self.plans.pop(old).release()
             pl = self._enc_plan(B, T) if kind == "enc" else self._dec_plan(B, T)
+        elif pl.last_stream is not None and pl.last_stream != cur:
+            cur.wait_stream(pl.last_stream)   # workspaces are shared per shape: order this use behind the previous one
+        pl.last_stream = cur
         self.plans[key] = pl   # most recently used last
         return pl
 
@@ -808,7 +836,9 @@ class Engine:
         if sid is None:
             raise ValueError("sid is required")
         stream = torch.cuda.current_stream(self.dev).cuda_stream
-        with torch.cuda.device(self.dev):
+        # one infer at a time per engine (the reference's infer is stateless; here inputs, workspaces and graphs are persistent
+        # per shape), and a shape used on a new stream waits for its previous use (Engine.plan)
+        with self._lock, torch.cuda.device(self.dev):
             pe = self.plan("enc", B, T)
             pe.phone.copy_(phone, non_blocking=True)
             pe.lengths.copy_(phone_lengths, non_blocking=True)
@@ -839,15 +869,18 @@ class Engine:
             # the kernel sequence of a (B, T, head) shape is static: capture it once into a CUDA graph and replay it
             # (inputs / noise were copied into the plans' persistent buffers above; RNG draws stay outside the graph)
             key = (B, T, head)
-            gr = self.graphs.get(key) if self.use_graph else None
+            ent = self.graphs.pop(key, None) if self.use_graph else None
+            gr = ent[0] if ent is not None else None
             if self.use_graph and gr is None and key in self._warm:
                 if len(self.graphs) >= self.max_plans // 2:
-                    self.graphs.pop(next(iter(self.graphs)))
+                    self.graphs.pop(next(iter(self.graphs)))   # least recently replayed
                 gr = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize(self.dev)
                 with torch.cuda.graph(gr):
                     body(torch.cuda.current_stream(self.dev).cuda_stream)
-                self.graphs[key] = gr
+                ent = (gr, (("enc", B, T), ("dec", B, T2)))
+            if ent is not None:
+                self.graphs[key] = ent   # most recently used last
             if gr is not None:
                 gr.replay()
             else:

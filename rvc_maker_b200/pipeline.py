@@ -225,8 +225,19 @@ class StreamConverter:
         self._peak.zero_()
         self.h2d.wait_stream(comp)
         self.d2h.wait_stream(comp)
-        pieces, keep, short, h2d_bytes, shapes = {}, [], False, 0, set()
         staged = self._stage(groups[0], embed, pitch, pitchf, sid) if groups else None
+        prev_noise = getattr(self.net, "_noise_override", None)
+        try:
+            return self._convert_groups(groups, staged, embed, pitch, pitchf, sid, protect, noise_fn, comp, st, t_pad_tgt, lens, offs, total,
+                                        spans, owner, rank, world, to_host)
+        finally:
+            # the pinned draws belong to this call only: later infer()/convert() calls draw fresh noise again, as the reference does
+            if noise_fn is not None:
+                self.net._noise_override = prev_noise
+
+    def _convert_groups(self, groups, staged, embed, pitch, pitchf, sid, protect, noise_fn, comp, st, t_pad_tgt, lens, offs, total, spans, owner,
+                        rank, world, to_host):
+        pieces, keep, short, h2d_bytes, shapes = {}, [], False, 0, set()
         for gi, group in enumerate(groups):
             cur = staged
             comp.wait_event(cur["ev"])
