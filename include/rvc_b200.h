@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 21
+#define RVC_ABI_VERSION 22
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -200,6 +200,9 @@ typedef struct {
     const float* nz_har; const float* nz_w; const float* nz_b;
     int64_t nz_har_bs;
     int32_t nz_kn, nz_sn, nz_pn, reserved2;
+    /* optional second packed output next to y_act (fp16 only): y_lo = fp16(leaky_relu(v, act_slope) - float(y_act)), the low half of
+     * the split-fp16 residual stream the fused ResBlock steps read (rvc_pair_job.a_lo) */
+    void* y_lo;
 } rvc_tc_job;
 /*
  * up > 1 selects the ConvTranspose1d phase mode (GeneratorNSF.ups, synthesizers.py:133,156): the packed weights hold `up`
@@ -235,6 +238,13 @@ typedef struct {
     const void* w2; const float* b2;
     const float* res; float* y; void* y_act;
     int32_t K1, dil1, K2, reserved;
+    /* Split-fp16 residual stream (fp16 only; optional, both NULL = the fp32 streams above).  The stream carries y = lrelu(x) as TWO
+     * packed fp16 planes, hi = fp16(y) — which IS the conv operand `a` — and lo = fp16(y - hi): 22 significant bits in 4 bytes,
+     * against 4 (fp32 x) + 2 (packed operand) bytes.  a_lo != NULL: the residual is x = inv_lrelu(float(a) + float(a_lo)) and `res`
+     * is ignored;  y_lo != NULL: the result is written as y_act = fp16(lrelu(x')) and y_lo = fp16(lrelu(x') - float(y_act)) and `y`
+     * is ignored (plain mode; in sum mode the average still leaves through y / y_act).  A step then moves 8 bytes per element
+     * instead of 12; |x - x_fp32| <= 2^-22 |y| + 3e-8 (the lo plane's subnormal spacing), slope > 0 required. */
+    const void* a_lo; void* y_lo;
 } rvc_pair_job;
 typedef struct {
     rvc_pair_job jobs[3];

@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 21
+ABI_VERSION = 22
 DT_BF16, DT_FP16 = 0, 2
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -61,6 +61,7 @@ class TcJob(C.Structure):
         ("a_bs", _i64), ("w_bs", _i64), ("y_act_bs", _i64),
         ("w_cs", _i32), ("reserved", _i32),
         ("nz_har", _vp), ("nz_w", _vp), ("nz_b", _vp), ("nz_har_bs", _i64), ("nz_kn", _i32), ("nz_sn", _i32), ("nz_pn", _i32), ("reserved2", _i32),
+        ("y_lo", _vp),
     ]
 
 
@@ -72,7 +73,7 @@ class Conv1dTcDesc(C.Structure):
 class PairJob(C.Structure):
     """rvc_pair_job (include/rvc_b200.h)."""
     _fields_ = [("a", _vp), ("w1", _vp), ("b1", _vp), ("w2", _vp), ("b2", _vp), ("res", _vp), ("y", _vp), ("y_act", _vp),
-                ("K1", _i32), ("dil1", _i32), ("K2", _i32), ("reserved", _i32)]
+                ("K1", _i32), ("dil1", _i32), ("K2", _i32), ("reserved", _i32), ("a_lo", _vp), ("y_lo", _vp)]
 
 
 class ResblockPairDesc(C.Structure):

@@ -518,6 +518,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                         pk.z = pack2(lrelu_max(v[8 * u + 4], sl), lrelu_max(v[8 * u + 5], sl), p.fp16);
                         pk.w = pack2(lrelu_max(v[8 * u + 6], sl), lrelu_max(v[8 * u + 7], sl), p.fp16);
                         *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp_out * 16) = pk;
+                        if (jb.y_lo) {   // low half of the split-fp16 residual stream: fp16(value - float(hi))  (fp16 launches only)
+                            const uint32_t hw[4] = {pk.x, pk.y, pk.z, pk.w};
+                            uint32_t lw[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+                                lw[i] = pack2(lrelu_max(v[8 * u + 2 * i], sl) - hf.x, lrelu_max(v[8 * u + 2 * i + 1], sl) - hf.y, 1);
+                            }
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(jb.y_lo) + (yb - reinterpret_cast<uint8_t*>(jb.y_act)) + (size_t)u * p.Lp_out * 16) =
+                                make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
                     }
                 }
             }
@@ -678,6 +689,8 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
         if ((jb.gated ? 1 : 0) != gated) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: jobs of one launch must agree on `gated`");
         if (jb.gated && !jb.bias) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: gated job needs a bias");
         if (!(jb.act_slope >= 0.f && jb.act_slope <= 1.f)) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: act_slope must be in [0, 1]");
+        if (jb.y_lo && (!jb.y_act || d.dtype != RVC_DT_FP16 || ((uintptr_t)jb.y_lo & 15)))
+            return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: y_lo goes with y_act, fp16 operands and 16-byte alignment");
         if (jb.nz_har) {
             if (j != 0 || d.sum_jobs || gated || jb.res) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: the fused noise conv belongs to job 0, replaces res, and excludes sum_jobs / gated");
             if (!jb.nz_w || jb.nz_kn < 1 || jb.nz_kn > 4 || jb.nz_sn < 1 || jb.nz_pn < 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: fused noise conv needs 1 <= kn <= 4, sn >= 1, pn >= 0");

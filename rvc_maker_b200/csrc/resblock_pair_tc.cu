@@ -45,7 +45,8 @@ struct PParams {
     int sum_jobs;                    // every tile runs ALL jobs; conv2 of all jobs accumulates into one tile (stage average)
     int y_ncl;                       // sum mode: y is plain [B, C, L] instead of channel-blocked
     int dbg;                         // timing experiments only: 1 = no MMA issue, 2 = no epilogue-2 global I/O, 4 = no residual loads
-    float slope, alpha;
+    int split_in, split_out;         // split-fp16 residual stream: residual = inv_lrelu(a + a_lo);  outputs y_act (hi) + y_lo
+    float slope, alpha, inv_slope;
 };
 
 __device__ __forceinline__ uint32_t pack2h(float a, float b, int fp16) {
@@ -55,6 +56,14 @@ __device__ __forceinline__ uint32_t pack2h(float a, float b, int fp16) {
     return r;
 }
 __device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
+// inverse of leaky_relu for 0 < slope <= 1 (inv = 1 / slope >= 1): y > 0 -> y, y < 0 -> y / slope
+__device__ __forceinline__ float lrelu_inv(float y, float inv) { return fminf(y, y * inv); }
+__device__ __forceinline__ float2 h2f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 
 // MT = 128-row sub-tiles per tile: 2, or 4 for C = 32 where TMEM holds twice the rows and the per-tile handshakes (about 2.3 us
 // of barrier round trips per tile with no MMA and no stores at all) were the bound rather than HBM
@@ -296,6 +305,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 const int r2 = m * BM + q * 32 + lane;
                 const int l = l02 + r2;
                 if (!(r2 < p.tmo[j2] && l < p.L) || (p.dbg & 6)) return;
+                if (p.split_in) {
+                    // split-fp16 stream: hi (= the conv operand plane, usually still in L2 from this tile's activation load) + lo
+                    const size_t poff = ((size_t)b2 * NCH + (size_t)(cb * (EB / 8))) * p.Lp + PADL + l;     // 16-byte units
+                    if (!p.sum_jobs) {   // raw bits now, decoded when the item is processed: the loads stay in flight meanwhile
+                        const uint4* ah = reinterpret_cast<const uint4*>(jb2.a) + poff;
+                        const uint4* al = reinterpret_cast<const uint4*>(jb2.a_lo) + poff;
+#pragma unroll
+                        for (int u = 0; u < EB / 8; ++u) {
+                            const uint4 h = ldg128(ah + (size_t)u * p.Lp), lo = ldg128(al + (size_t)u * p.Lp);
+                            dst[8 * u + 0] = __uint_as_float(h.x); dst[8 * u + 1] = __uint_as_float(h.y);
+                            dst[8 * u + 2] = __uint_as_float(h.z); dst[8 * u + 3] = __uint_as_float(h.w);
+                            dst[8 * u + 4] = __uint_as_float(lo.x); dst[8 * u + 5] = __uint_as_float(lo.y);
+                            dst[8 * u + 6] = __uint_as_float(lo.z); dst[8 * u + 7] = __uint_as_float(lo.w);
+                        }
+                    } else {             // stage average: x_0 + x_1 + x_2, all six loads of a chunk in flight before the first add
+                        const int j1i = 1 < p.njobs ? 1 : 0, j2i = 2 < p.njobs ? 2 : 0;
+                        const float s1 = p.njobs > 1 ? 1.f : 0.f, s2 = p.njobs > 2 ? 1.f : 0.f;
+                        const float inv = p.inv_slope;
+#pragma unroll
+                        for (int u = 0; u < EB / 8; ++u) {
+                            const size_t o = poff + (size_t)u * p.Lp;
+                            const uint4 h0 = ldg128(reinterpret_cast<const uint4*>(p.jobs[0].a) + o), l0 = ldg128(reinterpret_cast<const uint4*>(p.jobs[0].a_lo) + o);
+                            const uint4 h1 = ldg128(reinterpret_cast<const uint4*>(p.jobs[j1i].a) + o), l1 = ldg128(reinterpret_cast<const uint4*>(p.jobs[j1i].a_lo) + o);
+                            const uint4 h2 = ldg128(reinterpret_cast<const uint4*>(p.jobs[j2i].a) + o), l2 = ldg128(reinterpret_cast<const uint4*>(p.jobs[j2i].a_lo) + o);
+                            const uint32_t hw0[4] = {h0.x, h0.y, h0.z, h0.w}, lw0[4] = {l0.x, l0.y, l0.z, l0.w};
+                            const uint32_t hw1[4] = {h1.x, h1.y, h1.z, h1.w}, lw1[4] = {l1.x, l1.y, l1.z, l1.w};
+                            const uint32_t hw2[4] = {h2.x, h2.y, h2.z, h2.w}, lw2[4] = {l2.x, l2.y, l2.z, l2.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 a0 = h2f2(hw0[i]), b0 = h2f2(lw0[i]), a1 = h2f2(hw1[i]), b1_ = h2f2(lw1[i]), a2 = h2f2(hw2[i]), b2_ = h2f2(lw2[i]);
+                                dst[8 * u + 2 * i] = (lrelu_inv(a0.x + b0.x, inv) + s1 * lrelu_inv(a1.x + b1_.x, inv)) + s2 * lrelu_inv(a2.x + b2_.x, inv);
+                                dst[8 * u + 2 * i + 1] = (lrelu_inv(a0.y + b0.y, inv) + s1 * lrelu_inv(a1.y + b1_.y, inv)) + s2 * lrelu_inv(a2.y + b2_.y, inv);
+                            }
+                        }
+                    }
+                    return;
+                }
                 const size_t off = (size_t)b2 * C * p.L + (size_t)(cb * (EB / 8)) * cs + (size_t)l * 8;
 #pragma unroll
                 for (int u = 0; u < EB / 8; ++u) tc::ldg256(jb2.res + off + (size_t)u * cs, dst + 8 * u);
@@ -374,6 +420,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                     tc::tmem_ld<EB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * MT * C + (g * MT + m) * C + cb * EB), r);
                     tc::tmem_ld_wait();
                     if (!ok) continue;
+                    if (p.split_in && !p.sum_jobs) {   // raw hi / lo words -> x = inv_lrelu(hi + lo)
+                        const float inv = p.inv_slope;
+#pragma unroll
+                        for (int u = 0; u < EB / 8; ++u) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[8 * u + i]);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 h = h2f2(w[i]), lo = h2f2(w[4 + i]);
+                                v[8 * u + 2 * i] = lrelu_inv(h.x + lo.x, inv);
+                                v[8 * u + 2 * i + 1] = lrelu_inv(h.y + lo.y, inv);
+                            }
+                        }
+                    }
                     const float4* bs4 = reinterpret_cast<const float4*>(bias_s + (j2 * 2 + 1) * C + cb * EB);
 #pragma unroll
                     for (int i4 = 0; i4 < EB / 4; ++i4) {
@@ -398,7 +459,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                             for (int u = 0; u < EB / 8; ++u) tc::stg256(yp + (size_t)u * cs, v + 8 * u);
                         }
                     }
-                    if (jb2.y_act) {
+                    if (p.split_out) {
+                        // split-fp16 stream out: hi = fp16(lrelu(x')) (the next conv1's operand), lo = fp16(lrelu(x') - hi)
+                        const size_t poff = ((size_t)b2 * NCH * p.Lp + ((size_t)cb * (EB / 8)) * p.Lp + PADL + l) * 16;
+                        uint8_t* yh = reinterpret_cast<uint8_t*>(jb2.y_act) + poff;
+                        uint8_t* yl = reinterpret_cast<uint8_t*>(jb2.y_lo) + poff;
+#pragma unroll
+                        for (int u = 0; u < EB / 8; ++u) {
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float f0 = lrelu_max(v[8 * u + 2 * i], p.slope), f1 = lrelu_max(v[8 * u + 2 * i + 1], p.slope);
+                                hw[i] = pack2h(f0, f1, 1);
+                                const float2 hf = h2f2(hw[i]);
+                                lw[i] = pack2h(f0 - hf.x, f1 - hf.y, 1);
+                            }
+                            *reinterpret_cast<uint4*>(yh + (size_t)u * p.Lp * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            *reinterpret_cast<uint4*>(yl + (size_t)u * p.Lp * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
+                    } else if (jb2.y_act) {
                         uint8_t* yb = reinterpret_cast<uint8_t*>(jb2.y_act) + (size_t)b2 * NCH * p.Lp * 16 + (((size_t)cb * (EB / 8)) * p.Lp + PADL + l) * 16;
 #pragma unroll
                         for (int u = 0; u < EB / 8; ++u) {
@@ -476,13 +555,24 @@ RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream)
     p.njobs = d.njobs; p.B = d.B; p.C = d.C; p.L = d.L; p.Lp = packed_rows(d.L); p.fp16 = d.dtype == RVC_DT_FP16; p.slope = d.slope;
     p.sum_jobs = d.sum_jobs ? 1 : 0; p.y_ncl = d.y_ncl ? 1 : 0; p.alpha = d.sum_jobs ? d.alpha : 1.f;
     p.dbg = d.reserved;
+    p.split_in = d.jobs[0].a_lo != nullptr;
+    p.split_out = !d.sum_jobs && d.jobs[0].y_lo != nullptr;
+    p.inv_slope = d.slope > 0.f ? 1.f / d.slope : 1.f;
     int halo1 = 0, k2max = 1;
     long total = 0;
     for (int j = 0; j < d.njobs; ++j) {
         const rvc_pair_job& jb = d.jobs[j];
         const bool outs = !d.sum_jobs || j == 0;      // the stage average writes through job 0 only
-        if (!jb.a || !jb.w1 || !jb.w2 || !jb.res) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d has a null pointer", j);
-        if (!d.sum_jobs && (!jb.y || !jb.y_act)) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d needs y and y_act", j);
+        if (!jb.a || !jb.w1 || !jb.w2 || !(jb.res || jb.a_lo)) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d has a null pointer", j);
+        if ((jb.a_lo != nullptr) != (d.jobs[0].a_lo != nullptr) || (!d.sum_jobs && (jb.y_lo != nullptr) != (d.jobs[0].y_lo != nullptr)))
+            return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: the jobs of one launch must agree on the split-fp16 stream (a_lo / y_lo)");
+        if ((jb.a_lo || (!d.sum_jobs && jb.y_lo)) && (d.dtype != RVC_DT_FP16 || !(d.slope > 0.f)))
+            return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: the split-fp16 stream needs dtype = RVC_DT_FP16 and slope > 0");
+        if (!d.sum_jobs && (!(jb.y || jb.y_lo) || !jb.y_act)) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d needs y_act and y (or y_lo)", j);
+        // (y_lo may alias a_lo: the lo plane is read only at a tile's own output rows, by the thread that rewrites them)
+        if (outs && !d.sum_jobs && jb.y_lo && ((uintptr_t)jb.y_lo & 15))
+            return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: y_lo must be 16-byte aligned", j);
+        if (jb.a_lo && ((uintptr_t)jb.a_lo & 15)) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: a_lo needs 16-byte alignment", j);
         if (d.sum_jobs && j == 0 && !jb.y && !jb.y_act) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: sum_jobs needs y or y_act on job 0");
         if (outs && jb.a == jb.y_act)
             return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: y_act must not alias a (tiles read a with halos while others write y_act)", j);

@@ -125,6 +125,9 @@ class Engine:
         self.use_graph = bool(getattr(m, "use_cuda_graph", True))
         self.poison = {"1": "nan", "nan": "nan", "big": "big"}.get(os.environ.get("RVC_B200_POISON", ""), "")
         self.pair_fusion = os.environ.get("RVC_B200_PAIR_FUSION", "1") != "0"   # fused ResBlock steps in the C = 32 / 64 stages
+        # ... with the residual stream of those stages carried as two packed fp16 planes (hi = the conv operand, lo = the rounding
+        # remainder: 22 bits in 4 bytes) instead of fp32 + a packed operand copy: 8 instead of 12 bytes per element and step
+        self.pair_split = os.environ.get("RVC_B200_PAIR_SPLIT", "1") != "0"
 
     # ------------------------------------------------------------------ weight folding / packing
     def _fold(self, m):
@@ -337,6 +340,8 @@ class Engine:
                 jb.y_f32, jb.y_bs, jb.y_cs = j["y"].ptr, j["y"].bs, j["y"].cs
             if j.get("y_act") is not None:
                 jb.y_act = j["y_act"] if isinstance(j["y_act"], int) else j["y_act"].data_ptr()
+            if j.get("y_lo") is not None:
+                jb.y_lo = j["y_lo"].data_ptr()
             jb.K, jb.dil = j.get("K", 1), j.get("dil", 1)
             jb.pad = j.get("pad", (jb.K - 1) // 2 * jb.dil)
             jb.gated, jb.relu = int(j.get("gated", False)), int(j.get("relu", 0))
@@ -347,7 +352,7 @@ class Engine:
                 jb.nz_kn, jb.nz_sn, jb.nz_pn = j["nz_kn"], j["nz_sn"], j["nz_pn"]
             ce = Cout // 2 if jb.gated else Cout
             fl += 2.0 * B * Cin * Cout * jb.K * L
-            by += B * L * (2.0 * Cin + up * ce * (4.0 * (j.get("res") is not None) + 4.0 * (j.get("y") is not None) + 2.0 * (j.get("y_act") is not None)))
+            by += B * L * (2.0 * Cin + up * ce * (4.0 * (j.get("res") is not None) + 4.0 * (j.get("y") is not None) + 2.0 * (j.get("y_act") is not None) + 2.0 * (j.get("y_lo") is not None)))
         plan.keep.append(d)
         plan.keep.append(jobs)
         plan.add(name, self.lib.rvc_conv1d_tc, C.byref(d), flops=fl if flops is None else flops, bytes_=by,
@@ -615,6 +620,7 @@ class Engine:
             blk = self.up_dt[i] is not None and dt is not None and dt == self.up_dt[i] and Ci % 8 == 0
             if blk:
                 vs0 = V(S[0], Ci, Li, cs=8 * Li)
+            split, x_lo = False, None
             if self.up_dt[i] is not None:
                 # ---- ConvTranspose1d on tensor cores: u phase GEMMs; the noise conv result is the epilogue's residual input
                 udt = self.up_dt[i]
@@ -637,11 +643,14 @@ class Engine:
                           kind="noise_conv_f32")
                 if dt is not None and dt == udt:
                     xa = self._packed(p, B, Ci, Li)
+                # narrow fused stages: the stage input leaves the ups as the split-fp16 stream (xa = hi, x_lo), no fp32 copy
+                split = blk and Ci in (32, 64) and self.pair_fusion and self.pair_split and dt == DT_FP16 and xa is not None
+                x_lo = self._buf(p, xa.numel(), dtype=torch.uint8) if split else None
                 M = -(-k // u)
                 nz = dict(nz_har=har.data_ptr(), nz_w=W[f"nz_w{i}"].data_ptr(), nz_b=W[f"nz_b{i}"].data_ptr(), nz_har_bs=Lfin, nz_kn=kn, nz_sn=sn,
                           nz_pn=pn) if nz_fused else {}
-                self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(vs0 if c["f0"] and not nz_fused else None), y=vs0, y_act=xa,
-                                             act_slope=LRELU_SLOPE, K=M, pad=M - 1, **nz)],
+                self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(vs0 if c["f0"] and not nz_fused else None),
+                                             y=(None if split else vs0), y_act=xa, y_lo=x_lo, act_slope=LRELU_SLOPE, K=M, pad=M - 1, **nz)],
                          B=B, Cin=curC, Cout=Ci, L=curL, dtype=udt, up=u, pshift=(k - u) // 2, tag=f"ups",
                          flops=2.0 * B * curC * Ci * k * curL, blocked=3 if blk else 0)
             else:
@@ -704,6 +713,8 @@ class Engine:
                 # stays in shared memory, rvc_resblock_pair_tc) for every step but the last, whose conv2 is the fused stage average
                 use_pair = blk and Ci in (32, 64) and self.pair_fusion
                 src_a = {j: xa for j in range(nk)}     # packed lrelu(x_j) read by the next conv1
+                # split-fp16 stream: lo plane of each block's stream (step 0 reads the shared x_lo; later steps update lo[j] in place)
+                lo_j = [self._buf(p, xa.numel(), dtype=torch.uint8) for _ in range(nk)] if (use_pair and split) else None
                 t_of = {}
                 for mm in range(nsteps):
                     last = mm == nsteps - 1
@@ -720,19 +731,27 @@ class Engine:
                             pj.a = src_a[j].data_ptr()
                             pj.w1, pj.b1 = W[f"rb{i}_{j}_c1w{mm}"].data_ptr(), W[f"rb{i}_{j}_c1b{mm}"].data_ptr()
                             pj.w2, pj.b2 = W[f"rb{i}_{j}_c2w{mm}"].data_ptr(), W[f"rb{i}_{j}_c2b{mm}"].data_ptr()
-                            pj.res = (S[0] if mm == 0 else P[j]).data_ptr()
+                            if split:
+                                pj.a_lo = (x_lo if mm == 0 else lo_j[j]).data_ptr()
+                            else:
+                                pj.res = (S[0] if mm == 0 else P[j]).data_ptr()
                             pj.K1, pj.dil1, pj.K2 = kk, rds[j][mm], kk
                             if not last:
                                 dst_a = pa[j] if src_a[j] is not pa[j] else ta[j]     # ping-pong: tiles read `a` with halos while others write y_act
-                                pj.y, pj.y_act = P[j].data_ptr(), dst_a.data_ptr()
+                                pj.y_act = dst_a.data_ptr()
+                                if split:
+                                    pj.y_lo = lo_j[j].data_ptr()
+                                else:
+                                    pj.y = P[j].data_ptr()
                                 src_a[j] = dst_a
                             elif slot == 0:
                                 pj.y = avg.data_ptr() if need_f32 else None
                                 pj.y_act = next_ua.data_ptr() if next_ua is not None else None
                             fl += 4.0 * B * Ci * Ci * kk * Li
                         p.keep.append(pd)
-                        by = nk * B * Ci * Li * (esz + 8.0 + esz) if not last else \
-                            B * Ci * Li * (nk * (esz + 4.0) + (4.0 if need_f32 else 0.0) + (esz if next_ua is not None else 0.0))
+                        rbytes = 2.0 * esz if split else 4.0      # residual stream: hi (the operand itself, re-read through L2) + lo | fp32
+                        by = nk * B * Ci * Li * (esz + 2 * rbytes - (esz if split else 0.0) + (0.0 if split else esz)) if not last else \
+                            B * Ci * Li * (nk * (esz + rbytes - (esz if split else 0.0)) + (4.0 if need_f32 else 0.0) + (esz if next_ua is not None else 0.0))
                         p.add(f"rbpair{i}_s{mm}", lib.rvc_resblock_pair_tc, C.byref(pd), flops=fl, bytes_=by,
                               kind=f"resblock_pair_tc_{'bf16' if dt == DT_BF16 else 'fp16'}[C{Ci}]")
                         continue

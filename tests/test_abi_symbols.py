@@ -34,22 +34,30 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.rvc_abi_version() == 21
+    assert lib.rvc_abi_version() == 22
     # argument validation happens before any CUDA call, so it is checkable without a GPU
     rc = lib.rvc_conv1d_f32(None, None)
     assert rc == -1
     assert b"null descriptor" in lib.rvc_last_error()
 
 
-def test_desc_struct_layout_matches_header():
-    """ctypes struct sizes must equal the C structs (LP64, natural alignment): computed from the header field list."""
-    from rvc_maker_b200._lib import Conv1dDesc, ConvTr1dDesc
+def test_desc_struct_layout_matches_header(tmp_path):
+    """ctypes struct sizes must equal the C structs: sizeof() as gcc sees include/rvc_b200.h (plain C, LP64) against the ctypes mirrors."""
+    import subprocess
 
-    assert ctypes.sizeof(Conv1dDesc) == 176
-    assert ctypes.sizeof(ConvTr1dDesc) == 160
-    from rvc_maker_b200._lib import Conv1dTcDesc, TcJob
+    from rvc_maker_b200._lib import Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc, PairJob, ResblockPairDesc, TcJob
 
-    assert ctypes.sizeof(TcJob) == 216 and ctypes.sizeof(Conv1dTcDesc) == 696
+    pairs = [("rvc_conv1d_desc", Conv1dDesc), ("rvc_convtr1d_desc", ConvTr1dDesc), ("rvc_tc_job", TcJob), ("rvc_conv1d_tc_desc", Conv1dTcDesc),
+             ("rvc_pair_job", PairJob), ("rvc_resblock_pair_desc", ResblockPairDesc)]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "rvc_b200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("%zu\\n", sizeof({c}));\n' for c, _ in pairs) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    for (cname, ct), sz in zip(pairs, sizes):
+        assert ctypes.sizeof(ct) == sz, (cname, ctypes.sizeof(ct), sz)
+    assert ctypes.sizeof(TcJob) == 224 and ctypes.sizeof(PairJob) == 96
     assert lib_rows(1000) == 64 + 1024 + 64
 
 

@@ -573,3 +573,152 @@ def test_fused_noise_conv_in_ups_epilogue(Cin, Cout, k, u, Lin, sn):
     ref = F.conv_transpose1d(rnd(F.leaky_relu(x, 0.1), dtype).double(), rnd(w, dtype).double(), bias.double(), stride=u, padding=(k - u) // 2) \
         + F.conv1d(har.unsqueeze(1).double(), nzw.double(), nzb.double(), stride=sn, padding=pn)
     assert float((from_blocked(outs[1][0]).double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------ split-fp16 residual stream
+def pack_host(t, rows):
+    """fp32 [B, C, L] -> packed fp16 plane [B][C/8][rows][8] (position l at row 64 + l, other rows zero) as uint8 on the device."""
+    B, C_, L = t.shape
+    out = torch.zeros(B, C_ // 8, rows, 8, dtype=torch.float16)
+    out[:, :, 64:64 + L, :] = t.view(B, C_ // 8, 8, L).permute(0, 1, 3, 2).to(torch.float16)
+    return out.view(torch.uint8).reshape(-1).to(DEV)
+
+
+def split_planes(x, rows, slope=0.1):
+    """the stream's two planes for a residual value x: hi = fp16(lrelu(x)), lo = fp16(lrelu(x) - hi); and the x they decode to"""
+    y = F.leaky_relu(x, slope)
+    hi = y.to(torch.float16).float()
+    lo = (y - hi).to(torch.float16).float()
+    s = hi + lo
+    return pack_host(hi, rows), pack_host(lo, rows), torch.minimum(s, s * (1.0 / torch.tensor(slope, dtype=torch.float32)))
+
+
+def decode_split(hi_buf, lo_buf, B, C_, L, rows, slope=0.1):
+    s = unpack(hi_buf, B, C_, L, FP16, rows) + unpack(lo_buf, B, C_, L, FP16, rows)
+    return torch.minimum(s, s * (1.0 / torch.tensor(slope, dtype=torch.float32, device=s.device)))
+
+
+@pytest.mark.parametrize("Cc,L,B", [(64, 3001, 2), (32, 20000, 1), (64, 246, 1), (32, 1, 1), (32, 777, 3)])
+def test_fused_resblock_pair_split_stream(Cc, L, B):
+    """Split-fp16 residual stream (rvc_pair_job.a_lo / y_lo): same step as the fp32-stream launch on the value the two planes decode to.
+    conv results are bit-identical (same operand plane), so the two x' differ only by the output split: <= 2^-21 |lrelu(x')| + 1e-7."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(77 + Cc + L)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(L)
+    n = B * Cc * rows * 2
+    pd_s, pd_f = _lib.ResblockPairDesc(), _lib.ResblockPairDesc()
+    for pd in (pd_s, pd_f):
+        pd.njobs, pd.B, pd.C, pd.L, pd.dtype, pd.slope = 3, B, Cc, L, FP16, 0.1
+    keep, outs = [], []
+    for j, (k, dil) in enumerate(((11, 5), (7, 3), (3, 1))):
+        x = 2.0 * torch.randn(B, Cc, L, generator=g)
+        hi, lo, xdec = split_planes(x, rows)
+        w1 = (torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+        w2 = (torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+        b1, b2 = torch.randn(Cc, generator=g).to(DEV), torch.randn(Cc, generator=g).to(DEV)
+        w1p, w2p = torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV), torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+        _lib.check(lib.rvc_pack_weight(w1.data_ptr(), w1p.data_ptr(), Cc, Cc, k, FP16, st), "pack_weight")
+        _lib.check(lib.rvc_pack_weight(w2.data_ptr(), w2p.data_ptr(), Cc, Cc, k, FP16, st), "pack_weight")
+        xb = to_blocked(xdec.to(DEV))
+        y_f, ya_f = torch.zeros_like(xb), torch.zeros(n, dtype=torch.uint8, device=DEV)
+        yh, yl = torch.zeros(n, dtype=torch.uint8, device=DEV), lo.clone()     # the lo plane is updated in place
+        for pd, split in ((pd_s, True), (pd_f, False)):
+            pj = pd.jobs[j]
+            pj.a, pj.w1, pj.b1, pj.w2, pj.b2 = hi.data_ptr(), w1p.data_ptr(), b1.data_ptr(), w2p.data_ptr(), b2.data_ptr()
+            pj.K1, pj.dil1, pj.K2 = k, dil, k
+            if split:
+                pj.a_lo, pj.y_act, pj.y_lo = yl.data_ptr(), yh.data_ptr(), yl.data_ptr()
+            else:
+                pj.res, pj.y, pj.y_act = xb.data_ptr(), y_f.data_ptr(), ya_f.data_ptr()
+        keep += [hi, lo, w1, w2, b1, b2, w1p, w2p, xb]
+        outs.append((y_f, ya_f, yh, yl))
+    _lib.check(lib.rvc_resblock_pair_tc(C.byref(pd_f), st), "pair fp32 stream")
+    _lib.check(lib.rvc_resblock_pair_tc(C.byref(pd_s), st), "pair split stream")
+    torch.cuda.synchronize()
+    for y_f, ya_f, yh, yl in outs:
+        assert torch.equal(yh, ya_f)                                   # hi plane == the packed operand of the fp32-stream launch
+        assert pad_rows_zero(yh, B, Cc, L, FP16, rows)
+        xs, xf = decode_split(yh, yl, B, Cc, L, rows), from_blocked(y_f)
+        bound = 2.0 ** -21 * F.leaky_relu(xf, 0.1).abs() * 10.0 + 1e-6      # (x 10: the inverse of slope 0.1 on the negative side)
+        assert bool(((xs - xf).abs() <= bound).all()), float(((xs - xf).abs() - bound).max())
+
+
+@pytest.mark.parametrize("Cc,L,B,y_ncl", [(64, 3001, 2, 1), (32, 20000, 1, 0), (32, 5, 2, 1)])
+def test_fused_resblock_pair_split_stream_stage_average(Cc, L, B, y_ncl):
+    """sum_jobs with split-fp16 inputs: the three residuals decode from (a, a_lo); bit-identical to the fp32-stream launch fed the decoded values."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(91 + Cc + L)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(L)
+    n = B * Cc * rows * 2
+    pd_s, pd_f = _lib.ResblockPairDesc(), _lib.ResblockPairDesc()
+    for pd in (pd_s, pd_f):
+        pd.njobs, pd.B, pd.C, pd.L, pd.dtype, pd.slope, pd.sum_jobs, pd.y_ncl, pd.alpha = 3, B, Cc, L, FP16, 0.1, 1, y_ncl, 1.0 / 3.0
+    shape = (B, Cc, L) if y_ncl else (B, Cc // 8, L, 8)
+    y_s, y_f = torch.zeros(shape, device=DEV), torch.zeros(shape, device=DEV)
+    ya_s, ya_f = torch.zeros(n, dtype=torch.uint8, device=DEV), torch.zeros(n, dtype=torch.uint8, device=DEV)
+    keep = []
+    for j, (k, dil) in enumerate(((11, 5), (7, 5), (3, 5))):
+        hi, lo, xdec = split_planes(torch.randn(B, Cc, L, generator=g), rows)
+        w1 = (torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+        w2 = (torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+        b1, b2 = torch.randn(Cc, generator=g).to(DEV), torch.randn(Cc, generator=g).to(DEV)
+        w1p, w2p = torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV), torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+        _lib.check(lib.rvc_pack_weight(w1.data_ptr(), w1p.data_ptr(), Cc, Cc, k, FP16, st), "pack_weight")
+        _lib.check(lib.rvc_pack_weight(w2.data_ptr(), w2p.data_ptr(), Cc, Cc, k, FP16, st), "pack_weight")
+        xb = to_blocked(xdec.to(DEV))
+        for pd, split in ((pd_s, True), (pd_f, False)):
+            pj = pd.jobs[j]
+            pj.a, pj.w1, pj.b1, pj.w2, pj.b2 = hi.data_ptr(), w1p.data_ptr(), b1.data_ptr(), w2p.data_ptr(), b2.data_ptr()
+            pj.K1, pj.dil1, pj.K2 = k, dil, k
+            if split:
+                pj.a_lo = lo.data_ptr()
+            else:
+                pj.res = xb.data_ptr()
+            if j == 0:
+                pj.y, pj.y_act = (y_s if split else y_f).data_ptr(), (ya_s if split else ya_f).data_ptr()
+        keep += [hi, lo, w1, w2, b1, b2, w1p, w2p, xb]
+    _lib.check(lib.rvc_resblock_pair_tc(C.byref(pd_f), st), "pair sum fp32 stream")
+    _lib.check(lib.rvc_resblock_pair_tc(C.byref(pd_s), st), "pair sum split stream")
+    torch.cuda.synchronize()
+    assert float(y_f.abs().max()) > 0.1
+    assert torch.equal(y_s, y_f) and torch.equal(ya_s, ya_f)
+
+
+def test_tc_conv_split_stream_output():
+    """rvc_tc_job.y_lo: the low plane next to y_act — hi + lo reproduces leaky_relu(y_f32) to 2^-21 relative (+ the fp16 subnormal step)."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    B, Cc, L, k = 2, 64, 3001, 3
+    g = torch.Generator(device="cpu").manual_seed(5)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(L)
+    n = B * Cc * rows * 2
+    x = torch.randn(B, Cc, L, generator=g).to(DEV)
+    w = (3.0 * torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+    bias = torch.randn(Cc, generator=g).to(DEV)
+    a, wp = torch.zeros(n, dtype=torch.uint8, device=DEV), torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.rvc_pack_act(x.data_ptr(), None, None, 1.0, Cc * L, L, None, a.data_ptr(), B, Cc, L, FP16, 1.0, st), "pack_act")
+    _lib.check(lib.rvc_pack_weight(w.data_ptr(), wp.data_ptr(), Cc, Cc, k, FP16, st), "pack_weight")
+    y, yh, yl = torch.zeros(B, Cc, L, device=DEV), torch.zeros(n, dtype=torch.uint8, device=DEV), torch.zeros(n, dtype=torch.uint8, device=DEV)
+    d = _lib.Conv1dTcDesc()
+    d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype = 1, B, Cc, Cc, L, FP16
+    jb = d.jobs[0]
+    jb.a, jb.w, jb.bias, jb.y_act, jb.y_lo = a.data_ptr(), wp.data_ptr(), bias.data_ptr(), yh.data_ptr(), yl.data_ptr()
+    jb.y_f32, jb.y_bs, jb.y_cs = y.data_ptr(), Cc * L, L
+    jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = k, 1, 1, 1.0, 0.1
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "conv")
+    torch.cuda.synchronize()
+    ref = F.leaky_relu(y, 0.1)
+    hi, lo = unpack(yh, B, Cc, L, FP16, rows), unpack(yl, B, Cc, L, FP16, rows)
+    assert torch.equal(hi, ref.to(torch.float16).float())
+    assert bool(((hi + lo - ref).abs() <= 2.0 ** -21 * ref.abs() + 6e-8).all())
+    assert pad_rows_zero(yl, B, Cc, L, FP16, rows)
+    d.dtype = BF16
+    assert lib.rvc_conv1d_tc(C.byref(d), st) != 0 and b"y_lo" in lib.rvc_last_error()
