@@ -159,6 +159,9 @@ int rvc_sine_source_f32(const float* f0, const float* noise, const float* lin_w,
  */
 #define RVC_DT_BF16 0
 #define RVC_DT_FP16 2
+/* output format of rvc_pack_rows / rvc_layernorm_f32 only: TWO fp16 planes per batch item, [b][2*C/8][rows][8] — chunks [0, C/8) hold
+ * hi = fp16(x), chunks [C/8, 2*C/8) hold lo = fp16(x - hi); the operands of the split-precision GEMMs (rvc_conv1d_tc_desc.sum_jobs) */
+#define RVC_DT_FP16_SPLIT 3
 int64_t rvc_packed_rows(int32_t L);
 /* y_packed = DT(leaky_relu(in, slope) * mask) for fp32 x[B,C,L] with element strides (slope = 1 -> identity, mask may be NULL);
  * in = x, or (x + x2 + x3) / in_div when x2/x3 are given (the `xs / num_kernels` of a generator stage). */
@@ -176,7 +179,7 @@ int rvc_pack_weight(const float* w, void* y, int32_t Cout, int32_t Cin, int32_t 
  *   relu == 1: v = max(v, 0);   res: v = res[b][c][l] + alpha * v;   relu == 2: v = leaky_relu(v, act_slope) (then y_act adds none);
  *   mask: v *= mask[b][l]
  *   y_f32[b][c][l] = v (element strides y_bs / y_cs);   y_act = DT(leaky_relu(v, act_slope)) in the packed layout.
- * Up to three jobs sharing (B, Cin, Cout, L, dtype) run in one persistent launch.  nt / mt = 0 let the library pick the tile.
+ * Up to six jobs sharing (B, Cin, Cout, L, dtype) run in one persistent launch.  nt / mt = 0 let the library pick the tile.
  */
 typedef struct {
     const void* a; const void* w;
@@ -212,6 +215,10 @@ typedef struct {
  *
  * sum_jobs = 1 (stage average of the ResBlocks, synthesizers.py:157-159): every tile runs ALL jobs into one accumulator and
  * the epilogue of job 0 receives v = alpha * (sum_j conv_j + sum_j bias_j + sum_j res_j); outputs / mask / act_slope of job 0.
+ * sum_jobs = g >= 2: the same per GROUP of g consecutive jobs (njobs % g == 0; up to 6 jobs): group leader = job k*g holds the
+ * outputs and epilogue options, members contribute conv + bias (+ res when they have one).  Used for the split-precision GEMMs
+ * of the TextEncoder: a.W ~= a_hi.W_hi + a_lo.W_hi + a_hi.W_lo with fp16 planes hi = fp16(x), lo = fp16(x - hi) of both operands
+ * (three jobs, one accumulator): ~2^-21 operand precision on the fp16 tensor-core path.
  *
  * f32_blocked (bit 0: res, bit 1: y_f32 of every job): the fp32 tensor is channel-blocked, [b][c/8][l][8] — element (b, c, l)
  * at b*bs + (c/8)*cs + l*8 + c%8 with cs = the stride between 8-channel blocks (8*L when dense).  The epilogue then moves
@@ -219,7 +226,7 @@ typedef struct {
  * use it (measured: 5.5 vs 4.4 TB/s for the conv2 epilogue's traffic, tools/epilogue_pattern_bench.cu).
  */
 typedef struct {
-    rvc_tc_job jobs[3];
+    rvc_tc_job jobs[6];
     int32_t njobs, B, Cin, Cout, L, dtype, nt, mt, up, pshift, sum_jobs, f32_blocked;
 } rvc_conv1d_tc_desc;
 int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librvc_b200.so")
 ABI_VERSION = 22
-DT_BF16, DT_FP16 = 0, 2
+DT_BF16, DT_FP16, DT_FP16_SPLIT = 0, 2, 3
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
@@ -66,7 +66,7 @@ class TcJob(C.Structure):
 
 
 class Conv1dTcDesc(C.Structure):
-    _fields_ = [("jobs", TcJob * 3), ("njobs", _i32), ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("L", _i32), ("dtype", _i32),
+    _fields_ = [("jobs", TcJob * 6), ("njobs", _i32), ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("L", _i32), ("dtype", _i32),
                 ("nt", _i32), ("mt", _i32), ("up", _i32), ("pshift", _i32), ("sum_jobs", _i32), ("f32_blocked", _i32)]
 
 

@@ -30,7 +30,7 @@ constexpr int NSTAGE = 4;        // weight ring slots
 constexpr int STAGE_BYTES = 16384;
 constexpr int NTHREADS = 512;      // 16 warps: warpgroup 0 = A producer, MMA issuers, W producer; warpgroups 1-3 = epilogue
 constexpr int NEG = 3;             // epilogue warpgroups
-constexpr int MAXJOBS = 3;
+constexpr int MAXJOBS = 6;
 constexpr int MAXABUF = 8;        // activation ring slots (as many as fit next to the weight ring)
 constexpr int MAXNG = 4;          // TMEM accumulator groups
 
@@ -63,7 +63,8 @@ struct Params {
     FastDiv fd_tpj, fd_up, fd_nnt, fd_nlt;
     int fp16;         // operand format: 0 = bf16, 1 = fp16
     int nabuf;        // activation ring depth (2..MAXABUF)
-    int sum_jobs;     // 1: every tile runs ALL jobs into one accumulator (stage average of the ResBlocks)
+    int sum_jobs;     // 1: every tile runs all G jobs of its group into one accumulator (stage average of the ResBlocks; split-precision terms)
+    int G;            // group size: 1 = every job has its own tiles; otherwise jobs [g*G, (g+1)*G) share the tiles of group g
     int has_res;      // some job carries a residual (enables the epilogue's residual prefetch)
     int blocked;      // bit 0: res is channel-blocked fp32 [b][c/8][l][8]; bit 1: y_f32 is
     int dbg;          // timing experiments only: 1 = epilogue skips global I/O, 2 = skip MMA issue, 4 = skip operand loads,
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * MAXABUF + MAXNG + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * MAXABUF + 2 * MAXNG);
     float* bias_s = reinterpret_cast<float*>(bars + 2 * NSTAGE + 2 * MAXABUF + 2 * MAXNG + 2);   // [njobs][Cout], 16-byte aligned
-    float4* nzw_s = reinterpret_cast<float4*>(bias_s + ((p.njobs * p.Cout + 3) & ~3));             // [Cout] noise-conv taps of job 0 (<= 4, zero padded)
+    float4* nzw_s = reinterpret_cast<float4*>(bias_s + (((p.njobs / p.G) * p.Cout + 3) & ~3));             // [Cout] noise-conv taps of job 0 (<= 4, zero padded)
     float* nzb_s = reinterpret_cast<float*>(nzw_s + p.Cout);                                       // [Cout] noise-conv bias
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
@@ -135,11 +136,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     }
     if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
     if (warp >= 4)   // biases of all jobs -> shared memory (read back with broadcast LDS.128 in the epilogue)
-        for (int i = threadIdx.x - 128; i < p.njobs * p.Cout; i += NTHREADS - 128) {
-            const int j = i / p.Cout, c = i - j * p.Cout;
-            float v = p.jobs[j].bias ? p.jobs[j].bias[c] : 0.f;
-            if (p.sum_jobs && j == 0)
-                for (int jj = 1; jj < p.njobs; ++jj) v += p.jobs[jj].bias ? p.jobs[jj].bias[c] : 0.f;
+        for (int i = threadIdx.x - 128; i < (p.njobs / p.G) * p.Cout; i += NTHREADS - 128) {   // one (summed) bias row per job group
+            const int g = i / p.Cout, c = i - g * p.Cout;
+            float v = 0.f;
+            for (int jj = 0; jj < p.G; ++jj) v += p.jobs[g * p.G + jj].bias ? p.jobs[g * p.G + jj].bias[c] : 0.f;
             bias_s[i] = v;
         }
     if (warp >= 4 && p.jobs[0].nz_har) {
@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int j, b, lt, nt, ph;
             decode(tile, j, b, lt, nt, ph);
-            for (int jj = 0; jj < (p.sum_jobs ? p.njobs : 1); ++jj) {
-            const rvc_tc_job& jb = p.jobs[p.sum_jobs ? jj : j];
+            for (int jj = 0; jj < p.G; ++jj) {
+            const rvc_tc_job& jb = p.jobs[j * p.G + jj];
             const int pad = jb.pad;
             const int row0 = PADL + lt * TM - pad;                           // >= 0 (host checks pad <= PADL)
             // the last tile must not read past the chunk's Lp rows (ragged L, TM = 512, the extra tile of the transposed mode):
@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int j, b, lt, nt, ph;
             decode(tile, j, b, lt, nt, ph);
-            for (int jj = 0; jj < (p.sum_jobs ? p.njobs : 1); ++jj) {
-            const rvc_tc_job& jb = p.jobs[p.sum_jobs ? jj : j];
+            for (int jj = 0; jj < p.G; ++jj) {
+            const rvc_tc_job& jb = p.jobs[j * p.G + jj];
             const size_t w_cs = jb.w_cs ? (size_t)jb.w_cs : (size_t)p.Cout;      // rows between consecutive weight chunks
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(jb.w) + (size_t)b * jb.w_bs + (size_t)ph * jb.K * p.nch * w_cs * 16;
             for (int cs = 0; cs < p.ncs; ++cs) {
@@ -271,9 +271,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             tc::fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)((g * MT + m) * NT);   // + 2*NT for this issuer's second sub-tile
             uint32_t accumulate = 0;
-            for (int jj = 0; jj < (p.sum_jobs ? p.njobs : 1); ++jj) {
-            const int K = p.jobs[p.sum_jobs ? jj : j].K;
-            const uint32_t dil = (uint32_t)p.jobs[p.sum_jobs ? jj : j].dil;
+            for (int jj = 0; jj < p.G; ++jj) {
+            const int K = p.jobs[j * p.G + jj].K;
+            const uint32_t dil = (uint32_t)p.jobs[j * p.G + jj].dil;
             for (int cs = 0; cs < p.ncs; ++cs) {
                 const int na = min(p.ach, p.nch - cs * p.ach);
                 tc::mbar_wait(A_FULL(ast), aph);
@@ -340,8 +340,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
 #pragma unroll
                 for (int u = 0; u < EBP / 8; ++u) tc::ldg256(rp + (size_t)u * jn.res_cs, vn + 8 * u);
                 if (p.sum_jobs)
-                    for (int jj = 1; jj < p.njobs; ++jj) {
-                        const rvc_tc_job& j2 = p.jobs[jj];
+                    for (int jj = 1; jj < p.G; ++jj) {
+                        const rvc_tc_job& j2 = (&jn)[jj];
+                        if (!j2.res) continue;
                         const float* rp2 = j2.res + (size_t)b_ * j2.res_bs + (size_t)(co_ >> 3) * j2.res_cs + (size_t)l_ * 8;
 #pragma unroll
                         for (int u = 0; u < EBP / 8; ++u) {
@@ -357,8 +358,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
 #pragma unroll
             for (int i = 0; i < EBP; ++i) vn[i] = rp[(size_t)i * jn.res_cs];
             if (p.sum_jobs)
-                for (int jj = 1; jj < p.njobs; ++jj) {
-                    const rvc_tc_job& j2 = p.jobs[jj];
+                for (int jj = 1; jj < p.G; ++jj) {
+                    const rvc_tc_job& j2 = (&jn)[jj];
+                    if (!j2.res) continue;
                     const float* rp2 = j2.res + (size_t)b_ * j2.res_bs + (size_t)co_ * j2.res_cs + l_;
 #pragma unroll
                     for (int i = 0; i < EBP; ++i) vn[i] += rp2[(size_t)i * j2.res_cs];
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             if (tile_ >= p.total_tiles) return;
             int j_, b_, lt_, nt_, ph_;
             decode(tile_, j_, b_, lt_, nt_, ph_);
-            const rvc_tc_job& jn = p.jobs[j_];
+            const rvc_tc_job& jn = p.jobs[j_ * p.G];
             if (jn.res && eg < MT * (jn.gated ? (NT / EBP) / 2 : NT / EBP)) load_res(jn, b_, lt_, nt_, ph_, eg, vn);
         };
         if constexpr (PF) {
@@ -381,7 +383,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             int j, b, lt, nt, ph;
             decode(tile, j, b, lt, nt, ph);
-            const rvc_tc_job& jb = p.jobs[j];
+            const int jl = j * p.G;                 // the group's leader: outputs, bias slot, epilogue options
+            const rvc_tc_job& jb = p.jobs[jl];
             const int g = it % NG;
             const uint32_t gph = (it / NG) & 1;
             const float* bb = jb.bias_b ? jb.bias_b + (size_t)b * jb.bias_b_bs : nullptr;
@@ -674,7 +677,9 @@ RVC_API int rvc_pack_weight(const float* w, void* y, int32_t Cout, int32_t Cin, 
 RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     if (!dp) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: null descriptor");
     const rvc_conv1d_tc_desc& d = *dp;
-    if (d.njobs < 1 || d.njobs > MAXJOBS) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: njobs must be 1..3");
+    if (d.njobs < 1 || d.njobs > MAXJOBS) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: njobs must be 1..%d", MAXJOBS);
+    const int G = d.sum_jobs <= 0 ? 1 : (d.sum_jobs == 1 ? d.njobs : d.sum_jobs);     // jobs per tile group
+    if (d.njobs % G) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs = %d does not divide njobs = %d", d.sum_jobs, d.njobs);
     if (d.dtype != RVC_DT_BF16 && d.dtype != RVC_DT_FP16) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: dtype must be RVC_DT_BF16 or RVC_DT_FP16");
     if (d.B <= 0 || d.L <= 0 || d.Cin <= 0 || d.Cout <= 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: bad shape");
     if (d.Cin % 16) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: Cin=%d must be a multiple of 16", d.Cin);
@@ -709,11 +714,11 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     // transposed mode: input positions q in [0, L + ceil(pshift/up)) reach valid outputs (rows past L are zero in the packed buffer)
     const int Lq = up > 1 ? d.L + rvc::cdiv(d.pshift, up) : d.L;
     const int Lout = up > 1 ? d.L * up : d.L;
-    const int njt = d.sum_jobs ? 1 : d.njobs;   // jobs that multiply the tile count
-    if (d.sum_jobs) {
+    const int njt = d.njobs / G;                // job groups multiply the tile count
+    if (G > 1) {
         if (gated || up > 1) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs excludes gated / transposed mode");
-        for (int j = 1; j < d.njobs; ++j)
-            if ((d.jobs[j].res == nullptr) != (d.jobs[0].res == nullptr)) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs needs res on all jobs or none");
+        for (int j = 0; j < d.njobs; ++j)      // (a member's residual is added when it has one; a leader without one takes none at all)
+            if (d.jobs[j].res && !d.jobs[j / G * G].res) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs: a member has res but its group leader has none");
     }
     auto ntiles = [&](int nt_, int mt_) { return (long)njt * d.B * rvc::cdiv(Lq, BM * mt_) * (d.Cout / nt_) * up; };
     // wide layers on short sequences (the C = 256 generator stage: L = 10-12 k) are bound by streaming the weights of each tile
@@ -767,12 +772,13 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     p.total_tiles = p.tiles_per_job * njt;
     p.fd_tpj.init((uint32_t)p.tiles_per_job); p.fd_up.init((uint32_t)up); p.fd_nnt.init((uint32_t)p.n_nt); p.fd_nlt.init((uint32_t)p.n_lt);
     p.fp16 = d.dtype == RVC_DT_FP16;
-    p.sum_jobs = d.sum_jobs ? 1 : 0;
+    p.sum_jobs = d.sum_jobs > 0 ? 1 : 0;
+    p.G = G;
     p.dbg = d.jobs[0].reserved;
     p.blocked = d.f32_blocked;
     p.has_res = 0;
     for (int j = 0; j < d.njobs; ++j) p.has_res |= d.jobs[j].res != nullptr;
-    const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512 + (size_t)d.njobs * d.Cout * sizeof(float) + (d.jobs[0].nz_har ? 16 + (size_t)d.Cout * 20 : 0);
+    const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512 + (size_t)(d.njobs / G) * d.Cout * sizeof(float) + (d.jobs[0].nz_har ? 16 + (size_t)d.Cout * 20 : 0);
     const size_t limit = 227 * 1024;
     // activation stage: as many channel chunks as fit twice (double buffer); even count
     int ach = p.nch;

@@ -81,6 +81,13 @@ __device__ __forceinline__ uint32_t ln_pack2(float a, float b, int fp16) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// low plane of the split-fp16 form: fp16(value - float(hi)) for the two values packed in `hi`
+__device__ __forceinline__ uint32_t ln_lo2(float a, float b, uint32_t hi) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    __half2 h = __floats2half2_rn(a - hf.x, b - hf.y);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ r,
                                                             const float* __restrict__ r2, const float* __restrict__ r3,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -145,8 +152,13 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
         }
         if (y_act) {  // packed copy is always masked: it only ever feeds convs whose input the reference masks (or 1x1 convs)
             uint4 pk;
-            pk.x = ln_pack2(o[0] * mk, o[1] * mk, fp16); pk.y = ln_pack2(o[2] * mk, o[3] * mk, fp16);
-            pk.z = ln_pack2(o[4] * mk, o[5] * mk, fp16); pk.w = ln_pack2(o[6] * mk, o[7] * mk, fp16);
+            pk.x = ln_pack2(o[0] * mk, o[1] * mk, fp16 & 1); pk.y = ln_pack2(o[2] * mk, o[3] * mk, fp16 & 1);
+            pk.z = ln_pack2(o[4] * mk, o[5] * mk, fp16 & 1); pk.w = ln_pack2(o[6] * mk, o[7] * mk, fp16 & 1);
+            if (fp16 & 2) {   // RVC_DT_FP16_SPLIT: planes [hi | lo] of 2 * nchunk chunks per batch item, lo = fp16(value - hi)
+                *reinterpret_cast<uint4*>(y_act + (((size_t)b * 2 * nchunk + ch) * Lp + 64 + t) * 16) = pk;
+                *reinterpret_cast<uint4*>(y_act + (((size_t)b * 2 * nchunk + nchunk + ch) * Lp + 64 + t) * 16) =
+                    make_uint4(ln_lo2(o[0] * mk, o[1] * mk, pk.x), ln_lo2(o[2] * mk, o[3] * mk, pk.y), ln_lo2(o[4] * mk, o[5] * mk, pk.z), ln_lo2(o[6] * mk, o[7] * mk, pk.w));
+            } else
             *reinterpret_cast<uint4*>(y_act + (((size_t)b * nchunk + ch) * Lp + 64 + t) * 16) = pk;
         }
     }
@@ -240,8 +252,13 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restr
         }
         if (y_act) {
             uint4 pk;
-            pk.x = ln_pack2(o[0] * mk, o[1] * mk, fp16); pk.y = ln_pack2(o[2] * mk, o[3] * mk, fp16);
-            pk.z = ln_pack2(o[4] * mk, o[5] * mk, fp16); pk.w = ln_pack2(o[6] * mk, o[7] * mk, fp16);
+            pk.x = ln_pack2(o[0] * mk, o[1] * mk, fp16 & 1); pk.y = ln_pack2(o[2] * mk, o[3] * mk, fp16 & 1);
+            pk.z = ln_pack2(o[4] * mk, o[5] * mk, fp16 & 1); pk.w = ln_pack2(o[6] * mk, o[7] * mk, fp16 & 1);
+            if (fp16 & 2) {   // RVC_DT_FP16_SPLIT: planes [hi | lo] of 2 * nchunk chunks per batch item, lo = fp16(value - hi)
+                *reinterpret_cast<uint4*>(y_act + (((size_t)b * 2 * nchunk + ch) * Lp + 64 + t) * 16) = pk;
+                *reinterpret_cast<uint4*>(y_act + (((size_t)b * 2 * nchunk + nchunk + ch) * Lp + 64 + t) * 16) =
+                    make_uint4(ln_lo2(o[0] * mk, o[1] * mk, pk.x), ln_lo2(o[2] * mk, o[3] * mk, pk.y), ln_lo2(o[4] * mk, o[5] * mk, pk.z), ln_lo2(o[6] * mk, o[7] * mk, pk.w));
+            } else
             *reinterpret_cast<uint4*>(y_act + (((size_t)b * nchunk + ch) * Lp + 64 + t) * 16) = pk;
         }
     }
@@ -447,8 +464,14 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
     const float4* xp = reinterpret_cast<const float4*>(x + ((int64_t)b * T + t) * D + c * 8);
     const float4 a = xp[0], d = xp[1];
     uint4 pk;
-    pk.x = ln_pack2(a.x, a.y, fp16); pk.y = ln_pack2(a.z, a.w, fp16);
-    pk.z = ln_pack2(d.x, d.y, fp16); pk.w = ln_pack2(d.z, d.w, fp16);
+    pk.x = ln_pack2(a.x, a.y, fp16 & 1); pk.y = ln_pack2(a.z, a.w, fp16 & 1);
+    pk.z = ln_pack2(d.x, d.y, fp16 & 1); pk.w = ln_pack2(d.z, d.w, fp16 & 1);
+    if (fp16 & 2) {   // RVC_DT_FP16_SPLIT: [hi | lo] planes
+        *reinterpret_cast<uint4*>(y + (((int64_t)b * 2 * (D / 8) + c) * Lp + 64 + t) * 16) = pk;
+        *reinterpret_cast<uint4*>(y + (((int64_t)b * 2 * (D / 8) + D / 8 + c) * Lp + 64 + t) * 16) =
+            make_uint4(ln_lo2(a.x, a.y, pk.x), ln_lo2(a.z, a.w, pk.y), ln_lo2(d.x, d.y, pk.z), ln_lo2(d.z, d.w, pk.w));
+        return;
+    }
     *reinterpret_cast<uint4*>(y + (((int64_t)b * (D / 8) + c) * Lp + 64 + t) * 16) = pk;
 }
 }  // namespace
@@ -465,11 +488,13 @@ RVC_API int rvc_embed_prep(const int64_t* pitch, const int64_t* lengths, const f
 
 RVC_API int rvc_pack_rows(const float* x, void* y, int32_t B, int32_t T, int32_t D, int32_t dtype, void* stream) {
     if (!x || !y) return rvc::fail(RVC_EINVAL, "rvc_pack_rows: null pointer");
-    if (dtype != RVC_DT_BF16 && dtype != RVC_DT_FP16) return rvc::fail(RVC_EINVAL, "rvc_pack_rows: dtype must be RVC_DT_BF16 or RVC_DT_FP16");
+    if (dtype != RVC_DT_BF16 && dtype != RVC_DT_FP16 && dtype != RVC_DT_FP16_SPLIT)
+        return rvc::fail(RVC_EINVAL, "rvc_pack_rows: dtype must be RVC_DT_BF16, RVC_DT_FP16 or RVC_DT_FP16_SPLIT");
     if (B <= 0 || B > 65535 || T < 0 || D <= 0 || D % 8 || (reinterpret_cast<uintptr_t>(x) & 15)) return rvc::fail(RVC_ESHAPE, "rvc_pack_rows: bad shape / alignment");
     if (T == 0) return 0;
     dim3 grid(rvc::cdiv(T, 256), D / 8, B);
-    rvc::launch_pdl(pack_rows_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, x, (uint8_t*)y, T, D, (int)rvc_packed_rows(T), dtype == RVC_DT_FP16);
+    rvc::launch_pdl(pack_rows_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, x, (uint8_t*)y, T, D, (int)rvc_packed_rows(T),
+                    dtype == RVC_DT_FP16 ? 1 : dtype == RVC_DT_FP16_SPLIT ? 3 : 0);
     return rvc::check_launch("rvc_pack_rows");
 }
 
@@ -490,11 +515,11 @@ RVC_API int rvc_layernorm_f32(const float* x, const float* r, const float* r2, c
     if (!x || !gamma || !beta || !y || (out_mask && !mask)) return rvc::fail(RVC_EINVAL, "rvc_layernorm_f32: null pointer");
     if ((r2 == nullptr) != (r3 == nullptr) || (r2 && !r)) return rvc::fail(RVC_EINVAL, "rvc_layernorm_f32: r2 and r3 go together (and need r)");
     if (B <= 0 || B > 65535 || C <= 0 || T < 0) return rvc::fail(RVC_ESHAPE, "rvc_layernorm_f32: bad shape");
-    if (y_act && (C % 8 || !mask || (act_dtype != RVC_DT_BF16 && act_dtype != RVC_DT_FP16)))
+    if (y_act && (C % 8 || !mask || (act_dtype != RVC_DT_BF16 && act_dtype != RVC_DT_FP16 && act_dtype != RVC_DT_FP16_SPLIT)))
         return rvc::fail(RVC_EINVAL, "rvc_layernorm_f32: packed output needs C %% 8 == 0, a mask and a bf16/fp16 dtype");
     if (T == 0) return 0;
     dim3 grid(rvc::cdiv(T, 32), B);
-    const int Lp = (int)rvc_packed_rows(T), f16 = act_dtype == RVC_DT_FP16;
+    const int Lp = (int)rvc_packed_rows(T), f16 = act_dtype == RVC_DT_FP16 ? 1 : act_dtype == RVC_DT_FP16_SPLIT ? 3 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int nper = rvc::cdiv(C, 64);   // 8-channel chunks per thread
     if (nper == 1) rvc::launch_pdl(layernorm_reg_kernel<1>, dim3(grid), dim3(32, 8), (size_t)0, st, x, r, r2, r3, gamma, beta, mask, y, C, T, eps, out_mask, (uint8_t*)y_act, Lp, f16);

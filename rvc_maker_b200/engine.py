@@ -238,7 +238,10 @@ class Engine:
         half = I // 2
         dims_ok = all(v % 16 == 0 for v in (H, c["Fc"], half, I)) and all(v % 32 == 0 for v in (H, 3 * H, c["Fc"], 2 * I, half, c["U"])) \
             and H % 64 == 0 and c["ks"] % 2 == 1
-        self.enc_tc = self.tc and dims_ok
+        # (RVC_B200_ENC_TC=0 / RVC_B200_FLOW_TC=0: error-budget experiments — that part runs on the fp32 CUDA-core kernels instead)
+        self.enc_split = os.environ.get("RVC_B200_ENC_SPLIT", "1") != "0"     # split-precision encoder GEMMs (see _enc_plan)
+        self.enc_tc = self.tc and dims_ok and os.environ.get("RVC_B200_ENC_TC", "1") != "0"
+        self.flow_tc = self.tc and dims_ok and os.environ.get("RVC_B200_FLOW_TC", "1") != "0"   # flow + conv_pre
         if self.enc_tc:
             dt = DT_FP16
             e = m.enc_p
@@ -255,6 +258,12 @@ class Engine:
             tc_w["t_proj_w"] = (_f(e.proj.weight), dt)
             if c["D"] % 16 == 0:
                 tc_w["t_emb_w"] = (_f(e.emb_phone.weight).unsqueeze(-1).contiguous(), dt)   # Linear as a 1x1 conv [H, D, 1]
+            if self.enc_split:   # low weight planes of the split-precision GEMMs: fp16(W - fp16(W))
+                for k in [k for k in tc_w if k.startswith(("t_qkv_w", "t_o_w", "t_proj_w", "t_emb_w"))]:
+                    w_ = tc_w[k][0]
+                    tc_w[k + "_lo"] = ((w_ - w_.half().float()).contiguous(), dt)
+        if self.flow_tc:
+            dt = DT_FP16
             # gated in_layers: weight columns ordered per 64-wide N tile as [32 tanh | 32 sigmoid] (see include/rvc_b200.h)
             perm = []
             for t in range(2 * H // 64):
@@ -319,11 +328,11 @@ class Engine:
         bytes_ = 4.0 * (B * Cin * L + B * Cout * L * (1 + (res is not None) + (beta != 0.0)) + Cin * K * Cout * g2)
         plan.add(name, self.lib.rvc_conv1d_f32, C.byref(d), flops=flops, bytes_=bytes_, kind=f"conv1d_f32[C{Cout}k{K}]")
 
-    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag="", up=1, pshift=0, flops=None, blocked=0):
-        """One persistent tcgen05 launch over up to three jobs (dicts of rvc_tc_job fields; V views for res / y)."""
+    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag="", up=1, pshift=0, flops=None, blocked=0, sum_jobs=0):
+        """One persistent tcgen05 launch over up to six jobs (dicts of rvc_tc_job fields; V views for res / y)."""
         d = Conv1dTcDesc()
         d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.nt, d.mt = len(jobs), B, Cin, Cout, L, dtype, nt, mt
-        d.up, d.pshift, d.f32_blocked = up, pshift, blocked
+        d.up, d.pshift, d.f32_blocked, d.sum_jobs = up, pshift, blocked, sum_jobs
         fl = by = 0.0
         for slot, j in enumerate(jobs):
             jb = d.jobs[slot]
@@ -341,7 +350,7 @@ class Engine:
             if j.get("y_act") is not None:
                 jb.y_act = j["y_act"] if isinstance(j["y_act"], int) else j["y_act"].data_ptr()
             if j.get("y_lo") is not None:
-                jb.y_lo = j["y_lo"].data_ptr()
+                jb.y_lo = j["y_lo"] if isinstance(j["y_lo"], int) else j["y_lo"].data_ptr()
             jb.K, jb.dil = j.get("K", 1), j.get("dil", 1)
             jb.pad = j.get("pad", (jb.K - 1) // 2 * jb.dil)
             jb.gated, jb.relu = int(j.get("gated", False)), int(j.get("relu", 0))
@@ -416,80 +425,114 @@ class Engine:
                   p.mask.data_ptr(), B, T, D, H, flops=2.0 * B * T * D * H, bytes_=4.0 * B * T * (D + H), kind="embed_f32")
         if self.enc_tc:
             dt = DT_FP16
-            xa, atta, ha = self._packed(p, B, H, T), self._packed(p, B, H, T), self._packed(p, B, Fc, T)
-            y2, y3 = self._buf(p, B, H, T), self._buf(p, B, H, T)      # split-K partial sums of the FFN's second conv
-            Lp = int(lib.rvc_packed_rows(T))
-            if tc_embed:
-                # x = lrelu((phone.W^T + b + E[pitch]) * sqrt(H), 0.1) * mask  (synthesizers.py:367): exact gather + tensor-core Linear
-                pha = self._packed(p, B, D, T)
-                pbias = self._buf(p, B, H, T) if c["f0"] else None
-                sq = math.sqrt(H)
-                p.add("embed_prep", lib.rvc_embed_prep, p.pitch.data_ptr() if c["f0"] else None, p.lengths.data_ptr(),
-                      W["emb_pitch"].data_ptr() if c["f0"] else None, sq, pbias.data_ptr() if c["f0"] else None, p.mask.data_ptr(), B, T, H,
-                      bytes_=8.0 * B * H * T, kind="embed_prep")
-                p.add("pack_phone", lib.rvc_pack_rows, p.phone.data_ptr(), pha.data_ptr(), B, T, D, dt, bytes_=6.0 * B * T * D, kind="pack_act")
-                self._tc(p, "embed", [dict(a=pha, w=W["t_emb_w"], bias=W["emb_b"], res=(V(pbias, H, T) if c["f0"] else None), alpha=sq,
-                                           relu=2, act_slope=0.1, mask=p.mask, y=vx, y_act=xa)], B=B, Cin=D, Cout=H, L=T, dtype=dt, tag="enc")
-            else:
-                p.add("pack_x", lib.rvc_pack_act, x.data_ptr(), None, None, 1.0, H * T, T, None, xa.data_ptr(), B, H, T, dt, 1.0, kind="pack_act",
-                      bytes_=6.0 * B * H * T)
             nh = c["nh"]
             dk = H // nh
             tc_attn = nh <= 3 and dk % 32 == 0
+            Lp = int(lib.rvc_packed_rows(T))
+            # Split-precision GEMMs (self.enc_split): the error of the tensor-core path's waveform is dominated by the fp16 operand
+            # rounding of the encoder's 1x1 GEMMs (every site feeds the softmax logits, tests/encoder_rounding_study.py), and those
+            # launches are latency-bound — so they run as a.W ~= a_hi.W_hi + a_lo.W_hi + a_hi.W_lo: three jobs of one accumulator
+            # (rvc_conv1d_tc_desc.sum_jobs = 3) over [hi | lo] activation planes and two weight planes.  FFN and P.v stay plain fp16.
+            split = self.enc_split and tc_embed and tc_attn
+            npl = 2 if split else 1
+            adt = _lib.DT_FP16_SPLIT if split else dt
+            pk = lambda Cch: self._zbuf(p, B * npl * Cch * Lp * 2)        # packed activations, [hi | lo] planes when split
+            xa, atta, ha = pk(H), pk(H), self._packed(p, B, Fc, T)
+            y2, y3 = self._buf(p, B, H, T), self._buf(p, B, H, T)      # split-K partial sums of the FFN's second conv
+            cb = Lp * 16                                                   # bytes per 8-channel chunk of a packed buffer
+
+            def gemm(name, a, cin, wkey, cout, lead, tag="enc", wlo=None):
+                """1x1 conv over the packed buffer `a` (cin channels per plane); `lead` = epilogue options of the (leading) job."""
+                a_bs = npl * (cin // 8) * cb
+                if not split:
+                    self._tc(p, name, [dict(a=a, w=W[wkey], a_bs=a_bs, **lead)], B=B, Cin=cin, Cout=cout, L=T, dtype=dt, tag=tag)
+                    return
+                base = a.data_ptr()
+                jobs = [dict(a=base, w=W[wkey], a_bs=a_bs, **lead), dict(a=base + (cin // 8) * cb, w=W[wkey], a_bs=a_bs),
+                        dict(a=base, w=W[wlo or wkey + "_lo"], a_bs=a_bs)]
+                self._tc(p, name, jobs, B=B, Cin=cin, Cout=cout, L=T, dtype=dt, tag=tag, sum_jobs=3, flops=2.0 * B * cin * cout * T)
+
+            def outs(buf, cout):
+                """packed output planes of a launch writing `cout` channels per plane into `buf`"""
+                d = dict(y_act=buf, y_act_bs=npl * (cout // 8) * cb)
+                if split:
+                    d["y_lo"] = buf.data_ptr() + (cout // 8) * cb
+                return d
+
+            if tc_embed:
+                # x = lrelu((phone.W^T + b + E[pitch]) * sqrt(H), 0.1) * mask  (synthesizers.py:367): exact gather + tensor-core Linear
+                pha = pk(D)
+                pbias = self._buf(p, B, H, T) if c["f0"] else None
+                sq = math.sqrt(H)
+                # plain: v = E[pitch]*sqrt(H) + sqrt(H)*(acc + b); split (sum mode): v = sqrt(H)*(E[pitch] + acc + b), the reference's own order
+                p.add("embed_prep", lib.rvc_embed_prep, p.pitch.data_ptr() if c["f0"] else None, p.lengths.data_ptr(),
+                      W["emb_pitch"].data_ptr() if c["f0"] else None, 1.0 if split else sq, pbias.data_ptr() if c["f0"] else None, p.mask.data_ptr(), B, T, H,
+                      bytes_=8.0 * B * H * T, kind="embed_prep")
+                p.add("pack_phone", lib.rvc_pack_rows, p.phone.data_ptr(), pha.data_ptr(), B, T, D, adt, bytes_=(4.0 + 2.0 * npl) * B * T * D, kind="pack_act")
+                gemm("embed", pha, D, "t_emb_w", H, dict(bias=W["emb_b"], res=(V(pbias, H, T) if c["f0"] else None), alpha=sq,
+                                                          relu=2, act_slope=0.1, mask=p.mask, y=vx, **outs(xa, H)))
+            else:
+                p.add("pack_x", lib.rvc_pack_act, x.data_ptr(), None, None, 1.0, H * T, T, None, xa.data_ptr(), B, H, T, dt, 1.0, kind="pack_act",
+                      bytes_=6.0 * B * H * T)
             if tc_attn:
-                Lp = int(lib.rvc_packed_rows(T))
                 Tk = (T + 127) // 128 * 128
-                qkva = self._packed(p, B, 3 * H, T)
+                qkva = pk(3 * H)
                 Sb = self._buf(p, B, nh, Tk, T)
                 Pb = self._zbuf(p, B * nh * (Tk // 8) * Lp * 16)
                 Rb = self._buf(p, B, H, T)
                 vwb = self._buf(p, B * nh * (Tk // 8) * dk * 4, dtype=torch.int32)
-                qkv_bs = (3 * H // 8) * Lp * 16
+                qkv_bs = npl * (3 * H // 8) * cb
             for i in range(c["nl"]):
-                self._tc(p, f"qkv{i}", [dict(a=xa, w=W[f"t_qkv_w{i}"], bias=W[f"qkv_b{i}"], y=vqkv, y_act=(qkva if tc_attn else None))],
-                         B=B, Cin=H, Cout=3 * H, L=T, dtype=dt, tag="enc")
+                gemm(f"qkv{i}", xa, H, f"t_qkv_w{i}", 3 * H, dict(bias=W[f"qkv_b{i}"], y=vqkv, **(outs(qkva, 3 * H) if tc_attn else {})))
                 if tc_attn:
                     # S[b][h][key/8][query][8] = q . k^T (channel-blocked over the keys): the packed k activations of each batch item are the GEMM's weights
-                    jobs = [dict(a=qkva.data_ptr() + (h * dk // 8) * Lp * 16, a_bs=qkv_bs,
-                                 w=qkva.data_ptr() + (((H + h * dk) // 8) * Lp + 64) * 16, w_bs=qkv_bs, w_cs=Lp,
-                                 y=V(Sb, nh * Tk, T, h * Tk, cs=8 * T)) for h in range(nh)]
-                    self._tc(p, f"attn_qk{i}", jobs, B=B, Cin=dk, Cout=Tk, L=T, dtype=dt, tag="attn", flops=2.0 * B * H * T * T, blocked=2)
+                    jobs = []
+                    for h in range(nh):
+                        q_hi, k_hi = qkva.data_ptr() + (h * dk // 8) * cb, qkva.data_ptr() + (((H + h * dk) // 8) * Lp + 64) * 16
+                        lo = (3 * H // 8) * cb
+                        terms = [(q_hi, k_hi), (q_hi + lo, k_hi), (q_hi, k_hi + lo)] if split else [(q_hi, k_hi)]
+                        for t_i, (qa, kw) in enumerate(terms):
+                            jobs.append(dict(a=qa, a_bs=qkv_bs, w=kw, w_bs=qkv_bs, w_cs=Lp, y=(V(Sb, nh * Tk, T, h * Tk, cs=8 * T) if t_i == 0 else None)))
+                    self._tc(p, f"attn_qk{i}", jobs, B=B, Cin=dk, Cout=Tk, L=T, dtype=dt, tag="attn", flops=2.0 * B * H * T * T, blocked=2,
+                             sum_jobs=3 if split else 0)
                     p.add(f"attn_sm{i}", lib.rvc_attn_softmax, Sb.data_ptr(), qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(),
                           W[f"ev{i}"].data_ptr(), Pb.data_ptr(), Rb.data_ptr(), vwb.data_ptr(), B, H, nh, T, Tk, WINDOW,
                           bytes_=B * nh * Tk * T * 10.0, kind="attn_softmax")
                     # O = P . v + R, written straight into the packed input of conv_o
-                    jobs = [dict(a=Pb.data_ptr() + h * (Tk // 8) * Lp * 16, a_bs=nh * (Tk // 8) * Lp * 16,
-                                 w=vwb.data_ptr() + h * (Tk // 8) * dk * 16, w_bs=nh * (Tk // 8) * dk * 16,
-                                 res=V(Rb, H, T, h * dk), y_act=atta.data_ptr() + (h * dk // 8) * Lp * 16, y_act_bs=(H // 8) * Lp * 16)
-                            for h in range(nh)]
+                    jobs = []
+                    for h in range(nh):
+                        ya = atta.data_ptr() + (h * dk // 8) * cb
+                        jobs.append(dict(a=Pb.data_ptr() + h * (Tk // 8) * cb, a_bs=nh * (Tk // 8) * cb,
+                                         w=vwb.data_ptr() + h * (Tk // 8) * dk * 16, w_bs=nh * (Tk // 8) * dk * 16,
+                                         res=V(Rb, H, T, h * dk), y_act=ya, y_act_bs=npl * (H // 8) * cb, y_lo=(ya + (H // 8) * cb if split else None)))
                     self._tc(p, f"attn_pv{i}", jobs, B=B, Cin=Tk, Cout=dk, L=T, dtype=dt, tag="attn", flops=2.0 * B * H * T * T)
                 else:
                     p.add(f"attn{i}", lib.rvc_rel_attention_f32, qkv.data_ptr(), p.mask.data_ptr(), W[f"ek{i}"].data_ptr(), W[f"ev{i}"].data_ptr(),
                           att.data_ptr(), B, H, nh, T, WINDOW, flops=4.0 * B * H * T * T, bytes_=16.0 * B * H * T, kind="rel_attention_f32")
                     p.add(f"pack_att{i}", lib.rvc_pack_act, att.data_ptr(), None, None, 1.0, H * T, T, None, atta.data_ptr(), B, H, T, dt, 1.0,
                           kind="pack_act", bytes_=6.0 * B * H * T)
-                self._tc(p, f"attn_o{i}", [dict(a=atta, w=W[f"t_o_w{i}"], bias=W[f"o_b{i}"], y=vy)], B=B, Cin=H, Cout=H, L=T, dtype=dt, tag="enc")
+                gemm(f"attn_o{i}", atta, H, f"t_o_w{i}", H, dict(bias=W[f"o_b{i}"], y=vy))
                 p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), None, None, W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
-                      p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0, xa.data_ptr(), dt, kind="layernorm_f32", bytes_=14.0 * B * H * T)
-                self._tc(p, f"ffn1_{i}", [dict(a=xa, w=W[f"t_f1_w{i}"], bias=W[f"f1_b{i}"], relu=True, mask=p.mask, y_act=ha, K=ks)],
+                      p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0, xa.data_ptr(), adt, kind="layernorm_f32", bytes_=(12.0 + 2.0 * npl) * B * H * T)
+                self._tc(p, f"ffn1_{i}", [dict(a=xa, a_bs=npl * (H // 8) * cb, w=W[f"t_f1_w{i}"], bias=W[f"f1_b{i}"], relu=True, mask=p.mask, y_act=ha, K=ks)],
                          B=B, Cin=H, Cout=Fc, L=T, dtype=dt, tag="enc")
                 # conv_2 (Fc -> H, Fc = 4H input channels): with few position tiles the launch is a handful of CTAs streaming long K
                 # loops (14.5 us at T = 1000).  Three input-channel slices as three jobs fill the GPU (7.2 us); LayerNorm adds the
                 # three partial sums.
-                split = f"t_f2_w{i}_k0" in W and B * (-(-T // 128)) * (H // 32) < 100
-                if split:
+                ksplit = f"t_f2_w{i}_k0" in W and B * (-(-T // 128)) * (H // 32) < 100
+                if ksplit:
                     fs = Fc // 3
-                    jobs = [dict(a=ha.data_ptr() + sp * (fs // 8) * Lp * 16, a_bs=(Fc // 8) * Lp * 16, w=W[f"t_f2_w{i}_k{sp}"],
+                    jobs = [dict(a=ha.data_ptr() + sp * (fs // 8) * cb, a_bs=(Fc // 8) * cb, w=W[f"t_f2_w{i}_k{sp}"],
                                  bias=(W[f"f2_b{i}"] if sp == 0 else None), mask=p.mask, y=(vy, V(y2, H, T), V(y3, H, T))[sp], K=ks) for sp in range(3)]
                     self._tc(p, f"ffn2_{i}", jobs, B=B, Cin=fs, Cout=H, L=T, dtype=dt, tag="enc")
                 else:
                     self._tc(p, f"ffn2_{i}", [dict(a=ha, w=W[f"t_f2_w{i}"], bias=W[f"f2_b{i}"], mask=p.mask, y=vy, K=ks)],
                              B=B, Cin=Fc, Cout=H, L=T, dtype=dt, tag="enc")
-                p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), y2.data_ptr() if split else None, y3.data_ptr() if split else None,
+                p.add(f"ln2_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), y2.data_ptr() if ksplit else None, y3.data_ptr() if ksplit else None,
                       W[f"ln2_g{i}"].data_ptr(), W[f"ln2_b{i}"].data_ptr(),
-                      p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 1 if i == c["nl"] - 1 else 0, xa.data_ptr(), dt, kind="layernorm_f32",
-                      bytes_=14.0 * B * H * T)
-            self._tc(p, "proj", [dict(a=xa, w=W["t_proj_w"], bias=W["proj_b"], mask=p.mask, y=vst)], B=B, Cin=H, Cout=2 * I, L=T, dtype=dt, tag="enc")
+                      p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 1 if i == c["nl"] - 1 else 0, xa.data_ptr(), adt, kind="layernorm_f32",
+                      bytes_=(12.0 + 2.0 * npl) * B * H * T)
+            gemm("proj", xa, H, "t_proj_w", 2 * I, dict(bias=W["proj_b"], mask=p.mask, y=vst))
             p.add("sample_zp", lib.rvc_sample_zp_f32, p.stats.data_ptr(), p.eps_z.data_ptr(), p.mask.data_ptr(), p.zp.data_ptr(), B, I, T)
             return p
         for i in range(c["nl"]):
@@ -534,7 +577,7 @@ class Engine:
               flops=2.0 * B * G * self.cond_total, bytes_=4.0 * G * self.cond_total, kind="cond_gemv_f32")
         z_t, zp_t = p.z, p.zp   # (capture the tensors, not the plan: a closure over `p` would be a reference cycle that keeps an evicted plan's workspace alive)
         p.add_py(lambda: z_t.copy_(zp_t))
-        for f in ((3, 2, 1, 0) if self.enc_tc else ()):
+        for f in ((3, 2, 1, 0) if self.flow_tc else ()):
             dt = DT_FP16
             if f == 3:
                 x0a, hpa, acta, oa = self._packed(p, B, half, T), self._packed(p, B, H, T), self._packed(p, B, H, T), self._packed(p, B, H, T)
@@ -558,7 +601,7 @@ class Engine:
             # x1 <- (x1 - post(...)*mask)*mask; its packed copy is the next coupling's x0
             self._tc(p, f"fl{f}_post", [dict(a=oa, w=W[f"t_fl{f}_post_w"], bias=W[f"fl{f}_post_b"], res=dst, alpha=-1.0, mask=p.mask, y=dst,
                                              y_act=(x0a if f > 0 else None))], B=B, Cin=H, Cout=half, L=T, dtype=dt, tag="flow")
-        for f in (() if self.enc_tc else (3, 2, 1, 0)):
+        for f in (() if self.flow_tc else (3, 2, 1, 0)):
             flipped = f in (3, 1)
             src = V(p.z, I, T, half if flipped else 0)
             dst = V(p.z, I, T, 0 if flipped else half)
@@ -585,7 +628,7 @@ class Engine:
                   scratch.data_ptr(), har.data_ptr(), B, T, upp, c["sr"], launches=2, bytes_=8.0 * B * Lfin, kind="sine_source_f32")
         xpre = self._buf(p, B, U, T)
         xpre_a = None
-        if self.enc_tc:
+        if self.flow_tc:
             za = self._packed(p, B, I, T)
             p.add("pack_z", lib.rvc_pack_act, p.z.data_ptr(), None, None, 1.0, I * T, T, p.mask.data_ptr(), za.data_ptr(), B, I, T, DT_FP16, 1.0, kind="pack_act",
                   bytes_=6.0 * B * I * T)

@@ -722,3 +722,99 @@ def test_tc_conv_split_stream_output():
     assert pad_rows_zero(yl, B, Cc, L, FP16, rows)
     d.dtype = BF16
     assert lib.rvc_conv1d_tc(C.byref(d), st) != 0 and b"y_lo" in lib.rvc_last_error()
+
+
+@pytest.mark.parametrize("Cin,Cout,L,B", [(192, 576, 1000, 2), (96, 256, 300, 3), (768, 192, 257, 1)])
+def test_split_precision_gemm_job_groups(Cin, Cout, L, B):
+    """sum_jobs = 3 over six jobs: two independent GEMMs, each as a_hi.W_hi + a_lo.W_hi + a_hi.W_lo in one accumulator (the encoder's
+    split-precision form).  Against fp64 on the UNROUNDED operands: <= 4e-6 * max|ref| (a plain fp16 launch is >= 30x worse), and the
+    [hi | lo] output planes reproduce the fp32 result to 2^-21."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(11 + Cin + L)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(L)
+    cb = rows * 16
+    d = _lib.Conv1dTcDesc()
+    d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.sum_jobs = 6, B, Cin, Cout, L, FP16, 3
+    dp = _lib.Conv1dTcDesc()
+    dp.njobs, dp.B, dp.Cin, dp.Cout, dp.L, dp.dtype = 2, B, Cin, Cout, L, FP16
+    keep, outs = [], []
+    for grp in range(2):
+        x = torch.randn(B, Cin, L, generator=g)
+        w = torch.randn(Cout, Cin, 1, generator=g) / Cin ** 0.5
+        bias = torch.randn(Cout, generator=g).to(DEV)
+        x_hi = x.half().float()
+        a = pack_host(torch.cat([x_hi, x - x_hi], 1), rows)                 # [hi | lo] planes, 2 * Cin / 8 chunks per item
+        w_hi = w.half().float()
+        wh, wl = torch.zeros(Cin * Cout * 2, dtype=torch.uint8, device=DEV), torch.zeros(Cin * Cout * 2, dtype=torch.uint8, device=DEV)
+        wd, wld = w.to(DEV), (w - w_hi).to(DEV)
+        _lib.check(lib.rvc_pack_weight(wd.data_ptr(), wh.data_ptr(), Cout, Cin, 1, FP16, st), "pack_weight")
+        _lib.check(lib.rvc_pack_weight(wld.data_ptr(), wl.data_ptr(), Cout, Cin, 1, FP16, st), "pack_weight")
+        y, yp = torch.zeros(B, Cout, L, device=DEV), torch.zeros(B, Cout, L, device=DEV)
+        ya = torch.zeros(B * 2 * (Cout // 8) * cb, dtype=torch.uint8, device=DEV)
+        a_bs = 2 * (Cin // 8) * cb
+        for t_i, (ao, wp) in enumerate(((0, wh), ((Cin // 8) * cb, wh), (0, wl))):
+            jb = d.jobs[3 * grp + t_i]
+            jb.a, jb.w, jb.a_bs = a.data_ptr() + ao, wp.data_ptr(), a_bs
+            jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = 1, 1, 0, 1.0, 1.0
+            if t_i == 0:
+                jb.bias, jb.y_f32, jb.y_bs, jb.y_cs = bias.data_ptr(), y.data_ptr(), Cout * L, L
+                jb.y_act, jb.y_act_bs, jb.y_lo = ya.data_ptr(), 2 * (Cout // 8) * cb, ya.data_ptr() + (Cout // 8) * cb
+        jb = dp.jobs[grp]
+        jb.a, jb.w, jb.a_bs, jb.bias = a.data_ptr(), wh.data_ptr(), a_bs, bias.data_ptr()
+        jb.y_f32, jb.y_bs, jb.y_cs = yp.data_ptr(), Cout * L, L
+        jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = 1, 1, 0, 1.0, 1.0
+        keep += [a, wh, wl, wd, wld, bias]
+        outs.append((x, w, bias, y, yp, ya))
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "split gemm")
+    _lib.check(lib.rvc_conv1d_tc(C.byref(dp), st), "plain gemm")
+    torch.cuda.synchronize()
+    for x, w, bias, y, yp, ya in outs:
+        ref = F.conv1d(x.double(), w.double(), bias.double().cpu())
+        scale = float(ref.abs().max())
+        e_split, e_plain = float((y.cpu().double() - ref).abs().max()), float((yp.cpu().double() - ref).abs().max())
+        assert e_split <= 4e-6 * scale, (e_split, scale)
+        assert e_plain >= 30 * e_split, (e_plain, e_split)
+        planes = ya.view(torch.float16).view(B, 2 * (Cout // 8), rows, 8)[:, :, 64:64 + L, :].permute(0, 1, 3, 2).reshape(B, 2 * Cout, L).float()
+        assert torch.equal(planes[:, :Cout], y.half().float())
+        assert bool(((planes[:, :Cout] + planes[:, Cout:] - y).abs() <= 2.0 ** -21 * y.abs() + 6e-8).all())
+
+
+def test_layernorm_and_pack_rows_split_planes():
+    """RVC_DT_FP16_SPLIT outputs of rvc_layernorm_f32 / rvc_pack_rows: [hi | lo] planes, hi identical to the plain fp16 output."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    B, H, T, D = 2, 192, 333, 768
+    g = torch.Generator(device="cpu").manual_seed(3)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(T)
+    x, r = torch.randn(B, H, T, generator=g).to(DEV), torch.randn(B, H, T, generator=g).to(DEV)
+    gamma, beta = torch.randn(H, generator=g).to(DEV), torch.randn(H, generator=g).to(DEV)
+    mask = (torch.arange(T)[None, :] < torch.tensor([T, T - 40])[:, None]).float().to(DEV)
+    y1, y2 = torch.zeros_like(x), torch.zeros_like(x)
+    p1 = torch.zeros(B * (H // 8) * rows * 16, dtype=torch.uint8, device=DEV)
+    p2 = torch.zeros(B * 2 * (H // 8) * rows * 16, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.rvc_layernorm_f32(x.data_ptr(), r.data_ptr(), None, None, gamma.data_ptr(), beta.data_ptr(), mask.data_ptr(), y1.data_ptr(), B, H, T, 1e-5, 0,
+                                     p1.data_ptr(), FP16, st), "ln")
+    _lib.check(lib.rvc_layernorm_f32(x.data_ptr(), r.data_ptr(), None, None, gamma.data_ptr(), beta.data_ptr(), mask.data_ptr(), y2.data_ptr(), B, H, T, 1e-5, 0,
+                                     p2.data_ptr(), 3, st), "ln split")
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    hi1 = unpack(p1, B, H, T, FP16, rows)
+    pl = p2.view(torch.float16).view(B, 2 * (H // 8), rows, 8)[:, :, 64:64 + T, :].permute(0, 1, 3, 2).reshape(B, 2 * H, T).float()
+    ym = y1 * mask[:, None, :]
+    assert torch.equal(pl[:, :H], hi1)
+    assert bool(((pl[:, :H] + pl[:, H:] - ym).abs() <= 2.0 ** -21 * ym.abs() + 6e-8).all())
+    ph = torch.randn(B, T, D, generator=g).to(DEV)
+    q1 = torch.zeros(B * (D // 8) * rows * 16, dtype=torch.uint8, device=DEV)
+    q2 = torch.zeros(B * 2 * (D // 8) * rows * 16, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.rvc_pack_rows(ph.data_ptr(), q1.data_ptr(), B, T, D, FP16, st), "pack_rows")
+    _lib.check(lib.rvc_pack_rows(ph.data_ptr(), q2.data_ptr(), B, T, D, 3, st), "pack_rows split")
+    torch.cuda.synchronize()
+    pl = q2.view(torch.float16).view(B, 2 * (D // 8), rows, 8)[:, :, 64:64 + T, :].permute(0, 1, 3, 2).reshape(B, 2 * D, T).float()
+    pt = ph.transpose(1, 2)
+    assert torch.equal(pl[:, :D], unpack(q1, B, D, T, FP16, rows))
+    assert bool(((pl[:, :D] + pl[:, D:] - pt).abs() <= 2.0 ** -21 * pt.abs() + 6e-8).all())
