@@ -147,8 +147,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
         if (p.B == 1) { b = 0; lt = r; }
         else { b = r / p.n_lt[j]; lt = r - b * p.n_lt[j]; }
     };
-    const int n_my = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
+    // snake walk over the cost-sorted tile list (heavy jobs first), see conv1d_tc.cu: even waves deal tiles to CTA 0..P-1, odd ones back
+    const int P = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int n_waves = p.total_tiles / P, rem = p.total_tiles - n_waves * P;
+    const int n_my = n_waves + ((((n_waves & 1) ? P - 1 - cta : cta) < rem) ? 1 : 0);
+    auto tile_of = [&](int it) { return it * P + ((it & 1) ? P - 1 - cta : cta); };
     // a *unit* is one (tile, job) conv pair: in the plain mode every tile is one unit of its own job; with sum_jobs a tile is
     // njobs consecutive units whose phase 2 accumulates into the same accumulator
     const int J = p.sum_jobs ? p.njobs : 1;
