@@ -232,6 +232,23 @@ typedef struct {
 int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);
 
 /*
+ * A chain of DEPENDENT rvc_conv1d_tc launches as ONE persistent kernel with a grid-wide barrier between the phases (the flow's
+ * 32 convs, residuals.py:87-95,127-137 + modules.py:35-51; the FFN pairs of the TextEncoder, synthesizers.py:302-315): at T = 1000
+ * such launches are latency-bound (8-9 us each for 1-2 us of tensor work); in a chain the weight stream of phase i+1 overlaps the
+ * epilogue of phase i and a phase boundary costs a barrier instead of a kernel boundary.  Phase i = descs[i] with the tile fixed
+ * at 128 x 64 (results bit-identical to rvc_conv1d_tc with nt = 64, mt = 1); restrictions: up <= 1, no per-batch weights (w_bs),
+ * no fused noise conv, njobs <= 3, Cout % 64 == 0 — a layer with fewer channels pads its packed weights with zero rows and
+ * passes the real count in cout_valid[i] (multiple of 32; NULL / 0 = Cout): only those channels are stored.
+ *   rvc_conv1d_tc_chain_build: host only; writes a 64-byte header + the phase table into `blob` (rvc_conv1d_tc_chain_blob_bytes(n)
+ *     bytes).  The caller copies the blob to 16-byte aligned DEVICE memory once and keeps the host copy of the header.
+ *   rvc_conv1d_tc_chain_run: one launch.  dev_sync: 4 zero-initialised uint32 in device memory owned by this chain (barrier counter,
+ *     exit counter, error flag [2] = 1 if a barrier timed out, spare); the kernel leaves the counters at zero.
+ */
+int64_t rvc_conv1d_tc_chain_blob_bytes(int32_t n);
+int rvc_conv1d_tc_chain_build(const rvc_conv1d_tc_desc* descs, const int32_t* cout_valid, int32_t n, void* blob, int64_t blob_cap);
+int rvc_conv1d_tc_chain_run(const void* host_header, const void* dev_blob, uint32_t* dev_sync, void* stream);
+
+/*
  * One ResBlock step  x' = c2(lrelu(c1_d(lrelu(x)) + b1)) + b2 + x  (ResBlockBase.forward, residuals.py:32-36) in ONE kernel for
  * the narrow generator stages (C = 32 or 64): the intermediate stays in shared memory as the second conv's tensor-core operand.
  * Up to three jobs (the three ResBlocks of a stage) per persistent launch.  Per job: a = packed lrelu(x) [B][C/8][rows][8];

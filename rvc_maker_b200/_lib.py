@@ -106,6 +106,9 @@ SIGNATURES = {
     "rvc_pack_act": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_conv1d_tc": (C.c_int, [C.POINTER(Conv1dTcDesc), _vp]),
+    "rvc_conv1d_tc_chain_blob_bytes": (C.c_int64, [_i32]),
+    "rvc_conv1d_tc_chain_build": (C.c_int, [C.POINTER(Conv1dTcDesc), C.POINTER(_i32), _i32, _vp, _i64]),
+    "rvc_conv1d_tc_chain_run": (C.c_int, [_vp, _vp, _vp, _vp]),
     "rvc_attn_softmax": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }
 

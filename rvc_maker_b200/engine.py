@@ -128,6 +128,9 @@ class Engine:
         # ... with the residual stream of those stages carried as two packed fp16 planes (hi = the conv operand, lo = the rounding
         # remainder: 22 bits in 4 bytes) instead of fp32 + a packed operand copy: 8 instead of 12 bytes per element and step
         self.pair_split = os.environ.get("RVC_B200_PAIR_SPLIT", "1") != "0"
+        # dependent short-sequence launches (the flow) as one persistent kernel with grid barriers between the layers (rvc_conv1d_tc_chain_*)
+        self.use_chain = os.environ.get("RVC_B200_CHAIN", "1") != "0"
+        self._chain = None
 
     # ------------------------------------------------------------------ weight folding / packing
     def _fold(self, m):
@@ -276,6 +279,9 @@ class Engine:
                 pre_w, post_w = _f(cp.pre.weight), _f(cp.post.weight)
                 if flipped:
                     pre_w, post_w = pre_w.flip(1), post_w.flip(0)
+                # (post: Cout = I/2 = 96 rows, padded with zero rows to a multiple of the chain kernel's 64-column tile)
+                self.post_rows = -(-post_w.shape[0] // 64) * 64
+                post_w = torch.cat([post_w, post_w.new_zeros(self.post_rows - post_w.shape[0], *post_w.shape[1:])], 0)
                 tc_w[f"t_fl{f}_pre_w"], tc_w[f"t_fl{f}_post_w"] = (pre_w.contiguous(), dt), (post_w.contiguous(), dt)
                 cw, cb = _fold_wn(cp.enc.cond_layer), _f(cp.enc.cond_layer.bias)
                 for l in range(3):
@@ -328,7 +334,7 @@ class Engine:
         bytes_ = 4.0 * (B * Cin * L + B * Cout * L * (1 + (res is not None) + (beta != 0.0)) + Cin * K * Cout * g2)
         plan.add(name, self.lib.rvc_conv1d_f32, C.byref(d), flops=flops, bytes_=bytes_, kind=f"conv1d_f32[C{Cout}k{K}]")
 
-    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag="", up=1, pshift=0, flops=None, blocked=0, sum_jobs=0):
+    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag="", up=1, pshift=0, flops=None, blocked=0, sum_jobs=0, cout_valid=None):
         """One persistent tcgen05 launch over up to six jobs (dicts of rvc_tc_job fields; V views for res / y)."""
         d = Conv1dTcDesc()
         d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.nt, d.mt = len(jobs), B, Cin, Cout, L, dtype, nt, mt
@@ -364,8 +370,30 @@ class Engine:
             by += B * L * (2.0 * Cin + up * ce * (4.0 * (j.get("res") is not None) + 4.0 * (j.get("y") is not None) + 2.0 * (j.get("y_act") is not None) + 2.0 * (j.get("y_lo") is not None)))
         plan.keep.append(d)
         plan.keep.append(jobs)
+        if self._chain is not None:     # inside a chain scope: collected, launched as one kernel by _chain_end
+            self._chain.append((d, cout_valid or 0, fl if flops is None else flops, by))
+            return
         plan.add(name, self.lib.rvc_conv1d_tc, C.byref(d), flops=fl if flops is None else flops, bytes_=by,
                  kind=f"conv1d_tc_{'bf16' if dtype == DT_BF16 else 'fp16'}[{tag or 'C%d' % Cout}]")
+
+    def _chain_begin(self):
+        self._chain = []
+
+    def _chain_end(self, plan, name, tag):
+        """Turn the rvc_conv1d_tc descriptors collected since _chain_begin into ONE persistent launch (rvc_conv1d_tc_chain_run)."""
+        items, self._chain = self._chain, None
+        n = len(items)
+        descs = (Conv1dTcDesc * n)(*[it[0] for it in items])
+        cv = (C.c_int32 * n)(*[it[1] for it in items])
+        nbytes = int(self.lib.rvc_conv1d_tc_chain_blob_bytes(n))
+        blob = (C.c_uint8 * nbytes)()
+        _lib.check(self.lib.rvc_conv1d_tc_chain_build(descs, cv, n, C.addressof(blob), nbytes), "rvc_conv1d_tc_chain_build")
+        dev_blob = torch.frombuffer(blob, dtype=torch.uint8).to(self.dev)
+        sync = torch.zeros(4, dtype=torch.int32, device=self.dev)
+        plan.keep += [descs, cv, blob, dev_blob, sync]
+        plan.chain_flags = getattr(plan, "chain_flags", []) + [sync]
+        plan.add(name, self.lib.rvc_conv1d_tc_chain_run, C.addressof(blob), dev_blob.data_ptr(), sync.data_ptr(), flops=sum(it[2] for it in items),
+                 bytes_=sum(it[3] for it in items), kind=f"conv1d_tc_chain[{tag}]")
 
     def _packed(self, plan, B, Cch, L):
         return self._zbuf(plan, B * Cch * int(self.lib.rvc_packed_rows(L)) * 2)
@@ -577,6 +605,7 @@ class Engine:
               flops=2.0 * B * G * self.cond_total, bytes_=4.0 * G * self.cond_total, kind="cond_gemv_f32")
         z_t, zp_t = p.z, p.zp   # (capture the tensors, not the plan: a closure over `p` would be a reference cycle that keeps an evicted plan's workspace alive)
         p.add_py(lambda: z_t.copy_(zp_t))
+        chain = self.flow_tc and self.use_chain and H % 64 == 0 and half % 32 == 0
         for f in ((3, 2, 1, 0) if self.flow_tc else ()):
             dt = DT_FP16
             if f == 3:
@@ -584,6 +613,8 @@ class Engine:
                 # x0 of the first coupling = (flipped) second half of z_p, not masked (residuals.py:128,137)
                 p.add("pack_x0", lib.rvc_pack_act, p.z.data_ptr() + half * T * 4, None, None, 1.0, I * T, T, None, x0a.data_ptr(), B, half, T, dt, 1.0,
                       kind="pack_act", bytes_=6.0 * B * half * T)
+                if chain:
+                    self._chain_begin()
             flipped = f in (3, 1)
             dst = V(p.z, I, T, 0 if flipped else half)
             self._tc(p, f"fl{f}_pre", [dict(a=x0a, w=W[f"t_fl{f}_pre_w"], bias=W[f"fl{f}_pre_b"], mask=p.mask, y=vh, y_act=hpa)],
@@ -599,8 +630,13 @@ class Engine:
                     jobs = [dict(a=acta, w=W[f"t_fl{f}_skip_w{l}"], bias=W[f"fl{f}_skip_b{l}"], res=vo, mask=p.mask, y_act=oa)]
                 self._tc(p, f"fl{f}_rs{l}", jobs, B=B, Cin=H, Cout=H, L=T, dtype=dt, tag="flow")
             # x1 <- (x1 - post(...)*mask)*mask; its packed copy is the next coupling's x0
-            self._tc(p, f"fl{f}_post", [dict(a=oa, w=W[f"t_fl{f}_post_w"], bias=W[f"fl{f}_post_b"], res=dst, alpha=-1.0, mask=p.mask, y=dst,
-                                             y_act=(x0a if f > 0 else None))], B=B, Cin=H, Cout=half, L=T, dtype=dt, tag="flow")
+            post = dict(a=oa, w=W[f"t_fl{f}_post_w"], bias=W[f"fl{f}_post_b"], res=dst, alpha=-1.0, mask=p.mask, y=dst, y_act=(x0a if f > 0 else None))
+            if chain:
+                self._tc(p, f"fl{f}_post", [post], B=B, Cin=H, Cout=self.post_rows, cout_valid=half, L=T, dtype=dt, tag="flow")
+            else:
+                self._tc(p, f"fl{f}_post", [dict(post, w_cs=self.post_rows)], B=B, Cin=H, Cout=half, L=T, dtype=dt, tag="flow")
+            if chain and f == 0:
+                self._chain_end(p, "flow_chain", "flow")
         for f in (() if self.flow_tc else (3, 2, 1, 0)):
             flipped = f in (3, 1)
             src = V(p.z, I, T, half if flipped else 0)

@@ -819,3 +819,101 @@ def test_layernorm_and_pack_rows_split_planes():
     pt = ph.transpose(1, 2)
     assert torch.equal(pl[:, :D], unpack(q1, B, D, T, FP16, rows))
     assert bool(((pl[:, :D] + pl[:, D:] - pt).abs() <= 2.0 ** -21 * pt.abs() + 6e-8).all())
+
+
+@pytest.mark.parametrize("B,T", [(1, 1000), (2, 130), (3, 64)])
+def test_conv_chain_equals_separate_launches(B, T):
+    """rvc_conv1d_tc_chain_*: a WaveNet-like chain (k = 5 gated conv -> res / skip 1x1 pair -> 1x1 into 96 channels from zero-padded
+    weights, twice over, every phase reading what the previous one wrote, in-place residual updates) as ONE persistent kernel with grid
+    barriers — bit-identical to the same descriptors launched one by one through rvc_conv1d_tc, replayed three times (the barrier
+    counters must come back to zero)."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    H, half = 192, 96
+    g = torch.Generator(device="cpu").manual_seed(1000 * B + T)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(T)
+    keep = []
+
+    def wpack(cout, cin, k, pad_to=None, perm=None):
+        w = torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5
+        if perm is not None:
+            w = w[perm]
+        if pad_to:
+            w = torch.cat([w, torch.zeros(pad_to - cout, cin, k)], 0)
+        wd = w.to(DEV).contiguous()
+        out = torch.zeros(wd.numel() * 2, dtype=torch.uint8, device=DEV)
+        _lib.check(lib.rvc_pack_weight(wd.data_ptr(), out.data_ptr(), wd.shape[0], cin, k, FP16, st), "pack_weight")
+        keep.append(out)
+        return out
+
+    vec = lambda n: torch.randn(n, generator=g).to(DEV)
+    mask = (torch.arange(T)[None, :] < torch.randint(T // 2, T + 1, (B,), generator=g)[:, None]).float().to(DEV)
+    perm = gate_perm(H, 64)
+    layers = [dict(w_in=wpack(2 * H, H, 5, perm=perm), b_in=vec(2 * H), w_res=wpack(H, H, 1), b_res=vec(H), w_skip=wpack(H, H, 1), b_skip=vec(H),
+                   w_post=wpack(half, H, 1, pad_to=128), b_post=vec(half)) for _ in range(2)]
+    x0 = torch.randn(B, H, T, generator=g)
+    z0 = torch.randn(B, half, T, generator=g)
+
+    def state():
+        h = (x0 * mask.cpu()[:, None, :]).to(DEV).contiguous()
+        hp = pack_host(x0 * mask.cpu()[:, None, :], rows)
+        return dict(h=h, hp=hp, acts=torch.zeros(B * H * rows * 2, dtype=torch.uint8, device=DEV), skip=torch.zeros(B, H, T, device=DEV),
+                    z=z0.to(DEV).contiguous(), za=torch.zeros(B * half * rows * 2, dtype=torch.uint8, device=DEV))
+
+    def descs(s, chain):
+        out, cvs = [], []
+        for li, ly in enumerate(layers):
+            d = _lib.Conv1dTcDesc()
+            d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.nt, d.mt = 1, B, H, 2 * H, T, FP16, 64, 1
+            jb = d.jobs[0]
+            jb.a, jb.w, jb.bias, jb.y_act = s["hp"].data_ptr(), ly["w_in"].data_ptr(), ly["b_in"].data_ptr(), s["acts"].data_ptr()
+            jb.K, jb.dil, jb.pad, jb.gated, jb.alpha, jb.act_slope = 5, 1, 2, 1, 1.0, 1.0
+            out.append(d); cvs.append(0)
+            d = _lib.Conv1dTcDesc()
+            d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.nt, d.mt = 2, B, H, H, T, FP16, 64, 1
+            jb = d.jobs[0]     # h <- (h + res(acts)) * mask, packed copy for the next layer
+            jb.a, jb.w, jb.bias, jb.mask = s["acts"].data_ptr(), ly["w_res"].data_ptr(), ly["b_res"].data_ptr(), mask.data_ptr()
+            jb.res, jb.res_bs, jb.res_cs, jb.y_f32, jb.y_bs, jb.y_cs, jb.y_act = s["h"].data_ptr(), H * T, T, s["h"].data_ptr(), H * T, T, s["hp"].data_ptr()
+            jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = 1, 1, 0, 1.0, 1.0
+            jb = d.jobs[1]     # skip += skip(acts)
+            jb.a, jb.w, jb.bias = s["acts"].data_ptr(), ly["w_skip"].data_ptr(), ly["b_skip"].data_ptr()
+            jb.res, jb.res_bs, jb.res_cs, jb.y_f32, jb.y_bs, jb.y_cs = s["skip"].data_ptr(), H * T, T, s["skip"].data_ptr(), H * T, T
+            jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = 1, 1, 0, 1.0, 1.0
+            out.append(d); cvs.append(0)
+            d = _lib.Conv1dTcDesc()    # z <- (z - post(hp)) * mask   (96 real channels, weights padded to 128 rows)
+            d.njobs, d.B, d.Cin, d.L, d.dtype = 1, B, H, T, FP16
+            jb = d.jobs[0]
+            jb.a, jb.w, jb.bias, jb.mask = s["hp"].data_ptr(), ly["w_post"].data_ptr(), ly["b_post"].data_ptr(), mask.data_ptr()
+            jb.res, jb.res_bs, jb.res_cs, jb.y_f32, jb.y_bs, jb.y_cs, jb.y_act = s["z"].data_ptr(), half * T, T, s["z"].data_ptr(), half * T, T, s["za"].data_ptr()
+            jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = 1, 1, 0, -1.0, 0.1
+            if chain:
+                d.Cout, d.nt, d.mt = 128, 64, 1
+                cvs.append(half)
+            else:
+                d.Cout, d.nt, d.mt, jb.w_cs = half, 32, 1, 128
+                cvs.append(0)
+            out.append(d)
+        return out, cvs
+
+    ref = state()
+    for d in descs(ref, False)[0]:
+        _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "separate launch")
+    torch.cuda.synchronize()
+    assert float(ref["h"].abs().max()) > 0.5 and float(ref["skip"].abs().max()) > 0.5
+    sync = torch.zeros(4, dtype=torch.int32, device=DEV)
+    for rep in range(3):
+        cand = state()
+        dl, cvs = descs(cand, True)
+        n = len(dl)
+        arr, cv = (_lib.Conv1dTcDesc * n)(*dl), (C.c_int32 * n)(*cvs)
+        nbytes = lib.rvc_conv1d_tc_chain_blob_bytes(n)
+        blob = (C.c_uint8 * nbytes)()
+        _lib.check(lib.rvc_conv1d_tc_chain_build(arr, cv, n, C.addressof(blob), nbytes), "chain build")
+        dev_blob = torch.frombuffer(blob, dtype=torch.uint8).to(DEV)
+        _lib.check(lib.rvc_conv1d_tc_chain_run(C.addressof(blob), dev_blob.data_ptr(), sync.data_ptr(), st), "chain run")
+        torch.cuda.synchronize()
+        assert sync.tolist() == [0, 0, 0, 0], (rep, sync.tolist())      # counters reset, no barrier timed out
+        for k in ("h", "hp", "acts", "skip", "z", "za"):
+            assert torch.equal(cand[k], ref[k]), (rep, k)
