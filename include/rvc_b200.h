@@ -249,6 +249,31 @@ int rvc_conv1d_tc_chain_build(const rvc_conv1d_tc_desc* descs, const int32_t* co
 int rvc_conv1d_tc_chain_run(const void* host_header, const void* dev_blob, uint32_t* dev_sync, void* stream);
 
 /*
+ * The reverse ResidualCouplingBlock in ONE kernel (residuals.py:87-95, :127-137; WaveNet modules.py:35-51) for the standard RVC flow:
+ * 4 couplings of 2 x 96 channels, WaveNet of 3 layers, hidden 192, kernel 5.  A cluster of six CTAs carries a tile of 128 frames (80 kept,
+ * 24 frames of halo per side recomputed) through all 32 convs: operands are exchanged through distributed shared memory, the hidden stream
+ * and the skip sum are accumulated in TMEM, weights stream from L2; global memory is touched for z_p (read once) and z (written once).
+ * Per coupling f (index = position in flow.flows / 2; processed 3, 2, 1, 0; the four Flips folded into channel-reversed pre / post weights
+ * by the caller): packed fp16 weights as for rvc_conv1d_tc — pre_w [192 <- 96], in_w[l] [384 <- 192, k = 5] with its columns gate-ordered
+ * (per 64 columns: 32 tanh then the matching 32 sigmoid), res_w[l] / skip_w[l] [192 <- 192] (l = 2: all of res_skip_layers[2] is skip),
+ * post_w [post_rows >= 96 <- 192] (zero rows past 96); fp32 biases: hb[l] = b_pre + sum_{l' < l} b_res[l'] (what the hidden stream lacks
+ * when in_layers[l] reads it), in_b[l] gate-ordered, sb = sum_l b_skip[l], post_b; gc = cond_layer(g) [B][...] with row stride gc_bs,
+ * gate-ordered, 3 x 384 values per coupling from gc_off.  x0 / x1 = the halves of z_p [B, 192, T] (coupling 3 and 1 read the second half
+ * and update the first, 2 and 0 the other way round); z [B, 192, T] receives the result, za (optional) its masked packed fp16 copy.
+ */
+typedef struct {
+    const void* pre_w; const void* in_w[3]; const void* res_w[2]; const void* skip_w[3]; const void* post_w;
+    const float* hb[3]; const float* in_b[3]; const float* sb; const float* post_b;
+    int32_t gc_off, reserved;
+} rvc_flow_coupling;
+typedef struct {
+    rvc_flow_coupling flows[4];
+    const float* zp; float* z; void* za; const float* mask; const float* gc; int64_t gc_bs;
+    int32_t B, T, hidden, half, n_flows, n_layers, kernel_size, post_rows;
+} rvc_flow_desc;
+int rvc_flow_reverse_tc(const rvc_flow_desc* d, void* stream);
+
+/*
  * One ResBlock step  x' = c2(lrelu(c1_d(lrelu(x)) + b1)) + b2 + x  (ResBlockBase.forward, residuals.py:32-36) in ONE kernel for
  * the narrow generator stages (C = 32 or 64): the intermediate stays in shared memory as the second conv's tensor-core operand.
  * Up to three jobs (the three ResBlocks of a stage) per persistent launch.  Per job: a = packed lrelu(x) [B][C/8][rows][8];

@@ -76,6 +76,19 @@ class PairJob(C.Structure):
                 ("K1", _i32), ("dil1", _i32), ("K2", _i32), ("reserved", _i32), ("a_lo", _vp), ("y_lo", _vp)]
 
 
+class FlowCoupling(C.Structure):
+    """rvc_flow_coupling."""
+    _fields_ = [("pre_w", _vp), ("in_w", _vp * 3), ("res_w", _vp * 2), ("skip_w", _vp * 3), ("post_w", _vp),
+                ("hb", _vp * 3), ("in_b", _vp * 3), ("sb", _vp), ("post_b", _vp), ("gc_off", _i32), ("reserved", _i32)]
+
+
+class FlowDesc(C.Structure):
+    """rvc_flow_desc."""
+    _fields_ = [("flows", FlowCoupling * 4), ("zp", _vp), ("z", _vp), ("za", _vp), ("mask", _vp), ("gc", _vp), ("gc_bs", _i64),
+                ("B", _i32), ("T", _i32), ("hidden", _i32), ("half", _i32), ("n_flows", _i32), ("n_layers", _i32), ("kernel_size", _i32),
+                ("post_rows", _i32)]
+
+
 class ResblockPairDesc(C.Structure):
     """rvc_resblock_pair_desc."""
     _fields_ = [("jobs", PairJob * 3), ("njobs", _i32), ("B", _i32), ("C", _i32), ("L", _i32), ("dtype", _i32), ("slope", _f32),
@@ -106,6 +119,7 @@ SIGNATURES = {
     "rvc_pack_act": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_conv1d_tc": (C.c_int, [C.POINTER(Conv1dTcDesc), _vp]),
+    "rvc_flow_reverse_tc": (C.c_int, [C.POINTER(FlowDesc), _vp]),
     "rvc_conv1d_tc_chain_blob_bytes": (C.c_int64, [_i32]),
     "rvc_conv1d_tc_chain_build": (C.c_int, [C.POINTER(Conv1dTcDesc), C.POINTER(_i32), _i32, _vp, _i64]),
     "rvc_conv1d_tc_chain_run": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -14,7 +14,7 @@ import threading
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc, ResblockPairDesc
+from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc, FlowDesc, ResblockPairDesc
 
 LRELU_SLOPE = 0.1
 WINDOW = 10
@@ -130,6 +130,8 @@ class Engine:
         self.pair_split = os.environ.get("RVC_B200_PAIR_SPLIT", "1") != "0"
         # dependent short-sequence launches (the flow) as one persistent kernel with grid barriers between the layers (rvc_conv1d_tc_chain_*)
         self.use_chain = os.environ.get("RVC_B200_CHAIN", "1") != "0"
+        # ... or, for the standard flow shape, the whole reverse flow as one cluster kernel that keeps every intermediate on the chip (rvc_flow_reverse_tc)
+        self.use_flow_cluster = os.environ.get("RVC_B200_FLOW_CLUSTER", "1") != "0"
         self._chain = None
 
     # ------------------------------------------------------------------ weight folding / packing
@@ -294,6 +296,14 @@ class Engine:
                         tc_w[f"t_fl{f}_skip_w{l}"] = (rs_w.contiguous(), dt)
                     cond_w2.append(cw[l * 2 * H:(l + 1) * 2 * H][perm])
                     cond_b2.append(cb[l * 2 * H:(l + 1) * 2 * H][perm])
+            # rvc_flow_reverse_tc accumulates the hidden stream / skip sum in TMEM and adds the biases when it reads them
+            for f in range(4):
+                acc = W[f"fl{f}_pre_b"].clone()
+                for l in range(3):
+                    W[f"t_fl{f}_hb{l}"] = acc.clone()
+                    if l < 2:
+                        acc = acc + W[f"fl{f}_res_b{l}"]
+                W[f"t_fl{f}_sb"] = (W[f"fl{f}_skip_b0"] + W[f"fl{f}_skip_b1"] + W[f"fl{f}_skip_b2"]).contiguous()
             cond_w2.append(_f(m.dec.cond.weight))
             cond_b2.append(_f(m.dec.cond.bias))
             W["cond_w"] = _pack_conv(torch.cat(cond_w2, 0))      # same layout as before, gate-permuted rows
@@ -603,10 +613,30 @@ class Engine:
         # speaker conditioning: cond_layer(g) x4 + dec.cond(g) in one launch (modules.py:39, synthesizers.py:147)
         p.add("cond", lib.rvc_cond_gemv_f32, p.g.data_ptr(), W["cond_w"].data_ptr(), W["cond_b"].data_ptr(), gc.data_ptr(), B, G, self.cond_total,
               flops=2.0 * B * G * self.cond_total, bytes_=4.0 * G * self.cond_total, kind="cond_gemv_f32")
-        z_t, zp_t = p.z, p.zp   # (capture the tensors, not the plan: a closure over `p` would be a reference cycle that keeps an evicted plan's workspace alive)
-        p.add_py(lambda: z_t.copy_(zp_t))
+        cluster = self.flow_tc and self.use_flow_cluster and (H, half) == (192, 96)     # (the flow's WaveNet is always 3 layers of k = 5, x 4 couplings)
+        za = self._packed(p, B, I, T) if self.flow_tc else None       # masked packed z: conv_pre's operand
+        if cluster:
+            # ---- the whole reverse flow in one cluster kernel: reads z_p, writes z and its packed copy
+            fd = FlowDesc()
+            for f in range(4):
+                cp = fd.flows[f]
+                cp.pre_w, cp.post_w = W[f"t_fl{f}_pre_w"].data_ptr(), W[f"t_fl{f}_post_w"].data_ptr()
+                cp.post_b, cp.sb, cp.gc_off = W[f"fl{f}_post_b"].data_ptr(), W[f"t_fl{f}_sb"].data_ptr(), self.cond_off[f]
+                for l in range(3):
+                    cp.in_w[l], cp.in_b[l], cp.hb[l] = W[f"t_fl{f}_in_w{l}"].data_ptr(), W[f"t_fl{f}_in_b{l}"].data_ptr(), W[f"t_fl{f}_hb{l}"].data_ptr()
+                    cp.skip_w[l] = W[f"t_fl{f}_skip_w{l}"].data_ptr()
+                    if l < 2:
+                        cp.res_w[l] = W[f"t_fl{f}_res_w{l}"].data_ptr()
+            fd.zp, fd.z, fd.za, fd.mask, fd.gc, fd.gc_bs = p.zp.data_ptr(), p.z.data_ptr(), za.data_ptr(), p.mask.data_ptr(), gc.data_ptr(), self.cond_total
+            fd.B, fd.T, fd.hidden, fd.half, fd.n_flows, fd.n_layers, fd.kernel_size, fd.post_rows = B, T, H, half, 4, 3, 5, self.post_rows
+            p.keep.append(fd)
+            p.add("flow_cluster", lib.rvc_flow_reverse_tc, C.byref(fd), flops=4 * (2.0 * B * T * (half * H + 3 * H * 2 * H * 5 + 2 * H * 2 * H + H * H + H * half)),
+                  bytes_=4.0 * B * I * T * 2 + 2.0 * B * I * T, kind="flow_cluster_tc")
+        else:
+            z_t, zp_t = p.z, p.zp   # (capture the tensors, not the plan: a closure over `p` would be a reference cycle that keeps an evicted plan's workspace alive)
+            p.add_py(lambda: z_t.copy_(zp_t))
         chain = self.flow_tc and self.use_chain and H % 64 == 0 and half % 32 == 0
-        for f in ((3, 2, 1, 0) if self.flow_tc else ()):
+        for f in ((3, 2, 1, 0) if (self.flow_tc and not cluster) else ()):
             dt = DT_FP16
             if f == 3:
                 x0a, hpa, acta, oa = self._packed(p, B, half, T), self._packed(p, B, H, T), self._packed(p, B, H, T), self._packed(p, B, H, T)
@@ -665,9 +695,9 @@ class Engine:
         xpre = self._buf(p, B, U, T)
         xpre_a = None
         if self.flow_tc:
-            za = self._packed(p, B, I, T)
-            p.add("pack_z", lib.rvc_pack_act, p.z.data_ptr(), None, None, 1.0, I * T, T, p.mask.data_ptr(), za.data_ptr(), B, I, T, DT_FP16, 1.0, kind="pack_act",
-                  bytes_=6.0 * B * I * T)
+            if not cluster:
+                p.add("pack_z", lib.rvc_pack_act, p.z.data_ptr(), None, None, 1.0, I * T, T, p.mask.data_ptr(), za.data_ptr(), B, I, T, DT_FP16, 1.0, kind="pack_act",
+                      bytes_=6.0 * B * I * T)
             xpre_a = self._packed(p, B, U, T) if self.up_dt[0] == DT_FP16 else None
             self._tc(p, "conv_pre", [dict(a=za, w=W["t_pre_w"], bias=W["pre_b"], K=7, y=V(xpre, U, T), y_act=xpre_a, act_slope=LRELU_SLOPE,
                                           bias_b=gc.data_ptr() + self.cond_off[4] * 4, bias_b_bs=self.cond_total)],

@@ -281,3 +281,28 @@ def test_infer_to_host_matches_infer():
         got = net.infer_to_host(*a)
         assert got.device.type == "cpu" and got.is_pinned() and got.dtype == torch.float32 and got.shape == want.shape
         assert torch.equal(got, want.float().cpu())
+
+
+@pytest.mark.parametrize("B,T", [(1, 1000), (2, 173), (3, 80), (2, 81), (1, 1), (40, 64)])
+def test_flow_cluster_kernel_matches_per_layer_path(B, T, monkeypatch):
+    """rvc_flow_reverse_tc (one cluster kernel, operands through distributed shared memory, state in TMEM) against the per-layer path on the
+    same model: same fp16 operand rounding points, only the fp32 summation order of the hidden stream differs -> z agrees to ~1e-5 * max|z|
+    (tile seams at multiples of 80 frames, ragged lengths, T below one tile)."""
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=31, heated=True)
+    inp = cases.synth_inputs(cfg, B, T, seed=7 * B + T, ragged=B > 1)
+    monkeypatch.setenv("RVC_B200_FLOW_CLUSTER", "0")
+    ref_net = build_net(cfg, sd, True, precision="tc")
+    ref = run_net(ref_net, inp)
+    assert not any(m and m["name"] == "flow_cluster" for m in ref_net._engine.plan("dec", B, T).meta)
+    monkeypatch.setenv("RVC_B200_FLOW_CLUSTER", "1")
+    net = build_net(cfg, sd, True, precision="tc")
+    out = run_net(net, inp)
+    assert any(m and m["name"] == "flow_cluster" for m in net._engine.plan("dec", B, T).meta)
+    scale = float(ref["z"].abs().max())
+    assert torch.isfinite(out["z"]).all()
+    err = float((out["z"] - ref["z"]).abs().max())
+    assert err <= 2e-4 * max(1.0, scale), (err, scale)
+    assert float((out["o"] - ref["o"]).abs().max()) <= 2e-4
+    again = run_net(net, inp)      # captured graph
+    assert torch.equal(again["z"], out["z"]) and torch.equal(again["o"], out["o"])
