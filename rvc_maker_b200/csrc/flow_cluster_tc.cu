@@ -35,7 +35,7 @@ constexpr int HALO = (KW - 1) / 2 * NL * NF;   // 24 frames per side
 constexpr int KEEP = BM - 2 * HALO;            // 80 frames kept per tile
 constexpr int HPAD = (KW - 1) / 2;             // zero rows around the h tile
 constexpr int HROWS = BM + 2 * HPAD;
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 6;             // weight ring: 96 KB (an in_layer slice is 120 KB: the stream is latency-bound, depth is what hides it)
 constexpr int STAGE_BYTES = 16384;
 constexpr int NTHREADS = 256;      // warp 0: weight producer, warp 1: MMA issuer, warps 4-7: epilogue (TMEM lane quarter = warp % 4)
 constexpr int PADL = 64;
@@ -76,22 +76,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
+// bulk copy own shared memory -> a peer CTA's shared memory (async proxy), completing `bytes` on the PEER's mbarrier
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
 }
 // generic -> async proxy ordering for every state space (the operand tiles are written through the cluster's shared-memory window)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -138,7 +127,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) flow_cluster_kernel(const FlowPar
     const uint32_t bar0 = tc::smem_u32(bars);
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
     auto W_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
-    const uint32_t OPR = bar0 + 8u * (2 * NSTAGE);          // operands of the next layer are complete (24 arrivals: 6 CTAs x 4 epilogue warps)
+    const uint32_t OPR = bar0 + 8u * (2 * NSTAGE);          // operands of the next layer are complete: own slice written + the five peers' slices landed
     const uint32_t ACC_FULL = bar0 + 8u * (2 * NSTAGE + 1);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2);
     const uint32_t xt = tc::smem_u32(xt_s), ht = tc::smem_u32(ht_s), at = tc::smem_u32(at_s);
@@ -152,7 +141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) flow_cluster_kernel(const FlowPar
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(W_FULL(s), 1); tc::mbar_init(W_EMPTY(s), 1); }
-        tc::mbar_init(OPR, CS * 4);
+        tc::mbar_init(OPR, 1);
         tc::mbar_init(ACC_FULL, 1);
         tc::fence_barrier_init();
     }
@@ -201,8 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) flow_cluster_kernel(const FlowPar
         uint32_t wst = 0, wph = 0;
         for (int ph = 0; ph < NF * 8; ++ph) {
             const int f = NF - 1 - (ph >> 3), t = ph & 7;
-            mbar_wait_cluster(OPR, (uint32_t)(ph & 1));                 // this layer's operands: written by all six CTAs (generic proxy, DSMEM)
-            fence_proxy_async_all();                                    // ... ordered before the tensor core's async-proxy reads
+            tc::mbar_wait(OPR, (uint32_t)(ph & 1));                     // this layer's operands: own slice + five slices copied in by the peers
             tc::fence_after_sync();
             for (int wc = 0; wc < n_chains(t); ++wc) {
                 const Chain ch = get_chain(p, f, t, wc, c, xt, ht, at);
@@ -243,24 +231,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) flow_cluster_kernel(const FlowPar
         const bool inside = pos >= 0 && pos < p.T;
         const float mk = inside ? p.mask[(size_t)b * p.T + pos] : 0.f;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t opr_remote[CS], xt_r[CS], ht_r[CS], at_r[CS];
+        const int er = threadIdx.x - 128;      // 0 .. 127
+        // Publish this CTA's channel slice of an operand tile: every thread stores its frame's 16-byte chunks into the LOCAL tile, the slice
+        // (whole 8-channel chunks, contiguous) is then copied into the same place of the five peers' tiles by the copy engine
+        // (cp.async.bulk shared::cta -> shared::cluster), which completes the bytes on the peer's OPR barrier; this CTA's own OPR phase
+        // expects the five slices coming the other way.  (Per-thread st.shared::cluster stores to six CTAs cost the epilogue 24 stores
+        // per thread and the SM's shared-memory port ~1.4 us per layer.)
+        auto publish = [&](uint8_t* tile, uint32_t tile_addr, int rows, int row, int chunk0, const uint4* pk, int nchunk) {
+            for (int u = 0; u < nchunk; ++u) *reinterpret_cast<uint4*>(tile + ((size_t)(chunk0 + u) * rows + row) * 16) = pk[u];
+            fence_proxy_async_all();                       // generic stores -> visible to the async proxy (bulk-copy source, tensor-core operand)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (er == 0) {
+                const uint32_t bytes = (uint32_t)(nchunk * rows * 16), off = (uint32_t)(chunk0 * rows * 16);
+                tc::mbar_arrive_expect_tx(OPR, (CS - 1) * bytes);
 #pragma unroll
-        for (int k = 0; k < CS; ++k) {
-            opr_remote[k] = mapa(OPR, (uint32_t)k);
-            xt_r[k] = mapa(xt, (uint32_t)k);
-            ht_r[k] = mapa(ht, (uint32_t)k);
-            at_r[k] = mapa(at, (uint32_t)k);
-        }
-        // publish nchunk 16-byte chunks (8 channels each) of this frame into the same tile of all six CTAs, then signal them
-        auto publish = [&](const uint32_t (&tile_r)[CS], int rows, int row, int chunk0, const uint4* pk, int nchunk) {
-#pragma unroll
-            for (int k = 0; k < CS; ++k)
-                for (int u = 0; u < nchunk; ++u) st_cluster_v4(tile_r[k] + (uint32_t)(((chunk0 + u) * rows + row) * 16), pk[u]);
-            fence_proxy_async_all();
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < CS; ++k) mbar_arrive_remote(opr_remote[k]);
+                for (int k = 1; k < CS; ++k) {
+                    const uint32_t peer = (uint32_t)((c + k) % CS);
+                    bulk_s2peer(mapa(tile_addr + off, peer), tile_addr + off, bytes, mapa(OPR, peer));
+                }
             }
         };
         // the two coupling halves of this CTA's 16-channel slice: xa = the half read as x0 by the next coupling, xb = the half it updates
@@ -277,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) flow_cluster_kernel(const FlowPar
             for (int u = 0; u < 2; ++u)
                 pk[u] = make_uint4(pack2h(xa[8 * u + 0], xa[8 * u + 1]), pack2h(xa[8 * u + 2], xa[8 * u + 3]), pack2h(xa[8 * u + 4], xa[8 * u + 5]),
                                    pack2h(xa[8 * u + 6], xa[8 * u + 7]));
-            publish(xt_r, BM, r, 2 * c, pk, 2);
+            publish(xt_s, xt, BM, r, 2 * c, pk, 2);
         }
         const float* gcb = p.gc + (size_t)b * p.gc_bs;
         for (int ph = 0; ph < NF * 8; ++ph) {
@@ -303,7 +291,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) flow_cluster_kernel(const FlowPar
                         pk[u] = make_uint4(pack2h(xa[8 * u + 0], xa[8 * u + 1]), pack2h(xa[8 * u + 2], xa[8 * u + 3]), pack2h(xa[8 * u + 4], xa[8 * u + 5]),
                                            pack2h(xa[8 * u + 6], xa[8 * u + 7]));
                     tc::fence_before_sync();
-                    publish(xt_r, BM, r, 2 * c, pk, 2);
+                    publish(xt_s, xt, BM, r, 2 * c, pk, 2);
                 }
             } else if (t & 1) {
                 // ---- in_layer: acts = tanh(a_t) * sigmoid(a_s), a = acc + b_in + cond  (commons.py:35-41); not masked (modules.py:45)
@@ -312,21 +300,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) flow_cluster_kernel(const FlowPar
                 tc::tmem_ld<32>(t_row + COL_G, vt);
                 tc::tmem_ld<32>(t_row + COL_G + 32, vs);
                 tc::tmem_ld_wait();
-                const float* ib = p.in_b[f][l] + 64 * c;
-                const float* cb = gcb + p.gc_off[f] + l * 2 * H + 64 * c;
+                const float4* ib = reinterpret_cast<const float4*>(p.in_b[f][l] + 64 * c);                       // 16 x (tanh) then 16 x (sigmoid)
+                const float4* cb = reinterpret_cast<const float4*>(gcb + p.gc_off[f] + l * 2 * H + 64 * c);
                 uint4 pk[4];
                 uint32_t w[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float a0 = gate_fast(__uint_as_float(vt[i]) + __ldg(ib + i) + __ldg(cb + i), __uint_as_float(vs[i]) + __ldg(ib + 32 + i) + __ldg(cb + 32 + i));
-                    const float a1 = gate_fast(__uint_as_float(vt[i + 1]) + __ldg(ib + i + 1) + __ldg(cb + i + 1),
-                                               __uint_as_float(vs[i + 1]) + __ldg(ib + 33 + i) + __ldg(cb + 33 + i));
-                    w[i >> 1] = pack2h(a0, a1);
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 bt = __ldg(ib + i4), bs_ = __ldg(ib + 8 + i4), ct = __ldg(cb + i4), cs_ = __ldg(cb + 8 + i4);
+                    const float a0 = gate_fast(__uint_as_float(vt[4 * i4 + 0]) + bt.x + ct.x, __uint_as_float(vs[4 * i4 + 0]) + bs_.x + cs_.x);
+                    const float a1 = gate_fast(__uint_as_float(vt[4 * i4 + 1]) + bt.y + ct.y, __uint_as_float(vs[4 * i4 + 1]) + bs_.y + cs_.y);
+                    const float a2 = gate_fast(__uint_as_float(vt[4 * i4 + 2]) + bt.z + ct.z, __uint_as_float(vs[4 * i4 + 2]) + bs_.z + cs_.z);
+                    const float a3 = gate_fast(__uint_as_float(vt[4 * i4 + 3]) + bt.w + ct.w, __uint_as_float(vs[4 * i4 + 3]) + bs_.w + cs_.w);
+                    w[2 * i4] = pack2h(a0, a1);
+                    w[2 * i4 + 1] = pack2h(a2, a3);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) pk[u] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
                 tc::fence_before_sync();
-                publish(at_r, BM, r, 4 * c, pk, 4);
+                publish(at_s, at, BM, r, 4 * c, pk, 4);
             } else {
                 // ---- pre / res+skip: read the hidden stream (t = 0, 2, 4: the next in_layer's operand) or the finished skip sum (t = 6: post's operand)
                 const bool skip = t == 6;
@@ -342,8 +333,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) flow_cluster_kernel(const FlowPar
 #pragma unroll
                 for (int u = 0; u < 4; ++u) pk[u] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
                 tc::fence_before_sync();
-                if (skip) publish(at_r, BM, r, 4 * c, pk, 4);
-                else publish(ht_r, HROWS, r + HPAD, 4 * c, pk, 4);
+                if (skip) publish(at_s, at, BM, r, 4 * c, pk, 4);
+                else publish(ht_s, ht, HROWS, r + HPAD, 4 * c, pk, 4);     // (whole chunks travel, zero rows included)
             }
         }
         // ---- result: z = [first half | second half], fp32 [B, 192, T] and (optionally) the masked packed copy conv_pre reads
