@@ -82,8 +82,6 @@ __device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, uint32_t src_c
                  ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster)
                  : "memory");
 }
-// generic -> async proxy ordering for every state space (the operand tiles are written through the cluster's shared-memory window)
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -239,7 +237,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) flow_cluster_kernel(const FlowPar
         // per thread and the SM's shared-memory port ~1.4 us per layer.)
         auto publish = [&](uint8_t* tile, uint32_t tile_addr, int rows, int row, int chunk0, const uint4* pk, int nchunk) {
             for (int u = 0; u < nchunk; ++u) *reinterpret_cast<uint4*>(tile + ((size_t)(chunk0 + u) * rows + row) * 16) = pk[u];
-            fence_proxy_async_all();                       // generic stores -> visible to the async proxy (bulk-copy source, tensor-core operand)
+            tc::fence_proxy_async();                       // generic stores to OWN shared memory -> visible to the async proxy (bulk-copy source,
+                                                           // tensor-core operand); the all-spaces form of the fence cost 0.9 us per layer here
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (er == 0) {
                 const uint32_t bytes = (uint32_t)(nchunk * rows * 16), off = (uint32_t)(chunk0 * rows * 16);

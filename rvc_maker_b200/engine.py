@@ -318,6 +318,17 @@ class Engine:
                 out = torch.empty(wd.numel() * 2, dtype=torch.uint8, device=self.dev)
                 _lib.check(self.lib.rvc_pack_weight(wd.data_ptr(), out.data_ptr(), wd.shape[0], wd.shape[1], wd.shape[2], dt, st), "pack_weight")
                 self.W[k] = out
+            # speaker conditioning is a function of sid alone ("precompute per sid"): one row of cond_layer(g) x 4 | dec.cond(g)
+            # per speaker, computed once by the same GEMV kernel the plans would run (bit-identical), gathered by sid at infer time
+            self.cond_table = None
+            nspk = self.W["emb_g"].shape[0]
+            if nspk * self.cond_total * 4 <= (256 << 20) and os.environ.get("RVC_B200_COND_TABLE", "1") != "0":
+                tab = torch.empty(nspk, self.cond_total, dtype=torch.float32, device=self.dev)
+                for s0 in range(0, nspk, 4096):
+                    n = min(4096, nspk - s0)
+                    _lib.check(self.lib.rvc_cond_gemv_f32(self.W["emb_g"][s0:s0 + n].contiguous().data_ptr(), self.W["cond_w"].data_ptr(), self.W["cond_b"].data_ptr(),
+                                                          tab[s0:s0 + n].data_ptr(), n, c["G"], self.cond_total, st), "cond table")
+                self.cond_table = tab
             torch.cuda.synchronize(self.dev)
 
     # ------------------------------------------------------------------ descriptor helpers
@@ -608,11 +619,13 @@ class Engine:
         p.out_offsets = (n_o, n_m, n_z)
         p.g = self._buf(p, B, G)
         gc = self._buf(p, B, self.cond_total)
+        p.gc = gc
         hb, acts, outb = self._buf(p, B, H, T), self._buf(p, B, H, T), self._buf(p, B, H, T)
         vh, va, vo = V(hb, H, T), V(acts, H, T), V(outb, H, T)
         # speaker conditioning: cond_layer(g) x4 + dec.cond(g) in one launch (modules.py:39, synthesizers.py:147)
-        p.add("cond", lib.rvc_cond_gemv_f32, p.g.data_ptr(), W["cond_w"].data_ptr(), W["cond_b"].data_ptr(), gc.data_ptr(), B, G, self.cond_total,
-              flops=2.0 * B * G * self.cond_total, bytes_=4.0 * G * self.cond_total, kind="cond_gemv_f32")
+        if self.cond_table is None:   # (otherwise infer() gathers the rows of the per-speaker table straight into gc)
+            p.add("cond", lib.rvc_cond_gemv_f32, p.g.data_ptr(), W["cond_w"].data_ptr(), W["cond_b"].data_ptr(), gc.data_ptr(), B, G, self.cond_total,
+                  flops=2.0 * B * G * self.cond_total, bytes_=4.0 * G * self.cond_total, kind="cond_gemv_f32")
         cluster = self.flow_tc and self.use_flow_cluster and (H, half) == (192, 96)     # (the flow's WaveNet is always 3 layers of k = 5, x 4 couplings)
         za = self._packed(p, B, I, T) if self.flow_tc else None       # masked packed z: conv_pre's operand
         if cluster:
@@ -743,9 +756,9 @@ class Engine:
                     x3 = cur[2].data_ptr() if cur[2] is not None else None
                     p.add(f"pack_up{i}", lib.rvc_pack_act, cur[0].data_ptr(), x2, x3, float(nk), curC * curL, curL, None, ua.data_ptr(), B, curC,
                           curL, udt, LRELU_SLOPE, bytes_=B * curC * curL * (2.0 + (12.0 if x2 else 4.0)), kind="pack_act")
-                # short noise convs (kernel <= 4: the last two stages) are computed inside the ups epilogue instead of a launch of
+                # short noise convs (kernel <= 8: every stage but the first) are computed inside the ups epilogue instead of a launch of
                 # their own followed by an fp32 round trip (rvc_tc_job.nz_*); the long ones keep their kernel
-                nz_fused = bool(c["f0"]) and blk and kn <= 4
+                nz_fused = bool(c["f0"]) and blk and kn <= 8
                 if c["f0"] and not nz_fused:
                     p.add(f"noise{i}", lib.rvc_noise_conv_f32, har.data_ptr(), Lfin, W[f"nz_w{i}"].data_ptr(), W[f"nz_b{i}"].data_ptr(),
                           S[0].data_ptr(), Ci * Li, B, Ci, Li, kn, sn, pn, int(blk), flops=2.0 * B * Ci * Li * kn, bytes_=4.0 * B * (Ci * Li + Li * sn),
@@ -979,7 +992,10 @@ class Engine:
             head = int(T * (1.0 - rate)) if rate is not None else 0
             T2 = T - head
             pd = self.plan("dec", B, T2)
-            pd.g.copy_(self.W["emb_g"][sid.to(self.dev, non_blocking=True)])  # emb_g(sid), :447 (no host sync for a pinned sid)
+            if self.cond_table is not None:   # cond_layer(emb_g(sid)) x 4 + dec.cond(emb_g(sid)), precomputed per speaker at load time
+                pd.gc.copy_(self.cond_table[sid.to(self.dev, non_blocking=True)])
+            else:
+                pd.g.copy_(self.W["emb_g"][sid.to(self.dev, non_blocking=True)])  # emb_g(sid), :447 (no host sync for a pinned sid)
             if c["f0"]:
                 pd.f0.copy_(nsff0[:, head:], non_blocking=True)
                 if noise is not None:
