@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int AQ = 16, AG = 32, ANT = AQ * AG;
+constexpr int AG = 32;
 
 // one key chunk of S for one query: 8 consecutive keys = 32 contiguous bytes in the channel-blocked layout [key/8][query][8]
 __device__ __forceinline__ void ld_chunk(const float* p, float (&v)[8]) {
@@ -29,18 +29,23 @@ __device__ __forceinline__ uint32_t h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Short-sequence variant (a thread's share of the key row is CPT <= 4 chunks of 8 keys, i.e. T <= 1024): every score of the
-// row is loaded ONCE with all loads in flight together (no per-chunk online rescale), max / sum / probabilities come from
-// registers, and the 2W+1 band probabilities a query needs for the relative-value term are exchanged through shared memory
-// instead of being recomputed from global memory.  The launch is latency-bound (126 CTAs at T = 1000): 29 -> ~17 us.
+// Short-sequence variant (T <= 1024: a lane's share of a key row is CPT <= 4 chunks of 8 keys): ONE WARP PER QUERY.  The launch is
+// latency-bound (2 M scores per layer at T = 1000), so the kernel is organised to have as few dependent steps as possible and no block-wide
+// barrier after the table staging: all of a query's scores are loaded once (lane = key chunk modulo 32), max / sum are warp shuffles, the
+// relative-key dot products q.Ek[r] run on lanes r < 2W+1 from a per-warp copy of q in shared memory, the 2W+1 band probabilities go
+// through a per-warp shared array into the relative-value sum.  The eight warps of a block own eight consecutive queries, so the
+// 32-byte score chunks / probability stores of a block are 256 contiguous bytes.  (The previous 16-query x 32-group block needed four
+// block barriers and took 20 us per layer; this one takes ~5.)
+constexpr int WQ = 8;            // queries (= warps) per block
 template <int CPT>
-__global__ void __launch_bounds__(ANT) attn_softmax_fast_kernel(const float* __restrict__ S, const float* __restrict__ qkv, const float* __restrict__ mask,
-                                                                const float* __restrict__ emb_k, const float* __restrict__ emb_v, uint8_t* __restrict__ P,
-                                                                float* __restrict__ R, uint8_t* __restrict__ vw, int H, int nh, int T, int Tk, int Lp,
-                                                                int W, int nqb, int nvb, int BH) {
+__global__ void __launch_bounds__(WQ * 32) attn_softmax_fast_kernel(const float* __restrict__ S, const float* __restrict__ qkv, const float* __restrict__ mask,
+                                                                    const float* __restrict__ emb_k, const float* __restrict__ emb_v, uint8_t* __restrict__ P,
+                                                                    float* __restrict__ R, uint8_t* __restrict__ vw, int H, int nh, int T, int Tk, int Lp,
+                                                                    int W, int nqb, int nvb, int BH) {
     rvc::pdl_prologue();
     extern __shared__ float sm[];
-    const int dk = H / nh, NR = 2 * W + 1;
+    constexpr int NTH = WQ * 32;
+    const int dk = H / nh, NR = 2 * W + 1, dkp = dk + 1;
     const int nsm = nqb * BH;
     const bool is_pack = (int)blockIdx.x >= nsm;
     const int bh = is_pack ? ((int)blockIdx.x - nsm) / nvb : (int)blockIdx.x / nqb;
@@ -50,7 +55,7 @@ __global__ void __launch_bounds__(ANT) attn_softmax_fast_kernel(const float* __r
     const int tid = threadIdx.x;
     const float* vb = qkv + ((int64_t)b * 3 * H + 2 * H + h * dk) * T;
     if (is_pack) {
-        const int idx = bx * ANT + tid;
+        const int idx = bx * NTH + tid;
         if (idx >= dk * nchunk) return;
         const int d = idx / nchunk, c = idx - d * nchunk;
         float v[8];
@@ -59,126 +64,111 @@ __global__ void __launch_bounds__(ANT) attn_softmax_fast_kernel(const float* __r
         *reinterpret_cast<uint4*>(vw + ((((int64_t)b * nh + h) * nchunk + c) * dk + d) * 16) = make_uint4(h2(v[0], v[1]), h2(v[2], v[3]), h2(v[4], v[5]), h2(v[6], v[7]));
         return;
     }
-    float* qe_s = sm;                    // [AQ][NR]
-    float* ev_s = qe_s + AQ * NR;        // [NR][dk]
-    float* m_s = ev_s + NR * dk;         // [AG][AQ]
-    float* l_s = m_s + AG * AQ;          // [AG][AQ]
-    float* q_s = l_s + AG * AQ;          // [dk][AQ]   q / sqrt(dk)
-    float* ek_s = q_s + dk * AQ;         // [NR][dk]
-    float* pb_s = ek_s + NR * dk;        // [AQ][NR]   band probabilities p[i][i + r - W]
-    const int ti = tid % AQ, g = tid / AQ;
-    const int i0 = bx * AQ, i = i0 + ti;
+    float* ek_s = sm;                        // [NR][dk + 1]  (padded: lanes r read row r at the same column)
+    float* ev_s = ek_s + NR * dkp;           // [NR][dk]
+    float* wq_s = ev_s + NR * dk;            // [WQ][dk]      q_i / sqrt(dk)
+    float* qe_s = wq_s + WQ * dk;            // [WQ][32]      q_i . Ek[r]
+    float* pb_s = qe_s + WQ * 32;            // [WQ][32]      band probabilities p[i][i + r - W]
+    const int w = tid >> 5, lane = tid & 31;
+    const int i = bx * WQ + w;
+    const bool qok = i < T;
     const float* qb = qkv + ((int64_t)b * 3 * H + h * dk) * T;
     const float* mb = mask + (int64_t)b * T;
     const float* Sb = S + ((int64_t)b * nh + h) * Tk * T;
-    const float rs = sqrtf((float)dk);
-    const bool qok = i < T;
+    const float rs = sqrtf((float)dk), inv = 1.f / rs;
 
-    // all of this thread's raw scores and key masks: issued before the table staging so that their latency overlaps it
+    // this query's raw scores and key masks first: their latency overlaps the table staging
     float sc[CPT][8], km[CPT][8];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
-        const int c = g + k * AG;
-        if (qok && c < nchunk) ld_chunk(Sb + ((int64_t)c * T + i) * 8, sc[k]);
+        const int c = lane + 32 * k;
+        const bool cok = qok && c < nchunk;
+        if (cok) ld_chunk(Sb + ((int64_t)c * T + i) * 8, sc[k]);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int j = 8 * c + u;
-            const bool in = qok && c < nchunk && j < T;
+            const bool in = cok && j < T;
             if (!in) sc[k][u] = -INFINITY;
             km[k][u] = in ? mb[j] : 0.f;
         }
     }
-    for (int idx = tid; idx < NR * dk; idx += ANT) { ev_s[idx] = emb_v[idx]; ek_s[idx] = emb_k[idx]; }
-    for (int idx = tid; idx < dk * AQ; idx += ANT) {
-        const int q = idx % AQ, d = idx / AQ;
-        q_s[idx] = (i0 + q < T) ? qb[(int64_t)d * T + i0 + q] / rs : 0.f;
+    for (int idx = tid; idx < NR * dk; idx += NTH) {
+        const int r = idx / dk, d = idx - r * dk;
+        ek_s[r * dkp + d] = emb_k[idx];
+        ev_s[idx] = emb_v[idx];
     }
-    for (int idx = tid; idx < AQ * NR; idx += ANT) pb_s[idx] = 0.f;
+    for (int d = lane; d < dk; d += 32) wq_s[w * dk + d] = qok ? qb[(int64_t)d * T + i] / rs : 0.f;
+    if (lane < 32) pb_s[w * 32 + lane] = 0.f;
     __syncthreads();
-    for (int idx = tid; idx < AQ * NR; idx += ANT) {
-        const int q = idx % AQ, r = idx / AQ;
+    if (!qok) return;          // (no block barrier below)
+    if (lane < NR) {
         float a0 = 0.f, a1 = 0.f;
+        const float* e = ek_s + lane * dkp;
+        const float* q = wq_s + w * dk;
         for (int d = 0; d + 1 < dk; d += 2) {
-            a0 = fmaf(q_s[d * AQ + q], ek_s[r * dk + d], a0);
-            a1 = fmaf(q_s[(d + 1) * AQ + q], ek_s[r * dk + d + 1], a1);
+            a0 = fmaf(q[d], e[d], a0);
+            a1 = fmaf(q[d + 1], e[d + 1], a1);
         }
-        if (dk & 1) a0 = fmaf(q_s[(dk - 1) * AQ + q], ek_s[r * dk + dk - 1], a0);
-        qe_s[q * NR + r] = a0 + a1;
+        if (dk & 1) a0 = fmaf(q[dk - 1], e[dk - 1], a0);
+        qe_s[w * 32 + lane] = a0 + a1;
     }
-    __syncthreads();
+    __syncwarp();
 
-    const float mq = qok ? mb[i] : 0.f;
-    const float inv = 1.f / rs;
+    const float mq = mb[i];
     float m = -INFINITY;
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
-        const int c = g + k * AG;
+        const int c = lane + 32 * k;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int j = 8 * c + u;
-            if (sc[k][u] != -INFINITY) {           // same arithmetic as the generic kernel's score()
+            if (sc[k][u] != -INFINITY) {           // same arithmetic as the long-sequence kernel's chunk_scores()
                 float s = sc[k][u] * inv;
                 const int rel = j - i + W;
-                if (rel >= 0 && rel < NR) s += qe_s[ti * NR + rel];
+                if (rel >= 0 && rel < NR) s += qe_s[w * 32 + rel];
                 if (mq * km[k][u] == 0.f) s = -1e4f;
                 sc[k][u] = s;
                 m = fmaxf(m, s);
             }
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     float l = 0.f;
-    if (m != -INFINITY) {
 #pragma unroll
-        for (int k = 0; k < CPT; ++k)
+    for (int k = 0; k < CPT; ++k)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) l += __expf(sc[k][u] - m);
-    }
-    m_s[g * AQ + ti] = m;
-    l_s[g * AQ + ti] = l;
-    __syncthreads();
-    float M = -INFINITY, Lsum = 0.f;
+        for (int u = 0; u < 8; ++u) {
+            sc[k][u] = __expf(sc[k][u] - m);         // exp(-inf) = 0 for keys >= T
+            l += sc[k][u];
+        }
 #pragma unroll
-    for (int gg = 0; gg < AG; ++gg) M = fmaxf(M, m_s[gg * AQ + ti]);
-#pragma unroll
-    for (int gg = 0; gg < AG; ++gg) {
-        const float mg = m_s[gg * AQ + ti];
-        if (mg != -INFINITY) Lsum += l_s[gg * AQ + ti] * __expf(mg - M);
-    }
-    const float rl = qok ? 1.f / Lsum : 0.f;
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float rl = 1.f / l;
 
-    // probabilities -> packed fp16; band members also go to shared memory for the relative-value term
     uint8_t* Pb = P + (((int64_t)b * nh + h) * nchunk * Lp + 64 + i) * 16;
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
-        const int c = g + k * AG;
-        if (qok && c < nchunk) {
+        const int c = lane + 32 * k;
+        if (c < nchunk) {
             float p8[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                p8[u] = __expf(sc[k][u] - M) * rl;            // exp(-inf) = 0 for keys >= T
+                p8[u] = sc[k][u] * rl;
                 const int rel = 8 * c + u - i + W;
-                if (rel >= 0 && rel < NR) pb_s[ti * NR + rel] = p8[u];
+                if (rel >= 0 && rel < NR) pb_s[w * 32 + rel] = p8[u];
             }
             *reinterpret_cast<uint4*>(Pb + (int64_t)c * Lp * 16) = make_uint4(h2(p8[0], p8[1]), h2(p8[2], p8[3]), h2(p8[4], p8[5]), h2(p8[6], p8[7]));
         }
     }
-    __syncthreads();
-    if (!qok) return;
-    // relative-value term: group g owns output dims [g*dk/AG, (g+1)*dk/AG)
-    const int dpg = dk / AG, d0 = g * dpg;
-    float acc[16];
-#pragma unroll
-    for (int dd = 0; dd < 16; ++dd) acc[dd] = 0.f;
-    for (int r = 0; r < NR; ++r) {
-        const float pv = pb_s[ti * NR + r];                    // 0 where i + r - W falls outside [0, T)
-#pragma unroll
-        for (int dd = 0; dd < 16; ++dd)
-            if (dd < dpg) acc[dd] = fmaf(pv, ev_s[r * dk + d0 + dd], acc[dd]);
+    __syncwarp();
+    // relative-value term: lane owns output dims lane, lane + 32, ...
+    float* Rb = R + ((int64_t)b * H + h * dk) * T + i;
+    for (int d = lane; d < dk; d += 32) {
+        float acc = 0.f;
+        for (int r = 0; r < NR; ++r) acc = fmaf(pb_s[w * 32 + r], ev_s[r * dk + d], acc);     // 0 where i + r - W falls outside [0, T)
+        Rb[(int64_t)d * T] = acc;
     }
-    float* Rb = R + ((int64_t)b * H + h * dk + d0) * T + i;
-#pragma unroll
-    for (int dd = 0; dd < 16; ++dd)
-        if (dd < dpg) Rb[(int64_t)dd * T] = acc[dd];
 }
 
 // Long-sequence variant (T > 1024, e.g. the 4000-frame chunks of a stream): S no longer fits in registers, so it is read twice
@@ -331,18 +321,19 @@ RVC_API int rvc_attn_softmax(const float* S, const float* qkv, const float* mask
     if (dk % AG || dk / AG > 16) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: head dim %d must be a multiple of 32 and <= 512", dk);
     if ((int64_t)B * n_heads > 65535) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: B*heads > 65535");
     const int NR = 2 * window + 1;
-    const size_t smem = (size_t)(2 * AQ * NR + 2 * NR * dk + 2 * AG * AQ + dk * AQ) * sizeof(float);
+    if (NR > 32) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: window %d > 15", window);
+    const size_t smem = (size_t)(NR * (dk + 1) + NR * dk + WQ * dk + 2 * WQ * 32) * sizeof(float);
     if (smem > 200 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_attn_softmax: window too large");
-    const int nqb = rvc::cdiv(T, AQ);
-    const int nvb = rvc::cdiv(dk * (Tk / 8), ANT);
+    const int nqb = rvc::cdiv(T, WQ);
+    const int nvb = rvc::cdiv(dk * (Tk / 8), WQ * 32);
     dim3 grid((unsigned)((nqb + nvb) * B * n_heads));
-    const int cpt = rvc::cdiv(Tk / 8, AG);     // key chunks per thread
+    const int cpt = rvc::cdiv(Tk / 8, 32);     // key chunks per lane
     auto launch = [&](auto kern) -> int {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return rvc::fail((int)e, "rvc_attn_softmax: smem opt-in: %s", cudaGetErrorString(e));
         }
-        rvc::launch_pdl(kern, dim3(grid), dim3(ANT), (size_t)(smem), (cudaStream_t)stream, S, qkv, mask, emb_k, emb_v, (uint8_t*)P, R, (uint8_t*)vw, H, n_heads, T, Tk,
+        rvc::launch_pdl(kern, dim3(grid), dim3(WQ * 32), (size_t)(smem), (cudaStream_t)stream, S, qkv, mask, emb_k, emb_v, (uint8_t*)P, R, (uint8_t*)vw, H, n_heads, T, Tk,
                         (int)rvc_packed_rows(T), window, nqb, nvb, B * n_heads);
         return rvc::check_launch("rvc_attn_softmax");
     };
