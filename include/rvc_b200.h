@@ -198,7 +198,7 @@ typedef struct {
     int32_t w_cs, reserved;
     /* optional, in place of `res`: the NSF noise conv of a generator stage (synthesizers.py:134-136, :156) computed in the
      * epilogue — v += nz_b[c] + sum_{j < nz_kn} nz_w[c*nz_kn + j] * nz_har[b*nz_har_bs + l*nz_sn - nz_pn + j] at output
-     * position l (source samples outside [0, Lout*nz_sn) read as 0), nz_kn <= 8.  Same arithmetic as rvc_noise_conv_f32
+     * position l (source samples outside [0, Lout*nz_sn) read as 0), nz_kn <= 4.  Same arithmetic as rvc_noise_conv_f32
      * followed by res: bit-identical, without the extra launch and the fp32 round trip. */
     const float* nz_har; const float* nz_w; const float* nz_b;
     int64_t nz_har_bs;

@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * MAXABUF + MAXNG + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * MAXABUF + 2 * MAXNG);
     float* bias_s = reinterpret_cast<float*>(bars + 2 * NSTAGE + 2 * MAXABUF + 2 * MAXNG + 2);   // [njobs][Cout], 16-byte aligned
-    float4* nzw_s = reinterpret_cast<float4*>(bias_s + (((p.njobs / p.G) * p.Cout + 3) & ~3));             // [2][Cout] noise-conv taps of job 0 (taps 0-3, taps 4-7; zero padded)
-    float* nzb_s = reinterpret_cast<float*>(nzw_s + 2 * p.Cout);                                   // [Cout] noise-conv bias
+    float4* nzw_s = reinterpret_cast<float4*>(bias_s + (((p.njobs / p.G) * p.Cout + 3) & ~3));             // [Cout] noise-conv taps of job 0 (<= 4, zero padded)
+    float* nzb_s = reinterpret_cast<float*>(nzw_s + p.Cout);                                       // [Cout] noise-conv bias
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
     const int lane = threadIdx.x & 31;
@@ -145,10 +145,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     if (warp >= 4 && p.jobs[0].nz_har) {
         const rvc_tc_job& j0 = p.jobs[0];
         for (int c = threadIdx.x - 128; c < p.Cout; c += NTHREADS - 128) {
-            float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
             for (int j = 0; j < j0.nz_kn; ++j) t[j] = j0.nz_w[(size_t)c * j0.nz_kn + j];
             nzw_s[c] = make_float4(t[0], t[1], t[2], t[3]);
-            nzw_s[p.Cout + c] = make_float4(t[4], t[5], t[6], t[7]);
             nzb_s[c] = j0.nz_b ? j0.nz_b[c] : 0.f;
         }
     }
@@ -430,9 +429,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                         // fused noise conv (taps in the reference kernel's order: bias, then fma per tap)
                         const int64_t h0 = (int64_t)l * jb.nz_sn - jb.nz_pn, hlen = (int64_t)p.Lout * jb.nz_sn;
                         const float* hb = jb.nz_har + (size_t)b * jb.nz_har_bs;
-                        float hv[8];
+                        float hv[4];
 #pragma unroll
-                        for (int jx = 0; jx < 8; ++jx) hv[jx] = (jx < jb.nz_kn && h0 + jx >= 0 && h0 + jx < hlen) ? hb[h0 + jx] : 0.f;
+                        for (int jx = 0; jx < 4; ++jx) hv[jx] = (jx < jb.nz_kn && h0 + jx >= 0 && h0 + jx < hlen) ? hb[h0 + jx] : 0.f;
                         const int kn = jb.nz_kn;
 #pragma unroll
                         for (int i = 0; i < EB; ++i) {
@@ -442,13 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                             if (kn > 1) a = fmaf(w4.y, hv[1], a);
                             if (kn > 2) a = fmaf(w4.z, hv[2], a);
                             if (kn > 3) a = fmaf(w4.w, hv[3], a);
-                            if (kn > 4) {   // (uniform branch) taps 4-7: the second-stage noise conv of the 40k / 48k models (k = 8, stride 4)
-                                const float4 w8 = nzw_s[p.Cout + co0 + i];
-                                a = fmaf(w8.x, hv[4], a);
-                                if (kn > 5) a = fmaf(w8.y, hv[5], a);
-                                if (kn > 6) a = fmaf(w8.z, hv[6], a);
-                                if (kn > 7) a = fmaf(w8.w, hv[7], a);
-                            }
+
                             v[i] = a;
                         }
                     }
@@ -717,7 +710,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
             return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: y_lo goes with y_act, fp16 operands and 16-byte alignment");
         if (jb.nz_har) {
             if (j != 0 || d.sum_jobs || gated || jb.res) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: the fused noise conv belongs to job 0, replaces res, and excludes sum_jobs / gated");
-            if (!jb.nz_w || jb.nz_kn < 1 || jb.nz_kn > 8 || jb.nz_sn < 1 || jb.nz_pn < 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: fused noise conv needs 1 <= kn <= 8, sn >= 1, pn >= 0");
+            if (!jb.nz_w || jb.nz_kn < 1 || jb.nz_kn > 4 || jb.nz_sn < 1 || jb.nz_pn < 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: fused noise conv needs 1 <= kn <= 4, sn >= 1, pn >= 0");
         }
         const int halo = (jb.K - 1) * jb.dil;
         if (jb.pad > PADL || halo - jb.pad > PADR)
@@ -797,7 +790,7 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     p.blocked = d.f32_blocked;
     p.has_res = 0;
     for (int j = 0; j < d.njobs; ++j) p.has_res |= d.jobs[j].res != nullptr;
-    const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512 + (size_t)(d.njobs / G) * d.Cout * sizeof(float) + (d.jobs[0].nz_har ? 16 + (size_t)d.Cout * 36 : 0);
+    const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512 + (size_t)(d.njobs / G) * d.Cout * sizeof(float) + (d.jobs[0].nz_har ? 16 + (size_t)d.Cout * 20 : 0);
     const size_t limit = 227 * 1024;
     // activation stage: as many channel chunks as fit twice (double buffer); even count
     int ach = p.nch;

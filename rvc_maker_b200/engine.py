@@ -756,10 +756,10 @@ class Engine:
                     x3 = cur[2].data_ptr() if cur[2] is not None else None
                     p.add(f"pack_up{i}", lib.rvc_pack_act, cur[0].data_ptr(), x2, x3, float(nk), curC * curL, curL, None, ua.data_ptr(), B, curC,
                           curL, udt, LRELU_SLOPE, bytes_=B * curC * curL * (2.0 + (12.0 if x2 else 4.0)), kind="pack_act")
-                # short noise convs (kernel <= 4: the last two stages) are computed inside the ups epilogue (the kernel takes up to 8 taps, but
-                # the 8-tap conv of stage 1 costs the issue-bound ups epilogue more than its own launch: ups1 61 -> 116 us against 29 us saved) instead of a launch of
-                # their own followed by an fp32 round trip (rvc_tc_job.nz_*); the long ones keep their kernel
-                nz_fused = bool(c["f0"]) and blk and kn <= int(os.environ.get("RVC_B200_NZ_FUSE_MAX", "4"))
+                # short noise convs (kernel <= 4: the last two stages) are computed inside the ups epilogue instead of a launch of
+                # their own followed by an fp32 round trip (rvc_tc_job.nz_*); the long ones keep their kernel (tried in round 2: the 8-tap
+                # conv of stage 1 inside the issue-bound ups epilogue cost 55 us against 29 us saved)
+                nz_fused = bool(c["f0"]) and blk and kn <= 4
                 if c["f0"] and not nz_fused:
                     p.add(f"noise{i}", lib.rvc_noise_conv_f32, har.data_ptr(), Lfin, W[f"nz_w{i}"].data_ptr(), W[f"nz_b{i}"].data_ptr(),
                           S[0].data_ptr(), Ci * Li, B, Ci, Li, kn, sn, pn, int(blk), flops=2.0 * B * Ci * Li * kn, bytes_=4.0 * B * (Ci * Li + Li * sn),

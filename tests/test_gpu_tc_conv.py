@@ -520,7 +520,7 @@ def test_fused_resblock_pair_stage_average(Cc, L, B, y_ncl):
     assert torch.equal(ya_fused, ya_ref)
 
 
-@pytest.mark.parametrize("Cin,Cout,k,u,Lin,sn", [(128, 64, 4, 2, 5001, 2), (64, 32, 4, 2, 7777, 1), (32, 16, 4, 2, 3000, 1), (256, 128, 20, 10, 1201, 4)])
+@pytest.mark.parametrize("Cin,Cout,k,u,Lin,sn", [(128, 64, 4, 2, 5001, 2), (64, 32, 4, 2, 7777, 1), (32, 16, 4, 2, 3000, 1)])
 def test_fused_noise_conv_in_ups_epilogue(Cin, Cout, k, u, Lin, sn):
     """rvc_tc_job.nz_*: the short NSF noise conv computed in the ConvTranspose epilogue equals rvc_noise_conv_f32 + res, bit for bit."""
     from rvc_maker_b200 import _lib
