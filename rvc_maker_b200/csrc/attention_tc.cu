@@ -38,7 +38,7 @@ __device__ __forceinline__ uint32_t h2(float a, float b) {
 // block barriers and took 20 us per layer; this one takes ~5.)
 constexpr int WQ = 8;            // queries (= warps) per block
 template <int CPT>
-__global__ void __launch_bounds__(WQ * 32) attn_softmax_fast_kernel(const float* __restrict__ S, const float* __restrict__ qkv, const float* __restrict__ mask,
+__global__ void __launch_bounds__(WQ * 32, 3) attn_softmax_fast_kernel(const float* __restrict__ S, const float* __restrict__ qkv, const float* __restrict__ mask,
                                                                     const float* __restrict__ emb_k, const float* __restrict__ emb_v, uint8_t* __restrict__ P,
                                                                     float* __restrict__ R, uint8_t* __restrict__ vw, int H, int nh, int T, int Tk, int Lp,
                                                                     int W, int nqb, int nvb, int BH) {
@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(WQ * 32) attn_softmax_fast_kernel(const float*
     const float rs = sqrtf((float)dk), inv = 1.f / rs;
 
     // this query's raw scores and key masks first: their latency overlaps the table staging
-    float sc[CPT][8], km[CPT][8];
+    float sc[CPT][8];
+    uint32_t kmbits = 0;        // bit 8k + u: key mask of key 8 * (lane + 32k) + u is non-zero
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int c = lane + 32 * k;
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(WQ * 32) attn_softmax_fast_kernel(const float*
             const int j = 8 * c + u;
             const bool in = cok && j < T;
             if (!in) sc[k][u] = -INFINITY;
-            km[k][u] = in ? mb[j] : 0.f;
+            if (in && mb[j] != 0.f) kmbits |= 1u << (8 * k + u);
         }
     }
     for (int idx = tid; idx < NR * dk; idx += NTH) {
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(WQ * 32) attn_softmax_fast_kernel(const float*
                 float s = sc[k][u] * inv;
                 const int rel = j - i + W;
                 if (rel >= 0 && rel < NR) s += qe_s[w * 32 + rel];
-                if (mq * km[k][u] == 0.f) s = -1e4f;
+                if (mq == 0.f || !((kmbits >> (8 * k + u)) & 1u)) s = -1e4f;
                 sc[k][u] = s;
                 m = fmaxf(m, s);
             }
