@@ -229,3 +229,79 @@ class Synthesizer(nn.Module):
         out.copy_(o, non_blocking=True)
         torch.cuda.current_stream(o.device).synchronize()
         return out
+
+    @torch.no_grad()
+    def infer_stream(self, items, depth=2):
+        """Pipelined ``infer_to_host`` over an iterable of ``(phone, phone_lengths, pitch, nsff0, sid)`` tuples of (pinned) HOST tensors: yields
+        ``o`` as float32 ``[B, 1, L]`` views of pinned host buffers, in order.
+
+        The caller's chunk loop (main/inference/convert.py:442-447) is strictly serial: copy in, synthesise, copy out.  Here the host-to-device
+        copy of item n+1 runs on a copy stream while item n computes, and the read-back of item n runs on a second copy stream while item n+1
+        computes (``depth`` staging sets; every item's copies still happen, they are just off the critical path).  A yielded view stays valid
+        until ``depth`` further items have been yielded.  Same numerics and RNG order as ``infer`` called item by item.
+        """
+        dev = self.emb_g.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("rvc_maker_b200.Synthesizer.infer_stream needs its parameters on a CUDA device (no CPU fallback)")
+        comp = torch.cuda.current_stream(dev)
+        if getattr(self, "_pipe", None) is None or self._pipe["dev"] != dev or self._pipe["depth"] != depth:
+            self._pipe = dict(dev=dev, depth=depth, h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev), stage=[None] * depth, host=[None] * depth,
+                              consumed=[None] * depth, done=[None] * depth)
+        P = self._pipe
+        h2d, d2h = P["h2d"], P["d2h"]
+
+        def stage(k, item):
+            """host -> device staging set k on the copy stream (after the compute stream has consumed the set's previous content)"""
+            bufs = P["stage"][k]
+            if bufs is None or any((a is None) != (b is None) or (a is not None and (a.shape != b.shape or a.dtype != b.dtype)) for a, b in zip(bufs, item)):
+                bufs = P["stage"][k] = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=dev) for t in item]
+            if P["consumed"][k] is not None:
+                h2d.wait_event(P["consumed"][k])
+            with torch.cuda.stream(h2d):
+                for d, t in zip(bufs, item):
+                    if t is not None:
+                        d.copy_(t, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(h2d)
+            return ev
+
+        def run(k, ev_in):
+            comp.wait_event(ev_in)
+            o = self.infer(*P["stage"][k])[0]
+            P["consumed"][k] = torch.cuda.Event()
+            P["consumed"][k].record(comp)          # (infer has copied the staged inputs into its own buffers by now, in stream order)
+            n = o.numel()
+            if P["host"][k] is None or P["host"][k].numel() < n:
+                P["host"][k] = torch.empty(n, dtype=torch.float32).pin_memory()
+            out = P["host"][k][:n].view(o.shape)
+            ev_o = torch.cuda.Event()
+            ev_o.record(comp)
+            d2h.wait_event(ev_o)
+            with torch.cuda.stream(d2h):
+                out.copy_(o, non_blocking=True)
+                o.record_stream(d2h)
+                P["done"][k] = torch.cuda.Event()
+                P["done"][k].record(d2h)
+            return out
+
+        it = iter(items)
+        pending = []                      # (slot, host view) in flight
+        nxt = next(it, None)
+        ev_next = stage(0, nxt) if nxt is not None else None
+        n = 0
+        while nxt is not None:
+            k = n % depth
+            cur_ev = ev_next
+            nxt = next(it, None)
+            if nxt is not None:
+                ev_next = stage((n + 1) % depth, nxt)       # overlaps the compute of item n
+            pending.append((k, run(k, cur_ev)))
+            n += 1
+            if len(pending) >= depth:                       # keep `depth` items in flight, hand out the oldest
+                kk, out = pending.pop(0)
+                P["done"][kk].synchronize()
+                yield out
+        for kk, out in pending:
+            P["done"][kk].synchronize()
+            yield out
+

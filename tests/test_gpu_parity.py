@@ -308,3 +308,31 @@ def test_flow_cluster_kernel_matches_per_layer_path(B, T, monkeypatch):
     print(f"[flow cluster B={B} T={T}] z err {err:.2e} (max|z| {scale:.2f}), o diff {float((out['o'] - ref['o']).abs().max()):.2e}")
     again = run_net(net, inp)      # captured graph
     assert torch.equal(again["z"], out["z"]) and torch.equal(again["o"], out["o"])
+
+
+def test_infer_stream_equals_item_by_item_calls():
+    """Synthesizer.infer_stream (copies of neighbouring items overlap compute, two staging sets) yields, in order, exactly what infer_to_host returns
+    for each item — five items of two different shapes, pinned noise."""
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=5, heated=True)
+    net = build_net(cfg, sd, True, precision="tc")
+    shapes = [(1, 200), (2, 130), (1, 200), (1, 200), (2, 130)]
+    items, want = [], []
+    for n, (B, T) in enumerate(shapes):
+        inp = cases.synth_inputs(cfg, B, T, seed=100 + n, ragged=B > 1)
+        items.append(inp)
+    for inp in items:
+        net._noise_override = (inp["eps_z"], inp["eps_src"])
+        want.append(net.infer_to_host(inp["phone"].pin_memory(), inp["phone_lengths"].pin_memory(), inp["pitch"].pin_memory(), inp["nsff0"].pin_memory(),
+                                      inp["sid"].pin_memory()).clone())
+
+    def gen():
+        for inp in items:
+            net._noise_override = (inp["eps_z"], inp["eps_src"])     # (read by infer() when the item is submitted)
+            yield (inp["phone"].pin_memory(), inp["phone_lengths"].pin_memory(), inp["pitch"].pin_memory(), inp["nsff0"].pin_memory(), inp["sid"].pin_memory())
+
+    got = [o.clone() for o in net.infer_stream(gen())]
+    net._noise_override = None
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and torch.equal(a, b)
