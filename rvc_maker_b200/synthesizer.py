@@ -232,7 +232,7 @@ class Synthesizer(nn.Module):
 
     @torch.no_grad()
     def infer_stream(self, items, depth=2):
-        """Pipelined ``infer_to_host`` over an iterable of ``(phone, phone_lengths, pitch, nsff0, sid)`` tuples of (pinned) HOST tensors: yields
+        """Pipelined ``infer_to_host`` over an iterable of ``(phone, phone_lengths, pitch, nsff0, sid[, noise])`` tuples of (pinned) HOST tensors: yields
         ``o`` as float32 ``[B, 1, L]`` views of pinned host buffers, in order.
 
         The caller's chunk loop (main/inference/convert.py:442-447) is strictly serial: copy in, synthesise, copy out.  Here the host-to-device
@@ -252,6 +252,7 @@ class Synthesizer(nn.Module):
 
         def stage(k, item):
             """host -> device staging set k on the copy stream (after the compute stream has consumed the set's previous content)"""
+            item = item[:5]
             bufs = P["stage"][k]
             if bufs is None or any((a is None) != (b is None) or (a is not None and (a.shape != b.shape or a.dtype != b.dtype)) for a, b in zip(bufs, item)):
                 bufs = P["stage"][k] = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=dev) for t in item]
@@ -265,9 +266,15 @@ class Synthesizer(nn.Module):
                 ev.record(h2d)
             return ev
 
-        def run(k, ev_in):
+        def run(k, ev_in, noise):
             comp.wait_event(ev_in)
-            o = self.infer(*P["stage"][k])[0]
+            prev = self._noise_override
+            if noise is not None:          # tests: a sixth tuple element pins this item's two noise draws
+                self._noise_override = noise
+            try:
+                o = self.infer(*P["stage"][k])[0]
+            finally:
+                self._noise_override = prev
             P["consumed"][k] = torch.cuda.Event()
             P["consumed"][k].record(comp)          # (infer has copied the staged inputs into its own buffers by now, in stream order)
             n = o.numel()
@@ -292,10 +299,11 @@ class Synthesizer(nn.Module):
         while nxt is not None:
             k = n % depth
             cur_ev = ev_next
+            cur_noise = nxt[5] if len(nxt) > 5 else None
             nxt = next(it, None)
             if nxt is not None:
                 ev_next = stage((n + 1) % depth, nxt)       # overlaps the compute of item n
-            pending.append((k, run(k, cur_ev)))
+            pending.append((k, run(k, cur_ev, cur_noise)))
             n += 1
             if len(pending) >= depth:                       # keep `depth` items in flight, hand out the oldest
                 kk, out = pending.pop(0)

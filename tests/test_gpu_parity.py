@@ -326,13 +326,15 @@ def test_infer_stream_equals_item_by_item_calls():
         want.append(net.infer_to_host(inp["phone"].pin_memory(), inp["phone_lengths"].pin_memory(), inp["pitch"].pin_memory(), inp["nsff0"].pin_memory(),
                                       inp["sid"].pin_memory()).clone())
 
+    net._noise_override = None
+
     def gen():
         for inp in items:
-            net._noise_override = (inp["eps_z"], inp["eps_src"])     # (read by infer() when the item is submitted)
-            yield (inp["phone"].pin_memory(), inp["phone_lengths"].pin_memory(), inp["pitch"].pin_memory(), inp["nsff0"].pin_memory(), inp["sid"].pin_memory())
+            yield (inp["phone"].pin_memory(), inp["phone_lengths"].pin_memory(), inp["pitch"].pin_memory(), inp["nsff0"].pin_memory(), inp["sid"].pin_memory(),
+                   (inp["eps_z"], inp["eps_src"]))
 
     got = [o.clone() for o in net.infer_stream(gen())]
-    net._noise_override = None
+    assert net._noise_override is None
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert a.shape == b.shape and torch.equal(a, b)
