@@ -323,6 +323,25 @@ int rvc_attn_softmax(const float* S, const float* qkv, const float* mask, const 
                      void* vw, int32_t B, int32_t H, int32_t n_heads, int32_t T, int32_t Tk, int32_t window, void* stream);
 
 /*
+ * Scores + softmax of the attention for T <= 1024, head dim 96, as one cluster kernel (MultiHeadAttention.attention, synthesizers.py:221-250): a cluster
+ * of ceil(T/128) CTAs per 128 queries of a (batch item, head), one 128-key tile each; S = q.k^T and the banded relative-key term on tensor cores from the
+ * packed q / k planes the qkv projection wrote (planes = 2: split precision, the lo plane lo_chunks chunks behind the hi plane), softmax on the accumulator
+ * with the row maxima / sums exchanged through distributed shared memory.  Replaces the S launch of rvc_conv1d_tc + rvc_attn_softmax (+ the R buffer):
+ *   P  : packed fp16 [b][h][Tk/8 + 4][rvc_packed_rows(T)][8], Tk = 128 * ceil(T/128): chunks < Tk/8 hold softmax(s) over the keys, the last four chunks the
+ *        2w+1 band probabilities p[i, i + r - w] as columns r (zero-initialised by the caller once: entries whose key falls outside [0, Tk) are never written);
+ *   vw : the weights of the following P.v GEMM, fp16 [b][h][Tk/8 + 4][96][8]: v^T over the keys (written here) and, in the last four chunks, emb_v^T over
+ *        the relative positions (written by the caller once) — the relative-value term rides along as four more k-steps of that GEMM (Cin = Tk + 32).
+ * qk: packed planes [b][...chunks][rows][8] with q of head h in chunks q_chunk0 + 12 h .., k in k_chunk0 + 12 h ..; ek: emb_rel_k packed as planes
+ * [planes][12][32][8] (row = relative position, zero past 2w+1); qkv: the fp32 [B, 3H, T] projection (v rows); window <= 11.
+ */
+typedef struct {
+    const void* qk; int64_t qk_bs; int32_t q_chunk0, k_chunk0, lo_chunks, planes;
+    const void* ek; const float* qkv; const float* mask; void* P; void* vw;
+    int32_t B, H, n_heads, T, window, reserved;
+} rvc_attn_scores_desc;
+int rvc_attn_scores_cluster_tc(const rvc_attn_scores_desc* d, void* stream);
+
+/*
  * Caller side of the path: the feature preparation VC.voice_conversion performs between the embedder and
  * Synthesizer.infer (main/inference/convert.py:361-378).
  *   out[b,t,:] = feats[b,t/2,:]                                    (feats0 == NULL: F.interpolate(scale_factor=2), :361)

@@ -89,6 +89,13 @@ class FlowDesc(C.Structure):
                 ("post_rows", _i32)]
 
 
+class AttnScoresDesc(C.Structure):
+    """rvc_attn_scores_desc."""
+    _fields_ = [("qk", _vp), ("qk_bs", _i64), ("q_chunk0", _i32), ("k_chunk0", _i32), ("lo_chunks", _i32), ("planes", _i32),
+                ("ek", _vp), ("qkv", _vp), ("mask", _vp), ("P", _vp), ("vw", _vp),
+                ("B", _i32), ("H", _i32), ("n_heads", _i32), ("T", _i32), ("window", _i32), ("reserved", _i32)]
+
+
 class ResblockPairDesc(C.Structure):
     """rvc_resblock_pair_desc."""
     _fields_ = [("jobs", PairJob * 3), ("njobs", _i32), ("B", _i32), ("C", _i32), ("L", _i32), ("dtype", _i32), ("slope", _f32),
@@ -120,6 +127,7 @@ SIGNATURES = {
     "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_conv1d_tc": (C.c_int, [C.POINTER(Conv1dTcDesc), _vp]),
     "rvc_flow_reverse_tc": (C.c_int, [C.POINTER(FlowDesc), _vp]),
+    "rvc_attn_scores_cluster_tc": (C.c_int, [C.POINTER(AttnScoresDesc), _vp]),
     "rvc_conv1d_tc_chain_blob_bytes": (C.c_int64, [_i32]),
     "rvc_conv1d_tc_chain_build": (C.c_int, [C.POINTER(Conv1dTcDesc), C.POINTER(_i32), _i32, _vp, _i64]),
     "rvc_conv1d_tc_chain_run": (C.c_int, [_vp, _vp, _vp, _vp]),

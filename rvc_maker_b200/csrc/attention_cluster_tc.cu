@@ -1,0 +1,329 @@
+// Scores + softmax of the relative-position attention (MultiHeadAttention.attention, synthesizers.py:221-250) for T <= 1024 as ONE kernel:
+//   s[i,j] = (q_i . k_j + [|j-i| <= w] q_i . Ek[j-i+w]) / sqrt(dk);   s = -1e4 where mask_i * mask_j == 0;   P = softmax_j(s)
+// A CLUSTER of ceil(T / 128) <= 8 CTAs owns 128 queries of one (batch item, head); CTA kt of the cluster owns the keys [128 kt, 128 kt + 128):
+//   * one tcgen05 tile S[128 queries, 128 keys] = Q . K^T per CTA, operands = the packed q / k activation planes the qkv projection wrote
+//     (three split-precision terms hi.hi + lo.hi + hi.lo when the planes come in pairs), plus a 32-column tile Q . Ek^T for the banded relative-key term;
+//   * the softmax runs on the accumulator (thread = query): scale, band term, mask, local max -> the eight CTAs exchange row maxima through
+//     distributed shared memory, exp, local sum -> second exchange, normalise; logits and exponentials are parked in TMEM between the passes
+//     (tcgen05.st), so the thread holds 32 values at a time;
+//   * P leaves as the packed fp16 A operand of the P.v GEMM, [b][h][key / 8][row][8]; the 2w+1 band probabilities of a row are ALSO written as 32 extra
+//     "key" columns (chunks Tk/8 .. Tk/8+3), whose matching weight rows are Ev^T: the relative-value term sum_r p[i, i+r-w] Ev[r] becomes four more
+//     k-steps of the P.v GEMM instead of a separate fp32 pass and a residual input;
+//   * the clusters of query tile 0 also write v^T (the P.v GEMM's per-batch weights) for their key tile.
+// Replaces the S = q.k^T launch (scores through HBM: 8 MB per layer at T = 1000), the softmax launch and the R buffer of the per-launch path.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+#include <math.h>
+
+namespace {
+
+constexpr int DK = 96;               // head dim
+constexpr int NCHK = DK / 8;
+constexpr int BM = 128;              // queries per CTA = keys per CTA
+constexpr int NRP = 32;              // relative positions, padded (2w+1 <= 32)
+constexpr int NTHREADS = 256;        // warp 0: loader, warp 1: MMA issuer, warps 2-3: v^T (query tile 0), warps 4-7: softmax
+constexpr int PADL = 64;
+constexpr int MAXC = 8;              // cluster size limit (portable)
+constexpr int PLANE_BYTES = NCHK * BM * 16;          // one fp16 plane of a 128-row, 96-channel tile
+constexpr int EKP_BYTES = NCHK * NRP * 16;
+constexpr int QE_LD = 24;
+constexpr int SMEM_BYTES = 4 * PLANE_BYTES + 2 * EKP_BYTES + BM * QE_LD * 4 + BM * 4 + 2 * MAXC * BM * 4 + 64;
+constexpr int COL_S = 0, COL_R = 128, TMEM_COLS = 256;
+
+struct AParams {
+    const uint8_t* qk;        // packed q / k planes of the qkv projection: [b][planes * cpp chunks][Lp][16 B]
+    int64_t qk_bs;            // bytes per batch item
+    int32_t q_chunk0, k_chunk0, head_chunks, lo_chunks;    // first chunk of q / k of head 0, chunks per head, chunk offset of the lo plane (0: single plane)
+    const uint8_t* ek;        // packed Ek planes of this layer: [planes][NCHK][32 rows = relative positions][16 B]
+    const float* qkv;         // fp32 [B, 3H, T] (v rows for the v^T weights)
+    const float* mask;        // [B, T]
+    uint8_t* P;               // [b][h][nchunk_tot][Lp][16 B]
+    uint8_t* vw;              // [b][h][nchunk_tot][DK][16 B]
+    int32_t B, H, nh, T, Lp, W, nkt, nchunk_tot, planes;
+    float inv;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+          "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+          "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t h2u(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const AParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* q_s = smem;                                  // [planes][NCHK][128][16]
+    uint8_t* k_s = q_s + 2 * PLANE_BYTES;
+    uint8_t* e_s = k_s + 2 * PLANE_BYTES;                 // [planes][NCHK][32][16]
+    float* qe_s = reinterpret_cast<float*>(e_s + 2 * EKP_BYTES);     // [128][QE_LD]  (q_i . Ek[r]) / sqrt(dk)
+    float* km_s = qe_s + BM * QE_LD;                      // [128] key mask of this CTA's keys (0 beyond T)
+    float* mx_s = km_s + BM;                              // [MAXC][128] row maxima of every CTA of the cluster
+    float* sm_s = mx_s + MAXC * BM;                       // [MAXC][128] row sums
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_s + MAXC * BM);
+    const uint32_t LOAD_FULL = tc::smem_u32(bars), ACC_FULL = LOAD_FULL + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int kt = (int)cluster_ctarank();
+    const int cl = (int)blockIdx.x / p.nkt;                // cluster -> (batch item, head, query tile)
+    const int qt = cl % p.nkt, bh = cl / p.nkt;
+    const int h = bh % p.nh, b = bh / p.nh;
+    const int nterm = p.planes == 2 ? 3 : 1;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(LOAD_FULL, 1);
+        tc::mbar_init(ACC_FULL, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp == 0) {
+        // ======================= loader: q tile, k tile (both planes), Ek planes =======================
+        const uint32_t nbytes = (uint32_t)p.planes * (2u * PLANE_BYTES + EKP_BYTES);
+        if (lane == 0) tc::mbar_arrive_expect_tx(LOAD_FULL, nbytes);
+        __syncwarp();
+        const uint8_t* base = p.qk + (size_t)b * p.qk_bs;
+        for (int u = lane; u < p.planes * NCHK * 3; u += 32) {
+            const int what = u / (p.planes * NCHK), rr = u - what * p.planes * NCHK;     // 0: q, 1: k, 2: Ek
+            const int pl = rr / NCHK, c = rr - pl * NCHK;
+            if (what == 2) {
+                tc::bulk_g2s(tc::smem_u32(e_s + (size_t)pl * EKP_BYTES + (size_t)c * NRP * 16), p.ek + ((size_t)pl * NCHK + c) * NRP * 16, NRP * 16, LOAD_FULL);
+            } else {
+                const int chunk = (what == 0 ? p.q_chunk0 : p.k_chunk0) + h * p.head_chunks + c + pl * p.lo_chunks;
+                const int row0 = PADL + (what == 0 ? qt : kt) * BM;
+                tc::bulk_g2s(tc::smem_u32((what == 0 ? q_s : k_s) + (size_t)pl * PLANE_BYTES + (size_t)c * BM * 16), base + ((size_t)chunk * p.Lp + row0) * 16, BM * 16,
+                             LOAD_FULL);
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer: S = sum_terms Q . K^T (N = 128), rel = sum_terms Q . Ek^T (N = 32) =======================
+        tc::mbar_wait(LOAD_FULL, 0);
+        tc::fence_after_sync();
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+        const uint32_t idS = tc::make_idesc(0u, 128), idR = tc::make_idesc(0u, NRP);
+        const uint32_t lboA = ((uint32_t)BM & 0x3FFFu) << 16, lboE = ((uint32_t)NRP & 0x3FFFu) << 16;
+        const uint32_t qa = tc::smem_u32(q_s) >> 4, ka = tc::smem_u32(k_s) >> 4, ea = tc::smem_u32(e_s) >> 4;
+        uint32_t accS = 0, accR = 0;
+        for (int t = 0; t < nterm; ++t) {
+            const uint32_t qp = t == 1 ? PLANE_BYTES / 16 : 0, kp = t == 2 ? PLANE_BYTES / 16 : 0, ep = t == 2 ? EKP_BYTES / 16 : 0;    // (hi,hi) (lo,hi) (hi,lo)
+            for (int ks = 0; ks < NCHK / 2; ++ks) {
+                const uint32_t da = lboA | ((qa + qp + (uint32_t)(2 * ks * BM)) & 0x3FFFu);
+                const uint32_t db = lboA | ((ka + kp + (uint32_t)(2 * ks * BM)) & 0x3FFFu);
+                const uint32_t de = lboE | ((ea + ep + (uint32_t)(2 * ks * NRP)) & 0x3FFFu);
+                if (tc::elect_one()) {
+                    tc::umma<false>(tmem_base + COL_S, ((uint64_t)desc_hi << 32) | da, ((uint64_t)desc_hi << 32) | db, idS, accS);
+                    tc::umma<false>(tmem_base + COL_R, ((uint64_t)desc_hi << 32) | da, ((uint64_t)desc_hi << 32) | de, idR, accR);
+                }
+                accS = accR = 1;
+            }
+        }
+        if (tc::elect_one()) tc::umma_commit(ACC_FULL);
+        __syncwarp();
+    } else if (warp < 4) {
+        // ======================= v^T for this CTA's keys (clusters of query tile 0 only): [key / 8][d][8 keys] fp16 =======================
+        if (qt == 0) {
+            const float* vb = p.qkv + ((size_t)b * 3 * p.H + 2 * p.H + h * DK) * p.T;
+            uint8_t* vw = p.vw + ((size_t)(b * p.nh + h) * p.nchunk_tot) * DK * 16;
+            for (int u = (warp - 2) * 32 + lane; u < (BM / 8) * DK; u += 64) {
+                const int cc = u / DK, d = u - cc * DK;
+                const int key0 = kt * BM + 8 * cc;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = key0 + i < p.T ? vb[(size_t)d * p.T + key0 + i] : 0.f;
+                *reinterpret_cast<uint4*>(vw + ((size_t)(key0 / 8) * DK + d) * 16) = make_uint4(h2u(v[0], v[1]), h2u(v[2], v[3]), h2u(v[4], v[5]), h2u(v[6], v[7]));
+            }
+        }
+    } else {
+        // ======================= softmax warps: thread r owns query 128 qt + r =======================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int i = qt * BM + r;
+        const bool qok = i < p.T;
+        const int key0 = kt * BM;
+        const float* mb = p.mask + (size_t)b * p.T;
+        const float mq = qok ? mb[i] : 0.f;
+        km_s[r] = key0 + r < p.T ? mb[key0 + r] : -1.f;          // -1: beyond the sequence (excluded), 0: masked (-1e4), else valid
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int NR = 2 * p.W + 1;
+        tc::mbar_wait(ACC_FULL, 0);
+        tc::fence_after_sync();
+        {   // (q_i . Ek[r]) / sqrt(dk) for the 2w+1 relative positions -> this thread's row of qe_s
+            uint32_t v[32];
+            tc::tmem_ld<32>(t_row + COL_R, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < QE_LD; ++t) qe_s[r * QE_LD + t] = __uint_as_float(v[t]) * p.inv;
+        }
+        // ---- pass A: logits (scale, relative-key term, mask) parked in TMEM; local maximum
+        float m = -INFINITY;
+        const int rel0 = key0 - i + p.W;                          // rel of column 0
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            uint32_t v[32];
+            tc::tmem_ld<32>(t_row + COL_S + cb * 32, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                const int col = cb * 32 + t;
+                const float km = km_s[col];
+                float s = __uint_as_float(v[t]) * p.inv;
+                const int rel = rel0 + col;
+                if ((unsigned)rel < (unsigned)NR) s += qe_s[r * QE_LD + rel];
+                if (mq * km == 0.f) s = -1e4f;
+                if (km < 0.f || !qok) s = -INFINITY;
+                m = fmaxf(m, s);
+                v[t] = __float_as_uint(s);
+            }
+            tmem_st32(t_row + COL_S + cb * 32, v);
+        }
+        tmem_st_wait();
+        {
+            const uint32_t a = tc::smem_u32(mx_s + kt * BM + r);
+            for (int k = 0; k < p.nkt; ++k) st_cluster_f32(mapa(a, (uint32_t)k), m);
+        }
+    }
+    cluster_sync_all();                                    // (1) row maxima of all key tiles are in place (every thread of the cluster takes part)
+    float M = -INFINITY, l = 0.f;
+    if (warp >= 4) {
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int k = 0; k < p.nkt; ++k) M = fmaxf(M, mx_s[k * BM + r]);
+        // ---- pass B: exponentials parked in TMEM; local sum
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            uint32_t v[32];
+            tc::tmem_ld<32>(t_row + COL_S + cb * 32, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                const float e = M == -INFINITY ? 0.f : __expf(__uint_as_float(v[t]) - M);      // exp(-inf) = 0 for keys beyond the sequence
+                l += e;
+                v[t] = __float_as_uint(e);
+            }
+            tmem_st32(t_row + COL_S + cb * 32, v);
+        }
+        tmem_st_wait();
+        const uint32_t a = tc::smem_u32(sm_s + kt * BM + r);
+        for (int k = 0; k < p.nkt; ++k) st_cluster_f32(mapa(a, (uint32_t)k), l);
+    }
+    cluster_sync_all();                                    // (2) row sums
+    if (warp >= 4) {
+        const int q = warp & 3, r = q * 32 + lane;
+        const int i = qt * BM + r;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        float L = 0.f;
+        for (int k = 0; k < p.nkt; ++k) L += sm_s[k * BM + r];
+        const float rl = (i < p.T && L > 0.f) ? 1.f / L : 0.f;
+        const int NR = 2 * p.W + 1;
+        const int key0 = kt * BM, rel0 = key0 - i + p.W;
+        uint8_t* Pb = p.P + ((size_t)(b * p.nh + h) * p.nchunk_tot * p.Lp + PADL + i) * 16;
+        // ---- pass C: probabilities -> packed fp16 (+ the band members as the extra "relative position" columns)
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            uint32_t v[32];
+            tc::tmem_ld<32>(t_row + COL_S + cb * 32, v);
+            tc::tmem_ld_wait();
+            if (i < p.T) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float p8[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) p8[t] = __uint_as_float(v[8 * u + t]) * rl;
+                    *reinterpret_cast<uint4*>(Pb + (size_t)(kt * (BM / 8) + cb * 4 + u) * p.Lp * 16) =
+                        make_uint4(h2u(p8[0], p8[1]), h2u(p8[2], p8[3]), h2u(p8[4], p8[5]), h2u(p8[6], p8[7]));
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int rel = rel0 + cb * 32 + 8 * u + t;
+                        if ((unsigned)rel < (unsigned)NR)
+                            *reinterpret_cast<__half*>(Pb + (size_t)(p.nchunk_tot - NRP / 8 + rel / 8) * p.Lp * 16 + (rel % 8) * 2) = __float2half_rn(p8[t]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc::fence_before_sync();
+    cluster_sync_all();          // no CTA leaves while a peer may still write its row maxima / sums into it
+    if (warp == 1) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace
+
+RVC_API int rvc_attn_scores_cluster_tc(const rvc_attn_scores_desc* dp, void* stream) {
+    if (!dp) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: null descriptor");
+    const rvc_attn_scores_desc& d = *dp;
+    if (!d.qk || !d.ek || !d.qkv || !d.mask || !d.P || !d.vw) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: null pointer");
+    if (d.B <= 0 || d.T <= 0 || d.T > BM * MAXC || d.n_heads <= 0 || d.H != d.n_heads * DK)
+        return rvc::fail(RVC_ESHAPE, "rvc_attn_scores_cluster_tc: built for head dim 96 and T <= 1024 (got H = %d, heads = %d, T = %d)", d.H, d.n_heads, d.T);
+    if (d.window < 0 || 2 * d.window + 1 > QE_LD) return rvc::fail(RVC_ESHAPE, "rvc_attn_scores_cluster_tc: window %d > 11", d.window);
+    if (d.planes != 1 && d.planes != 2) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: planes must be 1 or 2");
+    if (((uintptr_t)d.qk | (uintptr_t)d.ek | (uintptr_t)d.P | (uintptr_t)d.vw) & 15) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: packed buffers need 16-byte alignment");
+    AParams p;
+    p.qk = (const uint8_t*)d.qk; p.qk_bs = d.qk_bs; p.q_chunk0 = d.q_chunk0; p.k_chunk0 = d.k_chunk0; p.head_chunks = NCHK; p.lo_chunks = d.planes == 2 ? d.lo_chunks : 0;
+    p.ek = (const uint8_t*)d.ek; p.qkv = d.qkv; p.mask = d.mask; p.P = (uint8_t*)d.P; p.vw = (uint8_t*)d.vw;
+    p.B = d.B; p.H = d.H; p.nh = d.n_heads; p.T = d.T; p.Lp = (int)rvc_packed_rows(d.T); p.W = d.window;
+    p.nkt = (d.T + BM - 1) / BM; p.nchunk_tot = p.nkt * (BM / 8) + NRP / 8; p.planes = d.planes;
+    p.inv = 1.f / sqrtf((float)DK);
+    auto kern = attn_scores_cluster_kernel;
+    static bool opted[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !opted[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return rvc::fail((int)e, "rvc_attn_scores_cluster_tc: smem opt-in: %s", cudaGetErrorString(e));
+        if (dev >= 0 && dev < 64) opted[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(d.B * d.n_heads * p.nkt * p.nkt));
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.nkt; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+    if (le != cudaSuccess) return rvc::fail((int)le, "rvc_attn_scores_cluster_tc: launch: %s", cudaGetErrorString(le));
+    return rvc::check_launch("rvc_attn_scores_cluster_tc");
+}

@@ -14,7 +14,7 @@ import threading
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc, FlowDesc, ResblockPairDesc
+from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, AttnScoresDesc, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc, FlowDesc, ResblockPairDesc
 
 LRELU_SLOPE = 0.1
 WINDOW = 10
@@ -132,6 +132,8 @@ class Engine:
         self.use_chain = os.environ.get("RVC_B200_CHAIN", "1") != "0"
         # ... or, for the standard flow shape, the whole reverse flow as one cluster kernel that keeps every intermediate on the chip (rvc_flow_reverse_tc)
         self.use_flow_cluster = os.environ.get("RVC_B200_FLOW_CLUSTER", "1") != "0"
+        # attention scores + softmax of a layer as one cluster kernel for T <= 1024 (rvc_attn_scores_cluster_tc) instead of S launch + softmax launch
+        self.use_attn_cluster = os.environ.get("RVC_B200_ATTN_CLUSTER", "1") != "0"
         self._chain = None
 
     # ------------------------------------------------------------------ weight folding / packing
@@ -263,6 +265,19 @@ class Engine:
             tc_w["t_proj_w"] = (_f(e.proj.weight), dt)
             if c["D"] % 16 == 0:
                 tc_w["t_emb_w"] = (_f(e.emb_phone.weight).unsqueeze(-1).contiguous(), dt)   # Linear as a 1x1 conv [H, D, 1]
+            # attention cluster kernel: emb_rel_k as packed fp16 planes [hi | lo][dk/8][32 rows][8] (row = relative position), emb_rel_v^T as the
+            # four extra weight chunks of the P.v GEMM [4][dk][8] (relative positions as "keys")
+            if c["nh"] * 96 == H and 2 * WINDOW + 1 <= 24:
+                for i in range(c["nl"]):
+                    a = e.encoder.attn_layers[i]
+                    ek = torch.zeros(32, 96)
+                    ek[:2 * WINDOW + 1] = _f(a.emb_rel_k)[0]
+                    hi = ek.half()
+                    planes = torch.stack([hi, (ek - hi.float()).half()])                        # [2][32][96]
+                    W[f"t_ek_p{i}"] = planes.view(2, 32, 12, 8).permute(0, 2, 1, 3).contiguous().view(torch.uint8).reshape(-1)
+                    ev = torch.zeros(32, 96)
+                    ev[:2 * WINDOW + 1] = _f(a.emb_rel_v)[0]
+                    W[f"t_evT{i}"] = ev.view(4, 8, 96).permute(0, 2, 1).contiguous().half().view(torch.uint8).reshape(-1)   # [4][96][8]
             if self.enc_split:   # low weight planes of the split-precision GEMMs: fp16(W - fp16(W))
                 for k in [k for k in tc_w if k.startswith(("t_qkv_w", "t_o_w", "t_proj_w", "t_emb_w"))]:
                     w_ = tc_w[k][0]
@@ -523,17 +538,42 @@ class Engine:
             else:
                 p.add("pack_x", lib.rvc_pack_act, x.data_ptr(), None, None, 1.0, H * T, T, None, xa.data_ptr(), B, H, T, dt, 1.0, kind="pack_act",
                       bytes_=6.0 * B * H * T)
+            attn_cl = tc_attn and self.use_attn_cluster and dk == 96 and T <= 1024 and "t_ek_p0" in W
             if tc_attn:
                 Tk = (T + 127) // 128 * 128
                 qkva = pk(3 * H)
+                qkv_bs = npl * (3 * H // 8) * cb
+            if tc_attn and not attn_cl:
                 Sb = self._buf(p, B, nh, Tk, T)
                 Pb = self._zbuf(p, B * nh * (Tk // 8) * Lp * 16)
                 Rb = self._buf(p, B, H, T)
                 vwb = self._buf(p, B * nh * (Tk // 8) * dk * 4, dtype=torch.int32)
-                qkv_bs = npl * (3 * H // 8) * cb
+            if attn_cl:
+                nct = Tk // 8 + 4                                  # key chunks + the four "relative position" chunks of P / of the P.v weights
+                Pb = self._zbuf(p, B * nh * nct * Lp * 16)         # (band entries whose key falls outside the sequence stay zero)
+                vws = []
+                for i in range(c["nl"]):                           # per layer: v^T is rewritten every call, the emb_rel_v^T tail is constant
+                    vw_i = self._zbuf(p, B * nh * nct * dk * 16)
+                    vw_i.view(B * nh, nct, dk * 16)[:, Tk // 8:, :] = W[f"t_evT{i}"].view(1, 4, dk * 16)
+                    vws.append(vw_i)
             for i in range(c["nl"]):
                 gemm(f"qkv{i}", xa, H, f"t_qkv_w{i}", 3 * H, dict(bias=W[f"qkv_b{i}"], y=vqkv, **(outs(qkva, 3 * H) if tc_attn else {})))
-                if tc_attn:
+                if attn_cl:
+                    # scores + softmax in one cluster kernel; P carries the band probabilities as 32 extra columns, the P.v weights carry emb_rel_v^T
+                    ad = AttnScoresDesc()
+                    ad.qk, ad.qk_bs, ad.q_chunk0, ad.k_chunk0, ad.lo_chunks, ad.planes = qkva.data_ptr(), qkv_bs, 0, H // 8, 3 * H // 8, npl
+                    ad.ek, ad.qkv, ad.mask, ad.P, ad.vw = W[f"t_ek_p{i}"].data_ptr(), qkv.data_ptr(), p.mask.data_ptr(), Pb.data_ptr(), vws[i].data_ptr()
+                    ad.B, ad.H, ad.n_heads, ad.T, ad.window = B, H, nh, T, WINDOW
+                    p.keep.append(ad)
+                    p.add(f"attn_sc{i}", lib.rvc_attn_scores_cluster_tc, C.byref(ad), flops=2.0 * B * H * T * T, bytes_=B * nh * (Tk * T * 2.0 + 2.0 * 4 * H // nh * T),
+                          kind="attn_scores_cluster_tc")
+                    jobs = []
+                    for h in range(nh):
+                        ya = atta.data_ptr() + (h * dk // 8) * cb
+                        jobs.append(dict(a=Pb.data_ptr() + h * nct * cb, a_bs=nh * nct * cb, w=vws[i].data_ptr() + h * nct * dk * 16, w_bs=nh * nct * dk * 16,
+                                         y_act=ya, y_act_bs=npl * (H // 8) * cb, y_lo=(ya + (H // 8) * cb if split else None)))
+                    self._tc(p, f"attn_pv{i}", jobs, B=B, Cin=Tk + 32, Cout=dk, L=T, dtype=dt, tag="attn", flops=2.0 * B * H * T * T)
+                elif tc_attn:
                     # S[b][h][key/8][query][8] = q . k^T (channel-blocked over the keys): the packed k activations of each batch item are the GEMM's weights
                     jobs = []
                     for h in range(nh):

@@ -338,3 +338,30 @@ def test_infer_stream_equals_item_by_item_calls():
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert a.shape == b.shape and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,T", [(1, 1000), (2, 173), (3, 128), (2, 129), (1, 1), (2, 1024), (40, 64)])
+def test_attention_cluster_kernel_matches_per_launch_path(B, T, monkeypatch):
+    """rvc_attn_scores_cluster_tc (scores + softmax in one cluster kernel, row maxima / sums through distributed shared memory, the relative-value
+    term as four extra k-steps of the P.v GEMM) against the S launch + softmax launch path on the same model: same fp16 probabilities up to the last
+    bit of the exponentials; the relative-value term now sees fp16 P / fp16 Ev.  Key-tile seams at multiples of 128, ragged lengths, T = 1, T = 1024."""
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=77, heated=True)
+    inp = cases.synth_inputs(cfg, B, T, seed=3 * B + T, ragged=B > 1)
+    monkeypatch.setenv("RVC_B200_ATTN_CLUSTER", "0")
+    ref_net = build_net(cfg, sd, True, precision="tc")
+    ref = run_net(ref_net, inp)
+    assert not any(m and m["name"] == "attn_sc0" for m in ref_net._engine.plan("enc", B, T).meta)
+    monkeypatch.setenv("RVC_B200_ATTN_CLUSTER", "1")
+    net = build_net(cfg, sd, True, precision="tc")
+    out = run_net(net, inp)
+    assert any(m and m["name"] == "attn_sc0" for m in net._engine.plan("enc", B, T).meta)
+    for k in ("m_p", "logs_p", "z"):
+        assert torch.isfinite(out[k]).all(), k
+        scale = float(ref[k].abs().max())
+        err = float((out[k] - ref[k]).abs().max())
+        print(f"[attn cluster B={B} T={T}] {k}: err {err:.2e} (max|ref| {scale:.2f})")
+        assert err <= 2e-3 * max(1.0, scale), (k, err, scale)
+    assert float((out["o"] - ref["o"]).abs().max()) <= 6e-4
+    again = run_net(net, inp)
+    assert torch.equal(again["m_p"], out["m_p"]) and torch.equal(again["o"], out["o"])
