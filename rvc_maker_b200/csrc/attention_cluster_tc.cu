@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
             const float* vb = p.qkv + ((size_t)b * 3 * p.H + 2 * p.H + h * DK) * p.T;
             uint8_t* vw = p.vw + ((size_t)(b * p.nh + h) * p.nchunk_tot) * DK * 16;
             for (int u = (warp - 2) * 32 + lane; u < (BM / 8) * DK; u += 64) {
-                const int cc = u / DK, d = u - cc * DK;
+                const int d = u / (BM / 8), cc = u - d * (BM / 8);      // lanes run over the key chunks of one dim: 16 lanes read 512 contiguous bytes
                 const int key0 = kt * BM + 8 * cc;
                 float v[8];
 #pragma unroll
