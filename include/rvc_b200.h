@@ -324,10 +324,10 @@ int rvc_attn_softmax(const float* S, const float* qkv, const float* mask, const 
 
 /*
  * Scores + softmax of the attention for T <= 1024, head dim 96, as one cluster kernel (MultiHeadAttention.attention, synthesizers.py:221-250): a cluster
- * of ceil(T/128) CTAs per 128 queries of a (batch item, head), one 128-key tile each; S = q.k^T and the banded relative-key term on tensor cores from the
+ * of ceil(T/256) CTAs per 128 queries of a (batch item, head), one 256-key tile each; S = q.k^T and the banded relative-key term on tensor cores from the
  * packed q / k planes the qkv projection wrote (planes = 2: split precision, the lo plane lo_chunks chunks behind the hi plane), softmax on the accumulator
  * with the row maxima / sums exchanged through distributed shared memory.  Replaces the S launch of rvc_conv1d_tc + rvc_attn_softmax (+ the R buffer):
- *   P  : packed fp16 [b][h][Tk/8 + 4][rvc_packed_rows(T)][8], Tk = 128 * ceil(T/128): chunks < Tk/8 hold softmax(s) over the keys, the last four chunks the
+ *   P  : packed fp16 [b][h][Tk/8 + 4][rvc_packed_rows(T)][8], Tk = 256 * ceil(T/256): chunks < Tk/8 hold softmax(s) over the keys, the last four chunks the
  *        2w+1 band probabilities p[i, i + r - w] as columns r (zero-initialised by the caller once: entries whose key falls outside [0, Tk) are never written);
  *   vw : the weights of the following P.v GEMM, fp16 [b][h][Tk/8 + 4][96][8]: v^T over the keys (written here) and, in the last four chunks, emb_v^T over
  *        the relative positions (written by the caller once) — the relative-value term rides along as four more k-steps of that GEMM (Cin = Tk + 32).

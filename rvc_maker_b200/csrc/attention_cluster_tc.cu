@@ -1,11 +1,12 @@
 // Scores + softmax of the relative-position attention (MultiHeadAttention.attention, synthesizers.py:221-250) for T <= 1024 as ONE kernel:
 //   s[i,j] = (q_i . k_j + [|j-i| <= w] q_i . Ek[j-i+w]) / sqrt(dk);   s = -1e4 where mask_i * mask_j == 0;   P = softmax_j(s)
-// A CLUSTER of ceil(T / 128) <= 8 CTAs owns 128 queries of one (batch item, head); CTA kt of the cluster owns the keys [128 kt, 128 kt + 128):
-//   * one tcgen05 tile S[128 queries, 128 keys] = Q . K^T per CTA, operands = the packed q / k activation planes the qkv projection wrote
+// A CLUSTER of ceil(T / 256) <= 4 CTAs owns 128 queries of one (batch item, head); CTA kt of the cluster owns the keys [256 kt, 256 kt + 256)
+// (clusters of eight 128-key CTAs did not all fit the GPU at once: 15 of the 16 clusters of a T = 1000 layer, i.e. two rounds):
+//   * one tcgen05 tile S[128 queries, 256 keys] = Q . K^T per CTA, operands = the packed q / k activation planes the qkv projection wrote
 //     (three split-precision terms hi.hi + lo.hi + hi.lo when the planes come in pairs), plus a 32-column tile Q . Ek^T for the banded relative-key term;
-//   * the softmax runs on the accumulator (thread = query): scale, band term, mask, local max -> the eight CTAs exchange row maxima through
-//     distributed shared memory, exp, local sum -> second exchange, normalise; logits and exponentials are parked in TMEM between the passes
-//     (tcgen05.st), so the thread holds 32 values at a time;
+//   * the softmax runs on the accumulator with sixteen warps (thread = one query x 64 keys): scale, band term, mask, local max -> combined over
+//     the four column groups in shared memory, then over the CTAs of the cluster through distributed shared memory; exp, sums the same way,
+//     normalise; logits and exponentials are parked in TMEM between the passes (tcgen05.st), so a thread holds 32 values at a time;
 //   * P leaves as the packed fp16 A operand of the P.v GEMM, [b][h][key / 8][row][8]; the 2w+1 band probabilities of a row are ALSO written as 32 extra
 //     "key" columns (chunks Tk/8 .. Tk/8+3), whose matching weight rows are Ev^T: the relative-value term sum_r p[i, i+r-w] Ev[r] becomes four more
 //     k-steps of the P.v GEMM instead of a separate fp32 pass and a residual input;
@@ -20,16 +21,20 @@ namespace {
 
 constexpr int DK = 96;               // head dim
 constexpr int NCHK = DK / 8;
-constexpr int BM = 128;              // queries per CTA = keys per CTA
+constexpr int BM = 128;              // queries per CTA
+constexpr int BK = 256;              // keys per CTA
+constexpr int NG = 4;                // softmax column groups (64 keys each)
 constexpr int NRP = 32;              // relative positions, padded (2w+1 <= 32)
-constexpr int NTHREADS = 256;        // warp 0: loader, warp 1: MMA issuer, warps 2-3: v^T (query tile 0), warps 4-7: softmax
+constexpr int NEPI = NG * 128;       // softmax threads
+constexpr int NTHREADS = 128 + NEPI; // warp 0: loader, warp 1: MMA issuer, warps 2-3: idle, warps 4-19: softmax (lane quarter = warp % 4, group = (warp - 4) / 4)
 constexpr int PADL = 64;
-constexpr int MAXC = 8;              // cluster size limit (portable)
-constexpr int PLANE_BYTES = NCHK * BM * 16;          // one fp16 plane of a 128-row, 96-channel tile
+constexpr int MAXC = 4;              // CTAs per cluster
+constexpr int QPLANE_BYTES = NCHK * BM * 16;         // one fp16 plane of the 128-query tile
+constexpr int KPLANE_BYTES = NCHK * BK * 16;         // ... of the 256-key tile
 constexpr int EKP_BYTES = NCHK * NRP * 16;
 constexpr int QE_LD = 24;
-constexpr int SMEM_BYTES = 4 * PLANE_BYTES + 2 * EKP_BYTES + BM * QE_LD * 4 + BM * 4 + 2 * MAXC * BM * 4 + 64;
-constexpr int COL_S = 0, COL_R = 128, TMEM_COLS = 256;
+constexpr int SMEM_BYTES = 2 * QPLANE_BYTES + 2 * KPLANE_BYTES + 2 * EKP_BYTES + BM * QE_LD * 4 + BK * 4 + 2 * NG * BM * 4 + 2 * MAXC * BM * 4 + 64;
+constexpr int COL_S = 0, COL_R = 256, TMEM_COLS = 512;
 
 struct AParams {
     const uint8_t* qk;        // packed q / k planes of the qkv projection: [b][planes * cpp chunks][Lp][16 B]
@@ -40,7 +45,7 @@ struct AParams {
     const float* mask;        // [B, T]
     uint8_t* P;               // [b][h][nchunk_tot][Lp][16 B]
     uint8_t* vw;              // [b][h][nchunk_tot][DK][16 B]
-    int32_t B, H, nh, T, Lp, W, nkt, nchunk_tot, planes;
+    int32_t B, H, nh, T, Lp, W, nkt, nqt, nchunk_tot, planes;
     float inv;
 };
 
@@ -80,11 +85,13 @@ __device__ __forceinline__ uint32_t h2u(float a, float b) {
 __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const AParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* q_s = smem;                                  // [planes][NCHK][128][16]
-    uint8_t* k_s = q_s + 2 * PLANE_BYTES;
-    uint8_t* e_s = k_s + 2 * PLANE_BYTES;                 // [planes][NCHK][32][16]
+    uint8_t* k_s = q_s + 2 * QPLANE_BYTES;                // [planes][NCHK][256][16]
+    uint8_t* e_s = k_s + 2 * KPLANE_BYTES;                // [planes][NCHK][32][16]
     float* qe_s = reinterpret_cast<float*>(e_s + 2 * EKP_BYTES);     // [128][QE_LD]  (q_i . Ek[r]) / sqrt(dk)
-    float* km_s = qe_s + BM * QE_LD;                      // [128] key mask of this CTA's keys (0 beyond T)
-    float* mx_s = km_s + BM;                              // [MAXC][128] row maxima of every CTA of the cluster
+    float* km_s = qe_s + BM * QE_LD;                      // [256] key mask of this CTA's keys (-1 beyond T)
+    float* lm_s = km_s + BK;                              // [NG][128] row maxima of the column groups
+    float* ls_s = lm_s + NG * BM;                         // [NG][128] row sums of the column groups
+    float* mx_s = ls_s + NG * BM;                         // [MAXC][128] row maxima of every CTA of the cluster
     float* sm_s = mx_s + MAXC * BM;                       // [MAXC][128] row sums
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_s + MAXC * BM);
     const uint32_t LOAD_FULL = tc::smem_u32(bars), ACC_FULL = LOAD_FULL + 8;
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
     const int lane = threadIdx.x & 31;
     const int kt = (int)cluster_ctarank();
     const int cl = (int)blockIdx.x / p.nkt;                // cluster -> (batch item, head, query tile)
-    const int qt = cl % p.nkt, bh = cl / p.nkt;
+    const int qt = cl % p.nqt, bh = cl / p.nqt;
     const int h = bh % p.nh, b = bh / p.nh;
     const int nterm = p.planes == 2 ? 3 : 1;
 
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
 
     if (warp == 0) {
         // ======================= loader: q tile, k tile (both planes), Ek planes =======================
-        const uint32_t nbytes = (uint32_t)p.planes * (2u * PLANE_BYTES + EKP_BYTES);
+        const uint32_t nbytes = (uint32_t)p.planes * (QPLANE_BYTES + KPLANE_BYTES + EKP_BYTES);
         if (lane == 0) tc::mbar_arrive_expect_tx(LOAD_FULL, nbytes);
         __syncwarp();
         const uint8_t* base = p.qk + (size_t)b * p.qk_bs;
@@ -124,9 +131,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
                 tc::bulk_g2s(tc::smem_u32(e_s + (size_t)pl * EKP_BYTES + (size_t)c * NRP * 16), p.ek + ((size_t)pl * NCHK + c) * NRP * 16, NRP * 16, LOAD_FULL);
             } else {
                 const int chunk = (what == 0 ? p.q_chunk0 : p.k_chunk0) + h * p.head_chunks + c + pl * p.lo_chunks;
-                const int row0 = PADL + (what == 0 ? qt : kt) * BM;
-                tc::bulk_g2s(tc::smem_u32((what == 0 ? q_s : k_s) + (size_t)pl * PLANE_BYTES + (size_t)c * BM * 16), base + ((size_t)chunk * p.Lp + row0) * 16, BM * 16,
-                             LOAD_FULL);
+                if (what == 0)
+                    tc::bulk_g2s(tc::smem_u32(q_s + (size_t)pl * QPLANE_BYTES + (size_t)c * BM * 16), base + ((size_t)chunk * p.Lp + PADL + qt * BM) * 16, BM * 16, LOAD_FULL);
+                else   // (rows past the sequence are the zero rows of the packed buffer; the last key tile may end before 256 rows: Lp covers roundup(T, 256) + 64)
+                    tc::bulk_g2s(tc::smem_u32(k_s + (size_t)pl * KPLANE_BYTES + (size_t)c * BK * 16), base + ((size_t)chunk * p.Lp + PADL + kt * BK) * 16, BK * 16, LOAD_FULL);
             }
         }
     } else if (warp == 1) {
@@ -134,15 +142,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
         tc::mbar_wait(LOAD_FULL, 0);
         tc::fence_after_sync();
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-        const uint32_t idS = tc::make_idesc(0u, 128), idR = tc::make_idesc(0u, NRP);
-        const uint32_t lboA = ((uint32_t)BM & 0x3FFFu) << 16, lboE = ((uint32_t)NRP & 0x3FFFu) << 16;
+        const uint32_t idS = tc::make_idesc(0u, BK), idR = tc::make_idesc(0u, NRP);
+        const uint32_t lboA = ((uint32_t)BM & 0x3FFFu) << 16, lboK = ((uint32_t)BK & 0x3FFFu) << 16, lboE = ((uint32_t)NRP & 0x3FFFu) << 16;
         const uint32_t qa = tc::smem_u32(q_s) >> 4, ka = tc::smem_u32(k_s) >> 4, ea = tc::smem_u32(e_s) >> 4;
         uint32_t accS = 0, accR = 0;
         for (int t = 0; t < nterm; ++t) {
-            const uint32_t qp = t == 1 ? PLANE_BYTES / 16 : 0, kp = t == 2 ? PLANE_BYTES / 16 : 0, ep = t == 2 ? EKP_BYTES / 16 : 0;    // (hi,hi) (lo,hi) (hi,lo)
+            const uint32_t qp = t == 1 ? QPLANE_BYTES / 16 : 0, kp = t == 2 ? KPLANE_BYTES / 16 : 0, ep = t == 2 ? EKP_BYTES / 16 : 0;    // (hi,hi) (lo,hi) (hi,lo)
             for (int ks = 0; ks < NCHK / 2; ++ks) {
                 const uint32_t da = lboA | ((qa + qp + (uint32_t)(2 * ks * BM)) & 0x3FFFu);
-                const uint32_t db = lboA | ((ka + kp + (uint32_t)(2 * ks * BM)) & 0x3FFFu);
+                const uint32_t db = lboK | ((ka + kp + (uint32_t)(2 * ks * BK)) & 0x3FFFu);
                 const uint32_t de = lboE | ((ea + ep + (uint32_t)(2 * ks * NRP)) & 0x3FFFu);
                 if (tc::elect_one()) {
                     tc::umma<false>(tmem_base + COL_S, ((uint64_t)desc_hi << 32) | da, ((uint64_t)desc_hi << 32) | db, idS, accS);
@@ -153,81 +161,84 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
         }
         if (tc::elect_one()) tc::umma_commit(ACC_FULL);
         __syncwarp();
-    } else if (warp < 4) {
-        // ======================= v^T for this CTA's keys (clusters of query tile 0 only): [key / 8][d][8 keys] fp16 =======================
-        if (qt == 0) {
-            const float* vb = p.qkv + ((size_t)b * 3 * p.H + 2 * p.H + h * DK) * p.T;
-            uint8_t* vw = p.vw + ((size_t)(b * p.nh + h) * p.nchunk_tot) * DK * 16;
-            for (int u = (warp - 2) * 32 + lane; u < (BM / 8) * DK; u += 64) {
-                const int d = u / (BM / 8), cc = u - d * (BM / 8);      // lanes run over the key chunks of one dim: 16 lanes read 512 contiguous bytes
-                const int key0 = kt * BM + 8 * cc;
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = key0 + i < p.T ? vb[(size_t)d * p.T + key0 + i] : 0.f;
-                *reinterpret_cast<uint4*>(vw + ((size_t)(key0 / 8) * DK + d) * 16) = make_uint4(h2u(v[0], v[1]), h2u(v[2], v[3]), h2u(v[4], v[5]), h2u(v[6], v[7]));
-            }
-        }
-    } else {
-        // ======================= softmax warps: thread r owns query 128 qt + r =======================
-        const int q = warp & 3;
+    } else if (warp >= 4) {
+        // ======================= softmax warps: thread = query 128 qt + r, keys [64 g, 64 g + 64) of this CTA's 256 =======================
+        const int q = warp & 3, g = (warp - 4) >> 2;
         const int r = q * 32 + lane;
+        const int et = threadIdx.x - 128;
         const int i = qt * BM + r;
         const bool qok = i < p.T;
-        const int key0 = kt * BM;
+        const int key0 = kt * BK;
         const float* mb = p.mask + (size_t)b * p.T;
+        if (qt == 0) {
+            // v^T for this CTA's keys (the P.v GEMM's per-batch weights), written by the clusters of query tile 0: [key / 8][d][8 keys] fp16
+            const float* vb = p.qkv + ((size_t)b * 3 * p.H + 2 * p.H + h * DK) * p.T;
+            uint8_t* vw = p.vw + ((size_t)(b * p.nh + h) * p.nchunk_tot) * DK * 16;
+            for (int u = et; u < (BK / 8) * DK; u += NEPI) {
+                const int d = u / (BK / 8), cc = u - d * (BK / 8);      // lanes run over the key chunks of one dim: contiguous reads
+                const int k0 = key0 + 8 * cc;
+                float v[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[t] = k0 + t < p.T ? vb[(size_t)d * p.T + k0 + t] : 0.f;
+                *reinterpret_cast<uint4*>(vw + ((size_t)(k0 / 8) * DK + d) * 16) = make_uint4(h2u(v[0], v[1]), h2u(v[2], v[3]), h2u(v[4], v[5]), h2u(v[6], v[7]));
+            }
+        }
         const float mq = qok ? mb[i] : 0.f;
-        km_s[r] = key0 + r < p.T ? mb[key0 + r] : -1.f;          // -1: beyond the sequence (excluded), 0: masked (-1e4), else valid
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et < BK) km_s[et] = key0 + et < p.T ? mb[key0 + et] : -1.f;      // -1: beyond the sequence (excluded), 0: masked (-1e4), else valid
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
         const int NR = 2 * p.W + 1;
         tc::mbar_wait(ACC_FULL, 0);
         tc::fence_after_sync();
-        {   // (q_i . Ek[r]) / sqrt(dk) for the 2w+1 relative positions -> this thread's row of qe_s
+        if (g == 0) {   // (q_i . Ek[r]) / sqrt(dk) for the 2w+1 relative positions -> row r of qe_s
             uint32_t v[32];
             tc::tmem_ld<32>(t_row + COL_R, v);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int t = 0; t < QE_LD; ++t) qe_s[r * QE_LD + t] = __uint_as_float(v[t]) * p.inv;
         }
-        // ---- pass A: logits (scale, relative-key term, mask) parked in TMEM; local maximum
+        asm volatile("bar.sync 1, 512;" ::: "memory");           // km_s, qe_s
+        // ---- pass A: logits (scale, relative-key term, mask) parked in TMEM; maximum over this thread's 64 keys
         float m = -INFINITY;
-        const int rel0 = key0 - i + p.W;                          // rel of column 0
+        const int rel0 = key0 + 64 * g - i + p.W;                 // rel of this thread's column 0
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 0; cb < 2; ++cb) {
             uint32_t v[32];
-            tc::tmem_ld<32>(t_row + COL_S + cb * 32, v);
+            tc::tmem_ld<32>(t_row + COL_S + 64 * g + cb * 32, v);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
                 const int col = cb * 32 + t;
-                const float km = km_s[col];
-                float s = __uint_as_float(v[t]) * p.inv;
+                const float km = km_s[64 * g + col];
+                float sv = __uint_as_float(v[t]) * p.inv;
                 const int rel = rel0 + col;
-                if ((unsigned)rel < (unsigned)NR) s += qe_s[r * QE_LD + rel];
-                if (mq * km == 0.f) s = -1e4f;
-                if (km < 0.f || !qok) s = -INFINITY;
-                m = fmaxf(m, s);
-                v[t] = __float_as_uint(s);
+                if ((unsigned)rel < (unsigned)NR) sv += qe_s[r * QE_LD + rel];
+                if (mq * km == 0.f) sv = -1e4f;
+                if (km < 0.f || !qok) sv = -INFINITY;
+                m = fmaxf(m, sv);
+                v[t] = __float_as_uint(sv);
             }
-            tmem_st32(t_row + COL_S + cb * 32, v);
+            tmem_st32(t_row + COL_S + 64 * g + cb * 32, v);
         }
         tmem_st_wait();
-        {
+        lm_s[g * BM + r] = m;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (g == 0) {
+            const float mm = fmaxf(fmaxf(lm_s[r], lm_s[BM + r]), fmaxf(lm_s[2 * BM + r], lm_s[3 * BM + r]));
             const uint32_t a = tc::smem_u32(mx_s + kt * BM + r);
-            for (int k = 0; k < p.nkt; ++k) st_cluster_f32(mapa(a, (uint32_t)k), m);
+            for (int k = 0; k < p.nkt; ++k) st_cluster_f32(mapa(a, (uint32_t)k), mm);
         }
     }
     cluster_sync_all();                                    // (1) row maxima of all key tiles are in place (every thread of the cluster takes part)
-    float M = -INFINITY, l = 0.f;
     if (warp >= 4) {
-        const int q = warp & 3, r = q * 32 + lane;
+        const int q = warp & 3, g = (warp - 4) >> 2, r = q * 32 + lane;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        float M = -INFINITY, l = 0.f;
         for (int k = 0; k < p.nkt; ++k) M = fmaxf(M, mx_s[k * BM + r]);
-        // ---- pass B: exponentials parked in TMEM; local sum
+        // ---- pass B: exponentials parked in TMEM; sum over this thread's 64 keys
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 0; cb < 2; ++cb) {
             uint32_t v[32];
-            tc::tmem_ld<32>(t_row + COL_S + cb * 32, v);
+            tc::tmem_ld<32>(t_row + COL_S + 64 * g + cb * 32, v);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
@@ -235,42 +246,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
                 l += e;
                 v[t] = __float_as_uint(e);
             }
-            tmem_st32(t_row + COL_S + cb * 32, v);
+            tmem_st32(t_row + COL_S + 64 * g + cb * 32, v);
         }
         tmem_st_wait();
-        const uint32_t a = tc::smem_u32(sm_s + kt * BM + r);
-        for (int k = 0; k < p.nkt; ++k) st_cluster_f32(mapa(a, (uint32_t)k), l);
+        ls_s[g * BM + r] = l;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (g == 0) {
+            const float ll = (ls_s[r] + ls_s[BM + r]) + (ls_s[2 * BM + r] + ls_s[3 * BM + r]);
+            const uint32_t a = tc::smem_u32(sm_s + kt * BM + r);
+            for (int k = 0; k < p.nkt; ++k) st_cluster_f32(mapa(a, (uint32_t)k), ll);
+        }
     }
     cluster_sync_all();                                    // (2) row sums
     if (warp >= 4) {
-        const int q = warp & 3, r = q * 32 + lane;
+        const int q = warp & 3, g = (warp - 4) >> 2, r = q * 32 + lane;
         const int i = qt * BM + r;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
         float L = 0.f;
         for (int k = 0; k < p.nkt; ++k) L += sm_s[k * BM + r];
         const float rl = (i < p.T && L > 0.f) ? 1.f / L : 0.f;
         const int NR = 2 * p.W + 1;
-        const int key0 = kt * BM, rel0 = key0 - i + p.W;
+        const int rel0 = kt * BK + 64 * g - i + p.W;
         uint8_t* Pb = p.P + ((size_t)(b * p.nh + h) * p.nchunk_tot * p.Lp + PADL + i) * 16;
         // ---- pass C: probabilities -> packed fp16 (+ the band members as the extra "relative position" columns)
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 0; cb < 2; ++cb) {
             uint32_t v[32];
-            tc::tmem_ld<32>(t_row + COL_S + cb * 32, v);
+            tc::tmem_ld<32>(t_row + COL_S + 64 * g + cb * 32, v);
             tc::tmem_ld_wait();
             if (i < p.T) {
+                const bool band = rel0 + cb * 32 < NR && rel0 + cb * 32 + 31 >= 0;      // (any of these 32 keys within +-w of the query?)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     float p8[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) p8[t] = __uint_as_float(v[8 * u + t]) * rl;
-                    *reinterpret_cast<uint4*>(Pb + (size_t)(kt * (BM / 8) + cb * 4 + u) * p.Lp * 16) =
+                    *reinterpret_cast<uint4*>(Pb + (size_t)(kt * (BK / 8) + g * 8 + cb * 4 + u) * p.Lp * 16) =
                         make_uint4(h2u(p8[0], p8[1]), h2u(p8[2], p8[3]), h2u(p8[4], p8[5]), h2u(p8[6], p8[7]));
+                    if (band) {
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const int rel = rel0 + cb * 32 + 8 * u + t;
-                        if ((unsigned)rel < (unsigned)NR)
-                            *reinterpret_cast<__half*>(Pb + (size_t)(p.nchunk_tot - NRP / 8 + rel / 8) * p.Lp * 16 + (rel % 8) * 2) = __float2half_rn(p8[t]);
+                        for (int t = 0; t < 8; ++t) {
+                            const int rel = rel0 + cb * 32 + 8 * u + t;
+                            if ((unsigned)rel < (unsigned)NR)
+                                *reinterpret_cast<__half*>(Pb + (size_t)(p.nchunk_tot - NRP / 8 + rel / 8) * p.Lp * 16 + (rel % 8) * 2) = __float2half_rn(p8[t]);
+                        }
                     }
                 }
             }
@@ -291,7 +310,7 @@ RVC_API int rvc_attn_scores_cluster_tc(const rvc_attn_scores_desc* dp, void* str
     if (!dp) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: null descriptor");
     const rvc_attn_scores_desc& d = *dp;
     if (!d.qk || !d.ek || !d.qkv || !d.mask || !d.P || !d.vw) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: null pointer");
-    if (d.B <= 0 || d.T <= 0 || d.T > BM * MAXC || d.n_heads <= 0 || d.H != d.n_heads * DK)
+    if (d.B <= 0 || d.T <= 0 || d.T > BK * MAXC || d.n_heads <= 0 || d.H != d.n_heads * DK)
         return rvc::fail(RVC_ESHAPE, "rvc_attn_scores_cluster_tc: built for head dim 96 and T <= 1024 (got H = %d, heads = %d, T = %d)", d.H, d.n_heads, d.T);
     if (d.window < 0 || 2 * d.window + 1 > QE_LD) return rvc::fail(RVC_ESHAPE, "rvc_attn_scores_cluster_tc: window %d > 11", d.window);
     if (d.planes != 1 && d.planes != 2) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: planes must be 1 or 2");
@@ -300,7 +319,7 @@ RVC_API int rvc_attn_scores_cluster_tc(const rvc_attn_scores_desc* dp, void* str
     p.qk = (const uint8_t*)d.qk; p.qk_bs = d.qk_bs; p.q_chunk0 = d.q_chunk0; p.k_chunk0 = d.k_chunk0; p.head_chunks = NCHK; p.lo_chunks = d.planes == 2 ? d.lo_chunks : 0;
     p.ek = (const uint8_t*)d.ek; p.qkv = d.qkv; p.mask = d.mask; p.P = (uint8_t*)d.P; p.vw = (uint8_t*)d.vw;
     p.B = d.B; p.H = d.H; p.nh = d.n_heads; p.T = d.T; p.Lp = (int)rvc_packed_rows(d.T); p.W = d.window;
-    p.nkt = (d.T + BM - 1) / BM; p.nchunk_tot = p.nkt * (BM / 8) + NRP / 8; p.planes = d.planes;
+    p.nkt = (d.T + BK - 1) / BK; p.nqt = (d.T + BM - 1) / BM; p.nchunk_tot = p.nkt * (BK / 8) + NRP / 8; p.planes = d.planes;
     p.inv = 1.f / sqrtf((float)DK);
     auto kern = attn_scores_cluster_kernel;
     static bool opted[64] = {false};
@@ -312,7 +331,7 @@ RVC_API int rvc_attn_scores_cluster_tc(const rvc_attn_scores_desc* dp, void* str
         if (dev >= 0 && dev < 64) opted[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(d.B * d.n_heads * p.nkt * p.nkt));
+    cfg.gridDim = dim3((unsigned)(d.B * d.n_heads * p.nqt * p.nkt));
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = (cudaStream_t)stream;

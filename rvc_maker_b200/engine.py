@@ -549,6 +549,7 @@ class Engine:
                 Rb = self._buf(p, B, H, T)
                 vwb = self._buf(p, B * nh * (Tk // 8) * dk * 4, dtype=torch.int32)
             if attn_cl:
+                Tk = (T + 255) // 256 * 256                        # one 256-key tile per CTA of the cluster
                 nct = Tk // 8 + 4                                  # key chunks + the four "relative position" chunks of P / of the P.v weights
                 Pb = self._zbuf(p, B * nh * nct * Lp * 16)         # (band entries whose key falls outside the sequence stay zero)
                 vws = []
