@@ -39,11 +39,40 @@ class Plan:
         self.keep = []
         self.launches = 0
         self.last_stream = None   # torch stream of the last use (plan build included): a use on another stream waits for it first
+        self.side = None          # torch stream of the plan's side branch (ops added with side=True run there between fork and join)
+        self.side_ops = set()
 
-    def add(self, name, fn, *args, launches=1, flops=0.0, bytes_=0.0, kind="other"):
+    def add(self, name, fn, *args, launches=1, flops=0.0, bytes_=0.0, kind="other", side=False):
+        if side:
+            self.side_ops.add(len(self.ops))
         self.ops.append((name, fn, args))
         self.meta.append(dict(name=name, kind=kind, flops=float(flops), bytes=float(bytes_), launches=launches))
         self.launches += launches
+
+    def hoist_side(self, fork_at, join_at, side, dev):
+        """Move the ops added with side=True to position `fork_at` of the launch list, on the stream `side`: a fork (side waits for what the main
+        stream has issued so far) in front of them, a join (main waits for side) at the original position `join_at` of their first consumer.  Inside a
+        CUDA-graph capture the two waits become the fork / join edges of a parallel branch."""
+        if not self.side_ops or join_at is None or join_at <= fork_at:
+            self.side_ops = set()
+            return
+        items = list(zip(self.ops, self.meta))
+        moved = [items[i] for i in sorted(self.side_ops)]
+        fork = ((None, lambda: side.wait_stream(torch.cuda.current_stream(dev)), ()), None)
+        join = ((None, lambda: torch.cuda.current_stream(dev).wait_stream(side), ()), None)
+        out, flags = [], set()
+        for i in range(len(items) + 1):
+            if i == fork_at:
+                out.append(fork)
+                for it in moved:
+                    flags.add(len(out))
+                    out.append(it)
+            if i == join_at:
+                out.append(join)
+            if i < len(items) and i not in self.side_ops:
+                out.append(items[i])
+        self.ops, self.meta = [o for o, _ in out], [m for _, m in out]
+        self.side_ops, self.side = flags, side
 
     def add_py(self, fn):
         self.ops.append((None, fn, ()))
@@ -51,16 +80,17 @@ class Plan:
 
     def release(self):
         """Drop every buffer and launch record now (eviction from the engine's plan cache), without waiting for the garbage collector."""
-        self.ops, self.meta, self.keep = [], [], []
+        self.ops, self.meta, self.keep, self.side_ops = [], [], [], set()
         for k in [k for k, v in self.__dict__.items() if torch.is_tensor(v)]:
             delattr(self, k)
 
     def run(self, stream):
-        for name, fn, args in self.ops:
+        side = self.side.cuda_stream if self.side is not None else stream
+        for n, (name, fn, args) in enumerate(self.ops):
             if name is None:
                 fn()
             else:
-                rc = fn(*args, stream)
+                rc = fn(*args, side if n in self.side_ops else stream)
                 if rc != 0:
                     _lib.check(rc, name)
 
@@ -134,6 +164,10 @@ class Engine:
         self.use_flow_cluster = os.environ.get("RVC_B200_FLOW_CLUSTER", "1") != "0"
         # attention scores + softmax of a layer as one cluster kernel for T <= 1024 (rvc_attn_scores_cluster_tc) instead of S launch + softmax launch
         self.use_attn_cluster = os.environ.get("RVC_B200_ATTN_CLUSTER", "1") != "0"
+        # the NSF source (SineGen + the long noise convs: 70 us of CUDA-core work that depends on f0 only) on a side branch of the graph, next to the
+        # flow kernel, which occupies 78 of the 148 SMs for 130 us
+        self.use_side_branch = os.environ.get("RVC_B200_SIDE_BRANCH", "1") != "0"
+        self.side_stream = torch.cuda.Stream(self.dev)
         self._chain = None
 
     # ------------------------------------------------------------------ weight folding / packing
@@ -667,6 +701,8 @@ class Engine:
         if self.cond_table is None:   # (otherwise infer() gathers the rows of the per-speaker table straight into gc)
             p.add("cond", lib.rvc_cond_gemv_f32, p.g.data_ptr(), W["cond_w"].data_ptr(), W["cond_b"].data_ptr(), gc.data_ptr(), B, G, self.cond_total,
                   flops=2.0 * B * G * self.cond_total, bytes_=4.0 * G * self.cond_total, kind="cond_gemv_f32")
+        fork_at, join_at = len(p.ops), None      # side branch (NSF source): hoisted to here at the end of the build (Plan.hoist_side)
+        side = self.use_side_branch
         cluster = self.flow_tc and self.use_flow_cluster and (H, half) == (192, 96)     # (the flow's WaveNet is always 3 layers of k = 5, x 4 couplings)
         za = self._packed(p, B, I, T) if self.flow_tc else None       # masked packed z: conv_pre's operand
         if cluster:
@@ -745,7 +781,7 @@ class Engine:
             har = self._buf(p, B, Lfin)
             scratch = self._buf(p, B, T)
             p.add("sine_source", lib.rvc_sine_source_f32, p.f0.data_ptr(), p.eps_src.data_ptr(), W["lin_w"].data_ptr(), W["lin_b"].data_ptr(),
-                  scratch.data_ptr(), har.data_ptr(), B, T, upp, c["sr"], launches=2, bytes_=8.0 * B * Lfin, kind="sine_source_f32")
+                  scratch.data_ptr(), har.data_ptr(), B, T, upp, c["sr"], launches=2, bytes_=8.0 * B * Lfin, kind="sine_source_f32", side=side)
         xpre = self._buf(p, B, U, T)
         xpre_a = None
         if self.flow_tc:
@@ -801,10 +837,18 @@ class Engine:
                 # their own followed by an fp32 round trip (rvc_tc_job.nz_*); the long ones keep their kernel (tried in round 2: the 8-tap
                 # conv of stage 1 inside the issue-bound ups epilogue cost 55 us against 29 us saved)
                 nz_fused = bool(c["f0"]) and blk and kn <= 4
+                nzv = vs0                       # where the (unfused) noise conv leaves its result = the residual input of this stage's ups
                 if c["f0"] and not nz_fused:
+                    if side:
+                        # on the side branch the conv runs long before its stage: the first one may use S[0] (nothing touches it before ups0), later ones
+                        # need a buffer of their own
+                        if join_at is None:
+                            join_at = len(p.ops)
+                        else:
+                            nzv = V(self._buf(p, B * Ci * Li), Ci, Li, cs=(8 * Li if blk else None))
                     p.add(f"noise{i}", lib.rvc_noise_conv_f32, har.data_ptr(), Lfin, W[f"nz_w{i}"].data_ptr(), W[f"nz_b{i}"].data_ptr(),
-                          S[0].data_ptr(), Ci * Li, B, Ci, Li, kn, sn, pn, int(blk), flops=2.0 * B * Ci * Li * kn, bytes_=4.0 * B * (Ci * Li + Li * sn),
-                          kind="noise_conv_f32")
+                          nzv.ptr, Ci * Li, B, Ci, Li, kn, sn, pn, int(blk), flops=2.0 * B * Ci * Li * kn, bytes_=4.0 * B * (Ci * Li + Li * sn),
+                          kind="noise_conv_f32", side=side)
                 if dt is not None and dt == udt:
                     xa = self._packed(p, B, Ci, Li)
                 # narrow fused stages: the stage input leaves the ups as the split-fp16 stream (xa = hi, x_lo), no fp32 copy
@@ -813,7 +857,7 @@ class Engine:
                 M = -(-k // u)
                 nz = dict(nz_har=har.data_ptr(), nz_w=W[f"nz_w{i}"].data_ptr(), nz_b=W[f"nz_b{i}"].data_ptr(), nz_har_bs=Lfin, nz_kn=kn, nz_sn=sn,
                           nz_pn=pn) if nz_fused else {}
-                self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(vs0 if c["f0"] and not nz_fused else None),
+                self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(nzv if c["f0"] and not nz_fused else None),
                                              y=(None if split else vs0), y_act=xa, y_lo=x_lo, act_slope=LRELU_SLOPE, K=M, pad=M - 1, **nz)],
                          B=B, Cin=curC, Cout=Ci, L=curL, dtype=udt, up=u, pshift=(k - u) // 2, tag=f"ups",
                          flops=2.0 * B * curC * Ci * k * curL, blocked=3 if blk else 0)
@@ -970,6 +1014,7 @@ class Engine:
         p.add("conv_post", lib.rvc_conv_post_f32, cur[0].data_ptr(), x2, x3, float(nk), curC * curL, curL, W["post_w"].data_ptr(), p.o.data_ptr(),
               Lfin, B, curC, curL, 0.01, flops=2.0 * B * curC * 7 * curL, bytes_=4.0 * B * (curC * (3 if x2 else 1) + 1) * curL,
               kind="conv_post_f32")
+        p.hoist_side(fork_at, join_at, self.side_stream, self.dev)
         return p
 
     def plan(self, kind, B, T):
