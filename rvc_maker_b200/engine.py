@@ -165,8 +165,10 @@ class Engine:
         # attention scores + softmax of a layer as one cluster kernel for T <= 1024 (rvc_attn_scores_cluster_tc) instead of S launch + softmax launch
         self.use_attn_cluster = os.environ.get("RVC_B200_ATTN_CLUSTER", "1") != "0"
         # the NSF source (SineGen + the long noise convs: 70 us of CUDA-core work that depends on f0 only) on a side branch of the graph, next to the
-        # flow kernel, which occupies 78 of the 148 SMs for 130 us
-        self.use_side_branch = os.environ.get("RVC_B200_SIDE_BRANCH", "1") != "0"
+        # flow kernel, which occupies 78 of the 148 SMs for 130 us.  OFF by default: measured 2.365 ms per step against 2.345 without it (round 2v; the
+        # same experiment next to the per-launch flow in round 1: 2.58 vs 2.57) — the branch's CTAs delay the placement of the flow's clusters and the
+        # fork / join edges take the programmatic-dependent-launch overlap away from the kernels around them.
+        self.use_side_branch = os.environ.get("RVC_B200_SIDE_BRANCH", "0") != "0"
         self.side_stream = torch.cuda.Stream(self.dev)
         self._chain = None
 
