@@ -342,6 +342,25 @@ typedef struct {
 int rvc_attn_scores_cluster_tc(const rvc_attn_scores_desc* d, void* stream);
 
 /*
+ * The position-local tail of an encoder layer as one cluster kernel (Encoder.forward, synthesizers.py:344-347; LayerNorm :179-181; FFN :302-315), for
+ * hidden 192 / filter 768 / kernel 3:   x1 = LN1(x + conv_o(att));   y = LN2(x1 + conv_2(relu(conv_1(x1 * mask)) * mask) * mask).
+ * att: the packed [hi | lo] attention output ([b][2 * 24][rows][8], what the P.v GEMM wrote); x / y: the fp32 residual stream [B, 192, T] (may alias);
+ * ya: y * mask as packed [hi | lo] planes for the next layer's qkv projection / proj; wo_hi / wo_lo: conv_o as two packed planes, w1 / w2 packed fp16
+ * (rvc_pack_weight), fp32 biases and LayerNorm parameters; out_mask: y itself is masked too (the last layer, :348).  Replaces five launches
+ * (rvc_conv1d_tc x 3, rvc_layernorm_f32 x 2) — see csrc/encoder_tail_cluster_tc.cu.
+ */
+typedef struct {
+    const void* att; int64_t att_bs;
+    const float* x; float* y; void* ya; int64_t ya_bs; const float* mask;
+    const void* wo_hi; const void* wo_lo; const float* bo;
+    const void* w1; const float* b1; const void* w2; const float* b2;
+    const float* gamma1; const float* beta1; const float* gamma2; const float* beta2;
+    int32_t B, T, hidden, filter, kernel_size, out_mask;
+    float eps; int32_t reserved;
+} rvc_encoder_tail_desc;
+int rvc_encoder_tail_tc(const rvc_encoder_tail_desc* d, void* stream);
+
+/*
  * Caller side of the path: the feature preparation VC.voice_conversion performs between the embedder and
  * Synthesizer.infer (main/inference/convert.py:361-378).
  *   out[b,t,:] = feats[b,t/2,:]                                    (feats0 == NULL: F.interpolate(scale_factor=2), :361)

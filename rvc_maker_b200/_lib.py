@@ -96,6 +96,14 @@ class AttnScoresDesc(C.Structure):
                 ("B", _i32), ("H", _i32), ("n_heads", _i32), ("T", _i32), ("window", _i32), ("reserved", _i32)]
 
 
+class EncoderTailDesc(C.Structure):
+    """rvc_encoder_tail_desc."""
+    _fields_ = [("att", _vp), ("att_bs", _i64), ("x", _vp), ("y", _vp), ("ya", _vp), ("ya_bs", _i64), ("mask", _vp),
+                ("wo_hi", _vp), ("wo_lo", _vp), ("bo", _vp), ("w1", _vp), ("b1", _vp), ("w2", _vp), ("b2", _vp),
+                ("gamma1", _vp), ("beta1", _vp), ("gamma2", _vp), ("beta2", _vp),
+                ("B", _i32), ("T", _i32), ("hidden", _i32), ("filter", _i32), ("kernel_size", _i32), ("out_mask", _i32), ("eps", _f32), ("reserved", _i32)]
+
+
 class ResblockPairDesc(C.Structure):
     """rvc_resblock_pair_desc."""
     _fields_ = [("jobs", PairJob * 3), ("njobs", _i32), ("B", _i32), ("C", _i32), ("L", _i32), ("dtype", _i32), ("slope", _f32),
@@ -128,6 +136,7 @@ SIGNATURES = {
     "rvc_conv1d_tc": (C.c_int, [C.POINTER(Conv1dTcDesc), _vp]),
     "rvc_flow_reverse_tc": (C.c_int, [C.POINTER(FlowDesc), _vp]),
     "rvc_attn_scores_cluster_tc": (C.c_int, [C.POINTER(AttnScoresDesc), _vp]),
+    "rvc_encoder_tail_tc": (C.c_int, [C.POINTER(EncoderTailDesc), _vp]),
     "rvc_conv1d_tc_chain_blob_bytes": (C.c_int64, [_i32]),
     "rvc_conv1d_tc_chain_build": (C.c_int, [C.POINTER(Conv1dTcDesc), C.POINTER(_i32), _i32, _vp, _i64]),
     "rvc_conv1d_tc_chain_run": (C.c_int, [_vp, _vp, _vp, _vp]),

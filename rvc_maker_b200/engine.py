@@ -14,7 +14,7 @@ import threading
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, AttnScoresDesc, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc, FlowDesc, ResblockPairDesc
+from ._lib import ACT_NONE, ACT_RELU, DT_BF16, DT_FP16, AttnScoresDesc, Conv1dDesc, Conv1dTcDesc, ConvTr1dDesc, EncoderTailDesc, FlowDesc, ResblockPairDesc
 
 LRELU_SLOPE = 0.1
 WINDOW = 10
@@ -164,6 +164,8 @@ class Engine:
         self.use_flow_cluster = os.environ.get("RVC_B200_FLOW_CLUSTER", "1") != "0"
         # attention scores + softmax of a layer as one cluster kernel for T <= 1024 (rvc_attn_scores_cluster_tc) instead of S launch + softmax launch
         self.use_attn_cluster = os.environ.get("RVC_B200_ATTN_CLUSTER", "1") != "0"
+        # conv_o -> LayerNorm -> FFN -> LayerNorm of an encoder layer as one cluster kernel (rvc_encoder_tail_tc) instead of five launches
+        self.use_enc_tail = os.environ.get("RVC_B200_ENC_TAIL", "1") != "0"
         # the NSF source (SineGen + the long noise convs: 70 us of CUDA-core work that depends on f0 only) on a side branch of the graph, next to the
         # flow kernel, which occupies 78 of the 148 SMs for 130 us.  OFF by default: measured 2.365 ms per step against 2.345 without it (round 2v; the
         # same experiment next to the per-launch flow in round 1: 2.58 vs 2.57) — the branch's CTAs delay the placement of the flow's clusters and the
@@ -575,6 +577,8 @@ class Engine:
                 p.add("pack_x", lib.rvc_pack_act, x.data_ptr(), None, None, 1.0, H * T, T, None, xa.data_ptr(), B, H, T, dt, 1.0, kind="pack_act",
                       bytes_=6.0 * B * H * T)
             attn_cl = tc_attn and self.use_attn_cluster and dk == 96 and T <= 1024 and "t_ek_p0" in W
+            enc_tail = split and self.use_enc_tail and (H, Fc, ks) == (192, 768, 3)
+            xcur, xnxt = x, y        # (with the tail kernel the residual stream alternates between the two fp32 buffers)
             if tc_attn:
                 Tk = (T + 127) // 128 * 128
                 qkva = pk(3 * H)
@@ -637,6 +641,21 @@ class Engine:
                           att.data_ptr(), B, H, nh, T, WINDOW, flops=4.0 * B * H * T * T, bytes_=16.0 * B * H * T, kind="rel_attention_f32")
                     p.add(f"pack_att{i}", lib.rvc_pack_act, att.data_ptr(), None, None, 1.0, H * T, T, None, atta.data_ptr(), B, H, T, dt, 1.0,
                           kind="pack_act", bytes_=6.0 * B * H * T)
+                if enc_tail:
+                    # the rest of the layer in one cluster kernel: x (fp32, ping-pong between two buffers: neighbouring tiles read each other's halo rows) -> x'
+                    td = EncoderTailDesc()
+                    td.att, td.att_bs, td.x, td.y = atta.data_ptr(), npl * (H // 8) * cb, xcur.data_ptr(), xnxt.data_ptr()
+                    td.ya, td.ya_bs, td.mask = xa.data_ptr(), npl * (H // 8) * cb, p.mask.data_ptr()
+                    td.wo_hi, td.wo_lo, td.bo = W[f"t_o_w{i}"].data_ptr(), W[f"t_o_w{i}_lo"].data_ptr(), W[f"o_b{i}"].data_ptr()
+                    td.w1, td.b1, td.w2, td.b2 = W[f"t_f1_w{i}"].data_ptr(), W[f"f1_b{i}"].data_ptr(), W[f"t_f2_w{i}"].data_ptr(), W[f"f2_b{i}"].data_ptr()
+                    td.gamma1, td.beta1, td.gamma2, td.beta2 = (W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(), W[f"ln2_g{i}"].data_ptr(),
+                                                                W[f"ln2_b{i}"].data_ptr())
+                    td.B, td.T, td.hidden, td.filter, td.kernel_size, td.out_mask, td.eps = B, T, H, Fc, ks, int(i == c["nl"] - 1), 1e-5
+                    p.keep.append(td)
+                    p.add(f"enc_tail{i}", lib.rvc_encoder_tail_tc, C.byref(td), flops=2.0 * B * T * (H * H + 2 * ks * H * Fc), bytes_=B * H * T * (4.0 + 4.0 + 4.0 + 4.0),
+                          kind="encoder_tail_tc")
+                    xcur, xnxt = xnxt, xcur
+                    continue
                 gemm(f"attn_o{i}", atta, H, f"t_o_w{i}", H, dict(bias=W[f"o_b{i}"], y=vy))
                 p.add(f"ln1_{i}", lib.rvc_layernorm_f32, x.data_ptr(), y.data_ptr(), None, None, W[f"ln1_g{i}"].data_ptr(), W[f"ln1_b{i}"].data_ptr(),
                       p.mask.data_ptr(), x.data_ptr(), B, H, T, 1e-5, 0, xa.data_ptr(), adt, kind="layernorm_f32", bytes_=(12.0 + 2.0 * npl) * B * H * T)

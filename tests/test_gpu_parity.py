@@ -365,3 +365,31 @@ def test_attention_cluster_kernel_matches_per_launch_path(B, T, monkeypatch):
     assert float((out["o"] - ref["o"]).abs().max()) <= 6e-4
     again = run_net(net, inp)
     assert torch.equal(again["m_p"], out["m_p"]) and torch.equal(again["o"], out["o"])
+
+
+@pytest.mark.parametrize("B,T", [(1, 1000), (2, 173), (3, 124), (2, 125), (1, 1), (2, 1300), (40, 64)])
+def test_encoder_tail_cluster_kernel_matches_per_launch_path(B, T, monkeypatch):
+    """rvc_encoder_tail_tc (conv_o -> LayerNorm -> conv_1 -> relu -> conv_2 -> LayerNorm of a layer in one cluster kernel: LayerNorm statistics and the
+    K-split conv_2 partial sums through distributed shared memory) against the five launches it replaces, on the same model: same fp16 operand rounding
+    points, different fp32 summation orders.  Tile seams at multiples of 124 frames, ragged lengths, T = 1, T > 1024 (per-launch attention path)."""
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=78, heated=True)
+    inp = cases.synth_inputs(cfg, B, T, seed=5 * B + T, ragged=B > 1)
+    monkeypatch.setenv("RVC_B200_ENC_TAIL", "0")
+    ref_net = build_net(cfg, sd, True, precision="tc")
+    ref = run_net(ref_net, inp)
+    assert not any(m and m["name"] == "enc_tail0" for m in ref_net._engine.plan("enc", B, T).meta)
+    monkeypatch.setenv("RVC_B200_ENC_TAIL", "1")
+    net = build_net(cfg, sd, True, precision="tc")
+    out = run_net(net, inp)
+    assert any(m and m["name"] == "enc_tail0" for m in net._engine.plan("enc", B, T).meta)
+    for k in ("m_p", "logs_p", "z"):
+        assert torch.isfinite(out[k]).all(), k
+        scale = float(ref[k].abs().max())
+        err = float((out[k] - ref[k]).abs().max())
+        print(f"[enc tail B={B} T={T}] {k}: err {err:.2e} (max|ref| {scale:.2f})")
+        assert err <= 2e-3 * max(1.0, scale), (k, err, scale)
+    assert torch.equal(out["x_mask"], ref["x_mask"])
+    assert float((out["o"] - ref["o"]).abs().max()) <= 6e-4
+    again = run_net(net, inp)
+    assert torch.equal(again["m_p"], out["m_p"]) and torch.equal(again["o"], out["o"])
