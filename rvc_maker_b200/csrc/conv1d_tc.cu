@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 const int c0 = cs * p.ach;
                 const int nc = min(p.ach, p.nch - c0);
                 if (lane == 0) {
-                    tc::mbar_wait(A_EMPTY(ast), aph ^ 1);
+                    tc::mbar_wait_relaxed(A_EMPTY(ast), aph ^ 1);
                     if (p.dbg & 4) tc::mbar_arrive(A_FULL(ast));
                     else tc::mbar_arrive_expect_tx(A_FULL(ast), (uint32_t)nc * rows * 16);
                 }
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 for (int f0 = 0; f0 < nflat; f0 += SCH) {
                     const int nu = min(SCH, nflat - f0);
                     if (lane == 0) {
-                        tc::mbar_wait(W_EMPTY(wst), wph ^ 1);
+                        tc::mbar_wait_relaxed(W_EMPTY(wst), wph ^ 1);
                         if (p.dbg & 4) tc::mbar_arrive(W_FULL(wst));
                         else tc::mbar_arrive_expect_tx(W_FULL(wst), (uint32_t)nu * NT * 16);
                     }

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
             int rows = TMR + (jb.K1 - 1) * jb.dil1;
             rows = min(rows, p.Lp - row0);                                           // the last tile must not read past the buffer
             if (lane == 0) {
-                tc::mbar_wait(A_EMPTY(ast), aph ^ 1);
+                tc::mbar_wait_relaxed(A_EMPTY(ast), aph ^ 1);
                 tc::mbar_arrive_expect_tx(A_FULL(ast), (uint32_t)NCH * rows * 16);
             }
             __syncwarp();
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
             for (int f0 = 0; f0 < nflat; f0 += SCH) {
                 const int nu = min(SCH, nflat - f0);
                 if (lane == 0) {
-                    tc::mbar_wait(W_EMPTY(wst), wph ^ 1);
+                    tc::mbar_wait_relaxed(W_EMPTY(wst), wph ^ 1);
                     tc::mbar_arrive_expect_tx(W_FULL(wst), (uint32_t)nu * C * 16);
                     tc::bulk_g2s(tc::smem_u32(w_smem + wst * STAGE_BYTES), reinterpret_cast<const uint8_t*>(w) + (size_t)f0 * C * 16, (uint32_t)nu * C * 16,
                                  W_FULL(wst));

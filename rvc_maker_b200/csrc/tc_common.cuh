@@ -42,6 +42,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Producer-side wait ("slot free"): the waiter is never on the critical path by more than the hint, so it lets the hardware suspend the warp for up
+// to `ns` nanoseconds per probe instead of re-issuing the probe — the producers' polling took a quarter of the issued instructions of the fused
+// ResBlock kernel (ncu, profiles/r2f_ncu_full_pair_kernels.csv), on schedulers they share with three epilogue warps each.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns = 1000) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(ns)
+            : "memory");
+}
 
 // ---------------------------------------------------------------- bulk async copy global -> shared (UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
