@@ -308,6 +308,11 @@ typedef struct {
 } rvc_resblock_pair_desc;
 int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* d, void* stream);
 
+/* Debug aid (tools/pair_trace.py; only in the -DRVC_PAIR_TRACE build, RVC_EINVAL otherwise): registers a device buffer of `capacity` 64-bit slots that
+ * CTA 0 of rvc_resblock_pair_tc fills with the SM clock of the hand-offs between its producer / MMA / epilogue warps (slot 30 * unit + 6 * role + k);
+ * NULL switches it off. */
+int rvc_debug_pair_trace(void* dev_buf, int32_t capacity);
+
 /*
  * Softmax stage of the tensor-core attention (MultiHeadAttention.attention, synthesizers.py:221-250).  The contractions run
  * through rvc_conv1d_tc: S[b][h][j/8][i][j%8] = q_i . k_j (fp32, channel-blocked over the keys — f32_blocked output of the

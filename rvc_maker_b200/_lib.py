@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librvc_b200.so")
+# RVC_B200_LIB: debugging builds of the same library only (tools/pair_trace.py -> librvc_b200_trace.so); never a fallback
+LIB_PATH = os.environ.get("RVC_B200_LIB") or os.path.join(HERE, "librvc_b200.so")
 ABI_VERSION = 22
 DT_BF16, DT_FP16, DT_FP16_SPLIT = 0, 2, 3
 
@@ -130,6 +131,7 @@ SIGNATURES = {
     "rvc_feature_prep_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_absmax_f32": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp]),
     "rvc_resblock_pair_tc": (C.c_int, [C.POINTER(ResblockPairDesc), _vp]),
+    "rvc_debug_pair_trace": (C.c_int, [_vp, _i32]),
     "rvc_packed_rows": (_i64, [_i32]),
     "rvc_pack_act": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -41,19 +41,25 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
-        return LIB
+def build(force=False, verbose=False, trace=False):
+    """trace=True builds the debugging twin ``librvc_b200_trace.so`` (-DRVC_PAIR_TRACE: timeline records in the fused ResBlock kernel,
+    tools/pair_trace.py selects it through RVC_B200_LIB); the product library never carries the trace points."""
+    if trace:
+        lib, stamp, extra, tmpname = os.path.join(HERE, "librvc_b200_trace.so"), os.path.join(HERE, "librvc_b200_trace.so.stamp"), ["-DRVC_PAIR_TRACE"], "build_trace"
+    else:
+        lib, stamp, extra, tmpname = LIB, STAMP, [], "build"
+    dig = _digest() + ("+trace" if trace else "")
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return lib
     objs = []
     nvcc = _nvcc()
-    tmp = os.path.join(HERE, "build")
+    tmp = os.path.join(HERE, tmpname)
     os.makedirs(tmp, exist_ok=True)
     procs = []
     for src in _sources():
         obj = os.path.join(tmp, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-               "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v", "-c", src, "-o", obj]
+               "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"] + extra + ["-c", src, "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, obj, p in procs:
@@ -63,7 +69,7 @@ def build(force=False, verbose=False):
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    link = [nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcuda"]
+    link = [nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lcuda"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log.append(r.stdout)
     if r.returncode != 0:
@@ -71,12 +77,12 @@ def build(force=False, verbose=False):
         raise RuntimeError("link failed")
     with open(os.path.join(tmp, "ptxas.log"), "w") as fh:
         fh.write("\n".join(log))
-    with open(STAMP, "w") as fh:
+    with open(stamp, "w") as fh:
         fh.write(dig)
     if verbose:
         print("\n".join(log))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

@@ -49,6 +49,27 @@ struct PParams {
     float slope, alpha, inv_slope;
 };
 
+// Debug timeline (tools/pair_trace.py), compiled in only with -DRVC_PAIR_TRACE (python -m rvc_maker_b200.build --trace): when a buffer is
+// registered (rvc_debug_pair_trace), CTA 0 appends (event id, unit, SM clock) records — one lane per role — so that the producer / MMA /
+// epilogue hand-offs of the fused step can be laid out on one time axis.  The product build compiles trace() to nothing.
+#ifdef RVC_PAIR_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+// no atomics and no global reads per record (either costs a memory round trip and distorts what is measured): the kernel reads the buffer pointer
+// once, record (ev, unit) has its own slot 50 * unit + 10 * role + k  (role 0 producer [ev 1], 1 MMA warp [ev 2..7], 2 + eg epilogue group
+// [ev 10 + 3k + eg]); the store is fire-and-forget
+#define TRACE_SETUP unsigned long long* const tr_buf = blockIdx.x == 0 ? g_trace : nullptr; const unsigned int tr_cap = g_trace_cap;
+#define trace(ev, unit) do { if (tr_buf) { const int ev_ = (ev); const int role_ = ev_ == 1 ? 0 : ev_ < 10 ? 1 : 2 + (ev_ - 10) % 3; \
+    const int k_ = ev_ == 1 ? 0 : ev_ < 10 ? ev_ - 2 : (ev_ - 10) / 3; const unsigned int i_ = 50u * (unsigned)(unit) + 10u * role_ + k_; \
+    if (i_ < tr_cap) tr_buf[i_] = (unsigned long long)clock64(); } } while (0)
+// a record that is taken only once register `x` has arrived (a branch on its value makes the warp wait for the load / tcgen05.ld behind it)
+#define trace_after(ev, unit, x) do { if (tr_buf) { if (__float_as_uint(x) == 0x7fc12345u) tr_buf[0] = 0; trace(ev, unit); } } while (0)
+#else
+#define TRACE_SETUP
+#define trace(ev, unit) do {} while (0)
+#define trace_after(ev, unit, x) do {} while (0)
+#endif
+
 __device__ __forceinline__ uint32_t pack2h(float a, float b, int fp16) {
     uint32_t r;
     if (fp16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
@@ -104,6 +125,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+    TRACE_SETUP
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { tc::mbar_init(W_FULL(s), 1); tc::mbar_init(W_EMPTY(s), 2); }
@@ -179,6 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
             rows = min(rows, p.Lp - row0);                                           // the last tile must not read past the buffer
             if (lane == 0) {
                 tc::mbar_wait_relaxed(A_EMPTY(ast), aph ^ 1);
+                trace(1, n);
                 tc::mbar_arrive_expect_tx(A_FULL(ast), (uint32_t)NCH * rows * 16);
             }
             __syncwarp();
@@ -256,11 +279,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 const int g = n & 1;
                 const uint32_t gph = (n >> 1) & 1;
                 tc::mbar_wait(ACC1_EMPTY(g), gph ^ 1);
+                if (m == 0 && lane == 0) trace(2, n);
                 tc::mbar_wait(A_FULL(g), gph);
+                if (m == 0 && lane == 0) trace(3, n);
                 tc::fence_after_sync();
                 run_phase(tmem_base + (uint32_t)((g * MT + m) * C), tc::smem_u32(a_smem + (size_t)g * a_bytes) >> 4, (uint32_t)p.ra, p.jobs[j].K1,
                           (uint32_t)p.jobs[j].dil1, 0u);
                 if (tc::elect_one()) { tc::umma_commit(A_EMPTY(g)); tc::umma_commit(ACC1_FULL(g)); }
+                if (m == 0 && lane == 0) trace(4, n);
                 __syncwarp();
             }
             if (n > 0) {         // ---- phase 2 of unit n - 1 (accumulates over the jobs of a tile with sum_jobs)
@@ -269,7 +295,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 const uint32_t gph = ((n - 1) >> 1) & 1;
                 const int g2 = it & 1;
                 if (jj == 0) tc::mbar_wait(ACC2_EMPTY(g2), ((it >> 1) & 1) ^ 1);
+                if (m == 0 && lane == 0) trace(5, n - 1);
                 tc::mbar_wait(T_FULL(g), gph);
+                if (m == 0 && lane == 0) trace(6, n - 1);
                 tc::fence_after_sync();
                 run_phase(tmem_base + (uint32_t)(2 * MT * C + (g2 * MT + m) * C), tc::smem_u32(t_smem + (size_t)g * t_bytes) >> 4, (uint32_t)RT, p.jobs[j].K2, 1u,
                           jj ? 1u : 0u);
@@ -277,6 +305,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                     tc::umma_commit(T_EMPTY(g));
                     if (jj == J - 1) tc::umma_commit(ACC2_FULL(g2));
                 }
+                if (m == 0 && lane == 0) trace(7, n - 1);
                 __syncwarp();
             }
         }
@@ -294,6 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
         const int first2 = eg + NEG * ((NITEM - eg + NEG - 1) / NEG);    // this warpgroup's first epilogue-2 item index (>= NITEM)
         float vn[EB];
         for (int n = 0; n <= n_units; ++n) {
+            if (q == 0 && lane == 0) trace(28 + eg, n);
             const bool has1 = n < n_units;
             int it1 = 0, jj1 = 0, j1 = 0, b1 = 0, lt1 = 0, it2 = 0, jj2 = 0, j2 = 0, b2 = 0, lt2 = 0;
             if (has1) unit(n, it1, jj1, j1, b1, lt1);
@@ -371,8 +401,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 const int g = n & 1;
                 const uint32_t gph = (n >> 1) & 1;
                 const int l0 = lt1 * p.tmo[j1] - (jb.K2 - 1) / 2;        // position of t row 0
+                if (q == 0 && lane == 0) trace(10 + eg, n);
                 tc::mbar_wait(ACC1_FULL(g), gph);
+                if (q == 0 && lane == 0) trace(13 + eg, n);
                 tc::mbar_wait(T_EMPTY(g), gph ^ 1);
+                if (q == 0 && lane == 0) trace(16 + eg, n);
                 tc::fence_after_sync();
                 uint8_t* tb = t_smem + (size_t)g * t_bytes;
 #pragma unroll 1
@@ -401,12 +434,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 tc::fence_proxy_async();          // the t tile is read by the tensor core through the async proxy
                 __syncwarp();
                 if (lane == 0) { tc::mbar_arrive(T_FULL(g)); tc::mbar_arrive(ACC1_EMPTY(g)); }
+                if (q == 0 && lane == 0) trace(19 + eg, n);
             }
             if (has2) {
                 // ---- epilogue 2 of tile it2: x' = alpha * (acc2 + b2 + x)  ->  fp32 and packed lrelu(x')
                 const int g = it2 & 1;
                 const uint32_t gph = (it2 >> 1) & 1;
                 tc::mbar_wait(ACC2_FULL(g), gph);
+                if (q == 0 && lane == 0) trace(22 + eg, n - 1);
                 tc::fence_after_sync();
 #pragma unroll 1
                 for (int k = first2; k < 2 * NITEM; k += NEG) {
@@ -418,10 +453,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                     float v[EB];
 #pragma unroll
                     for (int i = 0; i < EB; ++i) v[i] = vn[i];
+                    if (k == first2 && q == 0 && lane == 0) trace_after(31 + eg, n - 1, v[EB - 1] + v[EB - 5]);      // hi and lo words of the last chunk
                     if (k + NEG < 2 * NITEM) res_load(k + NEG, vn);
                     uint32_t r[EB];
                     tc::tmem_ld<EB>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * MT * C + (g * MT + m) * C + cb * EB), r);
                     tc::tmem_ld_wait();
+                    if (k == first2 && q == 0 && lane == 0) trace_after(34 + eg, n - 1, __uint_as_float(r[EB - 1]));
                     if (!ok) continue;
                     if (p.split_in && !p.sum_jobs) {   // raw hi / lo words -> x = inv_lrelu(hi + lo)
                         const float inv = p.inv_slope;
@@ -492,10 +529,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                             *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp * 16) = pk;
                         }
                     }
+                    if (k == first2 && q == 0 && lane == 0) trace(37 + eg, n - 1);
                 }
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(ACC2_EMPTY(g));
+                if (q == 0 && lane == 0) trace(25 + eg, n - 1);
             }
         }
     }
@@ -610,4 +649,19 @@ RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream)
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     if (d.C == 64) return launch_pair<64, 2>(p, smem, grid, (cudaStream_t)stream);
     return launch_pair<32, 4>(p, smem, grid, (cudaStream_t)stream);
+}
+
+// Debug only (tools/pair_trace.py): register a device buffer of `capacity` 64-bit records for the timeline of CTA 0 (NULL / 0 switches it off);
+// slot 30 * unit + 6 * role + k holds the SM clock of that event (0 = not reached).  Returns 0, or RVC_EINVAL when the library was built without -DRVC_PAIR_TRACE.
+RVC_API int rvc_debug_pair_trace(void* dev_buf, int32_t capacity) {
+#ifdef RVC_PAIR_TRACE
+    unsigned int cap = dev_buf ? (unsigned int)capacity : 0u;
+    unsigned long long* ptr = (unsigned long long*)dev_buf;
+    cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap));
+    cudaMemcpyToSymbol(g_trace, &ptr, sizeof(ptr));
+    return 0;
+#else
+    (void)dev_buf; (void)capacity;
+    return rvc::fail(RVC_EINVAL, "rvc_debug_pair_trace: this build has no trace points (python -m rvc_maker_b200.build --trace)");
+#endif
 }
