@@ -309,7 +309,7 @@ typedef struct {
 int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* d, void* stream);
 
 /* Debug aid (tools/pair_trace.py; only in the -DRVC_PAIR_TRACE build, RVC_EINVAL otherwise): registers a device buffer of `capacity` 64-bit slots that
- * CTA 0 of rvc_resblock_pair_tc fills with the SM clock of the hand-offs between its producer / MMA / epilogue warps (slot 30 * unit + 6 * role + k);
+ * CTA 0 of rvc_resblock_pair_tc fills with the SM clock of the hand-offs between its producer / MMA / epilogue warps (slot 80 * unit + 16 * role + k);
  * NULL switches it off. */
 int rvc_debug_pair_trace(void* dev_buf, int32_t capacity);
 

@@ -41,14 +41,19 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False, trace=False):
+def build(force=False, verbose=False, trace=False, defines=(), suffix=""):
     """trace=True builds the debugging twin ``librvc_b200_trace.so`` (-DRVC_PAIR_TRACE: timeline records in the fused ResBlock kernel,
     tools/pair_trace.py selects it through RVC_B200_LIB); the product library never carries the trace points."""
-    if trace:
-        lib, stamp, extra, tmpname = os.path.join(HERE, "librvc_b200_trace.so"), os.path.join(HERE, "librvc_b200_trace.so.stamp"), ["-DRVC_PAIR_TRACE"], "build_trace"
+    if trace or suffix:
+        # experiment builds (tools/ only): extra -D switches, a library name of their own
+        name = "librvc_b200" + ("_trace" if trace else "") + (f"_{suffix}" if suffix else "") + ".so"
+        lib, stamp, tmpname = os.path.join(HERE, name), os.path.join(HERE, name + ".stamp"), "build" + ("_trace" if trace else "") + (f"_{suffix}" if suffix else "")
+        extra = (["-DRVC_PAIR_TRACE"] if trace else []) + [f"-D{d}" for d in defines]
     else:
+        if defines:
+            raise ValueError("the product library takes no extra defines; give the experiment build a suffix")
         lib, stamp, extra, tmpname = LIB, STAMP, [], "build"
-    dig = _digest() + ("+trace" if trace else "")
+    dig = _digest() + "+" + " ".join(extra)
     if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return lib
     objs = []
@@ -85,4 +90,6 @@ def build(force=False, verbose=False, trace=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))
+    _defs = [sys.argv[i + 1] for i, a in enumerate(sys.argv[:-1]) if a == "--define"]
+    _suf = sys.argv[sys.argv.index("--suffix") + 1] if "--suffix" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv, defines=_defs, suffix=_suf))

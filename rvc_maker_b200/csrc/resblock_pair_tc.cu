@@ -56,11 +56,11 @@ struct PParams {
 __device__ unsigned long long* g_trace = nullptr;
 __device__ unsigned int g_trace_cap = 0;
 // no atomics and no global reads per record (either costs a memory round trip and distorts what is measured): the kernel reads the buffer pointer
-// once, record (ev, unit) has its own slot 50 * unit + 10 * role + k  (role 0 producer [ev 1], 1 MMA warp [ev 2..7], 2 + eg epilogue group
+// once, record (ev, unit) has its own slot 80 * unit + 16 * role + k  (role 0 producer [ev 1], 1 MMA warp [ev 2..7], 2 + eg epilogue group
 // [ev 10 + 3k + eg]); the store is fire-and-forget
 #define TRACE_SETUP unsigned long long* const tr_buf = blockIdx.x == 0 ? g_trace : nullptr; const unsigned int tr_cap = g_trace_cap;
 #define trace(ev, unit) do { if (tr_buf) { const int ev_ = (ev); const int role_ = ev_ == 1 ? 0 : ev_ < 10 ? 1 : 2 + (ev_ - 10) % 3; \
-    const int k_ = ev_ == 1 ? 0 : ev_ < 10 ? ev_ - 2 : (ev_ - 10) / 3; const unsigned int i_ = 50u * (unsigned)(unit) + 10u * role_ + k_; \
+    const int k_ = ev_ == 1 ? 0 : ev_ < 10 ? ev_ - 2 : (ev_ - 10) / 3; const unsigned int i_ = 80u * (unsigned)(unit) + 16u * role_ + k_; \
     if (i_ < tr_cap) tr_buf[i_] = (unsigned long long)clock64(); } } while (0)
 // a record that is taken only once register `x` has arrived (a branch on its value makes the warp wait for the load / tcgen05.ld behind it)
 #define trace_after(ev, unit, x) do { if (tr_buf) { if (__float_as_uint(x) == 0x7fc12345u) tr_buf[0] = 0; trace(ev, unit); } } while (0)
@@ -80,16 +80,19 @@ __device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(
 // inverse of leaky_relu for 0 < slope <= 1 (inv = 1 / slope >= 1): y > 0 -> y, y < 0 -> y / slope
 __device__ __forceinline__ float lrelu_inv(float y, float inv) { return fminf(y, y * inv); }
 __device__ __forceinline__ float2 h2f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
-__device__ __forceinline__ uint4 ldg128(const void* p) {
-    uint4 v;
-    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
+using tc::ldg128;
 
 // MT = 128-row sub-tiles per tile: 2, or 4 for C = 32 where TMEM holds twice the rows and the per-tile handshakes (about 2.3 us
 // of barrier round trips per tile with no MMA and no stores at all) were the bound rather than HBM
-template <int C, int MT>
+// SUM / SPLIT (stage-average mode / split-fp16 residual stream) are template parameters: with the four modes behind run-time flags one kernel
+// was 75 KB of code whose hot path hopped between distant fragments (tools/pair_trace.py: the epilogue warps lost 1-2 us per unit at the loop head)
+template <int C, int MT, bool SUM, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParams p) {
+#ifdef RVC_PAIR_TRACE
+    const int dbg = dbg;                              // timing experiments exist in the trace build only
+#else
+    constexpr int dbg = 0;
+#endif
     constexpr int TMR = BM * MT;                        // rows per tile
     constexpr int RT = TMR + RTX;                       // rows of the t tile
     constexpr int MPI = MT / 2;                         // sub-tiles per issuer warp
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
             const int j = i / (2 * C), r = i - j * 2 * C;
             const float* src = r < C ? p.jobs[j].b1 : p.jobs[j].b2;
             float v = src ? src[r < C ? r : r - C] : 0.f;
-            if (p.sum_jobs && j == 0 && r >= C)       // the stage average adds every job's conv2 bias
+            if (SUM && j == 0 && r >= C)       // the stage average adds every job's conv2 bias
                 for (int jj = 1; jj < p.njobs; ++jj) v += p.jobs[jj].b2 ? p.jobs[jj].b2[r - C] : 0.f;
             bias_s[i] = v;
         }
@@ -162,12 +165,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
+    // tile -> (job, batch item, position tile).  Everything the decode needs sits in registers: the earlier version (a loop over p.tiles_before with
+    // indexed constant loads, called twice per unit by every role) cost the epilogue warps 0.45 us per unit (tools/pair_trace.py)
+    const int tb1 = p.tiles_before[1], tb2 = p.tiles_before[2];
+    const int nl0 = p.n_lt[0], nl1 = p.n_lt[1], nl2 = p.n_lt[2];
     auto decode = [&](int tile, int& j, int& b, int& lt) {
-        j = 0;
-        while (j + 1 < p.njobs && tile >= p.tiles_before[j + 1]) ++j;
-        const int r = tile - p.tiles_before[j];
+        j = (tile >= tb1 ? 1 : 0) + (tile >= tb2 ? 1 : 0);
+        const int r = tile - (j == 0 ? 0 : j == 1 ? tb1 : tb2);
         if (p.B == 1) { b = 0; lt = r; }
-        else { b = r / p.n_lt[j]; lt = r - b * p.n_lt[j]; }
+        else { const int nl = j == 0 ? nl0 : j == 1 ? nl1 : nl2; b = r / nl; lt = r - b * nl; }
     };
     // snake walk over the cost-sorted tile list (heavy jobs first), see conv1d_tc.cu: even waves deal tiles to CTA 0..P-1, odd ones back
     const int P = (int)gridDim.x, cta = (int)blockIdx.x;
@@ -176,13 +182,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
     auto tile_of = [&](int it) { return it * P + ((it & 1) ? P - 1 - cta : cta); };
     // a *unit* is one (tile, job) conv pair: in the plain mode every tile is one unit of its own job; with sum_jobs a tile is
     // njobs consecutive units whose phase 2 accumulates into the same accumulator
-    const int J = p.sum_jobs ? p.njobs : 1;
+    const int J = SUM ? p.njobs : 1;
     const int n_units = n_my * J;
     auto unit = [&](int n, int& it, int& jj, int& j, int& b, int& lt) {
-        it = J == 1 ? n : n / J;
+        it = J == 1 ? n : J == 2 ? (n >> 1) : (int)(__umulhi((unsigned)n, 0xAAAAAAABu) >> 1);     // n / J, J <= 3
         jj = n - it * J;
         decode(tile_of(it), j, b, lt);
-        if (p.sum_jobs) j = jj;
+        if (SUM) j = jj;
     };
 
     if (warp < 4) {
@@ -227,10 +233,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
             }
         };
+        int it = 0, jj = 0, j = 0, b = 0, lt = 0;
         for (int n = 0; n <= n_units; ++n) {
-            int it, jj, j, b, lt;
+            const int pj = j;                           // job of unit n - 1
             if (n < n_units) { unit(n, it, jj, j, b, lt); stream(p.jobs[j].w1, p.jobs[j].K1); }
-            if (n > 0) { unit(n - 1, it, jj, j, b, lt); stream(p.jobs[j].w2, p.jobs[j].K2); }
+            if (n > 0) stream(p.jobs[pj].w2, p.jobs[pj].K2);
         }
     } else {
         // ======================= MMA issuers: warp 1 -> rows 0..127, warp 3 -> rows 128..255 of the tile =======================
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 while (u < nu) {
                     const int run = min(nu - u, NCH - ch);
                     for (int r = 0; r < run; r += 2) {
-                        if (!(p.dbg & 1) && tc::elect_one()) {
+                        if (!(dbg & 1) && tc::elect_one()) {
                             tc::umma<false>(d_tmem, ((uint64_t)desc_hi << 32) | da_lo, ((uint64_t)desc_hi << 32) | db_lo, idesc, accumulate);
                             if constexpr (MPI == 2)   // sub-tile m + 2: same weights, rows 2*128 further down
                                 tc::umma<false>(d_tmem + 2u * C, ((uint64_t)desc_hi << 32) | (da_lo + 2u * BM), ((uint64_t)desc_hi << 32) | db_lo, idesc, accumulate);
@@ -272,8 +279,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
             }
         };
+        int it = 0, jj = 0, j = 0, b = 0, lt = 0;
         for (int n = 0; n <= n_units; ++n) {
-            int it, jj, j, b, lt;
+            const int pit = it, pjj = jj, pj = j;       // unit n - 1: decoded in the previous round
             if (n < n_units) {   // ---- phase 1 of unit n
                 unit(n, it, jj, j, b, lt);
                 const int g = n & 1;
@@ -290,20 +298,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 __syncwarp();
             }
             if (n > 0) {         // ---- phase 2 of unit n - 1 (accumulates over the jobs of a tile with sum_jobs)
-                unit(n - 1, it, jj, j, b, lt);
                 const int g = (n - 1) & 1;
                 const uint32_t gph = ((n - 1) >> 1) & 1;
-                const int g2 = it & 1;
-                if (jj == 0) tc::mbar_wait(ACC2_EMPTY(g2), ((it >> 1) & 1) ^ 1);
+                const int g2 = pit & 1;
+                if (pjj == 0) tc::mbar_wait(ACC2_EMPTY(g2), ((pit >> 1) & 1) ^ 1);
                 if (m == 0 && lane == 0) trace(5, n - 1);
                 tc::mbar_wait(T_FULL(g), gph);
                 if (m == 0 && lane == 0) trace(6, n - 1);
                 tc::fence_after_sync();
-                run_phase(tmem_base + (uint32_t)(2 * MT * C + (g2 * MT + m) * C), tc::smem_u32(t_smem + (size_t)g * t_bytes) >> 4, (uint32_t)RT, p.jobs[j].K2, 1u,
-                          jj ? 1u : 0u);
+                run_phase(tmem_base + (uint32_t)(2 * MT * C + (g2 * MT + m) * C), tc::smem_u32(t_smem + (size_t)g * t_bytes) >> 4, (uint32_t)RT, p.jobs[pj].K2, 1u,
+                          pjj ? 1u : 0u);
                 if (tc::elect_one()) {
                     tc::umma_commit(T_EMPTY(g));
-                    if (jj == J - 1) tc::umma_commit(ACC2_FULL(g2));
+                    if (pjj == J - 1) tc::umma_commit(ACC2_FULL(g2));
                 }
                 if (m == 0 && lane == 0) trace(7, n - 1);
                 __syncwarp();
@@ -322,26 +329,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
         const size_t cs = (size_t)p.L * 8;                               // stride between 8-channel blocks of the fp32 streams
         const int first2 = eg + NEG * ((NITEM - eg + NEG - 1) / NEG);    // this warpgroup's first epilogue-2 item index (>= NITEM)
         float vn[EB];
+        int it1 = 0, jj1 = 0, j1 = 0, b1 = 0, lt1 = 0;
         for (int n = 0; n <= n_units; ++n) {
             if (q == 0 && lane == 0) trace(28 + eg, n);
             const bool has1 = n < n_units;
-            int it1 = 0, jj1 = 0, j1 = 0, b1 = 0, lt1 = 0, it2 = 0, jj2 = 0, j2 = 0, b2 = 0, lt2 = 0;
+            int it2 = it1, jj2 = jj1, j2 = j1, b2 = b1, lt2 = lt1;      // unit n - 1: decoded in the previous round
             if (has1) unit(n, it1, jj1, j1, b1, lt1);
-            if (n > 0) unit(n - 1, it2, jj2, j2, b2, lt2);
             const bool has2 = n > 0 && jj2 == J - 1;      // unit n-1 closed its tile: the accumulator of tile it2 is complete
-            if (p.sum_jobs) j2 = 0;                       // outputs / summed bias of the stage average live in job 0
+            if (SUM) j2 = 0;                       // outputs / summed bias of the stage average live in job 0
             const rvc_pair_job& jb2 = p.jobs[j2];
             const int l02 = lt2 * p.tmo[j2];
+            if (q == 0 && lane == 0) trace_after(40 + eg, n, __int_as_float(l02 + lt1));
             auto res_load = [&](int k, float* dst) {      // residual(s) of epilogue-2 item k - NITEM of tile it2
                 const int item = k - NITEM;
                 const int m = item / NBLK, cb = item - m * NBLK;
                 const int r2 = m * BM + q * 32 + lane;
                 const int l = l02 + r2;
-                if (!(r2 < p.tmo[j2] && l < p.L) || (p.dbg & 6)) return;
-                if (p.split_in) {
+                if (!(r2 < p.tmo[j2] && l < p.L) || (dbg & 6)) return;
+                if (SPLIT) {
                     // split-fp16 stream: hi (= the conv operand plane, usually still in L2 from this tile's activation load) + lo
                     const size_t poff = ((size_t)b2 * NCH + (size_t)(cb * (EB / 8))) * p.Lp + PADL + l;     // 16-byte units
-                    if (!p.sum_jobs) {   // raw bits now, decoded when the item is processed: the loads stay in flight meanwhile
+                    if (!SUM) {   // raw bits now, decoded when the item is processed: the loads stay in flight meanwhile
                         const uint4* ah = reinterpret_cast<const uint4*>(jb2.a) + poff;
                         const uint4* al = reinterpret_cast<const uint4*>(jb2.a_lo) + poff;
 #pragma unroll
@@ -378,7 +386,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 const size_t off = (size_t)b2 * C * p.L + (size_t)(cb * (EB / 8)) * cs + (size_t)l * 8;
 #pragma unroll
                 for (int u = 0; u < EB / 8; ++u) tc::ldg256(jb2.res + off + (size_t)u * cs, dst + 8 * u);
-                if (p.sum_jobs) {
+                if (SUM) {
                     // the other jobs' residuals: all loads of a chunk are issued before the first add (a per-job loop serialised
                     // three DRAM round trips per item and made the stage-average epilogue the critical path)
                     const float* r1 = p.jobs[1 < p.njobs ? 1 : 0].res + off;
@@ -394,7 +402,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                     }
                 }
             };
-            if (has2 && first2 < 2 * NITEM) res_load(first2, vn);
+            if constexpr (SUM) {      // (the stage average converts its six planes as they arrive; that wait overlaps best ahead of epilogue 1)
+                if (has2 && first2 < 2 * NITEM) res_load(first2, vn);
+            }
             if (has1) {
                 // ---- epilogue 1 of unit n: t = lrelu(acc1 + b1) -> fp16 -> shared-memory operand tile (zeros outside [0, L))
                 const rvc_pair_job& jb = p.jobs[j1];
@@ -436,6 +446,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                 if (lane == 0) { tc::mbar_arrive(T_FULL(g)); tc::mbar_arrive(ACC1_EMPTY(g)); }
                 if (q == 0 && lane == 0) trace(19 + eg, n);
             }
+            // The residual of this warp's first epilogue-2 item is requested AFTER its epilogue-1 items: right after the store burst of the previous
+            // epilogue 2 the load/store path is backed up and the eight loads take 1-2 us to issue (tools/pair_trace.py) — time during which the
+            // MMA warps would wait for the t tile; and the proxy fence that ends epilogue 1 (MEMBAR.ALL.CTA) would wait for the loads to return.
+            if (!SUM && has2 && first2 < 2 * NITEM) {
+                if (q == 0 && lane == 0) trace(46 + eg, n);
+                res_load(first2, vn);
+                if (q == 0 && lane == 0) trace(49 + eg, n);
+            }
             if (has2) {
                 // ---- epilogue 2 of tile it2: x' = alpha * (acc2 + b2 + x)  ->  fp32 and packed lrelu(x')
                 const int g = it2 & 1;
@@ -449,7 +467,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                     const int m = item / NBLK, cb = item - m * NBLK;
                     const int r2 = m * BM + q * 32 + lane;
                     const int l = l02 + r2;
-                    const bool ok = r2 < p.tmo[j2] && l < p.L && !(p.dbg & 2);
+                    const bool ok = r2 < p.tmo[j2] && l < p.L && !(dbg & 2);
                     float v[EB];
 #pragma unroll
                     for (int i = 0; i < EB; ++i) v[i] = vn[i];
@@ -460,7 +478,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                     tc::tmem_ld_wait();
                     if (k == first2 && q == 0 && lane == 0) trace_after(34 + eg, n - 1, __uint_as_float(r[EB - 1]));
                     if (!ok) continue;
-                    if (p.split_in && !p.sum_jobs) {   // raw hi / lo words -> x = inv_lrelu(hi + lo)
+                    if (SPLIT && !SUM) {   // raw hi / lo words -> x = inv_lrelu(hi + lo)
                         const float inv = p.inv_slope;
 #pragma unroll
                         for (int u = 0; u < EB / 8; ++u) {
@@ -484,7 +502,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                         v[4 * i4 + 2] += __uint_as_float(r[4 * i4 + 2]) + b4.z;
                         v[4 * i4 + 3] += __uint_as_float(r[4 * i4 + 3]) + b4.w;
                     }
-                    if (p.sum_jobs) {
+                    if (SUM) {
 #pragma unroll
                         for (int i = 0; i < EB; ++i) v[i] *= p.alpha;
                     }
@@ -499,7 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                             for (int u = 0; u < EB / 8; ++u) tc::stg256(yp + (size_t)u * cs, v + 8 * u);
                         }
                     }
-                    if (p.split_out) {
+                    if ((SPLIT && !SUM)) {
                         // split-fp16 stream out: hi = fp16(lrelu(x')) (the next conv1's operand), lo = fp16(lrelu(x') - hi)
                         const size_t poff = ((size_t)b2 * NCH * p.Lp + ((size_t)cb * (EB / 8)) * p.Lp + PADL + l) * 16;
                         uint8_t* yh = reinterpret_cast<uint8_t*>(jb2.y_act) + poff;
@@ -514,8 +532,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                                 const float2 hf = h2f2(hw[i]);
                                 lw[i] = pack2h(f0 - hf.x, f1 - hf.y, 1);
                             }
-                            *reinterpret_cast<uint4*>(yh + (size_t)u * p.Lp * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                            *reinterpret_cast<uint4*>(yl + (size_t)u * p.Lp * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            tc::stg128(yh + (size_t)u * p.Lp * 16, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+                            tc::stg128(yl + (size_t)u * p.Lp * 16, make_uint4(lw[0], lw[1], lw[2], lw[3]));
                         }
                     } else if (jb2.y_act) {
                         uint8_t* yb = reinterpret_cast<uint8_t*>(jb2.y_act) + (size_t)b2 * NCH * p.Lp * 16 + (((size_t)cb * (EB / 8)) * p.Lp + PADL + l) * 16;
@@ -526,7 +544,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resblock_pair_kernel(const PParam
                             pk.y = pack2h(lrelu_max(v[8 * u + 2], p.slope), lrelu_max(v[8 * u + 3], p.slope), p.fp16);
                             pk.z = pack2h(lrelu_max(v[8 * u + 4], p.slope), lrelu_max(v[8 * u + 5], p.slope), p.fp16);
                             pk.w = pack2h(lrelu_max(v[8 * u + 6], p.slope), lrelu_max(v[8 * u + 7], p.slope), p.fp16);
-                            *reinterpret_cast<uint4*>(yb + (size_t)u * p.Lp * 16) = pk;
+                            tc::stg128(yb + (size_t)u * p.Lp * 16, pk);
                         }
                     }
                     if (k == first2 && q == 0 && lane == 0) trace(37 + eg, n - 1);
@@ -556,9 +574,9 @@ int sm_count() {
     return sms[dev] > 0 ? sms[dev] : 148;
 }
 
-template <int C, int MT>
+template <int C, int MT, bool SUM, bool SPLIT>
 int launch_pair(const PParams& p, size_t smem, int grid, cudaStream_t stream) {
-    auto kern = resblock_pair_kernel<C, MT>;
+    auto kern = resblock_pair_kernel<C, MT, SUM, SPLIT>;
     static bool opted[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -593,7 +611,7 @@ RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream)
     if (d.B <= 0 || d.L <= 0) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: bad shape");
     if (!(d.slope >= 0.f && d.slope <= 1.f)) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: slope must be in [0, 1]");
     const int TMR = BM * (d.C == 32 ? 4 : 2), RT = TMR + RTX;     // C = 32: four sub-tiles per tile (TMEM: 4 * MT * C columns)
-    PParams p;
+    PParams p = {};
     p.njobs = d.njobs; p.B = d.B; p.C = d.C; p.L = d.L; p.Lp = packed_rows(d.L); p.fp16 = d.dtype == RVC_DT_FP16; p.slope = d.slope;
     p.sum_jobs = d.sum_jobs ? 1 : 0; p.y_ncl = d.y_ncl ? 1 : 0; p.alpha = d.sum_jobs ? d.alpha : 1.f;
     p.dbg = d.reserved;
@@ -611,6 +629,8 @@ RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream)
         if ((jb.a_lo || (!d.sum_jobs && jb.y_lo)) && (d.dtype != RVC_DT_FP16 || !(d.slope > 0.f)))
             return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: the split-fp16 stream needs dtype = RVC_DT_FP16 and slope > 0");
         if (!d.sum_jobs && (!(jb.y || jb.y_lo) || !jb.y_act)) return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d needs y_act and y (or y_lo)", j);
+        if (!d.sum_jobs && ((jb.a_lo != nullptr) != (jb.y_lo != nullptr)))
+            return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: a pair step keeps its stream format (a_lo and y_lo go together)", j);
         // (y_lo may alias a_lo: the lo plane is read only at a tile's own output rows, by the thread that rewrites them)
         if (outs && !d.sum_jobs && jb.y_lo && ((uintptr_t)jb.y_lo & 15))
             return rvc::fail(RVC_EINVAL, "rvc_resblock_pair_tc: job %d: y_lo must be 16-byte aligned", j);
@@ -647,8 +667,22 @@ RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream)
     if (smem > 227 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: tile does not fit shared memory (%zu bytes)", smem);
     const int sms = sm_count();
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-    if (d.C == 64) return launch_pair<64, 2>(p, smem, grid, (cudaStream_t)stream);
-    return launch_pair<32, 4>(p, smem, grid, (cudaStream_t)stream);
+    const cudaStream_t st = (cudaStream_t)stream;
+    const int mode = (p.sum_jobs ? 2 : 0) | (p.split_in ? 1 : 0);
+    if (d.C == 64) {
+        switch (mode) {
+            case 0: return launch_pair<64, 2, false, false>(p, smem, grid, st);
+            case 1: return launch_pair<64, 2, false, true>(p, smem, grid, st);
+            case 2: return launch_pair<64, 2, true, false>(p, smem, grid, st);
+            default: return launch_pair<64, 2, true, true>(p, smem, grid, st);
+        }
+    }
+    switch (mode) {
+        case 0: return launch_pair<32, 4, false, false>(p, smem, grid, st);
+        case 1: return launch_pair<32, 4, false, true>(p, smem, grid, st);
+        case 2: return launch_pair<32, 4, true, false>(p, smem, grid, st);
+        default: return launch_pair<32, 4, true, true>(p, smem, grid, st);
+    }
 }
 
 // Debug only (tools/pair_trace.py): register a device buffer of `capacity` 64-bit records for the timeline of CTA 0 (NULL / 0 switches it off);

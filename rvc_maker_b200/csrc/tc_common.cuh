@@ -142,16 +142,33 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Cache hints of the epilogues' streaming global accesses (experiment switches; the defaults are what the product is built with)
+#ifndef RVC_LD_HINT
+#define RVC_LD_HINT ""
+#endif
+#ifndef RVC_ST_HINT
+#define RVC_ST_HINT ""
+#endif
 // 256-bit global accesses (one 32-byte sector per thread; sm_100 LDG/STG.256)
 __device__ __forceinline__ void ldg256(const float* p, float* v) {
-    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global" RVC_LD_HINT ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p));
 }
 __device__ __forceinline__ void stg256(float* p, const float* v) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+    asm volatile("st.global" RVC_ST_HINT ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                  : "memory");
+}
+
+// 128-bit streaming accesses with the same hints
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+    uint4 v;
+    asm volatile("ld.global" RVC_LD_HINT ".v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg128(void* p, uint4 v) {
+    asm volatile("st.global" RVC_ST_HINT ".v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {

@@ -25,12 +25,12 @@ lib = _lib.load()
 dev = "cuda:0"
 
 
-def run(Cc, L, sum_jobs, ks=((11, 5), (7, 3), (3, 1))):
+def run(Cc, L, sum_jobs, ks=((11, 5), (7, 3), (3, 1)), dbg=0):
     st = torch.cuda.current_stream().cuda_stream
     rows = lib.rvc_packed_rows(L)
     d = _lib.ResblockPairDesc()
     d.njobs, d.B, d.C, d.L, d.dtype, d.slope = 3, 1, Cc, L, 2, 0.1
-    d.sum_jobs, d.y_ncl, d.alpha, d.reserved = sum_jobs, sum_jobs, 1.0 / 3.0, 0
+    d.sum_jobs, d.y_ncl, d.alpha, d.reserved = sum_jobs, sum_jobs, 1.0 / 3.0, dbg
     keep = []
     avg = torch.zeros(Cc, L, device=dev)
     for j, (k, dil) in enumerate(ks):
@@ -45,7 +45,7 @@ def run(Cc, L, sum_jobs, ks=((11, 5), (7, 3), (3, 1))):
             pj.y = avg.data_ptr()
         pj.K1, pj.dil1, pj.K2 = k, dil, k
         keep += [a, lo, ya, w1, w2, b1, b2]
-    cap = 50 * 256
+    cap = 80 * 256
     buf = torch.zeros(cap, dtype=torch.int64, device=dev)
     for _ in range(2):    # warm-up without records
         _lib.check(lib.rvc_resblock_pair_tc(C.byref(d), st), "pair")
@@ -57,7 +57,7 @@ def run(Cc, L, sum_jobs, ks=((11, 5), (7, 3), (3, 1))):
     e1.record()
     torch.cuda.synchronize()
     lib.rvc_debug_pair_trace(None, 0)
-    rec = buf.cpu().numpy().reshape(-1, 5, 10)      # [unit][role][k]
+    rec = buf.cpu().numpy().reshape(-1, 5, 16)      # [unit][role][k]
     return rec, e0.elapsed_time(e1) * 1e3
 
 
@@ -68,15 +68,15 @@ def table(rec):
     t = {}
     evs = {1: (0, 0)}
     evs.update({2 + k: (1, k) for k in range(6)})
-    evs.update({10 + 3 * k + eg: (2 + eg, k) for k in range(10) for eg in range(3)})
+    evs.update({10 + 3 * k + eg: (2 + eg, k) for k in range(16) for eg in range(3)})
     for e, (role, k) in evs.items():
         col = rec[:nu, role, k]
         t[e] = np.where(col > 0, col - t0, -1)
     return t, nu
 
 
-def report(name, Cc, L, sum_jobs):
-    rec, us = run(Cc, L, sum_jobs)
+def report(name, Cc, L, sum_jobs, dbg=0):
+    rec, us = run(Cc, L, sum_jobs, dbg=dbg)
     t, nu = table(rec)
     lo, hi = 3, nu - 3       # steady state
     if hi - lo < 4:
@@ -85,7 +85,7 @@ def report(name, Cc, L, sum_jobs):
     mhz = 1965.0
     cyc = lambda x: float(np.mean(x)) / mhz     # us
     period = (t[4][hi - 1] - t[4][lo]) / (hi - 1 - lo) / mhz
-    print(f"== {name}: C={Cc} L={L} {'stage-average' if sum_jobs else 'pair'}: launch {us:.1f} us, {nu} units in CTA 0, {period:.2f} us per unit (steady state)")
+    print(f"== {name} dbg={dbg}: C={Cc} L={L} {'stage-average' if sum_jobs else 'pair'}: launch {us:.1f} us, {nu} units in CTA 0, {period:.2f} us per unit (steady state)")
     # MMA warp 1 (unit n: 2,3,4 ; unit n-1 phase 2: 5,6,7 recorded with unit n-1)
     d = {
         "wait ACC1_EMPTY": t[2][lo + 1:hi] - t[7][lo - 1:hi - 2],      # phase 1 of n follows phase 2 of n-2
@@ -99,12 +99,13 @@ def report(name, Cc, L, sum_jobs):
     for eg in range(3):
         b, a1, te, d1, a2, d2 = (t[x + eg] for x in (10, 13, 16, 19, 22, 25))
         parts = {
-            "prefetch+wait ACC1_FULL": a1[sl] - b[sl],
+            "wait ACC1_FULL": a1[sl] - b[sl],
             "wait T_EMPTY": te[sl] - a1[sl],
             "epilogue 1": d1[sl] - te[sl],
         }
         top, rr, tr, i1 = (t[x + eg] for x in (28, 31, 34, 37))
-        parts["loop top -> prefetch issued"] = b[sl] - top[sl]
+        parts["loop top -> decoded"] = t[40 + eg][sl] - top[sl]
+        parts["residual loads issued in"] = np.where(t[49 + eg][sl] > 0, t[49 + eg][sl] - t[46 + eg][sl], 0)
         if not sum_jobs:
             parts.update({"e2 item 1: residual regs": rr[lo - 1:hi - 1] - a2[lo - 1:hi - 1], "tmem": tr[lo - 1:hi - 1] - rr[lo - 1:hi - 1],
                           "math + stores": i1[lo - 1:hi - 1] - tr[lo - 1:hi - 1], "loop back": top[lo + 1:hi + 1] - d2[lo - 1:hi - 1]})
@@ -126,6 +127,11 @@ if __name__ == "__main__":
     if lib.rvc_debug_pair_trace(None, 0) < 0:
         raise SystemExit("this library has no trace points: python -m rvc_maker_b200.build --trace")
     report("stage 2", 64, 240000, 0)
+    if "--quick" in sys.argv:
+        report("stage 3", 32, 480000, 0)
+        raise SystemExit(0)
     report("stage 2", 64, 240000, 1)
     report("stage 3", 32, 480000, 0)
     report("stage 3", 32, 480000, 1)
+    for dbg in (4, 2, 1):       # no residual loads | no epilogue-2 global I/O | no MMA
+        report("stage 2", 64, 240000, 0, dbg=dbg)
