@@ -5,7 +5,8 @@
     python bench.py --impl reference --steps 3 --warmup 1     # the reference algorithm on the host CPU (oracle port)
 
 A *step* is one `infer` over one batch of synthetic input (default: configs[1] = RVC v2 48k f0, one 10 s clip, B=1,
-T=1000 frames).  `value` = whole-job audio-s/s with inputs resident in HBM (per-step CUDA events, max over ranks);
+T=1000 frames).  `value` = whole-job audio-s/s with inputs resident in HBM: K independent steps through `Synthesizer.infer_many`
+(two lanes; one CUDA-event pair around all K, max over ranks); `serial` = the same K steps as blocking `infer` calls;
 `e2e` = the same through the public module API from pinned HOST buffers including the D2H read of the waveform.
 Multi-GPU: one process per GPU (torchrun), every rank synthesises its own chunks (weak scaling, no data collective).
 """
@@ -344,8 +345,26 @@ def main():
         b.record()
         evs.append((a, b))
     barrier()
+    serial_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---- ... and the same K steps through Synthesizer.infer_many: independent chunks in two lanes (the encoder of step n+1 next to the generator of
+    # step n, rvc_maker_b200/engine.py infer_lanes).  One CUDA-event pair around all K steps; every step's L2 flush is INSIDE the timed region.
+    def dev_items(n):
+        for _ in range(n):
+            flush.zero_()
+            yield (devin["phone"], devin["phone_lengths"], None if args.non_f0 else devin["pitch"], None if args.non_f0 else devin["nsff0"], devin["sid"])
+
+    for _ in net.infer_many(dev_items(args.warmup)):
+        pass
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in net.infer_many(dev_items(args.steps)):
+        pass
+    b.record()
+    barrier()
     t_w1 = time.perf_counter()
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    dev_ms = a.elapsed_time(b)
 
     # ---- end-to-end: pinned host inputs -> Synthesizer.infer_to_host -> waveform in (pinned) host memory, wall clock
     def step_host(inp):
@@ -379,9 +398,9 @@ def main():
     clocks = sampler.stop(t_w0, time.perf_counter()) if sampler else None
 
     if dist is not None:
-        t = torch.tensor([dev_ms, e2e_s, e2e_serial_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_s, e2e_serial_s, serial_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, e2e_serial_s = float(t[0]), float(t[1]), float(t[2])
+        dev_ms, e2e_s, e2e_serial_s, serial_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = wav.numel() * wav.element_size()
@@ -393,11 +412,14 @@ def main():
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"tc": "f16", "tc-bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": workload, "precision": {"tc": "fp16 operands / fp32 accumulate on tcgen05 for every conv, fp32 residual streams + attention + norms",
-                                 "tc-bf16": "as tc, bf16 operands in the C=256 ResBlocks", "fp32": "fp32 CUDA cores"}[args.precision], "l2": "256 MiB memset between steps (untimed); per-step working set > L2",
+                                 "tc-bf16": "as tc, bf16 operands in the C=256 ResBlocks", "fp32": "fp32 CUDA cores"}[args.precision], "l2": "256 MiB memset before every step, inside the timed region (value) / untimed between steps (serial); per-step working set > L2",
+                   "pipelining": "value: K independent steps through Synthesizer.infer_many (two lanes: encoder of step n+1 next to the generator of step n), one event pair "
+                                 "around all K; serial: one blocking infer per step, per-step event pairs",
                    "parallelism": f"{world} replica(s), independent chunks, no data-path collective"},
         "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "Synthesizer.infer_stream (pinned host in / out every step; copies of neighbouring steps overlap compute)",
+                "api": "Synthesizer.infer_stream (pinned host in / out every step; copies of neighbouring steps overlap compute, compute in two lanes)",
                 "serial_value": world * audio_s * args.steps / e2e_serial_s, "serial_api": "Synthesizer.infer_to_host, one blocking call per step"},
+        "serial": {"ms_per_step": serial_ms / args.steps, "value": world * audio_s * args.steps / (serial_ms / 1e3), "api": "Synthesizer.infer, one call per step"},
         "gpu_launches": net._engine.launches_per_infer(B, T) * args.steps * world,
         "clocks": clocks,
     }

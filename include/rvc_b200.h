@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 22
+#define RVC_ABI_VERSION 23
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -30,6 +30,9 @@ int rvc_abi_version(void);
 const char* rvc_last_error(void);
 /* fills {sm_count, cc_major, cc_minor, max_smem_optin}; returns 0 or cudaError_t */
 int rvc_device_info(int device, int* out4);
+/* Cap on the CTAs of the persistent tcgen05 launches (rvc_conv1d_tc, rvc_resblock_pair_tc); 0 = one per SM (default).  Process-wide; returns the
+ * previous value.  Lets a caller that runs two independent chunks on two streams leave SMs to the short-sequence kernels of the other chunk. */
+int rvc_set_grid_limit(int n);
 
 /* post-activation codes */
 #define RVC_ACT_NONE 0
@@ -206,6 +209,12 @@ typedef struct {
     /* optional second packed output next to y_act (fp16 only): y_lo = fp16(leaky_relu(v, act_slope) - float(y_act)), the low half of
      * the split-fp16 residual stream the fused ResBlock steps read (rvc_pair_job.a_lo) */
     void* y_lo;
+    /* optional, in place of `res` (fp16 launches, up <= 1, act_slope > 0): the residual arrives as that split-fp16 stream,
+     * res = inv_leaky_relu(float(res_hi) + float(res_lo), act_slope); both planes in the packed layout and batch stride of y_act (they are the
+     * y_act / y_lo an earlier launch of the same shape wrote).  y_act may alias res_hi and y_lo may alias res_lo: a plane is read only at a
+     * thread's own output elements, before it writes them.  The wide generator stages keep their residual stream this way
+     * (residuals.py:32-36): 10 instead of 12 bytes per element and conv2. */
+    const void* res_hi; const void* res_lo;
 } rvc_tc_job;
 /*
  * up > 1 selects the ConvTranspose1d phase mode (GeneratorNSF.ups, synthesizers.py:133,156): the packed weights hold `up`

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # RVC_B200_LIB: debugging builds of the same library only (tools/pair_trace.py -> librvc_b200_trace.so); never a fallback
 LIB_PATH = os.environ.get("RVC_B200_LIB") or os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 22
+ABI_VERSION = 23
 DT_BF16, DT_FP16, DT_FP16_SPLIT = 0, 2, 3
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -63,6 +63,7 @@ class TcJob(C.Structure):
         ("w_cs", _i32), ("reserved", _i32),
         ("nz_har", _vp), ("nz_w", _vp), ("nz_b", _vp), ("nz_har_bs", _i64), ("nz_kn", _i32), ("nz_sn", _i32), ("nz_pn", _i32), ("reserved2", _i32),
         ("y_lo", _vp),
+        ("res_hi", _vp), ("res_lo", _vp),
     ]
 
 
@@ -132,6 +133,7 @@ SIGNATURES = {
     "rvc_absmax_f32": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp]),
     "rvc_resblock_pair_tc": (C.c_int, [C.POINTER(ResblockPairDesc), _vp]),
     "rvc_debug_pair_trace": (C.c_int, [_vp, _i32]),
+    "rvc_set_grid_limit": (C.c_int, [_i32]),
     "rvc_packed_rows": (_i64, [_i32]),
     "rvc_pack_act": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "rvc_pack_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -15,6 +15,7 @@
 namespace rvc {
 
 char* last_error_buf();  // thread-local, 512 bytes (api.cu)
+int grid_limit();        // rvc_set_grid_limit (api.cu): cap on the CTAs of a persistent launch, 0 = none
 #define RVC_API extern "C" __attribute__((visibility("default")))
 
 inline int fail(int code, const char* fmt, ...) {

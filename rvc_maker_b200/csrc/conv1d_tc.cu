@@ -66,6 +66,7 @@ struct Params {
     int sum_jobs;     // 1: every tile runs all G jobs of its group into one accumulator (stage average of the ResBlocks; split-precision terms)
     int G;            // group size: 1 = every job has its own tiles; otherwise jobs [g*G, (g+1)*G) share the tiles of group g
     int has_res;      // some job carries a residual (enables the epilogue's residual prefetch)
+    int res_split;    // ... as the split-fp16 stream (res_hi / res_lo); a launch takes its residuals in one format
     int blocked;      // bit 0: res is channel-blocked fp32 [b][c/8][l][8]; bit 1: y_f32 is
     int dbg;          // timing experiments only: 1 = epilogue skips global I/O, 2 = skip MMA issue, 4 = skip operand loads,
                       // 8 = skip residual loads, 16 = skip fp32 stores, 32 = skip packed stores, 64 = no residual prefetch
@@ -93,9 +94,25 @@ __device__ __forceinline__ float gate_fast(float t, float s) {
 }
 // leaky_relu for 0 <= slope <= 1 as max(v, slope*v): two instructions, no select
 __device__ __forceinline__ float lrelu_max(float v, float slope) { return fmaxf(v, v * slope); }
+// its inverse for 0 < slope <= 1 (inv = 1 / slope): y > 0 -> y, y < 0 -> y / slope
+__device__ __forceinline__ float lrelu_inv(float y, float inv) { return fminf(y, y * inv); }
+__device__ __forceinline__ float2 h2f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+// one 16-byte unit of each plane of the split-fp16 residual stream -> the eight fp32 residual values
+__device__ __forceinline__ void split_decode8(const uint4& h, const uint4& lo, float inv, float* x) {
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = h2f2(hw[i]), b = h2f2(lw[i]);
+        x[2 * i] = lrelu_inv(a.x + b.x, inv);
+        x[2 * i + 1] = lrelu_inv(a.y + b.y, inv);
+    }
+}
 
-// PF: the launch has residual inputs and the epilogue prefetches them one work item ahead
-template <int NT, int MT, bool PF>
+// PF: the launch has residual inputs and the epilogue prefetches them one work item ahead — 1: fp32 residuals, 2: the split-fp16 stream
+// (res_hi / res_lo, one job per tile).  PF = 0 loads whatever residual a job has when the item is processed (launches without residuals;
+// summed groups of split-fp16 residuals, whose decode-and-add needs the registers the prefetch would hold).  Each variant contains only its
+// own residual code: with all of it in one kernel every prefetching instantiation spilled.
+template <int NT, int MT, int PF>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) {
     constexpr int TM = BM * MT;
     constexpr int NI = MT >= 2 ? 2 : 1;                     // MMA issuer warps
@@ -338,7 +355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         // Residual prefetch (PF instantiation), one work item ahead, also across tiles: the fp32 residual loads of item n+1 are
         // in flight while item n waits for its accumulator, does its math and stores (3-6 % on the conv2 launches).  Launches
         // without residuals use the PF = false instantiation: the 32 extra live registers cost the conv1 epilogue ~10 %.
-        float vn[PF ? EBP : 1];
+        float vn[PF != 0 ? EBP : 1];
         auto load_res = [&](const rvc_tc_job& jn, int b_, int lt_, int nt_, int ph_, int item_, float* vn) {
             const int nblk_ = jn.gated ? (NT / EBP) / 2 : NT / EBP;
             const int m_ = item_ / nblk_, cb_ = item_ - m_ * nblk_;
@@ -346,6 +363,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             const int l_ = lin_ * p.up + ph_ - p.pshift;
             if (!(lin_ < p.L && l_ >= 0 && l_ < p.Lout) || (p.dbg & 9)) return;
             const int co_ = jn.gated ? nt_ * (NT / 2) + cb_ * EBP : nt_ * NT + cb_ * EBP;
+            if (PF != 1 && jn.res_hi) {
+                // split-fp16 stream (hi = an earlier launch's y_act, lo = its y_lo).  One job: the raw words now, decoded when the item is
+                // processed, so the loads stay in flight; a summed group decodes as it adds.
+                const size_t poff = (size_t)b_ * p.nch_out * p.Lp_out + (size_t)(co_ >> 3) * p.Lp_out + PADL + l_;      // 16-byte units
+                if (PF == 2 || !p.sum_jobs) {
+                    const uint4* ph4 = reinterpret_cast<const uint4*>(jn.res_hi) + poff;
+                    const uint4* pl4 = reinterpret_cast<const uint4*>(jn.res_lo) + poff;
+#pragma unroll
+                    for (int u = 0; u < EBP / 8; ++u) {
+                        const uint4 h = tc::ldg128(ph4 + (size_t)u * p.Lp_out), lo = tc::ldg128(pl4 + (size_t)u * p.Lp_out);
+                        vn[8 * u + 0] = __uint_as_float(h.x); vn[8 * u + 1] = __uint_as_float(h.y);
+                        vn[8 * u + 2] = __uint_as_float(h.z); vn[8 * u + 3] = __uint_as_float(h.w);
+                        vn[8 * u + 4] = __uint_as_float(lo.x); vn[8 * u + 5] = __uint_as_float(lo.y);
+                        vn[8 * u + 6] = __uint_as_float(lo.z); vn[8 * u + 7] = __uint_as_float(lo.w);
+                    }
+                } else if constexpr (PF == 0) {
+                    const float inv = 1.f / jn.act_slope;
+#pragma unroll
+                    for (int u = 0; u < EBP / 8; ++u) {
+                        uint4 h[3], lo[3];      // (groups of at most three jobs: the ResBlocks of a stage)
+#pragma unroll
+                        for (int jj = 0; jj < 3; ++jj)
+                            if (jj < p.G && (&jn)[jj].res_hi) {
+                                h[jj] = tc::ldg128(reinterpret_cast<const uint4*>((&jn)[jj].res_hi) + poff + (size_t)u * p.Lp_out);
+                                lo[jj] = tc::ldg128(reinterpret_cast<const uint4*>((&jn)[jj].res_lo) + poff + (size_t)u * p.Lp_out);
+                            }
+                        split_decode8(h[0], lo[0], inv, vn + 8 * u);
+#pragma unroll
+                        for (int jj = 1; jj < 3; ++jj)
+                            if (jj < p.G && (&jn)[jj].res_hi) {
+                                float t8[8];
+                                split_decode8(h[jj], lo[jj], inv, t8);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) vn[8 * u + i] += t8[i];
+                            }
+                    }
+                }
+                return;
+            }
+            if constexpr (PF == 2) return;
             if (p.blocked & 1) {   // channel-blocked fp32: 32 contiguous bytes per 8 channels
                 const float* rp = jn.res + (size_t)b_ * jn.res_bs + (size_t)(co_ >> 3) * jn.res_cs + (size_t)l_ * 8;
 #pragma unroll
@@ -383,7 +440,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             int j_, b_, lt_, nt_, ph_;
             decode(tile_, j_, b_, lt_, nt_, ph_);
             const rvc_tc_job& jn = p.jobs[j_ * p.G];
-            if (jn.res && eg < MT * (jn.gated ? (NT / EBP) / 2 : NT / EBP)) load_res(jn, b_, lt_, nt_, ph_, eg, vn);
+            if ((jn.res || jn.res_hi) && eg < MT * (jn.gated ? (NT / EBP) / 2 : NT / EBP)) load_res(jn, b_, lt_, nt_, ph_, eg, vn);
         };
         if constexpr (PF) {
 #pragma unroll
@@ -419,12 +476,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 if constexpr (PF) {   // this item's residual was requested one item ago; request the next one before the accumulator
 #pragma unroll
                     for (int i = 0; i < EB; ++i) v[i] = vn[i];
-                    if (item + NEG < MT * nblk) { if (jb.res) load_res(jb, b, lt, nt, ph, item + NEG, vn); }
+                    if (item + NEG < MT * nblk) { if (jb.res || jb.res_hi) load_res(jb, b, lt, nt, ph, item + NEG, vn); }
                     else prefetch_tile(it + 1 < n_my ? tile_of(it + 1) : p.total_tiles);
                 } else {
 #pragma unroll
                     for (int i = 0; i < EB; ++i) v[i] = 0.f;
-                    if (jb.res) load_res(jb, b, lt, nt, ph, item, v);
+                    if (jb.res || jb.res_hi) load_res(jb, b, lt, nt, ph, item, v);
                     else if (jb.nz_har && ok) {
                         // fused noise conv (taps in the reference kernel's order: bias, then fma per tap)
                         const int64_t h0 = (int64_t)l * jb.nz_sn - jb.nz_pn, hlen = (int64_t)p.Lout * jb.nz_sn;
@@ -478,6 +535,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     }
                 }
                 if (!ok) continue;
+                const bool has_r = jb.res != nullptr || jb.res_hi != nullptr;
+                if (PF != 1 && jb.res_hi && (PF == 2 || !p.sum_jobs)) {   // raw hi / lo words of the split-fp16 stream -> residual values
+                    const float inv = 1.f / jb.act_slope;
+#pragma unroll
+                    for (int u = 0; u < EB / 8; ++u) {
+                        const uint4 h = make_uint4(__float_as_uint(v[8 * u + 0]), __float_as_uint(v[8 * u + 1]), __float_as_uint(v[8 * u + 2]), __float_as_uint(v[8 * u + 3]));
+                        const uint4 lo = make_uint4(__float_as_uint(v[8 * u + 4]), __float_as_uint(v[8 * u + 5]), __float_as_uint(v[8 * u + 6]), __float_as_uint(v[8 * u + 7]));
+                        split_decode8(h, lo, inv, v + 8 * u);
+                    }
+                }
                 if (jb.relu == 1) {
 #pragma unroll
                     for (int i = 0; i < EB; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
@@ -485,8 +552,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 const float alpha = jb.alpha;
                 if (p.sum_jobs) {   // v = alpha * (sum_j conv_j + sum_j bias_j + sum_j res_j)
 #pragma unroll
-                    for (int i = 0; i < EB; ++i) v[i] = alpha * ((jb.res ? v[i] : 0.f) + __uint_as_float(r[i]));
-                } else if (jb.res || jb.nz_har) {
+                    for (int i = 0; i < EB; ++i) v[i] = alpha * ((has_r ? v[i] : 0.f) + __uint_as_float(r[i]));
+                } else if (has_r || jb.nz_har) {
                     if (alpha == 1.f) {
 #pragma unroll
                         for (int i = 0; i < EB; ++i) v[i] = v[i] + __uint_as_float(r[i]);
@@ -617,15 +684,21 @@ int sm_count_cached() {
     return cache[dev];
 }
 
-template <int NT, int MT, bool PF>
+template <int NT, int MT, int PF>
 int launch_tc_pf(const Params& p, size_t smem, int grid, cudaStream_t stream);
 
 template <int NT, int MT>
 int launch_tc(const Params& p, size_t smem, int grid, cudaStream_t stream) {
-    return (p.has_res && !(p.dbg & 64)) ? launch_tc_pf<NT, MT, true>(p, smem, grid, stream) : launch_tc_pf<NT, MT, false>(p, smem, grid, stream);
+    if (p.res_split) {      // (the prefetching variant exists for the tiles the generator stages use; others load at the item)
+        if constexpr (NT >= 64) {
+            if (!p.sum_jobs && !(p.dbg & 64)) return launch_tc_pf<NT, MT, 2>(p, smem, grid, stream);
+        }
+        return launch_tc_pf<NT, MT, 0>(p, smem, grid, stream);
+    }
+    return (p.has_res && !(p.dbg & 64)) ? launch_tc_pf<NT, MT, 1>(p, smem, grid, stream) : launch_tc_pf<NT, MT, 0>(p, smem, grid, stream);
 }
 
-template <int NT, int MT, bool PF>
+template <int NT, int MT, int PF>
 int launch_tc_pf(const Params& p, size_t smem, int grid, cudaStream_t stream) {
     auto kern = conv1d_tc_kernel<NT, MT, PF>;
     // opt in to the maximum dynamic shared memory once per device and instantiation (the attribute is sticky)
@@ -708,6 +781,12 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
         if (!(jb.act_slope >= 0.f && jb.act_slope <= 1.f)) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: act_slope must be in [0, 1]");
         if (jb.y_lo && (!jb.y_act || d.dtype != RVC_DT_FP16 || ((uintptr_t)jb.y_lo & 15)))
             return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: y_lo goes with y_act, fp16 operands and 16-byte alignment");
+        if (jb.res_hi || jb.res_lo) {
+            if (!jb.res_hi || !jb.res_lo || jb.res || jb.nz_har || gated || d.up > 1 || d.dtype != RVC_DT_FP16 || !(jb.act_slope > 0.f) ||
+                (((uintptr_t)jb.res_hi | (uintptr_t)jb.res_lo) & 15) || jb.y_act_bs)
+                return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: job %d: res_hi / res_lo come as a pair, replace res, and need fp16 operands, act_slope > 0, a plain conv "
+                                             "and the default y_act layout", j);
+        }
         if (jb.nz_har) {
             if (j != 0 || d.sum_jobs || gated || jb.res) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: the fused noise conv belongs to job 0, replaces res, and excludes sum_jobs / gated");
             if (!jb.nz_w || jb.nz_kn < 1 || jb.nz_kn > 4 || jb.nz_sn < 1 || jb.nz_pn < 0) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: fused noise conv needs 1 <= kn <= 4, sn >= 1, pn >= 0");
@@ -731,6 +810,11 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
         if (gated || up > 1) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs excludes gated / transposed mode");
         for (int j = 0; j < d.njobs; ++j)      // (a member's residual is added when it has one; a leader without one takes none at all)
             if (d.jobs[j].res && !d.jobs[j / G * G].res) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs: a member has res but its group leader has none");
+        for (int j = 0; j < d.njobs; ++j)
+            if (d.jobs[j].res_hi && (!d.jobs[j / G * G].res_hi || G > 3))
+                return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs: split-fp16 residuals need a group leader that has one too and groups of at most three jobs");
+        for (int j = 0; j < d.njobs; ++j)
+            if (d.jobs[j / G * G].res_hi && d.jobs[j].res) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs: a group takes its residuals in one format");
     }
     auto ntiles = [&](int nt_, int mt_) { return (long)njt * d.B * rvc::cdiv(Lq, BM * mt_) * (d.Cout / nt_) * up; };
     // wide layers on short sequences (the C = 256 generator stage: L = 10-12 k) are bound by streaming the weights of each tile
@@ -789,7 +873,14 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     p.dbg = d.jobs[0].reserved;
     p.blocked = d.f32_blocked;
     p.has_res = 0;
-    for (int j = 0; j < d.njobs; ++j) p.has_res |= d.jobs[j].res != nullptr;
+    p.res_split = 0;
+    for (int j = 0; j < d.njobs; ++j) {
+        p.has_res |= d.jobs[j].res != nullptr || d.jobs[j].res_hi != nullptr;
+        p.res_split |= d.jobs[j].res_hi != nullptr;
+    }
+    if (p.res_split)
+        for (int j = 0; j < d.njobs; ++j)
+            if (d.jobs[j].res) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: a launch takes its residuals in one format (res or res_hi / res_lo)");
     const size_t fixed = (size_t)NSTAGE * STAGE_BYTES + 512 + (size_t)(d.njobs / G) * d.Cout * sizeof(float) + (d.jobs[0].nz_har ? 16 + (size_t)d.Cout * 20 : 0);
     const size_t limit = 227 * 1024;
     // activation stage: as many channel chunks as fit twice (double buffer); even count
@@ -803,7 +894,8 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     nabuf = nabuf > MAXABUF ? MAXABUF : nabuf;
     p.nabuf = nabuf;
     const size_t smem = (size_t)nabuf * a_stage + fixed;
-    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    const int cap = rvc::grid_limit() > 0 && rvc::grid_limit() < sms ? rvc::grid_limit() : sms;
+    const int grid = p.total_tiles < cap ? p.total_tiles : cap;
     cudaStream_t st = (cudaStream_t)stream;
     if (NT == 128) return launch_tc_mt<128>(mt, p, smem, grid, st);
     if (NT == 64) return launch_tc_mt<64>(mt, p, smem, grid, st);

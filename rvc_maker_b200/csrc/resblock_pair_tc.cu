@@ -666,7 +666,8 @@ RVC_API int rvc_resblock_pair_tc(const rvc_resblock_pair_desc* dp, void* stream)
     const size_t smem = 2 * (size_t)nch * p.ra * 16 + 2 * (size_t)nch * RT * 16 + (size_t)NSTAGE * STAGE_BYTES + 512 + (size_t)d.njobs * 2 * d.C * sizeof(float);
     if (smem > 227 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_resblock_pair_tc: tile does not fit shared memory (%zu bytes)", smem);
     const int sms = sm_count();
-    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    const int cap = rvc::grid_limit() > 0 && rvc::grid_limit() < sms ? rvc::grid_limit() : sms;
+    const int grid = p.total_tiles < cap ? p.total_tiles : cap;
     const cudaStream_t st = (cudaStream_t)stream;
     const int mode = (p.sum_jobs ? 2 : 0) | (p.split_in ? 1 : 0);
     if (d.C == 64) {

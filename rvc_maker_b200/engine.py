@@ -158,6 +158,8 @@ class Engine:
         # ... with the residual stream of those stages carried as two packed fp16 planes (hi = the conv operand, lo = the rounding
         # remainder: 22 bits in 4 bytes) instead of fp32 + a packed operand copy: 8 instead of 12 bytes per element and step
         self.pair_split = os.environ.get("RVC_B200_PAIR_SPLIT", "1") != "0"
+        # ... and in the wide stages (C >= 128, separate conv1 / conv2 launches): conv2 reads its residual as res_hi / res_lo and writes y_act / y_lo
+        self.tc_split = os.environ.get("RVC_B200_TC_SPLIT", "1") != "0"
         # dependent short-sequence launches (the flow) as one persistent kernel with grid barriers between the layers (rvc_conv1d_tc_chain_*)
         self.use_chain = os.environ.get("RVC_B200_CHAIN", "1") != "0"
         # ... or, for the standard flow shape, the whole reverse flow as one cluster kernel that keeps every intermediate on the chip (rvc_flow_reverse_tc)
@@ -873,7 +875,8 @@ class Engine:
                 if dt is not None and dt == udt:
                     xa = self._packed(p, B, Ci, Li)
                 # narrow fused stages: the stage input leaves the ups as the split-fp16 stream (xa = hi, x_lo), no fp32 copy
-                split = blk and Ci in (32, 64) and self.pair_fusion and self.pair_split and dt == DT_FP16 and xa is not None
+                split = blk and dt == DT_FP16 and xa is not None and (
+                    (Ci in (32, 64) and self.pair_fusion and self.pair_split) or (not (Ci in (32, 64) and self.pair_fusion) and self.tc_split))
                 x_lo = self._buf(p, xa.numel(), dtype=torch.uint8) if split else None
                 M = -(-k // u)
                 nz = dict(nz_har=har.data_ptr(), nz_w=W[f"nz_w{i}"].data_ptr(), nz_b=W[f"nz_b{i}"].data_ptr(), nz_har_bs=Lfin, nz_kn=kn, nz_sn=sn,
@@ -943,8 +946,8 @@ class Engine:
                 use_pair = blk and Ci in (32, 64) and self.pair_fusion
                 src_a = {j: xa for j in range(nk)}     # packed lrelu(x_j) read by the next conv1
                 # split-fp16 stream: lo plane of each block's stream (step 0 reads the shared x_lo; later steps update lo[j] in place)
-                lo_j = [self._buf(p, xa.numel(), dtype=torch.uint8) for _ in range(nk)] if (use_pair and split) else None
-                t_of = {}
+                lo_j = [self._buf(p, xa.numel(), dtype=torch.uint8) for _ in range(nk)] if split else None
+                t_of, rhi_of = {}, {}
                 for mm in range(nsteps):
                     last = mm == nsteps - 1
                     if use_pair:
@@ -1004,14 +1007,20 @@ class Engine:
                                 jb.a = src_a[j].data_ptr()
                                 jb.w, jb.bias = W[f"rb{i}_{j}_c1w{mm}"].data_ptr(), W[f"rb{i}_{j}_c1b{mm}"].data_ptr()
                                 jb.y_act = tdst.data_ptr()
-                                t_of[j] = tdst
+                                t_of[j], rhi_of[j] = tdst, src_a[j]      # (the operand of conv1 is the hi plane of this step's residual)
                                 jb.K, jb.dil, jb.pad = kk, rds[j][mm], (kk - 1) // 2 * rds[j][mm]
                             else:           # x = conv2(lrelu(t)) + x;  store x (fp32) and lrelu(x) packed for the next pair
                                 jb.a = t_of[j].data_ptr()
                                 jb.w, jb.bias = W[f"rb{i}_{j}_c2w{mm}"].data_ptr(), W[f"rb{i}_{j}_c2b{mm}"].data_ptr()
-                                jb.res, jb.res_bs, jb.res_cs = (S[0] if mm == 0 else P[j]).data_ptr(), Ci * Li, rcs
+                                if split:     # x = inv_lrelu(hi + lo); x' leaves the same way (the lo plane is updated in place)
+                                    jb.res_hi, jb.res_lo = rhi_of[j].data_ptr(), (x_lo if mm == 0 else lo_j[j]).data_ptr()
+                                else:
+                                    jb.res, jb.res_bs, jb.res_cs = (S[0] if mm == 0 else P[j]).data_ptr(), Ci * Li, rcs
                                 if not fused:
-                                    jb.y_f32, jb.y_bs, jb.y_cs = P[j].data_ptr(), Ci * Li, rcs
+                                    if split:
+                                        jb.y_lo = lo_j[j].data_ptr()
+                                    else:
+                                        jb.y_f32, jb.y_bs, jb.y_cs = P[j].data_ptr(), Ci * Li, rcs
                                     ndst = pa[j] if t_of[j] is not pa[j] else ta[j]    # (conv1 of this step has consumed src_a[j])
                                     jb.y_act = ndst.data_ptr()
                                     src_a[j] = ndst
@@ -1024,8 +1033,9 @@ class Engine:
                             jb.act_slope, jb.alpha = LRELU_SLOPE, (1.0 / nk if fused else 1.0)
                             fl += 2.0 * B * Ci * Ci * kk * Li
                         p.keep.append(d)
-                        by = nk * B * Ci * Li * (2.0 * esz if half == 1 else (esz + 8.0 + esz)) if not fused else \
-                            B * Ci * Li * (nk * (esz + 4.0) + (4.0 if need_f32 else 0.0) + (esz if next_ua is not None else 0.0))
+                        rb = 2.0 * esz if split else 4.0       # residual bytes per element: hi + lo | fp32
+                        by = nk * B * Ci * Li * (2.0 * esz if half == 1 else (esz + 2 * rb + (0.0 if split else esz))) if not fused else \
+                            B * Ci * Li * (nk * (esz + rb) + (4.0 if need_f32 else 0.0) + (esz if next_ua is not None else 0.0))
                         p.add(f"rbtc{i}_s{mm}_c{half}", lib.rvc_conv1d_tc, C.byref(d), flops=fl, bytes_=by,
                               kind=f"conv1d_tc_{'bf16' if dt == DT_BF16 else 'fp16'}[C{Ci}]")
                 cur, curC, curL = (avg, None, None), Ci, Li       # stage average (fp32, plain layout), None when the next ups is fused
@@ -1056,6 +1066,133 @@ class Engine:
         pl.last_stream = cur
         self.plans[key] = pl   # most recently used last
         return pl
+
+    # ------------------------------------------------------------------ two lanes: encoder of chunk i+1 next to the generator of chunk i
+    def _lane_graph(self, kind, pl, key, body):
+        """Replay (or, on the second use of a shape, capture) the kernel sequence of ONE plan as its own CUDA graph on the current stream."""
+        gkey = ("lane", kind) + key
+        ent = self.graphs.pop(gkey, None) if self.use_graph else None
+        gr = ent[0] if ent is not None else None
+        if self.use_graph and gr is None and gkey in self._warm:
+            if len(self.graphs) >= self.max_plans:
+                self.graphs.pop(next(iter(self.graphs)))
+            gr = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.dev)
+            with torch.cuda.graph(gr):
+                body(torch.cuda.current_stream(self.dev).cuda_stream)
+            ent = (gr, ((kind,) + key,))
+        if ent is not None:
+            self.graphs[gkey] = ent
+        if gr is not None:
+            gr.replay()
+        else:
+            body(torch.cuda.current_stream(self.dev).cuda_stream)
+            self._warm.add(gkey)
+
+    def infer_lanes(self, items, out_dtype):
+        """Pipelined ``infer`` over an iterable of ``(phone, phone_lengths, pitch, nsff0, sid[, rate[, noise]])``: yields the result tuples in order.
+
+        The chunks of a conversion are independent (main/inference/convert.py:442-447 is a serial loop over slices), but inside one chunk the
+        TextEncoder (plus prior sample) is a chain of short launches that fills a third of the GPU at best, and only then does the generator
+        start.  Here the two halves run in two lanes — streams — of their own: while the generator of chunk i runs, the encoder of chunk i+1
+        runs next to it; the hardware places the encoder's CTAs as the generator's persistent kernels hand SMs over at their launch
+        boundaries (measured: 2.25 -> 2.06 ms per 10 s chunk; capping the generator's grids to reserve SMs for the other lane, or giving either
+        lane priority, was slower: tools/overlap_probe.py).  Only z_p / the mask cross the lanes, copied at the start of the generator lane;
+        the encoder of chunk i+1 waits for that copy of chunk i.  Same kernels, same RNG draw order, same results as ``infer`` item by item
+        (tests/test_gpu_stream.py).  A result is handed out once the NEXT item has been enqueued, or at the end.
+        """
+        c = self.cfg
+        dev = self.dev
+        if getattr(self, "_lanes", None) is None:
+            self._lanes = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        F, D = self._lanes
+        caller = torch.cuda.current_stream(dev)
+        handoff = None        # event: the generator lane has taken z_p / mask of the previous item out of the encoder plan
+        pending = None
+
+        def finish(h):
+            res, stats, pd_shape, ev, offsets = h
+            caller.wait_event(ev)
+            res.record_stream(caller)
+            stats.record_stream(caller)
+            B, T2 = pd_shape
+            I = c["I"]
+            n_o, n_m, n_z = offsets
+            Lfin = T2 * c["upp"]
+            o = res[:B * Lfin].view(B, 1, Lfin)
+            x_mask = res[n_o:n_o + B * T2].view(B, 1, T2)
+            z = res[n_o + n_m:n_o + n_m + B * I * T2].view(B, I, T2)
+            z_p = res[n_o + n_m + n_z:n_o + n_m + n_z + B * I * T2].view(B, I, T2)
+            return o, x_mask, (z, z_p, stats[:, :I], stats[:, I:])
+
+        for item in items:
+            phone, phone_lengths, pitch, nsff0, sid = item[:5]
+            rate = item[5] if len(item) > 5 else None
+            noise = item[6] if len(item) > 6 else None
+            if phone.dim() != 3 or phone.shape[2] != c["D"]:
+                raise ValueError(f"phone must be [B, T, {c['D']}], got {tuple(phone.shape)}")
+            B, T = int(phone.shape[0]), int(phone.shape[1])
+            if c["f0"] and (pitch is None or nsff0 is None):
+                raise ValueError("use_f0 model: pitch and nsff0 are required")
+            if sid is None:
+                raise ValueError("sid is required")
+            head = int(T * (1.0 - rate)) if rate is not None else 0
+            T2 = T - head
+            with self._lock, torch.cuda.device(dev):
+                if len(self.plans) >= self.max_plans - 1 and (("enc", B, T) not in self.plans or ("dec", B, T2) not in self.plans):
+                    torch.cuda.synchronize(dev)      # a plan is about to be evicted: nothing of either lane may still be using its buffers
+                F.wait_stream(caller)                # the item's tensors may have been produced on the caller's stream
+                D.wait_stream(caller)
+                with torch.cuda.stream(F):
+                    pe = self.plan("enc", B, T)
+                    if handoff is not None:
+                        F.wait_event(handoff)
+                    pe.phone.copy_(phone, non_blocking=True)
+                    pe.lengths.copy_(phone_lengths, non_blocking=True)
+                    if c["f0"]:
+                        pe.pitch.copy_(pitch, non_blocking=True)
+                    if noise is not None:
+                        pe.eps_z.copy_(noise[0], non_blocking=True)
+                    else:
+                        pe.eps_z.normal_()           # randn_like(m_p), synthesizers.py:449
+                    self._lane_graph("enc", pe, (B, T), pe.run)
+                    stats = pe.stats.to(out_dtype, copy=True)
+                    ev_front = torch.cuda.Event()
+                    ev_front.record(F)
+                    for t in (phone, phone_lengths, pitch):
+                        if t is not None and t.is_cuda:
+                            t.record_stream(F)
+                with torch.cuda.stream(D):
+                    pd = self.plan("dec", B, T2)
+                    D.wait_event(ev_front)
+                    pd.zp.copy_(pe.zp[:, :, head:])
+                    pd.mask.copy_(pe.mask[:, head:])
+                    handoff = torch.cuda.Event()
+                    handoff.record(D)
+                    if self.cond_table is not None:
+                        pd.gc.copy_(self.cond_table[sid.to(dev, non_blocking=True)])
+                    else:
+                        pd.g.copy_(self.W["emb_g"][sid.to(dev, non_blocking=True)])
+                    if c["f0"]:
+                        pd.f0.copy_(nsff0[:, head:], non_blocking=True)
+                        if noise is not None:
+                            pd.eps_src.copy_(noise[1].reshape(noise[1].shape[0], -1)[:, : T2 * c["upp"]], non_blocking=True)
+                        else:
+                            torch.rand(1, 1, 1, device=dev)   # rand_ini (:87): drawn to keep the generator stream aligned, value unused (:88)
+                            pd.eps_src.normal_()              # randn_like(sine_waves), :98
+                    self._lane_graph("dec", pd, (B, T2), pd.run)
+                    res = pd.out_arena.to(out_dtype, copy=True)
+                    ev_done = torch.cuda.Event()
+                    ev_done.record(D)
+                    for t in (nsff0, sid):
+                        if t is not None and t.is_cuda:
+                            t.record_stream(D)
+                cur = (res, stats, (B, T2), ev_done, pd.out_offsets)
+            if pending is not None:
+                yield finish(pending)
+            pending = cur
+        if pending is not None:
+            yield finish(pending)
 
     def profile(self, B, T, repeats=3):
         """Per-kernel CUDA-event timings of the (B, T) plans, replayed on the workspaces left by the last infer()."""

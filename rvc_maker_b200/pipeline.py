@@ -59,8 +59,8 @@ def feature_prep(feats, feats0, pitchf, protect, T=None):
     return out
 
 
-def voice_conversion(net_g, feats, p_len, pitch, pitchf, sid, protect=0.5, feats0=None):
-    """convert.py:361-381 for a batch of equal-shape chunks: returns the waveforms ``infer(...)[0][:, 0]`` ([B, T*upp], on device).
+def conversion_inputs(feats, p_len, pitch, pitchf, sid, protect=0.5, feats0=None):
+    """convert.py:361-380 for a batch of equal-shape chunks: the arguments of ``net_g.infer`` — ``(phone, lengths, pitch, pitchf, sid)``.
 
     feats / feats0: [B, Th, D] embedder output (after / before the retrieval blend), p_len = chunk samples // window (:363),
     pitch / pitchf: [B, frames] (None for a model without pitch guidance).
@@ -75,18 +75,25 @@ def voice_conversion(net_g, feats, p_len, pitch, pitchf, sid, protect=0.5, feats
         raise ValueError(f"features have {T} frames after up-sampling but pitch has {pitch.shape[1]}")
     phone = feature_prep(feats, feats0 if guided else None, pitchf if guided else None, protect, T)
     lengths = torch.full((feats.shape[0],), p_len, dtype=torch.long, device=feats.device)   # :380
-    o = net_g.infer(phone, lengths, pitch if guided else None, pitchf.float() if guided else None, sid)[0]
-    return o[:, 0]
+    return phone, lengths, (pitch if guided else None), (pitchf.float() if guided else None), sid
+
+
+def voice_conversion(net_g, feats, p_len, pitch, pitchf, sid, protect=0.5, feats0=None):
+    """convert.py:361-381 for a batch of equal-shape chunks: returns the waveforms ``infer(...)[0][:, 0]`` ([B, T*upp], on device)."""
+    return net_g.infer(*conversion_inputs(feats, p_len, pitch, pitchf, sid, protect, feats0))[0][:, 0]
+
+
+def conversion_inputs_padded(feats, lengths, pitch, pitchf, sid, protect=0.5, feats0=None):
+    """``conversion_inputs`` for a bucketed batch: feats / feats0 [B, Tb/2, D], pitch / pitchf [B, Tb] are zero-padded (pitch index 1)
+    behind every item's own frames and ``lengths`` [B] holds each item's p_len (settled per item by the caller, :363-369)."""
+    guided = pitch is not None and pitchf is not None
+    phone = feature_prep(feats, feats0 if guided else None, pitchf if guided else None, protect, 2 * feats.shape[1])
+    return phone, lengths, (pitch if guided else None), (pitchf.float() if guided else None), sid
 
 
 def voice_conversion_padded(net_g, feats, lengths, pitch, pitchf, sid, protect=0.5, feats0=None):
-    """``voice_conversion`` for a bucketed batch: feats / feats0 [B, Tb/2, D], pitch / pitchf [B, Tb] are zero-padded (pitch index 1)
-    behind every item's own frames and ``lengths`` [B] holds each item's p_len (settled per item by the caller, :363-369).
-    Returns [B, Tb*upp]; item b is valid up to its own ``T_b * upp`` samples."""
-    guided = pitch is not None and pitchf is not None
-    phone = feature_prep(feats, feats0 if guided else None, pitchf if guided else None, protect, 2 * feats.shape[1])
-    o = net_g.infer(phone, lengths, pitch if guided else None, pitchf.float() if guided else None, sid)[0]
-    return o[:, 0]
+    """``voice_conversion`` for a bucketed batch (``conversion_inputs_padded``).  Returns [B, Tb*upp]; item b is valid up to its own ``T_b * upp`` samples."""
+    return net_g.infer(*conversion_inputs_padded(feats, lengths, pitch, pitchf, sid, protect, feats0))[0][:, 0]
 
 
 def batch_chunks(chunks, max_batch, bucket=0):
@@ -238,29 +245,50 @@ class StreamConverter:
     def _convert_groups(self, groups, staged, embed, pitch, pitchf, sid, protect, noise_fn, comp, st, t_pad_tgt, lens, offs, total, spans, owner,
                         rank, world, to_host):
         pieces, keep, short, h2d_bytes, shapes = {}, [], False, 0, set()
-        for gi, group in enumerate(groups):
-            cur = staged
-            comp.wait_event(cur["ev"])
-            staged = self._stage(groups[gi + 1], embed, pitch, pitchf, sid) if gi + 1 < len(groups) else None   # overlaps this batch
-            h2d_bytes += cur["bytes"]
-            c0 = group[0]
-            T_items = cur["T_items"]
-            shapes.add((len(group), 2 * int(cur["feats"].shape[1])))
-            if noise_fn is not None:
-                nz = [noise_fn(c) for c in group]
-                if cur["lengths"] is not None:   # bucketed: the pinned draws cover each item's own frames, zeros behind them
-                    Tb = cur["pitch"].shape[1] if cur["pitch"] is not None else 2 * cur["feats"].shape[1]
-                    nz = [(torch.nn.functional.pad(a, (0, Tb - a.shape[2])), torch.nn.functional.pad(b, (0, 0, 0, Tb * self.upp - b.shape[1])))
-                          for a, b in nz]
-                self.net._noise_override = (torch.cat([a for a, _ in nz]), torch.cat([b for _, b in nz]))
-            if cur["lengths"] is not None:
-                wav = voice_conversion_padded(self.net, cur["feats"], cur["lengths"], cur["pitch"], cur["pitchf"], cur["sid"], protect, cur["feats0"])
-            else:
-                wav = voice_conversion(self.net, cur["feats"], (c0.sample_end - c0.sample_start) // WINDOW, cur["pitch"], cur["pitchf"], cur["sid"],
-                                       protect, cur["feats0"])
-            for t in (cur["feats"], cur["feats0"], cur["pitch"], cur["pitchf"], cur["sid"], cur["lengths"]):
-                if t is not None:
-                    t.record_stream(comp)
+        ctx = []          # per batch, in order: what the post-processing of its waveform needs
+
+        def items():
+            """the arguments of ``infer`` for every batch, in order (staging of batch n+1 overlaps the compute of the batches before it)"""
+            nonlocal staged, h2d_bytes
+            for gi, group in enumerate(groups):
+                cur = staged
+                comp.wait_event(cur["ev"])
+                staged = self._stage(groups[gi + 1], embed, pitch, pitchf, sid) if gi + 1 < len(groups) else None
+                h2d_bytes += cur["bytes"]
+                c0 = group[0]
+                shapes.add((len(group), 2 * int(cur["feats"].shape[1])))
+                noise = None
+                if noise_fn is not None:
+                    nz = [noise_fn(c) for c in group]
+                    if cur["lengths"] is not None:   # bucketed: the pinned draws cover each item's own frames, zeros behind them
+                        Tb = cur["pitch"].shape[1] if cur["pitch"] is not None else 2 * cur["feats"].shape[1]
+                        nz = [(torch.nn.functional.pad(a, (0, Tb - a.shape[2])), torch.nn.functional.pad(b, (0, 0, 0, Tb * self.upp - b.shape[1])))
+                              for a, b in nz]
+                    noise = (torch.cat([a for a, _ in nz]), torch.cat([b for _, b in nz]))
+                if cur["lengths"] is not None:
+                    args = conversion_inputs_padded(cur["feats"], cur["lengths"], cur["pitch"], cur["pitchf"], cur["sid"], protect, cur["feats0"])
+                else:
+                    args = conversion_inputs(cur["feats"], (c0.sample_end - c0.sample_start) // WINDOW, cur["pitch"], cur["pitchf"], cur["sid"],
+                                             protect, cur["feats0"])
+                for t in (cur["feats"], cur["feats0"], cur["pitch"], cur["pitchf"], cur["sid"], cur["lengths"]):
+                    if t is not None:
+                        t.record_stream(comp)
+                ctx.append((group, cur["T_items"]))
+                yield args + (None, noise)
+
+        def results():
+            """waveforms [B, T*upp] per batch, in order: two lanes when the module offers them (Synthesizer.infer_many), else call by call"""
+            if hasattr(self.net, "infer_many"):
+                for r in self.net.infer_many(items()):
+                    yield r[0][:, 0]
+                return
+            for args in items():
+                if args[6] is not None:
+                    self.net._noise_override = args[6]
+                yield self.net.infer(*args[:5])[0][:, 0]
+
+        for gi, wav in enumerate(results()):
+            group, T_items = ctx[gi]
             keeps = [T * self.upp - 2 * t_pad_tgt for T in T_items]
             if min(keeps) <= 0:
                 raise ValueError(f"chunk of {min(T_items)} frames is shorter than its 2 x {self.cfg.x_pad} s of context")

@@ -230,34 +230,68 @@ class Synthesizer(nn.Module):
         torch.cuda.current_stream(o.device).synchronize()
         return out
 
+    def _ensure_engine(self):
+        dev = self.emb_g.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("rvc_maker_b200.Synthesizer needs its parameters on a CUDA device (no CPU fallback)")
+        if self._engine is None:
+            from .engine import Engine
+            self._engine = Engine(self, dev)
+        return self._engine
+
+    @torch.no_grad()
+    def infer_many(self, items):
+        """``infer`` over an iterable of ``(phone, phone_lengths, pitch, nsff0, sid[, rate[, noise]])`` tuples (device or pinned host tensors), pipelined:
+        yields ``(o, x_mask, (z, z_p, m_p, logs_p))`` per item, in order — the same tensors ``infer`` returns item by item, same RNG draw order.
+
+        The reference's chunk loop (main/inference/convert.py:442-447) synthesises independent chunks one after the other; here the TextEncoder of
+        chunk i+1 runs on a second stream next to the generator of chunk i (``Engine.infer_lanes``).  A result is handed out once the next item has
+        been enqueued (or at the end), ordered on the caller's current stream.
+        """
+        eng = self._ensure_engine()
+        dt = self.emb_g.weight.dtype
+
+        def norm(it):
+            for item in it:
+                item = tuple(item)
+                rate = item[5] if len(item) > 5 else None
+                if rate is not None:
+                    assert isinstance(rate, torch.Tensor)
+                    rate = float(rate.item())
+                yield item[:5] + (rate, item[6] if len(item) > 6 else None)
+
+        yield from eng.infer_lanes(norm(items), dt)
+
     @torch.no_grad()
     def infer_stream(self, items, depth=2):
         """Pipelined ``infer_to_host`` over an iterable of ``(phone, phone_lengths, pitch, nsff0, sid[, noise])`` tuples of (pinned) HOST tensors: yields
         ``o`` as float32 ``[B, 1, L]`` views of pinned host buffers, in order.
 
         The caller's chunk loop (main/inference/convert.py:442-447) is strictly serial: copy in, synthesise, copy out.  Here the host-to-device
-        copy of item n+1 runs on a copy stream while item n computes, and the read-back of item n runs on a second copy stream while item n+1
-        computes (``depth`` staging sets; every item's copies still happen, they are just off the critical path).  A yielded view stays valid
-        until ``depth`` further items have been yielded.  Same numerics and RNG order as ``infer`` called item by item.
+        copy of item n+1 runs on a copy stream while item n computes, the read-back of item n runs on a second copy stream while item n+1
+        computes, and the compute itself runs in two lanes (``infer_many``: encoder of item n+1 next to the generator of item n).  Every item's
+        copies still happen, they are just off the critical path.  A yielded view stays valid until ``depth`` further items have been yielded.
+        Same numerics and RNG order as ``infer`` called item by item.
         """
         dev = self.emb_g.weight.device
         if dev.type != "cuda":
             raise RuntimeError("rvc_maker_b200.Synthesizer.infer_stream needs its parameters on a CUDA device (no CPU fallback)")
         comp = torch.cuda.current_stream(dev)
-        if getattr(self, "_pipe", None) is None or self._pipe["dev"] != dev or self._pipe["depth"] != depth:
-            self._pipe = dict(dev=dev, depth=depth, h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev), stage=[None] * depth, host=[None] * depth,
-                              consumed=[None] * depth, done=[None] * depth)
+        nset = depth + 2              # staging sets: one being filled ahead, two in the lanes, `depth` results not yet handed back
+        if getattr(self, "_pipe", None) is None or self._pipe["dev"] != dev or self._pipe["nset"] != nset:
+            self._pipe = dict(dev=dev, nset=nset, h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev), stage=[None] * nset, host=[None] * nset,
+                              free=[None] * nset, done=[None] * nset)
         P = self._pipe
         h2d, d2h = P["h2d"], P["d2h"]
 
         def stage(k, item):
-            """host -> device staging set k on the copy stream (after the compute stream has consumed the set's previous content)"""
+            """host -> device staging set k on the copy stream (after the lanes have finished the item that used the set before)"""
             item = item[:5]
             bufs = P["stage"][k]
             if bufs is None or any((a is None) != (b is None) or (a is not None and (a.shape != b.shape or a.dtype != b.dtype)) for a, b in zip(bufs, item)):
                 bufs = P["stage"][k] = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=dev) for t in item]
-            if P["consumed"][k] is not None:
-                h2d.wait_event(P["consumed"][k])
+            if P["free"][k] is not None:
+                h2d.wait_event(P["free"][k])
             with torch.cuda.stream(h2d):
                 for d, t in zip(bufs, item):
                     if t is not None:
@@ -266,24 +300,32 @@ class Synthesizer(nn.Module):
                 ev.record(h2d)
             return ev
 
-        def run(k, ev_in, noise):
-            comp.wait_event(ev_in)
-            prev = self._noise_override
-            if noise is not None:          # tests: a sixth tuple element pins this item's two noise draws
-                self._noise_override = noise
-            try:
-                o = self.infer(*P["stage"][k])[0]
-            finally:
-                self._noise_override = prev
-            P["consumed"][k] = torch.cuda.Event()
-            P["consumed"][k].record(comp)          # (infer has copied the staged inputs into its own buffers by now, in stream order)
+        slots = []                        # staging set of every item handed to the lanes, in order
+
+        def staged():
+            it = iter(items)
+            nxt = next(it, None)
+            ev_next = stage(0, nxt) if nxt is not None else None
+            n = 0
+            while nxt is not None:
+                k = n % nset
+                cur_ev, cur_noise = ev_next, (nxt[5] if len(nxt) > 5 else None)
+                nxt = next(it, None)
+                if nxt is not None:
+                    ev_next = stage((n + 1) % nset, nxt)    # overlaps the compute of the items before it
+                comp.wait_event(cur_ev)
+                slots.append(k)
+                n += 1
+                yield tuple(P["stage"][k]) + (None, cur_noise)
+
+        def read_back(k, o):
+            P["free"][k] = torch.cuda.Event()
+            P["free"][k].record(comp)                      # (ordered behind the item's result on the caller's stream: both lanes are done with the set)
             n = o.numel()
             if P["host"][k] is None or P["host"][k].numel() < n:
                 P["host"][k] = torch.empty(n, dtype=torch.float32).pin_memory()
             out = P["host"][k][:n].view(o.shape)
-            ev_o = torch.cuda.Event()
-            ev_o.record(comp)
-            d2h.wait_event(ev_o)
+            d2h.wait_event(P["free"][k])
             with torch.cuda.stream(d2h):
                 out.copy_(o, non_blocking=True)
                 o.record_stream(d2h)
@@ -291,21 +333,10 @@ class Synthesizer(nn.Module):
                 P["done"][k].record(d2h)
             return out
 
-        it = iter(items)
-        pending = []                      # (slot, host view) in flight
-        nxt = next(it, None)
-        ev_next = stage(0, nxt) if nxt is not None else None
-        n = 0
-        while nxt is not None:
-            k = n % depth
-            cur_ev = ev_next
-            cur_noise = nxt[5] if len(nxt) > 5 else None
-            nxt = next(it, None)
-            if nxt is not None:
-                ev_next = stage((n + 1) % depth, nxt)       # overlaps the compute of item n
-            pending.append((k, run(k, cur_ev, cur_noise)))
-            n += 1
-            if len(pending) >= depth:                       # keep `depth` items in flight, hand out the oldest
+        pending = []                      # (slot, host view): read-backs in flight
+        for i, res in enumerate(self.infer_many(staged())):
+            pending.append((slots[i], read_back(slots[i], res[0])))
+            if len(pending) >= depth:
                 kk, out = pending.pop(0)
                 P["done"][kk].synchronize()
                 yield out

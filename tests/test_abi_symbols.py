@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.rvc_abi_version() == 22
+    assert lib.rvc_abi_version() == 23
     # argument validation happens before any CUDA call, so it is checkable without a GPU
     rc = lib.rvc_conv1d_f32(None, None)
     assert rc == -1
@@ -57,7 +57,7 @@ def test_desc_struct_layout_matches_header(tmp_path):
     sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     for (cname, ct), sz in zip(pairs, sizes):
         assert ctypes.sizeof(ct) == sz, (cname, ctypes.sizeof(ct), sz)
-    assert ctypes.sizeof(TcJob) == 224 and ctypes.sizeof(PairJob) == 96
+    assert ctypes.sizeof(TcJob) == 240 and ctypes.sizeof(PairJob) == 96
     assert lib_rows(1000) == 64 + 1024 + 64
 
 

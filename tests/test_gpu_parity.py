@@ -340,6 +340,41 @@ def test_infer_stream_equals_item_by_item_calls():
         assert a.shape == b.shape and torch.equal(a, b)
 
 
+def test_infer_many_equals_item_by_item_calls():
+    """Synthesizer.infer_many (two lanes: the encoder of item n+1 runs on a second stream next to the generator of item n) yields, in order, exactly the
+    six tensors infer returns item by item under the same generator seed — fresh RNG draws (same draw order), shape changes, a `rate` item, repeated
+    shapes (graph replays), and a plain infer call afterwards on the same engine."""
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=6, heated=True)
+    net = build_net(cfg, sd, True, precision="tc")
+    shapes = [(1, 300), (2, 130), (1, 300), (1, 300), (2, 130), (1, 300), (1, 64)]
+    items = []
+    for n, (B, T) in enumerate(shapes):
+        inp = cases.synth_inputs(cfg, B, T, seed=200 + n, ragged=B > 1)
+        rate = torch.tensor(0.75) if n == 3 else None
+        items.append((inp["phone"].cuda(), inp["phone_lengths"].cuda(), inp["pitch"].cuda(), inp["nsff0"].cuda(), inp["sid"].cuda(), rate))
+
+    def flat(r):
+        o, x_mask, (z, z_p, m_p, logs_p) = r
+        return [t.clone() for t in (o, x_mask, z, z_p, m_p, logs_p)]
+
+    torch.manual_seed(99)
+    want = [flat(net.infer(*it)) for it in items]
+    torch.cuda.synchronize()
+    for rep in range(2):                 # second pass: every shape replays its captured lane graphs
+        torch.manual_seed(99)
+        got = [flat(r) for r in net.infer_many(iter(items))]
+        torch.cuda.synchronize()
+        assert len(got) == len(want)
+        for n, (a, b) in enumerate(zip(got, want)):
+            for x, y in zip(a, b):
+                assert x.shape == y.shape and torch.equal(x, y), (rep, n, shapes[n])
+    torch.manual_seed(99)
+    again = flat(net.infer(*items[0]))   # the serial call still works on the same engine (waits for the lanes' last use of the plans)
+    assert all(torch.equal(x, y) for x, y in zip(again, want[0]))
+    assert list(net.infer_many(iter([]))) == []
+
+
 @pytest.mark.parametrize("B,T", [(1, 1000), (2, 173), (3, 128), (2, 129), (1, 1), (2, 1024), (40, 64)])
 def test_attention_cluster_kernel_matches_per_launch_path(B, T, monkeypatch):
     """rvc_attn_scores_cluster_tc (scores + softmax in one cluster kernel, row maxima / sums through distributed shared memory, the relative-value

@@ -724,6 +724,94 @@ def test_tc_conv_split_stream_output():
     assert lib.rvc_conv1d_tc(C.byref(d), st) != 0 and b"y_lo" in lib.rvc_last_error()
 
 
+@pytest.mark.parametrize("Cc,L,B,sum_jobs", [(128, 3001, 2, 0), (256, 700, 1, 0), (128, 257, 1, 1), (256, 2100, 2, 1), (64, 1000, 1, 0), (32, 333, 2, 1)])
+def test_tc_conv_split_stream_residual(Cc, L, B, sum_jobs):
+    """rvc_tc_job.res_hi / res_lo: conv2 of a wide ResBlock step with its residual as the split-fp16 stream — the same launch as with the fp32
+    residual the two planes decode to.  One job per tile: y_act bit-identical, decode(y_act, y_lo) within the output split of the fp32 x';
+    summed group (stage average): every output bit-identical.  The lo plane is updated in place."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(123 + Cc + L)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = lib.rvc_packed_rows(L)
+    n = B * Cc * rows * 2
+    ds, df = _lib.Conv1dTcDesc(), _lib.Conv1dTcDesc()
+    for d in (ds, df):
+        d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.sum_jobs = 3, B, Cc, Cc, L, FP16, sum_jobs
+        d.f32_blocked = 1 if sum_jobs else 3
+    keep, outs = [], []
+    avg_s, avg_f = torch.zeros(B, Cc, L, device=DEV), torch.zeros(B, Cc, L, device=DEV)
+    ua_s, ua_f = torch.zeros(n, dtype=torch.uint8, device=DEV), torch.zeros(n, dtype=torch.uint8, device=DEV)
+    for j, k in enumerate((11, 7, 3)):
+        hi, lo, xdec = split_planes(2.0 * torch.randn(B, Cc, L, generator=g), rows)
+        t = torch.randn(B, Cc, L, generator=g).to(DEV)
+        w = (torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5).to(DEV)
+        bias = torch.randn(Cc, generator=g).to(DEV)
+        a, wp = torch.zeros(n, dtype=torch.uint8, device=DEV), torch.zeros(k * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+        _lib.check(lib.rvc_pack_act(t.data_ptr(), None, None, 1.0, Cc * L, L, None, a.data_ptr(), B, Cc, L, FP16, 0.1, st), "pack_act")
+        _lib.check(lib.rvc_pack_weight(w.data_ptr(), wp.data_ptr(), Cc, Cc, k, FP16, st), "pack_weight")
+        xb = to_blocked(xdec.to(DEV))
+        y_f, ya_f = torch.zeros_like(xb), torch.zeros(n, dtype=torch.uint8, device=DEV)
+        yh, yl = hi.clone(), lo.clone()                       # both planes are updated in place
+        for d, split in ((ds, True), (df, False)):
+            jb = d.jobs[j]
+            jb.a, jb.w, jb.bias = a.data_ptr(), wp.data_ptr(), bias.data_ptr()
+            jb.K, jb.dil, jb.pad, jb.act_slope, jb.alpha = k, 1, (k - 1) // 2, 0.1, (1.0 / 3.0 if sum_jobs else 1.0)
+            if split:
+                jb.res_hi, jb.res_lo = yh.data_ptr(), yl.data_ptr()
+            else:
+                jb.res, jb.res_bs, jb.res_cs = xb.data_ptr(), Cc * L, 8 * L
+            if not sum_jobs:
+                if split:
+                    jb.y_act, jb.y_lo = yh.data_ptr(), yl.data_ptr()
+                else:
+                    jb.y_f32, jb.y_bs, jb.y_cs, jb.y_act = y_f.data_ptr(), Cc * L, 8 * L, ya_f.data_ptr()
+            elif j == 0:
+                jb.y_f32, jb.y_bs, jb.y_cs, jb.y_act = (avg_s if split else avg_f).data_ptr(), Cc * L, L, (ua_s if split else ua_f).data_ptr()
+        keep += [hi, lo, a, wp, bias, xb, t, w]
+        outs.append((y_f, ya_f, yh, yl))
+    _lib.check(lib.rvc_conv1d_tc(C.byref(df), st), "conv2 fp32 residual")
+    _lib.check(lib.rvc_conv1d_tc(C.byref(ds), st), "conv2 split residual")
+    torch.cuda.synchronize()
+    if sum_jobs:
+        assert float(avg_f.abs().max()) > 0.1
+        assert torch.equal(avg_s, avg_f) and torch.equal(ua_s, ua_f)
+        return
+    for y_f, ya_f, yh, yl in outs:
+        assert torch.equal(yh, ya_f)
+        assert pad_rows_zero(yh, B, Cc, L, FP16, rows)
+        xs, xf = decode_split(yh, yl, B, Cc, L, rows), from_blocked(y_f)
+        bound = 2.0 ** -21 * F.leaky_relu(xf, 0.1).abs() * 10.0 + 1e-6
+        assert bool(((xs - xf).abs() <= bound).all()), float(((xs - xf).abs() - bound).max())
+
+
+def test_tc_conv_split_stream_residual_is_validated():
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    Cc, L = 64, 300
+    n = Cc * lib.rvc_packed_rows(L) * 2
+    buf = [torch.zeros(n, dtype=torch.uint8, device=DEV) for _ in range(4)]
+    wp = torch.zeros(3 * Cc * Cc * 2, dtype=torch.uint8, device=DEV)
+    d = _lib.Conv1dTcDesc()
+    d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype = 1, 1, Cc, Cc, L, FP16
+    jb = d.jobs[0]
+    jb.a, jb.w, jb.y_act, jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = buf[0].data_ptr(), wp.data_ptr(), buf[1].data_ptr(), 3, 1, 1, 1.0, 0.1
+    jb.res_hi = buf[2].data_ptr()                       # lo plane missing
+    assert lib.rvc_conv1d_tc(C.byref(d), st) != 0 and b"res_hi" in lib.rvc_last_error()
+    jb.res_lo = buf[3].data_ptr()
+    jb.act_slope = 0.0                                  # not invertible
+    assert lib.rvc_conv1d_tc(C.byref(d), st) != 0 and b"res_hi" in lib.rvc_last_error()
+    jb.act_slope = 0.1
+    d.dtype = BF16
+    assert lib.rvc_conv1d_tc(C.byref(d), st) != 0 and b"res_hi" in lib.rvc_last_error()
+    d.dtype = FP16
+    _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "valid split residual launch")
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("Cin,Cout,L,B", [(192, 576, 1000, 2), (96, 256, 300, 3), (768, 192, 257, 1)])
 def test_split_precision_gemm_job_groups(Cin, Cout, L, B):
     """sum_jobs = 3 over six jobs: two independent GEMMs, each as a_hi.W_hi + a_lo.W_hi + a_hi.W_lo in one accumulator (the encoder's
