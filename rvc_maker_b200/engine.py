@@ -84,9 +84,12 @@ class Plan:
         for k in [k for k, v in self.__dict__.items() if torch.is_tensor(v)]:
             delattr(self, k)
 
-    def run(self, stream):
+    def run(self, stream, lo=0, hi=None):
+        """Issue ops [lo, hi) (default: all) on `stream`."""
         side = self.side.cuda_stream if self.side is not None else stream
-        for n, (name, fn, args) in enumerate(self.ops):
+        for n, (name, fn, args) in enumerate(self.ops[:hi]):
+            if n < lo:
+                continue
             if name is None:
                 fn()
             else:
@@ -1048,8 +1051,8 @@ class Engine:
         p.hoist_side(fork_at, join_at, self.side_stream, self.dev)
         return p
 
-    def plan(self, kind, B, T):
-        key = (kind, B, T)
+    def plan(self, kind, B, T, slot=0):
+        key = (kind, B, T) if slot == 0 else (kind, B, T, slot)     # (slot > 0: a second set of workspaces of the same shape, for infer_lanes)
         pl = self.plans.pop(key, None)
         cur = torch.cuda.current_stream(self.dev) if self.dev.type == "cuda" else None
         if pl is None:
@@ -1068,19 +1071,18 @@ class Engine:
         return pl
 
     # ------------------------------------------------------------------ two lanes: encoder of chunk i+1 next to the generator of chunk i
-    def _lane_graph(self, kind, pl, key, body):
-        """Replay (or, on the second use of a shape, capture) the kernel sequence of ONE plan as its own CUDA graph on the current stream."""
-        gkey = ("lane", kind) + key
+    def _lane_graph(self, gkey, pkeys, body):
+        """Replay (or, on the second use of a shape, capture) one lane's kernel sequence as its own CUDA graph on the current stream."""
         ent = self.graphs.pop(gkey, None) if self.use_graph else None
         gr = ent[0] if ent is not None else None
         if self.use_graph and gr is None and gkey in self._warm:
-            if len(self.graphs) >= self.max_plans:
+            if len(self.graphs) >= 2 * self.max_plans:
                 self.graphs.pop(next(iter(self.graphs)))
             gr = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.dev)
             with torch.cuda.graph(gr):
                 body(torch.cuda.current_stream(self.dev).cuda_stream)
-            ent = (gr, ((kind,) + key,))
+            ent = (gr, pkeys)
         if ent is not None:
             self.graphs[gkey] = ent
         if gr is not None:
@@ -1089,17 +1091,28 @@ class Engine:
             body(torch.cuda.current_stream(self.dev).cuda_stream)
             self._warm.add(gkey)
 
+    @staticmethod
+    def _front_ops(pd):
+        """How many leading ops of a generator plan belong to the FRONT lane: the reverse flow (everything ahead of the NSF source / conv_pre)."""
+        if pd.side is not None:         # (a plan with a side branch keeps its fork / join ops together: everything stays in the back lane)
+            return 0
+        for i, op in enumerate(pd.ops):
+            if op[0] in ("sine_source", "conv_pre"):
+                return i
+        return 0
+
     def infer_lanes(self, items, out_dtype):
         """Pipelined ``infer`` over an iterable of ``(phone, phone_lengths, pitch, nsff0, sid[, rate[, noise]])``: yields the result tuples in order.
 
         The chunks of a conversion are independent (main/inference/convert.py:442-447 is a serial loop over slices), but inside one chunk the
-        TextEncoder (plus prior sample) is a chain of short launches that fills a third of the GPU at best, and only then does the generator
-        start.  Here the two halves run in two lanes — streams — of their own: while the generator of chunk i runs, the encoder of chunk i+1
-        runs next to it; the hardware places the encoder's CTAs as the generator's persistent kernels hand SMs over at their launch
-        boundaries (measured: 2.25 -> 2.06 ms per 10 s chunk; capping the generator's grids to reserve SMs for the other lane, or giving either
-        lane priority, was slower: tools/overlap_probe.py).  Only z_p / the mask cross the lanes, copied at the start of the generator lane;
-        the encoder of chunk i+1 waits for that copy of chunk i.  Same kernels, same RNG draw order, same results as ``infer`` item by item
-        (tests/test_gpu_stream.py).  A result is handed out once the NEXT item has been enqueued, or at the end.
+        TextEncoder and the reverse flow are chains of short launches that fill a third of the GPU at best, and only then does the generator
+        start.  Here the two halves run in two lanes — streams — of their own: while the generator of chunk i runs in the back lane, the encoder
+        and flow of chunk i+1 run next to it in the front lane; the hardware places the front lane's CTAs as the generator's persistent kernels
+        hand SMs over at their launch boundaries (measured: 2.25 -> 2.06 ms per 10 s chunk; capping the generator's grids to reserve SMs for
+        the other lane, giving either lane priority, or dealing the generator's tiles dynamically was no faster: tools/overlap_probe.py).
+        The generator plan exists twice (slots i % 2: chunk i+1's flow writes z while chunk i's generator still reads its own); the front lane
+        of chunk i+2 waits for the back lane of chunk i.  Same kernels, same RNG draw order, same results as ``infer`` item by item
+        (tests/test_gpu_parity.py).  A result is handed out once the NEXT item has been enqueued, or at the end.
         """
         c = self.cfg
         dev = self.dev
@@ -1107,8 +1120,10 @@ class Engine:
             self._lanes = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
         F, D = self._lanes
         caller = torch.cuda.current_stream(dev)
-        handoff = None        # event: the generator lane has taken z_p / mask of the previous item out of the encoder plan
+        done = [None, None]   # per slot: event "the back lane has finished the item that used this slot's generator plan"
+        used = []
         pending = None
+        n_item = 0
 
         def finish(h):
             res, stats, pd_shape, ev, offsets = h
@@ -1125,74 +1140,91 @@ class Engine:
             z_p = res[n_o + n_m + n_z:n_o + n_m + n_z + B * I * T2].view(B, I, T2)
             return o, x_mask, (z, z_p, stats[:, :I], stats[:, I:])
 
-        for item in items:
-            phone, phone_lengths, pitch, nsff0, sid = item[:5]
-            rate = item[5] if len(item) > 5 else None
-            noise = item[6] if len(item) > 6 else None
-            if phone.dim() != 3 or phone.shape[2] != c["D"]:
-                raise ValueError(f"phone must be [B, T, {c['D']}], got {tuple(phone.shape)}")
-            B, T = int(phone.shape[0]), int(phone.shape[1])
-            if c["f0"] and (pitch is None or nsff0 is None):
-                raise ValueError("use_f0 model: pitch and nsff0 are required")
-            if sid is None:
-                raise ValueError("sid is required")
-            head = int(T * (1.0 - rate)) if rate is not None else 0
-            T2 = T - head
-            with self._lock, torch.cuda.device(dev):
-                if len(self.plans) >= self.max_plans - 1 and (("enc", B, T) not in self.plans or ("dec", B, T2) not in self.plans):
-                    torch.cuda.synchronize(dev)      # a plan is about to be evicted: nothing of either lane may still be using its buffers
-                F.wait_stream(caller)                # the item's tensors may have been produced on the caller's stream
-                D.wait_stream(caller)
-                with torch.cuda.stream(F):
-                    pe = self.plan("enc", B, T)
-                    if handoff is not None:
-                        F.wait_event(handoff)
-                    pe.phone.copy_(phone, non_blocking=True)
-                    pe.lengths.copy_(phone_lengths, non_blocking=True)
-                    if c["f0"]:
-                        pe.pitch.copy_(pitch, non_blocking=True)
-                    if noise is not None:
-                        pe.eps_z.copy_(noise[0], non_blocking=True)
-                    else:
-                        pe.eps_z.normal_()           # randn_like(m_p), synthesizers.py:449
-                    self._lane_graph("enc", pe, (B, T), pe.run)
-                    stats = pe.stats.to(out_dtype, copy=True)
-                    ev_front = torch.cuda.Event()
-                    ev_front.record(F)
-                    for t in (phone, phone_lengths, pitch):
-                        if t is not None and t.is_cuda:
-                            t.record_stream(F)
-                with torch.cuda.stream(D):
-                    pd = self.plan("dec", B, T2)
-                    D.wait_event(ev_front)
-                    pd.zp.copy_(pe.zp[:, :, head:])
-                    pd.mask.copy_(pe.mask[:, head:])
-                    handoff = torch.cuda.Event()
-                    handoff.record(D)
-                    if self.cond_table is not None:
-                        pd.gc.copy_(self.cond_table[sid.to(dev, non_blocking=True)])
-                    else:
-                        pd.g.copy_(self.W["emb_g"][sid.to(dev, non_blocking=True)])
-                    if c["f0"]:
-                        pd.f0.copy_(nsff0[:, head:], non_blocking=True)
+        try:
+            for item in items:
+                phone, phone_lengths, pitch, nsff0, sid = item[:5]
+                rate = item[5] if len(item) > 5 else None
+                noise = item[6] if len(item) > 6 else None
+                if phone.dim() != 3 or phone.shape[2] != c["D"]:
+                    raise ValueError(f"phone must be [B, T, {c['D']}], got {tuple(phone.shape)}")
+                B, T = int(phone.shape[0]), int(phone.shape[1])
+                if c["f0"] and (pitch is None or nsff0 is None):
+                    raise ValueError("use_f0 model: pitch and nsff0 are required")
+                if sid is None:
+                    raise ValueError("sid is required")
+                head = int(T * (1.0 - rate)) if rate is not None else 0
+                T2 = T - head
+                slot = n_item % 2
+                n_item += 1
+                dkey = ("dec", B, T2) if slot == 0 else ("dec", B, T2, slot)
+                with self._lock, torch.cuda.device(dev):
+                    if len(self.plans) >= self.max_plans - 1 and (("enc", B, T) not in self.plans or dkey not in self.plans):
+                        torch.cuda.synchronize(dev)      # a plan is about to be evicted: nothing of either lane may still be using its buffers
+                    F.wait_stream(caller)                # the item's tensors may have been produced on the caller's stream
+                    D.wait_stream(caller)
+                    with torch.cuda.stream(F):
+                        pe = self.plan("enc", B, T)
+                        pd = self.plan("dec", B, T2, slot)
+                        used[:] = [pl for pl in used if pl is not pe and pl is not pd] + [pe, pd]
+                        if done[slot] is not None:
+                            F.wait_event(done[slot])     # this slot's generator plan is free again
+                        pe.phone.copy_(phone, non_blocking=True)
+                        pe.lengths.copy_(phone_lengths, non_blocking=True)
+                        if c["f0"]:
+                            pe.pitch.copy_(pitch, non_blocking=True)
                         if noise is not None:
-                            pd.eps_src.copy_(noise[1].reshape(noise[1].shape[0], -1)[:, : T2 * c["upp"]], non_blocking=True)
+                            pe.eps_z.copy_(noise[0], non_blocking=True)
                         else:
-                            torch.rand(1, 1, 1, device=dev)   # rand_ini (:87): drawn to keep the generator stream aligned, value unused (:88)
-                            pd.eps_src.normal_()              # randn_like(sine_waves), :98
-                    self._lane_graph("dec", pd, (B, T2), pd.run)
-                    res = pd.out_arena.to(out_dtype, copy=True)
-                    ev_done = torch.cuda.Event()
-                    ev_done.record(D)
-                    for t in (nsff0, sid):
-                        if t is not None and t.is_cuda:
-                            t.record_stream(D)
-                cur = (res, stats, (B, T2), ev_done, pd.out_offsets)
+                            pe.eps_z.normal_()           # randn_like(m_p), synthesizers.py:449
+                        # (the flow's WaveNets are conditioned on the speaker: cond_layer(emb_g(sid)) belongs to the front lane)
+                        if self.cond_table is not None:
+                            pd.gc.copy_(self.cond_table[sid.to(dev, non_blocking=True)])
+                        else:
+                            pd.g.copy_(self.W["emb_g"][sid.to(dev, non_blocking=True)])
+                        kf = self._front_ops(pd)
+
+                        def front(st, pe=pe, pd=pd, head=head, kf=kf):
+                            pe.run(st)
+                            pd.zp.copy_(pe.zp[:, :, head:])
+                            pd.mask.copy_(pe.mask[:, head:])
+                            pd.run(st, 0, kf)
+
+                        self._lane_graph(("lane-front", B, T, head, slot), (("enc", B, T), dkey), front)
+                        stats = pe.stats.to(out_dtype, copy=True)
+                        ev_front = torch.cuda.Event()
+                        ev_front.record(F)
+                        for t in (phone, phone_lengths, pitch, sid):
+                            if t is not None and t.is_cuda:
+                                t.record_stream(F)
+                    with torch.cuda.stream(D):
+                        D.wait_event(ev_front)
+                        if c["f0"]:
+                            pd.f0.copy_(nsff0[:, head:], non_blocking=True)
+                            if noise is not None:
+                                pd.eps_src.copy_(noise[1].reshape(noise[1].shape[0], -1)[:, : T2 * c["upp"]], non_blocking=True)
+                            else:
+                                torch.rand(1, 1, 1, device=dev)   # rand_ini (:87): drawn to keep the generator stream aligned, value unused (:88)
+                                pd.eps_src.normal_()              # randn_like(sine_waves), :98
+                        self._lane_graph(("lane-back", B, T2, slot), (dkey,), lambda st, pd=pd, kf=kf: pd.run(st, kf, None))
+                        res = pd.out_arena.to(out_dtype, copy=True)
+                        ev_done = torch.cuda.Event()
+                        ev_done.record(D)
+                        done[slot] = ev_done
+                        if nsff0 is not None and nsff0.is_cuda:
+                            nsff0.record_stream(D)
+                    cur = (res, stats, (B, T2), ev_done, pd.out_offsets)
+                if pending is not None:
+                    yield finish(pending)
+                pending = cur
             if pending is not None:
-                yield finish(pending)
-            pending = cur
-        if pending is not None:
-            yield finish(pending)
+                last, pending = pending, None
+                yield finish(last)
+        finally:
+            # whatever happens to this generator, later users of these plans (on any stream) queue behind both lanes
+            caller.wait_stream(F)
+            caller.wait_stream(D)
+            for pl in used:
+                pl.last_stream = caller
 
     def profile(self, B, T, repeats=3):
         """Per-kernel CUDA-event timings of the (B, T) plans, replayed on the workspaces left by the last infer()."""

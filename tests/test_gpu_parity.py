@@ -352,7 +352,8 @@ def test_infer_many_equals_item_by_item_calls():
     for n, (B, T) in enumerate(shapes):
         inp = cases.synth_inputs(cfg, B, T, seed=200 + n, ragged=B > 1)
         rate = torch.tensor(0.75) if n == 3 else None
-        items.append((inp["phone"].cuda(), inp["phone_lengths"].cuda(), inp["pitch"].cuda(), inp["nsff0"].cuda(), inp["sid"].cuda(), rate))
+        sid = torch.full((B,), (3 * n) % 7, dtype=torch.int64)      # a different speaker per item: stale conditioning in a lane would show
+        items.append((inp["phone"].cuda(), inp["phone_lengths"].cuda(), inp["pitch"].cuda(), inp["nsff0"].cuda(), sid.cuda(), rate))
 
     def flat(r):
         o, x_mask, (z, z_p, m_p, logs_p) = r
