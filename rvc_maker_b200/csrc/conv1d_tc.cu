@@ -108,10 +108,11 @@ __device__ __forceinline__ void split_decode8(const uint4& h, const uint4& lo, f
     }
 }
 
-// PF: the launch has residual inputs and the epilogue prefetches them one work item ahead — 1: fp32 residuals, 2: the split-fp16 stream
-// (res_hi / res_lo, one job per tile).  PF = 0 loads whatever residual a job has when the item is processed (launches without residuals;
-// summed groups of split-fp16 residuals, whose decode-and-add needs the registers the prefetch would hold).  Each variant contains only its
-// own residual code: with all of it in one kernel every prefetching instantiation spilled.
+// PF selects the residual code of the epilogue: 0 = fp32 residuals (if any) loaded when an item is processed — the launches without residuals;
+// 1 = fp32 residuals prefetched one work item ahead; 2 = the split-fp16 stream (res_hi / res_lo), prefetched (raw words, one job per tile);
+// 3 = the split-fp16 stream loaded when the item is processed (summed groups: their decode-and-add needs the registers a prefetch would hold).
+// Each variant contains only its own residual code: with all of it in one kernel the prefetching instantiations spilled and the others —
+// the conv1 and ConvTranspose launches — ran 5-10 % slower.
 template <int NT, int MT, int PF>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) {
     constexpr int TM = BM * MT;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         // Residual prefetch (PF instantiation), one work item ahead, also across tiles: the fp32 residual loads of item n+1 are
         // in flight while item n waits for its accumulator, does its math and stores (3-6 % on the conv2 launches).  Launches
         // without residuals use the PF = false instantiation: the 32 extra live registers cost the conv1 epilogue ~10 %.
-        float vn[PF != 0 ? EBP : 1];
+        float vn[(PF == 1 || PF == 2) ? EBP : 1];
         auto load_res = [&](const rvc_tc_job& jn, int b_, int lt_, int nt_, int ph_, int item_, float* vn) {
             const int nblk_ = jn.gated ? (NT / EBP) / 2 : NT / EBP;
             const int m_ = item_ / nblk_, cb_ = item_ - m_ * nblk_;
@@ -363,7 +364,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             const int l_ = lin_ * p.up + ph_ - p.pshift;
             if (!(lin_ < p.L && l_ >= 0 && l_ < p.Lout) || (p.dbg & 9)) return;
             const int co_ = jn.gated ? nt_ * (NT / 2) + cb_ * EBP : nt_ * NT + cb_ * EBP;
-            if (PF != 1 && jn.res_hi) {
+            if constexpr (PF >= 2) {
+                if (!jn.res_hi) return;
                 // split-fp16 stream (hi = an earlier launch's y_act, lo = its y_lo).  One job: the raw words now, decoded when the item is
                 // processed, so the loads stay in flight; a summed group decodes as it adds.
                 const size_t poff = (size_t)b_ * p.nch_out * p.Lp_out + (size_t)(co_ >> 3) * p.Lp_out + PADL + l_;      // 16-byte units
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                         vn[8 * u + 4] = __uint_as_float(lo.x); vn[8 * u + 5] = __uint_as_float(lo.y);
                         vn[8 * u + 6] = __uint_as_float(lo.z); vn[8 * u + 7] = __uint_as_float(lo.w);
                     }
-                } else if constexpr (PF == 0) {
+                } else if constexpr (PF == 3) {
                     const float inv = 1.f / jn.act_slope;
 #pragma unroll
                     for (int u = 0; u < EBP / 8; ++u) {
@@ -402,7 +404,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 }
                 return;
             }
-            if constexpr (PF == 2) return;
             if (p.blocked & 1) {   // channel-blocked fp32: 32 contiguous bytes per 8 channels
                 const float* rp = jn.res + (size_t)b_ * jn.res_bs + (size_t)(co_ >> 3) * jn.res_cs + (size_t)l_ * 8;
 #pragma unroll
@@ -440,9 +441,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             int j_, b_, lt_, nt_, ph_;
             decode(tile_, j_, b_, lt_, nt_, ph_);
             const rvc_tc_job& jn = p.jobs[j_ * p.G];
-            if ((jn.res || jn.res_hi) && eg < MT * (jn.gated ? (NT / EBP) / 2 : NT / EBP)) load_res(jn, b_, lt_, nt_, ph_, eg, vn);
+            if ((PF >= 2 ? jn.res_hi != nullptr : jn.res != nullptr) && eg < MT * (jn.gated ? (NT / EBP) / 2 : NT / EBP)) load_res(jn, b_, lt_, nt_, ph_, eg, vn);
         };
-        if constexpr (PF) {
+        constexpr bool PREFETCH = PF == 1 || PF == 2;
+        if constexpr (PREFETCH) {
 #pragma unroll
             for (int i = 0; i < EBP; ++i) vn[i] = 0.f;
             prefetch_tile(n_my > 0 ? tile_of(0) : p.total_tiles);
@@ -473,15 +475,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                 uint32_t r[EB];
                 float v[EB];
                 // this item's residual was prefetched one item ago; start the next item's loads before touching the accumulator
-                if constexpr (PF) {   // this item's residual was requested one item ago; request the next one before the accumulator
+                if constexpr (PREFETCH) {   // this item's residual was requested one item ago; request the next one before the accumulator
 #pragma unroll
                     for (int i = 0; i < EB; ++i) v[i] = vn[i];
-                    if (item + NEG < MT * nblk) { if (jb.res || jb.res_hi) load_res(jb, b, lt, nt, ph, item + NEG, vn); }
+                    if (item + NEG < MT * nblk) { if (PF >= 2 ? jb.res_hi != nullptr : jb.res != nullptr) load_res(jb, b, lt, nt, ph, item + NEG, vn); }
                     else prefetch_tile(it + 1 < n_my ? tile_of(it + 1) : p.total_tiles);
                 } else {
 #pragma unroll
                     for (int i = 0; i < EB; ++i) v[i] = 0.f;
-                    if (jb.res || jb.res_hi) load_res(jb, b, lt, nt, ph, item, v);
+                    if (PF >= 2 ? jb.res_hi != nullptr : jb.res != nullptr) load_res(jb, b, lt, nt, ph, item, v);
                     else if (jb.nz_har && ok) {
                         // fused noise conv (taps in the reference kernel's order: bias, then fma per tap)
                         const int64_t h0 = (int64_t)l * jb.nz_sn - jb.nz_pn, hlen = (int64_t)p.Lout * jb.nz_sn;
@@ -535,8 +537,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                     }
                 }
                 if (!ok) continue;
-                const bool has_r = jb.res != nullptr || jb.res_hi != nullptr;
-                if (PF != 1 && jb.res_hi && (PF == 2 || !p.sum_jobs)) {   // raw hi / lo words of the split-fp16 stream -> residual values
+                const bool has_r = PF >= 2 ? jb.res_hi != nullptr : jb.res != nullptr;
+                if (PF >= 2 && jb.res_hi && (PF == 2 || !p.sum_jobs)) {   // raw hi / lo words of the split-fp16 stream -> residual values
                     const float inv = 1.f / jb.act_slope;
 #pragma unroll
                     for (int u = 0; u < EB / 8; ++u) {
@@ -689,11 +691,11 @@ int launch_tc_pf(const Params& p, size_t smem, int grid, cudaStream_t stream);
 
 template <int NT, int MT>
 int launch_tc(const Params& p, size_t smem, int grid, cudaStream_t stream) {
-    if (p.res_split) {      // (the prefetching variant exists for the tiles the generator stages use; others load at the item)
-        if constexpr (NT >= 64) {
+    if (p.res_split) {
+        if constexpr (NT >= 64) {      // (the prefetching split-fp16 variant is built for the tiles the generator stages use)
             if (!p.sum_jobs && !(p.dbg & 64)) return launch_tc_pf<NT, MT, 2>(p, smem, grid, stream);
         }
-        return launch_tc_pf<NT, MT, 0>(p, smem, grid, stream);
+        return launch_tc_pf<NT, MT, 3>(p, smem, grid, stream);
     }
     return (p.has_res && !(p.dbg & 64)) ? launch_tc_pf<NT, MT, 1>(p, smem, grid, stream) : launch_tc_pf<NT, MT, 0>(p, smem, grid, stream);
 }

@@ -162,7 +162,9 @@ class Engine:
         # remainder: 22 bits in 4 bytes) instead of fp32 + a packed operand copy: 8 instead of 12 bytes per element and step
         self.pair_split = os.environ.get("RVC_B200_PAIR_SPLIT", "1") != "0"
         # ... and in the wide stages (C >= 128, separate conv1 / conv2 launches): conv2 reads its residual as res_hi / res_lo and writes y_act / y_lo
-        self.tc_split = os.environ.get("RVC_B200_TC_SPLIT", "1") != "0"
+        # OFF by default: measured on configs[1] (profiles/r3_history.md) conv2 gets 6 us faster per launch (117 vs 123 us at C = 128) but the ups launch that
+        # has to write the lo plane gets 6 us slower and the stage-average launch, which decodes three split residuals per item, 14 us slower
+        self.tc_split = os.environ.get("RVC_B200_TC_SPLIT", "0") != "0"
         # dependent short-sequence launches (the flow) as one persistent kernel with grid barriers between the layers (rvc_conv1d_tc_chain_*)
         self.use_chain = os.environ.get("RVC_B200_CHAIN", "1") != "0"
         # ... or, for the standard flow shape, the whole reverse flow as one cluster kernel that keeps every intermediate on the chip (rvc_flow_reverse_tc)
