@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 23
+#define RVC_ABI_VERSION 24
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -237,6 +237,12 @@ typedef struct {
 typedef struct {
     rvc_tc_job jobs[6];
     int32_t njobs, B, Cin, Cout, L, dtype, nt, mt, up, pshift, sum_jobs, f32_blocked;
+    /* up_cols = u > 1 ("phase columns", the stride-2 stages of the generator): a stride-u ConvTranspose1d as ONE plain conv (up <= 1) whose
+     * Cout = u * Cr weight columns are the u phases side by side — column block r holds block r of the `up` layout above, K = ceil(k/u) taps,
+     * pad = K - 1; bias has Cout entries (the layer's bias once per phase).  The column (r, c) of input position q lands at output position
+     * q*u + r - pshift, channel c: outputs (y_f32 / y_act / y_lo / mask / the fused noise conv) have Cr channels and length L*u.  Cr must be a
+     * power of two >= 32; no residual inputs.  Against u separate phase tiles: half the operand loads and tile hand-offs, MMAs of twice the width. */
+    int32_t up_cols, reserved;
 } rvc_conv1d_tc_desc;
 int rvc_conv1d_tc(const rvc_conv1d_tc_desc* d, void* stream);
 

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # RVC_B200_LIB: debugging builds of the same library only (tools/pair_trace.py -> librvc_b200_trace.so); never a fallback
 LIB_PATH = os.environ.get("RVC_B200_LIB") or os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 23
+ABI_VERSION = 24
 DT_BF16, DT_FP16, DT_FP16_SPLIT = 0, 2, 3
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -69,7 +69,7 @@ class TcJob(C.Structure):
 
 class Conv1dTcDesc(C.Structure):
     _fields_ = [("jobs", TcJob * 6), ("njobs", _i32), ("B", _i32), ("Cin", _i32), ("Cout", _i32), ("L", _i32), ("dtype", _i32),
-                ("nt", _i32), ("mt", _i32), ("up", _i32), ("pshift", _i32), ("sum_jobs", _i32), ("f32_blocked", _i32)]
+                ("nt", _i32), ("mt", _i32), ("up", _i32), ("pshift", _i32), ("sum_jobs", _i32), ("f32_blocked", _i32), ("up_cols", _i32), ("reserved", _i32)]
 
 
 class PairJob(C.Structure):

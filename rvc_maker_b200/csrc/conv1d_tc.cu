@@ -72,6 +72,7 @@ struct Params {
                       // 8 = skip residual loads, 16 = skip fp32 stores, 32 = skip packed stores, 64 = no residual prefetch
     int up, pshift;   // transposed-conv phase mode: output position = l * up + phase - pshift (up = 1: plain conv)
     int Lout, Lp_out; // output length and packed rows of the output
+    int ucols, cr_shift;   // phase-column mode (rvc_conv1d_tc_desc.up_cols): the Cout weight columns are ucols phase blocks of Cr = 1 << cr_shift channels
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         }
     if (warp >= 4 && p.jobs[0].nz_har) {
         const rvc_tc_job& j0 = p.jobs[0];
-        for (int c = threadIdx.x - 128; c < p.Cout; c += NTHREADS - 128) {
+        for (int c = threadIdx.x - 128; c < (p.ucols > 1 ? (1 << p.cr_shift) : p.Cout); c += NTHREADS - 128) {
             float t[4] = {0.f, 0.f, 0.f, 0.f};
             for (int j = 0; j < j0.nz_kn; ++j) t[j] = j0.nz_w[(size_t)c * j0.nz_kn + j];
             nzw_s[c] = make_float4(t[0], t[1], t[2], t[3]);
@@ -467,11 +468,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
             for (int item = eg; item < MT * nblk; item += NEG) {
                 const int m = item / nblk, cb = item - m * nblk;
                 const int lin = lt * TM + m * BM + q * 32 + lane;
-                const int l = lin * p.up + ph - p.pshift;          // output position
+                const int col0 = nt * NT + cb * EB;               // weight-column index (bias order)
+                int co0 = jb.gated ? nt * (NT / 2) + cb * EB : col0;         // output-channel index
+                int l = lin * p.up + ph - p.pshift;                // output position
+                if (p.ucols > 1) {   // phase columns: block r of Cr columns is phase r of a stride-ucols ConvTranspose
+                    const int r_ = col0 >> p.cr_shift;
+                    co0 = col0 - (r_ << p.cr_shift);
+                    l = lin * p.ucols + r_ - p.pshift;
+                }
                 const bool ok = lin < p.L && l >= 0 && l < p.Lout && !(p.dbg & 1);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * MT + m) * NT);
-                const int col0 = nt * NT + cb * EB;               // weight-column index (bias order)
-                const int co0 = jb.gated ? nt * (NT / 2) + cb * EB : col0;   // output-channel index
                 uint32_t r[EB];
                 float v[EB];
                 // this item's residual was prefetched one item ago; start the next item's loads before touching the accumulator
@@ -804,9 +810,21 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     int mt = d.mt, NT = d.nt;
     const int up = d.up > 0 ? d.up : 1;
     if (up > 1 && (d.pshift < 0 || d.pshift >= up + PADR)) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: bad pshift");
-    // transposed mode: input positions q in [0, L + ceil(pshift/up)) reach valid outputs (rows past L are zero in the packed buffer)
-    const int Lq = up > 1 ? d.L + rvc::cdiv(d.pshift, up) : d.L;
-    const int Lout = up > 1 ? d.L * up : d.L;
+    // phase columns (up_cols = u > 1): a stride-u ConvTranspose as ONE plain conv whose Cout = u * Cr weight columns hold the u phases side by side
+    const int ucols = d.up_cols > 1 ? d.up_cols : 1;
+    int cr_shift = 0;
+    if (ucols > 1) {
+        const int Cr = d.Cout / ucols;
+        while ((1 << cr_shift) < Cr) ++cr_shift;
+        if (up > 1 || gated || G > 1 || d.Cout % ucols || (1 << cr_shift) != Cr || Cr < 32 || d.pshift < 0 || d.pshift >= ucols + PADR)
+            return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: up_cols = %d needs up <= 1, no gate, no job groups, Cout = up_cols * (a power of two >= 32) and a valid pshift", ucols);
+        for (int j = 0; j < d.njobs; ++j)
+            if (d.jobs[j].res || d.jobs[j].res_hi) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: up_cols excludes residual inputs (the fused noise conv is allowed)");
+    }
+    const int ups = ucols > 1 ? ucols : up;       // output positions per input position
+    // transposed modes: input positions q in [0, L + ceil(pshift/ups)) reach valid outputs (rows past L are zero in the packed buffer)
+    const int Lq = ups > 1 ? d.L + rvc::cdiv(d.pshift, ups) : d.L;
+    const int Lout = ups > 1 ? d.L * ups : d.L;
     const int njt = d.njobs / G;                // job groups multiply the tile count
     if (G > 1) {
         if (gated || up > 1) return rvc::fail(RVC_EINVAL, "rvc_conv1d_tc: sum_jobs excludes gated / transposed mode");
@@ -860,9 +878,10 @@ RVC_API int rvc_conv1d_tc(const rvc_conv1d_tc_desc* dp, void* stream) {
     if (mt == 4 && NT > 64) return rvc::fail(RVC_ESHAPE, "rvc_conv1d_tc: mt = 4 needs nt <= 64");
     const int TM = BM * mt;
     p.njobs = d.njobs; p.B = d.B; p.Cin = d.Cin; p.Cout = d.Cout; p.L = Lq; p.Lp = packed_rows(d.L);
-    p.up = up; p.pshift = up > 1 ? d.pshift : 0; p.Lout = Lout; p.Lp_out = packed_rows(Lout);
+    p.up = up; p.pshift = ups > 1 ? d.pshift : 0; p.Lout = Lout; p.Lp_out = packed_rows(Lout);
+    p.ucols = ucols; p.cr_shift = cr_shift;
     p.nch = d.Cin / 8;
-    p.nch_out = (gated ? d.Cout / 2 : d.Cout) / 8;
+    p.nch_out = (gated ? d.Cout / 2 : ucols > 1 ? d.Cout / ucols : d.Cout) / 8;
     p.rows_max = TM + maxpad;
     p.n_lt = rvc::cdiv(Lq, TM);
     p.n_nt = d.Cout / NT;

@@ -545,7 +545,7 @@ RVC_API int rvc_conv1d_tc_chain_build(const rvc_conv1d_tc_desc* descs, const int
         if (d.dtype != RVC_DT_BF16 && d.dtype != RVC_DT_FP16) return rvc::fail(RVC_EINVAL, "chain phase %d: dtype must be RVC_DT_BF16 or RVC_DT_FP16", i);
         if (d.B <= 0 || d.L <= 0 || d.Cin <= 0 || d.Cout <= 0 || d.Cin % 16 || d.Cout % NT)
             return rvc::fail(RVC_ESHAPE, "chain phase %d: needs Cin %% 16 == 0 and Cout %% 64 == 0 (pad the weights), got %d -> %d", i, d.Cin, d.Cout);
-        if (d.up > 1 || (d.nt && d.nt != NT) || (d.mt && d.mt != 1)) return rvc::fail(RVC_EINVAL, "chain phase %d: plain convs with 128 x 64 tiles only", i);
+        if (d.up > 1 || d.up_cols > 1 || (d.nt && d.nt != NT) || (d.mt && d.mt != 1)) return rvc::fail(RVC_EINVAL, "chain phase %d: plain convs with 128 x 64 tiles only", i);
         if (d.f32_blocked & ~3) return rvc::fail(RVC_EINVAL, "chain phase %d: f32_blocked must be 0..3", i);
         const int G = d.sum_jobs <= 0 ? 1 : (d.sum_jobs == 1 ? d.njobs : d.sum_jobs);
         if (d.njobs % G) return rvc::fail(RVC_EINVAL, "chain phase %d: sum_jobs does not divide njobs", i);

@@ -149,6 +149,8 @@ class Engine:
         if self.precision not in ("tc", "tc-bf16", "fp32"):
             raise ValueError(f"precision must be 'tc', 'tc-bf16' or 'fp32', got {self.precision!r}")
         self.tc = self.precision != "fp32"
+        # stride-2 ConvTranspose stages with their two phases as column blocks of one plain conv (rvc_conv1d_tc_desc.up_cols)
+        self.up_cols = os.environ.get("RVC_B200_UP_COLS", "1") != "0"
         self._fold(m)
         self.plans = {}
         self.max_plans = 16   # encoder + decoder plans of the 8 most recently used (B, T) shapes (a bucketed stream needs 3-6)
@@ -270,6 +272,11 @@ class Engine:
                             wk[:, :, r * M + t] = wt[:, :, kk].t()
                 self.up_dt[i] = DT_FP16
                 tc_w[f"t_up_w{i}"] = (wk, self.up_dt[i])
+                # phase-column form for the stride-2 stages (rvc_conv1d_tc_desc.up_cols): the u phases side by side as u * Cout weight columns of
+                # one plain conv with M taps — half the tiles, MMAs of twice the width
+                if self.up_cols and u_i * cout_i <= 128 and cout_i >= 32 and cout_i & (cout_i - 1) == 0:
+                    tc_w[f"t_up_wm{i}"] = (wk.view(cout_i, cin_i, u_i, M).permute(2, 0, 1, 3).reshape(u_i * cout_i, cin_i, M).contiguous(), self.up_dt[i])
+                    W[f"up_bm{i}"] = W[f"up_b{i}"].repeat(u_i)
             if c["f0"]:
                 W[f"nz_w{i}"] = _f(d.noise_convs[i].weight)[:, 0, :].contiguous()
                 W[f"nz_b{i}"] = _f(d.noise_convs[i].bias)
@@ -415,11 +422,12 @@ class Engine:
         bytes_ = 4.0 * (B * Cin * L + B * Cout * L * (1 + (res is not None) + (beta != 0.0)) + Cin * K * Cout * g2)
         plan.add(name, self.lib.rvc_conv1d_f32, C.byref(d), flops=flops, bytes_=bytes_, kind=f"conv1d_f32[C{Cout}k{K}]")
 
-    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag="", up=1, pshift=0, flops=None, blocked=0, sum_jobs=0, cout_valid=None):
+    def _tc(self, plan, name, jobs, *, B, Cin, Cout, L, dtype, nt=0, mt=0, tag="", up=1, pshift=0, flops=None, blocked=0, sum_jobs=0, cout_valid=None,
+            up_cols=0):
         """One persistent tcgen05 launch over up to six jobs (dicts of rvc_tc_job fields; V views for res / y)."""
         d = Conv1dTcDesc()
         d.njobs, d.B, d.Cin, d.Cout, d.L, d.dtype, d.nt, d.mt = len(jobs), B, Cin, Cout, L, dtype, nt, mt
-        d.up, d.pshift, d.f32_blocked, d.sum_jobs = up, pshift, blocked, sum_jobs
+        d.up, d.pshift, d.f32_blocked, d.sum_jobs, d.up_cols = up, pshift, blocked, sum_jobs, up_cols
         fl = by = 0.0
         for slot, j in enumerate(jobs):
             jb = d.jobs[slot]
@@ -446,7 +454,7 @@ class Engine:
             if j.get("nz_har"):
                 jb.nz_har, jb.nz_w, jb.nz_b, jb.nz_har_bs = j["nz_har"], j["nz_w"], j["nz_b"], j["nz_har_bs"]
                 jb.nz_kn, jb.nz_sn, jb.nz_pn = j["nz_kn"], j["nz_sn"], j["nz_pn"]
-            ce = Cout // 2 if jb.gated else Cout
+            ce = Cout // 2 if jb.gated else Cout      # (phase columns: Cout = up_cols * Cr output values per input position)
             fl += 2.0 * B * Cin * Cout * jb.K * L
             by += B * L * (2.0 * Cin + up * ce * (4.0 * (j.get("res") is not None) + 4.0 * (j.get("y") is not None) + 2.0 * (j.get("y_act") is not None) + 2.0 * (j.get("y_lo") is not None)))
         plan.keep.append(d)
@@ -886,10 +894,17 @@ class Engine:
                 M = -(-k // u)
                 nz = dict(nz_har=har.data_ptr(), nz_w=W[f"nz_w{i}"].data_ptr(), nz_b=W[f"nz_b{i}"].data_ptr(), nz_har_bs=Lfin, nz_kn=kn, nz_sn=sn,
                           nz_pn=pn) if nz_fused else {}
-                self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(nzv if c["f0"] and not nz_fused else None),
-                                             y=(None if split else vs0), y_act=xa, y_lo=x_lo, act_slope=LRELU_SLOPE, K=M, pad=M - 1, **nz)],
-                         B=B, Cin=curC, Cout=Ci, L=curL, dtype=udt, up=u, pshift=(k - u) // 2, tag=f"ups",
-                         flops=2.0 * B * curC * Ci * k * curL, blocked=3 if blk else 0)
+                merged = f"t_up_wm{i}" in W and (nz_fused or not c["f0"])      # (phase columns take no residual input)
+                if merged:
+                    self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_wm{i}"], bias=W[f"up_bm{i}"], y=(None if split else vs0), y_act=xa, y_lo=x_lo,
+                                                 act_slope=LRELU_SLOPE, K=M, pad=M - 1, **nz)],
+                             B=B, Cin=curC, Cout=u * Ci, L=curL, dtype=udt, up_cols=u, pshift=(k - u) // 2, tag=f"ups",
+                             flops=2.0 * B * curC * Ci * k * curL, blocked=3 if blk else 0)
+                else:
+                    self._tc(p, f"ups{i}", [dict(a=ua, w=W[f"t_up_w{i}"], bias=W[f"up_b{i}"], res=(nzv if c["f0"] and not nz_fused else None),
+                                                 y=(None if split else vs0), y_act=xa, y_lo=x_lo, act_slope=LRELU_SLOPE, K=M, pad=M - 1, **nz)],
+                             B=B, Cin=curC, Cout=Ci, L=curL, dtype=udt, up=u, pshift=(k - u) // 2, tag=f"ups",
+                             flops=2.0 * B * curC * Ci * k * curL, blocked=3 if blk else 0)
             else:
                 d = ConvTr1dDesc()
                 vx = V(cur[0], curC, curL)

@@ -575,6 +575,77 @@ def test_fused_noise_conv_in_ups_epilogue(Cin, Cout, k, u, Lin, sn):
     assert float((from_blocked(outs[1][0]).double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("Cin,Cout,k,u,Lin,sn,B", [(128, 64, 4, 2, 5001, 2, 2), (64, 32, 4, 2, 7777, 1, 1), (128, 64, 4, 2, 1, 2, 1), (256, 32, 8, 4, 300, 0, 3)])
+def test_conv_transpose_phase_columns_equal_phase_tiles(Cin, Cout, k, u, Lin, sn, B):
+    """rvc_conv1d_tc_desc.up_cols: the u phases of a ConvTranspose as column blocks of ONE plain conv — every output (fp32, packed hi, lo plane,
+    zero pad rows) bit-identical to the phase-tile mode (`up`), with and without the fused noise conv."""
+    from rvc_maker_b200 import _lib
+
+    lib = _lib.load()
+    dtype = FP16
+    g = torch.Generator(device="cpu").manual_seed(5 + Cin + Lin)
+    st = torch.cuda.current_stream().cuda_stream
+    Lout = Lin * u
+    fused = sn > 0
+    kn = 0 if not fused else (1 if sn == 1 else 2 * sn)
+    pn = 0 if sn <= 1 else (kn - sn) // 2
+    x = torch.randn(B, Cin, Lin, generator=g).to(DEV)
+    w = (torch.randn(Cin, Cout, k, generator=g) / (Cin * k / u) ** 0.5).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    har = torch.randn(B, Lout * max(sn, 1), generator=g).to(DEV)
+    nzw, nzb = torch.randn(Cout, 1, max(kn, 1), generator=g).to(DEV), torch.randn(Cout, generator=g).to(DEV)
+    M = -(-k // u)
+    wk = torch.zeros(Cout, Cin, u * M, device=DEV)
+    for r in range(u):
+        for t in range(M):
+            kk = r + (M - 1 - t) * u
+            if kk < k:
+                wk[:, :, r * M + t] = w[:, :, kk].t()
+    wm = wk.view(Cout, Cin, u, M).permute(2, 0, 1, 3).reshape(u * Cout, Cin, M).contiguous()      # phase columns: [u * Cout][Cin][M]
+    rows_in, rows_out = lib.rvc_packed_rows(Lin), lib.rvc_packed_rows(Lout)
+    a = torch.zeros(B * Cin * rows_in * 2, dtype=torch.uint8, device=DEV)
+    wp, wmp = (torch.zeros(u * M * Cin * Cout * 2, dtype=torch.uint8, device=DEV) for _ in range(2))
+    _lib.check(lib.rvc_pack_act(x.data_ptr(), None, None, 1.0, Cin * Lin, Lin, None, a.data_ptr(), B, Cin, Lin, dtype, 0.1, st), "pack_act")
+    _lib.check(lib.rvc_pack_weight(wk.data_ptr(), wp.data_ptr(), Cout, Cin, u * M, dtype, st), "pack_weight")
+    _lib.check(lib.rvc_pack_weight(wm.data_ptr(), wmp.data_ptr(), u * Cout, Cin, M, dtype, st), "pack_weight")
+    bias_m = bias.repeat(u)
+    outs = []
+    for cols in (False, True):
+        yb = torch.zeros(B, Cout // 8, Lout, 8, device=DEV)
+        yh, yl = (torch.zeros(B * Cout * rows_out * 2, dtype=torch.uint8, device=DEV) for _ in range(2))
+        d = _lib.Conv1dTcDesc()
+        d.njobs, d.B, d.Cin, d.L, d.dtype, d.pshift, d.f32_blocked = 1, B, Cin, Lin, dtype, (k - u) // 2, 3
+        if cols:
+            d.Cout, d.up_cols = u * Cout, u
+        else:
+            d.Cout, d.up = Cout, u
+        jb = d.jobs[0]
+        jb.a, jb.w, jb.bias = a.data_ptr(), (wmp if cols else wp).data_ptr(), (bias_m if cols else bias).data_ptr()
+        jb.y_f32, jb.y_bs, jb.y_cs, jb.y_act, jb.y_lo = yb.data_ptr(), Cout * Lout, 8 * Lout, yh.data_ptr(), yl.data_ptr()
+        jb.K, jb.dil, jb.pad, jb.alpha, jb.act_slope = M, 1, M - 1, 1.0, 0.1
+        if fused:
+            jb.nz_har, jb.nz_w, jb.nz_b, jb.nz_har_bs, jb.nz_kn, jb.nz_sn, jb.nz_pn = har.data_ptr(), nzw.data_ptr(), nzb.data_ptr(), Lout * sn, kn, sn, pn
+        _lib.check(lib.rvc_conv1d_tc(C.byref(d), st), "conv1d_tc(up_cols)" if cols else "conv1d_tc(up)")
+        torch.cuda.synchronize()
+        outs.append((yb, yh, yl))
+    if not torch.equal(outs[0][0], outs[1][0]):        # diagnostics: where the two modes differ
+        d_ = (from_blocked(outs[0][0]) - from_blocked(outs[1][0])).abs()
+        bad = torch.nonzero(d_ > 0)
+        raise AssertionError(f"fp32 outputs differ at {bad.shape[0]} of {d_.numel()} elements, max {float(d_.max()):.3e}; first {bad[:6].tolist()}, "
+                             f"last {bad[-3:].tolist()}; channels {sorted(set(bad[:, 1].tolist()))[:12]}; positions mod {u}: {sorted(set((bad[:, 2] % u).tolist()))}")
+    for x_, y_ in zip(outs[0], outs[1]):
+        assert torch.equal(x_, y_)
+    assert pad_rows_zero(outs[1][1], B, Cout, Lout, FP16, rows_out)
+    ref = F.conv_transpose1d(rnd(F.leaky_relu(x, 0.1), dtype).double(), rnd(w, dtype).double(), bias.double(), stride=u, padding=(k - u) // 2)
+    if fused:
+        ref = ref + F.conv1d(har.unsqueeze(1).double(), nzw.double(), nzb.double(), stride=sn, padding=pn)
+    assert float((from_blocked(outs[1][0]).double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
+    # validation: residual inputs are refused, Cr must be a power of two >= 32
+    d.jobs[0].nz_har = None
+    d.jobs[0].res = outs[1][0].data_ptr()
+    assert lib.rvc_conv1d_tc(C.byref(d), st) != 0 and b"up_cols" in lib.rvc_last_error()
+
+
 # ------------------------------------------------------------------------------------------------ split-fp16 residual stream
 def pack_host(t, rows):
     """fp32 [B, C, L] -> packed fp16 plane [B][C/8][rows][8] (position l at row 64 + l, other rows zero) as uint8 on the device."""

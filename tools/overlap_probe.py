@@ -95,13 +95,29 @@ def measure(split, limit, prio_back, label, prio_front=0, skip=()):
 
 
 i_flow = next(i for i, n in enumerate(names) if n and "flow" in n) + 1
-i_sine = next(i for i, n in enumerate(names) if n and "sine" in n)
-i_pre = next(i for i, n in enumerate(names) if n and "conv_pre" in n) + 1
-i_nz0 = next(i for i, n in enumerate(names) if n and "noise0" in n) + 1
+
+
+def lanes_alone(split):
+    """each lane's graph replayed back to back on its own: what the overlapped run could reach at best = max(front, back) ... front + back"""
+    sf, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    gf = capture(lambda st: (run_ops(pe, 0, len(pe.ops), st), run_ops(pd, 0, split, st)), sf)
+    gb = capture(lambda st: run_ops(pd, split, len(pd.ops), st), sb)
+    out = []
+    for g, s_ in ((gf, sf), (gb, sb)):
+        with torch.cuda.stream(s_):
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s_)
+            for _ in range(steps):
+                g.replay()
+            b.record(s_)
+        torch.cuda.synchronize()
+        out.append(a.elapsed_time(b) / steps)
+    print(f"alone: front lane (encoder + flow) {out[0]:.3f} ms, back lane {out[1]:.3f} ms per step")
+
+
+lanes_alone(i_flow)
 for rep in range(2):
     measure(i_flow, 0, 0, "enc + flow")
-    measure(i_flow, 0, 0, "enc + flow, front high", prio_front=-1)
-    measure(i_pre, 0, 0, "enc + flow + conv_pre", skip=(i_sine,))
-    measure(i_pre, 0, 0, "enc + flow + sine + conv_pre")
-    measure(i_nz0, 0, 0, "enc + flow + sine + conv_pre + noise0")
-    measure(0, 0, 0, "enc only")
