@@ -140,8 +140,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
     auto ACC_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * MAXABUF + MAXNG + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * MAXABUF + 2 * MAXNG);
     float* bias_s = reinterpret_cast<float*>(bars + 2 * NSTAGE + 2 * MAXABUF + 2 * MAXNG + 2);   // [njobs][Cout], 16-byte aligned
-    float4* nzw_s = reinterpret_cast<float4*>(bias_s + (((p.njobs / p.G) * p.Cout + 3) & ~3));             // [Cout] noise-conv taps of job 0 (<= 4, zero padded)
-    float* nzb_s = reinterpret_cast<float*>(nzw_s + p.Cout);                                       // [Cout] noise-conv bias
+    // fused noise conv of job 0: taps TAP-major, [4][Cout] (zero padded), then the bias [Cout] — the epilogue reads four channels per LDS.128
+    // (8 + 8 kn loads per 32-channel item instead of 64)
+    float* nzw_s = bias_s + (((p.njobs / p.G) * p.Cout + 3) & ~3);
+    float* nzb_s = nzw_s + 4 * p.Cout;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
     const int lane = threadIdx.x & 31;
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
         for (int c = threadIdx.x - 128; c < (p.ucols > 1 ? (1 << p.cr_shift) : p.Cout); c += NTHREADS - 128) {
             float t[4] = {0.f, 0.f, 0.f, 0.f};
             for (int j = 0; j < j0.nz_kn; ++j) t[j] = j0.nz_w[(size_t)c * j0.nz_kn + j];
-            nzw_s[c] = make_float4(t[0], t[1], t[2], t[3]);
+            for (int j = 0; j < 4; ++j) nzw_s[j * p.Cout + c] = t[j];
             nzb_s[c] = j0.nz_b ? j0.nz_b[c] : 0.f;
         }
     }
@@ -499,15 +501,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const Params p) 
                         for (int jx = 0; jx < 4; ++jx) hv[jx] = (jx < jb.nz_kn && h0 + jx >= 0 && h0 + jx < hlen) ? hb[h0 + jx] : 0.f;
                         const int kn = jb.nz_kn;
 #pragma unroll
-                        for (int i = 0; i < EB; ++i) {
-                            const float4 w4 = nzw_s[co0 + i];
-                            float a = nzb_s[co0 + i];
-                            a = fmaf(w4.x, hv[0], a);
-                            if (kn > 1) a = fmaf(w4.y, hv[1], a);
-                            if (kn > 2) a = fmaf(w4.z, hv[2], a);
-                            if (kn > 3) a = fmaf(w4.w, hv[3], a);
-
-                            v[i] = a;
+                        for (int i4 = 0; i4 < EB / 4; ++i4) {      // (reference order per channel: bias, then one fma per tap)
+                            float4 a = *reinterpret_cast<const float4*>(nzb_s + co0 + 4 * i4);
+#pragma unroll
+                            for (int jx = 0; jx < 4; ++jx)
+                                if (jx < kn) {
+                                    const float4 w4 = *reinterpret_cast<const float4*>(nzw_s + jx * p.Cout + co0 + 4 * i4);
+                                    a.x = fmaf(w4.x, hv[jx], a.x); a.y = fmaf(w4.y, hv[jx], a.y); a.z = fmaf(w4.z, hv[jx], a.z); a.w = fmaf(w4.w, hv[jx], a.w);
+                                }
+                            v[4 * i4 + 0] = a.x; v[4 * i4 + 1] = a.y; v[4 * i4 + 2] = a.z; v[4 * i4 + 3] = a.w;
                         }
                     }
                 }
