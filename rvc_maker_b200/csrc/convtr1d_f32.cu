@@ -127,7 +127,35 @@ __global__ void __launch_bounds__(256) conv_post_f32_kernel(const float* __restr
     const float* xb = x + (int64_t)b * x_bs;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const bool interior = !x2 && (l0 >= 4) && (l0 + 8 <= L) && ((x_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0);
-    for (int c = 0; c < C; ++c) {
+    int c_first = 0;
+    if (interior) {
+        // four channels at a time, all twelve 128-bit loads in flight before the first use: channel by channel the thread made C dependent
+        // round trips to memory (27 us at C = 32, L = 480 000 for 61 MB).  Same accumulation order (c ascending, tap ascending).
+        for (; c_first + 4 <= C; c_first += 4) {
+            float4 q[4][3];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* xr = xb + (int64_t)(c_first + u) * x_cs;
+                q[u][0] = *reinterpret_cast<const float4*>(xr + l0 - 4);
+                q[u][1] = *reinterpret_cast<const float4*>(xr + l0);
+                q[u][2] = *reinterpret_cast<const float4*>(xr + l0 + 4);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float win[12] = {q[u][0].x, q[u][0].y, q[u][0].z, q[u][0].w, q[u][1].x, q[u][1].y, q[u][1].z, q[u][1].w,
+                                 q[u][2].x, q[u][2].y, q[u][2].z, q[u][2].w};
+#pragma unroll
+                for (int j = 0; j < 12; ++j) win[j] = rvc::lrelu(win[j], slope);
+#pragma unroll
+                for (int kk = 0; kk < 7; ++kk) {
+                    const float wv = w_s[(c_first + u) * 7 + kk];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i] = fmaf(wv, win[i + kk + 1], acc[i]);
+                }
+            }
+        }
+    }
+    for (int c = c_first; c < C; ++c) {
         const float* xr = xb + (int64_t)c * x_cs;
         float win[12];  // x[l0-4 .. l0+7]
         if (x2) {
@@ -231,7 +259,25 @@ __global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __rest
         const int c = i / kn, j = i - c * kn;
         w_s[j * 32 + c] = (co0 + c < C) ? w[(int64_t)(co0 + c) * kn + j] : 0.f;
     }
-    for (int i = threadIdx.x; i < span; i += 128) {
+    // the source window: 128-bit loads where the window lies inside the signal and is 16-byte aligned (a long window — 10 280 samples at sn = 40 —
+    // filled one sample per thread and round trip was a third of the launch)
+    const bool vec = (((g0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(hb) & 15) == 0) && ((har_bs & 3) == 0));
+    const int nvec = vec ? span / 4 : 0;
+#pragma unroll 4
+    for (int i4 = threadIdx.x; i4 < nvec; i4 += 128) {
+        const int64_t idx = g0 + 4 * (int64_t)i4;
+        float4 v;
+        if (idx >= 0 && idx + 3 < hlen) v = *reinterpret_cast<const float4*>(hb + idx);
+        else {
+            v.x = (idx >= 0 && idx < hlen) ? hb[idx] : 0.f;
+            v.y = (idx + 1 >= 0 && idx + 1 < hlen) ? hb[idx + 1] : 0.f;
+            v.z = (idx + 2 >= 0 && idx + 2 < hlen) ? hb[idx + 2] : 0.f;
+            v.w = (idx + 3 >= 0 && idx + 3 < hlen) ? hb[idx + 3] : 0.f;
+        }
+        const int i = 4 * i4;
+        h_s[hpad(i)] = v.x; h_s[hpad(i + 1)] = v.y; h_s[hpad(i + 2)] = v.z; h_s[hpad(i + 3)] = v.w;
+    }
+    for (int i = 4 * nvec + threadIdx.x; i < span; i += 128) {
         const int64_t idx = g0 + i;
         h_s[hpad(i)] = (idx >= 0 && idx < hlen) ? hb[idx] : 0.f;
     }
@@ -262,9 +308,11 @@ __global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __rest
 #pragma unroll
             for (int g = 0; g < 4; ++g)
                 if (co0 + 8 * g < C) {
-                    float4* yp = reinterpret_cast<float4*>(y + (int64_t)b * y_bs + ((int64_t)(co0 / 8 + g) * Lout + l) * 8);
-                    yp[0] = make_float4(acc[half][8 * g], acc[half][8 * g + 1], acc[half][8 * g + 2], acc[half][8 * g + 3]);
-                    yp[1] = make_float4(acc[half][8 * g + 4], acc[half][8 * g + 5], acc[half][8 * g + 6], acc[half][8 * g + 7]);
+                    // ONE 256-bit store per lane: a warp writes 1 KB of whole 32-byte sectors (two 128-bit stores per lane touch every sector twice, half each)
+                    float* yp = y + (int64_t)b * y_bs + ((int64_t)(co0 / 8 + g) * Lout + l) * 8;
+                    const float* v = &acc[half][8 * g];
+                    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                 ::"l"(yp), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
                 }
         } else {
 #pragma unroll
