@@ -239,12 +239,14 @@ RVC_API int rvc_conv_post_f32(const float* x, const float* x2, const float* x3, 
 // One thread = one output position; its har window sits in registers (16 taps at a time) and is reused by 32 channels.
 // ------------------------------------------------------------------------------------------------
 namespace {
-// One thread = TWO output positions (t and t + 128 of the CTA's 256) x 32 channels: a tap costs 2 source reads + 8 broadcast
-// LDS.128 of weights for 64 FMAs.  The source window is stored with one pad word per 32 (index i + i/32): threads read it at
+// One thread = NP output positions (t, t + 128, ... of the CTA's 128 * NP) x 32 channels: a tap costs NP source reads + 8 broadcast
+// LDS.128 of weights for 32 * NP FMAs.  NP = 1 (64 registers, 8 CTAs per SM): with NP = 2 the 160 registers of a thread limited an SM to three CTAs —
+// 12 warps, one wave of 376 CTAs at stage 0, 4.2 waves at stage 1 — and both launches were latency-bound (ncu: warps active 16 %, issue 42 %).  The source window is stored with one pad word per 32 (index i + i/32): threads read it at
 // stride sn, and e.g. sn = 40 would otherwise put every 4th thread on the same bank (8-way conflict).
 __device__ __forceinline__ int hpad(int i) { return i + (i >> 5); }
 
-__global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __restrict__ har, int64_t har_bs, const float* __restrict__ w,
+template <int NP>
+__global__ void __launch_bounds__(128, NP == 1 ? 8 : 3) noise_conv_f32_kernel(const float* __restrict__ har, int64_t har_bs, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y, int64_t y_bs, int C,
                                                              int Lout, int kn, int sn, int pn, int blocked) {
     rvc::pdl_prologue();
@@ -253,8 +255,8 @@ __global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __rest
     const int co0 = blockIdx.y * 32, b = blockIdx.z;
     const int64_t hlen = (int64_t)Lout * sn;
     const float* hb = har + (int64_t)b * har_bs;
-    const int64_t g0 = (int64_t)blockIdx.x * 256 * sn - pn;       // source index of window element 0
-    const int span = 255 * sn + kn;
+    const int64_t g0 = (int64_t)blockIdx.x * (128 * NP) * sn - pn;       // source index of window element 0
+    const int span = (128 * NP - 1) * sn + kn;
     for (int i = threadIdx.x; i < 32 * kn; i += 128) {
         const int c = i / kn, j = i - c * kn;
         w_s[j * 32 + c] = (co0 + c < C) ? w[(int64_t)(co0 + c) * kn + j] : 0.f;
@@ -282,26 +284,34 @@ __global__ void __launch_bounds__(128) noise_conv_f32_kernel(const float* __rest
         h_s[hpad(i)] = (idx >= 0 && idx < hlen) ? hb[idx] : 0.f;
     }
     __syncthreads();
-    const int l0 = blockIdx.x * 256 + threadIdx.x;
+    const int l0 = blockIdx.x * (128 * NP) + threadIdx.x;
     if (l0 >= Lout) return;
-    float acc[2][32];
+    float acc[NP][32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc[0][c] = acc[1][c] = (co0 + c < C && bias) ? bias[co0 + c] : 0.f;
-    const int h0 = threadIdx.x * sn, h1 = (threadIdx.x + 128) * sn;
+    for (int c = 0; c < 32; ++c) {
+        const float bv = (co0 + c < C && bias) ? bias[co0 + c] : 0.f;
+#pragma unroll
+        for (int h = 0; h < NP; ++h) acc[h][c] = bv;
+    }
     for (int j = 0; j < kn; ++j) {
-        const float hv0 = h_s[hpad(h0 + j)], hv1 = h_s[hpad(h1 + j)];
+        float hv[NP];
+#pragma unroll
+        for (int h = 0; h < NP; ++h) hv[h] = h_s[hpad((threadIdx.x + 128 * h) * sn + j)];
         const float4* wj = reinterpret_cast<const float4*>(w_s + j * 32);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
             const float4 wv = wj[c4];
-            acc[0][4 * c4 + 0] = fmaf(wv.x, hv0, acc[0][4 * c4 + 0]); acc[1][4 * c4 + 0] = fmaf(wv.x, hv1, acc[1][4 * c4 + 0]);
-            acc[0][4 * c4 + 1] = fmaf(wv.y, hv0, acc[0][4 * c4 + 1]); acc[1][4 * c4 + 1] = fmaf(wv.y, hv1, acc[1][4 * c4 + 1]);
-            acc[0][4 * c4 + 2] = fmaf(wv.z, hv0, acc[0][4 * c4 + 2]); acc[1][4 * c4 + 2] = fmaf(wv.z, hv1, acc[1][4 * c4 + 2]);
-            acc[0][4 * c4 + 3] = fmaf(wv.w, hv0, acc[0][4 * c4 + 3]); acc[1][4 * c4 + 3] = fmaf(wv.w, hv1, acc[1][4 * c4 + 3]);
+#pragma unroll
+            for (int h = 0; h < NP; ++h) {
+                acc[h][4 * c4 + 0] = fmaf(wv.x, hv[h], acc[h][4 * c4 + 0]);
+                acc[h][4 * c4 + 1] = fmaf(wv.y, hv[h], acc[h][4 * c4 + 1]);
+                acc[h][4 * c4 + 2] = fmaf(wv.z, hv[h], acc[h][4 * c4 + 2]);
+                acc[h][4 * c4 + 3] = fmaf(wv.w, hv[h], acc[h][4 * c4 + 3]);
+            }
         }
     }
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < NP; ++half) {
         const int l = l0 + 128 * half;
         if (l >= Lout) break;
         if (blocked) {   // [b][c/8][l][8]: one 32-byte sector per 8 channels
@@ -329,14 +339,21 @@ RVC_API int rvc_noise_conv_f32(const float* har, int64_t har_bs, const float* w,
     if (blocked && ((C & 7) || ((uintptr_t)y & 31) || (y_bs & 7))) return rvc::fail(RVC_ESHAPE, "rvc_noise_conv_f32: blocked output needs C %% 8 == 0 and 32-byte alignment");
     if (B <= 0 || B > 65535 || C <= 0 || Lout < 0 || kn <= 0 || kn > 1024 || sn <= 0 || pn < 0) return rvc::fail(RVC_ESHAPE, "rvc_noise_conv_f32: bad shape");
     if (Lout == 0) return 0;
-    const int span = 255 * sn + kn;
+    // short kernels (stage >= 1: 8 taps and fewer) are latency-bound: one position per thread, 8 CTAs per SM (stage 1: 31 -> 23 us); the long
+    // stage-0 kernel (80 taps) is bound by its shared-memory reads, which two positions per thread halve (33 us against 35)
+    const int NP = kn > 16 ? 2 : 1;
+    const int span = (128 * NP - 1) * sn + kn;
     const size_t smem = (size_t)(32 * kn + span + span / 32 + 1) * sizeof(float);
     if (smem > 200 * 1024) return rvc::fail(RVC_ESHAPE, "rvc_noise_conv_f32: kn = %d, sn = %d need %zu bytes of shared memory", kn, sn, smem);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(noise_conv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = NP == 2 ? cudaFuncSetAttribute(noise_conv_f32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(noise_conv_f32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return rvc::fail((int)e, "rvc_noise_conv_f32: smem opt-in: %s", cudaGetErrorString(e));
     }
-    dim3 grid(rvc::cdiv(Lout, 256), rvc::cdiv(C, 32), B);
-    rvc::launch_pdl(noise_conv_f32_kernel, dim3(grid), dim3(128), smem, (cudaStream_t)stream, har, har_bs, w, bias, y, y_bs, C, Lout, kn, sn, pn, (int)blocked);
+    dim3 grid(rvc::cdiv(Lout, 128 * NP), rvc::cdiv(C, 32), B);
+    if (NP == 2)
+        rvc::launch_pdl(noise_conv_f32_kernel<2>, dim3(grid), dim3(128), smem, (cudaStream_t)stream, har, har_bs, w, bias, y, y_bs, C, Lout, kn, sn, pn, (int)blocked);
+    else
+        rvc::launch_pdl(noise_conv_f32_kernel<1>, dim3(grid), dim3(128), smem, (cudaStream_t)stream, har, har_bs, w, bias, y, y_bs, C, Lout, kn, sn, pn, (int)blocked);
     return rvc::check_launch("rvc_noise_conv_f32");
 }
