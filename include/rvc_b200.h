@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 24
+#define RVC_ABI_VERSION 25
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -358,6 +358,12 @@ typedef struct {
     const void* qk; int64_t qk_bs; int32_t q_chunk0, k_chunk0, lo_chunks, planes;
     const void* ek; const float* qkv; const float* mask; void* P; void* vw;
     int32_t B, H, n_heads, T, window, reserved;
+    /* att != NULL: the P.v GEMM runs in the same kernel (P and vw are then unused and may be NULL) — every CTA multiplies its 256-key slice of P
+     * (which never leaves shared memory) with v^T of its keys, the partial sums are reduce-scattered through distributed shared memory and the
+     * cluster writes att, the packed fp16 operand of conv_o: [b][chunks][rvc_packed_rows(T)][8] with head h, dim d in chunk (96 h + d) / 8, batch
+     * stride att_bs bytes, the lo plane fp16(O - hi) att_lo_chunks chunks behind the hi plane (0: no lo plane); evT = emb_rel_v^T packed
+     * [4][96][8] fp16 (relative position major, zero past 2w+1). */
+    void* att; int64_t att_bs; const void* evT; int32_t att_lo_chunks, reserved2;
 } rvc_attn_scores_desc;
 int rvc_attn_scores_cluster_tc(const rvc_attn_scores_desc* d, void* stream);
 

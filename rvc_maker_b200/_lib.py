@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # RVC_B200_LIB: debugging builds of the same library only (tools/pair_trace.py -> librvc_b200_trace.so); never a fallback
 LIB_PATH = os.environ.get("RVC_B200_LIB") or os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 24
+ABI_VERSION = 25
 DT_BF16, DT_FP16, DT_FP16_SPLIT = 0, 2, 3
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -95,7 +95,8 @@ class AttnScoresDesc(C.Structure):
     """rvc_attn_scores_desc."""
     _fields_ = [("qk", _vp), ("qk_bs", _i64), ("q_chunk0", _i32), ("k_chunk0", _i32), ("lo_chunks", _i32), ("planes", _i32),
                 ("ek", _vp), ("qkv", _vp), ("mask", _vp), ("P", _vp), ("vw", _vp),
-                ("B", _i32), ("H", _i32), ("n_heads", _i32), ("T", _i32), ("window", _i32), ("reserved", _i32)]
+                ("B", _i32), ("H", _i32), ("n_heads", _i32), ("T", _i32), ("window", _i32), ("reserved", _i32),
+                ("att", _vp), ("att_bs", _i64), ("evT", _vp), ("att_lo_chunks", _i32), ("reserved2", _i32)]
 
 
 class EncoderTailDesc(C.Structure):

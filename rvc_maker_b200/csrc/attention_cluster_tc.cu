@@ -33,8 +33,13 @@ constexpr int QPLANE_BYTES = NCHK * BM * 16;         // one fp16 plane of the 12
 constexpr int KPLANE_BYTES = NCHK * BK * 16;         // ... of the 256-key tile
 constexpr int EKP_BYTES = NCHK * NRP * 16;
 constexpr int QE_LD = 24;
-constexpr int SMEM_BYTES = 2 * QPLANE_BYTES + 2 * KPLANE_BYTES + 2 * EKP_BYTES + BM * QE_LD * 4 + BK * 4 + 2 * NG * BM * 4 + 2 * MAXC * BM * 4 + 64;
-constexpr int COL_S = 0, COL_R = 256, TMEM_COLS = 512;
+constexpr int SMEM_BASE = 2 * QPLANE_BYTES + 2 * KPLANE_BYTES + 2 * EKP_BYTES + BM * QE_LD * 4 + BK * 4 + 2 * NG * BM * 4 + 2 * MAXC * BM * 4 + 64;
+constexpr int RS_BYTES = NCHK * BM * 32;             // fused P.v: fp32 partial sums received from the CTAs of the cluster, [src][chunk][row][8] = 12 x 4 KB
+constexpr int SMEM_BYTES = SMEM_BASE + RS_BYTES;
+constexpr int COL_S = 0, COL_R = 256, COL_O = 288, TMEM_COLS = 512;
+constexpr int PCH = BK / 8 + NRP / 8;                // chunks of the P tile / of the v^T tile: 32 key chunks + 4 relative-position chunks
+// fused P.v: the P tile [PCH][128 rows][16 B] and the v^T tile [PCH][96 dims][16 B] take the place of the q / k tiles once S is complete
+static_assert(PCH * BM * 16 + PCH * DK * 16 <= 2 * QPLANE_BYTES + 2 * KPLANE_BYTES, "P and v^T tiles must fit the q / k region");
 
 struct AParams {
     const uint8_t* qk;        // packed q / k planes of the qkv projection: [b][planes * cpp chunks][Lp][16 B]
@@ -47,6 +52,8 @@ struct AParams {
     uint8_t* vw;              // [b][h][nchunk_tot][DK][16 B]
     int32_t B, H, nh, T, Lp, W, nkt, nqt, nchunk_tot, planes;
     float inv;
+    // fused P.v (att != NULL): O = P.v + sum_r p[i, i+r-w] Ev[r] computed here, written as the packed fp16 operand of conv_o
+    uint8_t* att; int64_t att_bs; int32_t att_lo_chunks; const uint8_t* evT;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -61,6 +68,18 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t h2u_sat(float a, float b) {      // as the conv epilogue packs: saturating
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -82,6 +101,8 @@ __device__ __forceinline__ uint32_t h2u(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// PV: the P.v GEMM (and the relative-value term) runs here too — P never leaves the chip — and the cluster writes att, the packed operand of conv_o
+template <bool PV>
 __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const AParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* q_s = smem;                                  // [planes][NCHK][128][16]
@@ -94,8 +115,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
     float* mx_s = ls_s + NG * BM;                         // [MAXC][128] row maxima of every CTA of the cluster
     float* sm_s = mx_s + MAXC * BM;                       // [MAXC][128] row sums
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_s + MAXC * BM);
-    const uint32_t LOAD_FULL = tc::smem_u32(bars), ACC_FULL = LOAD_FULL + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const uint32_t LOAD_FULL = tc::smem_u32(bars), ACC_FULL = LOAD_FULL + 8, P_READY = LOAD_FULL + 16, O_FULL = LOAD_FULL + 24;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint8_t* p_s = smem;                                  // PV: [PCH][128][16] probabilities (K-major A operand), over the dead q / k tiles
+    uint8_t* v_s = smem + PCH * BM * 16;                  // PV: [PCH][96][16] v^T of this CTA's keys + Ev^T (K-major B operand)
+    float* rs_s = reinterpret_cast<float*>(smem + SMEM_BASE);     // PV: [src CTA][chunk][128][8] partial sums of this CTA's output chunks
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -108,6 +132,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
     if (threadIdx.x == 0) {
         tc::mbar_init(LOAD_FULL, 1);
         tc::mbar_init(ACC_FULL, 1);
+        tc::mbar_init(P_READY, NEPI / 32);
+        tc::mbar_init(O_FULL, 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
@@ -170,7 +196,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
         const bool qok = i < p.T;
         const int key0 = kt * BK;
         const float* mb = p.mask + (size_t)b * p.T;
-        if (qt == 0) {
+        // PV: this thread's share of v^T (six 8-key units of one dim each), requested now, converted and stored once the q / k tiles are dead
+        constexpr int VU = (BK / 8) * DK / NEPI;           // 6
+        float vst[PV ? VU : 1][8];
+        if constexpr (PV) {
+            const float* vb = p.qkv + ((size_t)b * 3 * p.H + 2 * p.H + h * DK) * p.T;
+#pragma unroll
+            for (int n = 0; n < VU; ++n) {
+                const int u = et + n * NEPI;
+                const int d = u / (BK / 8), cc = u - d * (BK / 8);      // lanes run over the key chunks of one dim: contiguous reads
+                const int k0 = key0 + 8 * cc;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) vst[n][t] = k0 + t < p.T ? vb[(size_t)d * p.T + k0 + t] : 0.f;
+            }
+        }
+        if (!PV && qt == 0) {
             // v^T for this CTA's keys (the P.v GEMM's per-batch weights), written by the clusters of query tile 0: [key / 8][d][8 keys] fp16
             const float* vb = p.qkv + ((size_t)b * 3 * p.H + 2 * p.H + h * DK) * p.T;
             uint8_t* vw = p.vw + ((size_t)(b * p.nh + h) * p.nchunk_tot) * DK * 16;
@@ -189,6 +229,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
         const int NR = 2 * p.W + 1;
         tc::mbar_wait(ACC_FULL, 0);
         tc::fence_after_sync();
+        if constexpr (PV) {
+            // S is complete: the q / k tiles are dead.  v^T of this CTA's keys, Ev^T behind it, zeros in the band chunks of the P tile.
+#pragma unroll
+            for (int n = 0; n < VU; ++n) {
+                const int u = et + n * NEPI;
+                const int d = u / (BK / 8), cc = u - d * (BK / 8);
+                *reinterpret_cast<uint4*>(v_s + ((size_t)cc * DK + d) * 16) =
+                    make_uint4(h2u(vst[n][0], vst[n][1]), h2u(vst[n][2], vst[n][3]), h2u(vst[n][4], vst[n][5]), h2u(vst[n][6], vst[n][7]));
+            }
+            if (et < (NRP / 8) * DK) *reinterpret_cast<uint4*>(v_s + ((size_t)(BK / 8) * DK + et) * 16) = reinterpret_cast<const uint4*>(p.evT)[et];
+            *reinterpret_cast<uint4*>(p_s + ((size_t)(BK / 8) * BM + et) * 16) = make_uint4(0, 0, 0, 0);      // 4 chunks x 128 rows = 512 units
+        }
         if (g == 0) {   // (q_i . Ek[r]) / sqrt(dk) for the 2w+1 relative positions -> row r of qe_s
             uint32_t v[32];
             tc::tmem_ld<32>(t_row + COL_R, v);
@@ -258,6 +310,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
         }
     }
     cluster_sync_all();                                    // (2) row sums
+    if constexpr (PV) {
+        if (warp == 1) {
+            // O[128, 96] = P[128, 256 + 32] . v^T[96, 256 + 32]^T once the softmax warps have written the P tile (pass C) and v^T is staged
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+            tc::mbar_wait(P_READY, 0);
+            tc::fence_after_sync();
+            const uint32_t idO = tc::make_idesc(0u, DK);
+            const uint32_t lboP = ((uint32_t)BM & 0x3FFFu) << 16, lboV = ((uint32_t)DK & 0x3FFFu) << 16;
+            const uint32_t pa = tc::smem_u32(p_s) >> 4, va = tc::smem_u32(v_s) >> 4;
+            for (int ks = 0; ks < PCH / 2; ++ks) {
+                const uint32_t da = lboP | ((pa + (uint32_t)(2 * ks * BM)) & 0x3FFFu);
+                const uint32_t db = lboV | ((va + (uint32_t)(2 * ks * DK)) & 0x3FFFu);
+                if (tc::elect_one()) tc::umma<false>(tmem_base + COL_O, ((uint64_t)desc_hi << 32) | da, ((uint64_t)desc_hi << 32) | db, idO, ks ? 1u : 0u);
+            }
+            if (tc::elect_one()) tc::umma_commit(O_FULL);
+            __syncwarp();
+        }
+    }
     if (warp >= 4) {
         const int q = warp & 3, g = (warp - 4) >> 2, r = q * 32 + lane;
         const int i = qt * BM + r;
@@ -274,25 +344,80 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
             uint32_t v[32];
             tc::tmem_ld<32>(t_row + COL_S + 64 * g + cb * 32, v);
             tc::tmem_ld_wait();
-            if (i < p.T) {
+            if (PV || i < p.T) {      // (PV: the whole tile is an MMA operand — rows past the sequence are written as zeros, rl = 0)
                 const bool band = rel0 + cb * 32 < NR && rel0 + cb * 32 + 31 >= 0;      // (any of these 32 keys within +-w of the query?)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     float p8[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) p8[t] = __uint_as_float(v[8 * u + t]) * rl;
-                    *reinterpret_cast<uint4*>(Pb + (size_t)(kt * (BK / 8) + g * 8 + cb * 4 + u) * p.Lp * 16) =
-                        make_uint4(h2u(p8[0], p8[1]), h2u(p8[2], p8[3]), h2u(p8[4], p8[5]), h2u(p8[6], p8[7]));
-                    if (band) {
+                    const uint4 pk = make_uint4(h2u(p8[0], p8[1]), h2u(p8[2], p8[3]), h2u(p8[4], p8[5]), h2u(p8[6], p8[7]));
+                    if constexpr (PV) *reinterpret_cast<uint4*>(p_s + ((size_t)(g * 8 + cb * 4 + u) * BM + r) * 16) = pk;
+                    else *reinterpret_cast<uint4*>(Pb + (size_t)(kt * (BK / 8) + g * 8 + cb * 4 + u) * p.Lp * 16) = pk;
+                    if (band && i < p.T) {
 #pragma unroll
                         for (int t = 0; t < 8; ++t) {
                             const int rel = rel0 + cb * 32 + 8 * u + t;
-                            if ((unsigned)rel < (unsigned)NR)
-                                *reinterpret_cast<__half*>(Pb + (size_t)(p.nchunk_tot - NRP / 8 + rel / 8) * p.Lp * 16 + (rel % 8) * 2) = __float2half_rn(p8[t]);
+                            if ((unsigned)rel < (unsigned)NR) {
+                                if constexpr (PV) *reinterpret_cast<__half*>(p_s + ((size_t)(BK / 8 + rel / 8) * BM + r) * 16 + (rel % 8) * 2) = __float2half_rn(p8[t]);
+                                else *reinterpret_cast<__half*>(Pb + (size_t)(p.nchunk_tot - NRP / 8 + rel / 8) * p.Lp * 16 + (rel % 8) * 2) = __float2half_rn(p8[t]);
+                            }
                         }
                     }
                 }
             }
+        }
+        if constexpr (PV) {
+            // ---- O = P . v: hand the tiles to the tensor core, then reduce-scatter the partial sums of the cluster's key tiles
+            tc::fence_before_sync();
+            tc::fence_proxy_async();          // the P / v^T tiles are read through the async proxy
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(P_READY);
+            tc::mbar_wait(O_FULL, 0);
+            tc::fence_after_sync();
+            // thread (r, g) holds output chunks 3g .. 3g+2 (8 dims each) of query r; chunk c belongs to CTA c / cpd of the cluster
+            const int cpd = NCHK / p.nkt;
+            uint32_t o16[16], o8[8];
+            tc::tmem_ld<16>(t_row + COL_O + 24 * g, o16);
+            tmem_ld8(t_row + COL_O + 24 * g + 16, o8);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int c8 = 0; c8 < 3; ++c8) {
+                const int ch = 3 * g + c8, dst = ch / cpd, pos = ch - dst * cpd;
+                const uint32_t a = mapa(tc::smem_u32(rs_s + ((size_t)(kt * cpd + pos) * BM + r) * 8), (uint32_t)dst);
+                const uint32_t* o = c8 < 2 ? &o16[8 * c8] : &o8[0];
+                st_cluster_v4(a, __uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
+                st_cluster_v4(a + 16, __uint_as_float(o[4]), __uint_as_float(o[5]), __uint_as_float(o[6]), __uint_as_float(o[7]));
+            }
+        }
+    }
+    if constexpr (PV) {
+        tc::fence_before_sync();
+        cluster_sync_all();                                // (3) every CTA holds the partial sums of its output chunks
+        if (warp >= 4) {
+            const int q = warp & 3, g = (warp - 4) >> 2, r = q * 32 + lane;
+            const int i = qt * BM + r;
+            const int cpd = NCHK / p.nkt;
+            if (i < p.T)
+                for (int pos = g; pos < cpd; pos += NG) {
+                    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    for (int k = 0; k < p.nkt; ++k) {
+                        const float4 a = *reinterpret_cast<const float4*>(rs_s + ((size_t)(k * cpd + pos) * BM + r) * 8);
+                        const float4 c = *reinterpret_cast<const float4*>(rs_s + ((size_t)(k * cpd + pos) * BM + r) * 8 + 4);
+                        o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w; o[4] += c.x; o[5] += c.y; o[6] += c.z; o[7] += c.w;
+                    }
+                    // the packed operand of conv_o: hi = fp16(O), lo = fp16(O - hi) (what the P.v launch's epilogue writes: y_act / y_lo)
+                    uint8_t* dstp = p.att + (size_t)b * p.att_bs + ((size_t)(h * NCHK + kt * cpd + pos) * p.Lp + PADL + i) * 16;
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        hw[t] = h2u_sat(o[2 * t], o[2 * t + 1]);
+                        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[t]));
+                        lw[t] = h2u_sat(o[2 * t] - hf.x, o[2 * t + 1] - hf.y);
+                    }
+                    *reinterpret_cast<uint4*>(dstp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    if (p.att_lo_chunks) *reinterpret_cast<uint4*>(dstp + (size_t)p.att_lo_chunks * p.Lp * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
         }
     }
 
@@ -309,26 +434,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_scores_cluster_kernel(const 
 RVC_API int rvc_attn_scores_cluster_tc(const rvc_attn_scores_desc* dp, void* stream) {
     if (!dp) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: null descriptor");
     const rvc_attn_scores_desc& d = *dp;
-    if (!d.qk || !d.ek || !d.qkv || !d.mask || !d.P || !d.vw) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: null pointer");
+    const bool pv = d.att != nullptr;
+    if (!d.qk || !d.ek || !d.qkv || !d.mask || (!pv && (!d.P || !d.vw))) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: null pointer");
+    if (pv && (!d.evT || (((uintptr_t)d.att | (uintptr_t)d.evT) & 15) || d.att_bs <= 0 || d.att_lo_chunks < 0))
+        return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: the fused P.v needs evT, a 16-byte aligned att and its batch stride");
     if (d.B <= 0 || d.T <= 0 || d.T > BK * MAXC || d.n_heads <= 0 || d.H != d.n_heads * DK)
         return rvc::fail(RVC_ESHAPE, "rvc_attn_scores_cluster_tc: built for head dim 96 and T <= 1024 (got H = %d, heads = %d, T = %d)", d.H, d.n_heads, d.T);
     if (d.window < 0 || 2 * d.window + 1 > QE_LD) return rvc::fail(RVC_ESHAPE, "rvc_attn_scores_cluster_tc: window %d > 11", d.window);
     if (d.planes != 1 && d.planes != 2) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: planes must be 1 or 2");
-    if (((uintptr_t)d.qk | (uintptr_t)d.ek | (uintptr_t)d.P | (uintptr_t)d.vw) & 15) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: packed buffers need 16-byte alignment");
+    if (((uintptr_t)d.qk | (uintptr_t)d.ek | (uintptr_t)(pv ? nullptr : d.P) | (uintptr_t)(pv ? nullptr : d.vw)) & 15) return rvc::fail(RVC_EINVAL, "rvc_attn_scores_cluster_tc: packed buffers need 16-byte alignment");
     AParams p;
     p.qk = (const uint8_t*)d.qk; p.qk_bs = d.qk_bs; p.q_chunk0 = d.q_chunk0; p.k_chunk0 = d.k_chunk0; p.head_chunks = NCHK; p.lo_chunks = d.planes == 2 ? d.lo_chunks : 0;
     p.ek = (const uint8_t*)d.ek; p.qkv = d.qkv; p.mask = d.mask; p.P = (uint8_t*)d.P; p.vw = (uint8_t*)d.vw;
     p.B = d.B; p.H = d.H; p.nh = d.n_heads; p.T = d.T; p.Lp = (int)rvc_packed_rows(d.T); p.W = d.window;
     p.nkt = (d.T + BK - 1) / BK; p.nqt = (d.T + BM - 1) / BM; p.nchunk_tot = p.nkt * (BK / 8) + NRP / 8; p.planes = d.planes;
     p.inv = 1.f / sqrtf((float)DK);
-    auto kern = attn_scores_cluster_kernel;
-    static bool opted[64] = {false};
+    p.att = (uint8_t*)d.att; p.att_bs = d.att_bs; p.att_lo_chunks = d.att_lo_chunks; p.evT = (const uint8_t*)d.evT;
+    auto kern = pv ? attn_scores_cluster_kernel<true> : attn_scores_cluster_kernel<false>;
+    static bool opted[2][64] = {{false}};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !opted[dev]) {
+    if (dev < 0 || dev >= 64 || !opted[pv][dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return rvc::fail((int)e, "rvc_attn_scores_cluster_tc: smem opt-in: %s", cudaGetErrorString(e));
-        if (dev >= 0 && dev < 64) opted[dev] = true;
+        if (dev >= 0 && dev < 64) opted[pv][dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(d.B * d.n_heads * p.nqt * p.nkt));

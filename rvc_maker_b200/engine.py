@@ -173,6 +173,8 @@ class Engine:
         self.use_flow_cluster = os.environ.get("RVC_B200_FLOW_CLUSTER", "1") != "0"
         # attention scores + softmax of a layer as one cluster kernel for T <= 1024 (rvc_attn_scores_cluster_tc) instead of S launch + softmax launch
         self.use_attn_cluster = os.environ.get("RVC_B200_ATTN_CLUSTER", "1") != "0"
+        # ... with the P.v GEMM inside it (P stays in shared memory, the key tiles' partial sums are reduce-scattered through DSMEM): one launch less per layer
+        self.attn_pv = os.environ.get("RVC_B200_ATTN_PV", "1") != "0"
         # conv_o -> LayerNorm -> FFN -> LayerNorm of an encoder layer as one cluster kernel (rvc_encoder_tail_tc) instead of five launches
         self.use_enc_tail = os.environ.get("RVC_B200_ENC_TAIL", "1") != "0"
         # the NSF source (SineGen + the long noise convs: 70 us of CUDA-core work that depends on f0 only) on a side branch of the graph, next to the
@@ -603,7 +605,8 @@ class Engine:
                 Pb = self._zbuf(p, B * nh * (Tk // 8) * Lp * 16)
                 Rb = self._buf(p, B, H, T)
                 vwb = self._buf(p, B * nh * (Tk // 8) * dk * 4, dtype=torch.int32)
-            if attn_cl:
+            attn_pv = attn_cl and self.attn_pv
+            if attn_cl and not attn_pv:
                 Tk = (T + 255) // 256 * 256                        # one 256-key tile per CTA of the cluster
                 nct = Tk // 8 + 4                                  # key chunks + the four "relative position" chunks of P / of the P.v weights
                 Pb = self._zbuf(p, B * nh * nct * Lp * 16)         # (band entries whose key falls outside the sequence stay zero)
@@ -612,23 +615,33 @@ class Engine:
                     vw_i = self._zbuf(p, B * nh * nct * dk * 16)
                     vw_i.view(B * nh, nct, dk * 16)[:, Tk // 8:, :] = W[f"t_evT{i}"].view(1, 4, dk * 16)
                     vws.append(vw_i)
+            elif attn_cl:
+                Tk = (T + 255) // 256 * 256
             for i in range(c["nl"]):
                 gemm(f"qkv{i}", xa, H, f"t_qkv_w{i}", 3 * H, dict(bias=W[f"qkv_b{i}"], y=vqkv, **(outs(qkva, 3 * H) if tc_attn else {})))
                 if attn_cl:
                     # scores + softmax in one cluster kernel; P carries the band probabilities as 32 extra columns, the P.v weights carry emb_rel_v^T
                     ad = AttnScoresDesc()
                     ad.qk, ad.qk_bs, ad.q_chunk0, ad.k_chunk0, ad.lo_chunks, ad.planes = qkva.data_ptr(), qkv_bs, 0, H // 8, 3 * H // 8, npl
-                    ad.ek, ad.qkv, ad.mask, ad.P, ad.vw = W[f"t_ek_p{i}"].data_ptr(), qkv.data_ptr(), p.mask.data_ptr(), Pb.data_ptr(), vws[i].data_ptr()
+                    ad.ek, ad.qkv, ad.mask = W[f"t_ek_p{i}"].data_ptr(), qkv.data_ptr(), p.mask.data_ptr()
                     ad.B, ad.H, ad.n_heads, ad.T, ad.window = B, H, nh, T, WINDOW
                     p.keep.append(ad)
-                    p.add(f"attn_sc{i}", lib.rvc_attn_scores_cluster_tc, C.byref(ad), flops=2.0 * B * H * T * T, bytes_=B * nh * (Tk * T * 2.0 + 2.0 * 4 * H // nh * T),
-                          kind="attn_scores_cluster_tc")
-                    jobs = []
-                    for h in range(nh):
-                        ya = atta.data_ptr() + (h * dk // 8) * cb
-                        jobs.append(dict(a=Pb.data_ptr() + h * nct * cb, a_bs=nh * nct * cb, w=vws[i].data_ptr() + h * nct * dk * 16, w_bs=nh * nct * dk * 16,
-                                         y_act=ya, y_act_bs=npl * (H // 8) * cb, y_lo=(ya + (H // 8) * cb if split else None)))
-                    self._tc(p, f"attn_pv{i}", jobs, B=B, Cin=Tk + 32, Cout=dk, L=T, dtype=dt, tag="attn", flops=2.0 * B * H * T * T)
+                    if attn_pv:
+                        # ... and P.v (+ the relative-value term) in the same kernel: it writes the packed operand of conv_o directly
+                        ad.att, ad.att_bs, ad.att_lo_chunks, ad.evT = atta.data_ptr(), npl * (H // 8) * cb, (H // 8 if split else 0), W[f"t_evT{i}"].data_ptr()
+                        p.add(f"attn_sc{i}", lib.rvc_attn_scores_cluster_tc, C.byref(ad), flops=4.0 * B * H * T * T, bytes_=B * (2.0 * 4 * H * T + 4.0 * H * T),
+                              kind="attn_scores_cluster_tc")
+                    else:
+                        ad.P, ad.vw = Pb.data_ptr(), vws[i].data_ptr()
+                        p.add(f"attn_sc{i}", lib.rvc_attn_scores_cluster_tc, C.byref(ad), flops=2.0 * B * H * T * T, bytes_=B * nh * (Tk * T * 2.0 + 2.0 * 4 * H // nh * T),
+                              kind="attn_scores_cluster_tc")
+                    if not attn_pv:
+                        jobs = []
+                        for h in range(nh):
+                            ya = atta.data_ptr() + (h * dk // 8) * cb
+                            jobs.append(dict(a=Pb.data_ptr() + h * nct * cb, a_bs=nh * nct * cb, w=vws[i].data_ptr() + h * nct * dk * 16, w_bs=nh * nct * dk * 16,
+                                             y_act=ya, y_act_bs=npl * (H // 8) * cb, y_lo=(ya + (H // 8) * cb if split else None)))
+                        self._tc(p, f"attn_pv{i}", jobs, B=B, Cin=Tk + 32, Cout=dk, L=T, dtype=dt, tag="attn", flops=2.0 * B * H * T * T)
                 elif tc_attn:
                     # S[b][h][key/8][query][8] = q . k^T (channel-blocked over the keys): the packed k activations of each batch item are the GEMM's weights
                     jobs = []

@@ -403,6 +403,35 @@ def test_attention_cluster_kernel_matches_per_launch_path(B, T, monkeypatch):
     assert torch.equal(again["m_p"], out["m_p"]) and torch.equal(again["o"], out["o"])
 
 
+@pytest.mark.parametrize("B,T", [(1, 1000), (2, 173), (3, 128), (2, 129), (1, 1), (2, 1024), (2, 700), (2, 300), (40, 64)])
+def test_attention_cluster_fused_pv_matches_separate_launch(B, T, monkeypatch):
+    """rvc_attn_scores_desc.att: the P.v GEMM (and the relative-value term) inside the attention cluster kernel — P stays in shared memory, every CTA
+    multiplies its 256-key slice, the partial sums are reduce-scattered through distributed shared memory — against the same kernel followed by the
+    separate P.v launch: identical fp16 P and v, fp32 sums in a different order.  Clusters of 1, 2, 3 and 4 CTAs, ragged lengths, T = 1."""
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=79, heated=True)
+    inp = cases.synth_inputs(cfg, B, T, seed=7 * B + T, ragged=B > 1)
+    monkeypatch.setenv("RVC_B200_ATTN_PV", "0")
+    ref_net = build_net(cfg, sd, True, precision="tc")
+    ref = run_net(ref_net, inp)
+    assert any(m and m["name"] == "attn_pv0" for m in ref_net._engine.plan("enc", B, T).meta)
+    monkeypatch.setenv("RVC_B200_ATTN_PV", "1")
+    net = build_net(cfg, sd, True, precision="tc")
+    out = run_net(net, inp)
+    names = [m["name"] for m in net._engine.plan("enc", B, T).meta if m]
+    assert "attn_sc0" in names and "attn_pv0" not in names
+    for k in ("m_p", "logs_p", "z"):
+        assert torch.isfinite(out[k]).all(), k
+        scale = float(ref[k].abs().max())
+        err = float((out[k] - ref[k]).abs().max())
+        print(f"[attn fused P.v B={B} T={T}] {k}: err {err:.2e} (max|ref| {scale:.2f})")
+        # (a last-bit difference of O flips fp16 roundings further down the six layers: the same size as between the other kernel paths)
+        assert err <= 2e-3 * max(1.0, scale), (k, err, scale)
+    assert float((out["o"] - ref["o"]).abs().max()) <= 6e-4
+    again = run_net(net, inp)
+    assert torch.equal(again["m_p"], out["m_p"]) and torch.equal(again["o"], out["o"])
+
+
 @pytest.mark.parametrize("B,T", [(1, 1000), (2, 173), (3, 124), (2, 125), (1, 1), (2, 1300), (40, 64)])
 def test_encoder_tail_cluster_kernel_matches_per_launch_path(B, T, monkeypatch):
     """rvc_encoder_tail_tc (conv_o -> LayerNorm -> conv_1 -> relu -> conv_2 -> LayerNorm of a layer in one cluster kernel: LayerNorm statistics and the

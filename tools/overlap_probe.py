@@ -119,5 +119,48 @@ def lanes_alone(split):
 
 
 lanes_alone(i_flow)
+
+
+def measure_front_subset(frac, label, front_limit=0):
+    """front lane with only a fraction of the encoder's launches (timing only): is the overlapped step bound by the front lane's progress?
+    front_limit: cap on the CTAs of the front lane's persistent launches (they are latency-bound: fewer CTAs steal less SM time from the generator)"""
+    sf, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    n_enc = int(len(pe.ops) * frac)
+    lib.rvc_set_grid_limit(front_limit)
+    gf = capture(lambda st: (run_ops(pe, 0, n_enc, st), run_ops(pd, 0, i_flow, st)), sf)
+    lib.rvc_set_grid_limit(0)
+    gb = capture(lambda st: run_ops(pd, i_flow, len(pd.ops), st), sb)
+    def piped(n):
+        evf = [torch.cuda.Event() for _ in range(n)]
+        with torch.cuda.stream(sf):
+            gf.replay(); evf[0].record(sf)
+        for i in range(n):
+            if i + 1 < n:
+                with torch.cuda.stream(sf):
+                    gf.replay(); evf[i + 1].record(sf)
+            with torch.cuda.stream(sb):
+                sb.wait_event(evf[i])
+                gb.replay()
+        sf.wait_stream(sb)
+    piped(3)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(sf):
+        a.record(sf)
+    piped(steps)
+    with torch.cuda.stream(sf):
+        sf.wait_stream(sb)
+        b.record(sf)
+    torch.cuda.synchronize()
+    print(f"{label}: {n_enc} of {len(pe.ops)} encoder launches + flow in the front lane, front grid limit {front_limit}: overlapped {a.elapsed_time(b) / steps:.3f} ms/step")
+
+
+for rep in range(2):
+    for lim in (0, 96, 64, 48, 32, 24, 16, 8):
+        measure_front_subset(1.0, "front grid cap", front_limit=lim)
+for rep in range(1):
+    measure(i_flow, 0, 0, "enc + flow")
+raise SystemExit(0)
+
 for rep in range(2):
     measure(i_flow, 0, 0, "enc + flow")
