@@ -8,7 +8,8 @@ python bench.py --steps 20 --warmup 3 --ops-json $O/${L}_ops.json > $O/${L}_benc
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${L}_bench_reference_arm.json 2>> $O/${L}_bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum,launch__grid_size --clock-control none -k "$K" -s 116 -c 140 --csv --log-file $O/${L}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${L}_ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv1d_tc_kernel -s 23 -c 6 -f -o $O/${L}_full_C128 \
+# (the C = 128 stage: ups1 is the first <128, 2, ...> launch of a pass, the six ResBlock launches follow)
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:conv1d_tc_kernel<\(int\)128, \(int\)2' -s 1 -c 6 -f -o $O/${L}_full_C128 \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${L}_ncu_full_C128.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:resblock_pair -s 0 -c 6 -f -o $O/${L}_full_pair \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${L}_ncu_full_pair.log 2>&1
