@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 25
+#define RVC_ABI_VERSION 26
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -401,6 +401,31 @@ int rvc_feature_prep_f32(const float* feats, const float* feats0, const float* p
 /* result[b] = max(result[b], max_i |x[b*x_bs + i]|), i < n — the peak the pipeline normalises by (`np.abs(audio_opt).max()`,
  * convert.py:451), accumulated chunk by chunk on the device; the caller zeroes `result` first. */
 int rvc_absmax_f32(const float* x, int64_t x_bs, int64_t n, float* result, int32_t B, void* stream);
+
+/*
+ * The f0 tail between the RMVPE network and Synthesizer.infer (round 2, third session; SURVEY 8f-2, post-network part).  The reference moves
+ * the salience map to the host and does this in numpy (float64; float32 for the salience sums); here it stays on the device.
+ *
+ * rvc_rmvpe_decode_f32 — RMVPE.decode + to_local_average_cents (main/library/predictors/RMVPE.py:217-221, :237-252):
+ *   salience [T][360] fp32 (row stride in elements) -> f0 [T] float64 (Hz, 0 = unvoiced).  Per frame: first arg-max, the 9 bins around it
+ *   (zero padding outside 0..359), cents = sum(s*c)/sum(s) with the reference's operation order and widths (products float64, the 9-term
+ *   sums in numpy's pairwise order, denominator summed in float32), 0 where max <= thred, f0 = 10*2^(cents/1200), f0 == 10 -> 0.
+ *   gate_hi > 0: f0 outside [gate_lo, gate_hi] -> 0 (`infer_from_audio_with_pitch`, :229-233, the "rmvpe-legacy" method).
+ * rvc_f0_coarse_f64 — the tail of VC.get_f0 (main/inference/convert.py:308-323) on a float64 f0 track of n frames:
+ *   notes != NULL: Autotune.autotune_f0 (:173-179) towards the nearest of n_notes device-resident note frequencies (:200), by `strength`;
+ *   f0 *= shift (shift = pow(2, semitones/12) computed by the caller in double, :311); coarse = rint(clip(mel map to 1..255)) (:318-323) with
+ *   mel_min / mel_max = 1127*ln(1 + {50,1100}/700) (:198-199).  Writes pitch (int64, `.long()` of :439), pitchf (float32 of the shifted f0,
+ *   `.float()` of :439) and, when f0_out != NULL, the shifted float64 f0.  f0 / f0_out may alias.
+ * rvc_rmvpe_pitch_f32 — both in one launch (salience -> pitch, pitchf [, f0]).
+ * Integer results are bit-exact; exp2 / log are the CUDA double routines (<= 1 ulp).
+ */
+int rvc_rmvpe_decode_f32(const float* salience, int64_t row_stride, int32_t T, float thred, double gate_lo, double gate_hi, double* f0,
+                         void* stream);
+int rvc_f0_coarse_f64(const double* f0, int64_t n, const double* notes, int32_t n_notes, double strength, double shift, double mel_min,
+                      double mel_max, int64_t* pitch, float* pitchf, double* f0_out, void* stream);
+int rvc_rmvpe_pitch_f32(const float* salience, int64_t row_stride, int32_t T, float thred, double gate_lo, double gate_hi,
+                        const double* notes, int32_t n_notes, double strength, double shift, double mel_min, double mel_max,
+                        int64_t* pitch, float* pitchf, double* f0_out, void* stream);
 
 #ifdef __cplusplus
 }

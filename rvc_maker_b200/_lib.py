@@ -10,12 +10,12 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # RVC_B200_LIB: debugging builds of the same library only (tools/pair_trace.py -> librvc_b200_trace.so); never a fallback
 LIB_PATH = os.environ.get("RVC_B200_LIB") or os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 25
+ABI_VERSION = 26
 DT_BF16, DT_FP16, DT_FP16_SPLIT = 0, 2, 3
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
-_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 
 class Conv1dDesc(C.Structure):
@@ -132,6 +132,9 @@ SIGNATURES = {
     "rvc_noise_conv_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rvc_feature_prep_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rvc_absmax_f32": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp]),
+    "rvc_rmvpe_decode_f32": (C.c_int, [_vp, _i64, _i32, _f32, _f64, _f64, _vp, _vp]),
+    "rvc_f0_coarse_f64": (C.c_int, [_vp, _i64, _vp, _i32, _f64, _f64, _f64, _f64, _vp, _vp, _vp, _vp]),
+    "rvc_rmvpe_pitch_f32": (C.c_int, [_vp, _i64, _i32, _f32, _f64, _f64, _vp, _i32, _f64, _f64, _f64, _f64, _vp, _vp, _vp, _vp]),
     "rvc_resblock_pair_tc": (C.c_int, [C.POINTER(ResblockPairDesc), _vp]),
     "rvc_debug_pair_trace": (C.c_int, [_vp, _i32]),
     "rvc_set_grid_limit": (C.c_int, [_i32]),

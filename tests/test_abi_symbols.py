@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.rvc_abi_version() == 25
+    assert lib.rvc_abi_version() == 26
     # argument validation happens before any CUDA call, so it is checkable without a GPU
     rc = lib.rvc_conv1d_f32(None, None)
     assert rc == -1
@@ -83,3 +83,27 @@ def test_no_oracle_import_in_product():
             isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n) for n in ast.walk(node))
         if uses:
             assert isinstance(node, ast.FunctionDef) and node.name in ("cpu_baseline", "gpu_eager_baseline"), getattr(node, "name", node)
+
+
+def test_f0_tail_argument_errors(lib):
+    """rvc_rmvpe_decode_f32 / rvc_f0_coarse_f64 / rvc_rmvpe_pitch_f32 validate before any CUDA call."""
+    assert lib.rvc_rmvpe_decode_f32(None, 360, 10, 0.03, 0.0, 0.0, None, None) == -1
+    assert lib.rvc_rmvpe_decode_f32(8, 359, 10, 0.03, 0.0, 0.0, 8, None) == -2 and b"360" in lib.rvc_last_error()
+    assert lib.rvc_f0_coarse_f64(8, 10, None, 0, 1.0, 0.0, 1.0, 2.0, 8, 8, None, None) == -1 and b"shift" in lib.rvc_last_error()
+    assert lib.rvc_f0_coarse_f64(8, 10, 8, 0, 1.0, 1.0, 1.0, 2.0, 8, 8, None, None) == -1 and b"n_notes" in lib.rvc_last_error()
+    assert lib.rvc_rmvpe_pitch_f32(8, 360, 10, 0.03, 0.0, 0.0, None, 0, 1.0, 1.0, 2.0, 1.0, 8, 8, None, None) == -1 and b"mel_max" in lib.rvc_last_error()
+    assert lib.rvc_rmvpe_pitch_f32(8, 360, 0, 0.03, 0.0, 0.0, None, 0, 1.0, 1.0, 1.0, 2.0, 8, 8, None, None) == 0      # T == 0: nothing to do
+
+
+def test_pitch_module_refuses_cpu_tensors():
+    import numpy as np
+    import torch
+
+    from rvc_maker_b200 import pitch
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pitch.decode(torch.zeros(4, 360))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pitch.rmvpe_pitch(np.zeros((4, 360), np.float32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pitch.get_f0_tail(torch.zeros(4, dtype=torch.float64))

@@ -1,0 +1,67 @@
+"""Timing of the f0 tail kernels (csrc/f0_post.cu) with CUDA events, and of the reference's host path (numpy oracle) beside it.
+
+    python tools/f0_tail_probe.py [--json out.json]
+
+Algorithmic bytes of rvc_rmvpe_pitch_f32: the salience map read once (T x 360 x 4 B) + 12 B of pitch / pitchf written per frame."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import f0_oracle  # noqa: E402  (timing baseline only)
+from rvc_maker_b200 import pitch as P  # noqa: E402
+
+
+def time_gpu(fn, iters=50, flush=None):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    rows = []
+    for T in (1001, 60001, 1_000_000):
+        sal_h = f0_oracle.synthetic_salience(min(T, 60001), 3)
+        sal = torch.from_numpy(sal_h).cuda()
+        if T > sal.shape[0]:
+            sal = sal.repeat(-(-T // sal.shape[0]), 1)[:T].contiguous()
+        nbytes = T * 360 * 4 + T * 12
+        med, best = time_gpu(lambda: P.rmvpe_pitch(sal, pitch=2), flush=flush)
+        med_t, _ = time_gpu(lambda: P.rmvpe_pitch(sal, pitch=2, f0_autotune=True), flush=flush)
+        f0 = P.decode(sal)
+        med_c, _ = time_gpu(lambda: P.get_f0_tail(f0, pitch=2), flush=flush)
+        row = dict(T=T, audio_s=T / 100.0, rmvpe_pitch_us=med, rmvpe_pitch_best_us=best, rmvpe_pitch_autotune_us=med_t, f0_coarse_us=med_c,
+                   gbs=nbytes / med / 1e3, hbm_frac=nbytes / med / 1e3 / peaks["hbm_gbs"])
+        if T <= 60001:
+            t0 = time.perf_counter()
+            with np.errstate(all="ignore"):
+                f0_oracle.get_f0_tail(f0_oracle.decode(sal_h), pitch=2)
+            row["numpy_host_us"] = (time.perf_counter() - t0) * 1e6
+            t0 = time.perf_counter()
+            h = sal.cpu().numpy()                                     # the D2H copy the reference pays first (RMVPE.py:226)
+            row["d2h_copy_us"] = (time.perf_counter() - t0) * 1e6
+        rows.append(row)
+        print(json.dumps(row))
+    if "--json" in sys.argv:
+        json.dump(rows, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
