@@ -1131,6 +1131,14 @@ class Engine:
                 return i
         return 0
 
+    GROUP_MAX = 8
+
+    def group_size(self, B, T):
+        """How many consecutive items of shape (B, T) ``infer_lanes`` runs as one batch: as many as fit RVC_B200_GROUP_FRAMES frames (default 3000,
+        i.e. three 10 s chunks; 0 = every item on its own), at most GROUP_MAX.  Measured on the 10 s clip of configs[1] (bench.py, ms per chunk):
+        1 chunk per pass 2.06, 2: 1.88, 3: 1.83 - 1.89, 4: 1.85 - 1.91, 6: 1.92, 8: 1.93 (larger batches run into the power cap)."""
+        return max(1, min(self.GROUP_MAX, int(os.environ.get("RVC_B200_GROUP_FRAMES", "3000")) // max(1, B * T)))
+
     def infer_lanes(self, items, out_dtype):
         """Pipelined ``infer`` over an iterable of ``(phone, phone_lengths, pitch, nsff0, sid[, rate[, noise]])``: yields the result tuples in order.
 
@@ -1141,8 +1149,12 @@ class Engine:
         hand SMs over at their launch boundaries (measured: 2.25 -> 2.06 ms per 10 s chunk; capping the generator's grids to reserve SMs for
         the other lane, giving either lane priority, or dealing the generator's tiles dynamically was no faster: tools/overlap_probe.py).
         The generator plan exists twice (slots i % 2: chunk i+1's flow writes z while chunk i's generator still reads its own); the front lane
-        of chunk i+2 waits for the back lane of chunk i.  Same kernels, same RNG draw order, same results as ``infer`` item by item
-        (tests/test_gpu_parity.py).  A result is handed out once the NEXT item has been enqueued, or at the end.
+        of chunk i+2 waits for the back lane of chunk i.  Consecutive short items of one shape are batched (``group_size``: three 10 s chunks per pass —
+        the encoder's chains of launches take as long for two chunks as for one); every item keeps its own inputs, speaker and noise draws.  Same
+        kernels and RNG draw order as ``infer`` item by item; a group's results equal ``infer`` on the stacked batch bit for bit, and ``infer`` item by
+        item up to the summation order of the tensor-core generator, whose tile shapes follow the batch (rvc_conv1d_tc; ~2e-4 on the waveform; the
+        encoder and flow outputs are bit-identical).  With RVC_B200_GROUP_FRAMES=0 nothing is batched and everything is bit-identical
+        (tests/test_gpu_parity.py).  The results of a group are handed out once the NEXT group has been enqueued, or at the end.
         """
         c = self.cfg
         dev = self.dev
@@ -1159,42 +1171,70 @@ class Engine:
         n_item = 0
 
         def finish(h):
-            res, stats, pd_shape, ev, offsets = h
+            """the result tuples of the items of one group: views of the group's (fresh) result arena, one slice of the batch per item"""
+            res, stats, pd_shape, ev, offsets, G = h
             caller.wait_event(ev)
             res.record_stream(caller)
             stats.record_stream(caller)
-            B, T2 = pd_shape
+            GB, T2 = pd_shape
+            B = GB // G
             I = c["I"]
             n_o, n_m, n_z = offsets
             Lfin = T2 * c["upp"]
-            o = res[:B * Lfin].view(B, 1, Lfin)
-            x_mask = res[n_o:n_o + B * T2].view(B, 1, T2)
-            z = res[n_o + n_m:n_o + n_m + B * I * T2].view(B, I, T2)
-            z_p = res[n_o + n_m + n_z:n_o + n_m + n_z + B * I * T2].view(B, I, T2)
-            return o, x_mask, (z, z_p, stats[:, :I], stats[:, I:])
+            o = res[:GB * Lfin].view(GB, 1, Lfin)
+            x_mask = res[n_o:n_o + GB * T2].view(GB, 1, T2)
+            z = res[n_o + n_m:n_o + n_m + GB * I * T2].view(GB, I, T2)
+            z_p = res[n_o + n_m + n_z:n_o + n_m + n_z + GB * I * T2].view(GB, I, T2)
+            for i in range(G):
+                sl = slice(i * B, (i + 1) * B)
+                yield o[sl], x_mask[sl], (z[sl], z_p[sl], stats[sl, :I], stats[sl, I:])
+
+        def signature(item):
+            phone, lengths, pitch, nsff0, sid = item[:5]
+            if phone.dim() != 3 or phone.shape[2] != c["D"]:
+                raise ValueError(f"phone must be [B, T, {c['D']}], got {tuple(phone.shape)}")
+            if c["f0"] and (pitch is None or nsff0 is None):
+                raise ValueError("use_f0 model: pitch and nsff0 are required")
+            if sid is None:
+                raise ValueError("sid is required")
+            rate = item[5] if len(item) > 5 else None
+            noise = item[6] if len(item) > 6 else None
+            return (int(phone.shape[0]), int(phone.shape[1]), rate, noise is None)
+
+        def grouped(it):
+            """consecutive items of one shape, as many as fit ``group_frames`` frames: they run as ONE batch (a chunk's encoder and flow are chains of
+            launches that take as long for two short chunks as for one), every item with its own inputs, speaker and noise draws"""
+            grp, sig = [], None
+            for item in it:
+                item = tuple(item)
+                s_ = signature(item)
+                if grp and (s_ != sig or len(grp) >= gmax):
+                    yield grp
+                    grp = []
+                if not grp:
+                    sig = s_
+                    gmax = self.group_size(s_[0], s_[1])
+                grp.append(item)
+            if grp:
+                yield grp
 
         try:
-            for item in items:
-                phone, phone_lengths, pitch, nsff0, sid = item[:5]
-                rate = item[5] if len(item) > 5 else None
-                noise = item[6] if len(item) > 6 else None
-                if phone.dim() != 3 or phone.shape[2] != c["D"]:
-                    raise ValueError(f"phone must be [B, T, {c['D']}], got {tuple(phone.shape)}")
-                B, T = int(phone.shape[0]), int(phone.shape[1])
-                if c["f0"] and (pitch is None or nsff0 is None):
-                    raise ValueError("use_f0 model: pitch and nsff0 are required")
-                if sid is None:
-                    raise ValueError("sid is required")
+            for grp in grouped(items):
+                G = len(grp)
+                Bi, T = int(grp[0][0].shape[0]), int(grp[0][0].shape[1])
+                B = G * Bi
+                rate = grp[0][5] if len(grp[0]) > 5 else None
                 head = int(T * (1.0 - rate)) if rate is not None else 0
                 T2 = T - head
                 slot = n_item % 2
                 n_item += 1
                 F = F0 if B * T < lane_max else D
                 dkey = ("dec", B, T2) if slot == 0 else ("dec", B, T2, slot)
+                rows = [slice(i * Bi, (i + 1) * Bi) for i in range(G)]
                 with self._lock, torch.cuda.device(dev):
                     if len(self.plans) >= self.max_plans - 1 and (("enc", B, T) not in self.plans or dkey not in self.plans):
                         torch.cuda.synchronize(dev)      # a plan is about to be evicted: nothing of either lane may still be using its buffers
-                    F.wait_stream(caller)                # the item's tensors may have been produced on the caller's stream
+                    F.wait_stream(caller)                # the items' tensors may have been produced on the caller's stream
                     D.wait_stream(caller)
                     with torch.cuda.stream(F):
                         pe = self.plan("enc", B, T)
@@ -1202,19 +1242,39 @@ class Engine:
                         used[:] = [pl for pl in used if pl is not pe and pl is not pd] + [pe, pd]
                         if done[slot] is not None:
                             F.wait_event(done[slot])     # this slot's generator plan is free again
-                        pe.phone.copy_(phone, non_blocking=True)
-                        pe.lengths.copy_(phone_lengths, non_blocking=True)
+                    # inputs and noise item by item, in the order ``infer`` called item by item would draw: randn_like(m_p) (front lane), then
+                    # rand_ini and randn_like(sine_waves) (back lane: the back lane is in order, so its buffers are free when the draws run)
+                    for item, r in zip(grp, rows):
+                        phone, phone_lengths, pitch, nsff0, sid = item[:5]
+                        noise = item[6] if len(item) > 6 else None
+                        with torch.cuda.stream(F):
+                            pe.phone[r].copy_(phone, non_blocking=True)
+                            pe.lengths[r].copy_(phone_lengths, non_blocking=True)
+                            if c["f0"]:
+                                pe.pitch[r].copy_(pitch, non_blocking=True)
+                            if noise is not None:
+                                pe.eps_z[r].copy_(noise[0], non_blocking=True)
+                            else:
+                                pe.eps_z[r].normal_()        # randn_like(m_p), synthesizers.py:449
+                            # (the flow's WaveNets are conditioned on the speaker: cond_layer(emb_g(sid)) belongs to the front lane)
+                            if self.cond_table is not None:
+                                pd.gc[r].copy_(self.cond_table[sid.to(dev, non_blocking=True)])
+                            else:
+                                pd.g[r].copy_(self.W["emb_g"][sid.to(dev, non_blocking=True)])
+                            for t in (phone, phone_lengths, pitch, sid):
+                                if t is not None and t.is_cuda:
+                                    t.record_stream(F)
                         if c["f0"]:
-                            pe.pitch.copy_(pitch, non_blocking=True)
-                        if noise is not None:
-                            pe.eps_z.copy_(noise[0], non_blocking=True)
-                        else:
-                            pe.eps_z.normal_()           # randn_like(m_p), synthesizers.py:449
-                        # (the flow's WaveNets are conditioned on the speaker: cond_layer(emb_g(sid)) belongs to the front lane)
-                        if self.cond_table is not None:
-                            pd.gc.copy_(self.cond_table[sid.to(dev, non_blocking=True)])
-                        else:
-                            pd.g.copy_(self.W["emb_g"][sid.to(dev, non_blocking=True)])
+                            with torch.cuda.stream(D):
+                                pd.f0[r].copy_(nsff0[:, head:], non_blocking=True)
+                                if noise is not None:
+                                    pd.eps_src[r].copy_(noise[1].reshape(noise[1].shape[0], -1)[:, : T2 * c["upp"]], non_blocking=True)
+                                else:
+                                    torch.rand(1, 1, 1, device=dev)   # rand_ini (:87): drawn to keep the generator stream aligned, value unused (:88)
+                                    pd.eps_src[r].normal_()           # randn_like(sine_waves), :98
+                                if nsff0.is_cuda:
+                                    nsff0.record_stream(D)
+                    with torch.cuda.stream(F):
                         kf = self._front_ops(pd)
 
                         def front(st, pe=pe, pd=pd, head=head, kf=kf):
@@ -1227,32 +1287,20 @@ class Engine:
                         stats = pe.stats.to(out_dtype, copy=True)
                         ev_front = torch.cuda.Event()
                         ev_front.record(F)
-                        for t in (phone, phone_lengths, pitch, sid):
-                            if t is not None and t.is_cuda:
-                                t.record_stream(F)
                     with torch.cuda.stream(D):
                         D.wait_event(ev_front)
-                        if c["f0"]:
-                            pd.f0.copy_(nsff0[:, head:], non_blocking=True)
-                            if noise is not None:
-                                pd.eps_src.copy_(noise[1].reshape(noise[1].shape[0], -1)[:, : T2 * c["upp"]], non_blocking=True)
-                            else:
-                                torch.rand(1, 1, 1, device=dev)   # rand_ini (:87): drawn to keep the generator stream aligned, value unused (:88)
-                                pd.eps_src.normal_()              # randn_like(sine_waves), :98
                         self._lane_graph(("lane-back", B, T2, slot), (dkey,), lambda st, pd=pd, kf=kf: pd.run(st, kf, None))
                         res = pd.out_arena.to(out_dtype, copy=True)
                         ev_done = torch.cuda.Event()
                         ev_done.record(D)
                         done[slot] = ev_done
-                        if nsff0 is not None and nsff0.is_cuda:
-                            nsff0.record_stream(D)
-                    cur = (res, stats, (B, T2), ev_done, pd.out_offsets)
+                    cur = (res, stats, (B, T2), ev_done, pd.out_offsets, G)
                 if pending is not None:
-                    yield finish(pending)
+                    yield from finish(pending)
                 pending = cur
             if pending is not None:
                 last, pending = pending, None
-                yield finish(last)
+                yield from finish(last)
         finally:
             # whatever happens to this generator, later users of these plans (on any stream) queue behind both lanes
             caller.wait_stream(F0)

@@ -242,11 +242,16 @@ class Synthesizer(nn.Module):
     @torch.no_grad()
     def infer_many(self, items):
         """``infer`` over an iterable of ``(phone, phone_lengths, pitch, nsff0, sid[, rate[, noise]])`` tuples (device or pinned host tensors), pipelined:
-        yields ``(o, x_mask, (z, z_p, m_p, logs_p))`` per item, in order — the same tensors ``infer`` returns item by item, same RNG draw order.
+        yields ``(o, x_mask, (z, z_p, m_p, logs_p))`` per item, in order, with the RNG draw order of ``infer`` called item by item.
 
         The reference's chunk loop (main/inference/convert.py:442-447) synthesises independent chunks one after the other; here the TextEncoder of
-        chunk i+1 runs on a second stream next to the generator of chunk i (``Engine.infer_lanes``).  A result is handed out once the next item has
-        been enqueued (or at the end), ordered on the caller's current stream.
+        chunk i+1 runs on a second stream next to the generator of chunk i (``Engine.infer_lanes``), and consecutive short items of one shape (three
+        10 s chunks, ``Engine.group_size``) run as one batch, each with its own inputs, speaker and noise draws: a group's results are bit-identical to
+        ``infer`` on the stacked batch with the same noise.  Against ``infer`` item by item the encoder and flow outputs are bit-identical too, while the
+        tensor-core generator picks its tile shapes by the batch and so sums in a different order (waveform differences of ~2e-4, the size of either
+        result's distance to the fp32 reference); RVC_B200_GROUP_FRAMES=0 switches the batching off and restores item-by-item bit-identity.  A result is
+        handed out once the next group has been enqueued (or at the end), ordered on the caller's current stream; the tensors of one item are views of
+        its group's fresh result buffer.
         """
         eng = self._ensure_engine()
         dt = self.emb_g.weight.dtype
@@ -271,76 +276,98 @@ class Synthesizer(nn.Module):
         copy of item n+1 runs on a copy stream while item n computes, the read-back of item n runs on a second copy stream while item n+1
         computes, and the compute itself runs in two lanes (``infer_many``: encoder of item n+1 next to the generator of item n).  Every item's
         copies still happen, they are just off the critical path.  A yielded view stays valid until ``depth`` further items have been yielded.
-        Same numerics and RNG order as ``infer`` called item by item.
+        Same RNG order as ``infer`` called item by item; numerics as ``infer_many`` (consecutive short items of one shape run as one batch).
         """
         dev = self.emb_g.weight.device
         if dev.type != "cuda":
             raise RuntimeError("rvc_maker_b200.Synthesizer.infer_stream needs its parameters on a CUDA device (no CPU fallback)")
         comp = torch.cuda.current_stream(dev)
-        nset = depth + 2              # staging sets: one being filled ahead, two in the lanes, `depth` results not yet handed back
-        if getattr(self, "_pipe", None) is None or self._pipe["dev"] != dev or self._pipe["nset"] != nset:
-            self._pipe = dict(dev=dev, nset=nset, h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev), stage=[None] * nset, host=[None] * nset,
-                              free=[None] * nset, done=[None] * nset)
+        # Two pools that grow on demand and are reused first-in first-out (allocated during the first calls, then steady): device staging sets
+        # (taken when an item is copied in, returned when its result has been enqueued for read-back: one being filled ahead + two groups in the
+        # lanes) and pinned host result buffers (taken at read-back, returned once `depth` further results have been handed out).
+        if getattr(self, "_pipe", None) is None or self._pipe["dev"] != dev:
+            self._pipe = dict(dev=dev, h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev), stage=[], free_stage=[], host=[], free_host=[])
         P = self._pipe
         h2d, d2h = P["h2d"], P["d2h"]
 
-        def stage(k, item):
-            """host -> device staging set k on the copy stream (after the lanes have finished the item that used the set before)"""
+        def stage(item):
+            """host -> device into a free staging set on the copy stream (after the lanes have finished the item that used the set before)"""
             item = item[:5]
-            bufs = P["stage"][k]
+            if P["free_stage"]:
+                k = P["free_stage"].pop(0)
+            else:
+                k = len(P["stage"])
+                P["stage"].append(dict(bufs=None, free=None))
+            S = P["stage"][k]
+            bufs = S["bufs"]
             if bufs is None or any((a is None) != (b is None) or (a is not None and (a.shape != b.shape or a.dtype != b.dtype)) for a, b in zip(bufs, item)):
-                bufs = P["stage"][k] = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=dev) for t in item]
-            if P["free"][k] is not None:
-                h2d.wait_event(P["free"][k])
+                bufs = S["bufs"] = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=dev) for t in item]
+            if S["free"] is not None:
+                h2d.wait_event(S["free"])
             with torch.cuda.stream(h2d):
                 for d, t in zip(bufs, item):
                     if t is not None:
                         d.copy_(t, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(h2d)
-            return ev
+            return k, ev
 
         slots = []                        # staging set of every item handed to the lanes, in order
 
         def staged():
             it = iter(items)
             nxt = next(it, None)
-            ev_next = stage(0, nxt) if nxt is not None else None
-            n = 0
+            k_next, ev_next = stage(nxt) if nxt is not None else (None, None)
             while nxt is not None:
-                k = n % nset
-                cur_ev, cur_noise = ev_next, (nxt[5] if len(nxt) > 5 else None)
+                k, cur_ev, cur_noise = k_next, ev_next, (nxt[5] if len(nxt) > 5 else None)
                 nxt = next(it, None)
                 if nxt is not None:
-                    ev_next = stage((n + 1) % nset, nxt)    # overlaps the compute of the items before it
+                    k_next, ev_next = stage(nxt)            # overlaps the compute of the items before it
                 comp.wait_event(cur_ev)
                 slots.append(k)
-                n += 1
-                yield tuple(P["stage"][k]) + (None, cur_noise)
+                yield tuple(P["stage"][k]["bufs"]) + (None, cur_noise)
 
         def read_back(k, o):
-            P["free"][k] = torch.cuda.Event()
-            P["free"][k].record(comp)                      # (ordered behind the item's result on the caller's stream: both lanes are done with the set)
+            S = P["stage"][k]
+            S["free"] = torch.cuda.Event()
+            S["free"].record(comp)                         # (ordered behind the item's result on the caller's stream: both lanes are done with the set)
+            P["free_stage"].append(k)
             n = o.numel()
-            if P["host"][k] is None or P["host"][k].numel() < n:
-                P["host"][k] = torch.empty(n, dtype=torch.float32).pin_memory()
-            out = P["host"][k][:n].view(o.shape)
-            d2h.wait_event(P["free"][k])
+            if P["free_host"]:
+                h = P["free_host"].pop(0)
+            else:
+                h = len(P["host"])
+                P["host"].append(None)
+            if P["host"][h] is None or P["host"][h].numel() < n:
+                P["host"][h] = torch.empty(n, dtype=torch.float32).pin_memory()
+            out = P["host"][h][:n].view(o.shape)
+            d2h.wait_event(S["free"])
             with torch.cuda.stream(d2h):
                 out.copy_(o, non_blocking=True)
                 o.record_stream(d2h)
-                P["done"][k] = torch.cuda.Event()
-                P["done"][k].record(d2h)
-            return out
+                done = torch.cuda.Event()
+                done.record(d2h)
+            return h, done, out
 
-        pending = []                      # (slot, host view): read-backs in flight
-        for i, res in enumerate(self.infer_many(staged())):
-            pending.append((slots[i], read_back(slots[i], res[0])))
-            if len(pending) >= depth:
-                kk, out = pending.pop(0)
-                P["done"][kk].synchronize()
+        pending, handed = [], []          # read-backs in flight; host buffers whose views the caller may still be using
+        try:
+            for i, res in enumerate(self.infer_many(staged())):
+                pending.append(read_back(slots[i], res[0]))
+                while len(pending) >= depth:
+                    h, done, out = pending.pop(0)
+                    done.synchronize()
+                    handed.append(h)
+                    if len(handed) > depth:
+                        P["free_host"].append(handed.pop(0))
+                    yield out
+            for h, done, out in pending:
+                done.synchronize()
+                handed.append(h)
                 yield out
-        for kk, out in pending:
-            P["done"][kk].synchronize()
-            yield out
-
+        finally:
+            P["free_host"].extend(handed)                  # (the views of this call expire with it)
+            for k in range(len(P["stage"])):               # (only after an exception: sets whose item never reached its read-back)
+                if k not in P["free_stage"]:
+                    P["stage"][k]["free"] = torch.cuda.Event()
+                    P["stage"][k]["free"].record(comp)     # infer_many has made the caller's stream wait for both lanes by now
+                    P["free_stage"].append(k)

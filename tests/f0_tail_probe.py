@@ -1,6 +1,6 @@
 """Timing of the f0 tail kernels (csrc/f0_post.cu) with CUDA events, and of the reference's host path (numpy oracle) beside it.
 
-    python tools/f0_tail_probe.py [--json out.json]
+    python tests/f0_tail_probe.py [--json out.json]
 
 Algorithmic bytes of rvc_rmvpe_pitch_f32: the salience map read once (T x 360 x 4 B) + 12 B of pitch / pitchf written per frame."""
 import json

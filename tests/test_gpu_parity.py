@@ -310,9 +310,10 @@ def test_flow_cluster_kernel_matches_per_layer_path(B, T, monkeypatch):
     assert torch.equal(again["z"], out["z"]) and torch.equal(again["o"], out["o"])
 
 
-def test_infer_stream_equals_item_by_item_calls():
-    """Synthesizer.infer_stream (copies of neighbouring items overlap compute, two staging sets) yields, in order, exactly what infer_to_host returns
-    for each item — five items of two different shapes, pinned noise."""
+def test_infer_stream_equals_item_by_item_calls(monkeypatch):
+    """Synthesizer.infer_stream (copies of neighbouring items overlap compute, pooled staging sets) yields, in order, exactly what infer_to_host returns
+    for each item — five items of two different shapes, pinned noise.  (Grouping off: with it, see test_infer_many_groups_equal_stacked_infer.)"""
+    monkeypatch.setenv("RVC_B200_GROUP_FRAMES", "0")
     cfg = cases.CONFIGS["v2_48k"]
     sd = cases.synth_state_dict(cfg, seed=5, heated=True)
     net = build_net(cfg, sd, True, precision="tc")
@@ -340,18 +341,22 @@ def test_infer_stream_equals_item_by_item_calls():
         assert a.shape == b.shape and torch.equal(a, b)
 
 
-def test_infer_many_equals_item_by_item_calls():
+def test_infer_many_equals_item_by_item_calls(monkeypatch):
     """Synthesizer.infer_many (two lanes: the encoder of item n+1 runs on a second stream next to the generator of item n) yields, in order, exactly the
     six tensors infer returns item by item under the same generator seed — fresh RNG draws (same draw order), shape changes, a `rate` item, repeated
-    shapes (graph replays), and a plain infer call afterwards on the same engine."""
+    shapes (graph replays), and a plain infer call afterwards on the same engine.  Pass 1 with the batching of consecutive items off (bit-identical),
+    pass 2 with it on: encoder / flow outputs still bit-identical (same RNG draws per item), the waveform within the tensor-core path's rounding."""
     cfg = cases.CONFIGS["v2_48k"]
     sd = cases.synth_state_dict(cfg, seed=6, heated=True)
     net = build_net(cfg, sd, True, precision="tc")
-    shapes = [(1, 300), (2, 130), (1, 300), (1, 300), (2, 130), (1, 300), (1, 64)]
+    # (consecutive items of one shape run as one batch, Engine.group_size: the three (1, 300), the (2, 130) pair, nine (1, 64) = a group of 8 + 1,
+    #  two (1, 1000); a `rate` item never joins its neighbours)
+    shapes = [(1, 300), (2, 130), (1, 300), (1, 300), (2, 130), (1, 300), (1, 64), (1, 300), (1, 300), (1, 300), (2, 130), (2, 130)] + [(1, 64)] * 9 + \
+        [(1, 1000), (1, 1000), (1, 300)]
     items = []
     for n, (B, T) in enumerate(shapes):
         inp = cases.synth_inputs(cfg, B, T, seed=200 + n, ragged=B > 1)
-        rate = torch.tensor(0.75) if n == 3 else None
+        rate = torch.tensor(0.75) if n in (3, 8) else None
         sid = torch.full((B,), (3 * n) % 7, dtype=torch.int64)      # a different speaker per item: stale conditioning in a lane would show
         items.append((inp["phone"].cuda(), inp["phone_lengths"].cuda(), inp["pitch"].cuda(), inp["nsff0"].cuda(), sid.cuda(), rate))
 
@@ -362,6 +367,7 @@ def test_infer_many_equals_item_by_item_calls():
     torch.manual_seed(99)
     want = [flat(net.infer(*it)) for it in items]
     torch.cuda.synchronize()
+    monkeypatch.setenv("RVC_B200_GROUP_FRAMES", "0")
     for rep in range(2):                 # second pass: every shape replays its captured lane graphs
         torch.manual_seed(99)
         got = [flat(r) for r in net.infer_many(iter(items))]
@@ -370,10 +376,72 @@ def test_infer_many_equals_item_by_item_calls():
         for n, (a, b) in enumerate(zip(got, want)):
             for x, y in zip(a, b):
                 assert x.shape == y.shape and torch.equal(x, y), (rep, n, shapes[n])
+    monkeypatch.delenv("RVC_B200_GROUP_FRAMES")
+    for rep in range(2):                 # consecutive items of one shape as one batch
+        torch.manual_seed(99)
+        got = [flat(r) for r in net.infer_many(iter(items))]
+        torch.cuda.synchronize()
+        assert len(got) == len(want)
+        worst = 0.0
+        for n, (a, b) in enumerate(zip(got, want)):
+            assert all(x.shape == y.shape for x, y in zip(a, b))
+            for x, y in zip(a[1:], b[1:]):     # x_mask, z, z_p, m_p, logs_p: the same noise draws, a batch-invariant encoder and flow
+                assert float((x - y).abs().max()) <= 1e-5 * max(1.0, float(y.abs().max())), (rep, n, shapes[n])
+            worst = max(worst, float((a[0] - b[0]).abs().max()))
+        assert worst <= 6e-4, worst
+        print(f"[infer_many grouped, pass {rep}] max |o - item-by-item o| = {worst:.2e}")
     torch.manual_seed(99)
     again = flat(net.infer(*items[0]))   # the serial call still works on the same engine (waits for the lanes' last use of the plans)
     assert all(torch.equal(x, y) for x, y in zip(again, want[0]))
     assert list(net.infer_many(iter([]))) == []
+    assert net._engine.group_size(1, 1000) == 3 and net._engine.group_size(1, 64) == 8 and net._engine.group_size(2, 4000) == 1
+
+
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+def test_infer_many_groups_equal_stacked_infer(precision, monkeypatch):
+    """A group of consecutive items is ONE batch: its results are bit-identical to infer on the stacked items with the same (pinned) noise, through
+    infer_many and through infer_stream; on the fp32 kernels (batch-invariant) also to infer item by item."""
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=8, heated=True)
+    net = build_net(cfg, sd, True, precision=precision)
+    T = 515
+    inps = [cases.synth_inputs(cfg, 1, T, seed=300 + n) for n in range(5)]
+    for n, inp in enumerate(inps):
+        inp["sid"] = torch.tensor([n])
+    monkeypatch.setenv("RVC_B200_GROUP_FRAMES", "1600")
+    G = net._ensure_engine().group_size(1, T)
+    assert G == 3
+    keys = ("phone", "phone_lengths", "pitch", "nsff0", "sid")
+    want = []
+    for g0 in range(0, 5, G):            # groups: items 0-2, items 3-4
+        grp = inps[g0:g0 + G]
+        net._noise_override = (torch.cat([i["eps_z"] for i in grp]), torch.cat([i["eps_src"] for i in grp]))
+        r = net.infer(*[torch.cat([i[k] for i in grp]).cuda() for k in keys])
+        want += [[t[j:j + 1].clone() for t in (r[0], r[2][0], r[2][2])] for j in range(len(grp))]
+    single = []
+    for inp in inps:
+        net._noise_override = (inp["eps_z"], inp["eps_src"])
+        r = net.infer(*[inp[k].cuda() for k in keys])
+        single.append([t.clone() for t in (r[0], r[2][0], r[2][2])])
+    net._noise_override = None
+    items = [tuple(inp[k].cuda() for k in keys) + (None, (inp["eps_z"], inp["eps_src"])) for inp in inps]
+    for rep in range(3):                 # eager, captured, replayed
+        got = [[t.clone() for t in (r[0], r[2][0], r[2][2])] for r in net.infer_many(iter(items))]
+        for n, (a, b) in enumerate(zip(got, want)):
+            assert all(torch.equal(x, y) for x, y in zip(a, b)), (rep, n)
+    hitems = [tuple(inp[k].pin_memory() for k in keys) + ((inp["eps_z"], inp["eps_src"]),) for inp in inps]
+    outs = [o.clone() for o in net.infer_stream(iter(hitems))]
+    assert all(torch.equal(o.cuda(), w[0]) for o, w in zip(outs, want))
+    for a, b in zip(want, single):
+        if precision == "fp32":
+            assert all(torch.equal(x, y) for x, y in zip(a, b))
+        else:
+            assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and float((a[0] - b[0]).abs().max()) <= 6e-4
+    monkeypatch.setenv("RVC_B200_GROUP_FRAMES", "0")
+    assert net._engine.group_size(1, T) == 1
+    got = [[t.clone() for t in (r[0], r[2][0], r[2][2])] for r in net.infer_many(iter(items))]
+    for a, b in zip(got, single):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
 @pytest.mark.parametrize("B,T", [(1, 1000), (2, 173), (3, 128), (2, 129), (1, 1), (2, 1024), (40, 64)])
