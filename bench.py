@@ -474,7 +474,9 @@ def main():
             pass
         roof["algorithmic_bytes_per_launch"] = f["bytes"] / max(f["launches"], 1)
         roof.update({"kernel": top, "launches_per_step": f["launches"], "share_of_step": f["ms"] / total_ms,
-                     "peak_source": "MEASURED_PEAKS.json (sustained)" if peaks else "fallback"})
+                     "peak_source": "MEASURED_PEAKS.json (sustained)" if peaks else "fallback",
+                     "measured_on": f"per-launch CUDA events on the launches of one step's own plan (B={B}, T={T}: the serial pass, which the ncu captures under "
+                                    "profiles/ show too); the batched passes of `value` launch the same kernels on the stacked shape"})
         out["roofline"] = roof
         # per-stage fraction of roofline: the bound is the side of the ridge (sustained tensor peak / HBM peak, flop per byte) the
         # family's algorithmic intensity falls on; launch-latency-bound families (short sequences) show up as small fractions of either

@@ -29,3 +29,5 @@ for l in open("$O/${L}_other_configs.jsonl"):
 x = json.load(open("$O/${L}_stream600_1gpu.json")); print("stream", x["value"], x["ms_per_step"])
 print(open("$O/${L}_bench_reference_arm.json").read()[:300])
 PY
+# the f0 tail kernels (tests/f0_tail_probe.py: CUDA-event timings, HBM fraction, the reference's host path beside them)
+python tests/f0_tail_probe.py --json $O/${L}_f0_tail_probe.json > $O/${L}_f0_tail_probe.log 2>&1
