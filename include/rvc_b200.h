@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 26
+#define RVC_ABI_VERSION 27
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -426,6 +426,18 @@ int rvc_f0_coarse_f64(const double* f0, int64_t n, const double* notes, int32_t 
 int rvc_rmvpe_pitch_f32(const float* salience, int64_t row_stride, int32_t T, float thred, double gate_lo, double gate_hi,
                         const double* notes, int32_t n_notes, double strength, double shift, double mel_min, double mel_max,
                         int64_t* pitch, float* pitchf, double* f0_out, void* stream);
+
+/*
+ * The RMVPE mel front end (pre-network part), one launch: MelSpectrogram.forward for keyshift = 0, speed = 1, center = True
+ * (main/library/predictors/RMVPE.py:161-181: torch.stft(n_fft = win = 1024, hop = 160, reflect padding), magnitude, mel_basis matmul,
+ * log(clamp(., clamp))) and the reflect padding of the frame axis that mel2hidden applies before the network (:212-213).
+ *   audio [n] fp32 (16 kHz), window [1024] (torch.hann_window(1024)), mel_basis [128][513] (the module's registered buffer, :146-148)
+ *   out [128][ld] fp32: columns 0..T-1 = log-mel frames (T = 1 + n / 160), columns T..Tp-1 = columns T-2, T-3, ... (Tp = T rounded up to 32 for
+ *   the network; Tp = T for the bare spectrogram).  Needs n > 512 and Tp - T < T, as the reference's two reflect paddings do.
+ * fp32 like the reference (is_half = False); the summation order differs from cuFFT / cuBLAS, so parity is by tolerance (tests/test_gpu_mel_front.py).
+ */
+int rvc_mel_spectrogram_f32(const float* audio, int64_t n, const float* window, const float* mel_basis, float* out, int64_t ld, int32_t T,
+                            int32_t Tp, float clamp, void* stream);
 
 #ifdef __cplusplus
 }

@@ -2,6 +2,8 @@
 
 Mirrors, by name and argument meaning, the reference functions between the RMVPE network and the synthesiser (post-network part):
 
+* ``mel_spectrogram(audio, mel_basis)`` — ``MelSpectrogram.forward`` + the frame padding of ``mel2hidden`` (RMVPE.py:161-181, :212-213): the input of
+  the RMVPE network, one launch instead of the reference's pad / FFT / abs / GEMM / clamp / log / pad;
 * ``decode(hidden, thred)`` / ``decode_with_pitch`` — ``RMVPE.decode`` / ``to_local_average_cents`` / the legacy gate
   (main/library/predictors/RMVPE.py:217-221, :229-233, :237-252), on a CUDA salience map ``[T, 360]``;
 * ``get_f0_tail(f0, pitch, f0_autotune, f0_autotune_strength)`` — the tail of ``VC.get_f0`` (main/inference/convert.py:308-323);
@@ -69,6 +71,36 @@ def _salience(hidden, what):
     if hidden.stride(1) != 1:
         hidden = hidden.contiguous()
     return hidden
+
+
+_window_cache = {}
+
+
+def mel_spectrogram(audio, mel_basis, clamp=1e-5, pad_frames=True):
+    """``MelSpectrogram.forward(audio, center=True)`` (keyshift 0, speed 1, fp32; RMVPE.py:161-181) in one launch, with — when ``pad_frames`` — the
+    reflect padding of the frame axis to a multiple of 32 that ``mel2hidden`` applies before the network (:212-213).
+
+    audio: [n] or [1, n] fp32 CUDA tensor (16 kHz); mel_basis: the reference module's ``mel_basis`` buffer [128, 513] on the same device.
+    Returns ``(mel [1, 128, Tp], n_frames)``: feed ``mel`` to the network and cut its output to ``[:, :n_frames]`` as ``mel2hidden`` does (:214)."""
+    import torch
+
+    from . import _lib
+
+    audio = _cuda(audio, "mel_spectrogram", torch.float32).reshape(-1).contiguous()
+    mel_basis = _cuda(mel_basis, "mel_spectrogram", torch.float32).contiguous()
+    if tuple(mel_basis.shape) != (128, 513):
+        raise ValueError(f"mel_basis must be [128, 513] (RMVPE: 128 mels, n_fft 1024), got {tuple(mel_basis.shape)}")
+    dev = audio.device
+    if str(dev) not in _window_cache:
+        _window_cache[str(dev)] = torch.hann_window(1024, device=dev)      # RMVPE.py:165
+    n = audio.numel()
+    T = 1 + n // 160
+    Tp = 32 * ((T - 1) // 32 + 1) if pad_frames else T
+    out = torch.empty(1, 128, Tp, dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.load().rvc_mel_spectrogram_f32(audio.data_ptr(), n, _window_cache[str(dev)].data_ptr(), mel_basis.data_ptr(), out.data_ptr(), Tp, T, Tp,
+                                                   float(clamp), st), "rvc_mel_spectrogram_f32")
+    return out, T
 
 
 def decode(hidden, thred=0.03, f0_min=None, f0_max=None):

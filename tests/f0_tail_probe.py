@@ -1,4 +1,4 @@
-"""Timing of the f0 tail kernels (csrc/f0_post.cu) with CUDA events, and of the reference's host path (numpy oracle) beside it.
+"""Timing of the f0 tail kernels (csrc/f0_post.cu) and the mel front end (csrc/mel_front.cu) with CUDA events, and of the reference's path beside them.
 
     python tests/f0_tail_probe.py [--json out.json]
 
@@ -57,6 +57,18 @@ def main():
             t0 = time.perf_counter()
             h = sal.cpu().numpy()                                     # the D2H copy the reference pays first (RMVPE.py:226)
             row["d2h_copy_us"] = (time.perf_counter() - t0) * 1e6
+        rows.append(row)
+        print(json.dumps(row))
+    # the mel front end: one launch against the reference's torch calls (oracle/mel_oracle.py on CUDA tensors = cuFFT + cuBLAS + elementwise kernels)
+    from oracle import mel_oracle
+    basis = torch.from_numpy(mel_oracle.mel_filterbank()).cuda()
+    for secs in (10, 600):
+        audio = mel_oracle.synthetic_audio(secs * 16000, 5).cuda()
+        med, best = time_gpu(lambda: P.mel_spectrogram(audio, basis), flush=flush)
+        med_ref, _ = time_gpu(lambda: mel_oracle.pad_frames(mel_oracle.mel_spectrogram(audio, basis)), iters=20, flush=flush)
+        T = 1 + audio.numel() // 160
+        row = dict(kernel="mel_spectrogram", audio_s=secs, frames=T, mel_us=med, mel_best_us=best, torch_eager_us=med_ref,
+                   gflops=(5.0 * 1024 * 10 + 2.0 * 128 * 513) * T / med / 1e3)
         rows.append(row)
         print(json.dumps(row))
     if "--json" in sys.argv:
