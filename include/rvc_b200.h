@@ -436,8 +436,11 @@ int rvc_rmvpe_pitch_f32(const float* salience, int64_t row_stride, int32_t T, fl
  *   the network; Tp = T for the bare spectrogram).  Needs n > 512 and Tp - T < T, as the reference's two reflect paddings do.
  * fp32 like the reference (is_half = False); the summation order differs from cuFFT / cuBLAS, so parity is by tolerance (tests/test_gpu_mel_front.py).
  */
-int rvc_mel_spectrogram_f32(const float* audio, int64_t n, const float* window, const float* mel_basis, float* out, int64_t ld, int32_t T,
-                            int32_t Tp, float clamp, void* stream);
+int rvc_mel_spectrogram_f32(const float* audio, int64_t n, const float* window, const float* mel_basis, const int32_t* ranges, float* out,
+                            int64_t ld, int32_t T, int32_t Tp, float clamp, void* stream);
+/* ranges [128][2] = [lo, hi) of the non-zero bins of every mel_basis row (triangular filters: 2 - 45 of 513 bins), computed once per filterbank;
+ * passed to rvc_mel_spectrogram_f32 it restricts the filterbank product to them (NULL: dense product). */
+int rvc_mel_basis_ranges(const float* mel_basis, int32_t* ranges, void* stream);
 
 #ifdef __cplusplus
 }

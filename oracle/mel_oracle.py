@@ -37,7 +37,7 @@ def mel_filterbank(sr=SR, n_fft=N_FFT, n_mels=N_MELS, fmin=FMIN, fmax=FMAX, htk=
 
 def mel_spectrogram(audio, mel_basis, n_fft=N_FFT, hop=HOP, clamp=CLAMP):
     """RMVPE.py:161-181 for keyshift = 0, speed = 1, center = True, fp32: audio [1, n] -> log-mel [1, 128, 1 + n // hop]."""
-    window = torch.hann_window(n_fft)                                                                        # :165
+    window = torch.hann_window(n_fft).to(audio.device)                                                                     # :165
     fft = torch.stft(audio, n_fft=n_fft, hop_length=hop, win_length=n_fft, window=window, center=True, return_complex=True)   # :167
     magnitude = torch.sqrt(fft.real.pow(2) + fft.imag.pow(2))                                                # :168
     mel_output = torch.matmul(mel_basis, magnitude)                                                          # :178

@@ -134,7 +134,8 @@ SIGNATURES = {
     "rvc_absmax_f32": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp]),
     "rvc_rmvpe_decode_f32": (C.c_int, [_vp, _i64, _i32, _f32, _f64, _f64, _vp, _vp]),
     "rvc_f0_coarse_f64": (C.c_int, [_vp, _i64, _vp, _i32, _f64, _f64, _f64, _f64, _vp, _vp, _vp, _vp]),
-    "rvc_mel_spectrogram_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp]),
+    "rvc_mel_spectrogram_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp]),
+    "rvc_mel_basis_ranges": (C.c_int, [_vp, _vp, _vp]),
     "rvc_rmvpe_pitch_f32": (C.c_int, [_vp, _i64, _i32, _f32, _f64, _f64, _vp, _i32, _f64, _f64, _f64, _f64, _vp, _vp, _vp, _vp]),
     "rvc_resblock_pair_tc": (C.c_int, [C.POINTER(ResblockPairDesc), _vp]),
     "rvc_debug_pair_trace": (C.c_int, [_vp, _i32]),

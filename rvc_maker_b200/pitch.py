@@ -74,13 +74,15 @@ def _salience(hidden, what):
 
 
 _window_cache = {}
+_ranges_cache = {}
 
 
-def mel_spectrogram(audio, mel_basis, clamp=1e-5, pad_frames=True):
+def mel_spectrogram(audio, mel_basis, clamp=1e-5, pad_frames=True, sparse=True):
     """``MelSpectrogram.forward(audio, center=True)`` (keyshift 0, speed 1, fp32; RMVPE.py:161-181) in one launch, with — when ``pad_frames`` — the
     reflect padding of the frame axis to a multiple of 32 that ``mel2hidden`` applies before the network (:212-213).
 
     audio: [n] or [1, n] fp32 CUDA tensor (16 kHz); mel_basis: the reference module's ``mel_basis`` buffer [128, 513] on the same device.
+    ``sparse``: multiply only the non-zero bins of every (triangular) filterbank row — same values, the zeros contribute nothing.
     Returns ``(mel [1, 128, Tp], n_frames)``: feed ``mel`` to the network and cut its output to ``[:, :n_frames]`` as ``mel2hidden`` does (:214)."""
     import torch
 
@@ -98,8 +100,19 @@ def mel_spectrogram(audio, mel_basis, clamp=1e-5, pad_frames=True):
     Tp = 32 * ((T - 1) // 32 + 1) if pad_frames else T
     out = torch.empty(1, 128, Tp, dtype=torch.float32, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(_lib.load().rvc_mel_spectrogram_f32(audio.data_ptr(), n, _window_cache[str(dev)].data_ptr(), mel_basis.data_ptr(), out.data_ptr(), Tp, T, Tp,
-                                                   float(clamp), st), "rvc_mel_spectrogram_f32")
+    lib = _lib.load()
+    rng = None
+    if sparse:
+        # the non-zero support of every filterbank row, computed once per buffer (keyed on storage and in-place version)
+        key = (mel_basis.data_ptr(), mel_basis._version, str(dev))
+        if _ranges_cache.get("key") != key:
+            r = torch.empty(128, 2, dtype=torch.int32, device=dev)
+            _lib.check(lib.rvc_mel_basis_ranges(mel_basis.data_ptr(), r.data_ptr(), st), "rvc_mel_basis_ranges")
+            _ranges_cache.update(key=key, ranges=r, basis=mel_basis)       # (holding the tensor keeps its address from being reused)
+        rng = _ranges_cache["ranges"]
+    _lib.check(lib.rvc_mel_spectrogram_f32(audio.data_ptr(), n, _window_cache[str(dev)].data_ptr(), mel_basis.data_ptr(),
+                                           rng.data_ptr() if rng is not None else None, out.data_ptr(), Tp, T, Tp, float(clamp), st),
+               "rvc_mel_spectrogram_f32")
     return out, T
 
 

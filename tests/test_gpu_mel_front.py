@@ -44,6 +44,9 @@ def test_mel_matches_reference_golden(name, gold):
     silent = ref == LOG_CLAMP                      # all-zero windows: the reference sits exactly on the clamp
     assert torch.equal(mel.cpu()[silent], ref[silent])
     print(f"[mel {name}] max err loud / all: {e[0]:.2e} / {e[1]:.2e}; clamped bins {int(silent.sum())}")
+    dense, _ = P.mel_spectrogram(audio, basis, pad_frames=False, sparse=False)     # the dense filterbank product: same terms, another order
+    check(dense.cpu(), ref)
+    assert float((dense - mel).abs().max()) <= 1e-4 and torch.equal(dense.cpu()[silent], ref[silent])
     if T > 17:                                     # mel2hidden's reflect padding of the frame axis (the reference raises for shorter clips)
         melp, T2 = P.mel_spectrogram(audio[0], basis)
         assert T2 == T and melp.shape[-1] % 32 == 0 and 0 <= melp.shape[-1] - T < 32
