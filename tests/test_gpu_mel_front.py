@@ -55,14 +55,14 @@ def test_mel_matches_reference_golden(name, gold):
 
 
 def test_mel_long_audio_against_oracle():
-    """100 s of audio (10 001 frames) against the torch CPU restatement."""
+    """602 s of audio (BASELINE configs[4]'s ten-minute stream with its padding: 60 201 frames) against the torch CPU restatement."""
     from rvc_maker_b200 import pitch as P
 
-    audio = mel_oracle.synthetic_audio(1_600_000, 7)
+    audio = mel_oracle.synthetic_audio(602 * 16000, 7)
     basis = torch.from_numpy(mel_oracle.mel_filterbank())
     ref = mel_oracle.pad_frames(mel_oracle.mel_spectrogram(audio, basis))
     mel, T = P.mel_spectrogram(audio.cuda(), basis.cuda())
-    assert T == 10001 and mel.shape == ref.shape
+    assert T == 60201 and mel.shape == ref.shape
     check(mel.cpu(), ref)
 
 
