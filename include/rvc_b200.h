@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 27
+#define RVC_ABI_VERSION 28
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -441,6 +441,18 @@ int rvc_mel_spectrogram_f32(const float* audio, int64_t n, const float* window, 
 /* ranges [128][2] = [lo, hi) of the non-zero bins of every mel_basis row (triangular filters: 2 - 45 of 513 bins), computed once per filterbank;
  * passed to rvc_mel_spectrogram_f32 it restricts the filterbank product to them (NULL: dense product). */
 int rvc_mel_basis_ranges(const float* mel_basis, int32_t* ranges, void* stream);
+
+/*
+ * The split-point search at the head of VC.pipeline's chunk loop (main/inference/convert.py:404-412): for every candidate t = t_center, 2 t_center, ... < n
+ * the first sample in [t - t_query, min(t + t_query, n)) at which |audio_sum| is smallest, audio_sum[p] = sum_{i < window} audio_pad[p + i] over the
+ * signal reflect-padded by window/2.  Each sum is formed like numpy forms it (sequentially from 0, one rounding per addition, in the signal's dtype:
+ * is_f64 = 1 for the float64 signal behind the reference's filtfilt, 0 for float32), so opt_ts is bit-identical to the reference's.
+ *   audio [n] (device), opt_ts [ (n - 1) / t_center ] int64 (device), ws: rvc_split_points_workspace(n, t_center, t_query) bytes (device, 16-byte aligned).
+ * The caller applies the reference's guard (`if audio_pad.shape[0] > t_max`, :406) itself.
+ */
+int64_t rvc_split_points_workspace(int64_t n, int64_t t_center, int64_t t_query);
+int rvc_split_points(const void* audio, int32_t is_f64, int64_t n, int32_t window, int64_t t_center, int64_t t_query, int64_t* opt_ts, void* ws,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,8 +18,11 @@ Mirrors ``VC.voice_conversion`` from the embedder output on (main/inference/conv
 * with several ranks every rank synthesises the chunks ``shard_chunks`` gives it; the pieces are gathered once over NCCL
   (the only collective, after the data path) and rank 0 assembles the stream.
 
-Out of scope (hooks instead): the embedder and FAISS retrieval that produce ``feats`` / ``feats0`` (:336-359), f0
-extraction (:431, 8f-2), the high-pass filter (:402) and ``change_rms`` (:450, only when volume_envelope != 1).
+* the split-point search at the head of the loop (:404-412; 160 host passes over the whole signal in the reference) is one launch over the
+  search windows, bit-identical indices (``split_points`` below; ``chunks.split_points`` is the host planner the CPU tests use).
+
+Out of scope (hooks instead): the embedder and FAISS retrieval that produce ``feats`` / ``feats0`` (:336-359), the f0 network
+(:431, 8f-2; its two ends are in ``rvc_maker_b200.pitch``), the high-pass filter (:402) and ``change_rms`` (:450, only when volume_envelope != 1).
 """
 from __future__ import annotations
 
@@ -28,6 +31,32 @@ import torch
 
 from . import _lib
 from .chunks import WINDOW, ChunkConfig, chunk_spans, shard_chunks
+
+
+def split_points(audio, cfg=ChunkConfig()):
+    """``chunks.split_points`` on the device — the search at the head of ``VC.pipeline``'s chunk loop (convert.py:404-412): ``opt_ts`` as a list of ints.
+
+    audio: 1-D CUDA tensor of the (unpadded) 16 kHz signal, float64 (what the reference's ``signal.filtfilt`` hands on, :402) or float32.  The 160
+    passes over the whole signal that the reference makes on the host (1.5 s for ten minutes of audio) become one launch over the 2 x ``x_query``
+    seconds around every candidate; the sums are formed in numpy's order and dtype, so the indices are the reference's, bit for bit."""
+    if not isinstance(audio, torch.Tensor) or audio.device.type != "cuda":
+        raise RuntimeError("rvc_maker_b200.pipeline.split_points needs a CUDA tensor (no CPU fallback; chunks.split_points is the host planner)")
+    if audio.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"audio must be float32 or float64, got {audio.dtype}")
+    audio = audio.reshape(-1).contiguous()
+    n = audio.numel()
+    if n + WINDOW <= cfg.t_max:                        # :406 (audio_pad.shape[0] > t_max)
+        return []
+    n_t = (n - 1) // cfg.t_center
+    if n_t == 0:
+        return []
+    lib = _lib.load()
+    ws = torch.empty(lib.rvc_split_points_workspace(n, cfg.t_center, cfg.t_query), dtype=torch.uint8, device=audio.device)
+    out = torch.empty(n_t, dtype=torch.int64, device=audio.device)
+    st = torch.cuda.current_stream(audio.device).cuda_stream
+    _lib.check(lib.rvc_split_points(audio.data_ptr(), int(audio.dtype == torch.float64), n, WINDOW, cfg.t_center, cfg.t_query, out.data_ptr(),
+                                    ws.data_ptr(), st), "rvc_split_points")
+    return out.tolist()
 
 
 def feature_prep(feats, feats0, pitchf, protect, T=None):

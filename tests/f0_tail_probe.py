@@ -71,6 +71,30 @@ def main():
                    gflops=(5.0 * 1024 * 10 + 2.0 * 128 * 513) * T / med / 1e3)
         rows.append(row)
         print(json.dumps(row))
+    # the split-point search of VC.pipeline: one launch against the reference's 160 host passes (oracle/chunk_oracle.py), after the reference's filtfilt
+    from scipy import signal
+    from oracle import chunk_oracle
+    from rvc_maker_b200 import pipeline as pl
+    bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)
+    for secs in (100, 600):
+        x = (np.random.default_rng(secs).standard_normal(secs * 16000) * 0.1).astype(np.float32)
+        t0 = time.perf_counter()
+        y = np.ascontiguousarray(signal.filtfilt(bh, ah, x))
+        t_filt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        want = chunk_oracle.reference_chunk_loop(y, lambda a, f0, f1: np.zeros(3 * 48000, np.float32), 48000)[1]
+        t_host = time.perf_counter() - t0
+        yd = torch.from_numpy(y).cuda()
+        assert pl.split_points(yd) == want
+        med, best = time_gpu(lambda: pl.split_points(yd), iters=20, flush=flush)      # (includes the .tolist() read-back of the indices)
+        yp = torch.from_numpy(y).pin_memory()
+        t0 = time.perf_counter()
+        yd2 = yp.cuda(non_blocking=True); torch.cuda.synchronize()
+        t_h2d = time.perf_counter() - t0
+        row = dict(kernel="split_points", audio_s=secs, candidates=len(want), device_us=med, device_best_us=best, h2d_pinned_us=t_h2d * 1e6,
+                   host_search_us=t_host * 1e6, host_filtfilt_us=t_filt * 1e6)
+        rows.append(row)
+        print(json.dumps(row))
     if "--json" in sys.argv:
         json.dump(rows, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
 

@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.rvc_abi_version() == 27
+    assert lib.rvc_abi_version() == 28
     # argument validation happens before any CUDA call, so it is checkable without a GPU
     rc = lib.rvc_conv1d_f32(None, None)
     assert rc == -1
@@ -107,3 +107,12 @@ def test_pitch_module_refuses_cpu_tensors():
         pitch.rmvpe_pitch(np.zeros((4, 360), np.float32))
     with pytest.raises(RuntimeError, match="CUDA"):
         pitch.get_f0_tail(torch.zeros(4, dtype=torch.float64))
+
+
+def test_split_points_argument_errors(lib):
+    assert lib.rvc_split_points_workspace(100 * 16000, 38 * 16000, 6 * 16000) == 2 * 94 * 16
+    assert lib.rvc_split_points(8, 1, 100 * 16000, 161, 38 * 16000, 6 * 16000, 8, 8, None) == -2 and b"even" in lib.rvc_last_error()
+    assert lib.rvc_split_points(8, 1, 50, 160, 38 * 16000, 6 * 16000, 8, 8, None) == -2
+    assert lib.rvc_split_points(8, 1, 100 * 16000, 160, 16000, 6 * 16000, 8, 8, None) == -2 and b"t_query" in lib.rvc_last_error()
+    assert lib.rvc_split_points(None, 1, 100 * 16000, 160, 38 * 16000, 6 * 16000, 8, 8, None) == -1
+    assert lib.rvc_split_points(None, 1, 30 * 16000, 160, 38 * 16000, 6 * 16000, None, None, None) == 0      # no candidate: nothing to do
