@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 28
+#define RVC_ABI_VERSION 29
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -453,6 +453,21 @@ int rvc_mel_basis_ranges(const float* mel_basis, int32_t* ranges, void* stream);
 int64_t rvc_split_points_workspace(int64_t n, int64_t t_center, int64_t t_query);
 int rvc_split_points(const void* audio, int32_t is_f64, int64_t n, int32_t window, int64_t t_center, int64_t t_query, int64_t* opt_ts, void* ws,
                      void* stream);
+
+/*
+ * The zero-phase high-pass at the head of VC.pipeline, `audio = signal.filtfilt(bh, ah, audio)` (main/inference/convert.py:402; scipy defaults: odd
+ * extension by padlen = 3 * ncoef, steady-state initial conditions), in float64 on the device: the direct-form-II-transposed recurrence of scipy's
+ * lfilter with scipy's operation order inside blocks of rvc_filtfilt_block(n) samples (2048 or 4096, by the signal length), the blocks' start states chained through ML = M^block (the
+ * state-transition matrix of the recurrence raised to the block length, row-major [order][order]; rvc_maker_b200.pipeline obtains it by running the
+ * recurrence).  Not bit-identical to scipy's sample-by-sample evaluation: ~2e-8 absolute on a signal of amplitude 0.5, the rounding-noise level of the
+ * filter itself.
+ *   x [n] float32 / float64 (device), b, a [ncoef], zi [ncoef - 1] (scipy.signal.lfilter_zi), ML: HOST pointers; y [n] float64 (device);
+ *   ws: rvc_filtfilt_workspace(n, ncoef) bytes (device).  Needs a[0] == 1 and n > 3 * ncoef.
+ */
+int32_t rvc_filtfilt_block(int64_t n);
+int64_t rvc_filtfilt_workspace(int64_t n, int32_t ncoef);
+int rvc_filtfilt(const void* x, int32_t is_f64, int64_t n, const double* b, const double* a, int32_t ncoef, const double* zi, const double* ML,
+                 double* y, void* ws, void* stream);
 
 #ifdef __cplusplus
 }

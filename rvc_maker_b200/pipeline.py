@@ -21,8 +21,11 @@ Mirrors ``VC.voice_conversion`` from the embedder output on (main/inference/conv
 * the split-point search at the head of the loop (:404-412; 160 host passes over the whole signal in the reference) is one launch over the
   search windows, bit-identical indices (``split_points`` below; ``chunks.split_points`` is the host planner the CPU tests use).
 
+* the high-pass in front of it (``signal.filtfilt``, :402) has a device version (``filtfilt`` below: scipy's recurrence in blocks, within the filter's
+  rounding noise of scipy, not bit-identical — read its docstring before building plans on it).
+
 Out of scope (hooks instead): the embedder and FAISS retrieval that produce ``feats`` / ``feats0`` (:336-359), the f0 network
-(:431, 8f-2; its two ends are in ``rvc_maker_b200.pitch``), the high-pass filter (:402) and ``change_rms`` (:450, only when volume_envelope != 1).
+(:431, 8f-2; its two ends are in ``rvc_maker_b200.pitch``) and ``change_rms`` (:450, only when volume_envelope != 1).
 """
 from __future__ import annotations
 
@@ -31,6 +34,7 @@ import torch
 
 from . import _lib
 from .chunks import WINDOW, ChunkConfig, chunk_spans, shard_chunks
+from .chunks import split_points as ch_split_points   # the host planner (numpy), next to the device search below
 
 
 def split_points(audio, cfg=ChunkConfig()):
@@ -57,6 +61,54 @@ def split_points(audio, cfg=ChunkConfig()):
     _lib.check(lib.rvc_split_points(audio.data_ptr(), int(audio.dtype == torch.float64), n, WINDOW, cfg.t_center, cfg.t_query, out.data_ptr(),
                                     ws.data_ptr(), st), "rvc_split_points")
     return out.tolist()
+
+
+_filt_cache = {}
+
+
+def _filter_constants(b, a, block):
+    """(b, a, zi, M^block) as contiguous float64 arrays.  zi as scipy.signal.lfilter_zi computes it (steady state of the step response); M^block by running
+    the zero-input recurrence ``block`` steps from every unit state — the companion form is far from normal, repeated squaring of M loses everything."""
+    key = (tuple(b), tuple(a), block)
+    if key not in _filt_cache:
+        b64, a64 = np.asarray(b, np.float64), np.asarray(a, np.float64)
+        if b64.shape != a64.shape or b64.ndim != 1:
+            raise ValueError("b and a must be 1-D and of equal length (scipy.signal.butter gives them so)")
+        if a64[0] != 1.0:
+            b64, a64 = b64 / a64[0], a64 / a64[0]
+        y_inf = np.sum(b64) / np.sum(a64)
+        zi = np.flip(np.cumsum(np.flip(b64 - y_inf * a64)))[1:].copy()
+        ns = len(a64) - 1
+        Z = np.eye(ns)                                     # column j = the state reached from unit state j
+        for _ in range(block):
+            y = Z[0].copy()
+            Z[:-1] = Z[1:] - a64[1:-1, None] * y[None, :]
+            Z[-1] = -a64[-1] * y
+        _filt_cache[key] = (np.ascontiguousarray(b64), np.ascontiguousarray(a64), zi, np.ascontiguousarray(Z))
+    return _filt_cache[key]
+
+
+def filtfilt(audio, b, a):
+    """``scipy.signal.filtfilt(b, a, audio)`` (scipy's defaults, as convert.py:402 calls it) on the device: a float64 CUDA tensor [n].
+
+    audio: 1-D CUDA tensor, float32 or float64; b, a: the coefficients (``signal.butter(N=5, Wn=48, btype="high", fs=16000)``, convert.py:29).  The
+    recurrence and its operation order are scipy's inside blocks of 2048 / 4096 samples, the blocks run in parallel (137 - 259 ms on the host per 10 minutes of
+    audio, 4 ms here); the result agrees with scipy's to ~2e-8 absolute at amplitude 0.5 — the rounding noise of the filter itself —
+    not to the bit, so keep scipy's call where bit-identical split points matter (``split_points`` is exact for whatever signal it is given)."""
+    if not isinstance(audio, torch.Tensor) or audio.device.type != "cuda":
+        raise RuntimeError("rvc_maker_b200.pipeline.filtfilt needs a CUDA tensor (no CPU fallback)")
+    if audio.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"audio must be float32 or float64, got {audio.dtype}")
+    lib = _lib.load()
+    audio = audio.reshape(-1).contiguous()
+    n = audio.numel()
+    b64, a64, zi, ML = _filter_constants(b, a, lib.rvc_filtfilt_block(n))
+    y = torch.empty(n, dtype=torch.float64, device=audio.device)
+    ws = torch.empty(max(lib.rvc_filtfilt_workspace(n, len(b64)), 8), dtype=torch.uint8, device=audio.device)
+    st = torch.cuda.current_stream(audio.device).cuda_stream
+    _lib.check(lib.rvc_filtfilt(audio.data_ptr(), int(audio.dtype == torch.float64), n, b64.ctypes.data, a64.ctypes.data, len(b64), zi.ctypes.data,
+                                ML.ctypes.data, y.data_ptr(), ws.data_ptr(), st), "rvc_filtfilt")
+    return y
 
 
 def feature_prep(feats, feats0, pitchf, protect, T=None):

@@ -91,6 +91,12 @@ def main():
         t0 = time.perf_counter()
         yd2 = yp.cuda(non_blocking=True); torch.cuda.synchronize()
         t_h2d = time.perf_counter() - t0
+        xd = torch.from_numpy(x).cuda()
+        pl.filtfilt(xd, bh, ah)
+        med_f, _ = time_gpu(lambda: pl.filtfilt(xd, bh, ah), iters=10, flush=flush)
+        err = float((pl.filtfilt(xd, bh, ah).cpu() - torch.from_numpy(y)).abs().max())
+        rows.append(dict(kernel="filtfilt", audio_s=secs, device_us=med_f, host_scipy_us=t_filt * 1e6, max_abs_diff_vs_scipy=err))
+        print(json.dumps(rows[-1]))
         row = dict(kernel="split_points", audio_s=secs, candidates=len(want), device_us=med, device_best_us=best, h2d_pinned_us=t_h2d * 1e6,
                    host_search_us=t_host * 1e6, host_filtfilt_us=t_filt * 1e6)
         rows.append(row)

@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.rvc_abi_version() == 28
+    assert lib.rvc_abi_version() == 29
     # argument validation happens before any CUDA call, so it is checkable without a GPU
     rc = lib.rvc_conv1d_f32(None, None)
     assert rc == -1
@@ -116,3 +116,17 @@ def test_split_points_argument_errors(lib):
     assert lib.rvc_split_points(8, 1, 100 * 16000, 160, 16000, 6 * 16000, 8, 8, None) == -2 and b"t_query" in lib.rvc_last_error()
     assert lib.rvc_split_points(None, 1, 100 * 16000, 160, 38 * 16000, 6 * 16000, 8, 8, None) == -1
     assert lib.rvc_split_points(None, 1, 30 * 16000, 160, 38 * 16000, 6 * 16000, None, None, None) == 0      # no candidate: nothing to do
+
+
+def test_filtfilt_argument_errors(lib):
+    import numpy as np
+
+    one = np.ones(6)
+    p = one.ctypes.data
+    assert lib.rvc_filtfilt_block(9_600_000) == 4096 and lib.rvc_filtfilt_block(160000) == 2048
+    assert lib.rvc_filtfilt_workspace(160000, 6) == (160036 + 2 * 79 * 8) * 8
+    assert lib.rvc_filtfilt(8, 0, 1000, p, p, 12, p, p, 8, 8, None) == -2
+    assert lib.rvc_filtfilt(8, 0, 18, p, p, 6, p, p, 8, 8, None) == -2 and b"padlen" in lib.rvc_last_error()
+    two = 2 * one
+    assert lib.rvc_filtfilt(8, 0, 1000, p, two.ctypes.data, 6, p, p, 8, 8, None) == -1 and b"normalise" in lib.rvc_last_error()
+    assert lib.rvc_filtfilt(None, 0, 1000, p, p, 6, p, p, None, None, None) == -1
