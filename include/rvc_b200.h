@@ -457,7 +457,7 @@ int rvc_split_points(const void* audio, int32_t is_f64, int64_t n, int32_t windo
 /*
  * The zero-phase high-pass at the head of VC.pipeline, `audio = signal.filtfilt(bh, ah, audio)` (main/inference/convert.py:402; scipy defaults: odd
  * extension by padlen = 3 * ncoef, steady-state initial conditions), in float64 on the device: the direct-form-II-transposed recurrence of scipy's
- * lfilter with scipy's operation order inside blocks of rvc_filtfilt_block(n) samples (2048 or 4096, by the signal length), the blocks' start states chained through ML = M^block (the
+ * lfilter with scipy's operation order inside blocks of rvc_filtfilt_block(n) samples (4096), the blocks' start states chained through ML = M^block (the
  * state-transition matrix of the recurrence raised to the block length, row-major [order][order]; rvc_maker_b200.pipeline obtains it by running the
  * recurrence).  Not bit-identical to scipy's sample-by-sample evaluation: ~2e-8 absolute on a signal of amplitude 0.5, the rounding-noise level of the
  * filter itself.

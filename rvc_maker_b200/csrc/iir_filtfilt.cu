@@ -2,7 +2,7 @@
 // device, in float64 like scipy: odd extension by padlen = 3 max(len a, len b) samples, forward pass with the steady-state initial state zi * ext[0],
 // backward pass with zi * y[-1], the padding dropped.  scipy's lfilter is the direct-form-II-transposed recurrence
 //     y = b0 x + z0;   z_k = (b_{k+1} x + z_{k+1}) - a_{k+1} y
-// one sample after the other (137 - 259 ms per 10 minutes of audio on the host).  Here the signal is cut into blocks of 2048 / 4096 samples, one thread each:
+// one sample after the other (137 - 259 ms per 10 minutes of audio on the host).  Here the signal is cut into blocks of 4096 samples, one thread each:
 // (1) every block runs the recurrence from a zero state and keeps its end state, (2) one thread chains the blocks' true start states,
 // s_{c+1} = M^block s_c + e_c (M^block comes from the host, obtained by running the recurrence itself), (3) every block runs again from its true state and
 // writes its outputs.  Inside a block the operations and their order are scipy's (separate roundings, no fma); what differs is the rounding of the
@@ -13,7 +13,7 @@
 namespace {
 
 constexpr int MAXS = 8;        // filter order <= 8
-constexpr int LCMAX = 4096;    // samples per block: 2048 or 4096 by the signal length (rvc_filtfilt_block)
+constexpr int LCMAX = 4096;    // samples per block (rvc_filtfilt_block)
 constexpr int PF = 16;         // inputs requested ahead of the recurrence
 
 struct Coef {
@@ -43,12 +43,14 @@ __device__ __forceinline__ double input_at(const T* __restrict__ x, const double
     return BACK ? y1[N - 1 - i] : ext_at<T>(x, n, pl, i);
 }
 
+// NS > 0: the order is a compile-time constant (NS = 5 is the reference's filter: no predicated-off operations in the dependent chain); NS = 0: c.ns
+template <int NS>
 __device__ __forceinline__ double step(const Coef& c, double (&z)[MAXS], double x) {
     const double y = __dadd_rn(__dmul_rn(c.b[0], x), z[0]);
 #pragma unroll
-    for (int k = 0; k < MAXS; ++k) {
-        if (k < c.ns) {
-            const double zn = k + 1 < MAXS ? z[k + 1] : 0.0;      // (z[ns] is kept at zero)
+    for (int k = 0; k < (NS ? NS : MAXS); ++k) {
+        if (NS || k < c.ns) {
+            const double zn = k + 1 < (NS ? NS : MAXS) ? z[k + 1] : 0.0;      // (the state behind the last one is zero)
             z[k] = __dsub_rn(__dadd_rn(__dmul_rn(c.b[k + 1], x), zn), __dmul_rn(c.a[k + 1], y));
         }
     }
@@ -56,7 +58,7 @@ __device__ __forceinline__ double step(const Coef& c, double (&z)[MAXS], double 
 }
 
 // (1) end state of every block but the last from a zero start
-template <typename T, bool BACK>
+template <typename T, bool BACK, int NS>
 __global__ void __launch_bounds__(32) iir_block_end_kernel(const T* __restrict__ x, const double* __restrict__ y1, int64_t n, int pl, int64_t N, Coef c,
                                                            int nblk, int LC, double* __restrict__ ends) {
     const int blk = blockIdx.x * 32 + threadIdx.x;
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(32) iir_block_end_kernel(const T* __restrict__
             for (int j = 0; j < PF; ++j) nxt[j] = input_at<T, BACK>(x, y1, n, pl, N, i0 + i + PF + j);
         }
 #pragma unroll
-        for (int j = 0; j < PF; ++j) step(c, z, cur[j]);
+        for (int j = 0; j < PF; ++j) step<NS>(c, z, cur[j]);
 #pragma unroll
         for (int j = 0; j < PF; ++j) cur[j] = nxt[j];
     }
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(32) iir_block_end_kernel(const T* __restrict__
 // (2) true start states: s_0 = zi * input[0], s_{c+1} = M^LC s_c + e_c.  One thread walks the chain; the block stages the end states through
 // shared memory in tiles (a global load per link would cost more than the link itself).
 constexpr int CT = 512;        // blocks per tile
-template <typename T, bool BACK>
+template <typename T, bool BACK, int NS>
 __global__ void __launch_bounds__(256) iir_chain_kernel(const T* __restrict__ x, const double* __restrict__ y1, int64_t n, int pl, int64_t N, Coef c,
                                                         int nblk, const double* __restrict__ ends, double* __restrict__ starts) {
     __shared__ double tile[CT * MAXS];
@@ -106,11 +108,16 @@ __global__ void __launch_bounds__(256) iir_chain_kernel(const T* __restrict__ x,
                 double t[MAXS];
 #pragma unroll
                 for (int k = 0; k < MAXS; ++k) {
+                    if (NS && k >= NS) {              // (states beyond the order stay zero)
+                        t[k] = 0.0;
+                        tile[b * MAXS + k] = 0.0;
+                        continue;
+                    }
                     double acc = tile[b * MAXS + k];
 #pragma unroll
-                    for (int j = 0; j < MAXS; ++j)
-                        if (j < c.ns) acc += c.ML[k * MAXS + j] * s[j];
-                    t[k] = k < c.ns ? acc : 0.0;
+                    for (int j = 0; j < (NS ? NS : MAXS); ++j)
+                        if (NS || j < c.ns) acc += c.ML[k * MAXS + j] * s[j];
+                    t[k] = (NS || k < c.ns) ? acc : 0.0;
                     tile[b * MAXS + k] = s[k];        // the start state of block b0 + b takes the slot of its end state
                 }
 #pragma unroll
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(256) iir_chain_kernel(const T* __restrict__ x,
 }
 
 // (3) the outputs.  Forward: y1[i]; backward: the final signal, out[N - 1 - i - pl] for the samples that are not padding
-template <typename T, bool BACK>
+template <typename T, bool BACK, int NS>
 __global__ void __launch_bounds__(32) iir_block_apply_kernel(const T* __restrict__ x, const double* __restrict__ y1, int64_t n, int pl, int64_t N, Coef c,
                                                              int nblk, int LC, const double* __restrict__ starts, double* __restrict__ out) {
     const int blk = blockIdx.x * 32 + threadIdx.x;
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(32) iir_block_apply_kernel(const T* __restrict
 #pragma unroll
         for (int j = 0; j < PF; ++j) {
             if (i + j < cnt) {
-                const double y = step(c, z, cur[j]);
+                const double y = step<NS>(c, z, cur[j]);
                 if (BACK) {
                     const int64_t q = N - 1 - (i0 + i + j) - pl;
                     if (q >= 0 && q < n) out[q] = y;
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(32) iir_block_apply_kernel(const T* __restrict
     }
 }
 
-template <typename T>
+template <typename T, int NS>
 int run(const T* x, int64_t n, int pl, int LC, const Coef& c, double* y, double* ws, cudaStream_t st) {
     const int64_t N = n + 2 * pl;
     const int nblk = (int)((N + LC - 1) / LC);
@@ -165,22 +172,22 @@ int run(const T* x, int64_t n, int pl, int LC, const Coef& c, double* y, double*
     double* ends = y1 + N;
     double* starts = ends + (size_t)nblk * MAXS;
     const int grid = (nblk + 31) / 32;
-    iir_block_end_kernel<T, false><<<grid, 32, 0, st>>>(x, y1, n, pl, N, c, nblk, LC, ends);
-    iir_chain_kernel<T, false><<<1, 256, 0, st>>>(x, y1, n, pl, N, c, nblk, ends, starts);
-    iir_block_apply_kernel<T, false><<<grid, 32, 0, st>>>(x, y1, n, pl, N, c, nblk, LC, starts, y1);
-    iir_block_end_kernel<T, true><<<grid, 32, 0, st>>>(x, y1, n, pl, N, c, nblk, LC, ends);
-    iir_chain_kernel<T, true><<<1, 256, 0, st>>>(x, y1, n, pl, N, c, nblk, ends, starts);
-    iir_block_apply_kernel<T, true><<<grid, 32, 0, st>>>(x, y1, n, pl, N, c, nblk, LC, starts, y);
+    iir_block_end_kernel<T, false, NS><<<grid, 32, 0, st>>>(x, y1, n, pl, N, c, nblk, LC, ends);
+    iir_chain_kernel<T, false, NS><<<1, 256, 0, st>>>(x, y1, n, pl, N, c, nblk, ends, starts);
+    iir_block_apply_kernel<T, false, NS><<<grid, 32, 0, st>>>(x, y1, n, pl, N, c, nblk, LC, starts, y1);
+    iir_block_end_kernel<T, true, NS><<<grid, 32, 0, st>>>(x, y1, n, pl, N, c, nblk, LC, ends);
+    iir_chain_kernel<T, true, NS><<<1, 256, 0, st>>>(x, y1, n, pl, N, c, nblk, ends, starts);
+    iir_block_apply_kernel<T, true, NS><<<grid, 32, 0, st>>>(x, y1, n, pl, N, c, nblk, LC, starts, y);
     return rvc::check_launch("rvc_filtfilt");
 }
 
 }  // namespace
 
-static int pick_block(int64_t n) {
+static int pick_block(int64_t) {
     // 4 passes of `block` dependent steps against 2 chains of n / block links favour block ~ sqrt(1.3 n), but the hand-off s_{c+1} = M^block s_c + e_c is
-    // only harmless once M^block has decayed: the companion form is far from normal, |M^256| ~ 1e8 turns the rounding of s_c into errors of 1e-3
-    // (measured: split points moved), |M^2048| ~ 2e2 and |M^4096| ~ 2e-3 keep the result at the filter's own noise floor
-    return n >= 3000000 ? LCMAX : LCMAX / 2;
+    // only harmless once M^block has decayed (the companion form is far from normal): measured max |y - scipy| at amplitude 0.5 — blocks of 256 - 1024:
+    // up to 1e-3 (split points moved); 2048 (|M^2048| ~ 2e2): 1.6e-7; 4096 (|M^4096| ~ 2e-3): 4e-8, the filter's own noise floor
+    return LCMAX;
 }
 
 RVC_API int32_t rvc_filtfilt_block(int64_t n) { return n > 0 ? pick_block(n) : 0; }
@@ -207,6 +214,8 @@ RVC_API int rvc_filtfilt(const void* x, int32_t is_f64, int64_t n, const double*
     for (int k = 0; k < c.ns; ++k)
         for (int j = 0; j < c.ns; ++j) c.ML[k * MAXS + j] = ML[k * c.ns + j];
     const int lc = pick_block(n);
-    if (is_f64) return run((const double*)x, n, pl, lc, c, y, (double*)ws, (cudaStream_t)stream);
-    return run((const float*)x, n, pl, lc, c, y, (double*)ws, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c.ns == 5)                                 // the reference's Butterworth (convert.py:29)
+        return is_f64 ? run<double, 5>((const double*)x, n, pl, lc, c, y, (double*)ws, st) : run<float, 5>((const float*)x, n, pl, lc, c, y, (double*)ws, st);
+    return is_f64 ? run<double, 0>((const double*)x, n, pl, lc, c, y, (double*)ws, st) : run<float, 0>((const float*)x, n, pl, lc, c, y, (double*)ws, st);
 }

@@ -92,8 +92,8 @@ def filtfilt(audio, b, a):
     """``scipy.signal.filtfilt(b, a, audio)`` (scipy's defaults, as convert.py:402 calls it) on the device: a float64 CUDA tensor [n].
 
     audio: 1-D CUDA tensor, float32 or float64; b, a: the coefficients (``signal.butter(N=5, Wn=48, btype="high", fs=16000)``, convert.py:29).  The
-    recurrence and its operation order are scipy's inside blocks of 2048 / 4096 samples, the blocks run in parallel (137 - 259 ms on the host per 10 minutes of
-    audio, 4 ms here); the result agrees with scipy's to ~2e-8 absolute at amplitude 0.5 — the rounding noise of the filter itself —
+    recurrence and its operation order are scipy's inside blocks of 4096 samples, the blocks run in parallel (137 - 259 ms on the host per 10 minutes of
+    audio, 2 ms here); the result agrees with scipy's to ~2e-8 absolute at amplitude 0.5 — the rounding noise of the filter itself —
     not to the bit, so keep scipy's call where bit-identical split points matter (``split_points`` is exact for whatever signal it is given)."""
     if not isinstance(audio, torch.Tensor) or audio.device.type != "cuda":
         raise RuntimeError("rvc_maker_b200.pipeline.filtfilt needs a CUDA tensor (no CPU fallback)")

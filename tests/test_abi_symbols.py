@@ -123,8 +123,8 @@ def test_filtfilt_argument_errors(lib):
 
     one = np.ones(6)
     p = one.ctypes.data
-    assert lib.rvc_filtfilt_block(9_600_000) == 4096 and lib.rvc_filtfilt_block(160000) == 2048
-    assert lib.rvc_filtfilt_workspace(160000, 6) == (160036 + 2 * 79 * 8) * 8
+    assert lib.rvc_filtfilt_block(9_600_000) == 4096 and lib.rvc_filtfilt_block(160000) == 4096
+    assert lib.rvc_filtfilt_workspace(160000, 6) == (160036 + 2 * 40 * 8) * 8
     assert lib.rvc_filtfilt(8, 0, 1000, p, p, 12, p, p, 8, 8, None) == -2
     assert lib.rvc_filtfilt(8, 0, 18, p, p, 6, p, p, 8, 8, None) == -2 and b"padlen" in lib.rvc_last_error()
     two = 2 * one
