@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RVC_ABI_VERSION 29
+#define RVC_ABI_VERSION 30
 
 #define RVC_EINVAL (-1)   /* bad argument */
 #define RVC_ESHAPE (-2)   /* shape not supported by this kernel */
@@ -468,6 +468,15 @@ int32_t rvc_filtfilt_block(int64_t n);
 int64_t rvc_filtfilt_workspace(int64_t n, int32_t ncoef);
 int rvc_filtfilt(const void* x, int32_t is_f64, int64_t n, const double* b, const double* a, int32_t ncoef, const double* zi, const double* ML,
                  double* y, void* ws, void* stream);
+
+/*
+ * The retrieval blend of VC.voice_conversion behind the FAISS search (main/inference/convert.py:354-359; the search itself, :353, stays the caller's):
+ *   weight = square(1 / score); weight /= weight.sum(1); npy = sum_k big_npy[ix[:, k]] * weight[:, k]; out = npy * index_rate + (1 - index_rate) * feats
+ * feats, out [T][D] fp32, big_npy [N][D] fp32 (index.reconstruct_n(0, ntotal), :395, resident on the device), score [T][8] fp32, ix [T][8] int64.
+ * one_minus_rate = (float)(1 - index_rate) computed by the caller in double, as Python does.  numpy's orders and roundings: bit-identical.
+ */
+int rvc_retrieval_blend_f32(const float* feats, const float* big_npy, const float* score, const int64_t* ix, float index_rate, float one_minus_rate,
+                            float* out, int32_t T, int32_t D, int32_t K, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,14 @@ import torch.nn.functional as F
 from .chunk_oracle import reference_chunk_loop
 
 
+def reference_retrieval_blend(feats, big_npy, score, ix, index_rate):
+    """convert.py:354-359 with (score, ix) = index.search(npy, k=8) given: feats [1, T, D] fp32 torch (CPU), returns the blended feats."""
+    weight = np.square(1 / score)                                                                # :354
+    weight /= weight.sum(axis=1, keepdims=True)                                                  # :355
+    npy = np.sum(big_npy[ix] * np.expand_dims(weight, axis=2), axis=1)                           # :356
+    return torch.from_numpy(npy).unsqueeze(0) * index_rate + (1 - index_rate) * feats            # :359
+
+
 def reference_voice_conversion(infer_fn, feats, feats0, n_audio_samples, pitch, pitchf, sid, protect, window=160):
     """feats [1, Th, D] = embedder output after the retrieval blend, feats0 = before it (None when protect >= 0.5 or no pitch)."""
     pitch_guidance = pitch is not None and pitchf is not None                                   # :329

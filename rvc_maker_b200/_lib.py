@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # RVC_B200_LIB: debugging builds of the same library only (tools/pair_trace.py -> librvc_b200_trace.so); never a fallback
 LIB_PATH = os.environ.get("RVC_B200_LIB") or os.path.join(HERE, "librvc_b200.so")
-ABI_VERSION = 29
+ABI_VERSION = 30
 DT_BF16, DT_FP16, DT_FP16_SPLIT = 0, 2, 3
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -141,6 +141,7 @@ SIGNATURES = {
     "rvc_filtfilt_block": (_i32, [_i64]),
     "rvc_filtfilt_workspace": (_i64, [_i64, _i32]),
     "rvc_filtfilt": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "rvc_retrieval_blend_f32": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _f32, _vp, _i32, _i32, _i32, _vp]),
     "rvc_rmvpe_pitch_f32": (C.c_int, [_vp, _i64, _i32, _f32, _f64, _f64, _vp, _i32, _f64, _f64, _f64, _f64, _vp, _vp, _vp, _vp]),
     "rvc_resblock_pair_tc": (C.c_int, [C.POINTER(ResblockPairDesc), _vp]),
     "rvc_debug_pair_trace": (C.c_int, [_vp, _i32]),

@@ -53,7 +53,47 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
     }
 }
 
+// The retrieval blend of VC.voice_conversion after `score, ix = index.search(npy, k=8)` (main/inference/convert.py:353-359):
+//   weight = np.square(1 / score);  weight /= weight.sum(axis=1, keepdims=True)
+//   npy = np.sum(big_npy[ix] * np.expand_dims(weight, axis=2), axis=1)
+//   feats = torch.from_numpy(npy).to(device) * index_rate + (1 - index_rate) * feats
+// with numpy's roundings and orders: the 8 weights summed pairwise (numpy's contiguous-axis reduction), the 8 weighted neighbours added one after
+// the other (a reduction over a middle axis), every product / quotient / sum rounded separately, then torch's mul, mul, add.
+__global__ void __launch_bounds__(256) retrieval_blend_kernel(const float* __restrict__ feats, const float* __restrict__ big, const float* __restrict__ score,
+                                                              const int64_t* __restrict__ ix, float rate, float one_minus_rate, float* __restrict__ out,
+                                                              int D) {
+    rvc::pdl_prologue();
+    const int t = blockIdx.x;
+    float w[8];
+    const float* rows[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float r = __fdiv_rn(1.f, score[(int64_t)t * 8 + k]);
+        w[k] = __fmul_rn(r, r);
+        rows[k] = big + ix[(int64_t)t * 8 + k] * (int64_t)D;
+    }
+    const float ws = __fadd_rn(__fadd_rn(__fadd_rn(w[0], w[1]), __fadd_rn(w[2], w[3])), __fadd_rn(__fadd_rn(w[4], w[5]), __fadd_rn(w[6], w[7])));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __fdiv_rn(w[k], ws);
+    for (int d = threadIdx.x; d < D; d += 256) {
+        float acc = __fmul_rn(rows[0][d], w[0]);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) acc = __fadd_rn(acc, __fmul_rn(rows[k][d], w[k]));
+        out[(int64_t)t * D + d] = __fadd_rn(__fmul_rn(acc, rate), __fmul_rn(one_minus_rate, feats[(int64_t)t * D + d]));
+    }
+}
+
 }  // namespace
+
+RVC_API int rvc_retrieval_blend_f32(const float* feats, const float* big_npy, const float* score, const int64_t* ix, float index_rate,
+                                    float one_minus_rate, float* out, int32_t T, int32_t D, int32_t K, void* stream) {
+    if (!feats || !big_npy || !score || !ix || !out) return rvc::fail(RVC_EINVAL, "rvc_retrieval_blend_f32: null pointer");
+    if (K != 8) return rvc::fail(RVC_ESHAPE, "rvc_retrieval_blend_f32: k must be 8 (index.search(npy, k=8), convert.py:353; numpy's summation order depends on it)");
+    if (T < 0 || D <= 0) return rvc::fail(RVC_ESHAPE, "rvc_retrieval_blend_f32: bad shape");
+    if (T == 0) return 0;
+    retrieval_blend_kernel<<<T, 256, 0, (cudaStream_t)stream>>>(feats, big_npy, score, ix, index_rate, one_minus_rate, out, D);
+    return rvc::check_launch("rvc_retrieval_blend_f32");
+}
 
 RVC_API int rvc_feature_prep_f32(const float* feats, const float* feats0, const float* pitchf, int64_t pitchf_bs, float protect, float* out,
                                  int32_t B, int32_t Th, int32_t T, int32_t D, void* stream) {

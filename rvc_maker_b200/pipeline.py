@@ -24,7 +24,9 @@ Mirrors ``VC.voice_conversion`` from the embedder output on (main/inference/conv
 * the high-pass in front of it (``signal.filtfilt``, :402) has a device version (``filtfilt`` below: scipy's recurrence in blocks, within the filter's
   rounding noise of scipy, not bit-identical — read its docstring before building plans on it).
 
-Out of scope (hooks instead): the embedder and FAISS retrieval that produce ``feats`` / ``feats0`` (:336-359), the f0 network
+* the retrieval blend behind the FAISS search (:354-359) runs on a device-resident ``big_npy``, bit-identical (``retrieval_blend`` below).
+
+Out of scope (hooks instead): the embedder and the FAISS search that produce ``feats`` / ``feats0`` (:336-353), the f0 network
 (:431, 8f-2; its two ends are in ``rvc_maker_b200.pitch``) and ``change_rms`` (:450, only when volume_envelope != 1).
 """
 from __future__ import annotations
@@ -109,6 +111,30 @@ def filtfilt(audio, b, a):
     _lib.check(lib.rvc_filtfilt(audio.data_ptr(), int(audio.dtype == torch.float64), n, b64.ctypes.data, a64.ctypes.data, len(b64), zi.ctypes.data,
                                 ML.ctypes.data, y.data_ptr(), ws.data_ptr(), st), "rvc_filtfilt")
     return y
+
+
+def retrieval_blend(feats, big_npy, score, ix, index_rate):
+    """The blend behind ``score, ix = index.search(npy, k=8)`` (convert.py:354-359) on the device: ``feats`` [T, D] (or [1, T, D]) fp32 CUDA, ``big_npy``
+    [N, D] fp32 CUDA (``index.reconstruct_n(0, index.ntotal)``, :395, uploaded once), ``score`` [T, 8] fp32 and ``ix`` [T, 8] int64 as FAISS returns
+    them (host or device).  Returns the blended features in ``feats``' shape, bit-identical to the reference's numpy + torch statements; the
+    reference gathers the [T, 8, D] neighbours on the host and copies the result up again."""
+    if not isinstance(feats, torch.Tensor) or feats.device.type != "cuda" or not isinstance(big_npy, torch.Tensor) or big_npy.device != feats.device:
+        raise RuntimeError("rvc_maker_b200.pipeline.retrieval_blend needs feats and big_npy as CUDA tensors on one device (no CPU fallback)")
+    shape = feats.shape
+    f2 = feats.float().reshape(-1, shape[-1]).contiguous()
+    T, D = f2.shape
+    big_npy = big_npy.float().contiguous()
+    score = torch.as_tensor(score, dtype=torch.float32).to(feats.device).contiguous()
+    ix = torch.as_tensor(ix, dtype=torch.int64).to(feats.device).contiguous()
+    if tuple(score.shape) != (T, 8) or tuple(ix.shape) != (T, 8) or big_npy.dim() != 2 or big_npy.shape[1] != D:
+        raise ValueError(f"need score / ix [T={T}, 8] and big_npy [N, {D}], got {tuple(score.shape)}, {tuple(ix.shape)}, {tuple(big_npy.shape)}")
+    if T and (int(ix.min()) < 0 or int(ix.max()) >= big_npy.shape[0]):
+        raise ValueError("ix holds indices outside big_npy (FAISS returns -1 when a list has fewer than k vectors)")
+    out = torch.empty_like(f2)
+    st = torch.cuda.current_stream(feats.device).cuda_stream
+    _lib.check(_lib.load().rvc_retrieval_blend_f32(f2.data_ptr(), big_npy.data_ptr(), score.data_ptr(), ix.data_ptr(), float(index_rate),
+                                                   float(1 - index_rate), out.data_ptr(), T, D, 8, st), "rvc_retrieval_blend_f32")
+    return out.reshape(shape)
 
 
 def feature_prep(feats, feats0, pitchf, protect, T=None):

@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.rvc_abi_version() == 29
+    assert lib.rvc_abi_version() == 30
     # argument validation happens before any CUDA call, so it is checkable without a GPU
     rc = lib.rvc_conv1d_f32(None, None)
     assert rc == -1
@@ -130,3 +130,9 @@ def test_filtfilt_argument_errors(lib):
     two = 2 * one
     assert lib.rvc_filtfilt(8, 0, 1000, p, two.ctypes.data, 6, p, p, 8, 8, None) == -1 and b"normalise" in lib.rvc_last_error()
     assert lib.rvc_filtfilt(None, 0, 1000, p, p, 6, p, p, None, None, None) == -1
+
+
+def test_retrieval_blend_argument_errors(lib):
+    assert lib.rvc_retrieval_blend_f32(8, 8, 8, 8, 0.5, 0.5, 8, 10, 768, 4, None) == -2 and b"k must be 8" in lib.rvc_last_error()
+    assert lib.rvc_retrieval_blend_f32(None, 8, 8, 8, 0.5, 0.5, 8, 10, 768, 8, None) == -1
+    assert lib.rvc_retrieval_blend_f32(8, 8, 8, 8, 0.5, 0.5, 8, 0, 768, 8, None) == 0

@@ -444,6 +444,31 @@ def test_infer_many_groups_equal_stacked_infer(precision, monkeypatch):
         assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
+def test_infer_many_groups_non_f0_and_v1():
+    """Grouping on the other model families: the non-f0 generator (no pitch / nsff0 / source noise) and v1 (256-d features, five stages) — a group of
+    four equals infer on the stacked items, bit for bit."""
+    for cname, use_f0 in (("v2_40k", False), ("v1_32k", True)):
+        cfg = cases.CONFIGS[cname]
+        sd = cases.synth_state_dict(cfg, use_f0=use_f0, seed=9, heated=True)
+        net = build_net(cfg, sd, use_f0, precision="tc")
+        inps = [cases.synth_inputs(cfg, 1, 200, seed=400 + n, use_f0=use_f0) for n in range(4)]
+        for n, inp in enumerate(inps):
+            inp["sid"] = torch.tensor([n % 3])
+        keys = ("phone", "phone_lengths", "pitch", "nsff0", "sid")
+        cat = lambda k: None if inps[0][k] is None else torch.cat([i[k] for i in inps]).cuda()
+        net._noise_override = (torch.cat([i["eps_z"] for i in inps]), None if inps[0]["eps_src"] is None else torch.cat([i["eps_src"] for i in inps]))
+        r = net.infer(*[cat(k) for k in keys])
+        want = [[t[j:j + 1].clone() for t in (r[0], r[2][0], r[2][2])] for j in range(4)]
+        net._noise_override = None
+        items = [tuple(None if inp[k] is None else inp[k].cuda() for k in keys) + (None, (inp["eps_z"], inp["eps_src"])) for inp in inps]
+        assert net._engine.group_size(1, 200) >= 4
+        for rep in range(2):
+            got = [[t.clone() for t in (r[0], r[2][0], r[2][2])] for r in net.infer_many(iter(items))]
+            assert len(got) == 4
+            for a, b in zip(got, want):
+                assert all(torch.equal(x, y) for x, y in zip(a, b)), (cname, rep)
+
+
 @pytest.mark.parametrize("B,T", [(1, 1000), (2, 173), (3, 128), (2, 129), (1, 1), (2, 1024), (40, 64)])
 def test_attention_cluster_kernel_matches_per_launch_path(B, T, monkeypatch):
     """rvc_attn_scores_cluster_tc (scores + softmax in one cluster kernel, row maxima / sums through distributed shared memory, the relative-value

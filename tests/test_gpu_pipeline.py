@@ -223,3 +223,19 @@ def test_stream_converter_with_the_model_matches_the_reference_loop():
     m = cases.metrics(torch.from_numpy(got.copy()), torch.from_numpy(want))
     print(f"\n[pipeline 83 s, batches (4000 x2) + 900, tc] max_abs={m['max_abs']:.3e} snr={m['snr_db']:.1f} dB")
     assert m["max_abs"] <= 1e-3 and m["snr_db"] >= 40.0, m
+
+
+@pytest.mark.parametrize("T,D,N,rate", [(500, 768, 3000, 0.5), (37, 256, 100, 0.75), (1, 768, 9, 1.0), (200, 768, 2000, 0.3)])
+def test_retrieval_blend_is_bit_exact(T, D, N, rate):
+    """convert.py:354-359 behind a stand-in for index.search (exact top-8 by squared L2 distance): numpy's roundings and summation orders, bit for bit."""
+    rng = np.random.Generator(np.random.PCG64(T + N))
+    big = rng.standard_normal((N, D)).astype(np.float32)
+    feats = torch.from_numpy(rng.standard_normal((1, T, D)).astype(np.float32))
+    d2 = ((feats[0].numpy()[:, None, :] - big[None, :200 if N > 200 else N, :]) ** 2).sum(-1)       # (a slice keeps the stand-in search cheap)
+    ix = np.argsort(d2, axis=1)[:, :8].astype(np.int64)
+    score = np.take_along_axis(d2, ix, axis=1).astype(np.float32)
+    want = pipeline_oracle.reference_retrieval_blend(feats, big, score.copy(), ix, rate)
+    got = pl.retrieval_blend(feats.to(DEV), torch.from_numpy(big).to(DEV), score, ix, rate)
+    assert got.shape == want.shape and torch.equal(got.cpu(), want)
+    with pytest.raises(ValueError):
+        pl.retrieval_blend(feats.to(DEV), torch.from_numpy(big).to(DEV), score, ix - 1000, rate)
