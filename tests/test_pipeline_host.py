@@ -132,3 +132,24 @@ def test_two_rank_gloo_piece_gather(tmp_path):
     got = np.load(out)
     assert np.array_equal(got[:-1].astype(np.float32), want)
     assert got[-1] == np.float32(want.max())
+
+
+def test_filter_constants_match_scipy():
+    """Host side of pipeline.filtfilt: zi is scipy.signal.lfilter_zi to the bit, and M^block's columns are the states scipy's own lfilter reaches from
+    the unit states after `block` zero-input steps (bit-identical: the same recurrence, run rather than exponentiated)."""
+    import numpy as np
+    from scipy import signal
+
+    from rvc_maker_b200 import pipeline as pl
+
+    for order, wn, btype in ((5, 48, "high"), (3, 200, "high"), (8, 4000, "low")):
+        b, a = signal.butter(N=order, Wn=wn, btype=btype, fs=16000)
+        b64, a64, zi, ML = pl._filter_constants(b, a, 4096)
+        assert np.array_equal(zi, signal.lfilter_zi(b, a)) and ML.shape == (order, order)
+        for j in range(order):
+            z0 = np.zeros(order)
+            z0[j] = 1.0
+            _, zf = signal.lfilter(b, a, np.zeros(4096), zi=z0)
+            assert np.array_equal(zf, ML[:, j]), (order, j)
+    with pytest.raises(ValueError):
+        pl._filter_constants([1.0, 2.0], [1.0], 4096)
