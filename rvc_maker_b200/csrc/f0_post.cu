@@ -108,9 +108,12 @@ __global__ void __launch_bounds__(256) rmvpe_decode_kernel(const float* __restri
 template <bool TAIL>
 void launch_decode(const float* sal, int64_t row_stride, int T, float thred, const TailArgs& a, double* f0, int64_t* pitch, float* pitchf,
                    cudaStream_t st) {
-    // short tracks: one frame per warp (latency); long tracks: eight, so that the scalar tail is issued once per eight frames (HBM-bound)
+    // short tracks: one frame per warp (latency); long tracks: eight, so that the scalar tail is issued once per eight frames (HBM-bound); in
+    // between (a ten-minute file is 60 001 frames) four, which still gives a few waves of CTAs to overlap loads, reductions and tails
     if (T < 8192)
         rmvpe_decode_kernel<TAIL, 1><<<rvc::cdiv(T, 8), 256, 0, st>>>(sal, row_stride, T, thred, a, f0, pitch, pitchf);
+    else if (T < 200000)
+        rmvpe_decode_kernel<TAIL, 4><<<rvc::cdiv(T, 32), 256, 0, st>>>(sal, row_stride, T, thred, a, f0, pitch, pitchf);
     else
         rmvpe_decode_kernel<TAIL, 8><<<rvc::cdiv(T, 64), 256, 0, st>>>(sal, row_stride, T, thred, a, f0, pitch, pitchf);
 }

@@ -59,9 +59,10 @@ def test_get_f0_tail_matches_reference_golden(name, gold):
     assert ulp_close(f0s.cpu().numpy(), gold[name + ".pitchf64"], ulps=1)
 
 
-@pytest.mark.parametrize("T,legacy,tune", [(1, False, False), (7, True, True), (60001, False, True), (60001, True, False)])
+@pytest.mark.parametrize("T,legacy,tune", [(1, False, False), (7, True, True), (60001, False, True), (60001, True, False), (200003, False, False)])
 def test_rmvpe_pitch_against_oracle_at_size(T, legacy, tune):
-    """Sizes beyond the fixtures (10 minutes of audio at 100 frames/s) against the numpy oracle on the same seeded salience."""
+    """Sizes beyond the fixtures (10 minutes of audio at 100 frames/s; 200 003 frames for the eight-frames-per-warp variant) against the numpy oracle
+    on the same seeded salience."""
     from rvc_maker_b200 import pitch as P
 
     sal = f0_oracle.synthetic_salience(T, 1000 + T, sharp=bool(T & 1))
