@@ -111,3 +111,29 @@ def test_wide_ragged_batch_tc_repeated_fresh_engines():
         else:
             for k in ("o", "z", "m_p", "logs_p"):
                 assert torch.equal(out[k], first[k]), (rep, k, float((out[k] - first[k]).abs().max()))
+
+
+def test_headline_path_against_the_oracle():
+    """What bench.py's `value` runs — configs[1] (v2-48k f0, 10 s clips of T = 1000 frames) through Synthesizer.infer_many, three clips to a pass on
+    the tensor-core kernel set, each clip with its own speaker and (pinned) noise — against the CPU oracle clip by clip: the north-star bars."""
+    import torch
+
+    cfg = cases.CONFIGS["v2_48k"]
+    sd = cases.synth_state_dict(cfg, seed=1234, heated=True)
+    net = build_net(cfg, sd, True, precision="tc")
+    inps = [cases.synth_inputs(cfg, 1, 1000, seed=50 + n) for n in range(4)]          # a pass of three + a pass of one
+    for n, inp in enumerate(inps):
+        inp["sid"] = torch.tensor([n])
+    keys = ("phone", "phone_lengths", "pitch", "nsff0", "sid")
+    items = [tuple(inp[k].cuda() for k in keys) + (None, (inp["eps_z"], inp["eps_src"])) for inp in inps]
+    assert net._ensure_engine().group_size(1, 1000) == 3
+    got = [dict(o=r[0].clone(), x_mask=r[1].clone(), z=r[2][0].clone(), z_p=r[2][1].clone(), m_p=r[2][2].clone(), logs_p=r[2][3].clone())
+           for r in net.infer_many(iter(items))]
+    assert len(got) == 4
+    for n, (inp, out) in enumerate(zip(inps, got)):
+        ro, rmask, (rz, rzp, rm, rl) = synth_oracle.infer(sd, cfg, inp["phone"], inp["phone_lengths"], inp["pitch"], inp["nsff0"], inp["sid"],
+                                                          eps_z=inp["eps_z"], eps_src=inp["eps_src"])
+        ref = dict(o=ro, x_mask=rmask, z=rz, z_p=rzp, m_p=rm, logs_p=rl)
+        m = cases.metrics(out["o"].float().cpu(), ro)
+        print(f"[infer_many, clip {n} of 4, T=1000 tc] o: max_abs={m['max_abs']:.3e} snr={m['snr_db']:.1f} dB")
+        assert_close(out, ref, "tc", tag=f"headline clip {n}")
